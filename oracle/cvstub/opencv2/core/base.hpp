@@ -1,0 +1,2 @@
+// stand-in header: see ../opencv.hpp (oracle/cvstub, TEST INFRASTRUCTURE)
+#include "../opencv.hpp"

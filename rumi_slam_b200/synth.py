@@ -1,0 +1,87 @@
+"""Deterministic synthetic grayscale frames of the shapes BASELINE.json names.
+
+Band-limited noise (three octaves) plus ~100 filled rectangles / triangles, clipped to u8.  Tuned so that
+level 0 of a 640x480 frame yields a few thousand FAST candidates, some 35-px cells are empty at
+iniThFAST=20 (exercising the minThFAST fallback) and the quad-tree's sorted final phase triggers.
+numpy + scipy only; seeds are `np.random.default_rng(seed)`.
+"""
+import numpy as np
+from scipy import ndimage
+
+
+def _octave(rng, h, w, down, sigma):
+    hh, ww = -(-h // down) + 2, -(-w // down) + 2
+    n = ndimage.gaussian_filter(rng.standard_normal((hh, ww)).astype(np.float32), sigma, mode="reflect")
+    n /= n.std() + 1e-6
+    if down > 1:
+        n = ndimage.zoom(n, down, order=1)
+    return n[:h, :w]
+
+
+def synthetic_frame(seed, w=640, h=480, texture=1.0, shapes=100):
+    rng = np.random.default_rng(seed)
+    img = 22.0 * texture * _octave(rng, h, w, 1, 2.5)
+    img += 18.0 * _octave(rng, h, w, 2, 3.0)
+    img += 30.0 * _octave(rng, h, w, 5, 3.0)
+    # smooth low-texture mask so that some cells fall below iniThFAST
+    m = _octave(rng, h, w, 8, 2.0)
+    img *= np.clip(0.55 + 0.6 * m, 0.05, 1.4)
+    img += 128.0
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(shapes):
+        val = float(rng.integers(20, 236))
+        cx, cy = int(rng.integers(0, w)), int(rng.integers(0, h))
+        sw, sh = int(rng.integers(6, 70)), int(rng.integers(6, 70))
+        x0, x1 = max(cx - sw // 2, 0), min(cx + sw // 2 + 1, w)
+        y0, y1 = max(cy - sh // 2, 0), min(cy + sh // 2 + 1, h)
+        if x1 <= x0 or y1 <= y0:
+            continue
+        if rng.random() < 0.5:
+            img[y0:y1, x0:x1] = val
+        else:
+            px = rng.integers(x0, x1, 3).astype(np.float32)
+            py = rng.integers(y0, y1, 3).astype(np.float32)
+            sx, sy = xx[y0:y1, x0:x1].astype(np.float32), yy[y0:y1, x0:x1].astype(np.float32)
+
+            def edge(i, j):
+                return (px[j] - px[i]) * (sy - py[i]) - (py[j] - py[i]) * (sx - px[i])
+
+            e0, e1, e2 = edge(0, 1), edge(1, 2), edge(2, 0)
+            inside = ((e0 >= 0) & (e1 >= 0) & (e2 >= 0)) | ((e0 <= 0) & (e1 <= 0) & (e2 <= 0))
+            img[y0:y1, x0:x1][inside] = val
+    img += 2.0 * rng.standard_normal((h, w)).astype(np.float32)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def synthetic_batch(n, w=640, h=480, seed0=0, unique=None):
+    """n frames [n,h,w] u8.  `unique` < n generates that many distinct frames and fills the rest with
+    circular shifts of them (distinct content, cheap to make) -- used by bench.py for the 1024-frame batch."""
+    unique = n if unique is None else min(unique, n)
+    base = [synthetic_frame(seed0 + i, w, h) for i in range(unique)]
+    out = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        b = base[i % unique]
+        k = i // unique
+        out[i] = b if k == 0 else np.roll(b, (7 * k, 13 * k), axis=(0, 1))
+    return out
+
+
+def stereo_pair(seed, w=752, h=480, max_disp=40):
+    """Left frame + right frame = left warped by a per-row-constant disparity plus independent noise."""
+    left = synthetic_frame(2 * seed, w, h)
+    rng = np.random.default_rng(2 * seed + 1)
+    disp = ndimage.gaussian_filter1d(rng.uniform(2, max_disp, h).astype(np.float32), 25.0, mode="reflect")
+    right = np.empty_like(left)
+    for y in range(h):
+        right[y] = np.roll(left[y], -int(round(float(disp[y]))))
+    right = np.clip(right.astype(np.float32) + 1.5 * rng.standard_normal((h, w)), 0, 255)
+    return left, np.rint(right).astype(np.uint8)
+
+
+def perturbed_descriptors(desc, n, seed=7, flip_p=0.1):
+    """Tile descriptor rows to n rows and flip each bit with probability flip_p (SURVEY.md 8d cfg 5b)."""
+    rng = np.random.default_rng(seed)
+    reps = -(-n // len(desc))
+    d = np.tile(desc, (reps, 1))[:n].copy()
+    flips = np.packbits(rng.random((n, 256)) < flip_p, axis=1, bitorder="little")
+    return d ^ flips

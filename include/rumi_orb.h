@@ -1,0 +1,127 @@
+/* rumi_orb.h -- C ABI of the B200-native ORB front-end (librumi_orb.so).
+ *
+ * Drop-in boundary for RUMI-SLAM's feature front-end.  Each entry point names the reference interface it
+ * replaces (R/ = src/rumi-slam/ of Changfei-Fu/RUMI-SLAM).  Plain C: opaque handles, plain pointers and sizes,
+ * int return codes (0 = ok, < 0 = error, text via rumi_last_error()).  No exceptions cross this boundary and
+ * there is NO CPU fallback: without a usable CUDA device every call fails with RUMI_ERR_CUDA.
+ *
+ * Threading: one handle = one CUDA stream + one workspace; a handle is single-threaded (like a reference
+ * ORBextractor instance, which mutates mvImagePyramid), distinct handles may be used concurrently
+ * (R/lib_src/Frame.cc:116-119 runs the left/right extractors in two threads).
+ */
+#ifndef RUMI_ORB_H
+#define RUMI_ORB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RUMI_OK 0
+#define RUMI_ERR_EMPTY (-1)      /* empty image: ORBextractor::operator() returns -1 (ORBextractor.cc:1017) */
+#define RUMI_ERR_ARG (-2)
+#define RUMI_ERR_SHAPE (-3)      /* shape the reference itself cannot process (level smaller than one 35-px cell, ...) */
+#define RUMI_ERR_CUDA (-4)
+#define RUMI_ERR_CAPACITY (-5)
+#define RUMI_ERR_BORDER (-6)     /* keypoint closer than 19 px to the image border (reference reads out of bounds) */
+
+/* == cv::KeyPoint, 28 bytes (pt.x, pt.y, size, angle [deg], response, octave, class_id) */
+typedef struct rumi_kp {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} rumi_kp;
+
+typedef struct rumi_orb rumi_orb;
+typedef struct rumi_match rumi_match;
+
+const char* rumi_last_error(void);
+int rumi_device_count(void);
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)   R/lib_src/ORBextractor.cc:405-461
+ * `max_batch` = frames processed per internal chunk (workspace is sized for it); w/h are learned at first use. */
+int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
+                    int min_th_fast, int device, int max_batch);
+void rumi_orb_destroy(rumi_orb* h);
+
+/* GetLevels / GetScaleFactor(s) / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * R/include/cloud_edge_slam_lib/ORBextractor.h:62-84.  Each table has nlevels floats; mnFeaturesPerLevel in quota. */
+int rumi_orb_levels(const rumi_orb* h);
+int rumi_orb_tables(const rumi_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota);
+
+/* Upper bound of keypoints per frame for a w x h image (sum over levels of quota + 3): size kps/desc with it. */
+int rumi_orb_frame_capacity(rumi_orb* h, int w, int h_px);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)   R/lib_src/ORBextractor.cc:1014-1091
+ * img: HOST pointer, 8-bit gray, `stride` bytes per row.  lap0/lap1 = vLappingArea.  Writes up to `cap` keypoints
+ * (28 B each) and descriptors (32 B each) in the reference's output order; *n_kp = total, *n_mono = return value
+ * of operator() (monoIndex).  NULL/0-sized image -> RUMI_ERR_EMPTY (reference returns -1). */
+int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1,
+                     rumi_kp* kps, uint8_t* desc, int cap, int* n_kp, int* n_mono);
+
+/* Same for n frames (frame i at imgs + i*frame_pitch); frame-sharded work unit of the back-submap rebuild
+ * (SURVEY.md 8e).  HOST pointers; H2D, kernels and D2H of consecutive chunks overlap on two streams.
+ * kps: [n][cap_per_frame], desc: [n][cap_per_frame][32], n_kp/n_mono: [n].  cap_per_frame >= frame capacity. */
+int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h_px, size_t stride,
+                           size_t frame_pitch, int lap0, int lap1, rumi_kp* kps, uint8_t* desc,
+                           int cap_per_frame, int* n_kp, int* n_mono);
+
+/* Same with every buffer already resident in device memory (inputs stay in HBM, results stay in HBM).
+ * Asynchronous on the handle's stream unless `sync` != 0. */
+int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int w, int h_px, size_t stride,
+                                  size_t frame_pitch, int lap0, int lap1, rumi_kp* d_kps, uint8_t* d_desc,
+                                  int cap_per_frame, int* d_n_kp, int* d_n_mono, int sync);
+
+/* ORBextractor::CloudFrameComputeDescriptors(image, keypoints, descriptors)   R/lib_src/ORBextractor.cc:989-1011
+ * HOST pointers.  Returns n (like the reference) or an error code. */
+int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,
+                      uint8_t* desc);
+
+/* mvImagePyramid[level] of the LAST rumi_orb_extract call (R/include/cloud_edge_slam_lib/ORBextractor.h:86;
+ * read by Frame::ComputeStereoMatches, R/lib_src/Frame.cc:834,918-932).  Copies the level to host memory. */
+int rumi_orb_pyramid_level(rumi_orb* h, int level, uint8_t* dst, size_t dst_stride, int* w, int* h_px);
+/* Blurred level of the last call (test hook for the 7x7 Gaussian, R/lib_src/ORBextractor.cc:1057-1058). */
+int rumi_orb_blurred_level(rumi_orb* h, int level, uint8_t* dst, size_t dst_stride, int* w, int* h_px);
+/* Stage-level test hooks: FAST candidates of `level` of the last single-frame call in the reference's insertion
+ * order, as (x, y, response) int32 triples relative to (16,16); returns the count (<= cap written). */
+int rumi_orb_debug_candidates(rumi_orb* h, int level, int32_t* xyr, int cap);
+int rumi_orb_debug_selected(rumi_orb* h, int level, int32_t* xyr, int cap);
+/* Test hook: arms (out == NULL) or reads back the shared-memory image + score tile of FAST cell `cell` of frame 0. */
+int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* dims5);
+
+/* ---- matching ---- */
+int rumi_match_create(rumi_match** out, int device);
+void rumi_match_destroy(rumi_match* m);
+
+/* Brute-force top-2 Hamming of nq query vs nt train descriptors (32 B rows).  Semantics of the best/second-best
+ * scan shared by ORBmatcher (R/lib_src/ORBmatcher.cc:253-261) and BFMatcher.knnMatch(k=2) (R/lib_src/Frame.cc:1139):
+ * ascending train index, strict '<' -> ties keep the earliest index; d2 may equal d1; no candidate -> 256 / -1.
+ * HOST pointers. */
+int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, int32_t* idx1,
+                      uint16_t* d1, uint16_t* d2);
+/* Device-resident variant; train indices are reported as t_base + local index (train shard of a larger set). */
+int rumi_hamming_top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int t_base,
+                             int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync);
+/* Shard exchange step: pack local results into 8-byte candidates for the all-gather, and merge
+ * `nshards` gathered candidate arrays ([shard][nq], ascending train ranges) with the same '<' rule. */
+int rumi_top2_pack_device(rumi_match* m, const int32_t* d_idx1, const uint16_t* d_d1, const uint16_t* d_d2, int nq,
+                          uint64_t* d_packed, int sync);
+int rumi_top2_merge_device(rumi_match* m, const uint64_t* d_packed, int nshards, int nq, int32_t* d_idx1,
+                           uint16_t* d_d1, uint16_t* d_d2, int sync);
+
+/* Stereo row-band best-1 search of Frame::ComputeStereoMatches (R/lib_src/Frame.cc:828-905): for every left
+ * keypoint the right keypoint with the smallest Hamming distance among those whose row band [y-2s, y+2s] covers the
+ * left row, octave within +-1 and uR in [uL-max_d, uL-min_d]; best_dist starts at TH_HIGH=100, ties keep the lowest
+ * right index; best_r = -1 when nothing beat 100.  HOST pointers; keypoints are rumi_kp records (n < 2^20). */
+int rumi_stereo_best1(rumi_match* m, const rumi_kp* Lk, const uint8_t* Ld, int nL, const rumi_kp* Rk,
+                      const uint8_t* Rd, int nR, const float* scale_factors, int nlevels, int n_rows, float min_d,
+                      float max_d, int32_t* best_r, uint16_t* best_dist);
+
+/* ORBmatcher::DescriptorDistance for one pair (host inline popcount; the API, not a fallback). */
+int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUMI_ORB_H */

@@ -1,0 +1,734 @@
+// C ABI of librumi_orb.so (declared in include/rumi_orb.h): handle management, workspace layout in HBM, stream
+// orchestration.  No arithmetic of the hot path happens on the host; without a CUDA device every call fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rumi_orb.h"
+#include "kernels.cuh"
+#include "orb_geom.h"
+
+using namespace rumi;
+
+static_assert(sizeof(rumi_kp) == 28 && sizeof(KeyPointRec) == 28, "cv::KeyPoint layout");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                     \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(RUMI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D u8 tensor map (x, y, frame) with box (boxW, boxH, 1).  Returns false when TMA's alignment rules are not met.
+bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, int nframes, int stride, long long pitch, int boxW,
+               int boxH) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    if (((uintptr_t)base & 15) || (stride & 15) || (pitch & 15) || boxW > 256 || boxH > 256 || (boxW & 15)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nframes};
+    cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)pitch};
+    cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    uint8_t *pyr = nullptr, *blur = nullptr;
+    uint32_t *cand = nullptr, *candOrdered = nullptr, *sel = nullptr;
+    int *levelCount = nullptr, *cellOff = nullptr, *cellCount = nullptr, *selCount = nullptr, *slot = nullptr;
+    uint64_t* bigKeys = nullptr;
+    KeyPointRec* kps = nullptr;
+    uint8_t* desc = nullptr;
+    int *nkp = nullptr, *nmono = nullptr;
+    CUtensorMap tmap[kMaxLevels];      // tmap[l]: source map (internal level l-1) used to produce level l
+    bool tmapOk[kMaxLevels];
+    int lastFrames = 0;
+};
+
+}  // namespace
+
+struct rumi_orb {
+    int device = 0;
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0, chunk = 1;
+    float scaleFactor = 1.2f;
+    ScaleTables tables;
+    bool useTMA = true;
+    // geometry-dependent state
+    int W = 0, H = 0;
+    OrbConst oc;
+    ResizeCoef* coef = nullptr;                       // all levels, x then y
+    const ResizeCoef *xc[kMaxLevels], *yc[kMaxLevels];
+    int boxW[kMaxLevels], boxH[kMaxLevels];
+    long long pyrLevelOff[kMaxLevels], candLevelOff[kMaxLevels], bigKeysLevelOff[kMaxLevels];
+    int bigKeysCap[kMaxLevels];
+    long long pyrBytes = 0, candElems = 0, bigKeysElems = 0;
+    int fastTilePitch = 0, fastTileRows = 0, fastScorePitch = 0, fastScoreRows = 0, fastMaskWords = 0;
+    int smemKeys = 4096, maxNodeCap = 0;
+    Workspace ws[2];
+    int lastWs = 0;
+    uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
+    int dbgCell = 0;
+};
+
+namespace {
+
+void free_workspace(Workspace& w) {
+    cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
+    cudaFree(w.levelCount); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
+    cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono);
+    cudaStream_t s = w.stream;
+    w = Workspace();
+    w.stream = s;
+}
+
+LevelView internal_view(const rumi_orb* h, const uint8_t* base, int l) {
+    LevelView v;
+    const LevelGeom& g = h->oc.lv[l];
+    v.ptr = base + h->pyrLevelOff[l];
+    v.stride = g.stride;
+    v.pitch = (long long)g.stride * g.h;
+    v.w = g.w; v.h = g.h;
+    return v;
+}
+
+int alloc_workspace(rumi_orb* h, Workspace& w) {
+    const OrbConst& oc = h->oc;
+    const long long n = h->chunk;
+    CU_TRY(cudaMalloc(&w.pyr, h->pyrBytes));
+    CU_TRY(cudaMalloc(&w.blur, h->pyrBytes));
+    CU_TRY(cudaMalloc(&w.cand, 4 * h->candElems));
+    CU_TRY(cudaMalloc(&w.candOrdered, 4 * h->candElems));
+    CU_TRY(cudaMalloc(&w.bigKeys, 8 * h->bigKeysElems));
+    CU_TRY(cudaMalloc(&w.levelCount, 4 * n * oc.nlevels));
+    CU_TRY(cudaMalloc(&w.selCount, 4 * n * oc.nlevels));
+    CU_TRY(cudaMalloc(&w.cellOff, 4 * n * oc.totalCells));
+    CU_TRY(cudaMalloc(&w.cellCount, 4 * n * oc.totalCells));
+    CU_TRY(cudaMalloc(&w.sel, 4 * n * oc.kpCap));
+    CU_TRY(cudaMalloc(&w.slot, 4 * n * oc.kpCap));
+    CU_TRY(cudaMalloc(&w.kps, sizeof(KeyPointRec) * n * oc.kpCap));
+    CU_TRY(cudaMalloc(&w.desc, 32 * n * oc.kpCap));
+    CU_TRY(cudaMalloc(&w.nkp, 4 * n));
+    CU_TRY(cudaMalloc(&w.nmono, 4 * n));
+    CU_TRY(cudaMemset(w.pyr, 0, h->pyrBytes));
+    CU_TRY(cudaMemset(w.blur, 0, h->pyrBytes));
+    for (int l = 1; l < oc.nlevels; ++l) {
+        const LevelView src = internal_view(h, w.pyr, l - 1);
+        w.tmapOk[l] = h->useTMA && make_tmap(&w.tmap[l], src.ptr, src.w, src.h, h->chunk, src.stride, src.pitch,
+                                             h->boxW[l], h->boxH[l]);
+    }
+    return RUMI_OK;
+}
+
+// (Re)builds everything that depends on the image shape.
+int ensure_geometry(rumi_orb* h, int W, int H) {
+    if (h->W == W && h->H == H && h->coef) return RUMI_OK;
+    CU_TRY(cudaSetDevice(h->device));
+    OrbConst oc;
+    const int rc = build_orb_const(oc, W, H, h->nfeatures, h->scaleFactor, h->nlevels, h->iniTh, h->minTh);
+    if (rc) return fail(RUMI_ERR_SHAPE, "image %dx%d cannot be processed with %d levels (code %d)", W, H, h->nlevels, rc);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
+        free_workspace(h->ws[i]);
+    }
+    cudaFree(h->coef);
+    h->coef = nullptr;
+    h->oc = oc;
+    h->W = W; h->H = H;
+    // resize coefficient tables + per-level source box of a 64x32 tile
+    std::vector<ResizeCoef> all;
+    std::vector<size_t> xo(oc.nlevels, 0), yo(oc.nlevels, 0);
+    for (int l = 1; l < oc.nlevels; ++l) {
+        const LevelGeom &s = oc.lv[l - 1], &d = oc.lv[l];
+        AxisCoef cx = make_axis_coef(s.w, d.w), cy = make_axis_coef(s.h, d.h);
+        xo[l] = all.size();
+        for (int i = 0; i < d.w; ++i) all.push_back(ResizeCoef{cx.ofs[i], cx.a0[i], cx.a1[i], 0});
+        yo[l] = all.size();
+        for (int i = 0; i < d.h; ++i) all.push_back(ResizeCoef{cy.ofs[i], cy.a0[i], cy.a1[i], 0});
+        int bw = 0, bh = 0;
+        for (int ox = 0; ox < d.w; ox += kPyrTileW) {
+            const int last = std::min(ox + kPyrTileW, d.w) - 1;
+            bw = std::max(bw, std::min(cx.ofs[last] + 1, s.w - 1) - (cx.ofs[ox] & ~15) + 1);   // box starts 16-aligned
+        }
+        for (int oy = 0; oy < d.h; oy += kPyrTileH) {
+            const int last = std::min(oy + kPyrTileH, d.h) - 1;
+            bh = std::max(bh, std::min(cy.ofs[last] + 1, s.h - 1) - cy.ofs[oy] + 1);
+        }
+        h->boxW[l] = align_up(bw, 16);
+        h->boxH[l] = bh;
+    }
+    if (!all.empty()) {
+        CU_TRY(cudaMalloc(&h->coef, all.size() * sizeof(ResizeCoef)));
+        CU_TRY(cudaMemcpy(h->coef, all.data(), all.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice));
+    } else {
+        CU_TRY(cudaMalloc(&h->coef, sizeof(ResizeCoef)));
+    }
+    for (int l = 1; l < oc.nlevels; ++l) { h->xc[l] = h->coef + xo[l]; h->yc[l] = h->coef + yo[l]; }
+    // level-major workspace offsets for `chunk` frames
+    long long pb = 0, ce = 0, be = 0;
+    int tp = 0, tr = 0, sp = 0, sr = 0, mw = 0, nodeCap = 0;
+    for (int l = 0; l < oc.nlevels; ++l) {
+        const LevelGeom& g = oc.lv[l];
+        h->pyrLevelOff[l] = pb; pb += (long long)h->chunk * g.stride * g.h;
+        pb = (pb + 255) & ~255ll;
+        h->candLevelOff[l] = ce; ce += (long long)h->chunk * g.candCap;
+        int cap = 2;
+        while (cap < g.candCap) cap <<= 1;
+        h->bigKeysCap[l] = cap;
+        h->bigKeysLevelOff[l] = be; be += (long long)h->chunk * cap;
+        tp = std::max(tp, align_up(g.wCell + 6, 4)); tr = std::max(tr, g.hCell + 6);
+        sp = std::max(sp, align_up(g.wCell + 2, 4)); sr = std::max(sr, g.hCell + 2);
+        mw = std::max(mw, (g.wCell * g.hCell + 31) / 32);
+        const int slots = (l + 1 < oc.nlevels ? oc.lv[l + 1].kpBase : oc.kpCap) - g.kpBase;
+        nodeCap = std::max(nodeCap, slots + 1);
+        if (g.candCap >= (1 << 19)) return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, g.candCap);
+    }
+    h->pyrBytes = pb + 256; h->candElems = ce; h->bigKeysElems = be;
+    h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScorePitch = sp; h->fastScoreRows = sr; h->fastMaskWords = mw;
+    h->maxNodeCap = nodeCap;
+    h->smemKeys = 4096;
+    while (h->smemKeys > 256 && octree_smem_bytes(h->smemKeys, nodeCap, 256) > 200 * 1024) h->smemKeys >>= 1;
+    if (octree_smem_bytes(h->smemKeys, nodeCap, 256) > 220 * 1024)
+        return fail(RUMI_ERR_CAPACITY, "nfeatures %d needs more shared memory than one SM has", h->nfeatures);
+    return RUMI_OK;
+}
+
+int ensure_workspace(rumi_orb* h, int idx) {
+    Workspace& w = h->ws[idx];
+    if (!w.stream) CU_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    if (w.pyr) return RUMI_OK;
+    return alloc_workspace(h, w);
+}
+
+// Enqueues the whole extraction of `n` frames whose level 0 is `l0` (internal buffer or caller device memory).
+int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, int n, int lap0, int lap1,
+              KeyPointRec* dKps, uint8_t* dDesc, int outCap, int* dNkp, int* dNmono) {
+    const OrbConst& oc = h->oc;
+    cudaStream_t s = w.stream;
+    ChunkView cv;
+    cv.nframes = n;
+    for (int l = 0; l < oc.nlevels; ++l) {
+        cv.src[l] = l == 0 ? l0 : internal_view(h, w.pyr, l);
+        cv.blur[l] = internal_view(h, w.blur, l);
+    }
+    CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
+    for (int l = 1; l < oc.nlevels; ++l) {
+        PyramidLevelArgs pa;
+        pa.src = cv.src[l - 1]; pa.dst = cv.src[l];
+        pa.xc = h->xc[l]; pa.yc = h->yc[l];
+        pa.boxW = h->boxW[l]; pa.boxH = h->boxH[l];
+        pa.nframes = n;
+        const CUtensorMap* tm = nullptr;
+        CUtensorMap dyn;
+        if (h->useTMA) {
+            if (l > 1 || l0Internal) {
+                if (w.tmapOk[l]) tm = &w.tmap[l];
+            } else if (make_tmap(&dyn, l0.ptr, l0.w, l0.h, n, l0.stride, l0.pitch, h->boxW[1], h->boxH[1])) {
+                tm = &dyn;
+            }
+        }
+        launch_pyramid_level(pa, tm, s);
+    }
+    FastArgs fa;
+    fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
+    fa.tilePitch = h->fastTilePitch; fa.tileRows = h->fastTileRows; fa.scorePitch = h->fastScorePitch;
+    fa.scoreRows = h->fastScoreRows; fa.maskWords = h->fastMaskWords;
+    fa.dbg = h->dbgBuf; fa.dbgCell = h->dbgCell;
+    OctreeArgs oa;
+    oa.nframes = n; oa.cand = w.cand; oa.candOrdered = w.candOrdered; oa.levelCount = w.levelCount;
+    oa.cellOff = w.cellOff; oa.cellCount = w.cellCount; oa.bigKeys = w.bigKeys; oa.sel = w.sel;
+    oa.selCount = w.selCount; oa.smemKeys = h->smemKeys; oa.maxNodeCap = h->maxNodeCap;
+    for (int l = 0; l < oc.nlevels; ++l) {
+        // per-call frame stride inside a level block is candCap / bigKeysCap, the level offsets assume `chunk` frames
+        fa.candLevelOff[l] = oa.candLevelOff[l] = h->candLevelOff[l];
+        oa.bigKeysLevelOff[l] = h->bigKeysLevelOff[l];
+        oa.bigKeysCap[l] = h->bigKeysCap[l];
+    }
+    launch_fast(fa, oc, s);
+    launch_octree(oa, oc, s);
+    DescribeArgs da;
+    da.cv = cv; da.sel = w.sel; da.selCount = w.selCount; da.lap0 = lap0; da.lap1 = lap1; da.slot = w.slot;
+    da.kps = dKps; da.desc = dDesc; da.nkp = dNkp; da.nmono = dNmono; da.outCap = outCap;
+    launch_assign_slots(da, oc, s);
+    launch_blur(cv, oc, s);
+    launch_describe(da, oc, s);
+    CU_TRY(cudaGetLastError());
+    w.lastFrames = n;
+    return RUMI_OK;
+}
+
+int upload_level0(rumi_orb* h, Workspace& w, const uint8_t* imgs, int n, size_t stride, size_t framePitch) {
+    const LevelGeom& g = h->oc.lv[0];
+    uint8_t* dst = w.pyr + h->pyrLevelOff[0];
+    if (framePitch == stride * (size_t)g.h || n == 1) {
+        CU_TRY(cudaMemcpy2DAsync(dst, g.stride, imgs, stride, g.w, (size_t)n * g.h, cudaMemcpyHostToDevice, w.stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            CU_TRY(cudaMemcpy2DAsync(dst + (size_t)i * g.stride * g.h, g.stride, imgs + i * framePitch, stride, g.w,
+                                     g.h, cudaMemcpyHostToDevice, w.stream));
+    }
+    return RUMI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rumi_last_error(void) { return g_err.c_str(); }
+
+int rumi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
+                    int min_th_fast, int device, int max_batch) {
+    if (!out) return fail(RUMI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (nlevels < 1 || nlevels > kMaxLevels || nfeatures < 0 || scale_factor <= 1.0f || max_batch < 1)
+        return fail(RUMI_ERR_ARG, "bad ORB parameters");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RUMI_ERR_CUDA, "no CUDA device: librumi_orb has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RUMI_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU_TRY(cudaSetDevice(device));
+    rumi_orb* h = new rumi_orb();
+    h->device = device; h->nfeatures = nfeatures; h->scaleFactor = scale_factor; h->nlevels = nlevels;
+    h->iniTh = ini_th_fast; h->minTh = min_th_fast; h->chunk = max_batch;
+    h->tables = make_scale_tables(nfeatures, scale_factor, nlevels);
+    const char* e = getenv("RUMI_NO_TMA");
+    h->useTMA = !(e && e[0] == '1');
+    *out = h;
+    return RUMI_OK;
+}
+
+void rumi_orb_destroy(rumi_orb* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
+        free_workspace(h->ws[i]);
+        if (h->ws[i].stream) cudaStreamDestroy(h->ws[i].stream);
+    }
+    cudaFree(h->coef);
+    cudaFree(h->dbgBuf);
+    delete h;
+}
+
+int rumi_orb_levels(const rumi_orb* h) { return h ? h->nlevels : 0; }
+
+int rumi_orb_tables(const rumi_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    for (int l = 0; l < h->nlevels; ++l) {
+        if (scale) scale[l] = h->tables.scale[l];
+        if (inv_scale) inv_scale[l] = h->tables.invScale[l];
+        if (sigma2) sigma2[l] = h->tables.sigma2[l];
+        if (inv_sigma2) inv_sigma2[l] = h->tables.invSigma2[l];
+        if (quota) quota[l] = h->tables.quota[l];
+    }
+    return RUMI_OK;
+}
+
+int rumi_orb_frame_capacity(rumi_orb* h, int w, int h_px) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    OrbConst oc;
+    const int rc = build_orb_const(oc, w, h_px, h->nfeatures, h->scaleFactor, h->nlevels, h->iniTh, h->minTh);
+    if (rc) return fail(RUMI_ERR_SHAPE, "image %dx%d cannot be processed (code %d)", w, h_px, rc);
+    return oc.kpCap;
+}
+
+int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h_px, size_t stride,
+                           size_t frame_pitch, int lap0, int lap1, rumi_kp* kps, uint8_t* desc, int cap_per_frame,
+                           int* n_kp, int* n_mono) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    if (!imgs || w <= 0 || h_px <= 0 || n <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (!kps || !desc || !n_kp || !n_mono || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad output / stride");
+    CU_TRY(cudaSetDevice(h->device));
+    int rc = ensure_geometry(h, w, h_px);
+    if (rc) return rc;
+    const OrbConst& oc = h->oc;
+    if (cap_per_frame < oc.kpCap)
+        return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, oc.kpCap);
+    const int nchunks = (n + h->chunk - 1) / h->chunk;
+    for (int c = 0; c < nchunks; ++c) {
+        const int wi = c & 1;
+        if ((rc = ensure_workspace(h, wi))) return rc;
+        Workspace& ws = h->ws[wi];
+        const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);
+        // stream order makes the reuse of workspace `wi` (two chunks ago) safe
+        if ((rc = upload_level0(h, ws, imgs + (size_t)f0 * frame_pitch, m, stride, frame_pitch))) return rc;
+        const LevelView l0 = internal_view(h, ws.pyr, 0);
+        if ((rc = run_chunk(h, ws, l0, true, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
+        // results: dense [m][kpCap] blocks -> caller's [n][cap_per_frame] layout
+        CU_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap_per_frame, sizeof(rumi_kp) * (size_t)cap_per_frame, ws.kps,
+                                 sizeof(rumi_kp) * (size_t)oc.kpCap, sizeof(rumi_kp) * (size_t)oc.kpCap, m,
+                                 cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap_per_frame * 32, 32 * (size_t)cap_per_frame, ws.desc,
+                                 32 * (size_t)oc.kpCap, 32 * (size_t)oc.kpCap, m, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaMemcpyAsync(n_kp + f0, ws.nkp, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaMemcpyAsync(n_mono + f0, ws.nmono, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
+        h->lastWs = wi;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+    return RUMI_OK;
+}
+
+int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1,
+                     rumi_kp* kps, uint8_t* desc, int cap, int* n_kp, int* n_mono) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    if (!img || w <= 0 || h_px <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (!n_kp || !n_mono || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad output / stride");
+    CU_TRY(cudaSetDevice(h->device));
+    int rc = ensure_geometry(h, w, h_px);
+    if (rc) return rc;
+    if ((rc = ensure_workspace(h, 0))) return rc;
+    Workspace& ws = h->ws[0];
+    const OrbConst& oc = h->oc;
+    if ((rc = upload_level0(h, ws, img, 1, stride, stride * (size_t)h_px))) return rc;
+    const LevelView l0 = internal_view(h, ws.pyr, 0);
+    if ((rc = run_chunk(h, ws, l0, true, 1, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
+    int counts[2];
+    CU_TRY(cudaMemcpyAsync(&counts[0], ws.nkp, 4, cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(cudaMemcpyAsync(&counts[1], ws.nmono, 4, cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(cudaStreamSynchronize(ws.stream));
+    if (h->useTMA && read_tma_timeout_flag() != 0) return fail(RUMI_ERR_CUDA, "TMA transaction timed out");
+    *n_kp = counts[0]; *n_mono = counts[1];
+    const int m = std::min(counts[0], cap);
+    if (m > 0) {
+        if (!kps || !desc) return fail(RUMI_ERR_ARG, "kps/desc NULL");
+        CU_TRY(cudaMemcpy(kps, ws.kps, sizeof(rumi_kp) * (size_t)m, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(desc, ws.desc, 32 * (size_t)m, cudaMemcpyDeviceToHost));
+    }
+    h->lastWs = 0;
+    return RUMI_OK;
+}
+
+int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int w, int h_px, size_t stride,
+                                  size_t frame_pitch, int lap0, int lap1, rumi_kp* d_kps, uint8_t* d_desc,
+                                  int cap_per_frame, int* d_n_kp, int* d_n_mono, int sync) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    if (!d_imgs || w <= 0 || h_px <= 0 || n <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (!d_kps || !d_desc || !d_n_kp || !d_n_mono || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad output / stride");
+    CU_TRY(cudaSetDevice(h->device));
+    int rc = ensure_geometry(h, w, h_px);
+    if (rc) return rc;
+    if (cap_per_frame < h->oc.kpCap)
+        return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, h->oc.kpCap);
+    const int nchunks = (n + h->chunk - 1) / h->chunk;
+    for (int c = 0; c < nchunks; ++c) {
+        const int wi = c & 1;
+        if ((rc = ensure_workspace(h, wi))) return rc;
+        Workspace& ws = h->ws[wi];
+        const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);
+        LevelView l0;
+        l0.ptr = d_imgs + (size_t)f0 * frame_pitch; l0.pitch = (long long)frame_pitch; l0.stride = (int)stride;
+        l0.w = w; l0.h = h_px;
+        if ((rc = run_chunk(h, ws, l0, false, m, lap0, lap1, reinterpret_cast<KeyPointRec*>(d_kps) + (size_t)f0 * cap_per_frame,
+                            d_desc + (size_t)f0 * cap_per_frame * 32, cap_per_frame, d_n_kp + f0, d_n_mono + f0)))
+            return rc;
+        h->lastWs = wi;
+    }
+    if (sync)
+        for (int i = 0; i < 2; ++i)
+            if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+    return RUMI_OK;
+}
+
+int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,
+                      uint8_t* desc) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    if (!img || w <= 0 || h_px <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (n < 0 || (n > 0 && (!kps || !desc)) || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad arguments");
+    if (n == 0) return 0;
+    for (int i = 0; i < n; ++i) {
+        const int x = rint_f(kps[i].x), y = rint_f(kps[i].y);
+        if (x < kEdge || y < kEdge || x >= w - kEdge || y >= h_px - kEdge)
+            return fail(RUMI_ERR_BORDER, "keypoint %d at (%d,%d) is closer than 19 px to the border", i, x, y);
+    }
+    CU_TRY(cudaSetDevice(h->device));
+    if (!h->ws[0].stream) CU_TRY(cudaStreamCreateWithFlags(&h->ws[0].stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->ws[0].stream;
+    uint8_t *dImg = nullptr, *dDesc = nullptr;
+    KeyPointRec* dK = nullptr;
+    const int dstride = align_up(w, 16);
+    CU_TRY(cudaMalloc(&dImg, (size_t)dstride * h_px));
+    CU_TRY(cudaMalloc(&dDesc, 32 * (size_t)n));
+    CU_TRY(cudaMalloc(&dK, sizeof(KeyPointRec) * (size_t)n));
+    CU_TRY(cudaMemcpy2DAsync(dImg, dstride, img, stride, w, h_px, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(dK, kps, sizeof(KeyPointRec) * (size_t)n, cudaMemcpyHostToDevice, s));
+    launch_describe_given(dImg, w, h_px, dstride, dK, n, dDesc, s);
+    CU_TRY(cudaMemcpyAsync(desc, dDesc, 32 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(dImg); cudaFree(dDesc); cudaFree(dK);
+    return n;
+}
+
+static int copy_level(rumi_orb* h, const uint8_t* base, int level, uint8_t* dst, size_t dst_stride, int* w, int* hp) {
+    if (!h || !h->coef) return fail(RUMI_ERR_ARG, "no extraction has run on this handle");
+    if (level < 0 || level >= h->nlevels) return fail(RUMI_ERR_ARG, "level out of range");
+    const LevelView v = internal_view(h, base, level);
+    if (w) *w = v.w;
+    if (hp) *hp = v.h;
+    if (!dst) return RUMI_OK;
+    if (dst_stride < (size_t)v.w) return fail(RUMI_ERR_ARG, "dst_stride too small");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->ws[h->lastWs].stream));
+    CU_TRY(cudaMemcpy2D(dst, dst_stride, v.ptr, v.stride, v.w, v.h, cudaMemcpyDeviceToHost));
+    return RUMI_OK;
+}
+
+int rumi_orb_pyramid_level(rumi_orb* h, int level, uint8_t* dst, size_t dst_stride, int* w, int* h_px) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    return copy_level(h, h->ws[h->lastWs].pyr, level, dst, dst_stride, w, h_px);
+}
+
+int rumi_orb_blurred_level(rumi_orb* h, int level, uint8_t* dst, size_t dst_stride, int* w, int* h_px) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    return copy_level(h, h->ws[h->lastWs].blur, level, dst, dst_stride, w, h_px);
+}
+
+static int debug_list(rumi_orb* h, int level, int32_t* xyr, int cap, bool selected) {
+    if (!h || !h->coef) return fail(RUMI_ERR_ARG, "no extraction has run on this handle");
+    if (level < 0 || level >= h->nlevels) return fail(RUMI_ERR_ARG, "level out of range");
+    CU_TRY(cudaSetDevice(h->device));
+    Workspace& w = h->ws[h->lastWs];
+    CU_TRY(cudaStreamSynchronize(w.stream));
+    const OrbConst& oc = h->oc;
+    int cnt = 0;
+    const int* dcnt = (selected ? w.selCount : w.levelCount) + level;     // frame 0
+    CU_TRY(cudaMemcpy(&cnt, dcnt, 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> buf(std::max(cnt, 1));
+    const uint32_t* src = selected ? w.sel + oc.lv[level].kpBase : w.candOrdered + h->candLevelOff[level];
+    if (cnt > 0) CU_TRY(cudaMemcpy(buf.data(), src, 4 * (size_t)cnt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt && i < cap; ++i) {
+        xyr[3 * i] = cand_x(buf[i]); xyr[3 * i + 1] = cand_y(buf[i]); xyr[3 * i + 2] = cand_resp(buf[i]);
+    }
+    return cnt;
+}
+
+int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* dims5) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    if (!h->dbgBuf) { CU_TRY(cudaMalloc(&h->dbgBuf, 1 << 16)); CU_TRY(cudaMemset(h->dbgBuf, 0, 1 << 16)); }
+    h->dbgCell = cell;
+    if (out && h->coef) {
+        const int nb = h->fastTilePitch * h->fastTileRows + h->fastScorePitch * h->fastScoreRows;
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaMemcpy(out, h->dbgBuf, std::min(nb, cap), cudaMemcpyDeviceToHost));
+        if (dims5) { dims5[0] = h->fastTilePitch; dims5[1] = h->fastTileRows; dims5[2] = h->fastScorePitch; dims5[3] = h->fastScoreRows; dims5[4] = h->fastMaskWords; }
+        return nb;
+    }
+    return 0;
+}
+
+int rumi_orb_debug_candidates(rumi_orb* h, int level, int32_t* xyr, int cap) { return debug_list(h, level, xyr, cap, false); }
+int rumi_orb_debug_selected(rumi_orb* h, int level, int32_t* xyr, int cap) { return debug_list(h, level, xyr, cap, true); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// matching
+struct rumi_match {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t* partial = nullptr; size_t partialCap = 0;
+    uint8_t *dQ = nullptr, *dT = nullptr; size_t qCap = 0, tCap = 0;
+    uint8_t* dOut = nullptr; size_t outCap = 0;      // idx1 (4 B) | d1 (2 B) | d2 (2 B) per query
+};
+
+namespace {
+int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return RUMI_OK;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CU_TRY(cudaMalloc(p, need));
+    *cap = need;
+    return RUMI_OK;
+}
+
+int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int tBase, int32_t* dIdx,
+                uint16_t* dD1, uint16_t* dD2) {
+    if (((uintptr_t)dQ | (uintptr_t)dT) & 15) return fail(RUMI_ERR_ARG, "descriptor arrays must be 16-byte aligned");
+    const int slices = match_slices(nq, nt);
+    int rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq);
+    if (rc) return rc;
+    launch_hamming_top2_partial(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
+    launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
+    CU_TRY(cudaGetLastError());
+    return RUMI_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rumi_match_create(rumi_match** out, int device) {
+    if (!out) return fail(RUMI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RUMI_ERR_CUDA, "no CUDA device: librumi_orb has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RUMI_ERR_ARG, "device %d out of range", device);
+    CU_TRY(cudaSetDevice(device));
+    rumi_match* m = new rumi_match();
+    m->device = device;
+    CU_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    *out = m;
+    return RUMI_OK;
+}
+
+void rumi_match_destroy(rumi_match* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut);
+    delete m;
+}
+
+int rumi_hamming_top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int t_base,
+                             int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nq < 0 || nt < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (nq == 0) return RUMI_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const int rc = top2_device(m, dQ, nq, dT, nt, t_base, d_idx1, d_d1, d_d2);
+    if (rc) return rc;
+    if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, int32_t* idx1,
+                      uint16_t* d1, uint16_t* d2) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nq < 0 || nt < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (nq == 0) return RUMI_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    int rc;
+    if ((rc = grow((void**)&m->dQ, &m->qCap, 32 * (size_t)nq))) return rc;
+    if ((rc = grow((void**)&m->dT, &m->tCap, 32 * (size_t)std::max(nt, 1)))) return rc;
+    if ((rc = grow((void**)&m->dOut, &m->outCap, 8 * (size_t)nq))) return rc;
+    int32_t* dIdx = reinterpret_cast<int32_t*>(m->dOut);
+    uint16_t* dD1 = reinterpret_cast<uint16_t*>(m->dOut + 4 * (size_t)nq);
+    uint16_t* dD2 = dD1 + nq;
+    CU_TRY(cudaMemcpyAsync(m->dQ, Q, 32 * (size_t)nq, cudaMemcpyHostToDevice, m->stream));
+    if (nt > 0) CU_TRY(cudaMemcpyAsync(m->dT, T, 32 * (size_t)nt, cudaMemcpyHostToDevice, m->stream));
+    if ((rc = top2_device(m, m->dQ, nq, m->dT, nt, 0, dIdx, dD1, dD2))) return rc;
+    CU_TRY(cudaMemcpyAsync(idx1, dIdx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(d1, dD1, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(d2, dD2, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+int rumi_top2_pack_device(rumi_match* m, const int32_t* d_idx1, const uint16_t* d_d1, const uint16_t* d_d2, int nq,
+                          uint64_t* d_packed, int sync) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    CU_TRY(cudaSetDevice(m->device));
+    launch_pack_top2(d_idx1, d_d1, d_d2, nq, d_packed, m->stream);
+    CU_TRY(cudaGetLastError());
+    if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+int rumi_top2_merge_device(rumi_match* m, const uint64_t* d_packed, int nshards, int nq, int32_t* d_idx1,
+                           uint16_t* d_d1, uint16_t* d_d2, int sync) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nshards < 1) return fail(RUMI_ERR_ARG, "nshards < 1");
+    CU_TRY(cudaSetDevice(m->device));
+    launch_top2_merge(d_packed, nshards, nq, d_idx1, d_d1, d_d2, m->stream);
+    CU_TRY(cudaGetLastError());
+    if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+int rumi_stereo_best1(rumi_match* m, const rumi_kp* Lk, const uint8_t* Ld, int nL, const rumi_kp* Rk,
+                      const uint8_t* Rd, int nR, const float* scale_factors, int nlevels, int n_rows, float min_d,
+                      float max_d, int32_t* best_r, uint16_t* best_dist) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nL < 0 || nR < 0 || nR >= (1 << 20) || nlevels < 1 || !scale_factors) return fail(RUMI_ERR_ARG, "bad sizes");
+    if (nL == 0) return RUMI_OK;
+    for (int i = 0; i < nR; ++i)
+        if (Rk[i].octave < 0 || Rk[i].octave >= nlevels) return fail(RUMI_ERR_ARG, "right keypoint %d: bad octave", i);
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t kb = sizeof(KeyPointRec);
+    const size_t need = kb * ((size_t)nL + nR) + 32 * ((size_t)nL + nR) + 4 * (size_t)nlevels + 8 * (size_t)nL + 256;
+    int rc = grow((void**)&m->dT, &m->tCap, need);
+    if (rc) return rc;
+    uint8_t* p = m->dT;                                  // 16-byte aligned carve-out
+    uint8_t* dLd = p; p += 32 * (size_t)nL;
+    uint8_t* dRd = p; p += 32 * (size_t)std::max(nR, 1);
+    KeyPointRec* dLk = (KeyPointRec*)p; p += (kb * nL + 15) & ~(size_t)15;
+    KeyPointRec* dRk = (KeyPointRec*)p; p += (kb * std::max(nR, 1) + 15) & ~(size_t)15;
+    float* dSf = (float*)p; p += (4 * (size_t)nlevels + 15) & ~(size_t)15;
+    int32_t* dBest = (int32_t*)p; p += 4 * (size_t)nL;
+    uint16_t* dDist = (uint16_t*)p;
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(dLd, Ld, 32 * (size_t)nL, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(dLk, Lk, kb * nL, cudaMemcpyHostToDevice, s));
+    if (nR > 0) {
+        CU_TRY(cudaMemcpyAsync(dRd, Rd, 32 * (size_t)nR, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(dRk, Rk, kb * nR, cudaMemcpyHostToDevice, s));
+    }
+    CU_TRY(cudaMemcpyAsync(dSf, scale_factors, 4 * (size_t)nlevels, cudaMemcpyHostToDevice, s));
+    launch_stereo_best1(dLk, dLd, nL, dRk, dRd, nR, dSf, n_rows, min_d, max_d, dBest, dDist, s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(best_r, dBest, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(best_dist, dDist, 2 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return RUMI_OK;
+}
+
+int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t x, y;
+        memcpy(&x, a + 8 * i, 8);
+        memcpy(&y, b + 8 * i, 8);
+        d += __builtin_popcountll(x ^ y);
+    }
+    return d;
+}
+
+}  // extern "C"

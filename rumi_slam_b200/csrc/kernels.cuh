@@ -1,0 +1,105 @@
+// Kernel launch interface of the sm_100a ORB front-end (internal; the public boundary is include/rumi_orb.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "orb_common.h"
+
+namespace rumi {
+
+// Per-call view of the images of one chunk of frames.  Level 0 may alias caller memory (device-resident input).
+struct LevelView {
+    const uint8_t* ptr;      // frame 0, row 0
+    long long pitch;         // bytes between frames
+    int stride;              // bytes between rows
+    int w, h;
+};
+
+struct ChunkView {
+    int nframes;
+    LevelView src[kMaxLevels];     // un-blurred pyramid
+    LevelView blur[kMaxLevels];    // 7x7 Gaussian of each level
+};
+
+// One destination index of the fixed-point bilinear resize (cv::resize INTER_LINEAR, 8U).
+struct ResizeCoef { uint16_t ofs; int16_t a0, a1; uint16_t pad; };
+
+// Pyramid tile shape (output pixels per CTA) -- also fixes the TMA box computed on the host.
+constexpr int kPyrTileW = 64, kPyrTileH = 32, kPyrThreads = 256;
+
+struct PyramidLevelArgs {
+    LevelView src, dst;
+    const ResizeCoef* xc;    // [dst.w]
+    const ResizeCoef* yc;    // [dst.h]
+    int boxW, boxH;          // source box staged per tile (boxW multiple of 16)
+    int nframes;
+};
+
+void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap /* nullptr = plain loads */,
+                          cudaStream_t s);
+int read_tma_timeout_flag();     // 1 = a TMA load timed out since the module was loaded, -1 = query failed
+void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s);
+
+struct FastArgs {
+    ChunkView cv;
+    uint32_t* cand;          // level-major: [level][frame][candCap]
+    long long candLevelOff[kMaxLevels];   // element offset of (level, frame 0)
+    int* levelCount;         // [frame][nlevels] (zeroed by the caller)
+    int* cellOff;            // [frame][totalCells]
+    int* cellCount;          // [frame][totalCells]
+    int tilePitch, tileRows, scorePitch, scoreRows, maskWords;   // per-warp shared-memory tile sizes
+    uint8_t* dbg;            // optional: image + score tile of (frame 0, dbgCell) for tests
+    int dbgCell;
+};
+void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s);
+
+struct OctreeArgs {
+    int nframes;
+    const uint32_t* cand;    // as written by FAST
+    uint32_t* candOrdered;   // same layout, reference insertion order
+    long long candLevelOff[kMaxLevels];
+    const int* levelCount; const int* cellOff; const int* cellCount;
+    uint64_t* bigKeys;       // global sort scratch for problems that do not fit shared memory
+    long long bigKeysLevelOff[kMaxLevels];   // element offset of (level, frame 0)
+    int bigKeysCap[kMaxLevels];              // pow2 capacity per (level, frame)
+    uint32_t* sel;           // [frame][kpCap] packed selected candidates, level order
+    int* selCount;           // [frame][nlevels]
+    int smemKeys;            // keys that fit the shared-memory sort buffer
+    int maxNodeCap;
+};
+void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s);
+size_t octree_smem_bytes(int smemKeys, int maxNodeCap, int nthreads);
+
+struct DescribeArgs {
+    ChunkView cv;
+    const uint32_t* sel; const int* selCount;
+    int lap0, lap1;
+    int* slot;               // [frame][kpCap] output slot of each level-ordered keypoint
+    KeyPointRec* kps;        // [frame][outCap]
+    uint8_t* desc;           // [frame][outCap][32]
+    int* nkp; int* nmono;    // [frame]
+    int outCap;
+};
+void launch_assign_slots(const DescribeArgs& a, const OrbConst& oc, cudaStream_t s);
+void launch_describe(const DescribeArgs& a, const OrbConst& oc, cudaStream_t s);
+
+// CloudFrameComputeDescriptors: descriptors of given keypoints on a given (un-pyramided, un-blurred) image.
+void launch_describe_given(const uint8_t* img, int w, int h, int stride, const KeyPointRec* kps, int n,
+                           uint8_t* desc, cudaStream_t s);
+
+// ---- matching ----
+// partial[slice][nq] = {d1:16 | d2:16 | global train index:32} of train rows [slice*sliceRows, ...) (+tBase)
+int match_slices(int nq, int nt);
+void launch_hamming_top2_partial(const uint8_t* Q, int nq, const uint8_t* T, int nt, int tBase, int slices,
+                                 uint64_t* partial, cudaStream_t s);
+// merge per-shard candidates {d1,d2,idx} gathered in shard order: cand[shard][nq]
+void launch_top2_merge(const uint64_t* packed, int nshards, int nq, int32_t* idx1, uint16_t* d1, uint16_t* d2,
+                       cudaStream_t s);
+void launch_pack_top2(const int32_t* idx1, const uint16_t* d1, const uint16_t* d2, int nq, uint64_t* packed,
+                      cudaStream_t s);
+
+void launch_stereo_best1(const KeyPointRec* Lk, const uint8_t* Ld, int nL, const KeyPointRec* Rk, const uint8_t* Rd,
+                         int nR, const float* scaleFactors, int nRows, float minD, float maxD, int32_t* bestR,
+                         uint16_t* bestDist, cudaStream_t s);
+
+}  // namespace rumi

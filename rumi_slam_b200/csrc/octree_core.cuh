@@ -1,0 +1,470 @@
+// Quad-tree keypoint distribution (ORBextractor::DistributeOctTree, R/lib_src/ORBextractor.cc:538-724) re-designed
+// for one thread block per (frame, level) problem.  NOT a translation of the list-based reference:
+//
+//   1. every candidate gets its full root+path code (the tree geometry is data independent, :471-522), and the
+//      candidates are sorted by (code, insertion order) -> every tree node is a contiguous range;
+//   2. the level-synchronous phase (:587-650) is evaluated in closed form from the depth at which neighbouring codes
+//      first differ: |list| after pass t == number of distinct depth-t prefixes, nToExpand == groups with > 1 key;
+//   3. the node list after that phase is produced in the reference's std::list order by sorting leaves on
+//      (creation pass desc, prefix with alternating digit directions) -- push_front reverses the visiting order
+//      once per pass;
+//   4. only the final "largest nodes first" phase (:651-702) is serial (thread 0): it replays libstdc++'s
+//      std::sort (introsort, non-total comparator compareNodes :524-536) on (count, UL.x) pairs so that ties break
+//      exactly as in the reference, then splits from the back until the quota is reached;
+//   5. per-leaf arg-max of the response (:706-721; strict '>' => first in insertion order) in parallel.
+//
+// The same source compiles for the device (blockDim.x threads, __syncthreads) and for the host test harness
+// (1 thread), which is how it is checked against the oracle without a GPU.
+#pragma once
+#include "orb_common.h"
+#include "orb_math.cuh"
+
+namespace rumi {
+
+constexpr int kOrderBits = 19;                       // candidate insertion index (per frame, level) < 2^19
+constexpr int kKeyCodeShift = kOrderBits + 8;        // key = code << 28 | order << 8 | response
+constexpr int kRankBits = 20;
+
+RUMI_HD uint64_t make_tree_key(uint32_t code, uint32_t order, uint32_t resp) {
+    return ((uint64_t)code << kKeyCodeShift) | ((uint64_t)order << 8) | (uint64_t)resp;
+}
+RUMI_HD uint32_t key_code(uint64_t k) { return (uint32_t)(k >> kKeyCodeShift); }
+RUMI_HD uint32_t key_order(uint64_t k) { return (uint32_t)(k >> 8) & ((1u << kOrderBits) - 1u); }
+RUMI_HD uint32_t key_resp(uint64_t k) { return (uint32_t)k & 0xFFu; }
+
+RUMI_HD int highest_bit(uint32_t v) {     // v != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
+// Depth at which two codes first differ: 0 = different roots, j = digit j (1-based from the root), D+1 = identical.
+RUMI_HD int first_diff_depth(uint32_t a, uint32_t b, int D) {
+    const uint32_t x = a ^ b;
+    if (x == 0) return D + 1;
+    const int hb = highest_bit(x);
+    if (hb >= 2 * D) return 0;
+    return D - (hb >> 1);
+}
+
+// Bits to flip so that ascending order of (code ^ mask) on the first `cd` digits equals the reference's list order
+// of the nodes created in pass `cd` (children are pushed to the FRONT of the list while their parents are visited
+// front to back, so each pass reverses the visiting order of the pass before).
+RUMI_HD uint32_t list_order_mask(int cd, int D) {
+    uint32_t m = 0;
+    for (int i = 1; i <= cd; ++i)
+        if (((cd - i) & 1) == 0) m |= 3u << (2 * (D - i));
+    if (cd & 1) m |= ((1u << kRootBits) - 1u) << (2 * D);
+    return m;
+}
+
+struct OctreeWork {
+    uint64_t* keys;        // [Mpad]  sorted tree keys (padding = ~0)
+    uint64_t* lkeys;       // [Gpad]  leaf list keys, sorted = reference list order
+    uint32_t* glo;         // [nodeCap + 1] first key of each depth-t* group, in code order (+ sentinel M)
+    uint32_t* cr_lo;       // [createCap] nodes created by the sorted phase (range start)
+    uint32_t* cr_cnt;      // [createCap] (count; 0 = erased)
+    uint64_t* pend;        // [pendCap] sort elements: (count << 13 | UL.x) << 32 | node ref
+    uint32_t* next;        // [pendCap] node refs for the next round
+    int* hist;             // [2 * (kMaxTreeDepth + 2)]
+    int* part;             // [nthreads + 1] per-thread partial counts
+    int* scal;             // [8] scalars shared between threads
+    int nodeCap, createCap, pendCap;
+};
+
+enum { SC_TSTAR = 0, SC_PHASEB = 1, SC_G = 2, SC_NOUT = 3, SC_NCREATED = 4 };
+constexpr uint32_t kRefListBit = 0x80000000u;        // node ref: bit 31 set -> position in the leaf list
+
+// ---- bitonic sort of n (power of two) u64 ascending; all threads of the block participate ----
+template <class Ctx>
+RUMI_HD void bitonic_sort_u64(Ctx& ctx, uint64_t* a, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = ctx.tid; p < (n >> 1); p += ctx.nthr) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const int q = i | j;
+                const uint64_t x = a[i], y = a[q];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { a[i] = y; a[q] = x; }
+            }
+            ctx.sync();
+        }
+    }
+}
+
+RUMI_HD int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ---- libstdc++ std::sort replay (bits/stl_algo.h: __introsort_loop / __unguarded_partition_pivot /
+// __move_median_to_first / __final_insertion_sort, threshold 16, depth limit 2*lg(n), heapsort fallback) ----
+// Elements are u64; the comparator looks at the high 32 bits only (count, UL.x), exactly like compareNodes.
+namespace stdsort {
+RUMI_HD bool lt(uint64_t a, uint64_t b) { return (uint32_t)(a >> 32) < (uint32_t)(b >> 32); }
+RUMI_HD void swp(uint64_t* v, int i, int j) { const uint64_t t = v[i]; v[i] = v[j]; v[j] = t; }
+
+RUMI_HD void push_heap(uint64_t* v, int first, int hole, int top, uint64_t val) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && lt(v[first + parent], val)) {
+        v[first + hole] = v[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    v[first + hole] = val;
+}
+RUMI_HD void adjust_heap(uint64_t* v, int first, int hole, int len, uint64_t val) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (lt(v[first + child], v[first + child - 1])) --child;
+        v[first + hole] = v[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        v[first + hole] = v[first + child - 1];
+        hole = child - 1;
+    }
+    push_heap(v, first, hole, top, val);
+}
+RUMI_HD void make_heap(uint64_t* v, int first, int last) {
+    const int len = last - first;
+    if (len < 2) return;
+    int parent = (len - 2) / 2;
+    while (true) {
+        const uint64_t val = v[first + parent];
+        adjust_heap(v, first, parent, len, val);
+        if (parent == 0) return;
+        --parent;
+    }
+}
+RUMI_HD void pop_heap(uint64_t* v, int first, int last, int result) {
+    const uint64_t val = v[result];
+    v[result] = v[first];
+    adjust_heap(v, first, 0, last - first, val);
+}
+// __partial_sort(first, last, last) == heap_select + sort_heap over the whole range
+RUMI_HD void heap_sort(uint64_t* v, int first, int last) {
+    make_heap(v, first, last);
+    // __heap_select with middle == last: the loop over [middle, last) is empty
+    while (last - first > 1) {
+        --last;
+        pop_heap(v, first, last, last);
+    }
+}
+RUMI_HD void move_median_to_first(uint64_t* v, int result, int a, int b, int c) {
+    if (lt(v[a], v[b])) {
+        if (lt(v[b], v[c])) swp(v, result, b);
+        else if (lt(v[a], v[c])) swp(v, result, c);
+        else swp(v, result, a);
+    } else if (lt(v[a], v[c])) swp(v, result, a);
+    else if (lt(v[b], v[c])) swp(v, result, c);
+    else swp(v, result, b);
+}
+RUMI_HD int unguarded_partition(uint64_t* v, int first, int last, int pivot) {
+    while (true) {
+        while (lt(v[first], v[pivot])) ++first;
+        --last;
+        while (lt(v[pivot], v[last])) --last;
+        if (!(first < last)) return first;
+        swp(v, first, last);
+        ++first;
+    }
+}
+RUMI_HD void unguarded_linear_insert(uint64_t* v, int last) {
+    const uint64_t val = v[last];
+    int next = last - 1;
+    while (lt(val, v[next])) {
+        v[last] = v[next];
+        last = next;
+        --next;
+    }
+    v[last] = val;
+}
+RUMI_HD void insertion_sort(uint64_t* v, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (lt(v[i], v[first])) {
+            const uint64_t val = v[i];
+            for (int k = i; k > first; --k) v[k] = v[k - 1];     // move_backward(first, i, i + 1)
+            v[first] = val;
+        } else {
+            unguarded_linear_insert(v, i);
+        }
+    }
+}
+RUMI_HD void sort(uint64_t* v, int n) {
+    if (n < 2) return;
+    // __introsort_loop, with its tail recursion on the left part turned into an explicit stack of right parts
+    int depth_limit = 2 * highest_bit((uint32_t)n);
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 0;
+    int first = 0, last = n;
+    while (true) {
+        while (last - first > 16) {
+            if (depth_limit == 0) {
+                heap_sort(v, first, last);
+                break;                                   // this range is done
+            }
+            --depth_limit;
+            const int mid = first + (last - first) / 2;
+            move_median_to_first(v, first, first + 1, mid, last - 1);
+            const int cut = unguarded_partition(v, first + 1, last, first);
+            // reference recurses on [cut, last) first, then loops on [first, cut)
+            stack_first[sp] = first; stack_last[sp] = cut; stack_depth[sp] = depth_limit; ++sp;
+            first = cut;
+        }
+        if (sp == 0) break;
+        --sp;
+        first = stack_first[sp]; last = stack_last[sp]; depth_limit = stack_depth[sp];
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        insertion_sort(v, 0, 16);
+        for (int i = 16; i != n; ++i) unguarded_linear_insert(v, i);
+    } else {
+        insertion_sort(v, 0, n);
+    }
+}
+}  // namespace stdsort
+
+// Number of keys of [lo, lo+cnt) whose code digit at `depth` (1-based) is < q, i.e. start of child q.
+RUMI_HD uint32_t child_start(const uint64_t* keys, uint32_t lo, uint32_t cnt, int shift, uint32_t q) {
+    uint32_t a = lo, b = lo + cnt;
+    while (a < b) {
+        const uint32_t m = (a + b) >> 1;
+        if (((key_code(keys[m]) >> shift) & 3u) < q) a = m + 1; else b = m;
+    }
+    return a;
+}
+
+// The whole distribution for one (frame, level).  cand[0..M) are packed candidates in the reference's insertion
+// order.  Selected candidates are written to out[] (packed, level coordinates relative to (16,16)) in the
+// reference's output order; returns their number through scal[SC_NOUT].
+template <class Ctx>
+RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, const LevelGeom& g, OctreeWork& w,
+                                 uint32_t* out, int outCap) {
+    const int D = g.treeDepth;
+    const int height = g.h - 2 * kMinBorder;
+    const int Mpad = next_pow2(M > 1 ? M : 2);
+
+    // 1. keys
+    for (int i = ctx.tid; i < Mpad; i += ctx.nthr) {
+        uint64_t k = ~0ull;
+        if (i < M) {
+            const uint32_t c = cand[i];
+            k = make_tree_key(tree_code(cand_x(c), cand_y(c), g.hX, g.nIni, height, D), (uint32_t)i, cand_resp(c));
+        }
+        w.keys[i] = k;
+    }
+    for (int i = ctx.tid; i < 2 * (kMaxTreeDepth + 2); i += ctx.nthr) w.hist[i] = 0;
+    ctx.sync();
+    bitonic_sort_u64(ctx, w.keys, Mpad);
+
+    // 2. closed-form level-synchronous phase
+    int* histB = w.hist;                          // boundaries first visible at depth u
+    int* histS = w.hist + (kMaxTreeDepth + 2);    // keys that become singletons at depth u
+    for (int i = ctx.tid; i < M; i += ctx.nthr) {
+        const uint32_t c = key_code(w.keys[i]);
+        const int a = i == 0 ? 0 : first_diff_depth(key_code(w.keys[i - 1]), c, D);
+        const int b = i == M - 1 ? 0 : first_diff_depth(c, key_code(w.keys[i + 1]), D);
+        ctx.atomic_add(&histB[a], 1);
+        ctx.atomic_add(&histS[a > b ? a : b], 1);
+    }
+    ctx.sync();
+    if (ctx.tid == 0) {
+        int size = histB[0], singles = histS[0];
+        int tstar = 0, phaseB = 0;
+        if (M > 0) {
+            int prev = size;
+            for (int t = 1;; ++t) {
+                if (t <= D) { size += histB[t]; singles += histS[t]; }
+                tstar = t;
+                const int nexp = size - singles;
+                if (size >= N || size == prev) break;
+                if (size + 3 * nexp > N) { phaseB = 1; break; }
+                prev = size;
+            }
+            if (tstar > D) tstar = D;       // only reached when nothing can be split any more
+            w.scal[SC_G] = 0;
+            int s = 0;
+            for (int t = 0; t <= tstar; ++t) s += histB[t];
+            w.scal[SC_G] = s;
+        } else {
+            w.scal[SC_G] = 0;
+        }
+        w.scal[SC_TSTAR] = tstar;
+        w.scal[SC_PHASEB] = phaseB;
+        w.scal[SC_NOUT] = 0;
+        w.scal[SC_NCREATED] = 0;
+    }
+    ctx.sync();
+    const int tstar = w.scal[SC_TSTAR];
+    const int G = w.scal[SC_G];
+    if (M == 0 || G == 0) return;
+
+    // 3. groups at depth t* in code order (ordered compaction of the boundaries), then the list order
+    {
+        const int chunk = (M + ctx.nthr - 1) / ctx.nthr;
+        const int i0 = ctx.tid * chunk, i1 = (i0 + chunk < M) ? i0 + chunk : M;
+        int c = 0;
+        for (int i = i0; i < i1; ++i) {
+            const int a = i == 0 ? 0 : first_diff_depth(key_code(w.keys[i - 1]), key_code(w.keys[i]), D);
+            c += a <= tstar;
+        }
+        w.part[ctx.tid] = c;
+        ctx.sync();
+        if (ctx.tid == 0) {
+            int s = 0;
+            for (int t = 0; t < ctx.nthr; ++t) { const int v = w.part[t]; w.part[t] = s; s += v; }
+            w.glo[G] = (uint32_t)M;
+        }
+        ctx.sync();
+        int r = w.part[ctx.tid];
+        for (int i = i0; i < i1; ++i) {
+            const int a = i == 0 ? 0 : first_diff_depth(key_code(w.keys[i - 1]), key_code(w.keys[i]), D);
+            if (a <= tstar) w.glo[r++] = (uint32_t)i;
+        }
+        ctx.sync();
+    }
+    const int Gpad = next_pow2(G > 1 ? G : 2);
+    for (int r = ctx.tid; r < Gpad; r += ctx.nthr) {
+        uint64_t lk = ~0ull;
+        if (r < G) {
+            const uint32_t lo = w.glo[r], hi = w.glo[r + 1];
+            const uint32_t c = key_code(w.keys[lo]);
+            int cd = tstar;                                   // pass in which this leaf was created
+            if (hi - lo == 1) {
+                const int a = lo == 0 ? 0 : first_diff_depth(key_code(w.keys[lo - 1]), c, D);
+                const int b = hi == (uint32_t)M ? 0 : first_diff_depth(c, key_code(w.keys[hi]), D);
+                cd = a > b ? a : b;
+                if (cd > tstar) cd = tstar;
+            }
+            const int shift = 2 * (D - cd);
+            const uint32_t pref = ((c ^ list_order_mask(cd, D)) >> shift) << shift;
+            lk = ((uint64_t)(D - cd) << (2 * kMaxTreeDepth + kRootBits + kRankBits)) |
+                 ((uint64_t)pref << kRankBits) | (uint64_t)r;
+        }
+        w.lkeys[r] = lk;
+    }
+    ctx.sync();
+    bitonic_sort_u64(ctx, w.lkeys, Gpad);
+
+    // 4. sorted final phase (serial: it is defined by a sequential std::sort + early break)
+    if (ctx.tid == 0) {
+        const uint32_t rankMask = (1u << kRankBits) - 1u;
+        int ncreated = 0;
+        if (w.scal[SC_PHASEB]) {
+            int size = G;
+            int npend = 0;
+            // pending = multi-key nodes created in pass t*, in creation order == reverse list order
+            for (int k = G - 1; k >= 0; --k) {
+                const uint32_t r = (uint32_t)w.lkeys[k] & rankMask;
+                const uint32_t cnt = w.glo[r + 1] - w.glo[r];
+                if (cnt > 1) w.next[npend++] = kRefListBit | (uint32_t)k;
+            }
+            int depth = tstar;                       // depth of the pending nodes
+            bool done = false;
+            while (!done) {
+                const int prev = size;
+                for (int p = 0; p < npend; ++p) {
+                    const uint32_t ref = w.next[p];
+                    uint32_t lo, cnt;
+                    if (ref & kRefListBit) {
+                        const uint32_t r = (uint32_t)w.lkeys[ref & ~kRefListBit] & rankMask;
+                        lo = w.glo[r]; cnt = w.glo[r + 1] - lo;
+                    } else {
+                        lo = w.cr_lo[ref]; cnt = w.cr_cnt[ref];
+                    }
+                    const uint32_t prefix = key_code(w.keys[lo]) >> (2 * (D - depth));
+                    const uint32_t ulx = (uint32_t)tree_node_ulx(prefix, depth, g.hX);
+                    w.pend[p] = ((uint64_t)((cnt << 13) | ulx) << 32) | (uint64_t)ref;
+                }
+                stdsort::sort(w.pend, npend);
+                int nnext = 0;
+                const int shift = 2 * (D - depth - 1);
+                for (int j = npend - 1; j >= 0; --j) {
+                    const uint32_t ref = (uint32_t)w.pend[j];
+                    uint32_t lo, cnt;
+                    if (ref & kRefListBit) {
+                        const uint32_t k = ref & ~kRefListBit;
+                        const uint32_t r = (uint32_t)w.lkeys[k] & rankMask;
+                        lo = w.glo[r]; cnt = w.glo[r + 1] - lo;
+                        w.lkeys[k] |= 1ull << 63;                     // erased from the list
+                    } else {
+                        lo = w.cr_lo[ref]; cnt = w.cr_cnt[ref];
+                        w.cr_cnt[ref] = 0;                            // erased
+                    }
+                    uint32_t b[5];
+                    b[0] = lo; b[4] = lo + cnt;
+                    if (depth + 1 <= D) {
+                        b[1] = child_start(w.keys, lo, cnt, shift, 1);
+                        b[2] = child_start(w.keys, lo, cnt, shift, 2);
+                        b[3] = child_start(w.keys, lo, cnt, shift, 3);
+                    } else {
+                        b[1] = b[2] = b[3] = lo + cnt;                // cannot happen for distinct pixels
+                    }
+                    int nonempty = 0;
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t cc = b[q + 1] - b[q];
+                        if (cc == 0) continue;
+                        ++nonempty;
+                        w.cr_lo[ncreated] = b[q];
+                        w.cr_cnt[ncreated] = cc;
+                        if (cc > 1) w.next[nnext++] = (uint32_t)ncreated;
+                        ++ncreated;
+                    }
+                    size += nonempty - 1;
+                    if (size >= N) break;
+                }
+                if (size >= N || size == prev) done = true;
+                npend = nnext;
+                ++depth;
+                if (!done) {
+                    // drop erased entries so the tables stay within (quota + 3) live + one round of children
+                    int wpos = 0, pn = 0;
+                    for (int c = 0; c < ncreated; ++c) {
+                        if (w.cr_cnt[c] == 0) continue;
+                        if (pn < npend && w.next[pn] == (uint32_t)c) w.next[pn++] = (uint32_t)wpos;
+                        w.cr_lo[wpos] = w.cr_lo[c];
+                        w.cr_cnt[wpos] = w.cr_cnt[c];
+                        ++wpos;
+                    }
+                    ncreated = wpos;
+                }
+            }
+        }
+        w.scal[SC_NCREATED] = ncreated;
+        // final list: nodes created by the sorted phase, newest first, then the surviving pass-t* list
+        int n = 0;
+        for (int c = ncreated - 1; c >= 0; --c) {
+            if (w.cr_cnt[c] == 0) continue;
+            // reuse pend[] as the output leaf table: lo << 32 | cnt
+            w.pend[n++] = ((uint64_t)w.cr_lo[c] << 32) | (uint64_t)w.cr_cnt[c];
+        }
+        for (int k = 0; k < G; ++k) {
+            const uint64_t lk = w.lkeys[k];
+            if (lk >> 63) continue;
+            const uint32_t r = (uint32_t)lk & rankMask;
+            w.pend[n++] = ((uint64_t)w.glo[r] << 32) | (uint64_t)(w.glo[r + 1] - w.glo[r]);
+        }
+        w.scal[SC_NOUT] = n;
+    }
+    ctx.sync();
+
+    // 5. best response per leaf; ties keep the first candidate in insertion order
+    const int nout = w.scal[SC_NOUT] < outCap ? w.scal[SC_NOUT] : outCap;
+    for (int k = ctx.tid; k < nout; k += ctx.nthr) {
+        const uint32_t lo = (uint32_t)(w.pend[k] >> 32), cnt = (uint32_t)w.pend[k];
+        uint32_t bestResp = 0, bestOrd = 0xFFFFFFFFu;
+        for (uint32_t i = lo; i < lo + cnt; ++i) {
+            const uint64_t key = w.keys[i];
+            const uint32_t r = key_resp(key), o = key_order(key);
+            if (r > bestResp || (r == bestResp && o < bestOrd)) { bestResp = r; bestOrd = o; }
+        }
+        out[k] = cand[bestOrd];
+    }
+}
+
+}  // namespace rumi

@@ -1,0 +1,140 @@
+"""GPU parity tests of the extraction path: every stage and the full ORBextractor::operator() output are compared
+BIT-EXACTLY (keypoint order included) with the oracle on the same seeded synthetic frames, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from rumi_slam_b200.synth import synthetic_frame, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(640, 480, 1000), (752, 480, 1200), (1241, 376, 2000)]
+
+
+def make(nf, **kw):
+    from rumi_slam_b200 import ORBextractor
+    return ORBextractor(nf, 1.2, 8, 20, 7, **kw)
+
+
+@pytest.mark.parametrize("w,h,nf", SHAPES)
+@pytest.mark.parametrize("tma", [True, False])
+def test_pyramid_and_blur_bitexact(oracle, w, h, nf, tma):
+    os.environ["RUMI_NO_TMA"] = "0" if tma else "1"
+    try:
+        ex = make(nf)
+    finally:
+        os.environ["RUMI_NO_TMA"] = "0"
+    img = synthetic_frame(11, w, h)
+    ex(img)
+    ref = oracle.pyramid(img)
+    got = ex.mvImagePyramid
+    for l in range(8):
+        assert got[l].shape == ref[l].shape
+        assert np.array_equal(got[l], ref[l]), "pyramid level %d differs" % l
+    blur = ex.blurred_pyramid()
+    for l in range(8):
+        assert np.array_equal(blur[l], oracle.blur(ref[l])), "blurred level %d differs" % l
+
+
+@pytest.mark.parametrize("w,h,nf", SHAPES)
+def test_fast_candidates_and_octree_bitexact(oracle, w, h, nf):
+    ex = make(nf)
+    img = synthetic_frame(5, w, h)
+    ex(img)
+    ref_py = oracle.pyramid(img)
+    tb = oracle.tables(nf)
+    nfallback = 0
+    for l in range(8):
+        cand, nfb = oracle.grid_fast(ref_py[l])
+        nfallback += nfb
+        got = ex.debug_candidates(l)
+        assert np.array_equal(got, cand.astype(np.int32)), "FAST candidates (x,y,response,order) level %d" % l
+        lh, lw = ref_py[l].shape
+        sel = oracle.octree(cand, 16, lw - 16, 16, lh - 16, int(tb["quota"][l]))
+        gsel = ex.debug_candidates(l, selected=True)
+        assert np.array_equal(gsel, cand[sel].astype(np.int32)), "octree selection level %d" % l
+    assert nfallback > 0, "synthetic frame should exercise the minThFAST fallback"
+
+
+@pytest.mark.parametrize("w,h,nf", SHAPES + [(640, 480, 2000), (640, 480, 5000)])
+@pytest.mark.parametrize("lap", [(0, 0), (0, 1000)])
+def test_extract_matches_oracle(oracle, w, h, nf, lap):
+    ex = make(nf)
+    for seed in (0, 1):
+        img = synthetic_frame(seed, w, h)
+        mono, kps, desc = ex(img, None, lap)
+        rk, rd, rmono = oracle.extract(img, nfeatures=nf, lapping=lap)
+        assert mono == rmono
+        assert len(kps) == len(rk)
+        for f in ("x", "y", "size", "response", "octave", "class_id"):
+            assert np.array_equal(kps[f], rk[f]), f
+        # north_star tolerance for angles is 1e-3 rad; this implementation is bit-exact
+        assert np.array_equal(kps["angle"], rk["angle"])
+        assert np.array_equal(desc, rd)
+
+
+def test_batch_equals_single_and_device_path(oracle):
+    import torch
+    n, w, h = 12, 640, 480
+    frames = synthetic_batch(n, w, h, seed0=40)
+    single = make(1000)
+    ref = [single(frames[i]) for i in range(n)]
+    ex = make(1000, max_batch=5)             # 3 chunks, the last one ragged
+    kps, desc, nkp, nmono = ex.extract_batch(frames)
+    for i in range(n):
+        m, k, d = ref[i]
+        assert nkp[i] == len(k) and nmono[i] == m
+        assert np.array_equal(kps[i, :nkp[i]], k) and np.array_equal(desc[i, :nkp[i]], d)
+    dk, dd, dn, dm = ex.extract_batch_device(torch.from_numpy(frames).cuda())
+    dk = dk.cpu().numpy().view(np.uint8).reshape(n, -1, 28)
+    for i in range(n):
+        m, k, d = ref[i]
+        assert int(dn[i]) == len(k) and int(dm[i]) == m
+        assert np.array_equal(dk[i, :len(k)].reshape(-1).view(k.dtype), k)
+        assert np.array_equal(dd[i, :len(k)].cpu().numpy(), d)
+    # unaligned device input (odd row stride) takes the plain-load pyramid path
+    pad = torch.zeros((n, h, w + 3), dtype=torch.uint8, device="cuda")
+    pad[:, :, :w] = torch.from_numpy(frames).cuda()
+    uk, ud, un, um = ex.extract_batch_device(pad[:, :, :w])
+    assert torch.equal(un, dn) and torch.equal(ud, dd)
+
+
+def test_edge_cases(oracle):
+    ex = make(1000)
+    mono, kps, desc = ex(np.zeros((0, 0), np.uint8))
+    assert mono == -1 and len(kps) == 0                       # ORBextractor.cc:1017
+    flat = np.full((480, 640), 77, np.uint8)
+    mono, kps, desc = ex(flat)
+    assert mono == 0 and len(kps) == 0                        # nkeypoints == 0 path (:1035-1036)
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (480, 640), dtype=np.uint8)  # stress: tens of thousands of candidates per level
+    mono, kps, desc = ex(noise)
+    rk, rd, rmono = oracle.extract(noise)
+    assert mono == rmono and np.array_equal(kps, rk) and np.array_equal(desc, rd)
+    small = synthetic_frame(9, 320, 240)                      # different shape on the same handle
+    ex4 = make(500)
+    from rumi_slam_b200 import RumiError
+    with pytest.raises(RumiError):
+        ex4(small[:100, :100])                                # level 7 smaller than one FAST cell: reference divides by 0
+    ex5 = __import__("rumi_slam_b200").ORBextractor(500, 1.2, 4, 20, 7)
+    mono, kps, desc = ex5(small)
+    rk, rd, rmono = oracle.extract(small, nfeatures=500, nlevels=4)
+    assert mono == rmono and np.array_equal(kps, rk) and np.array_equal(desc, rd)
+    view = np.zeros((240, 400), np.uint8)
+    view[:, :320] = small
+    mono2, kps2, desc2 = ex5(view[:, :320])                   # non-contiguous rows (stride 400)
+    assert np.array_equal(kps2, rk) and np.array_equal(desc2, rd)
+
+
+def test_cloud_frame_compute_descriptors(oracle):
+    ex = make(1000)
+    img = synthetic_frame(21, 640, 480)
+    _, kps, _ = oracle.extract(img)[0:3]
+    kps = oracle.extract(img)[0]
+    level0 = kps[kps["octave"] == 0]
+    n, desc = ex.CloudFrameComputeDescriptors(img, level0)
+    rc, rdesc = oracle.describe(img, level0)
+    assert n == rc == len(level0)
+    assert np.array_equal(desc, rdesc)
+    assert ex.CloudFrameComputeDescriptors(np.zeros((0, 0), np.uint8), level0)[0] == -1

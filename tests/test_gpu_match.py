@@ -1,0 +1,93 @@
+"""GPU parity tests of the Hamming matching path (bit-exact indices and distances) through the C ABI."""
+import numpy as np
+import pytest
+
+from rumi_slam_b200.synth import synthetic_frame, perturbed_descriptors, stereo_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def matcher(**kw):
+    from rumi_slam_b200 import ORBmatcher
+    return ORBmatcher(**kw)
+
+
+def real_descriptors(oracle, seeds):
+    return np.concatenate([oracle.extract(synthetic_frame(s))[1] for s in seeds])
+
+
+def test_top2_kats():
+    m = matcher()
+    zeros, ones = np.zeros((1, 32), np.uint8), np.full((1, 32), 255, np.uint8)
+    i1, d1, d2 = m.top2(zeros, ones)
+    assert (i1[0], d1[0], d2[0]) == (-1, 256, 256)            # 256 is not < the initial 256 (ORBmatcher.cc:236-240)
+    one = zeros.copy(); one[0, 7] = 0x10
+    i1, d1, d2 = m.top2(zeros, np.concatenate([ones, one, one, zeros]))
+    assert (i1[0], d1[0], d2[0]) == (3, 0, 1)
+    i1, d1, d2 = m.top2(zeros, np.concatenate([one, one]))    # duplicate rows: earliest index, d2 == d1
+    assert (i1[0], d1[0], d2[0]) == (0, 1, 1)
+    i1, d1, d2 = m.top2(zeros, np.zeros((0, 32), np.uint8))   # no candidates
+    assert (i1[0], d1[0], d2[0]) == (-1, 256, 256)
+
+
+def test_top2_kat_all_ones_index(oracle):
+    # the reference scan starts at bestDist=256 with strict '<': a distance of exactly 256 never becomes best
+    i1, d1, d2 = oracle.hamming_top2(np.zeros((1, 32), np.uint8), np.full((1, 32), 255, np.uint8))
+    assert (i1[0], d1[0], d2[0]) == (-1, 256, 256)
+    gi, gd1, gd2 = matcher().top2(np.zeros((1, 32), np.uint8), np.full((1, 32), 255, np.uint8))
+    assert (gi[0], gd1[0], gd2[0]) == (-1, 256, 256)
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (37, 1000), (1000, 1000), (2049, 4099), (5000, 700)])
+def test_top2_matches_oracle(oracle, nq, nt):
+    base = real_descriptors(oracle, (0, 1))
+    Q = perturbed_descriptors(base, nq, seed=1, flip_p=0.05)
+    T = perturbed_descriptors(base[::-1].copy(), nt, seed=2, flip_p=0.05)
+    T[nt // 2] = T[0]                                          # force exact ties
+    i1, d1, d2 = matcher().top2(Q, T)
+    ri, rd1, rd2 = oracle.hamming_top2(Q, T)
+    assert np.array_equal(i1, ri) and np.array_equal(d1, rd1) and np.array_equal(d2, rd2)
+
+
+def test_sharded_merge_equals_single(oracle):
+    import torch
+    base = real_descriptors(oracle, (2, 3, 4))
+    Q = torch.from_numpy(perturbed_descriptors(base, 3000, seed=3)).cuda()
+    T = torch.from_numpy(perturbed_descriptors(base, 8000, seed=4)).cuda()
+    m = matcher()
+    i1, d1, d2 = m.top2_device(Q, T)
+    for shards in (2, 3, 8):
+        bounds = np.linspace(0, T.shape[0], shards + 1).astype(int)
+        packed = torch.empty((shards, Q.shape[0]), dtype=torch.int64, device="cuda")
+        for s in range(shards):
+            a, b, c = m.top2_device(Q, T[bounds[s]:bounds[s + 1]].contiguous(), t_base=int(bounds[s]))
+            m.pack_device(a, b, c, out=packed[s])
+        gi, g1, g2 = m.merge_device(packed, shards, Q.shape[0])
+        assert torch.equal(gi, i1) and torch.equal(g1, d1) and torch.equal(g2, d2)
+    ri, rd1, rd2 = oracle.hamming_top2(Q.cpu().numpy(), T.cpu().numpy())
+    assert np.array_equal(i1.cpu().numpy(), ri) and np.array_equal(d1.cpu().numpy().astype(np.uint16), rd1)
+    assert np.array_equal(d2.cpu().numpy().astype(np.uint16), rd2)
+
+
+def test_stereo_best1_matches_oracle(oracle):
+    from rumi_slam_b200 import ORBextractor
+    left, right = stereo_pair(1)
+    ex = ORBextractor(1200, 1.2, 8, 20, 7)
+    _, lk, ld = ex(left)
+    _, rk, rd = ex(right)
+    lk, ld, rk, rd = lk.copy(), ld.copy(), rk.copy(), rd.copy()
+    sf = ex.GetScaleFactors()
+    fx, bf = 435.2, 47.9                                        # upstream ORB-SLAM3 EuRoC: maxD = bf / b = fx
+    best, dist = matcher().stereo_best1(lk, ld, rk, rd, sf, left.shape[0], 0.0, fx)
+    rbest, rdist = oracle.stereo_best1(lk, ld, rk, rd, sf, left.shape[0], 0.0, fx)
+    assert np.array_equal(best, rbest) and np.array_equal(dist, rdist)
+    assert (best >= 0).sum() > 100
+
+
+def test_descriptor_distance(oracle):
+    from rumi_slam_b200 import ORBmatcher
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        a, b = rng.integers(0, 256, (2, 32), dtype=np.uint8)
+        assert ORBmatcher.DescriptorDistance(a, b) == oracle.descriptor_distance(a, b) == \
+            int(np.unpackbits(a ^ b).sum())

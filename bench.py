@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""bench.py -- ORB frames/s (640x480, 1000 kp) + Hamming matches/s on B200s, beside the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = one pass of the hot path over one batch of synthetic frames (BASELINE.json configs[1]: 1024 synthetic
+640x480 frames, TUM ORB settings 1000/1.2/8/20/7).  Frames shard by frame across ranks with no data-path
+collective, each rank owning its own 1024-frame batch ("scaling": "weak").
+
+  value     frames/s over all ranks, inputs already resident in HBM, device-timed on the launching streams
+  e2e       same metric through ORBextractor.extract_batch (HOST pinned buffers; H2D + kernels + D2H timed)
+  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs the measured HBM peak
+  matching  cfg 5a (40 front + 40 back keyframes x 1000 descriptors, all-pairs top-2): matches/s and pairs/s
+  cpu_baseline  the oracle (oracle/_ref = the unmodified reference ORBextractor.cc over a cv stub, when built;
+                else the C++ port) on the host cores, bounded sample
+
+`--impl reference` times that CPU implementation alone on the same config / metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG, NFEAT = 640, 480, 1000
+ORB = dict(nfeatures=NFEAT, scale=1.2, nlevels=8, ini=20, mn=7)
+METRIC = "ORB frames/sec (640x480, 1000 kp)"
+
+
+def level_sizes(w, h, nlevels=8, scale=1.2):
+    s = np.float32(1.0)
+    out = []
+    for _ in range(nlevels):
+        inv = np.float32(1.0) / s
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+        s = np.float32(s * np.float32(scale))
+    return out
+
+
+def algorithmic_bytes(w, h, nkp):
+    """Per-frame ALGORITHMIC bytes of each stage (DESIGN.md 'bytes per unit')."""
+    px = [a * b for a, b in level_sizes(w, h)]
+    return {
+        "pyramid": sum(px[:-1]) + sum(px[1:]),          # read level l-1, write level l, l = 1..7
+        "fast": sum(px),                                 # read every level once
+        "octree": 0,                                     # candidate lists only (KBs): not an HBM-bound stage
+        "slots": 0,
+        "blur": 2 * sum(px),                             # read + write every level
+        "describe": nkp * (749 + 512 + 60),              # circular patch + 512 samples + 60 B out per keypoint
+        "frame": sum(px) + sum(px[1:]) + 60 * nkp,       # whole path: 1 653 864 B for 640x480 / 1000 kp
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while a timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.lines:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_extract_rate(frames, threads, seconds_hint=None):
+    """frames/s of the CPU reference path on `threads` host threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import orb_oracle, ref_lib
+    use_ref = ref_lib.available()
+    fn = ref_lib.extract if use_ref else orb_oracle.extract
+    orb_oracle.build()
+    fn(frames[0], **ORB)                                         # load + warm
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda im: fn(im, **ORB), frames))
+    dt = time.perf_counter() - t0
+    return len(frames) / dt, ("reference" if use_ref else "port"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rumi_slam_b200.synth import synthetic_batch
+    cores = len(os.sched_getaffinity(0))
+    per_step = max(2 * cores, 16)
+    frames = synthetic_batch(per_step, W_IMG, H_IMG, seed0=1000, unique=min(per_step, 16))
+    for _ in range(args.warmup):
+        cpu_extract_rate(frames[:cores], cores)
+    t0 = time.perf_counter()
+    kind = "port"
+    for _ in range(args.steps):
+        _, kind, _ = cpu_extract_rate(frames, cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ORB extraction, synthetic 640x480 frames, 1000 features / 8 levels / 1.2 / FAST 20-7",
+                       "frames_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "%d frames per step on %d host threads; oracle/_ref = unmodified reference "
+                                       "ORBextractor.cc compiled over oracle/cvstub (cv2-pinned primitives)"
+                                       % (per_step, cores)},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from rumi_slam_b200 import ORBextractor, ORBmatcher
+    from rumi_slam_b200.sharding import sharded_top2, train_shard
+    from rumi_slam_b200.synth import synthetic_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    nframes, chunk = args.frames, args.chunk
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic inputs: 1024 frames per rank, distinct seeds per rank ----
+    host = synthetic_batch(nframes, W_IMG, H_IMG, seed0=10000 * rank, unique=args.unique)
+    pinned = torch.from_numpy(host).pin_memory()
+    resident = pinned.to(dev)                                   # 315 MB > 126 MB of L2: no flush needed
+    ex = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_batch=chunk)
+    cap = ex.frame_capacity(W_IMG, H_IMG)
+    out_dev = (torch.zeros((nframes, cap, 7), dtype=torch.float32, device=dev),
+               torch.zeros((nframes, cap, 32), dtype=torch.uint8, device=dev),
+               torch.zeros(nframes, dtype=torch.int32, device=dev), torch.zeros(nframes, dtype=torch.int32, device=dev))
+    sampler = ClockSampler(local)
+    windows = []
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        ex.extract_batch_device(resident, out=out_dev, sync=True)
+    if rank == 0:
+        sampler.start()
+    ex.launch_count(reset=True)
+    ex.profile(True)
+    ex.profile_read(reset=True)
+    barrier()
+    t_a = time.perf_counter()
+    ex.timer_start()
+    for _ in range(args.steps):
+        ex.extract_batch_device(resident, out=out_dev, sync=False)
+    ms = ex.timer_stop()
+    barrier()
+    windows.append((t_a, time.perf_counter()))
+    ms = max_over_ranks(ms)
+    launches = ex.launch_count(reset=True)
+    stages = ex.profile_read(reset=True)
+    ex.profile(False)
+    value = world * nframes * args.steps / (ms / 1e3)
+    nkp_mean = float(out_dev[2].float().mean().item())
+
+    # ---- e2e: host pinned buffers through the public batch call (H2D + kernels + D2H inside the timed region) ----
+    from rumi_slam_b200 import KP_DTYPE
+    out_host = (torch.zeros((nframes, cap, 28), dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE).reshape(nframes, cap),
+                torch.zeros((nframes, cap, 32), dtype=torch.uint8).pin_memory().numpy(),
+                torch.zeros(nframes, dtype=torch.int32).pin_memory().numpy(),
+                torch.zeros(nframes, dtype=torch.int32).pin_memory().numpy())
+    host_pinned = pinned.numpy()
+    for _ in range(max(1, args.warmup - 1)):
+        ex.extract_batch(host_pinned, out=out_host)
+    barrier()
+    t_a = time.perf_counter()
+    ex.timer_start()
+    for _ in range(args.steps):
+        ex.extract_batch(host_pinned, out=out_host)
+    ms_e2e = ex.timer_stop()
+    barrier()
+    windows.append((t_a, time.perf_counter()))
+    ms_e2e = max_over_ranks(ms_e2e)
+    launches_e2e = ex.launch_count(reset=True)
+    e2e_value = world * nframes * args.steps / (ms_e2e / 1e3)
+    h2d = nframes * W_IMG * H_IMG
+    d2h = nframes * cap * (28 + 32) + 8 * nframes
+
+    # ---- matching: cfg 5a, 40 front + 40 back keyframes x 1000 descriptors, all pairs; train sharded over ranks ----
+    nq = nt = 40 * 1000
+    desc = out_dev[1][:80]                                      # 80 extracted frames of this rank
+    cnt = out_dev[2][:80].tolist()
+    rows = torch.cat([desc[i, :min(c, 1000)] for i, c in enumerate(cnt)])
+    reps = -(-(nq + nt) // rows.shape[0])
+    rows = rows.repeat(reps, 1)
+    Q, T = rows[:nq].contiguous(), rows[nq:nq + nt].flip(0).contiguous()
+    if world > 1:                                              # every rank must see the same Q / T
+        dist.broadcast(Q, 0); dist.broadcast(T, 0)
+    m = ORBmatcher(device=local)
+    b, e = train_shard(nt, rank, world)
+    T_local = T[b:e].contiguous()
+
+    def match_once():
+        if world == 1:
+            return m.top2_device(Q, T_local, t_base=b, sync=False)
+        return sharded_top2(m, Q, T_local, b)
+
+    for _ in range(3):
+        match_once()
+    barrier()
+    msteps = max(args.steps, 10)
+    t_a = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.timer_start()
+    for _ in range(msteps):
+        match_once()
+    ms_match = m.timer_stop()
+    barrier()
+    windows.append((t_a, time.perf_counter()))
+    ms_match = max_over_ranks(ms_match)
+    match_launches = m.launch_count(reset=True)
+    matches_per_s = nq * msteps / (ms_match / 1e3)
+    pairs_per_s = matches_per_s * nt
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    clocks = sampler.stop(windows)
+
+    # ---- roofline of the dominant kernel (stage with the largest share of the device time) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg = algorithmic_bytes(W_IMG, H_IMG, nkp_mean)
+    total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    stage_rows = {}
+    for name, (sms, nl) in stages.items():
+        by = alg[name] * nframes * args.steps                  # bytes this stage moved algorithmically in the region
+        gbs = by / (sms / 1e3) / 1e9 if sms > 0 else 0.0
+        stage_rows[name] = {"ms": round(sms, 3), "share": round(sms / total_stage_ms, 4), "launches": nl,
+                            "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)}
+    dom = max(stages, key=lambda k: stages[k][0])
+    dms, dn = stages[dom]
+    per_launch_bytes = alg[dom] * nframes * args.steps / max(dn, 1)
+    per_launch_s = dms / 1e3 / max(dn, 1)
+    achieved = per_launch_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(per_launch_bytes), "avg_launch_ms": round(per_launch_s * 1e3, 4),
+                "whole_step": {"algorithmic_bytes_per_frame": int(alg["frame"]),
+                               "achieved": round(value * alg["frame"] / 1e9, 2),
+                               "frac": round(value * alg["frame"] / 1e9 / hbm_peak, 5)},
+                "stages": stage_rows}
+
+    # ---- CPU baseline on the host cores (bounded sample, rank 0, N == 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = len(os.sched_getaffinity(0))
+        sample = max(4 * cores, 32)
+        rate, kind, dt = cpu_extract_rate(host[:sample], cores)
+        rate1, _, dt1 = cpu_extract_rate(host[:8], 1)
+        cpu = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": "%d of the same synthetic frames on %d host threads (%.1f s); 1 thread: %.1f frames/s"
+                         % (sample, cores, dt, rate1),
+               "single_thread": rate1}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ORB extraction, batch of %d synthetic 640x480 frames per GPU (BASELINE configs[1]), "
+                                   "1000 features / 8 levels / 1.2 / FAST 20-7, frame-sharded" % nframes,
+                       "frames_per_gpu": nframes, "chunk_frames": chunk, "mean_keypoints_per_frame": nkp_mean,
+                       "l2": "inputs (315 MB per GPU) exceed the 126 MB L2, no flush between steps"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "gpu_launches_e2e": launches_e2e,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "matching": {"workload": "cfg 5a: 40000 x 40000 descriptors all-pairs top-2, train set sharded over %d GPU(s)" % world,
+                         "matches_per_s": matches_per_s, "pairs_per_s": pairs_per_s, "ms_per_step": ms_match / msteps,
+                         "gpu_launches": match_launches, "steps": msteps},
+            "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("RUMI_CHUNK", "64")))
+    ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames generated per rank")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:          # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,18 @@ int rumi_orb_debug_selected(rumi_orb* h, int level, int32_t* xyr, int cap);
 /* Test hook: arms (out == NULL) or reads back the shared-memory image + score tile of FAST cell `cell` of frame 0. */
 int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* dims5);
 
+/* ---- measurement (bench.py) ----
+ * Device-side timing on the streams the kernels are launched on: start records an event on the handle's first
+ * stream (the second waits for it), stop joins both streams, records, synchronises and returns the elapsed ms. */
+int rumi_orb_timer_start(rumi_orb* h);
+int rumi_orb_timer_stop(rumi_orb* h, float* ms);
+/* Optional per-stage CUDA events around every launch group (0 pyramid, 1 FAST, 2 quad-tree, 3 slots, 4 blur,
+ * 5 orientation+descriptors).  profile_read synchronises, accumulates and returns the number of stages. */
+int rumi_orb_profile(rumi_orb* h, int enable);
+int rumi_orb_profile_read(rumi_orb* h, double* stage_ms, long long* stage_launches, int reset);
+/* Number of kernels this handle has launched (own kernels only; memsets / copies are not counted). */
+long long rumi_orb_launch_count(rumi_orb* h, int reset);
+
 /* ---- matching ---- */
 int rumi_match_create(rumi_match** out, int device);
 void rumi_match_destroy(rumi_match* m);
@@ -103,6 +115,10 @@ int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T,
 /* Device-resident variant; train indices are reported as t_base + local index (train shard of a larger set). */
 int rumi_hamming_top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int t_base,
                              int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync);
+int rumi_match_timer_start(rumi_match* m);
+int rumi_match_timer_stop(rumi_match* m, float* ms);
+long long rumi_match_launch_count(rumi_match* m, int reset);
+
 /* Shard exchange step: pack local results into 8-byte candidates for the all-gather, and merge
  * `nshards` gathered candidate arrays ([shard][nq], ascending train ranges) with the same '<' rule. */
 int rumi_top2_pack_device(rumi_match* m, const int32_t* d_idx1, const uint16_t* d_d1, const uint16_t* d_d2, int nq,

@@ -39,6 +39,14 @@ SIGNATURES = {
     "rumi_orb_debug_candidates": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "rumi_orb_debug_selected": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "rumi_orb_debug_fast_tile": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
+    "rumi_orb_timer_start": (C.c_int, [_vp]),
+    "rumi_orb_timer_stop": (C.c_int, [_vp, _f32p]),
+    "rumi_orb_profile": (C.c_int, [_vp, C.c_int]),
+    "rumi_orb_profile_read": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "rumi_orb_launch_count": (C.c_longlong, [_vp, C.c_int]),
+    "rumi_match_timer_start": (C.c_int, [_vp]),
+    "rumi_match_timer_stop": (C.c_int, [_vp, _f32p]),
+    "rumi_match_launch_count": (C.c_longlong, [_vp, C.c_int]),
     "rumi_match_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "rumi_match_destroy": (None, [_vp]),
     "rumi_hamming_top2": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),

@@ -110,6 +110,15 @@ struct rumi_orb {
     int lastWs = 0;
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     int dbgCell = 0;
+    // measurement: device-side timer on the launching streams, optional per-stage events, launch counter
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evJoin = nullptr;
+    bool profile = false;
+    std::vector<cudaEvent_t> evPool;
+    size_t evUsed = 0;
+    std::vector<std::pair<int, int>> evSpans;     // (stage, index of the first of two consecutive events)
+    double stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long stageLaunches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long launches = 0;
 };
 
 namespace {
@@ -241,6 +250,27 @@ int ensure_workspace(rumi_orb* h, int idx) {
     return alloc_workspace(h, w);
 }
 
+enum { ST_PYRAMID = 0, ST_FAST = 1, ST_OCTREE = 2, ST_SLOTS = 3, ST_BLUR = 4, ST_DESCRIBE = 5, ST_COUNT = 6 };
+
+cudaEvent_t prof_event(rumi_orb* h, cudaStream_t s) {
+    if (h->evUsed == h->evPool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->evPool.push_back(e);
+    }
+    cudaEvent_t e = h->evPool[h->evUsed++];
+    cudaEventRecord(e, s);
+    return e;
+}
+// closes stage `stage` (which issued `nlaunch` kernels) with an event; spans are resolved in rumi_orb_profile_read
+void prof_mark(rumi_orb* h, cudaStream_t s, int stage, int nlaunch) {
+    h->launches += nlaunch;
+    if (!h->profile) return;
+    h->stageLaunches[stage] += nlaunch;
+    h->evSpans.push_back(std::make_pair(stage, (int)h->evUsed - 1));
+    prof_event(h, s);
+}
+
 // Enqueues the whole extraction of `n` frames whose level 0 is `l0` (internal buffer or caller device memory).
 int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, int n, int lap0, int lap1,
               KeyPointRec* dKps, uint8_t* dDesc, int outCap, int* dNkp, int* dNmono) {
@@ -253,6 +283,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         cv.blur[l] = internal_view(h, w.blur, l);
     }
     CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
+    if (h->profile) prof_event(h, s);
     for (int l = 1; l < oc.nlevels; ++l) {
         PyramidLevelArgs pa;
         pa.src = cv.src[l - 1]; pa.dst = cv.src[l];
@@ -270,6 +301,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         }
         launch_pyramid_level(pa, tm, s);
     }
+    prof_mark(h, s, ST_PYRAMID, oc.nlevels - 1);
     FastArgs fa;
     fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
     fa.tilePitch = h->fastTilePitch; fa.tileRows = h->fastTileRows; fa.scorePitch = h->fastScorePitch;
@@ -286,13 +318,18 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         oa.bigKeysCap[l] = h->bigKeysCap[l];
     }
     launch_fast(fa, oc, s);
+    prof_mark(h, s, ST_FAST, 1);
     launch_octree(oa, oc, s);
+    prof_mark(h, s, ST_OCTREE, 1);
     DescribeArgs da;
     da.cv = cv; da.sel = w.sel; da.selCount = w.selCount; da.lap0 = lap0; da.lap1 = lap1; da.slot = w.slot;
     da.kps = dKps; da.desc = dDesc; da.nkp = dNkp; da.nmono = dNmono; da.outCap = outCap;
     launch_assign_slots(da, oc, s);
+    prof_mark(h, s, ST_SLOTS, 1);
     launch_blur(cv, oc, s);
+    prof_mark(h, s, ST_BLUR, 1);
     launch_describe(da, oc, s);
+    prof_mark(h, s, ST_DESCRIBE, 1);
     CU_TRY(cudaGetLastError());
     w.lastFrames = n;
     return RUMI_OK;
@@ -354,6 +391,10 @@ void rumi_orb_destroy(rumi_orb* h) {
     }
     cudaFree(h->coef);
     cudaFree(h->dbgBuf);
+    for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
+    if (h->evStart) cudaEventDestroy(h->evStart);
+    if (h->evStop) cudaEventDestroy(h->evStop);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
     delete h;
 }
 
@@ -549,6 +590,64 @@ static int debug_list(rumi_orb* h, int level, int32_t* xyr, int cap, bool select
     return cnt;
 }
 
+int rumi_orb_timer_start(rumi_orb* h) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < 2; ++i)
+        if (!h->ws[i].stream) CU_TRY(cudaStreamCreateWithFlags(&h->ws[i].stream, cudaStreamNonBlocking));
+    if (!h->evStart) {
+        CU_TRY(cudaEventCreate(&h->evStart)); CU_TRY(cudaEventCreate(&h->evStop)); CU_TRY(cudaEventCreate(&h->evJoin));
+    }
+    CU_TRY(cudaEventRecord(h->evStart, h->ws[0].stream));
+    CU_TRY(cudaStreamWaitEvent(h->ws[1].stream, h->evStart, 0));
+    return RUMI_OK;
+}
+
+int rumi_orb_timer_stop(rumi_orb* h, float* ms) {
+    if (!h || !h->evStart || !ms) return fail(RUMI_ERR_ARG, "timer not started");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaEventRecord(h->evJoin, h->ws[1].stream));
+    CU_TRY(cudaStreamWaitEvent(h->ws[0].stream, h->evJoin, 0));
+    CU_TRY(cudaEventRecord(h->evStop, h->ws[0].stream));
+    CU_TRY(cudaEventSynchronize(h->evStop));
+    CU_TRY(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+    return RUMI_OK;
+}
+
+int rumi_orb_profile(rumi_orb* h, int enable) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    h->profile = enable != 0;
+    return RUMI_OK;
+}
+
+int rumi_orb_profile_read(rumi_orb* h, double* stage_ms, long long* stage_launches, int reset) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < 2; ++i)
+        if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+    for (const auto& sp : h->evSpans) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, h->evPool[sp.second], h->evPool[sp.second + 1]));
+        h->stageMs[sp.first] += ms;
+    }
+    h->evSpans.clear();
+    h->evUsed = 0;
+    for (int i = 0; i < ST_COUNT; ++i) {
+        if (stage_ms) stage_ms[i] = h->stageMs[i];
+        if (stage_launches) stage_launches[i] = h->stageLaunches[i];
+    }
+    if (reset)
+        for (int i = 0; i < 8; ++i) { h->stageMs[i] = 0; h->stageLaunches[i] = 0; }
+    return ST_COUNT;
+}
+
+long long rumi_orb_launch_count(rumi_orb* h, int reset) {
+    if (!h) return 0;
+    const long long v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+
 int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* dims5) {
     if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
     CU_TRY(cudaSetDevice(h->device));
@@ -577,6 +676,8 @@ struct rumi_match {
     uint64_t* partial = nullptr; size_t partialCap = 0;
     uint8_t *dQ = nullptr, *dT = nullptr; size_t qCap = 0, tCap = 0;
     uint8_t* dOut = nullptr; size_t outCap = 0;      // idx1 (4 B) | d1 (2 B) | d2 (2 B) per query
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    long long launches = 0;
 };
 
 namespace {
@@ -597,6 +698,7 @@ int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int
     if (rc) return rc;
     launch_hamming_top2_partial(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
     launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
+    m->launches += 2;
     CU_TRY(cudaGetLastError());
     return RUMI_OK;
 }
@@ -624,6 +726,7 @@ void rumi_match_destroy(rumi_match* m) {
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
     cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut);
+    if (m->evStart) { cudaEventDestroy(m->evStart); cudaEventDestroy(m->evStop); }
     delete m;
 }
 
@@ -662,11 +765,36 @@ int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T,
     return RUMI_OK;
 }
 
+int rumi_match_timer_start(rumi_match* m) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    CU_TRY(cudaSetDevice(m->device));
+    if (!m->evStart) { CU_TRY(cudaEventCreate(&m->evStart)); CU_TRY(cudaEventCreate(&m->evStop)); }
+    CU_TRY(cudaEventRecord(m->evStart, m->stream));
+    return RUMI_OK;
+}
+
+int rumi_match_timer_stop(rumi_match* m, float* ms) {
+    if (!m || !m->evStart || !ms) return fail(RUMI_ERR_ARG, "timer not started");
+    CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(cudaEventRecord(m->evStop, m->stream));
+    CU_TRY(cudaEventSynchronize(m->evStop));
+    CU_TRY(cudaEventElapsedTime(ms, m->evStart, m->evStop));
+    return RUMI_OK;
+}
+
+long long rumi_match_launch_count(rumi_match* m, int reset) {
+    if (!m) return 0;
+    const long long v = m->launches;
+    if (reset) m->launches = 0;
+    return v;
+}
+
 int rumi_top2_pack_device(rumi_match* m, const int32_t* d_idx1, const uint16_t* d_d1, const uint16_t* d_d2, int nq,
                           uint64_t* d_packed, int sync) {
     if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
     CU_TRY(cudaSetDevice(m->device));
     launch_pack_top2(d_idx1, d_d1, d_d2, nq, d_packed, m->stream);
+    m->launches += 1;
     CU_TRY(cudaGetLastError());
     if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
     return RUMI_OK;
@@ -678,6 +806,7 @@ int rumi_top2_merge_device(rumi_match* m, const uint64_t* d_packed, int nshards,
     if (nshards < 1) return fail(RUMI_ERR_ARG, "nshards < 1");
     CU_TRY(cudaSetDevice(m->device));
     launch_top2_merge(d_packed, nshards, nq, d_idx1, d_d1, d_d2, m->stream);
+    m->launches += 1;
     CU_TRY(cudaGetLastError());
     if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
     return RUMI_OK;
@@ -713,6 +842,7 @@ int rumi_stereo_best1(rumi_match* m, const rumi_kp* Lk, const uint8_t* Ld, int n
     }
     CU_TRY(cudaMemcpyAsync(dSf, scale_factors, 4 * (size_t)nlevels, cudaMemcpyHostToDevice, s));
     launch_stereo_best1(dLk, dLd, nL, dRk, dRd, nR, dSf, n_rows, min_d, max_d, dBest, dDist, s);
+    m->launches += 1;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(best_r, dBest, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(best_dist, dDist, 2 * (size_t)nL, cudaMemcpyDeviceToHost, s));

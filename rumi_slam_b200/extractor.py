@@ -150,6 +150,29 @@ class ORBextractor:
     def blurred_pyramid(self):
         return [self._level(self._L.rumi_orb_blurred_level, l) for l in range(self.nlevels)]
 
+    # ---- measurement hooks (bench.py) ----
+    STAGES = ("pyramid", "fast", "octree", "slots", "blur", "describe")
+
+    def timer_start(self):
+        check(self._L.rumi_orb_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(self._L.rumi_orb_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        check(self._L.rumi_orb_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        ms = np.zeros(8, np.float64)
+        n = np.zeros(8, np.int64)
+        k = check(self._L.rumi_orb_profile_read(self._h, ptr(ms), ptr(n), 1 if reset else 0))
+        return {self.STAGES[i]: (float(ms[i]), int(n[i])) for i in range(k)}
+
+    def launch_count(self, reset=False):
+        return int(self._L.rumi_orb_launch_count(self._h, 1 if reset else 0))
+
     def debug_candidates(self, level, selected=False):
         fn = self._L.rumi_orb_debug_selected if selected else self._L.rumi_orb_debug_candidates
         n = check(fn(self._h, level, None, 0))

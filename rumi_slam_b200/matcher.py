@@ -87,6 +87,17 @@ class ORBmatcher:
                                              1 if sync else 0))
         return i1, d1, d2
 
+    def timer_start(self):
+        check(self._L.rumi_match_timer_start(self._m))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(self._L.rumi_match_timer_stop(self._m, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self, reset=False):
+        return int(self._L.rumi_match_launch_count(self._m, 1 if reset else 0))
+
     # ---- acceptance rules of the reference call sites, applied to the raw triple ----
     def accept_bow(self, d1, d2, th=None):
         """SearchByBoW KF->F (ORBmatcher.cc:290-291): best1 <= TH_LOW and (float)best1 < ratio*(float)best2."""

@@ -1,0 +1,51 @@
+// Accelerated core of ORB_SLAM3::ORBmatcher (R/include/cloud_edge_slam_lib/ORBmatcher.h:36-103).
+// ORBmatcher's Search*/Fuse methods are geometry + bookkeeping around one inner operation: scan candidates,
+// keep best / second-best DescriptorDistance, apply a threshold and a ratio (R/lib_src/ORBmatcher.cc:253-291 etc.).
+// This header provides (1) DescriptorDistance with the reference's exact signature (host inline popcount, the API
+// itself), and (2) batched top-2 / stereo best-1 on the GPU returning the RAW triple so that every call site keeps
+// its own acceptance test (TH_LOW / TH_HIGH, '<' vs '<=', float casts) unchanged on the host.
+#ifndef ORBMATCHER_ACCEL_H
+#define ORBMATCHER_ACCEL_H
+
+#include <cstdint>
+#include <vector>
+#include <opencv2/core/core.hpp>
+
+struct rumi_match;
+
+namespace ORB_SLAM3 {
+
+class ORBmatcherAccel {
+public:
+    static const int TH_LOW = 50;       // R/lib_src/ORBmatcher.cc:32
+    static const int TH_HIGH = 100;     // R/lib_src/ORBmatcher.cc:31
+    static const int HISTO_LENGTH = 30; // R/lib_src/ORBmatcher.cc:33
+
+    explicit ORBmatcherAccel(float nnratio = 0.6f, int device = 0);
+    ~ORBmatcherAccel();
+
+    // == ORBmatcher::DescriptorDistance (R/lib_src/ORBmatcher.cc:1830-1844); rows must be 32 contiguous bytes.
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+
+    // Raw top-2 of every row of Q (nq x 32, CV_8U) against every row of T: earliest index among ties, d2 may equal
+    // d1, (-1, 256, 256) when T is empty.
+    void Top2(const cv::Mat& Q, const cv::Mat& T, std::vector<int>& idx1, std::vector<uint16_t>& d1,
+              std::vector<uint16_t>& d2);
+
+    // SearchByBoW-style acceptance (R/lib_src/ORBmatcher.cc:290-291): best1 <= TH_LOW && best1 < ratio * best2.
+    // matches12[q] = train index or -1.  Returns the number of matches.
+    int MatchRatio(const cv::Mat& Q, const cv::Mat& T, std::vector<int>& matches12, int th = TH_LOW);
+
+    // Frame::ComputeStereoMatches row-band best-1 (R/lib_src/Frame.cc:844-905).
+    void StereoBest1(const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
+                     const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,
+                     const std::vector<float>& scaleFactors, int nRows, float minD, float maxD,
+                     std::vector<int>& bestIdxR, std::vector<uint16_t>& bestDist);
+
+private:
+    rumi_match* ctx;
+    float mfNNratio;
+};
+
+}  // namespace ORB_SLAM3
+#endif

@@ -226,7 +226,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         while (cap < g.candCap) cap <<= 1;
         h->bigKeysCap[l] = cap;
         h->bigKeysLevelOff[l] = be; be += (long long)h->chunk * cap;
-        tp = std::max(tp, align_up(g.wCell + 6, 4)); tr = std::max(tr, g.hCell + 6);
+        tp = std::max(tp, align_up(g.wCell + 6 + 15, 16)); tr = std::max(tr, g.hCell + 6);   // 16-B aligned staging
         sp = std::max(sp, align_up(g.wCell + 2, 4)); sr = std::max(sr, g.hCell + 2);
         mw = std::max(mw, (g.wCell * g.hCell + 31) / 32);
         const int slots = (l + 1 < oc.nlevels ? oc.lv[l + 1].kpBase : oc.kpCap) - g.kpBase;

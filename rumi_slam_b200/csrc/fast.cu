@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
     // per-warp shared memory: image tile | score tile | survivor bitmap | corner list | queue
     const int tp = TP ? TP : a.tilePitch, sp = a.scorePitch;     // TP > 0: compile-time pitch -> immediate offsets
     const size_t perWarp = (size_t)tp * a.tileRows + (size_t)sp * a.scoreRows + 4u * a.maskWords +
-                           2u * 32u * a.maskWords + 2u * 64;
+                           2u * 32u * a.maskWords + 2u * 160;
     uint8_t* base = smem + (size_t)warp * ((perWarp + 15) & ~(size_t)15);
     uint8_t* tile = base;
     uint8_t* score = tile + (size_t)tp * a.tileRows;
@@ -172,38 +172,82 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
         ncorner += __popc(m);
     };
 
-    // ---- A. pretest on the 8 even ring pixels + B. exact test / score on the compacted survivors ----
-    for (int b = 0; b < npx; b += 32) {
-        const int idx = b + lane;
-        bool pass = false;
-        if (idx < npx) {
-            const int y = (int)div_magic((uint32_t)idx, magicW), x = idx - y * dw;
-            const uint8_t* p = t0 + y * tp + x;
-            const int v = p[0], hi = v + th, lo = v - th;
-            uint32_t br = 0, dk = 0;
-            int q;
-            q = p[3 * tp];      br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 0
-            q = p[2 * tp + 2];  br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 2
-            q = p[3];           br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 4
-            q = p[-2 * tp + 2]; br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 6
-            q = p[-3 * tp];     br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 8
-            q = p[-2 * tp - 2]; br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 10
-            q = p[-3];          br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 12
-            q = p[2 * tp - 2];  br = push_sign(br, hi - q); dk = push_sign(dk, q - lo);     // ring 14
-            // 4 consecutive (circular over 8) in either class
-            br = (br & 0xFFu) * 0x101u; dk = (dk & 0xFFu) * 0x101u;
-            uint32_t rb = br & (br >> 1), rd = dk & (dk >> 1);
-            rb &= rb >> 2; rd &= rd >> 2;
-            pass = ((rb | rd) & 0xFFu) != 0;
-        }
-        const unsigned m = __ballot_sync(kFull, pass);
-        if (pass) queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-            qn -= 32;
-            drain(queue[qn + lane], true);
+    // ---- A. SWAR pretest, 4 horizontally adjacent pixels per lane ----
+    // A 9-arc of the 16-ring always covers 4 consecutive EVEN ring positions, all differing from the centre by more
+    // than th.  Per lane: the 4-byte windows of the 8 even ring positions are cut out of aligned shared-memory words
+    // with funnel shifts, |centre - ring| comes from one VABSDIFF4 per position, "> th" sets bit 7 of each byte,
+    // and 16 ANDs + 4 ORs give "4 consecutive positions" for the 4 pixels at once.  (Sign-agnostic, so slightly
+    // weaker than the exact test: survivors go to phase B, which is exact.)
+    {
+        const int c0 = ox + 3;                           // tile column of detection x = 0
+        const int g0 = c0 >> 2, ng = ((c0 + dw - 1) >> 2) - g0 + 1;
+        const uint32_t magicG = magic_of((uint32_t)ng);
+        const uint32_t K = (uint32_t)(th <= 126 ? 127 - th : 0) * 0x01010101u;
+        const uint32_t forceAll = th <= 126 ? 0u : 0x80808080u;
+        const int ngroups = ng * dh;
+        const uint8_t* trow = tile + 3 * tp;            // tile row of detection y = 0
+        for (int b = 0; b < ngroups; b += 32) {
+            const int i = b + lane;
+            uint32_t pass4 = 0;
+            int y = 0, g = 0;
+            if (i < ngroups) {
+                y = (int)div_magic((uint32_t)i, magicG);
+                g = g0 + (i - y * ng);
+                const uint8_t* r0 = trow + y * tp;
+                const int wl = 4 * max(g - 1, 0), wc = 4 * g, wr = 4 * g + 4;
+#define LDW(row, off) (*reinterpret_cast<const uint32_t*>((row) + (off)))
+                const uint32_t ctr = LDW(r0, wc);
+                uint32_t fl[8];
+                {
+                    const uint32_t l = LDW(r0, wl), r = LDW(r0, wr);
+                    fl[2] = __vabsdiffu4(ctr, __funnelshift_r(ctr, r, 24));      // ring 4  (+3, 0)
+                    fl[6] = __vabsdiffu4(ctr, __funnelshift_r(l, ctr, 8));       // ring 12 (-3, 0)
+                }
+                fl[0] = __vabsdiffu4(ctr, LDW(r0 + 3 * tp, wc));                 // ring 0  (0, +3)
+                fl[4] = __vabsdiffu4(ctr, LDW(r0 - 3 * tp, wc));                 // ring 8  (0, -3)
+                {
+                    const uint8_t* rr = r0 + 2 * tp;
+                    const uint32_t l = LDW(rr, wl), m = LDW(rr, wc), r = LDW(rr, wr);
+                    fl[1] = __vabsdiffu4(ctr, __funnelshift_r(m, r, 16));        // ring 2  (+2, +2)
+                    fl[7] = __vabsdiffu4(ctr, __funnelshift_r(l, m, 16));        // ring 14 (-2, +2)
+                }
+                {
+                    const uint8_t* rr = r0 - 2 * tp;
+                    const uint32_t l = LDW(rr, wl), m = LDW(rr, wc), r = LDW(rr, wr);
+                    fl[3] = __vabsdiffu4(ctr, __funnelshift_r(m, r, 16));        // ring 6  (+2, -2)
+                    fl[5] = __vabsdiffu4(ctr, __funnelshift_r(l, m, 16));        // ring 10 (-2, -2)
+                }
+#undef LDW
+#pragma unroll
+                for (int k = 0; k < 8; ++k) fl[k] = (((fl[k] & 0x7F7F7F7Fu) + K) | fl[k]) | forceAll;   // bit 7: > th
+                uint32_t p2[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p2[k] = fl[k] & fl[(k + 1) & 7];
+                uint32_t any = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) any |= p2[k] & p2[(k + 2) & 7];
+                // bytes of this group that are inside the detection area
+                const int xlo = c0 - 4 * g, xhi = c0 + dw - 4 * g;              // valid bytes: xlo <= j < xhi
+                uint32_t valid = 0x80808080u;
+                if (xlo > 0) valid &= 0xFFFFFFFFu << (8 * xlo);
+                if (xhi < 4) valid &= 0xFFFFFFFFu >> (8 * (4 - xhi));
+                pass4 = any & valid;
+            }
+            const int idx0 = y * dw + 4 * g - c0;                                // detection index of byte 0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool pj = (pass4 >> (8 * j + 7)) & 1u;
+                const unsigned m = __ballot_sync(kFull, pj);
+                if (pj) queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(idx0 + j);
+                qn += __popc(m);
+            }
             __syncwarp();
+            // ---- B. exact score on the compacted survivors, 32 at a time ----
+            while (qn >= 32) {
+                qn -= 32;
+                drain(queue[qn + lane], true);
+                __syncwarp();
+            }
         }
     }
     drain(lane < qn ? queue[lane] : 0, lane < qn);
@@ -280,7 +324,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
 
 void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s) {
     const size_t perWarp = ((size_t)a.tilePitch * a.tileRows + (size_t)a.scorePitch * a.scoreRows +
-                            4u * a.maskWords + 2u * 32u * a.maskWords + 2u * 64 + 15) & ~(size_t)15;
+                            4u * a.maskWords + 2u * 32u * a.maskWords + 2u * 160 + 15) & ~(size_t)15;
     const size_t smem = perWarp * kFastWarps;
     dim3 grid((oc.totalCells + kFastWarps - 1) / kFastWarps, a.cv.nframes);
     auto go = [&](auto kernel) {

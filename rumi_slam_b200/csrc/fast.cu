@@ -22,7 +22,8 @@
 
 namespace rumi {
 
-constexpr int kFastWarps = 8;
+constexpr int kFastWarps = 4;
+constexpr int kCornerListCap = 512;        // corner list entries per cell; beyond that NMS scans the score tile
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // sign bit of a -> LSB of the running mask (one SHF per ring pixel)
@@ -37,7 +38,7 @@ __device__ __forceinline__ uint32_t push_sign(uint32_t mask, int a) { return __f
 __device__ __forceinline__ int fast_score16_packed(const int d[16]) {
     uint32_t R[8], S[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) R[i] = ((uint32_t)d[2 * i] & 0xFFFFu) | ((uint32_t)d[2 * i + 1] << 16);
+    for (int i = 0; i < 8; ++i) R[i] = __byte_perm((uint32_t)d[2 * i], (uint32_t)d[2 * i + 1], 0x5410);   // (lo16, lo16)
 #pragma unroll
     for (int i = 0; i < 8; ++i) S[i] = __byte_perm(R[i], R[(i + 1) & 7], 0x5432);       // (hi of R[i], lo of R[i+1])
     uint32_t Wn[8], Wx[8];
@@ -82,7 +83,7 @@ __device__ __forceinline__ uint32_t magic_of(uint32_t d) { return d <= 1 ? 0u : 
 __device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
 
 template <int TP>
-__global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_constant__ FastArgs a,
+__global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_constant__ FastArgs a,
                                                                   const __grid_constant__ OrbConst oc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,13 +100,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
     // per-warp shared memory: image tile | score tile | survivor bitmap | corner list | queue
     const int tp = TP ? TP : a.tilePitch, sp = a.scorePitch;     // TP > 0: compile-time pitch -> immediate offsets
     const size_t perWarp = (size_t)tp * a.tileRows + (size_t)sp * a.scoreRows + 4u * a.maskWords +
-                           2u * 32u * a.maskWords + 2u * 160;
+                           2u * kCornerListCap + 2u * 160;
     uint8_t* base = smem + (size_t)warp * ((perWarp + 15) & ~(size_t)15);
     uint8_t* tile = base;
     uint8_t* score = tile + (size_t)tp * a.tileRows;
     uint32_t* kept = reinterpret_cast<uint32_t*>(score + (size_t)sp * a.scoreRows);
     uint16_t* clist = reinterpret_cast<uint16_t*>(kept + a.maskWords);
-    uint16_t* queue = clist + 32 * a.maskWords;
+    uint16_t* queue = clist + kCornerListCap;
 
     // cell geometry (:748-763)
     const int maxBX = g.w - kMinBorder, maxBY = g.h - kMinBorder;
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
     uint8_t* s0 = score + sp + 1;
     const uint32_t magicW = magic_of((uint32_t)dw);
     int qn = 0, ncorner = 0;                            // queue fill, corner-list fill (warp uniform)
+    bool overflow = false;
 
     auto drain = [&](int idq, bool valid) {
         int sc = 0;
@@ -168,7 +170,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
             if (sc > 0) s0[y * sp + x] = (uint8_t)sc;
         }
         const unsigned m = __ballot_sync(kFull, sc > 0);
-        if (sc > 0) clist[ncorner + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idq;
+        if (ncorner + __popc(m) <= kCornerListCap) {
+            if (sc > 0) clist[ncorner + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idq;
+        } else {
+            overflow = true;                             // too many corners for the list: NMS will scan all pixels
+        }
         ncorner += __popc(m);
     };
 
@@ -234,12 +240,22 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
                 pass4 = any & valid;
             }
             const int idx0 = y * dw + 4 * g - c0;                                // detection index of byte 0
+            {   // append the (up to 4) surviving pixels of every lane: popc + shuffle prefix instead of 4 ballots
+                const int c = __popc(pass4);
+                int incl = c;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool pj = (pass4 >> (8 * j + 7)) & 1u;
-                const unsigned m = __ballot_sync(kFull, pj);
-                if (pj) queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(idx0 + j);
-                qn += __popc(m);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                int pos = qn + incl - c;
+                uint32_t t = pass4;
+                while (t) {
+                    const int bit = __ffs(t) - 1;
+                    t &= t - 1;
+                    queue[pos++] = (uint16_t)(idx0 + (bit >> 3));
+                }
+                qn += __shfl_sync(kFull, incl, 31);
             }
             __syncwarp();
             // ---- B. exact score on the compacted survivors, 32 at a time ----
@@ -260,15 +276,16 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
 
     // ---- C. NMS over the corner list ----
     int nIni = 0, nMin = 0;
-    for (int b = 0; b < ncorner; b += 32) {
+    const int nmsCount = overflow ? npx : ncorner;
+    for (int b = 0; b < nmsCount; b += 32) {
         bool k = false;
         int s = 0, idq = 0;
-        if (b + lane < ncorner) {
-            idq = clist[b + lane];
+        if (b + lane < nmsCount) {
+            idq = overflow ? b + lane : (int)clist[b + lane];
             const int y = (int)div_magic((uint32_t)idq, magicW), x = idq - y * dw;
             const uint8_t* q = s0 + y * sp + x;
             s = q[0];
-            k = s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] && s > q[sp - 1] &&
+            k = s > 0 && s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] && s > q[sp - 1] &&
                 s > q[sp] && s > q[sp + 1];
         }
         if (k) atomicOr(&kept[idq >> 5], 1u << (idq & 31));
@@ -324,7 +341,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 4) fast_kernel(const __grid_c
 
 void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s) {
     const size_t perWarp = ((size_t)a.tilePitch * a.tileRows + (size_t)a.scorePitch * a.scoreRows +
-                            4u * a.maskWords + 2u * 32u * a.maskWords + 2u * 160 + 15) & ~(size_t)15;
+                            4u * a.maskWords + 2u * kCornerListCap + 2u * 160 + 15) & ~(size_t)15;
     const size_t smem = perWarp * kFastWarps;
     dim3 grid((oc.totalCells + kFastWarps - 1) / kFastWarps, a.cv.nframes);
     auto go = [&](auto kernel) {

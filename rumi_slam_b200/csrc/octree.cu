@@ -16,7 +16,7 @@ struct BlockCtx {
 };
 
 struct OctreeSmemLayout {
-    size_t keys, lkeys, glo, crlo, crcnt, pend, next, hist, part, scal, cellScan, total;
+    size_t keys, lkeys, glo, crlo, crcnt, pend, next, next2, meta, qbase, hist, part, scal, cellScan, total;
     int nodeCap, createCap, pendCap;
 };
 
@@ -35,9 +35,12 @@ __host__ __device__ inline OctreeSmemLayout octree_layout(int smemKeys, int maxN
     L.crlo = o; o += 4ull * L.createCap;
     L.crcnt = o; o += 4ull * L.createCap;
     L.next = o; o += 4ull * L.pendCap;
+    L.next2 = o; o += 4ull * L.pendCap;
+    L.meta = o; o += 4ull * L.pendCap;
+    L.qbase = o; o += 4ull * L.pendCap;
     L.hist = o; o += 4ull * 2 * (kMaxTreeDepth + 2);
     L.part = o; o += 4ull * (nthreads + 1);
-    L.scal = o; o += 4ull * 8;
+    L.scal = o; o += 4ull * SC_COUNT;
     L.cellScan = o; o += 4ull * (nthreads + 1);
     L.total = (o + 15) & ~(size_t)15;
     return L;
@@ -95,6 +98,9 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
     w.cr_lo = reinterpret_cast<uint32_t*>(smem + L.crlo);
     w.cr_cnt = reinterpret_cast<uint32_t*>(smem + L.crcnt);
     w.next = reinterpret_cast<uint32_t*>(smem + L.next);
+    w.next2 = reinterpret_cast<uint32_t*>(smem + L.next2);
+    w.meta = reinterpret_cast<uint32_t*>(smem + L.meta);
+    w.qbase = reinterpret_cast<uint32_t*>(smem + L.qbase);
     w.hist = reinterpret_cast<int*>(smem + L.hist);
     w.part = reinterpret_cast<int*>(smem + L.part);
     w.scal = reinterpret_cast<int*>(smem + L.scal);

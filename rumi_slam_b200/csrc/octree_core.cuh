@@ -67,14 +67,18 @@ struct OctreeWork {
     uint32_t* cr_lo;       // [createCap] nodes created by the sorted phase (range start)
     uint32_t* cr_cnt;      // [createCap] (count; 0 = erased)
     uint64_t* pend;        // [pendCap] sort elements: (count << 13 | UL.x) << 32 | node ref
-    uint32_t* next;        // [pendCap] node refs for the next round
+    uint32_t* next;        // [pendCap] node refs of the current round
+    uint32_t* next2;       // [pendCap] node refs of the next round
+    uint32_t* meta;        // [pendCap] per pending node: non-empty children | multi-key children << 4
+    uint32_t* qbase;       // [pendCap] per split node (processing order): created base | next base << 16
     int* hist;             // [2 * (kMaxTreeDepth + 2)]
     int* part;             // [nthreads + 1] per-thread partial counts
-    int* scal;             // [8] scalars shared between threads
+    int* scal;             // [SC_COUNT] scalars shared between threads
     int nodeCap, createCap, pendCap;
 };
 
-enum { SC_TSTAR = 0, SC_PHASEB = 1, SC_G = 2, SC_NOUT = 3, SC_NCREATED = 4 };
+enum { SC_TSTAR = 0, SC_PHASEB = 1, SC_G = 2, SC_NOUT = 3, SC_NCREATED = 4, SC_NPEND = 5, SC_SIZE = 6, SC_DEPTH = 7,
+       SC_DONE = 8, SC_J = 9, SC_NEWC = 10, SC_NEWM = 11, SC_COUNT = 12 };
 constexpr uint32_t kRefListBit = 0x80000000u;        // node ref: bit 31 set -> position in the leaf list
 
 // ---- bitonic sort of n (power of two) u64 ascending; all threads of the block participate ----
@@ -351,105 +355,183 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
     ctx.sync();
     bitonic_sort_u64(ctx, w.lkeys, Gpad);
 
-    // 4. sorted final phase (serial: it is defined by a sequential std::sort + early break)
-    if (ctx.tid == 0) {
-        const uint32_t rankMask = (1u << kRankBits) - 1u;
-        int ncreated = 0;
-        if (w.scal[SC_PHASEB]) {
-            int size = G;
-            int npend = 0;
-            // pending = multi-key nodes created in pass t*, in creation order == reverse list order
-            for (int k = G - 1; k >= 0; --k) {
-                const uint32_t r = (uint32_t)w.lkeys[k] & rankMask;
-                const uint32_t cnt = w.glo[r + 1] - w.glo[r];
-                if (cnt > 1) w.next[npend++] = kRefListBit | (uint32_t)k;
+    // 4. sorted final phase.  Only the std::sort replay and the "split from the back until the quota is reached"
+    //    scan are sequential (thread 0); everything around them -- sort keys, child ranges, node creation, list
+    //    assembly -- is data parallel.
+    const uint32_t rankMask = (1u << kRankBits) - 1u;
+    auto node_range = [&](uint32_t ref, uint32_t& lo, uint32_t& cnt) {
+        if (ref & kRefListBit) {
+            const uint32_t r = (uint32_t)w.lkeys[ref & ~kRefListBit] & rankMask;
+            lo = w.glo[r]; cnt = w.glo[r + 1] - lo;
+        } else {
+            lo = w.cr_lo[ref]; cnt = w.cr_cnt[ref];
+        }
+    };
+    if (w.scal[SC_PHASEB]) {
+        // pending = multi-key nodes created in pass t*, in creation order == reverse list order (ordered compaction)
+        {
+            const int chunk = (G + ctx.nthr - 1) / ctx.nthr;
+            const int i0 = ctx.tid * chunk < G ? ctx.tid * chunk : G, i1 = (i0 + chunk < G) ? i0 + chunk : G;
+            int c = 0;
+            for (int i = i0; i < i1; ++i) {                     // i counts from the BACK of the list
+                const uint32_t r = (uint32_t)w.lkeys[G - 1 - i] & rankMask;
+                c += (w.glo[r + 1] - w.glo[r]) > 1;
             }
-            int depth = tstar;                       // depth of the pending nodes
-            bool done = false;
-            while (!done) {
-                const int prev = size;
-                for (int p = 0; p < npend; ++p) {
-                    const uint32_t ref = w.next[p];
-                    uint32_t lo, cnt;
-                    if (ref & kRefListBit) {
-                        const uint32_t r = (uint32_t)w.lkeys[ref & ~kRefListBit] & rankMask;
-                        lo = w.glo[r]; cnt = w.glo[r + 1] - lo;
-                    } else {
-                        lo = w.cr_lo[ref]; cnt = w.cr_cnt[ref];
-                    }
-                    const uint32_t prefix = key_code(w.keys[lo]) >> (2 * (D - depth));
-                    const uint32_t ulx = (uint32_t)tree_node_ulx(prefix, depth, g.hX);
-                    w.pend[p] = ((uint64_t)((cnt << 13) | ulx) << 32) | (uint64_t)ref;
+            w.part[ctx.tid] = c;
+            ctx.sync();
+            if (ctx.tid == 0) {
+                int sum = 0;
+                for (int t = 0; t < ctx.nthr; ++t) { const int v = w.part[t]; w.part[t] = sum; sum += v; }
+                w.scal[SC_NPEND] = sum;
+                w.scal[SC_SIZE] = G;
+                w.scal[SC_DEPTH] = tstar;
+                w.scal[SC_DONE] = 0;
+            }
+            ctx.sync();
+            int pos = w.part[ctx.tid];
+            for (int i = i0; i < i1; ++i) {
+                const int k = G - 1 - i;
+                const uint32_t r = (uint32_t)w.lkeys[k] & rankMask;
+                if ((w.glo[r + 1] - w.glo[r]) > 1) w.next[pos++] = kRefListBit | (uint32_t)k;
+            }
+            ctx.sync();
+        }
+        uint32_t* cur = w.next;
+        uint32_t* nxt = w.next2;
+        while (true) {
+            const int npend = w.scal[SC_NPEND];
+            const int depth = w.scal[SC_DEPTH];
+            const int shift = 2 * (D - depth - 1);
+            // (R1) sort key (count, UL.x) and number of non-empty / multi-key children of every pending node
+            for (int p = ctx.tid; p < npend; p += ctx.nthr) {
+                uint32_t lo, cnt;
+                node_range(cur[p], lo, cnt);
+                const uint32_t prefix = key_code(w.keys[lo]) >> (2 * (D - depth));
+                const uint32_t ulx = (uint32_t)tree_node_ulx(prefix, depth, g.hX);
+                w.pend[p] = ((uint64_t)((cnt << 13) | ulx) << 32) | (uint64_t)p;
+                uint32_t b[5];
+                b[0] = lo; b[4] = lo + cnt;
+                if (depth + 1 <= D) {
+                    b[1] = child_start(w.keys, lo, cnt, shift, 1);
+                    b[2] = child_start(w.keys, lo, cnt, shift, 2);
+                    b[3] = child_start(w.keys, lo, cnt, shift, 3);
+                } else {
+                    b[1] = b[2] = b[3] = lo + cnt;
                 }
+                uint32_t ne = 0, nm = 0;
+                for (int q = 0; q < 4; ++q) { const uint32_t cc = b[q + 1] - b[q]; ne += cc > 0; nm += cc > 1; }
+                w.meta[p] = ne | (nm << 4);
+            }
+            ctx.sync();
+            // (R2, R3) sequential: libstdc++ std::sort replay, then split from the back until size >= N
+            if (ctx.tid == 0) {
                 stdsort::sort(w.pend, npend);
-                int nnext = 0;
-                const int shift = 2 * (D - depth - 1);
+                int size = w.scal[SC_SIZE];
+                const int prev = size;
+                uint32_t cc = 0, mc = 0;
+                int J = 0;
                 for (int j = npend - 1; j >= 0; --j) {
-                    const uint32_t ref = (uint32_t)w.pend[j];
-                    uint32_t lo, cnt;
-                    if (ref & kRefListBit) {
-                        const uint32_t k = ref & ~kRefListBit;
-                        const uint32_t r = (uint32_t)w.lkeys[k] & rankMask;
-                        lo = w.glo[r]; cnt = w.glo[r + 1] - lo;
-                        w.lkeys[k] |= 1ull << 63;                     // erased from the list
-                    } else {
-                        lo = w.cr_lo[ref]; cnt = w.cr_cnt[ref];
-                        w.cr_cnt[ref] = 0;                            // erased
-                    }
-                    uint32_t b[5];
-                    b[0] = lo; b[4] = lo + cnt;
-                    if (depth + 1 <= D) {
-                        b[1] = child_start(w.keys, lo, cnt, shift, 1);
-                        b[2] = child_start(w.keys, lo, cnt, shift, 2);
-                        b[3] = child_start(w.keys, lo, cnt, shift, 3);
-                    } else {
-                        b[1] = b[2] = b[3] = lo + cnt;                // cannot happen for distinct pixels
-                    }
-                    int nonempty = 0;
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t cc = b[q + 1] - b[q];
-                        if (cc == 0) continue;
-                        ++nonempty;
-                        w.cr_lo[ncreated] = b[q];
-                        w.cr_cnt[ncreated] = cc;
-                        if (cc > 1) w.next[nnext++] = (uint32_t)ncreated;
-                        ++ncreated;
-                    }
-                    size += nonempty - 1;
+                    const uint32_t m = w.meta[(uint32_t)w.pend[j]];
+                    w.qbase[J++] = cc | (mc << 16);
+                    cc += m & 15u; mc += m >> 4;
+                    size += (int)(m & 15u) - 1;
                     if (size >= N) break;
                 }
-                if (size >= N || size == prev) done = true;
-                npend = nnext;
-                ++depth;
-                if (!done) {
-                    // drop erased entries so the tables stay within (quota + 3) live + one round of children
+                w.scal[SC_J] = J;
+                w.scal[SC_SIZE] = size;
+                w.scal[SC_NEWC] = (int)cc;
+                w.scal[SC_NEWM] = (int)mc;
+                w.scal[SC_DONE] = (size >= N || size == prev) ? 1 : 0;
+            }
+            ctx.sync();
+            // (R4) create the children of the J split nodes (processing order = from the back of the sorted array)
+            const int J = w.scal[SC_J];
+            const int cbase0 = w.scal[SC_NCREATED];
+            for (int q = ctx.tid; q < J; q += ctx.nthr) {
+                const uint32_t p = (uint32_t)w.pend[npend - 1 - q];
+                const uint32_t ref = cur[p];
+                uint32_t lo, cnt;
+                node_range(ref, lo, cnt);
+                if (ref & kRefListBit) w.lkeys[ref & ~kRefListBit] |= 1ull << 63;     // erased from the list
+                else w.cr_cnt[ref] = 0;
+                uint32_t b[5];
+                b[0] = lo; b[4] = lo + cnt;
+                if (depth + 1 <= D) {
+                    b[1] = child_start(w.keys, lo, cnt, shift, 1);
+                    b[2] = child_start(w.keys, lo, cnt, shift, 2);
+                    b[3] = child_start(w.keys, lo, cnt, shift, 3);
+                } else {
+                    b[1] = b[2] = b[3] = lo + cnt;
+                }
+                uint32_t ci = (uint32_t)cbase0 + (w.qbase[q] & 0xFFFFu), mi = w.qbase[q] >> 16;
+                for (int qd = 0; qd < 4; ++qd) {
+                    const uint32_t c2 = b[qd + 1] - b[qd];
+                    if (c2 == 0) continue;
+                    w.cr_lo[ci] = b[qd];
+                    w.cr_cnt[ci] = c2;
+                    if (c2 > 1) nxt[mi++] = ci;
+                    ++ci;
+                }
+            }
+            ctx.sync();
+            if (ctx.tid == 0) {
+                int ncreated = cbase0 + w.scal[SC_NEWC];
+                int nnext = w.scal[SC_NEWM];
+                if (!w.scal[SC_DONE] && ncreated + 2 * (w.nodeCap + 4) > w.createCap) {
+                    // rare: drop erased entries so one more round of children fits (keeps creation order)
                     int wpos = 0, pn = 0;
                     for (int c = 0; c < ncreated; ++c) {
                         if (w.cr_cnt[c] == 0) continue;
-                        if (pn < npend && w.next[pn] == (uint32_t)c) w.next[pn++] = (uint32_t)wpos;
+                        if (pn < nnext && nxt[pn] == (uint32_t)c) nxt[pn++] = (uint32_t)wpos;
                         w.cr_lo[wpos] = w.cr_lo[c];
                         w.cr_cnt[wpos] = w.cr_cnt[c];
                         ++wpos;
                     }
                     ncreated = wpos;
                 }
+                w.scal[SC_NCREATED] = ncreated;
+                w.scal[SC_NPEND] = nnext;
+                w.scal[SC_DEPTH] = depth + 1;
             }
+            ctx.sync();
+            if (w.scal[SC_DONE]) break;
+            uint32_t* tmp = cur; cur = nxt; nxt = tmp;
         }
-        w.scal[SC_NCREATED] = ncreated;
-        // final list: nodes created by the sorted phase, newest first, then the surviving pass-t* list
-        int n = 0;
-        for (int c = ncreated - 1; c >= 0; --c) {
-            if (w.cr_cnt[c] == 0) continue;
-            // reuse pend[] as the output leaf table: lo << 32 | cnt
-            w.pend[n++] = ((uint64_t)w.cr_lo[c] << 32) | (uint64_t)w.cr_cnt[c];
-        }
-        for (int k = 0; k < G; ++k) {
-            const uint64_t lk = w.lkeys[k];
-            if (lk >> 63) continue;
+    }
+    // final list: nodes created by the sorted phase, newest first, then the surviving pass-t* list (two ordered
+    // compactions into pend[] as lo << 32 | cnt)
+    {
+        const int ncreated = w.scal[SC_NCREATED];
+        const int total = ncreated + G;
+        const int chunk = (total + ctx.nthr - 1) / ctx.nthr;
+        const int i0 = ctx.tid * chunk < total ? ctx.tid * chunk : total, i1 = (i0 + chunk < total) ? i0 + chunk : total;
+        auto leaf = [&](int i, uint64_t& out) {          // i-th element of [created reversed | list]; false = erased
+            if (i < ncreated) {
+                const int c = ncreated - 1 - i;
+                if (w.cr_cnt[c] == 0) return false;
+                out = ((uint64_t)w.cr_lo[c] << 32) | (uint64_t)w.cr_cnt[c];
+                return true;
+            }
+            const uint64_t lk = w.lkeys[i - ncreated];
+            if (lk >> 63) return false;
             const uint32_t r = (uint32_t)lk & rankMask;
-            w.pend[n++] = ((uint64_t)w.glo[r] << 32) | (uint64_t)(w.glo[r + 1] - w.glo[r]);
+            out = ((uint64_t)w.glo[r] << 32) | (uint64_t)(w.glo[r + 1] - w.glo[r]);
+            return true;
+        };
+        int c = 0;
+        uint64_t v;
+        for (int i = i0; i < i1; ++i) c += leaf(i, v) ? 1 : 0;
+        w.part[ctx.tid] = c;
+        ctx.sync();
+        if (ctx.tid == 0) {
+            int sum = 0;
+            for (int t = 0; t < ctx.nthr; ++t) { const int x = w.part[t]; w.part[t] = sum; sum += x; }
+            w.scal[SC_NOUT] = sum;
         }
-        w.scal[SC_NOUT] = n;
+        ctx.sync();
+        int pos = w.part[ctx.tid];
+        for (int i = i0; i < i1; ++i)
+            if (leaf(i, v)) w.pend[pos++] = v;
     }
     ctx.sync();
 

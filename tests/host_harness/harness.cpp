@@ -69,10 +69,10 @@ int hh_octree(int W, int H, int nfeatures, float scale, int nlevels, int level, 
     const int nodeCap = std::max(N, 4 * g.nIni) + 4;
     w.nodeCap = nodeCap; w.createCap = 3 * nodeCap + 16; w.pendCap = 2 * nodeCap + 16;
     std::vector<uint64_t> keys(next_pow2(std::max(M, 2))), lkeys(next_pow2(nodeCap)), pend(w.pendCap);
-    std::vector<uint32_t> glo(nodeCap + 1), crlo(w.createCap), crcnt(w.createCap), next(w.pendCap);
-    std::vector<int> hist(2 * (kMaxTreeDepth + 2)), part(2), scal(8);
+    std::vector<uint32_t> glo(nodeCap + 1), crlo(w.createCap), crcnt(w.createCap), next(w.pendCap), next2(w.pendCap), meta(w.pendCap), qbase(w.pendCap);
+    std::vector<int> hist(2 * (kMaxTreeDepth + 2)), part(2), scal(SC_COUNT);
     w.keys = keys.data(); w.lkeys = lkeys.data(); w.glo = glo.data(); w.cr_lo = crlo.data(); w.cr_cnt = crcnt.data();
-    w.pend = pend.data(); w.next = next.data(); w.hist = hist.data(); w.part = part.data(); w.scal = scal.data();
+    w.pend = pend.data(); w.next = next.data(); w.next2 = next2.data(); w.meta = meta.data(); w.qbase = qbase.data(); w.hist = hist.data(); w.part = part.data(); w.scal = scal.data();
     HostCtx ctx;
     distribute_quadtree(ctx, cand, M, N, g, w, out, outCap);
     return scal[SC_NOUT];

@@ -338,7 +338,10 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
 int upload_level0(rumi_orb* h, Workspace& w, const uint8_t* imgs, int n, size_t stride, size_t framePitch) {
     const LevelGeom& g = h->oc.lv[0];
     uint8_t* dst = w.pyr + h->pyrLevelOff[0];
-    if (framePitch == stride * (size_t)g.h || n == 1) {
+    if ((framePitch == stride * (size_t)g.h || n == 1) && stride == (size_t)g.stride) {
+        // rows are contiguous on both sides: one linear copy (a 2-D copy pays per-row DMA descriptors)
+        CU_TRY(cudaMemcpyAsync(dst, imgs, (size_t)n * g.h * g.stride, cudaMemcpyHostToDevice, w.stream));
+    } else if (framePitch == stride * (size_t)g.h || n == 1) {
         CU_TRY(cudaMemcpy2DAsync(dst, g.stride, imgs, stride, g.w, (size_t)n * g.h, cudaMemcpyHostToDevice, w.stream));
     } else {
         for (int i = 0; i < n; ++i)
@@ -443,11 +446,18 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
         const LevelView l0 = internal_view(h, ws.pyr, 0);
         if ((rc = run_chunk(h, ws, l0, true, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
         // results: dense [m][kpCap] blocks -> caller's [n][cap_per_frame] layout
-        CU_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap_per_frame, sizeof(rumi_kp) * (size_t)cap_per_frame, ws.kps,
-                                 sizeof(rumi_kp) * (size_t)oc.kpCap, sizeof(rumi_kp) * (size_t)oc.kpCap, m,
-                                 cudaMemcpyDeviceToHost, ws.stream));
-        CU_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap_per_frame * 32, 32 * (size_t)cap_per_frame, ws.desc,
-                                 32 * (size_t)oc.kpCap, 32 * (size_t)oc.kpCap, m, cudaMemcpyDeviceToHost, ws.stream));
+        if (cap_per_frame == oc.kpCap) {
+            CU_TRY(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ws.kps, sizeof(rumi_kp) * (size_t)oc.kpCap * m,
+                                   cudaMemcpyDeviceToHost, ws.stream));
+            CU_TRY(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ws.desc, 32 * (size_t)oc.kpCap * m,
+                                   cudaMemcpyDeviceToHost, ws.stream));
+        } else {
+            CU_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap_per_frame, sizeof(rumi_kp) * (size_t)cap_per_frame, ws.kps,
+                                     sizeof(rumi_kp) * (size_t)oc.kpCap, sizeof(rumi_kp) * (size_t)oc.kpCap, m,
+                                     cudaMemcpyDeviceToHost, ws.stream));
+            CU_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap_per_frame * 32, 32 * (size_t)cap_per_frame, ws.desc,
+                                     32 * (size_t)oc.kpCap, 32 * (size_t)oc.kpCap, m, cudaMemcpyDeviceToHost, ws.stream));
+        }
         CU_TRY(cudaMemcpyAsync(n_kp + f0, ws.nkp, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
         CU_TRY(cudaMemcpyAsync(n_mono + f0, ws.nmono, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
         h->lastWs = wi;

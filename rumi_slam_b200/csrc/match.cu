@@ -15,30 +15,57 @@
 namespace rumi {
 
 constexpr int kMatchThreads = 128;
-constexpr int kQPT = 2;                       // queries per thread
+constexpr int kQPT = 4;                       // queries per thread
 constexpr int kTileRows = 256;                // train descriptors per shared-memory tile (8 KB)
+constexpr int kIdxBits = 21;                  // local train index inside one slice (slice <= 2^21 rows)
 
-// popcount of the 256-bit XOR of two descriptors held as 8 words each
-__device__ __forceinline__ int hamming256(const uint32_t q[8], const uint4 t0, const uint4 t1) {
-    const uint32_t x0 = q[0] ^ t0.x, x1 = q[1] ^ t0.y, x2 = q[2] ^ t0.z, x3 = q[3] ^ t0.w;
-    const uint32_t x4 = q[4] ^ t1.x, x5 = q[5] ^ t1.y, x6 = q[6] ^ t1.z, x7 = q[7] ^ t1.w;
-    // carry-save adders: (a,b,c) -> sum = a^b^c, carry = maj(a,b,c); both are single LOP3s
-    const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 | x1));
-    const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 | x4));
-    const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
-    // ones: s3, x7 ; twos: c1, c2, c3
-    return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+// Multiply-add that stays an IMAD (FMA pipe): the multiplier is a run-time value (blockDim.z == 1, which ptxas
+// cannot fold), so these additions do not compete with XOR / LOP3 / min-max for the ALU pipe, which ncu showed
+// at 88 % utilisation when they were plain IADD3s.
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
-struct Top2 { int b1, b2, i1; };
+// popcount of the 256-bit XOR of two descriptors held as 8 words each
+__device__ __forceinline__ uint32_t hamming256(const uint32_t q[8], const uint4 t0, const uint4 t1, uint32_t one,
+                                               uint32_t two) {
+    // The XOR words are materialised through opaque asm so that ptxas keeps the 8 XOR + 6 LOP3 form (14 ALU ops per
+    // pair); left to itself it re-associates the tree over (q, t) directly and spends 20 LOP3 per pair.
+    uint32_t x0, x1, x2, x3, x4, x5, x6, x7;
+    asm("xor.b32 %0, %1, %2;" : "=r"(x0) : "r"(q[0]), "r"(t0.x));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x1) : "r"(q[1]), "r"(t0.y));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x2) : "r"(q[2]), "r"(t0.z));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x3) : "r"(q[3]), "r"(t0.w));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x4) : "r"(q[4]), "r"(t1.x));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x5) : "r"(q[5]), "r"(t1.y));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x6) : "r"(q[6]), "r"(t1.z));
+    asm("xor.b32 %0, %1, %2;" : "=r"(x7) : "r"(q[7]), "r"(t1.w));
+    // carry-save adders: (a,b,c) -> sum = a^b^c (LOP3 0x96), carry = majority(a,b,c) (LOP3 0xE8)
+    uint32_t s1, c1, s2, c2, s3, c3;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s1) : "r"(x0), "r"(x1), "r"(x2));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c1) : "r"(x0), "r"(x1), "r"(x2));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s2) : "r"(x3), "r"(x4), "r"(x5));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c2) : "r"(x3), "r"(x4), "r"(x5));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s3) : "r"(s1), "r"(s2), "r"(x6));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c3) : "r"(s1), "r"(s2), "r"(x6));
+    // ones: s3, x7 ; twos: c1, c2, c3.  The additions run as IMADs (FMA pipe).
+    const uint32_t ones = imad((uint32_t)__popc(s3), one, (uint32_t)__popc(x7));
+    const uint32_t twos = imad((uint32_t)__popc(c1), one, imad((uint32_t)__popc(c2), one, (uint32_t)__popc(c3)));
+    return imad(twos, two, ones);
+}
 
+// Per query the running best is kept as ONE key (distance << 21 | local train index): a single min keeps the
+// smallest distance and, among equal distances, the earliest index; the second-best distance is
+// min(b2, max(key, previous best)) in the same key domain.  Keys start at 256 << 21 (the reference's initial 256).
 __global__ void __launch_bounds__(kMatchThreads)
 hamming_top2_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ T, int nt, int sliceRows,
                     int tBase, uint64_t* __restrict__ partial /* [gridDim.y][nq] */) {
     __shared__ uint4 tile[kTileRows * 2];
     const int q0 = blockIdx.x * (kMatchThreads * kQPT) + threadIdx.x;
     uint32_t q[kQPT][8];
-    Top2 best[kQPT];
+    uint32_t k1[kQPT], k2[kQPT];
 #pragma unroll
     for (int k = 0; k < kQPT; ++k) {
         const int qi = q0 + k * kMatchThreads;
@@ -46,8 +73,9 @@ hamming_top2_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __rest
         const uint4 a = src[0], b = src[1];
         q[k][0] = a.x; q[k][1] = a.y; q[k][2] = a.z; q[k][3] = a.w;
         q[k][4] = b.x; q[k][5] = b.y; q[k][6] = b.z; q[k][7] = b.w;
-        best[k].b1 = 256; best[k].b2 = 256; best[k].i1 = -1;
+        k1[k] = k2[k] = 256u << kIdxBits;
     }
+    const uint32_t one = blockDim.z, two = one + one, keyMul = one << kIdxBits;     // run-time constants (see imad)
     const int t0 = blockIdx.y * sliceRows, t1 = min(t0 + sliceRows, nt);
     for (int base = t0; base < t1; base += kTileRows) {
         const int rows = min(kTileRows, t1 - base);
@@ -55,14 +83,15 @@ hamming_top2_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __rest
         for (int i = threadIdx.x; i < rows * 2; i += kMatchThreads)
             tile[i] = reinterpret_cast<const uint4*>(T)[(size_t)base * 2 + i];
         __syncthreads();
-#pragma unroll 4
+        const uint32_t local = (uint32_t)(base - t0);
+#pragma unroll 2
         for (int r = 0; r < rows; ++r) {
             const uint4 a = tile[2 * r], b = tile[2 * r + 1];
 #pragma unroll
             for (int k = 0; k < kQPT; ++k) {
-                const int d = hamming256(q[k], a, b);
-                if (d < best[k].b1) { best[k].b2 = best[k].b1; best[k].b1 = d; best[k].i1 = base + r; }
-                else if (d < best[k].b2) best[k].b2 = d;
+                const uint32_t key = imad(hamming256(q[k], a, b, one, two), keyMul, local + (uint32_t)r);
+                k2[k] = min(k2[k], max(key, k1[k]));
+                k1[k] = min(k1[k], key);
             }
         }
     }
@@ -70,9 +99,10 @@ hamming_top2_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __rest
     for (int k = 0; k < kQPT; ++k) {
         const int qi = q0 + k * kMatchThreads;
         if (qi < nq) {
-            const uint32_t idx = best[k].i1 < 0 ? 0xFFFFFFFFu : (uint32_t)(best[k].i1 + tBase);
-            partial[(size_t)blockIdx.y * nq + qi] =
-                ((uint64_t)best[k].b1 << 48) | ((uint64_t)best[k].b2 << 32) | (uint64_t)idx;
+            const uint32_t d1 = k1[k] >> kIdxBits, d2 = k2[k] >> kIdxBits;
+            const uint32_t idx = d1 >= 256u ? 0xFFFFFFFFu
+                                            : (uint32_t)(t0 + tBase) + (k1[k] & ((1u << kIdxBits) - 1u));
+            partial[(size_t)blockIdx.y * nq + qi] = ((uint64_t)d1 << 48) | ((uint64_t)d2 << 32) | (uint64_t)idx;
         }
     }
 }
@@ -111,6 +141,8 @@ int match_slices(int nq, int nt) {
     if (want < 1) want = 1;
     if (want > maxSlices) want = maxSlices;
     if (want > 64) want = 64;
+    const int need = (int)(((long long)nt + (1 << kIdxBits) - 1) >> kIdxBits);   // local index must fit kIdxBits
+    if (want < need) want = need;
     return want;
 }
 

@@ -228,6 +228,18 @@ def run_b200(args):
     ms_e2e = max_over_ranks(ms_e2e)
     launches_e2e = ex.launch_count(reset=True)
     e2e_value = world * nframes * args.steps / (ms_e2e / 1e3)
+    # raw host->device bandwidth of the same pinned buffer (context for e2e: 307 200 B per frame must cross PCIe)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = torch.empty_like(resident)
+    scratch.copy_(pinned, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        scratch.copy_(pinned, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * pinned.numel() / (ev0.elapsed_time(ev1) / 1e3) / 1e9
+    del scratch
     h2d = nframes * W_IMG * H_IMG
     d2h = nframes * cap * (28 + 32) + 8 * nframes
 
@@ -255,7 +267,6 @@ def run_b200(args):
     barrier()
     msteps = max(args.steps, 10)
     t_a = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     m.timer_start()
     for _ in range(msteps):
         match_once()
@@ -306,9 +317,9 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0))
-        sample = max(4 * cores, 32)
+        sample = max(40 * cores, 64)
         rate, kind, dt = cpu_extract_rate(host[:sample], cores)
-        rate1, _, dt1 = cpu_extract_rate(host[:8], 1)
+        rate1, _, dt1 = cpu_extract_rate(host[:48], 1)
         cpu = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
                "sample": "%d of the same synthetic frames on %d host threads (%.1f s); 1 thread: %.1f frames/s"
                          % (sample, cores, dt, rate1),
@@ -322,14 +333,20 @@ def run_b200(args):
                        "frames_per_gpu": nframes, "chunk_frames": chunk, "mean_keypoints_per_frame": nkp_mean,
                        "l2": "inputs (315 MB per GPU) exceed the 126 MB L2, no flush between steps"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_GBps_raw": round(h2d_gbps, 2),
+                    "frames_per_s_at_raw_h2d": round(world * h2d_gbps * 1e9 / (W_IMG * H_IMG), 1)},
             "gpu_launches": launches,
             "gpu_launches_e2e": launches_e2e,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "matching": {"workload": "cfg 5a: 40000 x 40000 descriptors all-pairs top-2, train set sharded over %d GPU(s)" % world,
                          "matches_per_s": matches_per_s, "pairs_per_s": pairs_per_s, "ms_per_step": ms_match / msteps,
-                         "gpu_launches": match_launches, "steps": msteps},
+                         "gpu_launches": match_launches, "steps": msteps,
+                         "roofline": {"bound": "popc-pipe", "popc_per_pair": 5, "popc_per_clk_per_sm": 16,
+                                      "peak_pairs_per_s": world * 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 5,
+                                      "frac": pairs_per_s / (world * 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 5),
+                                      "note": "POPC rate measured 15.8/clk/SM (tools/probe/pipe_probe.cu); "
+                                              "5 POPC + 14 LOP3 per pair"}},
             "clocks": clocks}
     print(json.dumps(line))
     if world > 1:

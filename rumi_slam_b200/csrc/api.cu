@@ -89,6 +89,8 @@ struct Workspace {
 
 }  // namespace
 
+constexpr int kMaxWs = 4;
+
 struct rumi_orb {
     int device = 0;
     int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0, chunk = 1;
@@ -106,12 +108,13 @@ struct rumi_orb {
     long long pyrBytes = 0, candElems = 0, bigKeysElems = 0;
     int fastTilePitch = 0, fastTileRows = 0, fastScorePitch = 0, fastScoreRows = 0, fastMaskWords = 0;
     int smemKeys = 4096, maxNodeCap = 0;
-    Workspace ws[2];
+    Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
+    int nws = 4;
     int lastWs = 0;
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     int dbgCell = 0;
     // measurement: device-side timer on the launching streams, optional per-stage events, launch counter
-    cudaEvent_t evStart = nullptr, evStop = nullptr, evJoin = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evJoin[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};
     bool profile = false;
     std::vector<cudaEvent_t> evPool;
     size_t evUsed = 0;
@@ -177,7 +180,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
     OrbConst oc;
     const int rc = build_orb_const(oc, W, H, h->nfeatures, h->scaleFactor, h->nlevels, h->iniTh, h->minTh);
     if (rc) return fail(RUMI_ERR_SHAPE, "image %dx%d cannot be processed with %d levels (code %d)", W, H, h->nlevels, rc);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxWs; ++i) {
         if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
         free_workspace(h->ws[i]);
     }
@@ -250,7 +253,8 @@ int ensure_workspace(rumi_orb* h, int idx) {
     return alloc_workspace(h, w);
 }
 
-enum { ST_PYRAMID = 0, ST_FAST = 1, ST_OCTREE = 2, ST_SLOTS = 3, ST_BLUR = 4, ST_DESCRIBE = 5, ST_COUNT = 6 };
+enum { ST_PYRAMID = 0, ST_FAST = 1, ST_OCTREE = 2, ST_SLOTS = 3, ST_BLUR = 4, ST_DESCRIBE = 5, ST_H2D = 6, ST_D2H = 7,
+       ST_COUNT = 8 };
 
 cudaEvent_t prof_event(rumi_orb* h, cudaStream_t s) {
     if (h->evUsed == h->evPool.size()) {
@@ -380,6 +384,8 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     h->tables = make_scale_tables(nfeatures, scale_factor, nlevels);
     const char* e = getenv("RUMI_NO_TMA");
     h->useTMA = !(e && e[0] == '1');
+    const char* ns = getenv("RUMI_STREAMS");
+    if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) h->nws = ns[0] - '0';
     *out = h;
     return RUMI_OK;
 }
@@ -387,7 +393,7 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
 void rumi_orb_destroy(rumi_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxWs; ++i) {
         if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
         free_workspace(h->ws[i]);
         if (h->ws[i].stream) cudaStreamDestroy(h->ws[i].stream);
@@ -397,7 +403,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->evStart) cudaEventDestroy(h->evStart);
     if (h->evStop) cudaEventDestroy(h->evStop);
-    if (h->evJoin) cudaEventDestroy(h->evJoin);
+    for (int i = 0; i < kMaxWs; ++i) if (h->evJoin[i]) cudaEventDestroy(h->evJoin[i]);
     delete h;
 }
 
@@ -437,12 +443,14 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
         return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, oc.kpCap);
     const int nchunks = (n + h->chunk - 1) / h->chunk;
     for (int c = 0; c < nchunks; ++c) {
-        const int wi = c & 1;
+        const int wi = c % h->nws;
         if ((rc = ensure_workspace(h, wi))) return rc;
         Workspace& ws = h->ws[wi];
         const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);
         // stream order makes the reuse of workspace `wi` (two chunks ago) safe
+        if (h->profile) prof_event(h, ws.stream);
         if ((rc = upload_level0(h, ws, imgs + (size_t)f0 * frame_pitch, m, stride, frame_pitch))) return rc;
+        if (h->profile) { h->launches -= 0; h->evSpans.push_back(std::make_pair((int)ST_H2D, (int)h->evUsed - 1)); prof_event(h, ws.stream); }
         const LevelView l0 = internal_view(h, ws.pyr, 0);
         if ((rc = run_chunk(h, ws, l0, true, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
         // results: dense [m][kpCap] blocks -> caller's [n][cap_per_frame] layout
@@ -460,9 +468,10 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
         }
         CU_TRY(cudaMemcpyAsync(n_kp + f0, ws.nkp, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
         CU_TRY(cudaMemcpyAsync(n_mono + f0, ws.nmono, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
+        if (h->profile) { h->evSpans.push_back(std::make_pair((int)ST_D2H, (int)h->evUsed - 1)); prof_event(h, ws.stream); }
         h->lastWs = wi;
     }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kMaxWs; ++i)
         if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
     return RUMI_OK;
 }
@@ -510,7 +519,7 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
         return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, h->oc.kpCap);
     const int nchunks = (n + h->chunk - 1) / h->chunk;
     for (int c = 0; c < nchunks; ++c) {
-        const int wi = c & 1;
+        const int wi = c % h->nws;
         if ((rc = ensure_workspace(h, wi))) return rc;
         Workspace& ws = h->ws[wi];
         const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);
@@ -523,7 +532,7 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
         h->lastWs = wi;
     }
     if (sync)
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < kMaxWs; ++i)
             if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
     return RUMI_OK;
 }
@@ -603,21 +612,24 @@ static int debug_list(rumi_orb* h, int level, int32_t* xyr, int cap, bool select
 int rumi_orb_timer_start(rumi_orb* h) {
     if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
     CU_TRY(cudaSetDevice(h->device));
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kMaxWs; ++i)
         if (!h->ws[i].stream) CU_TRY(cudaStreamCreateWithFlags(&h->ws[i].stream, cudaStreamNonBlocking));
     if (!h->evStart) {
-        CU_TRY(cudaEventCreate(&h->evStart)); CU_TRY(cudaEventCreate(&h->evStop)); CU_TRY(cudaEventCreate(&h->evJoin));
+        CU_TRY(cudaEventCreate(&h->evStart)); CU_TRY(cudaEventCreate(&h->evStop));
+        for (int i = 0; i < kMaxWs; ++i) CU_TRY(cudaEventCreate(&h->evJoin[i]));
     }
     CU_TRY(cudaEventRecord(h->evStart, h->ws[0].stream));
-    CU_TRY(cudaStreamWaitEvent(h->ws[1].stream, h->evStart, 0));
+    for (int i = 1; i < kMaxWs; ++i) CU_TRY(cudaStreamWaitEvent(h->ws[i].stream, h->evStart, 0));
     return RUMI_OK;
 }
 
 int rumi_orb_timer_stop(rumi_orb* h, float* ms) {
     if (!h || !h->evStart || !ms) return fail(RUMI_ERR_ARG, "timer not started");
     CU_TRY(cudaSetDevice(h->device));
-    CU_TRY(cudaEventRecord(h->evJoin, h->ws[1].stream));
-    CU_TRY(cudaStreamWaitEvent(h->ws[0].stream, h->evJoin, 0));
+    for (int i = 1; i < kMaxWs; ++i) {
+        CU_TRY(cudaEventRecord(h->evJoin[i], h->ws[i].stream));
+        CU_TRY(cudaStreamWaitEvent(h->ws[0].stream, h->evJoin[i], 0));
+    }
     CU_TRY(cudaEventRecord(h->evStop, h->ws[0].stream));
     CU_TRY(cudaEventSynchronize(h->evStop));
     CU_TRY(cudaEventElapsedTime(ms, h->evStart, h->evStop));
@@ -633,7 +645,7 @@ int rumi_orb_profile(rumi_orb* h, int enable) {
 int rumi_orb_profile_read(rumi_orb* h, double* stage_ms, long long* stage_launches, int reset) {
     if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
     CU_TRY(cudaSetDevice(h->device));
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kMaxWs; ++i)
         if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
     for (const auto& sp : h->evSpans) {
         float ms = 0.f;

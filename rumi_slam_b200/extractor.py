@@ -151,7 +151,7 @@ class ORBextractor:
         return [self._level(self._L.rumi_orb_blurred_level, l) for l in range(self.nlevels)]
 
     # ---- measurement hooks (bench.py) ----
-    STAGES = ("pyramid", "fast", "octree", "slots", "blur", "describe")
+    STAGES = ("pyramid", "fast", "octree", "slots", "blur", "describe", "h2d", "d2h")
 
     def timer_start(self):
         check(self._L.rumi_orb_timer_start(self._h))

@@ -134,6 +134,15 @@ int rumi_stereo_best1(rumi_match* m, const rumi_kp* Lk, const uint8_t* Ld, int n
                       const uint8_t* Rd, int nR, const float* scale_factors, int nlevels, int n_rows, float min_d,
                       float max_d, int32_t* best_r, uint16_t* best_dist);
 
+/* Frame::ComputeStereoMatches, complete (R/lib_src/Frame.cc:828-985): rumi_stereo_best1, then the 11x11 SAD slide of
+ * +-5 px on the pyramids of the two extractors (the pyramids of their LAST rumi_orb_extract call are used where they
+ * are, in device memory), the parabola sub-pixel fit, disparity / depth, and the median outlier cut.
+ * u_right / depth == mvuRight / mvDepth (-1 where no stereo match).  mbf = baseline * fx, mb = baseline.
+ * HOST pointers; *n_matched = number of stereo matches kept. */
+int rumi_stereo_match(rumi_match* m, rumi_orb* left, rumi_orb* right, const rumi_kp* Lk, const uint8_t* Ld, int nL,
+                      const rumi_kp* Rk, const uint8_t* Rd, int nR, float mbf, float mb, float* u_right, float* depth,
+                      int* n_matched);
+
 /* ORBmatcher::DescriptorDistance for one pair (host inline popcount; the API, not a fallback). */
 int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b);
 

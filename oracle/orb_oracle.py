@@ -65,6 +65,8 @@ def lib():
         L.orc_stereo_best1.argtypes = [C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int, f32p, C.c_int,
                                        C.c_float, C.c_float, i32p, u16p]
         L.orc_stereo_best1.restype = None
+        L.orc_stereo_match.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_int, C.c_void_p, u8p, C.c_int,
+                                       C.c_void_p, u8p, C.c_int, C.c_float, C.c_float, f32p, f32p]
         _lib = L
     return _lib
 
@@ -237,3 +239,18 @@ def stereo_best1(Lk, Ld, Rk, Rd, scale_factors, n_rows, min_d, max_d):
                            _p(sf, C.c_float), n_rows, float(min_d), float(max_d), _p(best, C.c_int32),
                            _p(dist, C.c_uint16))
     return best, dist
+
+
+def stereo_match(imgL, imgR, Lk, Ld, Rk, Rd, mbf, mb, scale=1.2, nlevels=8):
+    """Frame::ComputeStereoMatches: returns (mvuRight, mvDepth, number of stereo matches kept)."""
+    imgL, imgR = _img(imgL), _img(imgR)
+    Lk = np.ascontiguousarray(Lk, KP_DTYPE)
+    Rk = np.ascontiguousarray(Rk, KP_DTYPE)
+    Ld = np.ascontiguousarray(Ld, np.uint8)
+    Rd = np.ascontiguousarray(Rd, np.uint8)
+    u = np.zeros(len(Lk), np.float32)
+    d = np.zeros(len(Lk), np.float32)
+    n = lib().orc_stereo_match(_p(imgL, C.c_uint8), _p(imgR, C.c_uint8), imgL.shape[1], imgL.shape[0], imgL.strides[0],
+                               scale, nlevels, Lk.ctypes.data, _p(Ld, C.c_uint8), len(Lk), Rk.ctypes.data,
+                               _p(Rd, C.c_uint8), len(Rk), float(mbf), float(mb), _p(u, C.c_float), _p(d, C.c_float))
+    return u, d, n

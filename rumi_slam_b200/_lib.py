@@ -55,6 +55,8 @@ SIGNATURES = {
     "rumi_top2_merge_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "rumi_stereo_best1": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float,
                                     C.c_float, _vp, _vp]),
+    "rumi_stereo_match": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp,
+                                    _i32p]),
     "rumi_descriptor_distance": (C.c_int, [_vp, _vp]),
 }
 

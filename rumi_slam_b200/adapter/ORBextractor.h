@@ -41,6 +41,8 @@ public:
     // Monocular callers that never read it can switch the device-to-host copy off.
     std::vector<cv::Mat> mvImagePyramid;
     void SetPyramidDownload(bool on) { downloadPyramid = on; }
+    // C-ABI handle (lets ORBmatcherAccel::ComputeStereoMatches use the device-resident pyramid in place)
+    rumi_orb* Handle() const { return handle; }
 
     // GPU selection for multi-GPU hosts (process-wide default for extractors constructed afterwards).
     static void SetDefaultDevice(int device);

@@ -65,4 +65,20 @@ void ORBmatcherAccel::StereoBest1(const std::vector<cv::KeyPoint>& keysL, const 
         throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
 }
 
+int ORBmatcherAccel::ComputeStereoMatches(rumi_orb* extractorLeft, rumi_orb* extractorRight,
+                                          const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
+                                          const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR, float mbf,
+                                          float mb, std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+    const std::vector<uint8_t> l = rows32(descL), r = rows32(descR);
+    mvuRight.assign(keysL.size(), -1.0f);
+    mvDepth.assign(keysL.size(), -1.0f);
+    int n = 0;
+    if (keysL.empty()) return 0;
+    if (rumi_stereo_match(ctx, extractorLeft, extractorRight, reinterpret_cast<const rumi_kp*>(keysL.data()), l.data(),
+                          (int)keysL.size(), reinterpret_cast<const rumi_kp*>(keysR.data()), r.data(),
+                          (int)keysR.size(), mbf, mb, mvuRight.data(), mvDepth.data(), &n) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    return n;
+}
+
 }  // namespace ORB_SLAM3

@@ -12,6 +12,7 @@
 #include <opencv2/core/core.hpp>
 
 struct rumi_match;
+struct rumi_orb;
 
 namespace ORB_SLAM3 {
 
@@ -41,6 +42,14 @@ public:
                      const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,
                      const std::vector<float>& scaleFactors, int nRows, float minD, float maxD,
                      std::vector<int>& bestIdxR, std::vector<uint16_t>& bestDist);
+
+    // Frame::ComputeStereoMatches, complete (R/lib_src/Frame.cc:828-985): fills mvuRight / mvDepth (-1 = no match)
+    // from the keypoints / descriptors the two extractors produced in their last call; the image pyramids stay on
+    // the device.  Returns the number of stereo matches kept after the median outlier cut.
+    int ComputeStereoMatches(struct rumi_orb* extractorLeft, struct rumi_orb* extractorRight,
+                             const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
+                             const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR, float mbf, float mb,
+                             std::vector<float>& mvuRight, std::vector<float>& mvDepth);
 
 private:
     rumi_match* ctx;

@@ -872,6 +872,88 @@ int rumi_stereo_best1(rumi_match* m, const rumi_kp* Lk, const uint8_t* Ld, int n
     return RUMI_OK;
 }
 
+int rumi_stereo_match(rumi_match* m, rumi_orb* left, rumi_orb* right, const rumi_kp* Lk, const uint8_t* Ld, int nL,
+                      const rumi_kp* Rk, const uint8_t* Rd, int nR, float mbf, float mb, float* u_right, float* depth,
+                      int* n_matched) {
+    if (!m || !left || !right) return fail(RUMI_ERR_ARG, "NULL handle");
+    if (!left->coef || !right->coef || left->W != right->W || left->H != right->H || left->nlevels != right->nlevels)
+        return fail(RUMI_ERR_ARG, "both extractors must have processed an image of the same shape");
+    if (left->device != m->device || right->device != m->device) return fail(RUMI_ERR_ARG, "handles on different devices");
+    if (nL < 0 || nR < 0 || nR >= (1 << 20)) return fail(RUMI_ERR_ARG, "bad sizes");
+    if (n_matched) *n_matched = 0;
+    if (nL == 0) return RUMI_OK;
+    const int nlevels = left->nlevels;
+    for (int i = 0; i < nR; ++i)
+        if (Rk[i].octave < 0 || Rk[i].octave >= nlevels) return fail(RUMI_ERR_ARG, "right keypoint %d: bad octave", i);
+    for (int i = 0; i < nL; ++i)
+        if (Lk[i].octave < 0 || Lk[i].octave >= nlevels) return fail(RUMI_ERR_ARG, "left keypoint %d: bad octave", i);
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t kb = sizeof(KeyPointRec);
+    const size_t need = (kb + 32) * ((size_t)nL + nR) + 4 * (size_t)nlevels + 20 * (size_t)nL + 512;
+    int rc = grow((void**)&m->dT, &m->tCap, need);
+    if (rc) return rc;
+    uint8_t* p = m->dT;
+    auto take = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 15) & ~(size_t)15; return r; };
+    uint8_t* dLd = take(32 * (size_t)nL);
+    uint8_t* dRd = take(32 * (size_t)std::max(nR, 1));
+    KeyPointRec* dLk = (KeyPointRec*)take(kb * nL);
+    KeyPointRec* dRk = (KeyPointRec*)take(kb * std::max(nR, 1));
+    float* dSf = (float*)take(4 * (size_t)nlevels);
+    int32_t* dBest = (int32_t*)take(4 * (size_t)nL);
+    uint16_t* dDist = (uint16_t*)take(2 * (size_t)nL);
+    float* dU = (float*)take(4 * (size_t)nL);
+    float* dD = (float*)take(4 * (size_t)nL);
+    int* dSad = (int*)take(4 * (size_t)nL);
+    cudaStream_t s = m->stream;
+    // the pyramids were produced on the extractors' own streams
+    CU_TRY(cudaStreamSynchronize(left->ws[left->lastWs].stream));
+    CU_TRY(cudaStreamSynchronize(right->ws[right->lastWs].stream));
+    CU_TRY(cudaMemcpyAsync(dLd, Ld, 32 * (size_t)nL, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(dLk, Lk, kb * nL, cudaMemcpyHostToDevice, s));
+    if (nR > 0) {
+        CU_TRY(cudaMemcpyAsync(dRd, Rd, 32 * (size_t)nR, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(dRk, Rk, kb * nR, cudaMemcpyHostToDevice, s));
+    }
+    CU_TRY(cudaMemcpyAsync(dSf, left->tables.scale.data(), 4 * (size_t)nlevels, cudaMemcpyHostToDevice, s));
+    const float minD = 0.f, maxD = mbf / mb;                                   // Frame.cc:856-858
+    launch_stereo_best1(dLk, dLd, nL, dRk, dRd, nR, dSf, left->H, minD, maxD, dBest, dDist, s);
+    StereoRefineArgs ra;
+    for (int l = 0; l < nlevels; ++l) {
+        ra.left[l] = internal_view(left, left->ws[left->lastWs].pyr, l);
+        ra.right[l] = internal_view(right, right->ws[right->lastWs].pyr, l);
+        ra.scale[l] = left->tables.scale[l];
+        ra.invScale[l] = left->tables.invScale[l];
+    }
+    ra.Lk = dLk; ra.Rk = dRk; ra.bestR = dBest; ra.bestDist = dDist; ra.nL = nL;
+    ra.minD = minD; ra.maxD = maxD; ra.mbf = mbf; ra.uRight = dU; ra.depth = dD; ra.sad = dSad;
+    launch_stereo_refine(ra, s);
+    m->launches += 2;
+    CU_TRY(cudaGetLastError());
+    std::vector<int> sad(nL);
+    CU_TRY(cudaMemcpyAsync(u_right, dU, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(depth, dD, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(sad.data(), dSad, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    // median-based outlier cut (Frame.cc:973-984): sequential host logic, kept as in the reference
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int i = 0; i < nL; ++i)
+        if (sad[i] >= 0) vDistIdx.push_back(std::make_pair(sad[i], i));
+    int kept = (int)vDistIdx.size();
+    if (!vDistIdx.empty()) {
+        std::sort(vDistIdx.begin(), vDistIdx.end());
+        const float median = (float)vDistIdx[vDistIdx.size() / 2].first;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = (int)vDistIdx.size() - 1; i >= 0; --i) {
+            if ((float)vDistIdx[i].first < thDist) break;
+            u_right[vDistIdx[i].second] = -1;
+            depth[vDistIdx[i].second] = -1;
+            --kept;
+        }
+    }
+    if (n_matched) *n_matched = kept;
+    return RUMI_OK;
+}
+
 int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     int d = 0;
     for (int i = 0; i < 4; ++i) {

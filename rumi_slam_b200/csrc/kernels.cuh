@@ -102,4 +102,15 @@ void launch_stereo_best1(const KeyPointRec* Lk, const uint8_t* Ld, int nL, const
                          int nR, const float* scaleFactors, int nRows, float minD, float maxD, int32_t* bestR,
                          uint16_t* bestDist, cudaStream_t s);
 
+struct StereoRefineArgs {
+    LevelView left[kMaxLevels], right[kMaxLevels];     // frame 0 of the two extractors' pyramids
+    float scale[kMaxLevels], invScale[kMaxLevels];
+    const KeyPointRec* Lk; const KeyPointRec* Rk;
+    const int32_t* bestR; const uint16_t* bestDist;
+    int nL;
+    float minD, maxD, mbf;
+    float* uRight; float* depth; int* sad;
+};
+void launch_stereo_refine(const StereoRefineArgs& a, cudaStream_t s);
+
 }  // namespace rumi

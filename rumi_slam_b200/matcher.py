@@ -130,3 +130,18 @@ class ORBmatcher:
         check(self._L.rumi_stereo_best1(self._m, ptr(Lk), ptr(Ld), len(Lk), ptr(Rk), ptr(Rd), len(Rk), ptr(sf),
                                         len(sf), int(n_rows), float(min_d), float(max_d), ptr(best), ptr(dist)))
         return best, dist
+
+    # ---- Frame::ComputeStereoMatches, complete (Frame.cc:828-985) ----
+    def stereo_match(self, ex_left, ex_right, Lk, Ld, Rk, Rd, mbf, mb):
+        """ex_left / ex_right: the ORBextractor objects whose LAST call produced (Lk, Ld) / (Rk, Rd); their device
+        pyramids are used in place.  Returns (mvuRight, mvDepth, number of matches kept)."""
+        Lk = np.ascontiguousarray(Lk, KP_DTYPE)
+        Rk = np.ascontiguousarray(Rk, KP_DTYPE)
+        Ld = np.ascontiguousarray(Ld, np.uint8)
+        Rd = np.ascontiguousarray(Rd, np.uint8)
+        u = np.zeros(len(Lk), np.float32)
+        d = np.zeros(len(Lk), np.float32)
+        n = C.c_int32(0)
+        check(self._L.rumi_stereo_match(self._m, ex_left._h, ex_right._h, ptr(Lk), ptr(Ld), len(Lk), ptr(Rk), ptr(Rd),
+                                        len(Rk), float(mbf), float(mb), ptr(u), ptr(d), C.byref(n)))
+        return u, d, n.value

@@ -91,3 +91,19 @@ def test_descriptor_distance(oracle):
         a, b = rng.integers(0, 256, (2, 32), dtype=np.uint8)
         assert ORBmatcher.DescriptorDistance(a, b) == oracle.descriptor_distance(a, b) == \
             int(np.unpackbits(a ^ b).sum())
+
+
+@pytest.mark.parametrize("w,h,nf,seed", [(752, 480, 1200, 1), (752, 480, 1200, 2), (1241, 376, 2000, 3)])
+def test_compute_stereo_matches_complete(oracle, w, h, nf, seed):
+    """Frame::ComputeStereoMatches end to end (cfg 3 / cfg 4 shapes): mvuRight and mvDepth bit-exact."""
+    from rumi_slam_b200 import ORBextractor
+    left, right = stereo_pair(seed, w, h)
+    exl, exr = ORBextractor(nf, 1.2, 8, 20, 7), ORBextractor(nf, 1.2, 8, 20, 7)     # two instances, as in Frame.cc:116-119
+    _, lk, ld = exl(left)
+    _, rk, rd = exr(right)
+    lk, ld, rk, rd = lk.copy(), ld.copy(), rk.copy(), rd.copy()
+    fx, bf = 435.2, 47.9
+    u, d, n = matcher().stereo_match(exl, exr, lk, ld, rk, rd, bf, bf / fx)
+    ru, rdp, rn = oracle.stereo_match(left, right, lk, ld, rk, rd, bf, bf / fx)
+    assert n == rn and n > 100
+    assert np.array_equal(u, ru) and np.array_equal(d, rdp)

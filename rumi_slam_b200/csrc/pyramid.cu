@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
     // ---- stage the source tile (reflect-101 at the image border) ----
     for (int i = threadIdx.x; i < kBlurSrcRows * kBlurSrcWords; i += kBlurThreads) {
         const int r = i / kBlurSrcWords, c = i - r * kBlurSrcWords;
-        const int gy = reflect101(min(oy - 3 + r, h + 2), h);
+        int gy = min(oy - 3 + r, h + 2);                 // rows past h+2 belong to unused outputs of a partial tile
+        gy = gy < 0 ? -gy : gy;                           // BORDER_REFLECT_101, branch-free (|overshoot| <= 3 < h)
+        gy = gy >= h ? 2 * h - 2 - gy : gy;
         const int gx = ox - 4 + 4 * c;
         const uint8_t* row = s + (long long)gy * sv.stride;
         uint32_t v;

@@ -295,6 +295,7 @@ def run_b200(args):
     alg = algorithmic_bytes(W_IMG, H_IMG, nkp_mean)
     total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
     stage_rows = {}
+    stages = {k: v for k, v in stages.items() if k in alg}      # h2d / d2h spans only exist in the e2e pass
     for name, (sms, nl) in stages.items():
         by = alg[name] * nframes * args.steps                  # bytes this stage moved algorithmically in the region
         gbs = by / (sms / 1e3) / 1e9 if sms > 0 else 0.0

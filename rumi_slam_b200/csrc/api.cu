@@ -163,8 +163,9 @@ int alloc_workspace(rumi_orb* h, Workspace& w) {
     CU_TRY(cudaMalloc(&w.desc, 32 * n * oc.kpCap));
     CU_TRY(cudaMalloc(&w.nkp, 4 * n));
     CU_TRY(cudaMalloc(&w.nmono, 4 * n));
-    CU_TRY(cudaMemset(w.pyr, 0, h->pyrBytes));
-    CU_TRY(cudaMemset(w.blur, 0, h->pyrBytes));
+    // the workspace streams are non-blocking: a legacy-stream memset would not be ordered before the first upload
+    CU_TRY(cudaMemsetAsync(w.pyr, 0, h->pyrBytes, w.stream));
+    CU_TRY(cudaMemsetAsync(w.blur, 0, h->pyrBytes, w.stream));
     for (int l = 1; l < oc.nlevels; ++l) {
         const LevelView src = internal_view(h, w.pyr, l - 1);
         w.tmapOk[l] = h->useTMA && make_tmap(&w.tmap[l], src.ptr, src.w, src.h, h->chunk, src.stride, src.pitch,
@@ -213,6 +214,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
     if (!all.empty()) {
         CU_TRY(cudaMalloc(&h->coef, all.size() * sizeof(ResizeCoef)));
         CU_TRY(cudaMemcpy(h->coef, all.data(), all.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice));
+        CU_TRY(cudaDeviceSynchronize());     // pageable H2D may still be in flight; the workspace streams do not wait for it
     } else {
         CU_TRY(cudaMalloc(&h->coef, sizeof(ResizeCoef)));
     }

@@ -1,5 +1,4 @@
-// K1: scale pyramid (ORBextractor::ComputePyramid, R/lib_src/ORBextractor.cc:1093-1112) and
-// K5: 7x7 fixed-point Gaussian of every level (R/lib_src/ORBextractor.cc:1057-1058).
+// K1: scale pyramid (ORBextractor::ComputePyramid, R/lib_src/ORBextractor.cc:1093-1112).  (K5, the blur, is blur.cu.)
 //
 // K1 restates cv::resize(INTER_LINEAR) on 8UC1 as the 11-bit fixed-point bilinear OpenCV uses.
 // One CTA produces a 64x32 tile of level l from a source box of level l-1 staged in shared memory by ONE TMA
@@ -124,118 +123,6 @@ void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap, cu
         memset(&dummy, 0, sizeof(dummy));
         pyramid_level_kernel<false><<<grid, kPyrThreads, smem, s>>>(dummy, a);
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K5: cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on 8UC1 == separable [18,34,48,56,48,34,18]/256 in
-// fixed point, exact 16-bit horizontal pass, (acc + 32768) >> 16 after the vertical pass.
-// All levels of all frames in one launch: blockIdx.x enumerates (level, tile), blockIdx.y the frame.
-constexpr int kBlurTW = 64, kBlurTH = 32, kBlurThreads = 256;
-
-struct BlurTable {
-    int tileBase[kMaxLevels + 1];
-    int tilesX[kMaxLevels];
-    int nlevels;
-};
-
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (n == 1) return 0;
-    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
-    return i;
-}
-
-// Work per CTA: 64x32 outputs.  Source tile = 38 rows x 72 columns starting 4 columns left of the tile so that
-// every row is a whole number of aligned 32-bit words.  Horizontal pass: a thread produces 4 adjacent outputs from
-// three words with byte-aligning funnel shifts and two DP4A each (weights 18,34,48,56 | 48,34,18,0).  The 16-bit
-// results are stored TRANSPOSED, so the vertical pass reads 10 consecutive u16 of one column as five words and
-// produces 4 vertically adjacent outputs with DP2A (weights (18,34) (48,56) (48,34) (18,0)).
-constexpr int kBlurSrcRows = kBlurTH + 6, kBlurSrcWords = 18, kBlurSrcPitch = 76, kBlurColPitch = 42;
-
-__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ ChunkView cv,
-                                                            const __grid_constant__ BlurTable bt) {
-    __shared__ __align__(16) uint8_t src[kBlurSrcRows * kBlurSrcPitch];
-    __shared__ __align__(16) uint16_t hbT[kBlurTW * kBlurColPitch];
-    int l = 0;
-    while (l + 1 < bt.nlevels && (int)blockIdx.x >= bt.tileBase[l + 1]) ++l;
-    const int t = blockIdx.x - bt.tileBase[l];
-    const int ox = (t % bt.tilesX[l]) * kBlurTW, oy = (t / bt.tilesX[l]) * kBlurTH;
-    const LevelView sv = cv.src[l], dv = cv.blur[l];
-    const int w = sv.w, h = sv.h;
-    const uint8_t* s = sv.ptr + (long long)blockIdx.y * sv.pitch;
-    const bool aligned = ((((uintptr_t)sv.ptr | (uintptr_t)sv.pitch | (uintptr_t)sv.stride) & 3) == 0);
-
-    // ---- stage the source tile (reflect-101 at the image border) ----
-    for (int i = threadIdx.x; i < kBlurSrcRows * kBlurSrcWords; i += kBlurThreads) {
-        const int r = i / kBlurSrcWords, c = i - r * kBlurSrcWords;
-        int gy = min(oy - 3 + r, h + 2);                 // rows past h+2 belong to unused outputs of a partial tile
-        gy = gy < 0 ? -gy : gy;                           // BORDER_REFLECT_101, branch-free (|overshoot| <= 3 < h)
-        gy = gy >= h ? 2 * h - 2 - gy : gy;
-        const int gx = ox - 4 + 4 * c;
-        const uint8_t* row = s + (long long)gy * sv.stride;
-        uint32_t v;
-        if (aligned && gx >= 0 && gx + 3 < w) {
-            v = *reinterpret_cast<const uint32_t*>(row + gx);
-        } else {
-            v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v |= (uint32_t)row[reflect101(min(gx + b, w + 2), w)] << (8 * b);
-        }
-        *reinterpret_cast<uint32_t*>(src + r * kBlurSrcPitch + 4 * c) = v;
-    }
-    __syncthreads();
-
-    // ---- horizontal pass: item = (row r, group g of 4 outputs); consecutive threads take consecutive rows ----
-    for (int i = threadIdx.x; i < kBlurSrcRows * (kBlurTW / 4); i += kBlurThreads) {
-        const int g = i / kBlurSrcRows, r = i - g * kBlurSrcRows;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + r * kBlurSrcPitch + 4 * g);
-        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
-        // output j (tile column 4g+4+j) uses bytes 1+j .. 7+j of the 12-byte window
-        const uint32_t a0 = __funnelshift_r(w0, w1, 8), b0 = __funnelshift_r(w1, w2, 8);
-        const uint32_t a1 = __funnelshift_r(w0, w1, 16), b1 = __funnelshift_r(w1, w2, 16);
-        const uint32_t a2 = __funnelshift_r(w0, w1, 24), b2 = __funnelshift_r(w1, w2, 24);
-        const uint32_t kLo = 0x38302212u, kHi = 0x00122230u;      // (18,34,48,56) and (48,34,18,0)
-        uint16_t* o = hbT + (4 * g) * kBlurColPitch + r;
-        o[0] = (uint16_t)__dp4a(a0, kLo, __dp4a(b0, kHi, 0u));
-        o[kBlurColPitch] = (uint16_t)__dp4a(a1, kLo, __dp4a(b1, kHi, 0u));
-        o[2 * kBlurColPitch] = (uint16_t)__dp4a(a2, kLo, __dp4a(b2, kHi, 0u));
-        o[3 * kBlurColPitch] = (uint16_t)__dp4a(w1, kLo, __dp4a(w2, kHi, 0u));
-    }
-    __syncthreads();
-
-    // ---- vertical pass: item = (column x, group of 4 rows) ----
-    uint8_t* d = const_cast<uint8_t*>(dv.ptr) + (long long)blockIdx.y * dv.pitch;
-    for (int i = threadIdx.x; i < kBlurTW * (kBlurTH / 4); i += kBlurThreads) {
-        const int yg = i / kBlurTW, x = i - yg * kBlurTW;
-        if (ox + x >= dv.stride) continue;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(hbT + x * kBlurColPitch + 4 * yg);
-        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
-        const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16);
-        const uint32_t s2 = __funnelshift_r(w2, w3, 16), s3 = __funnelshift_r(w3, w4, 16), s4 = w4 >> 16;
-        const uint32_t kA = 0x2212u, kB = 0x3830u, kC = 0x2230u, kD = 0x0012u;   // (18,34) (48,56) (48,34) (18,0)
-        uint32_t acc[4];
-        acc[0] = __dp2a_lo(w0, kA, __dp2a_lo(w1, kB, __dp2a_lo(w2, kC, __dp2a_lo(w3, kD, 32768u))));
-        acc[1] = __dp2a_lo(s0, kA, __dp2a_lo(s1, kB, __dp2a_lo(s2, kC, __dp2a_lo(s3, kD, 32768u))));
-        acc[2] = __dp2a_lo(w1, kA, __dp2a_lo(w2, kB, __dp2a_lo(w3, kC, __dp2a_lo(w4, kD, 32768u))));
-        acc[3] = __dp2a_lo(s1, kA, __dp2a_lo(s2, kB, __dp2a_lo(s3, kC, __dp2a_lo(s4, kD, 32768u))));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int y = oy + 4 * yg + j;
-            if (y < h) d[(long long)y * dv.stride + ox + x] = (uint8_t)(acc[j] >> 16);
-        }
-    }
-}
-
-void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s) {
-    BlurTable bt;
-    bt.nlevels = oc.nlevels;
-    int base = 0;
-    for (int l = 0; l < oc.nlevels; ++l) {
-        bt.tileBase[l] = base;
-        bt.tilesX[l] = (oc.lv[l].w + kBlurTW - 1) / kBlurTW;
-        base += bt.tilesX[l] * ((oc.lv[l].h + kBlurTH - 1) / kBlurTH);
-    }
-    bt.tileBase[oc.nlevels] = base;
-    blur_kernel<<<dim3(base, cv.nframes), kBlurThreads, 0, s>>>(cv, bt);
 }
 
 }  // namespace rumi

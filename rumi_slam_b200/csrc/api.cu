@@ -106,7 +106,8 @@ struct rumi_orb {
     long long pyrLevelOff[kMaxLevels], candLevelOff[kMaxLevels], bigKeysLevelOff[kMaxLevels];
     int bigKeysCap[kMaxLevels];
     long long pyrBytes = 0, candElems = 0, bigKeysElems = 0;
-    int fastTilePitch = 0, fastTileRows = 0, fastScorePitch = 0, fastScoreRows = 0, fastMaskWords = 0;
+    int fastTilePitch = 0, fastTileRows = 0, fastScoreRows = 0, fastMaskWords = 0;
+    FastCell* fastCells = nullptr;                    // [totalCells] cell geometry of all levels
     int smemKeys = 4096, maxNodeCap = 0;
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
@@ -186,7 +187,9 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         free_workspace(h->ws[i]);
     }
     cudaFree(h->coef);
+    cudaFree(h->fastCells);
     h->coef = nullptr;
+    h->fastCells = nullptr;
     h->oc = oc;
     h->W = W; h->H = H;
     // resize coefficient tables + per-level source box of a 64x32 tile
@@ -221,7 +224,8 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
     for (int l = 1; l < oc.nlevels; ++l) { h->xc[l] = h->coef + xo[l]; h->yc[l] = h->coef + yo[l]; }
     // level-major workspace offsets for `chunk` frames
     long long pb = 0, ce = 0, be = 0;
-    int tp = 0, tr = 0, sp = 0, sr = 0, mw = 0, nodeCap = 0;
+    int tp = 0, tr = 0, sr = 0, hc = 0, nodeCap = 0;
+    std::vector<FastCell> cells(oc.totalCells);
     for (int l = 0; l < oc.nlevels; ++l) {
         const LevelGeom& g = oc.lv[l];
         h->pyrLevelOff[l] = pb; pb += (long long)h->chunk * g.stride * g.h;
@@ -232,14 +236,27 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         h->bigKeysCap[l] = cap;
         h->bigKeysLevelOff[l] = be; be += (long long)h->chunk * cap;
         tp = std::max(tp, align_up(g.wCell + 6 + 15, 16)); tr = std::max(tr, g.hCell + 6);   // 16-B aligned staging
-        sp = std::max(sp, align_up(g.wCell + 2, 4)); sr = std::max(sr, g.hCell + 2);
-        mw = std::max(mw, (g.wCell * g.hCell + 31) / 32);
+        sr = std::max(sr, g.hCell + 2); hc = std::max(hc, g.hCell);
+        // FAST grid cells (R/lib_src/ORBextractor.cc:748-763): sub-image origin / size clipped to the level border
+        const int maxBX = g.w - kMinBorder, maxBY = g.h - kMinBorder;
+        for (int ci = 0; ci < g.nRows; ++ci)
+            for (int cj = 0; cj < g.nCols; ++cj) {
+                FastCell& c = cells[g.cellBase + ci * g.nCols + cj];
+                const int iniY = kMinBorder + ci * g.hCell, iniX = kMinBorder + cj * g.wCell;
+                const int maxY = std::min(iniY + g.hCell + 6, maxBY), maxX = std::min(iniX + g.wCell + 6, maxBX);
+                c.iniX = (uint16_t)iniX; c.iniY = (uint16_t)iniY; c.level = (uint8_t)l;
+                c.valid = !(iniY >= maxBY - 3 || iniX >= maxBX - 6) && maxX - iniX > 6 && maxY - iniY > 6;
+                c.cw = (uint8_t)(c.valid ? maxX - iniX : 0); c.ch = (uint8_t)(c.valid ? maxY - iniY : 0);
+            }
         const int slots = (l + 1 < oc.nlevels ? oc.lv[l + 1].kpBase : oc.kpCap) - g.kpBase;
         nodeCap = std::max(nodeCap, slots + 1);
         if (g.candCap >= (1 << 19)) return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, g.candCap);
     }
     h->pyrBytes = pb + 256; h->candElems = ce; h->bigKeysElems = be;
-    h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScorePitch = sp; h->fastScoreRows = sr; h->fastMaskWords = mw;
+    h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScoreRows = sr; h->fastMaskWords = (tp * hc + 31) / 32;
+    CU_TRY(cudaMalloc(&h->fastCells, sizeof(FastCell) * std::max<size_t>(cells.size(), 1)));
+    CU_TRY(cudaMemcpy(h->fastCells, cells.data(), sizeof(FastCell) * cells.size(), cudaMemcpyHostToDevice));
+    CU_TRY(cudaDeviceSynchronize());
     h->maxNodeCap = nodeCap;
     h->smemKeys = 4096;
     while (h->smemKeys > 256 && octree_smem_bytes(h->smemKeys, nodeCap, 256) > 200 * 1024) h->smemKeys >>= 1;
@@ -310,7 +327,8 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     prof_mark(h, s, ST_PYRAMID, oc.nlevels - 1);
     FastArgs fa;
     fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
-    fa.tilePitch = h->fastTilePitch; fa.tileRows = h->fastTileRows; fa.scorePitch = h->fastScorePitch;
+    fa.cells = h->fastCells;
+    fa.tilePitch = h->fastTilePitch; fa.tileRows = h->fastTileRows;
     fa.scoreRows = h->fastScoreRows; fa.maskWords = h->fastMaskWords;
     fa.dbg = h->dbgBuf; fa.dbgCell = h->dbgCell;
     OctreeArgs oa;
@@ -401,6 +419,7 @@ void rumi_orb_destroy(rumi_orb* h) {
         if (h->ws[i].stream) cudaStreamDestroy(h->ws[i].stream);
     }
     cudaFree(h->coef);
+    cudaFree(h->fastCells);
     cudaFree(h->dbgBuf);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->evStart) cudaEventDestroy(h->evStart);
@@ -678,10 +697,10 @@ int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* 
     if (!h->dbgBuf) { CU_TRY(cudaMalloc(&h->dbgBuf, 1 << 16)); CU_TRY(cudaMemset(h->dbgBuf, 0, 1 << 16)); }
     h->dbgCell = cell;
     if (out && h->coef) {
-        const int nb = h->fastTilePitch * h->fastTileRows + h->fastScorePitch * h->fastScoreRows;
+        const int nb = h->fastTilePitch * h->fastTileRows + h->fastTilePitch * h->fastScoreRows;
         CU_TRY(cudaDeviceSynchronize());
         CU_TRY(cudaMemcpy(out, h->dbgBuf, std::min(nb, cap), cudaMemcpyDeviceToHost));
-        if (dims5) { dims5[0] = h->fastTilePitch; dims5[1] = h->fastTileRows; dims5[2] = h->fastScorePitch; dims5[3] = h->fastScoreRows; dims5[4] = h->fastMaskWords; }
+        if (dims5) { dims5[0] = h->fastTilePitch; dims5[1] = h->fastTileRows; dims5[2] = h->fastTilePitch; dims5[3] = h->fastScoreRows; dims5[4] = h->fastMaskWords; }
         return nb;
     }
     return 0;

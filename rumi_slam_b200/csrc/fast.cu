@@ -24,44 +24,32 @@ namespace rumi {
 
 constexpr int kFastWarps = 4;
 constexpr int kCornerListCap = 512;        // corner list entries per cell; beyond that NMS scans the score tile
+constexpr int kQueueCap = 160;             // pretest survivors waiting for the exact score (< 32 + 4 * 32)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // sign bit of a -> LSB of the running mask (one SHF per ring pixel)
 __device__ __forceinline__ uint32_t push_sign(uint32_t mask, int a) { return __funnelshift_l((uint32_t)a, mask, 1); }
 
-// cornerScore<16> with 16-bit packed SIMD (sm_100a has native VIMNMX.S16x2 / VIMNMX3.S16x2).
-// Ring differences d[k] = centre - ring[k] are held as 8 registers of adjacent pairs R[i] = (d[2i], d[2i+1]); the
-// sliding min (and max) of 9 consecutive differences is min3 over k, k+1, k+2 followed by min3 over k, k+3, k+6:
-//   w3[k] = min3(d[k], d[k+1], d[k+2])          (pairs: R[i], S[i] = (d[2i+1], d[2i+2]), R[i+1])
-//   w9[k] = min3(w3[k], w3[k+3], w3[k+6])       (pairs: W[i], T[i+1] = (w3[2i+3], w3[2i+4]), W[i+3])
-// score = max(max_k w9min[k], -min_k w9max[k]) - 1.  The combination avoids max(a, -b) (see orb_math.cuh).
-__device__ __forceinline__ int fast_score16_packed(const int d[16]) {
-    uint32_t R[8], S[8];
+// cornerScore<16> with 16-bit packed SIMD (sm_100a has native VIMNMX3.S16x2), BOTH arc polarities in one pass.
+// For ring pixel p_k and centre v, ONE multiply-add builds the packed pair
+//     P[k] = p_k * 0xFFFF + K,  K = ((-v) << 16) | (v + 256)   ->   low lane = (v - p_k) + 256,  high lane = p_k - v
+// (p * 0xFFFF = (p-1) << 16 | (65536 - p); the low lane sum always carries exactly once because v + 256 - p >= 1).
+// The sliding minimum over 9 consecutive ring positions is min3 over k, k+1, k+2 followed by min3 over k, k+3, k+6,
+// evaluated on both lanes at once: the low lane yields max_w min_w (v - p) + 256 (dark arcs), the high lane
+// max_w min_w (p - v) (bright arcs); score = max(low - 256, high) - 1, exactly cv::cornerScore<16>.
+__device__ __forceinline__ int fast_score16_packed(const uint32_t P[16]) {
+    uint32_t w3[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) R[i] = __byte_perm((uint32_t)d[2 * i], (uint32_t)d[2 * i + 1], 0x5410);   // (lo16, lo16)
+    for (int k = 0; k < 16; ++k) w3[k] = __vimin3_s16x2(P[k], P[(k + 1) & 15], P[(k + 2) & 15]);
+    uint32_t best = 0x80008000u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) S[i] = __byte_perm(R[i], R[(i + 1) & 7], 0x5432);       // (hi of R[i], lo of R[i+1])
-    uint32_t Wn[8], Wx[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        Wn[i] = __vimin3_s16x2(R[i], S[i], R[(i + 1) & 7]);
-        Wx[i] = __vimax3_s16x2(R[i], S[i], R[(i + 1) & 7]);
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a = __vimin3_s16x2(w3[k], w3[(k + 3) & 15], w3[(k + 6) & 15]);
+        const uint32_t b = __vimin3_s16x2(w3[k + 1], w3[(k + 4) & 15], w3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a, b);
     }
-    uint32_t bestLo = 0x80008000u, bestHi = 0x7FFF7FFFu;      // packed running max of min9 / min of max9
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t Tn = __byte_perm(Wn[(i + 1) & 7], Wn[(i + 2) & 7], 0x5432);     // (w3[2i+3], w3[2i+4])
-        const uint32_t Tx = __byte_perm(Wx[(i + 1) & 7], Wx[(i + 2) & 7], 0x5432);
-        const uint32_t n9 = __vimin3_s16x2(Wn[i], Tn, Wn[(i + 3) & 7]);
-        const uint32_t x9 = __vimax3_s16x2(Wx[i], Tx, Wx[(i + 3) & 7]);
-        bestLo = __vmaxs2(bestLo, n9);
-        bestHi = __vmins2(bestHi, x9);
-    }
-    const int lo0 = (int)(short)(bestLo & 0xFFFFu), lo1 = (int)(short)(bestLo >> 16);
-    const int hi0 = (int)(short)(bestHi & 0xFFFFu), hi1 = (int)(short)(bestHi >> 16);
-    const int lo = lo0 > lo1 ? lo0 : lo1, hi = hi0 < hi1 ? hi0 : hi1;
-    const int best = (lo + hi > 0) ? lo : (0 - hi);
-    return best - 1;
+    const int lo = (int)(best & 0xFFFFu) - 256, hi = (int)(short)(best >> 16);
+    return (lo > hi ? lo : hi) - 1;
 }
 
 // exact score of the pixel whose centre is p (shared tile, row pitch tp); the pixel is a corner at threshold th
@@ -69,18 +57,30 @@ __device__ __forceinline__ int fast_score16_packed(const int d[16]) {
 template <int TP>
 __device__ __forceinline__ int corner_score(const uint8_t* p, int tpRuntime) {
     const int tp = TP ? TP : tpRuntime;
-    const int v = p[0];
-    int d[16];
-    d[0] = v - p[3 * tp];       d[1] = v - p[3 * tp + 1];   d[2] = v - p[2 * tp + 2];   d[3] = v - p[tp + 3];
-    d[4] = v - p[3];            d[5] = v - p[-tp + 3];      d[6] = v - p[-2 * tp + 2];  d[7] = v - p[-3 * tp + 1];
-    d[8] = v - p[-3 * tp];      d[9] = v - p[-3 * tp - 1];  d[10] = v - p[-2 * tp - 2]; d[11] = v - p[-tp - 3];
-    d[12] = v - p[-3];          d[13] = v - p[tp - 3];      d[14] = v - p[2 * tp - 2];  d[15] = v - p[3 * tp - 1];
-    return fast_score16_packed(d);
+    const uint32_t v = p[0];
+    const uint32_t K = ((0u - v) << 16) | (v + 256u);
+    uint32_t P[16];
+#define RUMI_RING(k, off) P[k] = (uint32_t)p[off] * 0xFFFFu + K
+    RUMI_RING(0, 3 * tp);       RUMI_RING(1, 3 * tp + 1);   RUMI_RING(2, 2 * tp + 2);   RUMI_RING(3, tp + 3);
+    RUMI_RING(4, 3);            RUMI_RING(5, -tp + 3);      RUMI_RING(6, -2 * tp + 2);  RUMI_RING(7, -3 * tp + 1);
+    RUMI_RING(8, -3 * tp);      RUMI_RING(9, -3 * tp - 1);  RUMI_RING(10, -2 * tp - 2); RUMI_RING(11, -tp - 3);
+    RUMI_RING(12, -3);          RUMI_RING(13, tp - 3);      RUMI_RING(14, 2 * tp - 2);  RUMI_RING(15, 3 * tp - 1);
+#undef RUMI_RING
+    return fast_score16_packed(P);
 }
 
 // magic-number division for small operands: q = n / d for n < 65536, d < 65536, magic = ceil(2^32 / d) (d > 1)
 __device__ __forceinline__ uint32_t magic_of(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); }
 __device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
+
+// Shared-memory layout of one warp.  The score tile and the survivor bitmap use the SAME pitch as the image tile,
+// so one 16-bit offset o = y * tp + x (detection-area coordinates) addresses all three and no phase after the
+// pretest needs a division.
+__host__ __device__ inline size_t fast_warp_bytes(int tp, int tileRows, int scoreRows, int maskWords) {
+    const size_t b = (size_t)tp * tileRows + ((size_t)tp * scoreRows + 32) + 4u * maskWords + 2u * kCornerListCap +
+                     2u * kQueueCap;
+    return (b + 15) & ~(size_t)15;
+}
 
 template <int TP>
 __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_constant__ FastArgs a,
@@ -91,41 +91,26 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     const int f = blockIdx.y;
     if (cellId >= oc.totalCells) return;
 
-    int l = 0;
-    while (l + 1 < oc.nlevels && cellId >= oc.lv[l + 1].cellBase) ++l;
-    const LevelGeom& g = oc.lv[l];
-    const int c = cellId - g.cellBase;
-    const int ci = c / g.nCols, cj = c - ci * g.nCols;
-
-    // per-warp shared memory: image tile | score tile | survivor bitmap | corner list | queue
-    const int tp = TP ? TP : a.tilePitch, sp = a.scorePitch;     // TP > 0: compile-time pitch -> immediate offsets
-    const size_t perWarp = (size_t)tp * a.tileRows + (size_t)sp * a.scoreRows + 4u * a.maskWords +
-                           2u * kCornerListCap + 2u * 160;
-    uint8_t* base = smem + (size_t)warp * ((perWarp + 15) & ~(size_t)15);
-    uint8_t* tile = base;
-    uint8_t* score = tile + (size_t)tp * a.tileRows;
-    uint32_t* kept = reinterpret_cast<uint32_t*>(score + (size_t)sp * a.scoreRows);
-    uint16_t* clist = reinterpret_cast<uint16_t*>(kept + a.maskWords);
-    uint16_t* queue = clist + kCornerListCap;
-
-    // cell geometry (:748-763)
-    const int maxBX = g.w - kMinBorder, maxBY = g.h - kMinBorder;
-    const int iniY = kMinBorder + ci * g.hCell, iniX = kMinBorder + cj * g.wCell;
-    int maxY = iniY + g.hCell + 6, maxX = iniX + g.wCell + 6;
+    // cell geometry (:748-763), precomputed on the host (api.cu: build_fast_cells)
+    const uint2 cellBits = *reinterpret_cast<const uint2*>(a.cells + cellId);     // FastCell is 8 bytes
+    const int l = (int)((cellBits.y >> 16) & 0xFFu);
     int* cellCount = a.cellCount + (long long)f * oc.totalCells + cellId;
     int* cellOff = a.cellOff + (long long)f * oc.totalCells + cellId;
-    if (iniY >= maxBY - 3 || iniX >= maxBX - 6) {
+    if ((cellBits.y >> 24) == 0u) {                     // cell outside the level border (:752, :759)
         if (lane == 0) { *cellCount = 0; *cellOff = 0; }
         return;
     }
-    if (maxY > maxBY) maxY = maxBY;
-    if (maxX > maxBX) maxX = maxBX;
-    const int cw = maxX - iniX, ch = maxY - iniY;       // sub-image
+    const int iniX = (int)(cellBits.x & 0xFFFFu), iniY = (int)(cellBits.x >> 16);
+    const int cw = (int)(cellBits.y & 0xFFu), ch = (int)((cellBits.y >> 8) & 0xFFu);       // sub-image
     const int dw = cw - 6, dh = ch - 6;                 // detection area, origin (iniX+3, iniY+3)
-    if (dw <= 0 || dh <= 0) {
-        if (lane == 0) { *cellCount = 0; *cellOff = 0; }
-        return;
-    }
+
+    // per-warp shared memory: image tile | score tile | survivor bitmap | corner list | queue
+    const int tp = TP ? TP : a.tilePitch;               // TP > 0: compile-time pitch -> immediate offsets
+    uint8_t* tile = smem + (size_t)warp * fast_warp_bytes(tp, a.tileRows, a.scoreRows, a.maskWords);
+    uint8_t* score = tile + (size_t)tp * a.tileRows;
+    uint32_t* kept = reinterpret_cast<uint32_t*>(score + (size_t)tp * a.scoreRows + 32);
+    uint16_t* clist = reinterpret_cast<uint16_t*>(kept + a.maskWords);
+    uint16_t* queue = clist + kCornerListCap;
 
     // ---- 0. stage the sub-image: tile column ox <-> image column iniX ----
     const LevelView lv = a.cv.src[l];
@@ -133,7 +118,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     int ox;
     if ((((uintptr_t)lv.ptr | (uintptr_t)lv.pitch | (uintptr_t)lv.stride) & 15) == 0) {
         ox = (int)((uintptr_t)img & 15);
-        const int nvec = (ox + cw + 15) >> 4;           // <= 8 for cells up to 76+15 columns
+        const int nvec = (ox + cw + 15) >> 4;           // <= 6 for cells up to 76+15 columns
         const int vc = lane & 7, rr = lane >> 3;
         if (vc < nvec) {
             const uint8_t* src = img - ox + 16 * vc;
@@ -148,30 +133,33 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
             for (int x = lane; x < cw; x += 32) tile[r * tp + x] = row[x];
         }
     }
-    // zero the score tile (1-px zero frame = "neighbour outside the detection area") and the survivor bitmap
-    const int npx = dw * dh, nwords = (npx + 31) >> 5;
-    for (int i = lane; i < (sp * (dh + 2) + 3) / 4; i += 32) reinterpret_cast<uint32_t*>(score)[i] = 0u;
-    for (int i = lane; i < nwords; i += 32) kept[i] = 0u;
+    // zero the score tile (everything outside the detection area stays 0 = "neighbour outside the sub-image") and
+    // the survivor bitmap
+    const int nbits = (dh - 1) * tp + dw, nwords = (nbits + 31) >> 5;
+    {
+        uint4* z = reinterpret_cast<uint4*>(score);
+        const int n16 = (tp * (dh + 2) + 32 + 15) >> 4;
+        for (int i = lane; i < n16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lane; i < nwords; i += 32) kept[i] = 0u;
+    }
     __syncwarp();
 
     const int th = oc.minTh;
-    const uint8_t* t0 = tile + 3 * tp + 3 + ox;         // detection-area origin inside the tile
-    uint8_t* s0 = score + sp + 1;
-    const uint32_t magicW = magic_of((uint32_t)dw);
+    const uint8_t* t0 = tile + 3 * tp + 3 + ox;         // detection-area origin inside the image tile
+    uint8_t* s0 = score + tp + 16;                      // same origin inside the score tile
     int qn = 0, ncorner = 0;                            // queue fill, corner-list fill (warp uniform)
     bool overflow = false;
 
-    auto drain = [&](int idq, bool valid) {
+    auto drain = [&](int o, bool valid) {
         int sc = 0;
         if (valid) {
-            const int y = (int)div_magic((uint32_t)idq, magicW), x = idq - y * dw;
-            sc = corner_score<TP>(t0 + y * tp + x, tp);
+            sc = corner_score<TP>(t0 + o, tp);
             if (sc < th) sc = 0;                         // not a corner at the low threshold
-            if (sc > 0) s0[y * sp + x] = (uint8_t)sc;
+            if (sc > 0) s0[o] = (uint8_t)sc;
         }
         const unsigned m = __ballot_sync(kFull, sc > 0);
         if (ncorner + __popc(m) <= kCornerListCap) {
-            if (sc > 0) clist[ncorner + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idq;
+            if (sc > 0) clist[ncorner + __popc(m & ((1u << lane) - 1u))] = (uint16_t)o;
         } else {
             overflow = true;                             // too many corners for the list: NMS will scan all pixels
         }
@@ -239,8 +227,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                 if (xhi < 4) valid &= 0xFFFFFFFFu >> (8 * (4 - xhi));
                 pass4 = any & valid;
             }
-            const int idx0 = y * dw + 4 * g - c0;                                // detection index of byte 0
-            {   // append the (up to 4) surviving pixels of every lane: popc + shuffle prefix instead of 4 ballots
+            const int o0 = y * tp + 4 * g - c0;                                  // offset of byte 0 of the group
+            {   // append the (up to 4) surviving pixels of every lane: popc + shuffle prefix, predicated stores
                 const int c = __popc(pass4);
                 int incl = c;
 #pragma unroll
@@ -249,12 +237,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                     if (lane >= o) incl += n;
                 }
                 int pos = qn + incl - c;
-                uint32_t t = pass4;
-                while (t) {
-                    const int bit = __ffs(t) - 1;
-                    t &= t - 1;
-                    queue[pos++] = (uint16_t)(idx0 + (bit >> 3));
-                }
+                if (pass4 & 0x00000080u) queue[pos++] = (uint16_t)o0;
+                if (pass4 & 0x00008000u) queue[pos++] = (uint16_t)(o0 + 1);
+                if (pass4 & 0x00800000u) queue[pos++] = (uint16_t)(o0 + 2);
+                if (pass4 & 0x80000000u) queue[pos] = (uint16_t)(o0 + 3);
                 qn += __shfl_sync(kFull, incl, 31);
             }
             __syncwarp();
@@ -266,29 +252,37 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
             }
         }
     }
-    drain(lane < qn ? queue[lane] : 0, lane < qn);
+    if (qn > 0) drain(lane < qn ? queue[lane] : 0, lane < qn);
     __syncwarp();
 
     if (a.dbg && f == 0 && cellId == a.dbgCell) {
-        const int nb = tp * a.tileRows + sp * a.scoreRows;
+        const int nb = tp * a.tileRows + tp * a.scoreRows;
         for (int i = lane; i < nb; i += 32) a.dbg[i] = tile[i];
     }
 
-    // ---- C. NMS over the corner list ----
+    // ---- C. NMS over the corner list: strict '>' against the 8 neighbours, branch-free ----
     int nIni = 0, nMin = 0;
+    const int npx = dw * dh;
+    const uint32_t magicW = magic_of((uint32_t)dw);
     const int nmsCount = overflow ? npx : ncorner;
     for (int b = 0; b < nmsCount; b += 32) {
         bool k = false;
-        int s = 0, idq = 0;
+        int s = 0, o = 0;
         if (b + lane < nmsCount) {
-            idq = overflow ? b + lane : (int)clist[b + lane];
-            const int y = (int)div_magic((uint32_t)idq, magicW), x = idq - y * dw;
-            const uint8_t* q = s0 + y * sp + x;
+            if (overflow) {
+                const int idq = b + lane, y = (int)div_magic((uint32_t)idq, magicW);
+                o = y * tp + (idq - y * dw);
+            } else {
+                o = (int)clist[b + lane];
+            }
+            const uint8_t* q = s0 + o;
             s = q[0];
-            k = s > 0 && s > q[-1] && s > q[1] && s > q[-sp - 1] && s > q[-sp] && s > q[-sp + 1] && s > q[sp - 1] &&
-                s > q[sp] && s > q[sp + 1];
+            const int m0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
+            const int m1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
+            const int m2 = max(max((int)q[tp], (int)q[tp + 1]), m0);
+            k = s > max(m1, m2);                         // s == 0 (overflow scan of a non-corner) can never pass
         }
-        if (k) atomicOr(&kept[idq >> 5], 1u << (idq & 31));
+        if (k) atomicOr(&kept[o >> 5], 1u << (o & 31));
         nMin += __popc(__ballot_sync(kFull, k));
         nIni += __popc(__ballot_sync(kFull, k && s >= oc.iniTh));
     }
@@ -304,9 +298,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     off = __shfl_sync(kFull, off, 0);
     if (total == 0) return;
 
-    // ---- D. raster-order emission from the survivor bitmap ----
-    uint32_t* out = a.cand + a.candLevelOff[l] + (long long)f * g.candCap + off;
+    // ---- D. raster-order emission from the survivor bitmap (bit index = y * tp + x, row major) ----
+    uint32_t* out = a.cand + a.candLevelOff[l] + (long long)f * oc.lv[l].candCap + off;
     const int relX = iniX + 3 - kMinBorder, relY = iniY + 3 - kMinBorder;   // candidate coords are relative to (16,16)
+    const uint32_t magicT = magic_of((uint32_t)tp);
     int w = 0;
     for (int wb = 0; wb < nwords; wb += 32) {
         uint32_t bits = wb + lane < nwords ? kept[wb + lane] : 0u;
@@ -315,9 +310,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
             while (t) {
                 const int bit = __ffs(t) - 1;
                 t &= t - 1;
-                const int idx = (wb + lane) * 32 + bit;
-                const int y = (int)div_magic((uint32_t)idx, magicW), x = idx - y * dw;
-                if (s0[y * sp + x] >= thEmit) keep |= 1u << bit;
+                if (s0[(wb + lane) * 32 + bit] >= thEmit) keep |= 1u << bit;
             }
             bits = keep;
         }
@@ -331,18 +324,16 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
         while (bits) {
             const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
-            const int idx = (wb + lane) * 32 + bit;
-            const int y = (int)div_magic((uint32_t)idx, magicW), x = idx - y * dw;
-            out[pos++] = pack_cand(relX + x, relY + y, s0[y * sp + x]);
+            const int o = (wb + lane) * 32 + bit;
+            const int y = TP == 64 ? (o >> 6) : (int)div_magic((uint32_t)o, magicT), x = o - y * tp;
+            out[pos++] = pack_cand(relX + x, relY + y, s0[o]);
         }
         w += __shfl_sync(kFull, pre, 31);
     }
 }
 
 void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s) {
-    const size_t perWarp = ((size_t)a.tilePitch * a.tileRows + (size_t)a.scorePitch * a.scoreRows +
-                            4u * a.maskWords + 2u * kCornerListCap + 2u * 160 + 15) & ~(size_t)15;
-    const size_t smem = perWarp * kFastWarps;
+    const size_t smem = fast_warp_bytes(a.tilePitch, a.tileRows, a.scoreRows, a.maskWords) * kFastWarps;
     dim3 grid((oc.totalCells + kFastWarps - 1) / kFastWarps, a.cv.nframes);
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

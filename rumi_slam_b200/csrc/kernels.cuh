@@ -40,14 +40,19 @@ void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap /* 
 int read_tma_timeout_flag();     // 1 = a TMA load timed out since the module was loaded, -1 = query failed
 void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s);
 
+// One FAST grid cell (R/lib_src/ORBextractor.cc:748-763): sub-image origin and size, clipped to the level border.
+struct alignas(8) FastCell { uint16_t iniX, iniY; uint8_t cw, ch, level, valid; };
+static_assert(sizeof(FastCell) == 8, "FastCell is read as one 8-byte word");
+
 struct FastArgs {
     ChunkView cv;
+    const FastCell* cells;   // [totalCells], all levels
     uint32_t* cand;          // level-major: [level][frame][candCap]
     long long candLevelOff[kMaxLevels];   // element offset of (level, frame 0)
     int* levelCount;         // [frame][nlevels] (zeroed by the caller)
     int* cellOff;            // [frame][totalCells]
     int* cellCount;          // [frame][totalCells]
-    int tilePitch, tileRows, scorePitch, scoreRows, maskWords;   // per-warp shared-memory tile sizes
+    int tilePitch, tileRows, scoreRows, maskWords;   // per-warp shared-memory tile sizes (score tile pitch == tilePitch)
     uint8_t* dbg;            // optional: image + score tile of (frame 0, dbgCell) for tests
     int dbgCell;
 };

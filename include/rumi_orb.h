@@ -89,6 +89,9 @@ int rumi_orb_debug_candidates(rumi_orb* h, int level, int32_t* xyr, int cap);
 int rumi_orb_debug_selected(rumi_orb* h, int level, int32_t* xyr, int cap);
 /* Test hook: arms (out == NULL) or reads back the shared-memory image + score tile of FAST cell `cell` of frame 0. */
 int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* dims5);
+/* profiling hook: first call arms per-phase cycle counters of the quad-tree kernel (frame 0 of every chunk), later
+   calls copy out[level*16 + phase] and reset them; returns the number of counters */
+int rumi_orb_debug_octree_clocks(rumi_orb* h, long long* out, int cap);
 
 /* ---- measurement (bench.py) ----
  * Device-side timing on the streams the kernels are launched on: start records an event on the handle's first

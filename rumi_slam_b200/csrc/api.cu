@@ -113,6 +113,7 @@ struct rumi_orb {
     int nws = 4;
     int lastWs = 0;
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
+    long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
     int dbgCell = 0;
     // measurement: device-side timer on the launching streams, optional per-stage events, launch counter
     cudaEvent_t evStart = nullptr, evStop = nullptr, evJoin[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};
@@ -332,7 +333,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     fa.scoreRows = h->fastScoreRows; fa.maskWords = h->fastMaskWords;
     fa.dbg = h->dbgBuf; fa.dbgCell = h->dbgCell;
     OctreeArgs oa;
-    oa.nframes = n; oa.cand = w.cand; oa.candOrdered = w.candOrdered; oa.levelCount = w.levelCount;
+    oa.nframes = n; oa.levelFirst = 0; oa.dbgClk = h->octClk; oa.cand = w.cand; oa.candOrdered = w.candOrdered; oa.levelCount = w.levelCount;
     oa.cellOff = w.cellOff; oa.cellCount = w.cellCount; oa.bigKeys = w.bigKeys; oa.sel = w.sel;
     oa.selCount = w.selCount; oa.smemKeys = h->smemKeys; oa.maxNodeCap = h->maxNodeCap;
     for (int l = 0; l < oc.nlevels; ++l) {
@@ -421,6 +422,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     cudaFree(h->coef);
     cudaFree(h->fastCells);
     cudaFree(h->dbgBuf);
+    cudaFree(h->octClk);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->evStart) cudaEventDestroy(h->evStart);
     if (h->evStop) cudaEventDestroy(h->evStop);
@@ -704,6 +706,18 @@ int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* 
         return nb;
     }
     return 0;
+}
+
+int rumi_orb_debug_octree_clocks(rumi_orb* h, long long* out, int cap) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    const int n = 16 * kMaxLevels;
+    if (!h->octClk) { CU_TRY(cudaMalloc(&h->octClk, 8 * n)); CU_TRY(cudaMemset(h->octClk, 0, 8 * n)); CU_TRY(cudaDeviceSynchronize()); return 0; }
+    CU_TRY(cudaDeviceSynchronize());
+    if (out) CU_TRY(cudaMemcpy(out, h->octClk, 8 * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemset(h->octClk, 0, 8 * n));
+    CU_TRY(cudaDeviceSynchronize());
+    return n;
 }
 
 int rumi_orb_debug_candidates(rumi_orb* h, int level, int32_t* xyr, int cap) { return debug_list(h, level, xyr, cap, false); }

@@ -17,6 +17,8 @@
 //   D. survivors are emitted in raster order from the bitmap (popc prefix over bitmap words) into a block reserved
 //      with one atomicAdd per cell.  The octree kernel later walks the cells in the reference's row-major order, so
 //      the result does not depend on the order of those reservations.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "orb_math.cuh"
 
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                                                                   const __grid_constant__ OrbConst oc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cellId = blockIdx.x * kFastWarps + warp;
+    const int cellId = blockIdx.x * (blockDim.x >> 5) + warp;
     const int f = blockIdx.y;
     if (cellId >= oc.totalCells) return;
 
@@ -333,11 +335,16 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
 }
 
 void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s) {
-    const size_t smem = fast_warp_bytes(a.tilePitch, a.tileRows, a.scoreRows, a.maskWords) * kFastWarps;
-    dim3 grid((oc.totalCells + kFastWarps - 1) / kFastWarps, a.cv.nframes);
+    static int warps = 0;                      // warps (= cells) per CTA; RUMI_FAST_WARPS overrides for experiments
+    if (!warps) {
+        const char* e = getenv("RUMI_FAST_WARPS");
+        warps = e && e[0] >= '1' && e[0] <= '0' + kFastWarps ? e[0] - '0' : kFastWarps;
+    }
+    const size_t smem = fast_warp_bytes(a.tilePitch, a.tileRows, a.scoreRows, a.maskWords) * warps;
+    dim3 grid((oc.totalCells + warps - 1) / warps, a.cv.nframes);
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kernel<<<grid, kFastWarps * 32, smem, s>>>(a, oc);
+        kernel<<<grid, warps * 32, smem, s>>>(a, oc);
     };
     switch (a.tilePitch) {
         case 64: go(fast_kernel<64>); break;

@@ -69,6 +69,8 @@ struct OctreeArgs {
     int bigKeysCap[kMaxLevels];              // pow2 capacity per (level, frame)
     uint32_t* sel;           // [frame][kpCap] packed selected candidates, level order
     int* selCount;           // [frame][nlevels]
+    long long* dbgClk;       // optional [nlevels][16] phase cycle counters of frame 0 (profiling hook)
+    int levelFirst;          // level of blockIdx.y == 0 (0 unless the launch is split per level)
     int smemKeys;            // keys that fit the shared-memory sort buffer
     int maxNodeCap;
 };

@@ -2,6 +2,8 @@
 // The algorithm itself lives in octree_core.cuh (shared with the host test harness); this file gathers the
 // FAST candidates in the reference's insertion order (cell-row-major, raster inside a cell, :800-806), carves the
 // work buffers out of shared memory (or a global scratch for pathological candidate counts) and runs it.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "octree_core.cuh"
 
@@ -9,14 +11,128 @@ namespace rumi {
 
 constexpr int kOctThreads = 256;
 
+// Block-wide ascending sort of n u64 keys (n a power of two, E <= n <= E * blockDim.x) held E per thread in REGISTERS:
+// a bitonic network whose stages with partner distance j < E are pure register compare-exchanges, E <= j < 32 E are
+// warp shuffles, and only j >= 32 E go through shared memory with block barriers (6 of the 66 stages for 2048 keys).
+// A lone warp walking a shared-memory network pays a dependent ~500-cycle round trip per stage; here the E
+// exchanges of a stage are independent instructions.
+template <int E>
+__device__ void block_sort_regs(uint64_t* a, int n, int tid) {
+    const int T = n / E;                                   // threads that hold data
+    const bool active = tid < T;
+    uint64_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) v[r] = active ? a[tid * E + r] : ~0ull;
+    for (int k = 2; k <= n; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 32 * E; j >>= 1) {                     // partner in another warp: through shared memory
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) a[tid * E + r] = v[r];
+            }
+            __syncthreads();
+            if (active) {
+                const int pt = tid ^ (j / E);
+                const bool lower = (tid & (j / E)) == 0;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const uint64_t o = a[pt * E + r];
+                    const bool up = (((tid * E + r) & k) == 0);
+                    const bool keepMin = lower == up;
+                    v[r] = ((v[r] < o) == keepMin) ? v[r] : o;
+                }
+            }
+        }
+        for (; j >= E; j >>= 1) {                          // partner in another lane: shuffles (all lanes take part)
+            const int lm = j / E;
+            const bool lower = (tid & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, v[r], lm);
+                const bool up = (((tid * E + r) & k) == 0);
+                const bool keepMin = lower == up;
+                v[r] = ((v[r] < o) == keepMin) ? v[r] : o;
+            }
+        }
+#pragma unroll
+        for (int js = E / 2; js > 0; js >>= 1) {           // partner in this thread: registers
+            if (js <= (k >> 1)) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & js) == 0) {
+                        const bool up = (((tid * E + r) & k) == 0);
+                        const uint64_t x = v[r], y = v[r | js];
+                        const bool sw = (x > y) == up;
+                        v[r] = sw ? y : x;
+                        v[r | js] = sw ? x : y;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) a[tid * E + r] = v[r];
+    }
+    __syncthreads();
+}
+
 struct BlockCtx {
     int tid, nthr;
+    long long* clk;          // optional phase clock accumulators (test / profiling hook), else nullptr
+    long long last;
+    // adds the cycles since the previous mark to accumulator `id` (thread 0 only)
+    __device__ __forceinline__ void mark(int id) {
+        if (clk && tid == 0) { const long long now = clock64(); clk[id] += now - last; last = now; }
+    }
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void sync_warp() { __syncwarp(); }
+    // ascending sort of n (power of two >= 8) u64 keys; everything written before the call is visible (callers sync)
+    __device__ __forceinline__ void sort_u64(uint64_t* a, int n) {
+        if (n <= 8 * nthr) block_sort_regs<8>(a, n, tid);
+        else if (n <= 16 * nthr) block_sort_regs<16>(a, n, tid);
+        else bitonic_sort_u64(*this, a, n);               // global-memory scratch for pathological candidate counts
+    }
+    __device__ __forceinline__ int warp_id() const { return tid >> 5; }
+    __device__ __forceinline__ int num_warps() const { return nthr >> 5; }
+    __device__ __forceinline__ int lane() const { return tid & 31; }
+    __device__ __forceinline__ int warp_size() const { return 32; }
     __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_min(int* p, int v) { atomicMin(p, v); }
+    // exclusive prefix sum of v over the block in thread order (+ block total); tmp holds >= nthr / 32 + 1 ints.
+    // Ends with a barrier, so everything written before the call is visible after it.
+    __device__ __forceinline__ int exclusive_scan(int v, int* tmp, int* total) {
+        const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        __syncthreads();                                   // tmp may still be read from a previous scan
+        if (lane == 31) tmp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = lane < nw ? tmp[lane] : 0;
+            int ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xFFFFFFFFu, ti, o);
+                if (lane >= o) ti += n;
+            }
+            if (lane < nw) tmp[lane] = ti - t;
+            if (lane == nw - 1) tmp[nw] = ti;
+        }
+        __syncthreads();
+        *total = tmp[nw];
+        return tmp[wid] + incl - v;
+    }
 };
 
 struct OctreeSmemLayout {
-    size_t keys, lkeys, glo, crlo, crcnt, pend, next, next2, meta, qbase, hist, part, scal, cellScan, total;
+    size_t keys, lkeys, glo, crlo, crcnt, pend, lsort, next, next2, meta, qbase, hist, part, scal, cellScan, total;
     int nodeCap, createCap, pendCap;
 };
 
@@ -31,6 +147,7 @@ __host__ __device__ inline OctreeSmemLayout octree_layout(int smemKeys, int maxN
     L.keys = o; o += 8ull * smemKeys;
     L.lkeys = o; o += 8ull * gpad;
     L.pend = o; o += 8ull * L.pendCap;
+    L.lsort = o; o += 8ull * L.pendCap;
     L.glo = o; o += 4ull * (maxNodeCap + 1);
     L.crlo = o; o += 4ull * L.createCap;
     L.crcnt = o; o += 4ull * L.createCap;
@@ -53,47 +170,66 @@ size_t octree_smem_bytes(int smemKeys, int maxNodeCap, int nthreads) {
 __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_constant__ OctreeArgs a,
                                                              const __grid_constant__ OrbConst oc) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int f = blockIdx.x, l = blockIdx.y;
+    const int f = blockIdx.x, l = blockIdx.y + a.levelFirst;
     const LevelGeom& g = oc.lv[l];
     const OctreeSmemLayout L = octree_layout(a.smemKeys, a.maxNodeCap, kOctThreads);
-    BlockCtx ctx{(int)threadIdx.x, kOctThreads};
+    BlockCtx ctx{(int)threadIdx.x, kOctThreads, (a.dbgClk && f == 0) ? a.dbgClk + 16 * l : nullptr, clock64()};
 
     const int M = a.levelCount[(long long)f * oc.nlevels + l];
     const uint32_t* cand = a.cand + a.candLevelOff[l] + (long long)f * g.candCap;
     uint32_t* ordered = a.candOrdered + a.candLevelOff[l] + (long long)f * g.candCap;
 
-    // ---- gather candidates in the reference's cell order: exclusive scan of the per-cell counts ----
+    // ---- gather candidates in the reference's cell order (cell-row-major, raster inside a cell, :800-806) ----
+    // exclusive scan of the per-cell counts -> first output index of every cell (kept in the not-yet-used key buffer),
+    // then one thread per OUTPUT element: binary search for its cell, independent loads batched four at a time.
     {
         int* scan = reinterpret_cast<int*>(smem + L.cellScan);
         const int ncell = g.nCols * g.nRows;
         const int* cc = a.cellCount + (long long)f * oc.totalCells + g.cellBase;
         const int* co = a.cellOff + (long long)f * oc.totalCells + g.cellBase;
+        int* cellDst = ncell + 1 <= 2 * a.smemKeys
+                           ? reinterpret_cast<int*>(smem + L.keys)
+                           : reinterpret_cast<int*>(a.bigKeys + a.bigKeysLevelOff[l] + (long long)f * a.bigKeysCap[l]);
         const int chunk = (ncell + kOctThreads - 1) / kOctThreads;
-        const int c0 = threadIdx.x * chunk, c1 = min(c0 + chunk, ncell);
+        const int c0 = min((int)threadIdx.x * chunk, ncell), c1 = min(c0 + chunk, ncell);
         int s = 0;
         for (int c = c0; c < c1; ++c) s += cc[c];
-        scan[threadIdx.x] = s;
+        int total;
+        int dst = ctx.exclusive_scan(s, scan, &total);
+        for (int c = c0; c < c1; ++c) { cellDst[c] = dst; dst += cc[c]; }
+        if (threadIdx.x == 0) cellDst[ncell] = M;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int run = 0;
-            for (int t = 0; t < kOctThreads; ++t) { const int v = scan[t]; scan[t] = run; run += v; }
-        }
-        __syncthreads();
-        int dst = scan[threadIdx.x];
-        for (int c = c0; c < c1; ++c) {
-            const int n = cc[c], o = co[c];
-            for (int k = 0; k < n; ++k) ordered[dst + k] = cand[o + k];
-            dst += n;
+        constexpr int U = 4;
+        for (int i0 = threadIdx.x; i0 < M; i0 += U * kOctThreads) {
+            uint32_t v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kOctThreads;
+                if (i < M) {
+                    int lo = 0, hi = ncell;                 // largest c with cellDst[c] <= i (empty cells share a start)
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (cellDst[mid] <= i) lo = mid; else hi = mid;
+                    }
+                    v[u] = cand[co[lo] + (i - cellDst[lo])];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * kOctThreads;
+                if (i < M) ordered[i] = v[u];
+            }
         }
         __syncthreads();
     }
 
     OctreeWork w;
-    const int Mpad = next_pow2(M > 1 ? M : 2);
+    const int Mpad = next_pow2(M > 8 ? M : 8);
     w.keys = Mpad <= a.smemKeys ? reinterpret_cast<uint64_t*>(smem + L.keys)
                                 : a.bigKeys + a.bigKeysLevelOff[l] + (long long)f * a.bigKeysCap[l];
     w.lkeys = reinterpret_cast<uint64_t*>(smem + L.lkeys);
     w.pend = reinterpret_cast<uint64_t*>(smem + L.pend);
+    w.lsort = reinterpret_cast<uint64_t*>(smem + L.lsort);
     w.glo = reinterpret_cast<uint32_t*>(smem + L.glo);
     w.cr_lo = reinterpret_cast<uint32_t*>(smem + L.crlo);
     w.cr_cnt = reinterpret_cast<uint32_t*>(smem + L.crcnt);
@@ -110,7 +246,10 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
     uint32_t* out = a.sel + (long long)f * oc.kpCap + g.kpBase;
     if (threadIdx.x == 0) w.scal[SC_NOUT] = 0;
     __syncthreads();
+    ctx.mark(10);
     distribute_quadtree(ctx, ordered, M, g.quota, g, w, out, slots);
+    ctx.mark(11);
+    if (ctx.clk && threadIdx.x == 0) { ctx.clk[12] = M; ctx.clk[13] = w.scal[SC_NOUT]; }
     __syncthreads();
     if (threadIdx.x == 0) a.selCount[(long long)f * oc.nlevels + l] = min(w.scal[SC_NOUT], slots);
 }
@@ -121,6 +260,16 @@ void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
+    }
+    static int split = -1;                      // RUMI_OCTREE_SPLIT=1: one launch per level (per-level timing under ncu)
+    if (split < 0) { const char* e = getenv("RUMI_OCTREE_SPLIT"); split = e && e[0] == '1'; }
+    if (split) {
+        for (int l = 0; l < oc.nlevels; ++l) {
+            OctreeArgs b = a;
+            b.levelFirst = l;
+            octree_kernel<<<dim3(a.nframes, 1), kOctThreads, smem, s>>>(b, oc);
+        }
+        return;
     }
     octree_kernel<<<dim3(a.nframes, oc.nlevels), kOctThreads, smem, s>>>(a, oc);
 }

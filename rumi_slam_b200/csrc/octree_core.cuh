@@ -67,6 +67,7 @@ struct OctreeWork {
     uint32_t* cr_lo;       // [createCap] nodes created by the sorted phase (range start)
     uint32_t* cr_cnt;      // [createCap] (count; 0 = erased)
     uint64_t* pend;        // [pendCap] sort elements: (count << 13 | UL.x) << 32 | node ref
+    uint64_t* lsort;       // [pendCap] scratch of the parallel stable rank sort
     uint32_t* next;        // [pendCap] node refs of the current round
     uint32_t* next2;       // [pendCap] node refs of the next round
     uint32_t* meta;        // [pendCap] per pending node: non-empty children | multi-key children << 4
@@ -82,20 +83,40 @@ enum { SC_TSTAR = 0, SC_PHASEB = 1, SC_G = 2, SC_NOUT = 3, SC_NCREATED = 4, SC_N
 constexpr uint32_t kRefListBit = 0x80000000u;        // node ref: bit 31 set -> position in the leaf list
 
 // ---- bitonic sort of n (power of two) u64 ascending; all threads of the block participate ----
+// Pair p of stage (k, j) touches elements i = ((p & ~(j-1)) << 1) | (p & (j-1)) and i | j.  Pairs are assigned to
+// warps in fixed ranges of kSortSegPairs, so every stage with j <= kSortSegPairs stays inside one warp's 2 *
+// kSortSegPairs elements and only needs a warp barrier; block barriers are left for the few stages with larger j
+// (6 instead of 66 for 2048 keys).
+constexpr int kSortSegPairs = 128;
+
+RUMI_HD void bitonic_cx(uint64_t* a, int p, int k, int j) {
+    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+    const int q = i | j;
+    const uint64_t x = a[i], y = a[q];
+    const bool up = (i & k) == 0;
+    if ((x > y) == up) { a[i] = y; a[q] = x; }
+}
+
 template <class Ctx>
 RUMI_HD void bitonic_sort_u64(Ctx& ctx, uint64_t* a, int n) {
+    const int half = n >> 1;
+    const int nseg = half > kSortSegPairs ? half / kSortSegPairs : 1;
     for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int p = ctx.tid; p < (n >> 1); p += ctx.nthr) {
-                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                const int q = i | j;
-                const uint64_t x = a[i], y = a[q];
-                const bool up = (i & k) == 0;
-                if ((x > y) == up) { a[i] = y; a[q] = x; }
-            }
+        int j = k >> 1;
+        for (; j > kSortSegPairs; j >>= 1) {                 // block-wide stages
             ctx.sync();
+            for (int p = ctx.tid; p < half; p += ctx.nthr) bitonic_cx(a, p, k, j);
+        }
+        if (k > 2 * kSortSegPairs) ctx.sync();               // the warp-local stages read what other warps wrote
+        for (int seg = ctx.warp_id(); seg < nseg; seg += ctx.num_warps()) {
+            const int pEnd = (seg + 1) * kSortSegPairs < half ? (seg + 1) * kSortSegPairs : half;
+            for (int jj = j; jj > 0; jj >>= 1) {
+                for (int p = seg * kSortSegPairs + ctx.lane(); p < pEnd; p += ctx.warp_size()) bitonic_cx(a, p, k, jj);
+                ctx.sync_warp();
+            }
         }
     }
+    ctx.sync();
 }
 
 RUMI_HD int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -198,9 +219,10 @@ RUMI_HD void insertion_sort(uint64_t* v, int first, int last) {
         }
     }
 }
-RUMI_HD void sort(uint64_t* v, int n) {
+// __introsort_loop only (the partitioning phase of std::sort): leaves segments of <= 16 elements unsorted
+RUMI_HD void introsort_loop(uint64_t* v, int n) {
     if (n < 2) return;
-    // __introsort_loop, with its tail recursion on the left part turned into an explicit stack of right parts
+    // tail recursion on the left part turned into an explicit stack of left parts
     int depth_limit = 2 * highest_bit((uint32_t)n);
     int stack_first[64], stack_last[64], stack_depth[64];
     int sp = 0;
@@ -223,13 +245,19 @@ RUMI_HD void sort(uint64_t* v, int n) {
         --sp;
         first = stack_first[sp]; last = stack_last[sp]; depth_limit = stack_depth[sp];
     }
-    // __final_insertion_sort
+}
+RUMI_HD void final_insertion_sort(uint64_t* v, int n) {
     if (n > 16) {
         insertion_sort(v, 0, 16);
         for (int i = 16; i != n; ++i) unguarded_linear_insert(v, i);
     } else {
         insertion_sort(v, 0, n);
     }
+}
+RUMI_HD void sort(uint64_t* v, int n) {
+    if (n < 2) return;
+    introsort_loop(v, n);
+    final_insertion_sort(v, n);
 }
 }  // namespace stdsort
 
@@ -251,7 +279,7 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                                  uint32_t* out, int outCap) {
     const int D = g.treeDepth;
     const int height = g.h - 2 * kMinBorder;
-    const int Mpad = next_pow2(M > 1 ? M : 2);
+    const int Mpad = next_pow2(M > 8 ? M : 8);
 
     // 1. keys
     for (int i = ctx.tid; i < Mpad; i += ctx.nthr) {
@@ -264,7 +292,9 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
     }
     for (int i = ctx.tid; i < 2 * (kMaxTreeDepth + 2); i += ctx.nthr) w.hist[i] = 0;
     ctx.sync();
-    bitonic_sort_u64(ctx, w.keys, Mpad);
+    ctx.mark(0);
+    ctx.sort_u64(w.keys, Mpad);
+    ctx.mark(1);
 
     // 2. closed-form level-synchronous phase
     int* histB = w.hist;                          // boundaries first visible at depth u
@@ -304,6 +334,7 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
         w.scal[SC_NCREATED] = 0;
     }
     ctx.sync();
+    ctx.mark(2);
     const int tstar = w.scal[SC_TSTAR];
     const int G = w.scal[SC_G];
     if (M == 0 || G == 0) return;
@@ -317,22 +348,17 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
             const int a = i == 0 ? 0 : first_diff_depth(key_code(w.keys[i - 1]), key_code(w.keys[i]), D);
             c += a <= tstar;
         }
-        w.part[ctx.tid] = c;
-        ctx.sync();
-        if (ctx.tid == 0) {
-            int s = 0;
-            for (int t = 0; t < ctx.nthr; ++t) { const int v = w.part[t]; w.part[t] = s; s += v; }
-            w.glo[G] = (uint32_t)M;
-        }
-        ctx.sync();
-        int r = w.part[ctx.tid];
+        int tot;
+        int r = ctx.exclusive_scan(c, w.part, &tot);
+        if (ctx.tid == 0) w.glo[G] = (uint32_t)M;
         for (int i = i0; i < i1; ++i) {
             const int a = i == 0 ? 0 : first_diff_depth(key_code(w.keys[i - 1]), key_code(w.keys[i]), D);
             if (a <= tstar) w.glo[r++] = (uint32_t)i;
         }
         ctx.sync();
     }
-    const int Gpad = next_pow2(G > 1 ? G : 2);
+    ctx.mark(3);
+    const int Gpad = next_pow2(G > 8 ? G : 8);
     for (int r = ctx.tid; r < Gpad; r += ctx.nthr) {
         uint64_t lk = ~0ull;
         if (r < G) {
@@ -353,7 +379,8 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
         w.lkeys[r] = lk;
     }
     ctx.sync();
-    bitonic_sort_u64(ctx, w.lkeys, Gpad);
+    ctx.sort_u64(w.lkeys, Gpad);
+    ctx.mark(4);
 
     // 4. sorted final phase.  Only the std::sort replay and the "split from the back until the quota is reached"
     //    scan are sequential (thread 0); everything around them -- sort keys, child ranges, node creation, list
@@ -377,18 +404,14 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                 const uint32_t r = (uint32_t)w.lkeys[G - 1 - i] & rankMask;
                 c += (w.glo[r + 1] - w.glo[r]) > 1;
             }
-            w.part[ctx.tid] = c;
-            ctx.sync();
+            int sum;
+            int pos = ctx.exclusive_scan(c, w.part, &sum);
             if (ctx.tid == 0) {
-                int sum = 0;
-                for (int t = 0; t < ctx.nthr; ++t) { const int v = w.part[t]; w.part[t] = sum; sum += v; }
                 w.scal[SC_NPEND] = sum;
                 w.scal[SC_SIZE] = G;
                 w.scal[SC_DEPTH] = tstar;
                 w.scal[SC_DONE] = 0;
             }
-            ctx.sync();
-            int pos = w.part[ctx.tid];
             for (int i = i0; i < i1; ++i) {
                 const int k = G - 1 - i;
                 const uint32_t r = (uint32_t)w.lkeys[k] & rankMask;
@@ -396,6 +419,7 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
             }
             ctx.sync();
         }
+        ctx.mark(5);
         uint32_t* cur = w.next;
         uint32_t* nxt = w.next2;
         while (true) {
@@ -423,27 +447,68 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                 w.meta[p] = ne | (nm << 4);
             }
             ctx.sync();
-            // (R2, R3) sequential: libstdc++ std::sort replay, then split from the back until size >= N
-            if (ctx.tid == 0) {
-                stdsort::sort(w.pend, npend);
-                int size = w.scal[SC_SIZE];
-                const int prev = size;
-                uint32_t cc = 0, mc = 0;
-                int J = 0;
-                for (int j = npend - 1; j >= 0; --j) {
-                    const uint32_t m = w.meta[(uint32_t)w.pend[j]];
-                    w.qbase[J++] = cc | (mc << 16);
-                    cc += m & 15u; mc += m >> 4;
-                    size += (int)(m & 15u) - 1;
-                    if (size >= N) break;
+            ctx.mark(6);
+            // (R2) libstdc++ std::sort replay.  Only __introsort_loop (the partitioning) is order dependent and runs on
+            // thread 0.  __final_insertion_sort is a STABLE sort of whatever the partitioning left (strict '<' in
+            // __unguarded_linear_insert, and an element smaller than the current minimum goes to the front), so its
+            // result is reproduced in parallel: position = #(smaller keys) + #(equal keys that sit earlier).
+            if (ctx.tid == 0) stdsort::introsort_loop(w.pend, npend);
+            ctx.sync();
+            {
+                uint64_t* sorted = w.lsort;
+                for (int i = ctx.tid; i < npend; i += ctx.nthr) {
+                    const uint64_t e = w.pend[i];
+                    const uint32_t ke = (uint32_t)(e >> 32);
+                    int rank = 0;
+                    for (int j = 0; j < npend; ++j) {
+                        const uint32_t kj = (uint32_t)(w.pend[j] >> 32);
+                        rank += (kj < ke) || (kj == ke && j < i);
+                    }
+                    sorted[rank] = e;
                 }
-                w.scal[SC_J] = J;
-                w.scal[SC_SIZE] = size;
-                w.scal[SC_NEWC] = (int)cc;
-                w.scal[SC_NEWM] = (int)mc;
-                w.scal[SC_DONE] = (size >= N || size == prev) ? 1 : 0;
+                ctx.sync();
+                for (int i = ctx.tid; i < npend; i += ctx.nthr) w.pend[i] = sorted[i];
+                if (ctx.tid == 0) w.scal[SC_J] = npend;
+                ctx.sync();
+            }
+            // (R3) split from the back of the sorted array until size >= N: prefix sums over the processing order q
+            // (q-th processed = sorted position npend-1-q) of the children each split creates.
+            {
+                const int size0 = w.scal[SC_SIZE];
+                const int chunk = (npend + ctx.nthr - 1) / ctx.nthr;
+                const int q0 = ctx.tid * chunk < npend ? ctx.tid * chunk : npend;
+                const int q1 = q0 + chunk < npend ? q0 + chunk : npend;
+                uint32_t loc = 0;
+                for (int q = q0; q < q1; ++q) {
+                    const uint32_t m = w.meta[(uint32_t)w.pend[npend - 1 - q]];
+                    loc += (m & 15u) | ((m >> 4) << 16);
+                }
+                int tot;
+                uint32_t run = (uint32_t)ctx.exclusive_scan((int)loc, w.part, &tot);
+                for (int q = q0; q < q1; ++q) {
+                    const uint32_t m = w.meta[(uint32_t)w.pend[npend - 1 - q]];
+                    w.qbase[q] = run;                                  // created before q | multi-key before q << 16
+                    run += (m & 15u) | ((m >> 4) << 16);
+                    // size after processing q = size0 + (children created so far) - (nodes split so far)
+                    if (size0 + (int)(run & 0xFFFFu) - (q + 1) >= N) ctx.atomic_min(&w.scal[SC_J], q + 1);
+                }
+                ctx.sync();
+                const int J = w.scal[SC_J];
+                if (J > 0 && J - 1 >= q0 && J - 1 < q1) {                  // owner of the last processed node
+                    const uint32_t m = w.meta[(uint32_t)w.pend[npend - J]];
+                    const uint32_t endRun = w.qbase[J - 1] + ((m & 15u) | ((m >> 4) << 16));
+                    const int size = size0 + (int)(endRun & 0xFFFFu) - J;
+                    w.scal[SC_SIZE] = size;
+                    w.scal[SC_NEWC] = (int)(endRun & 0xFFFFu);
+                    w.scal[SC_NEWM] = (int)(endRun >> 16);
+                    w.scal[SC_DONE] = (size >= N || size == size0) ? 1 : 0;
+                }
+                if (npend == 0 && ctx.tid == 0) {
+                    w.scal[SC_NEWC] = 0; w.scal[SC_NEWM] = 0; w.scal[SC_DONE] = 1;
+                }
             }
             ctx.sync();
+            ctx.mark(7);
             // (R4) create the children of the J split nodes (processing order = from the back of the sorted array)
             const int J = w.scal[SC_J];
             const int cbase0 = w.scal[SC_NCREATED];
@@ -494,6 +559,7 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                 w.scal[SC_DEPTH] = depth + 1;
             }
             ctx.sync();
+            ctx.mark(8);
             if (w.scal[SC_DONE]) break;
             uint32_t* tmp = cur; cur = nxt; nxt = tmp;
         }
@@ -521,20 +587,15 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
         int c = 0;
         uint64_t v;
         for (int i = i0; i < i1; ++i) c += leaf(i, v) ? 1 : 0;
-        w.part[ctx.tid] = c;
-        ctx.sync();
-        if (ctx.tid == 0) {
-            int sum = 0;
-            for (int t = 0; t < ctx.nthr; ++t) { const int x = w.part[t]; w.part[t] = sum; sum += x; }
-            w.scal[SC_NOUT] = sum;
-        }
-        ctx.sync();
-        int pos = w.part[ctx.tid];
+        int sum;
+        int pos = ctx.exclusive_scan(c, w.part, &sum);
+        if (ctx.tid == 0) w.scal[SC_NOUT] = sum;
         for (int i = i0; i < i1; ++i)
             if (leaf(i, v)) w.pend[pos++] = v;
     }
     ctx.sync();
 
+    ctx.mark(9);
     // 5. best response per leaf; ties keep the first candidate in insertion order
     const int nout = w.scal[SC_NOUT] < outCap ? w.scal[SC_NOUT] : outCap;
     for (int k = ctx.tid; k < nout; k += ctx.nthr) {

@@ -15,7 +15,16 @@ using namespace rumi;
 struct HostCtx {
     int tid = 0, nthr = 1;
     void sync() {}
+    void sync_warp() {}
+    void sort_u64(uint64_t* a, int n) { std::sort(a, a + n); }
+    int warp_id() const { return 0; }
+    int num_warps() const { return 1; }
+    int lane() const { return 0; }
+    int warp_size() const { return 1; }
     int atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+    int exclusive_scan(int v, int*, int* total) { *total = v; return 0; }
+    void mark(int) {}
+    void atomic_min(int* p, int v) { if (v < *p) *p = v; }
 };
 
 extern "C" {
@@ -68,10 +77,11 @@ int hh_octree(int W, int H, int nfeatures, float scale, int nlevels, int level, 
     OctreeWork w;
     const int nodeCap = std::max(N, 4 * g.nIni) + 4;
     w.nodeCap = nodeCap; w.createCap = 3 * nodeCap + 16; w.pendCap = 2 * nodeCap + 16;
-    std::vector<uint64_t> keys(next_pow2(std::max(M, 2))), lkeys(next_pow2(nodeCap)), pend(w.pendCap);
+    std::vector<uint64_t> keys(next_pow2(std::max(M, 8))), lkeys(next_pow2(std::max(nodeCap, 8))), pend(w.pendCap), lsort(w.pendCap);
     std::vector<uint32_t> glo(nodeCap + 1), crlo(w.createCap), crcnt(w.createCap), next(w.pendCap), next2(w.pendCap), meta(w.pendCap), qbase(w.pendCap);
     std::vector<int> hist(2 * (kMaxTreeDepth + 2)), part(2), scal(SC_COUNT);
     w.keys = keys.data(); w.lkeys = lkeys.data(); w.glo = glo.data(); w.cr_lo = crlo.data(); w.cr_cnt = crcnt.data();
+    w.lsort = lsort.data();
     w.pend = pend.data(); w.next = next.data(); w.next2 = next2.data(); w.meta = meta.data(); w.qbase = qbase.data(); w.hist = hist.data(); w.part = part.data(); w.scal = scal.data();
     HostCtx ctx;
     distribute_quadtree(ctx, cand, M, N, g, w, out, outCap);

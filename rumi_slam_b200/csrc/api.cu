@@ -85,6 +85,8 @@ struct Workspace {
     CUtensorMap tmap[kMaxLevels];      // tmap[l]: source map (internal level l-1) used to produce level l
     bool tmapOk[kMaxLevels];
     int lastFrames = 0;
+    int* pyrFlags = nullptr;           // [chunk][marchItems] completion epochs of the marching pyramid's work items
+    int pyrEpoch = 0;
 };
 
 }  // namespace
@@ -108,9 +110,17 @@ struct rumi_orb {
     long long pyrBytes = 0, candElems = 0, bigKeysElems = 0;
     int fastTilePitch = 0, fastTileRows = 0, fastScoreRows = 0, fastMaskWords = 0;
     FastCell* fastCells = nullptr;                    // [totalCells] cell geometry of all levels
+    // marching pyramid (K1'): per-level column-group / row tables, work-item geometry
+    bool useMarch = true, marchOk = false;
+    int marchSplit = kMaxLevels;                      // levels below this get their own launch, the rest is chained
+                                                      // inside one launch (RUMI_PYRAMID_SPLIT; measured: separate wins)
+    uint8_t* marchTables = nullptr;
+    PyrMarchLevel marchLv[kMaxLevels];
+    int marchItems = 0;
     int smemKeys = 4096, maxNodeCap = 0;
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
+    bool nwsSet = false;           // RUMI_STREAMS given: use it for every path
     int lastWs = 0;
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
@@ -131,7 +141,7 @@ namespace {
 void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
     cudaFree(w.levelCount); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
-    cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono);
+    cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono); cudaFree(w.pyrFlags);
     cudaStream_t s = w.stream;
     w = Workspace();
     w.stream = s;
@@ -165,6 +175,9 @@ int alloc_workspace(rumi_orb* h, Workspace& w) {
     CU_TRY(cudaMalloc(&w.desc, 32 * n * oc.kpCap));
     CU_TRY(cudaMalloc(&w.nkp, 4 * n));
     CU_TRY(cudaMalloc(&w.nmono, 4 * n));
+    CU_TRY(cudaMalloc(&w.pyrFlags, 4 * n * std::max(h->marchItems, 1)));
+    CU_TRY(cudaMemsetAsync(w.pyrFlags, 0, 4 * n * std::max(h->marchItems, 1), w.stream));
+    w.pyrEpoch = 0;
     // the workspace streams are non-blocking: a legacy-stream memset would not be ordered before the first upload
     CU_TRY(cudaMemsetAsync(w.pyr, 0, h->pyrBytes, w.stream));
     CU_TRY(cudaMemsetAsync(w.blur, 0, h->pyrBytes, w.stream));
@@ -189,8 +202,10 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
     }
     cudaFree(h->coef);
     cudaFree(h->fastCells);
+    cudaFree(h->marchTables);
     h->coef = nullptr;
     h->fastCells = nullptr;
+    h->marchTables = nullptr;
     h->oc = oc;
     h->W = W; h->H = H;
     // resize coefficient tables + per-level source box of a 64x32 tile
@@ -223,6 +238,68 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         CU_TRY(cudaMalloc(&h->coef, sizeof(ResizeCoef)));
     }
     for (int l = 1; l < oc.nlevels; ++l) { h->xc[l] = h->coef + xo[l]; h->yc[l] = h->coef + yo[l]; }
+    // marching pyramid tables: per group of 4 destination columns the 8-byte source window (first word, alignment
+    // shift, byte selectors, weights), per destination row the two source rows and the vertical weights << 16
+    {
+        std::vector<uint8_t> blob;
+        std::vector<size_t> colOff(oc.nlevels, 0), rowOff(oc.nlevels, 0);
+        bool ok = oc.nlevels > 1;
+        int items = 0;
+        for (int l = 1; l < oc.nlevels && ok; ++l) {
+            const LevelGeom &sg = oc.lv[l - 1], &dg = oc.lv[l];
+            AxisCoef cx = make_axis_coef(sg.w, dg.w), cy = make_axis_coef(sg.h, dg.h);
+            const int groups = (dg.w + 3) / 4;
+            std::vector<PyrColGroup> cols(groups);
+            for (int g = 0; g < groups; ++g) {
+                PyrColGroup& c = cols[g];
+                const int s0 = cx.ofs[std::min(4 * g, dg.w - 1)];
+                c.word0 = (uint16_t)(s0 >> 2); c.shift = (uint8_t)(8 * (s0 & 3)); c.pad = 0;
+                uint32_t sel = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int x = std::min(4 * g + k, dg.w - 1);
+                    const int i0 = cx.ofs[x] - s0, i1 = std::min(cx.ofs[x] + 1, sg.w - 1) - s0;
+                    if (i0 < 0 || i1 > 7) ok = false;                 // scale factor > 2: tile kernel handles it
+                    sel |= (uint32_t)((i0 & 15) | ((i1 & 15) << 4)) << (8 * k);
+                    c.coef[k] = (uint32_t)(uint16_t)cx.a0[x] | ((uint32_t)(uint16_t)cx.a1[x] << 16);
+                }
+                c.sel01 = (uint16_t)(sel & 0xFFFFu); c.sel23 = (uint16_t)(sel >> 16);
+            }
+            std::vector<PyrRow> rows(dg.h);
+            for (int y = 0; y < dg.h; ++y) {
+                rows[y].sy0 = cy.ofs[y];
+                rows[y].sy1 = (uint16_t)std::min(cy.ofs[y] + 1, sg.h - 1);
+                rows[y].b0s = (uint32_t)cy.a0[y] << 16;
+                rows[y].b1s = (uint32_t)cy.a1[y] << 16;
+            }
+            blob.resize((blob.size() + 15) & ~(size_t)15);
+            colOff[l] = blob.size();
+            blob.insert(blob.end(), (uint8_t*)cols.data(), (uint8_t*)(cols.data() + groups));
+            blob.resize((blob.size() + 15) & ~(size_t)15);
+            rowOff[l] = blob.size();
+            blob.insert(blob.end(), (uint8_t*)rows.data(), (uint8_t*)(rows.data() + dg.h));
+            PyrMarchLevel& m = h->marchLv[l];
+            m.groups = groups;
+            m.nColBlocks = (groups + 31) / 32;
+            // every item marches its rows serially, so the dependent chain of levels costs (levels x item time): the
+            // small levels get shorter strips (more, shorter items)
+            const long long px = (long long)dg.w * dg.h;
+            m.stripRows = px >= 120000 ? kPyrStripRows : px >= 50000 ? kPyrStripRows / 2 : kPyrStripRows / 4;
+            m.nStrips = (dg.h + m.stripRows - 1) / m.stripRows;
+            m.itemBase = items; items += m.nColBlocks * m.nStrips;
+            m.srcLastWord = (sg.w - 1) >> 2;
+        }
+        h->marchOk = ok;
+        h->marchItems = ok ? items : 0;
+        if (ok) {
+            CU_TRY(cudaMalloc(&h->marchTables, blob.size()));
+            CU_TRY(cudaMemcpy(h->marchTables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+            CU_TRY(cudaDeviceSynchronize());
+            for (int l = 1; l < oc.nlevels; ++l) {
+                h->marchLv[l].cols = reinterpret_cast<const PyrColGroup*>(h->marchTables + colOff[l]);
+                h->marchLv[l].rows = reinterpret_cast<const PyrRow*>(h->marchTables + rowOff[l]);
+            }
+        }
+    }
     // level-major workspace offsets for `chunk` frames
     long long pb = 0, ce = 0, be = 0;
     int tp = 0, tr = 0, sr = 0, hc = 0, nodeCap = 0;
@@ -308,6 +385,26 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     }
     CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
     if (h->profile) prof_event(h, s);
+    // K1': all levels in one launch when every source can be read as aligned 32-bit words (always true for the
+    // internal buffers; caller device memory only if it is 4-byte aligned with readable row padding)
+    bool march = h->useMarch && h->marchOk && oc.nlevels > 1;
+    if (march && !l0Internal)
+        march = ((((uintptr_t)l0.ptr | (uintptr_t)l0.pitch | (uintptr_t)l0.stride) & 3) == 0) &&
+                l0.stride >= 4 * (h->marchLv[1].srcLastWord + 1);
+    int pyrLaunches = oc.nlevels - 1;
+    if (march) {
+        PyrMarchArgs ma;
+        ma.cv = cv;
+        for (int l = 0; l < kMaxLevels; ++l) ma.lv[l] = h->marchLv[l];
+        ma.nlevels = oc.nlevels; ma.itemsPerFrame = h->marchItems;
+        ma.flags = w.pyrFlags; ma.epoch = ++w.pyrEpoch;
+        // levels [1, split) one launch each (large, throughput bound); levels [split, n) chained inside one launch
+        // (small, latency bound: the chain hides their launch gaps)
+        const int split = std::min(std::max(h->marchSplit, 1), oc.nlevels);
+        pyrLaunches = 0;
+        for (int l = 1; l < split; ++l) { ma.levelFirst = ma.levelLast = l; launch_pyramid_march(ma, s); ++pyrLaunches; }
+        if (split < oc.nlevels) { ma.levelFirst = split; ma.levelLast = oc.nlevels - 1; launch_pyramid_march(ma, s); ++pyrLaunches; }
+    } else
     for (int l = 1; l < oc.nlevels; ++l) {
         PyramidLevelArgs pa;
         pa.src = cv.src[l - 1]; pa.dst = cv.src[l];
@@ -325,7 +422,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         }
         launch_pyramid_level(pa, tm, s);
     }
-    prof_mark(h, s, ST_PYRAMID, oc.nlevels - 1);
+    prof_mark(h, s, ST_PYRAMID, pyrLaunches);
     FastArgs fa;
     fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
     fa.cells = h->fastCells;
@@ -405,8 +502,12 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     h->tables = make_scale_tables(nfeatures, scale_factor, nlevels);
     const char* e = getenv("RUMI_NO_TMA");
     h->useTMA = !(e && e[0] == '1');
+    const char* pm = getenv("RUMI_PYRAMID");                     // "march" (default) | "tiles" (TMA / plain tile kernel)
+    h->useMarch = !(pm && pm[0] == 't') && h->useTMA;            // RUMI_NO_TMA=1 selects the plain tile kernel
+    const char* ps = getenv("RUMI_PYRAMID_SPLIT");
+    if (ps && ps[0] >= '1' && ps[0] <= '9') h->marchSplit = ps[0] - '0';
     const char* ns = getenv("RUMI_STREAMS");
-    if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) h->nws = ns[0] - '0';
+    if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) { h->nws = ns[0] - '0'; h->nwsSet = true; }
     *out = h;
     return RUMI_OK;
 }
@@ -421,6 +522,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     }
     cudaFree(h->coef);
     cudaFree(h->fastCells);
+    cudaFree(h->marchTables);
     cudaFree(h->dbgBuf);
     cudaFree(h->octClk);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
@@ -518,6 +620,7 @@ int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t st
     CU_TRY(cudaMemcpyAsync(&counts[1], ws.nmono, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaStreamSynchronize(ws.stream));
     if (h->useTMA && read_tma_timeout_flag() != 0) return fail(RUMI_ERR_CUDA, "TMA transaction timed out");
+    if (h->useMarch && read_pyramid_wait_timeout_flag() != 0) return fail(RUMI_ERR_CUDA, "pyramid level dependency timed out");
     *n_kp = counts[0]; *n_mono = counts[1];
     const int m = std::min(counts[0], cap);
     if (m > 0) {
@@ -541,8 +644,12 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
     if (cap_per_frame < h->oc.kpCap)
         return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, h->oc.kpCap);
     const int nchunks = (n + h->chunk - 1) / h->chunk;
+    // resident input: two workspaces are enough to overlap the latency-bound kernels of one chunk with the
+    // throughput-bound ones of the next (measured: 2 streams 118k frames/s, 4 streams 110k -- more chunks in flight
+    // only thrash L2); the host path keeps nws workspaces because it also has copies to hide
+    const int nws = h->nwsSet ? h->nws : std::min(h->nws, 2);
     for (int c = 0; c < nchunks; ++c) {
-        const int wi = c % h->nws;
+        const int wi = c % nws;
         if ((rc = ensure_workspace(h, wi))) return rc;
         Workspace& ws = h->ws[wi];
         const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);

@@ -37,6 +37,40 @@ struct PyramidLevelArgs {
 
 void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap /* nullptr = plain loads */,
                           cudaStream_t s);
+// ---- K1', the default pyramid path: register-marching warps, all levels of a chunk in ONE launch ----
+// Per group of 4 destination columns: where the 8-byte source window starts and how its bytes map to the outputs.
+struct alignas(8) PyrColGroup {
+    uint16_t word0;          // first 32-bit source word of the window
+    uint8_t shift;           // 8 * (source byte offset & 3): funnel shift that aligns the window
+    uint8_t pad;
+    uint16_t sel01, sel23;   // PRMT selectors: (p0,p1) of outputs 0|1 and 2|3 as bytes of one register each
+    uint32_t coef[4];        // a0 | a1 << 16 (11-bit fixed-point weights) per output
+};
+struct PyrRow { uint16_t sy0, sy1; uint32_t b0s, b1s; };     // source rows and vertical weights << 16
+
+constexpr int kPyrStripRows = 32, kPyrBlockCols = 128, kPyrMarchWarps = 4;
+
+struct PyrMarchLevel {                                        // destination level l (source = level l-1)
+    const PyrColGroup* cols;   // [groups]
+    const PyrRow* rows;        // [dst.h]
+    int groups;                // ceil(dst.w / 4)
+    int nColBlocks, nStrips;   // work items of this level = nColBlocks * nStrips
+    int stripRows;             // destination rows per item (<= kPyrStripRows; smaller on the small levels)
+    int itemBase;              // first item of this level inside a frame
+    int srcLastWord;           // last readable 32-bit word of a source row
+    int blockBase, blocksPerFrame;   // filled per launch: first CTA of this level, CTAs per frame
+};
+struct PyrMarchArgs {
+    ChunkView cv;
+    PyrMarchLevel lv[kMaxLevels];
+    int nlevels, itemsPerFrame;
+    int levelFirst, levelLast; // destination levels produced by this launch (chained through the flags)
+    int* flags;                // [frame][itemsPerFrame] completion epoch of every item
+    int epoch;
+};
+void launch_pyramid_march(const PyrMarchArgs& a, cudaStream_t s);
+int read_pyramid_wait_timeout_flag();
+
 int read_tma_timeout_flag();     // 1 = a TMA load timed out since the module was loaded, -1 = query failed
 void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s);
 

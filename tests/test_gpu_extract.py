@@ -18,13 +18,16 @@ def make(nf, **kw):
 
 
 @pytest.mark.parametrize("w,h,nf", SHAPES)
-@pytest.mark.parametrize("tma", [True, False])
-def test_pyramid_and_blur_bitexact(oracle, w, h, nf, tma):
-    os.environ["RUMI_NO_TMA"] = "0" if tma else "1"
+@pytest.mark.parametrize("mode", ["march", "tma", "plain"])
+def test_pyramid_and_blur_bitexact(oracle, w, h, nf, mode):
+    # march = register-marching all-level kernel (default); tma / plain = the tile kernel with / without TMA staging
+    os.environ["RUMI_PYRAMID"] = "march" if mode == "march" else "tiles"
+    os.environ["RUMI_NO_TMA"] = "1" if mode == "plain" else "0"
     try:
         ex = make(nf)
     finally:
         os.environ["RUMI_NO_TMA"] = "0"
+        os.environ["RUMI_PYRAMID"] = "march"
     img = synthetic_frame(11, w, h)
     ex(img)
     ref = oracle.pyramid(img)

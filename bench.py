@@ -191,8 +191,6 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ex.launch_count(reset=True)
-    ex.profile(True)
-    ex.profile_read(reset=True)
     barrier()
     t_a = time.perf_counter()
     ex.timer_start()
@@ -203,8 +201,23 @@ def run_b200(args):
     windows.append((t_a, time.perf_counter()))
     ms = max_over_ranks(ms)
     launches = ex.launch_count(reset=True)
+    # per-stage durations: a second pass of the SAME work on ONE stream, so that the CUDA-event span of a stage is
+    # exclusive (in the timed region above chunks alternate between streams and stages of neighbouring chunks overlap)
+    psteps = max(2, args.steps // 2)
+    ex.set_streams(1)
+    ex.extract_batch_device(resident, out=out_dev, sync=True)
+    ex.profile(True)
+    ex.profile_read(reset=True)
+    t_a = time.perf_counter()
+    ex.timer_start()
+    for _ in range(psteps):
+        ex.extract_batch_device(resident, out=out_dev, sync=False)
+    ms_serial = ex.timer_stop()
+    windows.append((t_a, time.perf_counter()))
     stages = ex.profile_read(reset=True)
     ex.profile(False)
+    ex.set_streams(0)
+    ex.launch_count(reset=True)
     value = world * nframes * args.steps / (ms / 1e3)
     nkp_mean = float(out_dev[2].float().mean().item())
 
@@ -297,18 +310,34 @@ def run_b200(args):
     stage_rows = {}
     stages = {k: v for k, v in stages.items() if k in alg}      # h2d / d2h spans only exist in the e2e pass
     for name, (sms, nl) in stages.items():
-        by = alg[name] * nframes * args.steps                  # bytes this stage moved algorithmically in the region
+        by = alg[name] * nframes * psteps                      # bytes this stage moved algorithmically in the pass
         gbs = by / (sms / 1e3) / 1e9 if sms > 0 else 0.0
         stage_rows[name] = {"ms": round(sms, 3), "share": round(sms / total_stage_ms, 4), "launches": nl,
                             "alg_GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)}
     dom = max(stages, key=lambda k: stages[k][0])
     dms, dn = stages[dom]
-    per_launch_bytes = alg[dom] * nframes * args.steps / max(dn, 1)
+    per_launch_bytes = alg[dom] * nframes * psteps / max(dn, 1)
     per_launch_s = dms / 1e3 / max(dn, 1)
     achieved = per_launch_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch (one chunk) from the committed ncu --set full capture
+    traffic, ncu_ctx = None, None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")))
+        k = ncu["kernels"].get(dom)
+        if k and ncu.get("frames_per_launch") == chunk:
+            traffic = int(k["dram_read_bytes"] + k["dram_write_bytes"])
+            ncu_ctx = {kk: k[kk] for kk in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "lsu_pipe_pct",
+                                            "warps_active_pct", "warp_instructions") if kk in k}
+            ncu_ctx["source"] = "profiles/r1_ncu_kernels.json (ncu --set full, %d-frame chunk)" % chunk
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(per_launch_bytes), "avg_launch_ms": round(per_launch_s * 1e3, 4),
+                "note": "the path is integer-issue bound, not HBM bound (SURVEY.md 8d): the dominant kernel's binding "
+                        "resource is the ALU pipe, see ncu",
+                "ncu": ncu_ctx,
+                "stage_pass": {"streams": 1, "steps": psteps, "ms_per_step": round(ms_serial / psteps, 3)},
                 "whole_step": {"algorithmic_bytes_per_frame": int(alg["frame"]),
                                "achieved": round(value * alg["frame"] / 1e9, 2),
                                "frac": round(value * alg["frame"] / 1e9 / hbm_peak, 5)},

@@ -101,6 +101,9 @@ int rumi_orb_timer_stop(rumi_orb* h, float* ms);
 /* Optional per-stage CUDA events around every launch group (0 pyramid, 1 FAST, 2 quad-tree, 3 slots, 4 blur,
  * 5 orientation+descriptors).  profile_read synchronises, accumulates and returns the number of stages. */
 int rumi_orb_profile(rumi_orb* h, int enable);
+/* Number of workspaces / CUDA streams consecutive chunks alternate between (1..4; 0 restores the default).  With 1 the
+ * stages of a chunk run back to back on one stream, which makes the per-stage event times exclusive. */
+int rumi_orb_set_streams(rumi_orb* h, int n);
 int rumi_orb_profile_read(rumi_orb* h, double* stage_ms, long long* stage_launches, int reset);
 /* Number of kernels this handle has launched (own kernels only; memsets / copies are not counted). */
 long long rumi_orb_launch_count(rumi_orb* h, int reset);

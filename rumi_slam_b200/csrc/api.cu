@@ -121,6 +121,7 @@ struct rumi_orb {
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
     bool nwsSet = false;           // RUMI_STREAMS given: use it for every path
+    int nwsDefault = 4; bool nwsSetDefault = false;
     int lastWs = 0;
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
@@ -508,6 +509,7 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     if (ps && ps[0] >= '1' && ps[0] <= '9') h->marchSplit = ps[0] - '0';
     const char* ns = getenv("RUMI_STREAMS");
     if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) { h->nws = ns[0] - '0'; h->nwsSet = true; }
+    h->nwsDefault = h->nws; h->nwsSetDefault = h->nwsSet;
     *out = h;
     return RUMI_OK;
 }
@@ -763,6 +765,17 @@ int rumi_orb_timer_stop(rumi_orb* h, float* ms) {
     CU_TRY(cudaEventRecord(h->evStop, h->ws[0].stream));
     CU_TRY(cudaEventSynchronize(h->evStop));
     CU_TRY(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+    return RUMI_OK;
+}
+
+int rumi_orb_set_streams(rumi_orb* h, int n) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    if (n < 0 || n > kMaxWs) return fail(RUMI_ERR_ARG, "streams must be 0..%d", kMaxWs);
+    CU_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < kMaxWs; ++i)
+        if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+    if (n == 0) { h->nws = h->nwsDefault; h->nwsSet = h->nwsSetDefault; }
+    else { h->nws = n; h->nwsSet = true; }
     return RUMI_OK;
 }
 

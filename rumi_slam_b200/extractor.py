@@ -161,6 +161,10 @@ class ORBextractor:
         check(self._L.rumi_orb_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def set_streams(self, n):
+        """n workspaces / streams for consecutive chunks (0 = default); 1 makes per-stage event times exclusive."""
+        check(self._L.rumi_orb_set_streams(self._h, int(n)))
+
     def profile(self, enable=True):
         check(self._L.rumi_orb_profile(self._h, 1 if enable else 0))
 

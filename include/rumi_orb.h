@@ -149,6 +149,33 @@ int rumi_stereo_match(rumi_match* m, rumi_orb* left, rumi_orb* right, const rumi
                       const rumi_kp* Rk, const uint8_t* Rd, int nR, float mbf, float mb, float* u_right, float* depth,
                       int* n_matched);
 
+/* ---- bag of words ----
+ * rumi_vocab = the DBoW2 vocabulary tree (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,
+ * R/include/cloud_edge_slam_lib/ORBVocabulary.h; R/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) resident on the
+ * device.  Nodes are given in id order exactly as loadFromTextFile (:1338-1421) reads them: node 0 is the root,
+ * parent[i] < i, is_leaf[i] is the file's leaf flag (word ids are handed out to flagged nodes in id order), desc is
+ * [nnodes][32], weight the node weight (WordValue = double). */
+typedef struct rumi_vocab rumi_vocab;
+int rumi_vocab_create(rumi_vocab** out, int device, int k, int L, int nnodes, const int32_t* parent,
+                      const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
+void rumi_vocab_destroy(rumi_vocab* v);
+int rumi_vocab_words(const rumi_vocab* v);
+/* Per-feature tree descent == TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup) (:1218-1258):
+ * word id and weight of the leaf reached, node id at depth L - levelsup (0 = root when that depth is <= 0).  Host
+ * buffers; the BowVector / FeatureVector maps of Frame::ComputeBoW are assembled from these by the caller. */
+int rumi_bow_transform(rumi_vocab* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight,
+                       int32_t* node_id);
+/* Same with device-resident descriptors and outputs (16-byte aligned descriptors). */
+int rumi_bow_transform_device(rumi_vocab* v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word_id,
+                              double* d_weight, int32_t* d_node_id, int sync);
+long long rumi_vocab_launch_count(rumi_vocab* v, int reset);
+/* ORBmatcher::SearchByBoW distance blocks (R/lib_src/ORBmatcher.cc:198-370).  segs[s] = {aStart, aCount, bStart,
+ * bCount, outOff}: features a_idx[aStart .. aStart+aCount) of A and b_idx[bStart ..) of B share vocabulary node s;
+ * dist[outOff + i * bCount + j] = DescriptorDistance(A[a_idx[aStart+i]], B[b_idx[bStart+j]]).  Host buffers. */
+int rumi_bow_node_distances(rumi_match* m, const uint8_t* descA, int nA, const uint8_t* descB, int nB,
+                            const int32_t* a_idx, int n_a_idx, const int32_t* b_idx, int n_b_idx,
+                            const int32_t* segs, int nseg, uint16_t* dist, long long ndist);
+
 /* ORBmatcher::DescriptorDistance for one pair (host inline popcount; the API, not a fallback). */
 int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b);
 

@@ -1,0 +1,218 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (used by tests/, __graft_entry__.smoke() and bench.py's CPU arm; never by the
+// product path).
+//
+// CPU restatement of the bag-of-words side of the matching path:
+//   * DBoW2 vocabulary tree descent -- TemplatedVocabulary::transform, R/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h
+//     :1218-1258 (per feature) and :1128-1200 (BowVector / FeatureVector assembly = Frame::ComputeBoW),
+//     tree built like loadFromTextFile (:1338-1421), distance = FORB::distance (FORB.cpp:81-101);
+//   * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) -- R/lib_src/ORBmatcher.cc:198-370, the Nleft == -1 branch,
+//     with ComputeThreeMaxima (:1787-1828).
+// Parity: PINNED.  The tree descent and the vector assembly are checked against the UNMODIFIED reference DBoW2
+// compiled over oracle/cvstub (oracle/_ref/librefbow.so, tests/test_bow_oracle.py) and against the frozen vectors
+// tests/golden/bow_kats.npz.  SearchByBoW needs KeyFrame / Frame / MapPoint (not compilable here): restated from the
+// cited lines and checked on hand-built known answers.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace {
+
+struct Node {
+    std::vector<int> children;
+    int parent = 0, word = 0;
+    double weight = 0.0;
+    uint8_t desc[32];
+};
+struct Vocab {
+    int k = 0, L = 0, scoring = 0, weighting = 0;
+    std::vector<Node> nodes;       // node 0 = root
+    int nwords = 0;
+};
+
+// FORB.cpp:81-101 (bit-parallel popcount per 32-bit word)
+int forb_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        std::memcpy(&x, a + 4 * i, 4); std::memcpy(&y, b + 4 * i, 4);
+        uint32_t v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+// TemplatedVocabulary.h:1218-1258
+void transform_one(const Vocab& v, const uint8_t* f, int levelsup, int& word, double& weight, int& nid) {
+    const int nid_level = v.L - levelsup;
+    nid = 0;                                           // root when nid_level <= 0 (:1228)
+    int final_id = 0, current_level = 0;
+    do {
+        ++current_level;
+        const std::vector<int>& nodes = v.nodes[final_id].children;
+        final_id = nodes[0];
+        double best_d = forb_distance(f, v.nodes[final_id].desc);
+        for (size_t i = 1; i < nodes.size(); ++i) {
+            const double d = forb_distance(f, v.nodes[nodes[i]].desc);
+            if (d < best_d) { best_d = d; final_id = nodes[i]; }
+        }
+        if (current_level == nid_level) nid = final_id;
+    } while (!v.nodes[final_id].children.empty());
+    word = v.nodes[final_id].word;
+    weight = v.nodes[final_id].weight;
+}
+
+}  // namespace
+
+extern "C" {
+
+// nodes 1..nnodes-1 in id order: parent id, leaf flag, 32-byte descriptor, weight  (loadFromTextFile :1377-1417)
+void* bow_oracle_create(int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
+                        const uint8_t* is_leaf, const uint8_t* desc, const double* weight) {
+    Vocab* v = new Vocab();
+    v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting;
+    v->nodes.resize(nnodes);
+    for (int nid = 1; nid < nnodes; ++nid) {
+        Node& n = v->nodes[nid];
+        n.parent = parent[nid];
+        v->nodes[parent[nid]].children.push_back(nid);
+        std::memcpy(n.desc, desc + 32 * (size_t)nid, 32);
+        n.weight = weight[nid];
+        if (is_leaf[nid]) n.word = v->nwords++;
+    }
+    return v;
+}
+void bow_oracle_free(void* p) { delete static_cast<Vocab*>(p); }
+
+int bow_oracle_transform(void* p, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight,
+                         int32_t* node) {
+    const Vocab& v = *static_cast<Vocab*>(p);
+    for (int i = 0; i < n; ++i) {
+        int w, nid; double val;
+        transform_one(v, desc + 32 * (size_t)i, levelsup, w, val, nid);
+        word[i] = w; weight[i] = val; node[i] = nid;
+    }
+    return 0;
+}
+
+// TemplatedVocabulary.h:1128-1200 flattened like oracle/ref_bow_shim.cpp's refbow_vectors
+int bow_oracle_vectors(void* p, const uint8_t* desc, int n, int levelsup, int32_t* bow_ids, double* bow_vals,
+                       int32_t* fv_nodes, int32_t* fv_off, int32_t* fv_idx, int* nfv) {
+    const Vocab& v = *static_cast<Vocab*>(p);
+    std::map<unsigned, double> bv;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    // ScoringObject.h:73-89: every scoring but DOT_PRODUCT (5) normalises; L2_NORM (1) with L2, the others with L1
+    const bool must = v.scoring != 5;
+    const bool l2 = v.scoring == 1;
+    const bool tf = v.weighting == 1 || v.weighting == 0;     // BowVector.h: TF_IDF = 0, TF = 1, IDF = 2, BINARY = 3
+    for (int i = 0; i < n; ++i) {
+        int w, nid; double val;
+        transform_one(v, desc + 32 * (size_t)i, levelsup, w, val, nid);
+        if (val > 0) {
+            if (tf) bv[(unsigned)w] += val;                               // addWeight (BowVector.cpp:34-46)
+            else if (!bv.count((unsigned)w)) bv[(unsigned)w] = val;       // addIfNotExist (:50-58)
+            fv[(unsigned)nid].push_back((unsigned)i);                     // addFeature (FeatureVector.cpp)
+        }
+    }
+    if (tf && !bv.empty() && !must) {
+        const double nd = (double)bv.size();
+        for (auto& e : bv) e.second /= nd;
+    }
+    if (must) {                                                           // BowVector::normalize (:62-84)
+        double norm = 0.0;
+        if (!l2) { for (auto& e : bv) norm += std::fabs(e.second); }
+        else { for (auto& e : bv) norm += e.second * e.second; norm = std::sqrt(norm); }
+        if (norm > 0.0) for (auto& e : bv) e.second /= norm;
+    }
+    int k = 0;
+    for (auto& e : bv) { bow_ids[k] = (int32_t)e.first; bow_vals[k] = e.second; ++k; }
+    int m = 0, o = 0;
+    for (auto& e : fv) {
+        fv_nodes[m] = (int32_t)e.first; fv_off[m] = o;
+        for (unsigned idx : e.second) fv_idx[o++] = (int32_t)idx;
+        ++m;
+    }
+    fv_off[m] = o;
+    *nfv = m;
+    return k;
+}
+
+// ORBmatcher::ComputeThreeMaxima, R/lib_src/ORBmatcher.cc:1787-1828
+static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), R/lib_src/ORBmatcher.cc:198-370, F.Nleft == -1.
+// Feature vectors are flattened (sorted node ids, offsets, feature indices).  kf_valid[i] != 0 <=> the keyframe
+// feature has a map point that is not bad (:227-233).  match_f[j] = keyframe feature matched to frame feature j or -1
+// (the reference stores the MapPoint*).  Returns nmatches.
+int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid,
+                             const int32_t* kf_nodes, const int32_t* kf_off, const int32_t* kf_idx, int kf_nnodes,
+                             const uint8_t* desc_f, const float* angle_f, int nf,
+                             const int32_t* f_nodes, const int32_t* f_off, const int32_t* f_idx, int f_nnodes,
+                             float nnratio, int check_ori, int th_low, int32_t* match_f) {
+    const int HISTO_LENGTH = 30;
+    for (int j = 0; j < nf; ++j) match_f[j] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < kf_nnodes && b < f_nnodes) {
+        if (kf_nodes[a] == f_nodes[b]) {
+            for (int iKF = kf_off[a]; iKF < kf_off[a + 1]; ++iKF) {
+                const int realIdxKF = kf_idx[iKF];
+                if (!kf_valid[realIdxKF]) continue;
+                const uint8_t* dKF = desc_kf + 32 * (size_t)realIdxKF;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = f_off[b]; iF < f_off[b + 1]; ++iF) {
+                    const int realIdxF = f_idx[iF];
+                    if (match_f[realIdxF] >= 0) continue;                         // :249
+                    const int dist = forb_distance(dKF, desc_f + 32 * (size_t)realIdxF);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) { bestDist2 = dist; }
+                }
+                if (bestDist1 <= th_low) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match_f[bestIdxF] = realIdxKF;
+                        if (check_ori) {
+                            float rot = angle_kf[realIdxKF] - angle_f[bestIdxF];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)std::round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(bestIdxF);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (kf_nodes[a] < f_nodes[b]) {
+            a = (int)(std::lower_bound(kf_nodes + a, kf_nodes + kf_nnodes, f_nodes[b]) - kf_nodes);
+        } else {
+            b = (int)(std::lower_bound(f_nodes + b, f_nodes + f_nnodes, kf_nodes[a]) - f_nodes);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { match_f[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+}  // extern "C"

@@ -5,18 +5,22 @@
 // primitives (resize, FAST, GaussianBlur, fastAtan2) are declared here and defined in oracle/ref_shim.cpp
 // by the cv2-pinned integer restatements of oracle/orb_oracle.cpp.
 #pragma once
+#include "core/persistence_stub.hpp"
 #include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 
 inline int cvRound(double v) { return (int)std::nearbyint(v); }
 inline int cvRound(float v) { return (int)std::nearbyintf(v); }
@@ -60,14 +64,16 @@ public:
     std::shared_ptr<std::vector<uchar>> buf;
 
     Mat() : rows(0), cols(0), step(0), data(nullptr) {}
-    Mat(int r, int c, int) { alloc(r, c); }
-    Mat(Size s, int) { alloc(s.height, s.width); }
-    void alloc(int r, int c) {
-        rows = r; cols = c; step = (size_t)c;
-        buf = std::make_shared<std::vector<uchar>>((size_t)r * c + 64);
+    Mat(int r, int c, int t) { alloc(r, c, t); }
+    Mat(Size s, int t) { alloc(s.height, s.width, t); }
+    // `step` is in bytes; CV_32F (only used by the DBoW2 FORB helpers) has 4-byte elements, everything else is 8U
+    void alloc(int r, int c, int t = CV_8U) {
+        rows = r; cols = c; step = (size_t)c * (t == CV_32F ? 4 : 1);
+        buf = std::make_shared<std::vector<uchar>>((size_t)r * step + 64);
         data = buf->data();
     }
-    void create(int r, int c, int) { if (data && r == rows && c == cols) return; alloc(r, c); }
+    void create(int r, int c, int t) { if (data && r == rows && c == cols && step == (size_t)c * (t == CV_32F ? 4 : 1)) return; alloc(r, c, t); }
+    void release() { rows = cols = 0; step = 0; data = nullptr; buf.reset(); }
     int type() const { return CV_8UC1; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     size_t step1() const { return step; }
@@ -83,6 +89,7 @@ public:
     uchar* ptr(int i = 0) { return data + (size_t)i * step; }
     const uchar* ptr(int i = 0) const { return data + (size_t)i * step; }
     template <typename T> T* ptr(int i = 0) { return (T*)(data + (size_t)i * step); }
+    template <typename T> const T* ptr(int i = 0) const { return (const T*)(data + (size_t)i * step); }
     Mat clone() const {
         Mat m(rows, cols, 0);
         for (int y = 0; y < rows; ++y) std::memcpy(m.ptr(y), ptr(y), cols);
@@ -92,7 +99,7 @@ public:
     // Mat = MatExpr: create() is a no-op for a same-shape buffer, then the buffer is filled in place.
     Mat& operator=(const ZerosExpr& z) {
         create(z.rows, z.cols, z.type);
-        for (int y = 0; y < rows; ++y) std::memset(ptr(y), 0, cols);
+        for (int y = 0; y < rows; ++y) std::memset(ptr(y), 0, step);
         return *this;
     }
     inline void copyTo(const _OutputArray& o) const;

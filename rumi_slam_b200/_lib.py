@@ -60,6 +60,14 @@ SIGNATURES = {
     "rumi_stereo_match": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp,
                                     _i32p]),
     "rumi_descriptor_distance": (C.c_int, [_vp, _vp]),
+    "rumi_vocab_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "rumi_vocab_destroy": (None, [_vp]),
+    "rumi_vocab_words": (C.c_int, [_vp]),
+    "rumi_vocab_launch_count": (C.c_longlong, [_vp, C.c_int]),
+    "rumi_bow_transform": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "rumi_bow_transform_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "rumi_bow_node_distances": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
+                                          _vp, C.c_longlong]),
 }
 
 

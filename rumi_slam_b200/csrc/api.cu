@@ -1121,3 +1121,166 @@ int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// bag of words
+struct rumi_vocab {
+    int device = 0, k = 0, L = 0, nnodes = 0, nwords = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t* blob = nullptr;           // every tree array in one allocation
+    rumi::BowTreeView view;
+    uint8_t* scratch = nullptr;        // host-call staging: descriptors + outputs
+    size_t scratchCap = 0;
+    long long launches = 0;
+};
+
+extern "C" {
+
+int rumi_vocab_create(rumi_vocab** out, int device, int k, int L, int nnodes, const int32_t* parent,
+                      const uint8_t* is_leaf, const uint8_t* desc, const double* weight) {
+    if (!out) return fail(RUMI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (nnodes < 2 || !parent || !is_leaf || !desc || !weight || k < 1 || L < 1) return fail(RUMI_ERR_ARG, "bad vocabulary");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RUMI_ERR_CUDA, "no CUDA device: librumi_orb has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RUMI_ERR_ARG, "device %d out of range", device);
+    // children in the reference's push_back order: node ids ascending under each parent (loadFromTextFile :1390)
+    std::vector<int32_t> cnt(nnodes, 0), start(nnodes, 0), ids(std::max(nnodes - 1, 1), 0), word(nnodes, 0);
+    for (int i = 1; i < nnodes; ++i) {
+        if (parent[i] < 0 || parent[i] >= i) return fail(RUMI_ERR_ARG, "node %d: parent %d must precede it", i, parent[i]);
+        ++cnt[parent[i]];
+    }
+    if (cnt[0] == 0) return fail(RUMI_ERR_ARG, "root has no children");
+    int run = 0;
+    for (int i = 0; i < nnodes; ++i) { start[i] = run; run += cnt[i]; }
+    std::vector<int32_t> fill(start);
+    for (int i = 1; i < nnodes; ++i) ids[fill[parent[i]]++] = i;
+    int nwords = 0;
+    for (int i = 1; i < nnodes; ++i)
+        if (is_leaf[i]) word[i] = nwords++;                       // :1405-1411
+    CU_TRY(cudaSetDevice(device));
+    rumi_vocab* v = new rumi_vocab();
+    v->device = device; v->k = k; v->L = L; v->nnodes = nnodes; v->nwords = nwords;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oDesc = 0, oStart = al(32 * (size_t)nnodes), oCnt = oStart + al(4 * (size_t)nnodes),
+                 oIds = oCnt + al(4 * (size_t)nnodes), oWord = oIds + al(4 * ids.size()),
+                 oW = oWord + al(4 * (size_t)nnodes), total = oW + al(8 * (size_t)nnodes);
+    if (cudaMalloc(&v->blob, total) != cudaSuccess) { delete v; return fail(RUMI_ERR_CUDA, "cudaMalloc(%zu) failed", total); }
+    cudaMemcpy(v->blob + oDesc, desc, 32 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->blob + oStart, start.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->blob + oCnt, cnt.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->blob + oIds, ids.data(), 4 * ids.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(v->blob + oWord, word.data(), 4 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    cudaMemcpy(v->blob + oW, weight, 8 * (size_t)nnodes, cudaMemcpyHostToDevice);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaFree(v->blob); delete v;
+        return fail(RUMI_ERR_CUDA, "vocabulary upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    v->view.k = k; v->view.L = L; v->view.nnodes = nnodes;
+    v->view.desc = v->blob + oDesc;
+    v->view.childStart = reinterpret_cast<const int32_t*>(v->blob + oStart);
+    v->view.childCount = reinterpret_cast<const int32_t*>(v->blob + oCnt);
+    v->view.childIds = reinterpret_cast<const int32_t*>(v->blob + oIds);
+    v->view.wordId = reinterpret_cast<const int32_t*>(v->blob + oWord);
+    v->view.weight = reinterpret_cast<const double*>(v->blob + oW);
+    *out = v;
+    return RUMI_OK;
+}
+
+void rumi_vocab_destroy(rumi_vocab* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+    cudaFree(v->blob); cudaFree(v->scratch);
+    delete v;
+}
+
+int rumi_vocab_words(const rumi_vocab* v) { return v ? v->nwords : 0; }
+
+long long rumi_vocab_launch_count(rumi_vocab* v, int reset) {
+    if (!v) return 0;
+    const long long n = v->launches;
+    if (reset) v->launches = 0;
+    return n;
+}
+
+int rumi_bow_transform_device(rumi_vocab* v, const uint8_t* d_desc, int n, int levelsup, int32_t* d_word_id,
+                              double* d_weight, int32_t* d_node_id, int sync) {
+    if (!v) return fail(RUMI_ERR_ARG, "vocabulary is NULL");
+    if (n < 0 || levelsup < 0) return fail(RUMI_ERR_ARG, "negative argument");
+    if (n == 0) return RUMI_OK;
+    if (!d_desc || !d_word_id || !d_weight || !d_node_id || ((uintptr_t)d_desc & 15))
+        return fail(RUMI_ERR_ARG, "NULL / unaligned device buffer");
+    CU_TRY(cudaSetDevice(v->device));
+    launch_bow_transform(v->view, d_desc, n, levelsup, d_word_id, d_weight, d_node_id, v->stream);
+    v->launches += 1;
+    CU_TRY(cudaGetLastError());
+    if (sync) CU_TRY(cudaStreamSynchronize(v->stream));
+    return RUMI_OK;
+}
+
+int rumi_bow_transform(rumi_vocab* v, const uint8_t* desc, int n, int levelsup, int32_t* word_id, double* weight,
+                       int32_t* node_id) {
+    if (!v) return fail(RUMI_ERR_ARG, "vocabulary is NULL");
+    if (n < 0 || levelsup < 0) return fail(RUMI_ERR_ARG, "negative argument");
+    if (n == 0) return RUMI_OK;
+    if (!desc || !word_id || !weight || !node_id) return fail(RUMI_ERR_ARG, "NULL buffer");
+    CU_TRY(cudaSetDevice(v->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oW = al(32 * (size_t)n), oWord = oW + al(8 * (size_t)n), oNode = oWord + al(4 * (size_t)n),
+                 need = oNode + al(4 * (size_t)n);
+    int rc = grow((void**)&v->scratch, &v->scratchCap, need);
+    if (rc) return rc;
+    double* dW = reinterpret_cast<double*>(v->scratch + oW);
+    int32_t* dWord = reinterpret_cast<int32_t*>(v->scratch + oWord);
+    int32_t* dNode = reinterpret_cast<int32_t*>(v->scratch + oNode);
+    CU_TRY(cudaMemcpyAsync(v->scratch, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, v->stream));
+    if ((rc = rumi_bow_transform_device(v, v->scratch, n, levelsup, dWord, dW, dNode, 0))) return rc;
+    CU_TRY(cudaMemcpyAsync(word_id, dWord, 4 * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
+    CU_TRY(cudaMemcpyAsync(weight, dW, 8 * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
+    CU_TRY(cudaMemcpyAsync(node_id, dNode, 4 * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
+    CU_TRY(cudaStreamSynchronize(v->stream));
+    return RUMI_OK;
+}
+
+int rumi_bow_node_distances(rumi_match* m, const uint8_t* descA, int nA, const uint8_t* descB, int nB,
+                            const int32_t* a_idx, int n_a_idx, const int32_t* b_idx, int n_b_idx,
+                            const int32_t* segs, int nseg, uint16_t* dist, long long ndist) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nA < 0 || nB < 0 || nseg < 0 || ndist < 0 || n_a_idx < 0 || n_b_idx < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (nseg == 0 || ndist == 0) return RUMI_OK;
+    if (!descA || !descB || !a_idx || !b_idx || !segs || !dist) return fail(RUMI_ERR_ARG, "NULL buffer");
+    // validate the segment table on the host: the kernel trusts it
+    for (int s = 0; s < nseg; ++s) {
+        const int32_t* g = segs + 5 * (size_t)s;
+        if (g[0] < 0 || g[1] < 0 || g[2] < 0 || g[3] < 0 || g[4] < 0 || (long long)g[0] + g[1] > n_a_idx ||
+            (long long)g[2] + g[3] > n_b_idx || (long long)g[4] + (long long)g[1] * g[3] > ndist)
+            return fail(RUMI_ERR_ARG, "segment %d out of range", s);
+    }
+    for (int i = 0; i < n_a_idx; ++i) if (a_idx[i] < 0 || a_idx[i] >= nA) return fail(RUMI_ERR_ARG, "a_idx[%d] out of range", i);
+    for (int i = 0; i < n_b_idx; ++i) if (b_idx[i] < 0 || b_idx[i] >= nB) return fail(RUMI_ERR_ARG, "b_idx[%d] out of range", i);
+    CU_TRY(cudaSetDevice(m->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oB = al(32 * (size_t)nA), oAi = oB + al(32 * (size_t)nB), oBi = oAi + al(4 * (size_t)n_a_idx),
+                 oSeg = oBi + al(4 * (size_t)n_b_idx), oDist = oSeg + al(20 * (size_t)nseg),
+                 need = oDist + al(2 * (size_t)ndist);
+    int rc = grow((void**)&m->dT, &m->tCap, need);
+    if (rc) return rc;
+    uint8_t* p = m->dT;
+    CU_TRY(cudaMemcpyAsync(p, descA, 32 * (size_t)nA, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(p + oB, descB, 32 * (size_t)nB, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(p + oAi, a_idx, 4 * (size_t)n_a_idx, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(p + oBi, b_idx, 4 * (size_t)n_b_idx, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(p + oSeg, segs, 20 * (size_t)nseg, cudaMemcpyHostToDevice, m->stream));
+    launch_bow_node_distances(p, p + oB, reinterpret_cast<const int32_t*>(p + oAi), reinterpret_cast<const int32_t*>(p + oBi),
+                              reinterpret_cast<const BowSegment*>(p + oSeg), nseg, reinterpret_cast<uint16_t*>(p + oDist),
+                              m->stream);
+    m->launches += 1;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(dist, p + oDist, 2 * (size_t)ndist, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+}  // extern "C"

@@ -143,6 +143,22 @@ void launch_stereo_best1(const KeyPointRec* Lk, const uint8_t* Ld, int nL, const
                          int nR, const float* scaleFactors, int nRows, float minD, float maxD, int32_t* bestR,
                          uint16_t* bestDist, cudaStream_t s);
 
+// ---- bag of words (bow.cu) ----
+struct BowTreeView {            // DBoW2 vocabulary tree in CSR form, node 0 = root
+    int k, L, nnodes;
+    const int32_t* childStart;   // [nnodes] first entry of the node's children in childIds
+    const int32_t* childCount;   // [nnodes] 0 = leaf
+    const int32_t* childIds;     // children in the reference's push_back order (loadFromTextFile :1390)
+    const uint8_t* desc;         // [nnodes][32]
+    const int32_t* wordId;       // [nnodes] word id of a leaf
+    const double* weight;        // [nnodes]
+};
+struct BowSegment { int32_t aStart, aCount, bStart, bCount, outOff; };
+void launch_bow_transform(const BowTreeView& t, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight,
+                          int32_t* node, cudaStream_t s);
+void launch_bow_node_distances(const uint8_t* A, const uint8_t* B, const int32_t* aIdx, const int32_t* bIdx,
+                               const BowSegment* segs, int nseg, uint16_t* dist, cudaStream_t s);
+
 struct StereoRefineArgs {
     LevelView left[kMaxLevels], right[kMaxLevels];     // frame 0 of the two extractors' pyramids
     float scale[kMaxLevels], invScale[kMaxLevels];

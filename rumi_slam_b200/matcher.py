@@ -145,3 +145,96 @@ class ORBmatcher:
         check(self._L.rumi_stereo_match(self._m, ex_left._h, ex_right._h, ptr(Lk), ptr(Ld), len(Lk), ptr(Rk), ptr(Rd),
                                         len(Rk), float(mbf), float(mb), ptr(u), ptr(d), C.byref(n)))
         return u, d, n.value
+
+    # ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:198-370, F.Nleft == -1) ----
+    def SearchByBoW(self, desc_kf, angle_kf, kf_valid, featvec_kf, desc_f, angle_f, featvec_f):
+        """desc_*: [n,32] descriptors; angle_*: keypoint angles (mvKeysUn[i].angle / mvKeys[i].angle); kf_valid[i]:
+        the keyframe feature has a map point that is not bad (:227-233); featvec_*: FeatureVector {node: [indices]}.
+        Returns (nmatches, match_f) with match_f[j] = keyframe feature whose map point was assigned to frame feature
+        j, or -1.  The GPU computes every distance of every common vocabulary node; the acceptance (TH_LOW, ratio,
+        the "already matched" skip :249 and the rotation histogram) is replayed here in the reference's order."""
+        dk = np.ascontiguousarray(desc_kf, np.uint8).reshape(-1, 32)
+        df = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+        nodes_kf, nodes_f = sorted(featvec_kf), sorted(featvec_f)
+        common = sorted(set(nodes_kf) & set(nodes_f))             # the lower_bound walk visits exactly these, ascending
+        a_idx, b_idx, segs, off = [], [], [], 0
+        for nid in common:
+            ia, ib = featvec_kf[nid], featvec_f[nid]
+            segs.append((len(a_idx), len(ia), len(b_idx), len(ib), off))
+            a_idx += list(ia); b_idx += list(ib)
+            off += len(ia) * len(ib)
+        match_f = np.full(len(df), -1, np.int32)
+        if not segs or off == 0:
+            return 0, match_f
+        a_idx, b_idx = np.array(a_idx, np.int32), np.array(b_idx, np.int32)
+        segs_a = np.array(segs, np.int32).reshape(-1, 5)
+        dist = np.zeros(off, np.uint16)
+        check(self._L.rumi_bow_node_distances(self._m, ptr(dk), len(dk), ptr(df), len(df), ptr(a_idx), len(a_idx),
+                                              ptr(b_idx), len(b_idx), ptr(segs_a), len(segs_a), ptr(dist), off))
+        nmatches = 0
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
+        ratio = np.float32(self.mfNNratio)
+        for (a0, ac, b0, bc, o) in segs:
+            block = dist[o:o + ac * bc].reshape(ac, bc)
+            for i in range(ac):
+                real_kf = int(a_idx[a0 + i])
+                if not kf_valid[real_kf]:
+                    continue
+                best1, best_f, best2 = 256, -1, 256
+                for j in range(bc):
+                    real_f = int(b_idx[b0 + j])
+                    if match_f[real_f] >= 0:
+                        continue
+                    d = int(block[i, j])
+                    if d < best1:
+                        best2, best1, best_f = best1, d, real_f
+                    elif d < best2:
+                        best2 = d
+                if best1 <= self.TH_LOW and np.float32(best1) < ratio * np.float32(best2):
+                    match_f[best_f] = real_kf
+                    if self.mbCheckOrientation:
+                        rot = np.float32(angle_kf[real_kf]) - np.float32(angle_f[best_f])
+                        if rot < 0.0:
+                            rot = np.float32(rot + np.float32(360.0))
+                        b = _c_round(float(np.float32(rot * factor)))
+                        if b == self.HISTO_LENGTH:
+                            b = 0
+                        rot_hist[b].append(best_f)
+                    nmatches += 1
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for i in range(self.HISTO_LENGTH):
+                if i in keep:
+                    continue
+                for j in rot_hist[i]:
+                    match_f[j] = -1
+                    nmatches -= 1
+        return nmatches, match_f
+
+
+def _c_round(x):
+    """C round(): half away from zero (numpy rounds half to even)."""
+    import math
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def _three_maxima(histo):
+    """ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:1795-1828): indices of the three fullest bins (-1 dropped)."""
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, h in enumerate(histo):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if max2 < np.float32(0.1) * np.float32(max1):
+        ind2 = ind3 = -1
+    elif max3 < np.float32(0.1) * np.float32(max1):
+        ind3 = -1
+    return {ind1, ind2, ind3}

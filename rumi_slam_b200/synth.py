@@ -85,3 +85,45 @@ def perturbed_descriptors(desc, n, seed=7, flip_p=0.1):
     d = np.tile(desc, (reps, 1))[:n].copy()
     flips = np.packbits(rng.random((n, 256)) < flip_p, axis=1, bitorder="little")
     return d ^ flips
+
+
+def synthetic_vocabulary(k=10, L=6, seed=0, flip=0.08, stop_every=0):
+    """A DBoW2-shaped vocabulary tree (ORBvoc.txt is a missing blob of the reference): k children per node, L levels,
+    nodes in breadth-first id order (node 0 = root, parent id < child id, children of a node contiguous), child
+    descriptors = parent with a fraction `flip` of the 256 bits flipped, leaf weights ~ idf-like positive values
+    (every `stop_every`-th word gets weight 0 = a stopped word).  Returns (parent, is_leaf, desc, weight)."""
+    rng = np.random.default_rng(seed)
+    parent = [np.zeros(1, np.int32)]
+    leaf = [np.zeros(1, np.uint8)]
+    desc = [np.zeros((1, 32), np.uint8)]
+    weight = [np.zeros(1, np.float64)]
+    cur_desc = rng.integers(0, 256, (1, 32), dtype=np.uint8)     # virtual root centre
+    cur_ids = np.zeros(1, np.int64)
+    nxt = 1
+    for lev in range(1, L + 1):
+        n = len(cur_ids) * k
+        pd = np.repeat(cur_desc, k, axis=0)
+        mask = np.packbits(rng.random((n, 256)) < flip, axis=1)
+        d = pd ^ mask
+        parent.append(np.repeat(cur_ids, k).astype(np.int32))
+        leaf.append(np.full(n, 1 if lev == L else 0, np.uint8))
+        desc.append(d)
+        w = np.zeros(n, np.float64)
+        if lev == L:
+            w = 0.5 + 4.0 * rng.random(n)
+            if stop_every:
+                w[::stop_every] = 0.0
+        weight.append(w)
+        cur_desc, cur_ids = d, np.arange(nxt, nxt + n, dtype=np.int64)
+        nxt += n
+    return np.concatenate(parent), np.concatenate(leaf), np.concatenate(desc), np.concatenate(weight)
+
+
+def descriptors_near_vocabulary(desc_nodes, is_leaf, n, seed=0, flip=0.05):
+    """n descriptors = random leaves of the vocabulary with a few bits flipped (realistic descent: clear winners and
+    near ties)."""
+    rng = np.random.default_rng(seed)
+    leaves = np.flatnonzero(is_leaf)
+    pick = rng.choice(leaves, n)
+    mask = np.packbits(rng.random((n, 256)) < flip, axis=1)
+    return desc_nodes[pick] ^ mask

@@ -1,0 +1,115 @@
+"""GPU parity tests of the bag-of-words path (vocabulary tree descent, Frame::ComputeBoW vectors, SearchByBoW) against
+the oracle, through the C ABI.  Integer results (word / node ids, match indices) are bit-exact; BowVector values are
+the same doubles (the device only looks weights up, the arithmetic is the host's)."""
+import numpy as np
+import pytest
+
+from rumi_slam_b200.synth import synthetic_vocabulary, descriptors_near_vocabulary
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bow_oracle():
+    from oracle import bow_oracle as B
+    B.build()
+    return B
+
+
+def _features(desc, leaf, n, seed):
+    rng = np.random.default_rng(seed)
+    near = descriptors_near_vocabulary(desc, leaf, n - n // 4, seed)
+    return np.concatenate([near, rng.integers(0, 256, (n // 4, 32), dtype=np.uint8)])
+
+
+@pytest.mark.parametrize("k,L,n", [(10, 4, 3000), (4, 6, 2000), (17, 2, 1000), (20, 3, 777), (2, 9, 500)])
+def test_transform_matches_oracle(bow_oracle, k, L, n):
+    from rumi_slam_b200 import ORBVocabulary
+    par, leaf, desc, w = synthetic_vocabulary(k, L, seed=3 * k + L, stop_every=5)
+    O = bow_oracle.Vocabulary(k, L, par, leaf, desc, w)
+    V = ORBVocabulary(k, L, par, leaf, desc, w)
+    assert V.size() == int(leaf.sum())
+    f = _features(desc, leaf, n, 7)
+    for levelsup in (0, 1, 4, L, L + 3):
+        word, weight, node = V.transform_features(f, levelsup)
+        rw, rwt, rn = O.transform(f, levelsup)
+        assert np.array_equal(word, rw) and np.array_equal(node, rn) and np.array_equal(weight, rwt)
+        assert V.transform(f, levelsup) == O.vectors(f, levelsup)
+    assert V.transform_features(np.zeros((0, 32), np.uint8)) [0].shape == (0,)
+
+
+def test_transform_full_size_vocabulary_and_device_path(bow_oracle):
+    import torch
+    from rumi_slam_b200 import ORBVocabulary
+    k, L = 10, 6                                   # the shape of ORBvoc.txt: 1 111 111 nodes, 10^6 words
+    par, leaf, desc, w = synthetic_vocabulary(k, L, seed=1)
+    O = bow_oracle.Vocabulary(k, L, par, leaf, desc, w)
+    V = ORBVocabulary(k, L, par, leaf, desc, w)
+    f = _features(desc, leaf, 4000, 9)
+    word, weight, node = V.transform_features(f, 4)
+    rw, rwt, rn = O.transform(f, 4)
+    assert np.array_equal(word, rw) and np.array_equal(node, rn) and np.array_equal(weight, rwt)
+    dw, dwt, dn = V.transform_features_device(torch.from_numpy(f).cuda(), 4)
+    assert np.array_equal(dw.cpu().numpy(), rw) and np.array_equal(dn.cpu().numpy(), rn)
+    assert np.array_equal(dwt.cpu().numpy(), rwt)
+
+
+def test_unbalanced_tree_and_ties(bow_oracle):
+    from rumi_slam_b200 import ORBVocabulary
+    # root -> {1, 2, 3}; 1 is a leaf, 2 -> {4, 5}, 3 -> {6, 7, 8}; children 4 and 5 are IDENTICAL (tie -> first wins)
+    rng = np.random.default_rng(0)
+    d = rng.integers(0, 256, (9, 32), dtype=np.uint8)
+    d[5] = d[4]
+    d[2] = d[4]                                    # so that a feature equal to d[4] goes down through node 2
+    par = np.array([0, 0, 0, 0, 2, 2, 3, 3, 3], np.int32)
+    leaf = np.array([0, 1, 0, 0, 1, 1, 1, 1, 1], np.uint8)
+    w = np.array([0, 1.5, 0, 0, 2.5, 3.5, 0.0, 4.5, 5.5])
+    O = bow_oracle.Vocabulary(3, 2, par, leaf, d, w)
+    V = ORBVocabulary(3, 2, par, leaf, d, w)
+    f = np.concatenate([d[1:], rng.integers(0, 256, (200, 32), dtype=np.uint8)])
+    for levelsup in (0, 1, 2):
+        a, b = V.transform_features(f, levelsup), O.transform(f, levelsup)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    word, _, _ = V.transform_features(d[5:6], 0)
+    assert word[0] == 1                            # node 4 (the first of the tied children) is word 1, node 5 is word 2
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_search_by_bow_matches_oracle(bow_oracle, check_ori, seed):
+    from rumi_slam_b200 import ORBVocabulary, ORBmatcher
+    k, L = 10, 4
+    par, leaf, desc, w = synthetic_vocabulary(k, L, seed=11)
+    V = ORBVocabulary(k, L, par, leaf, desc, w)
+    rng = np.random.default_rng(seed)
+    nk, nf = 1000, 1100
+    dk = descriptors_near_vocabulary(desc, leaf, nk, 20 + seed, flip=0.04)
+    # frame features: noisy copies of 800 keyframe features (some duplicated) + unrelated ones, shuffled
+    src = rng.integers(0, nk, 900)
+    noise = np.packbits(rng.random((900, 256)) < 0.03, axis=1)
+    df = np.concatenate([dk[src] ^ noise, descriptors_near_vocabulary(desc, leaf, nf - 900, 30 + seed)])
+    perm = rng.permutation(nf)
+    df = df[perm]
+    ak = rng.random(nk).astype(np.float32) * 360
+    af = np.zeros(nf, np.float32)
+    af[np.argsort(perm)[:900]] = (ak[src] - 15 + rng.normal(0, 2, 900)).astype(np.float32) % 360
+    valid = (rng.random(nk) < 0.8).astype(np.uint8)
+    _, fv_k = V.transform(dk, 2)
+    _, fv_f = V.transform(df, 2)
+    m = ORBmatcher(0.75, check_ori)
+    n_gpu, match_gpu = m.SearchByBoW(dk, ak, valid, fv_k, df, af, fv_f)
+    n_ref, match_ref = bow_oracle.search_by_bow(dk, ak, valid, fv_k, df, af, fv_f, nnratio=0.75, check_ori=check_ori)
+    assert n_gpu == n_ref and n_ref > 100
+    assert np.array_equal(match_gpu, match_ref)
+
+
+def test_search_by_bow_edge_cases(bow_oracle):
+    from rumi_slam_b200 import ORBmatcher
+    m = ORBmatcher(0.75, True)
+    d = np.zeros((3, 32), np.uint8)
+    n, match = m.SearchByBoW(d, np.zeros(3), np.ones(3, np.uint8), {1: [0, 1, 2]}, d, np.zeros(3), {2: [0, 1, 2]})
+    assert n == 0 and list(match) == [-1, -1, -1]                 # no common node
+    n, match = m.SearchByBoW(d, np.zeros(3), np.zeros(3, np.uint8), {1: [0, 1, 2]}, d, np.zeros(3), {1: [0, 1, 2]})
+    assert n == 0                                                 # no valid map point
+    n, match = m.SearchByBoW(d, np.zeros(3), np.ones(3, np.uint8), {}, d, np.zeros(3), {1: [0]})
+    assert n == 0

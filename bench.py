@@ -291,6 +291,44 @@ def run_b200(args):
     matches_per_s = nq * msteps / (ms_match / 1e3)
     pairs_per_s = matches_per_s * nt
 
+    # ---- bag of words: Frame::ComputeBoW tree descent of this rank's descriptors on an ORBvoc-shaped vocabulary
+    #      (k = 10, L = 6: 1 111 111 nodes, 10^6 words; synthetic because ORBvoc.txt is a missing blob) ----
+    bow = None
+    if not args.no_bow:
+        from rumi_slam_b200 import ORBVocabulary
+        from rumi_slam_b200.synth import synthetic_vocabulary
+        par, leaf, vdesc, vw = synthetic_vocabulary(10, 6, seed=5)
+        voc = ORBVocabulary(10, 6, par, leaf, vdesc, vw, device=local)
+        feats = out_dev[1][:, :1000].reshape(-1, 32).contiguous()           # 1000 descriptors of each of the frames
+        for _ in range(3):
+            voc.transform_features_device(feats, 4, sync=True)
+        voc.launch_count(reset=True)
+        barrier()
+        t_a = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(msteps):
+            voc.transform_features_device(feats, 4, sync=True)                # own stream, synchronised per call
+        ev1.record()
+        torch.cuda.synchronize()
+        barrier()
+        windows.append((t_a, time.perf_counter()))
+        ms_bow = max_over_ranks(ev0.elapsed_time(ev1))
+        bow = {"workload": "DBoW2 tree descent (levelsup 4) of %d descriptors per GPU per step, vocabulary k=10 L=6 "
+                           "(1111111 nodes, synthetic)" % feats.shape[0],
+               "features_per_s": world * feats.shape[0] * msteps / (ms_bow / 1e3), "ms_per_step": ms_bow / msteps,
+               "distances_per_feature": 60, "gpu_launches": voc.launch_count(reset=True), "steps": msteps}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import bow_oracle
+            cpu_voc = bow_oracle.Vocabulary(10, 6, par, leaf, vdesc, vw)
+            sample = feats[:100000].cpu().numpy()
+            t0 = time.perf_counter()
+            cpu_voc.transform(sample, 4)
+            dt = time.perf_counter() - t0
+            bow["cpu_baseline"] = {"value": len(sample) / dt, "unit": "features/s", "cores": 1, "kind": "port",
+                                   "sample": "%d of the same descriptors, oracle/bow_oracle.cpp (pinned against the "
+                                             "reference DBoW2), 1 thread, %.2f s" % (len(sample), dt)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -377,6 +415,7 @@ def run_b200(args):
                                       "frac": pairs_per_s / (world * 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 5),
                                       "note": "POPC rate measured 15.8/clk/SM (tools/probe/pipe_probe.cu); "
                                               "5 POPC + 14 LOP3 per pair"}},
+            "bow": bow,
             "clocks": clocks}
     print(json.dumps(line))
     if world > 1:
@@ -393,6 +432,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("RUMI_CHUNK", "64")))
     ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames generated per rank")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bow", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -1,5 +1,6 @@
 #include "ORBmatcher_accel.h"
 
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -79,6 +80,95 @@ int ORBmatcherAccel::ComputeStereoMatches(rumi_orb* extractorLeft, rumi_orb* ext
                           (int)keysR.size(), mbf, mb, mvuRight.data(), mvDepth.data(), &n) != RUMI_OK)
         throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
     return n;
+}
+
+// R/lib_src/ORBmatcher.cc:1795-1828
+static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>& angleKF,
+                                 const std::vector<uint8_t>& kfValid,
+                                 const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF,
+                                 const cv::Mat& descF, const std::vector<float>& angleF,
+                                 const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF,
+                                 bool checkOrientation, std::vector<int>& matchF) {
+    matchF.assign(descF.rows, -1);
+    // common nodes in ascending order == the nodes the reference's lower_bound walk visits (:218-221, :345-353)
+    std::vector<int32_t> aIdx, bIdx, segs;
+    long long ndist = 0;
+    size_t a = 0, b = 0;
+    while (a < featVecKF.size() && b < featVecF.size()) {
+        if (featVecKF[a].first == featVecF[b].first) {
+            const std::vector<unsigned>&ia = featVecKF[a].second, &ib = featVecF[b].second;
+            segs.push_back((int32_t)aIdx.size()); segs.push_back((int32_t)ia.size());
+            segs.push_back((int32_t)bIdx.size()); segs.push_back((int32_t)ib.size());
+            segs.push_back((int32_t)ndist);
+            aIdx.insert(aIdx.end(), ia.begin(), ia.end());
+            bIdx.insert(bIdx.end(), ib.begin(), ib.end());
+            ndist += (long long)ia.size() * (long long)ib.size();
+            ++a; ++b;
+        } else if (featVecKF[a].first < featVecF[b].first) ++a;
+        else ++b;
+    }
+    if (segs.empty() || ndist == 0) return 0;
+    const std::vector<uint8_t> dk = rows32(descKF), df = rows32(descF);
+    std::vector<uint16_t> dist((size_t)ndist);
+    if (rumi_bow_node_distances(ctx, dk.data(), descKF.rows, df.data(), descF.rows, aIdx.data(), (int)aIdx.size(),
+                                bIdx.data(), (int)bIdx.size(), segs.data(), (int)(segs.size() / 5), dist.data(),
+                                ndist) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (size_t s = 0; s < segs.size(); s += 5) {
+        const int a0 = segs[s], ac = segs[s + 1], b0 = segs[s + 2], bc = segs[s + 3];
+        const uint16_t* block = dist.data() + segs[s + 4];
+        for (int iKF = 0; iKF < ac; iKF++) {
+            const int realIdxKF = aIdx[a0 + iKF];
+            if (!kfValid[realIdxKF]) continue;                                   // :229-233
+            int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+            for (int iF = 0; iF < bc; iF++) {
+                const int realIdxF = bIdx[b0 + iF];
+                if (matchF[realIdxF] >= 0) continue;                              // :249
+                const int d = block[(size_t)iKF * bc + iF];
+                if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = realIdxF; }
+                else if (d < bestDist2) { bestDist2 = d; }
+            }
+            if (bestDist1 <= TH_LOW) {
+                if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                    matchF[bestIdxF] = realIdxKF;
+                    if (checkOrientation) {
+                        float rot = angleKF[realIdxKF] - angleF[bestIdxF];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(bestIdxF);
+                    }
+                    nmatches++;
+                }
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { matchF[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
 }
 
 }  // namespace ORB_SLAM3

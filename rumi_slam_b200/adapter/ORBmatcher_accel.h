@@ -8,6 +8,7 @@
 #define ORBMATCHER_ACCEL_H
 
 #include <cstdint>
+#include <utility>
 #include <vector>
 #include <opencv2/core/core.hpp>
 
@@ -50,6 +51,18 @@ public:
                              const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
                              const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR, float mbf, float mb,
                              std::vector<float>& mvuRight, std::vector<float>& mvDepth);
+
+    // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (R/lib_src/ORBmatcher.cc:198-370), the
+    // F.Nleft == -1 branch, on flattened inputs: featVec* = the two DBoW2::FeatureVector maps as (node id, feature
+    // indices) pairs in ascending node order, kfValid[i] = the keyframe feature has a map point that is not bad,
+    // angle* = mvKeysUn[i].angle / mvKeys[i].angle.  matchF[j] = keyframe feature whose map point the reference
+    // would store in vpMapPointMatches[j], or -1.  All DescriptorDistance calls run on the device; the acceptance is
+    // replayed in the reference's order (it depends on earlier acceptances, :249).
+    int SearchByBoW(const cv::Mat& descKF, const std::vector<float>& angleKF, const std::vector<uint8_t>& kfValid,
+                    const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF, const cv::Mat& descF,
+                    const std::vector<float>& angleF,
+                    const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF, bool checkOrientation,
+                    std::vector<int>& matchF);
 
 private:
     rumi_match* ctx;

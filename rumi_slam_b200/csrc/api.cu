@@ -428,7 +428,8 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
     fa.cells = h->fastCells;
     fa.tilePitch = h->fastTilePitch; fa.tileRows = h->fastTileRows;
-    fa.scoreRows = h->fastScoreRows; fa.maskWords = h->fastMaskWords;
+    fa.scoreRows = h->fastScoreRows;
+    fa.lay = fast_layout(fa.tilePitch, fa.tileRows, fa.scoreRows);
     fa.dbg = h->dbgBuf; fa.dbgCell = h->dbgCell;
     OctreeArgs oa;
     oa.nframes = n; oa.levelFirst = 0; oa.dbgClk = h->octClk; oa.cand = w.cand; oa.candOrdered = w.candOrdered; oa.levelCount = w.levelCount;

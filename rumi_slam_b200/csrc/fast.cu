@@ -75,13 +75,18 @@ __device__ __forceinline__ int corner_score(const uint8_t* p, int tpRuntime) {
 __device__ __forceinline__ uint32_t magic_of(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); }
 __device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
 
-// Shared-memory layout of one warp.  The score tile and the survivor bitmap use the SAME pitch as the image tile,
-// so one 16-bit offset o = y * tp + x (detection-area coordinates) addresses all three and no phase after the
-// pretest needs a division.
-__host__ __device__ inline size_t fast_warp_bytes(int tp, int tileRows, int scoreRows, int maskWords) {
-    const size_t b = (size_t)tp * tileRows + ((size_t)tp * scoreRows + 32) + 4u * maskWords + 2u * kCornerListCap +
-                     2u * kQueueCap;
-    return (b + 15) & ~(size_t)15;
+// Shared-memory layout of one warp (offsets computed on the host, FastLayout).  The score tile uses the SAME pitch as
+// the image tile, so one 16-bit offset o = y * tp + x (detection-area coordinates) addresses both and no phase after
+// the pretest needs a division.
+constexpr int kValidCap = 32;              // column groups of 4 pixels per cell row (cells are < 128 px wide)
+FastLayout fast_layout(int tp, int tileRows, int scoreRows) {
+    FastLayout L;
+    L.score = tp * tileRows;
+    L.valid = L.score + tp * scoreRows + 32;
+    L.clist = L.valid + 4 * kValidCap;
+    L.queue = L.clist + 2 * kCornerListCap;
+    L.warpBytes = (L.queue + 2 * kQueueCap + 15) & ~15;
+    return L;
 }
 
 template <int TP>
@@ -106,13 +111,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     const int cw = (int)(cellBits.y & 0xFFu), ch = (int)((cellBits.y >> 8) & 0xFFu);       // sub-image
     const int dw = cw - 6, dh = ch - 6;                 // detection area, origin (iniX+3, iniY+3)
 
-    // per-warp shared memory: image tile | score tile | survivor bitmap | corner list | queue
+    // per-warp shared memory: image tile | score tile | valid-byte masks | corner list | queue
     const int tp = TP ? TP : a.tilePitch;               // TP > 0: compile-time pitch -> immediate offsets
-    uint8_t* tile = smem + (size_t)warp * fast_warp_bytes(tp, a.tileRows, a.scoreRows, a.maskWords);
-    uint8_t* score = tile + (size_t)tp * a.tileRows;
-    uint32_t* kept = reinterpret_cast<uint32_t*>(score + (size_t)tp * a.scoreRows + 32);
-    uint16_t* clist = reinterpret_cast<uint16_t*>(kept + a.maskWords);
-    uint16_t* queue = clist + kCornerListCap;
+    uint8_t* tile = smem + warp * a.lay.warpBytes;
+    uint8_t* score = tile + a.lay.score;
+    uint32_t* validTab = reinterpret_cast<uint32_t*>(tile + a.lay.valid);
+    uint16_t* clist = reinterpret_cast<uint16_t*>(tile + a.lay.clist);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(tile + a.lay.queue);
 
     // ---- 0. stage the sub-image: tile column ox <-> image column iniX ----
     const LevelView lv = a.cv.src[l];
@@ -135,14 +140,22 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
             for (int x = lane; x < cw; x += 32) tile[r * tp + x] = row[x];
         }
     }
-    // zero the score tile (everything outside the detection area stays 0 = "neighbour outside the sub-image") and
-    // the survivor bitmap
-    const int nbits = (dh - 1) * tp + dw, nwords = (nbits + 31) >> 5;
+    // zero the score tile (everything outside the detection area stays 0 = "neighbour outside the sub-image"); per
+    // column group of 4 pixels, the bytes that lie inside the detection area (bit 7 of each valid byte)
+    const int c0 = ox + 3;                               // tile column of detection x = 0
+    const int g0 = c0 >> 2, ng = ((c0 + dw - 1) >> 2) - g0 + 1;
     {
         uint4* z = reinterpret_cast<uint4*>(score);
         const int n16 = (tp * (dh + 2) + 32 + 15) >> 4;
         for (int i = lane; i < n16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = lane; i < nwords; i += 32) kept[i] = 0u;
+        if (lane < ng) {
+            const int g = g0 + lane;
+            const int xlo = c0 - 4 * g, xhi = c0 + dw - 4 * g;              // valid bytes: xlo <= j < xhi
+            uint32_t valid = 0x80808080u;
+            if (xlo > 0) valid &= 0xFFFFFFFFu << (8 * xlo);
+            if (xhi < 4) valid &= 0xFFFFFFFFu >> (8 * (4 - xhi));
+            validTab[lane] = valid;
+        }
     }
     __syncwarp();
 
@@ -175,8 +188,6 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     // and 16 ANDs + 4 ORs give "4 consecutive positions" for the 4 pixels at once.  (Sign-agnostic, so slightly
     // weaker than the exact test: survivors go to phase B, which is exact.)
     {
-        const int c0 = ox + 3;                           // tile column of detection x = 0
-        const int g0 = c0 >> 2, ng = ((c0 + dw - 1) >> 2) - g0 + 1;
         const uint32_t magicG = magic_of((uint32_t)ng);
         const uint32_t K = (uint32_t)(th <= 126 ? 127 - th : 0) * 0x01010101u;
         const uint32_t forceAll = th <= 126 ? 0u : 0x80808080u;
@@ -188,7 +199,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
             int y = 0, g = 0;
             if (i < ngroups) {
                 y = (int)div_magic((uint32_t)i, magicG);
-                g = g0 + (i - y * ng);
+                const int gl = i - y * ng;
+                g = g0 + gl;
                 const uint8_t* r0 = trow + y * tp;
                 const int wl = 4 * max(g - 1, 0), wc = 4 * g, wr = 4 * g + 4;
 #define LDW(row, off) (*reinterpret_cast<const uint32_t*>((row) + (off)))
@@ -222,12 +234,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                 uint32_t any = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) any |= p2[k] & p2[(k + 2) & 7];
-                // bytes of this group that are inside the detection area
-                const int xlo = c0 - 4 * g, xhi = c0 + dw - 4 * g;              // valid bytes: xlo <= j < xhi
-                uint32_t valid = 0x80808080u;
-                if (xlo > 0) valid &= 0xFFFFFFFFu << (8 * xlo);
-                if (xhi < 4) valid &= 0xFFFFFFFFu >> (8 * (4 - xhi));
-                pass4 = any & valid;
+                pass4 = any & validTab[gl];                                      // bytes inside the detection area
             }
             const int o0 = y * tp + 4 * g - c0;                                  // offset of byte 0 of the group
             {   // append the (up to 4) surviving pixels of every lane: popc + shuffle prefix, predicated stores
@@ -262,7 +269,9 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
         for (int i = lane; i < nb; i += 32) a.dbg[i] = tile[i];
     }
 
-    // ---- C. NMS over the corner list: strict '>' against the 8 neighbours, branch-free ----
+    // ---- C. NMS over the corner list: strict '>' against the 8 neighbours, branch-free.  Survivors are compacted IN
+    //         PLACE into the front of the list (entry i of iteration b is read before anything is written, and at most
+    //         b entries precede it) ----
     int nIni = 0, nMin = 0;
     const int npx = dw * dh;
     const uint32_t magicW = magic_of((uint32_t)dw);
@@ -284,8 +293,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
             const int m2 = max(max((int)q[tp], (int)q[tp + 1]), m0);
             k = s > max(m1, m2);                         // s == 0 (overflow scan of a non-corner) can never pass
         }
-        if (k) atomicOr(&kept[o >> 5], 1u << (o & 31));
-        nMin += __popc(__ballot_sync(kFull, k));
+        __syncwarp();
+        const unsigned mk = __ballot_sync(kFull, k);
+        if (k && !overflow) clist[nMin + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)o;
+        nMin += __popc(mk);
         nIni += __popc(__ballot_sync(kFull, k && s >= oc.iniTh));
     }
     __syncwarp();
@@ -300,37 +311,46 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     off = __shfl_sync(kFull, off, 0);
     if (total == 0) return;
 
-    // ---- D. raster-order emission from the survivor bitmap (bit index = y * tp + x, row major) ----
+    // ---- D. raster-order emission: rank of a survivor = number of emitted survivors with a smaller offset
+    //         (offset = y * tp + x is row major).  A cell keeps a handful of survivors, so the all-pairs rank is
+    //         cheaper than scanning a per-pixel bitmap ----
     uint32_t* out = a.cand + a.candLevelOff[l] + (long long)f * oc.lv[l].candCap + off;
     const int relX = iniX + 3 - kMinBorder, relY = iniY + 3 - kMinBorder;   // candidate coords are relative to (16,16)
     const uint32_t magicT = magic_of((uint32_t)tp);
-    int w = 0;
-    for (int wb = 0; wb < nwords; wb += 32) {
-        uint32_t bits = wb + lane < nwords ? kept[wb + lane] : 0u;
-        if (nIni > 0 && bits) {                        // keep only survivors with score >= iniThFAST
-            uint32_t keep = 0, t = bits;
-            while (t) {
-                const int bit = __ffs(t) - 1;
-                t &= t - 1;
-                if (s0[(wb + lane) * 32 + bit] >= thEmit) keep |= 1u << bit;
+    if (overflow) {
+        // more corners than the list holds (noise): the survivors were only counted; emit them from a second raster
+        // scan of the detection area that repeats the NMS test
+        int w = 0;
+        for (int b = 0; b < npx; b += 32) {
+            bool k = false;
+            int s = 0, x = 0, y = 0;
+            if (b + lane < npx) {
+                y = (int)div_magic((uint32_t)(b + lane), magicW);
+                x = b + lane - y * dw;
+                const uint8_t* q = s0 + y * tp + x;
+                s = q[0];
+                const int m0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
+                const int m1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
+                const int m2 = max(max((int)q[tp], (int)q[tp + 1]), m0);
+                k = s > max(m1, m2) && s >= thEmit;
             }
-            bits = keep;
+            const unsigned mk = __ballot_sync(kFull, k);
+            if (k) out[w + __popc(mk & ((1u << lane) - 1u))] = pack_cand(relX + x, relY + y, s);
+            w += __popc(mk);
         }
-        int cnt = __popc(bits), pre = cnt;             // inclusive prefix over lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(kFull, pre, o);
-            if (lane >= o) pre += n;
+        return;
+    }
+    for (int i = lane; i < nMin; i += 32) {
+        const int o = (int)clist[i];
+        const int sc = s0[o];
+        if (sc < thEmit) continue;                       // survivors below iniThFAST when the cell has stronger ones
+        int rank = 0;
+        for (int j = 0; j < nMin; ++j) {
+            const int oj = (int)clist[j];
+            rank += (oj < o) && (s0[oj] >= thEmit);
         }
-        int pos = w + pre - cnt;
-        while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int o = (wb + lane) * 32 + bit;
-            const int y = TP == 64 ? (o >> 6) : (int)div_magic((uint32_t)o, magicT), x = o - y * tp;
-            out[pos++] = pack_cand(relX + x, relY + y, s0[o]);
-        }
-        w += __shfl_sync(kFull, pre, 31);
+        const int y = TP == 64 ? (o >> 6) : (int)div_magic((uint32_t)o, magicT), x = o - y * tp;
+        out[rank] = pack_cand(relX + x, relY + y, sc);
     }
 }
 
@@ -340,7 +360,7 @@ void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s) {
         const char* e = getenv("RUMI_FAST_WARPS");
         warps = e && e[0] >= '1' && e[0] <= '0' + kFastWarps ? e[0] - '0' : 2;   // 2: less tail imbalance than 4 (measured)
     }
-    const size_t smem = fast_warp_bytes(a.tilePitch, a.tileRows, a.scoreRows, a.maskWords) * warps;
+    const size_t smem = (size_t)a.lay.warpBytes * warps;
     dim3 grid((oc.totalCells + warps - 1) / warps, a.cv.nframes);
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -78,6 +78,9 @@ void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s);
 struct alignas(8) FastCell { uint16_t iniX, iniY; uint8_t cw, ch, level, valid; };
 static_assert(sizeof(FastCell) == 8, "FastCell is read as one 8-byte word");
 
+struct FastLayout { int score, valid, clist, queue, warpBytes; };
+FastLayout fast_layout(int tilePitch, int tileRows, int scoreRows);
+
 struct FastArgs {
     ChunkView cv;
     const FastCell* cells;   // [totalCells], all levels
@@ -86,7 +89,8 @@ struct FastArgs {
     int* levelCount;         // [frame][nlevels] (zeroed by the caller)
     int* cellOff;            // [frame][totalCells]
     int* cellCount;          // [frame][totalCells]
-    int tilePitch, tileRows, scoreRows, maskWords;   // per-warp shared-memory tile sizes (score tile pitch == tilePitch)
+    int tilePitch, tileRows, scoreRows;   // per-warp shared-memory tile sizes (score tile pitch == tilePitch)
+    FastLayout lay;          // byte offsets of the per-warp shared-memory regions (fast_layout)
     uint8_t* dbg;            // optional: image + score tile of (frame 0, dbgCell) for tests
     int dbgCell;
 };

@@ -175,6 +175,12 @@ long long rumi_vocab_launch_count(rumi_vocab* v, int reset);
 int rumi_bow_node_distances(rumi_match* m, const uint8_t* descA, int nA, const uint8_t* descB, int nB,
                             const int32_t* a_idx, int n_a_idx, const int32_t* b_idx, int n_b_idx,
                             const int32_t* segs, int nseg, uint16_t* dist, long long ndist);
+/* MapPoint::ComputeDistinctiveDescriptors (R/lib_src/MapPoint.cc:355-426), batched over map points: the observed
+ * descriptors of point p are desc[offsets[p] .. offsets[p+1]) (32 bytes each); best_idx[p] = index (within the point's
+ * list) of the descriptor with the least median distance to the rest, first one on ties; best_median[p] that median
+ * (-1 / -1 for a point without observations).  Host buffers. */
+int rumi_distinctive_descriptors(rumi_match* m, const uint8_t* desc, const int32_t* offsets, int npoints,
+                                 int32_t* best_idx, int32_t* best_median);
 
 /* ORBmatcher::DescriptorDistance for one pair (host inline popcount; the API, not a fallback). */
 int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b);

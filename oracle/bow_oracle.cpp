@@ -215,4 +215,28 @@ int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, cons
     return nmatches;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors, R/lib_src/MapPoint.cc:392-426, for one map point with N observed descriptors.
+// (Restated; MapPoint.cc needs KeyFrame / Map and cannot be compiled here.)  Returns BestIdx, *median = BestMedian.
+int bow_oracle_distinctive(const uint8_t* desc, int N, int* median) {
+    if (N <= 0) { *median = -1; return -1; }
+    std::vector<std::vector<float>> D(N, std::vector<float>(N));
+    for (int i = 0; i < N; i++) {
+        D[i][i] = 0;
+        for (int j = i + 1; j < N; j++) {
+            const int distij = forb_distance(desc + 32 * (size_t)i, desc + 32 * (size_t)j);   // == ORBmatcher::DescriptorDistance
+            D[i][j] = (float)distij;
+            D[j][i] = (float)distij;
+        }
+    }
+    int BestMedian = 2147483647, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        std::vector<int> vDists(D[i].begin(), D[i].end());
+        std::sort(vDists.begin(), vDists.end());
+        const int med = vDists[(size_t)(0.5 * (N - 1))];
+        if (med < BestMedian) { BestMedian = med; BestIdx = i; }
+    }
+    *median = BestMedian;
+    return BestIdx;
+}
+
 }  // extern "C"

@@ -48,6 +48,7 @@ def lib():
                                          C.POINTER(C.c_int)]
         L.bow_oracle_search_by_bow.argtypes = [_u8p, _f32p, _u8p, _i32p, _i32p, _i32p, C.c_int, _u8p, _f32p, C.c_int,
                                                _i32p, _i32p, _i32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p]
+        L.bow_oracle_distinctive.argtypes = [_u8p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -140,3 +141,17 @@ def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnr
                                        _p(fo, _i32p), _p(fi, _i32p), len(fn), nnratio, 1 if check_ori else 0, th_low,
                                        _p(match, _i32p))
     return n, match[:len(df)]
+
+
+def distinctive(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors per map point (rows offsets[p]:offsets[p+1] of desc)."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(offsets) - 1
+    best, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    L = lib()
+    for p in range(n):
+        d = np.ascontiguousarray(desc[offsets[p]:offsets[p + 1]])
+        m = C.c_int(0)
+        best[p] = L.bow_oracle_distinctive(_p(d, _u8p), len(d), C.byref(m))
+        med[p] = m.value
+    return best, med

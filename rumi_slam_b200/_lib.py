@@ -66,6 +66,7 @@ SIGNATURES = {
     "rumi_vocab_launch_count": (C.c_longlong, [_vp, C.c_int]),
     "rumi_bow_transform": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rumi_bow_transform_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "rumi_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp]),
     "rumi_bow_node_distances": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
                                           _vp, C.c_longlong]),
 }

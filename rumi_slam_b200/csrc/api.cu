@@ -1284,4 +1284,34 @@ int rumi_bow_node_distances(rumi_match* m, const uint8_t* descA, int nA, const u
     return RUMI_OK;
 }
 
+int rumi_distinctive_descriptors(rumi_match* m, const uint8_t* desc, const int32_t* offsets, int npoints,
+                                 int32_t* best_idx, int32_t* best_median) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (npoints < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (npoints == 0) return RUMI_OK;
+    if (!offsets || !best_idx || !best_median) return fail(RUMI_ERR_ARG, "NULL buffer");
+    if (offsets[0] != 0) return fail(RUMI_ERR_ARG, "offsets[0] must be 0");
+    for (int p = 0; p < npoints; ++p)
+        if (offsets[p + 1] < offsets[p]) return fail(RUMI_ERR_ARG, "offsets must be non-decreasing");
+    const int total = offsets[npoints];
+    if (total > 0 && !desc) return fail(RUMI_ERR_ARG, "NULL descriptors");
+    CU_TRY(cudaSetDevice(m->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oOff = al(32 * (size_t)std::max(total, 1)), oIdx = oOff + al(4 * ((size_t)npoints + 1)),
+                 oMed = oIdx + al(4 * (size_t)npoints), need = oMed + al(4 * (size_t)npoints);
+    int rc = grow((void**)&m->dT, &m->tCap, need);
+    if (rc) return rc;
+    uint8_t* p = m->dT;
+    if (total > 0) CU_TRY(cudaMemcpyAsync(p, desc, 32 * (size_t)total, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(p + oOff, offsets, 4 * ((size_t)npoints + 1), cudaMemcpyHostToDevice, m->stream));
+    launch_distinctive(p, reinterpret_cast<const int32_t*>(p + oOff), npoints, reinterpret_cast<int32_t*>(p + oIdx),
+                       reinterpret_cast<int32_t*>(p + oMed), m->stream);
+    m->launches += 1;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(best_idx, p + oIdx, 4 * (size_t)npoints, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(best_median, p + oMed, 4 * (size_t)npoints, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
 }  // extern "C"

@@ -94,4 +94,53 @@ void launch_bow_node_distances(const uint8_t* A, const uint8_t* B, const int32_t
     bow_node_distances_kernel<<<(nseg + perBlock - 1) / perBlock, threads, 0, s>>>(A, B, aIdx, bIdx, segs, nseg, dist);
 }
 
+
+// K12: MapPoint::ComputeDistinctiveDescriptors (R/lib_src/MapPoint.cc:355-426), batched: one warp per map point.
+// For every observed descriptor i the lanes hold the distances to the other descriptors (lane j <-> descriptor j, in
+// chunks of 32); the median vDists[0.5 * (N - 1)] of the sorted row is found without sorting, by a 9-step binary search
+// on the value (distances are 0..256): the smallest t with #(d <= t) >= m + 1.  The first row with the smallest median
+// wins (strict '<', :412).
+__global__ void __launch_bounds__(128) distinctive_kernel(const uint8_t* __restrict__ desc,
+                                                          const int32_t* __restrict__ offsets, int npoints,
+                                                          int32_t* __restrict__ bestIdx, int32_t* __restrict__ bestMedian) {
+    const int pt = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (pt >= npoints) return;
+    const int base = offsets[pt], N = offsets[pt + 1] - base;
+    if (N <= 0) {
+        if (lane == 0) { bestIdx[pt] = -1; bestMedian[pt] = -1; }
+        return;
+    }
+    const int m = (int)(0.5 * (double)(N - 1));                   // index of the median in the sorted row (:407)
+    int best = 0x7FFFFFFF, bestI = 0;
+    for (int i = 0; i < N; ++i) {
+        const uint4* pi = reinterpret_cast<const uint4*>(desc + 32 * (size_t)(base + i));
+        const uint4 a0 = __ldg(pi), a1 = __ldg(pi + 1);
+        const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        int lo = 0, hi = 256;                                     // smallest t in [0, 256] with count(d <= t) >= m + 1
+        while (lo < hi) {
+            const int t = (lo + hi) >> 1;
+            int cnt = 0;
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                bool le = false;
+                if (j < N) {
+                    const uint4* pj = reinterpret_cast<const uint4*>(desc + 32 * (size_t)(base + j));
+                    le = hamming256(a, __ldg(pj), __ldg(pj + 1)) <= t;     // Distances[i][i] = 0 falls out of the formula
+                }
+                cnt += __popc(__ballot_sync(kFullMask, le));
+            }
+            if (cnt >= m + 1) hi = t; else lo = t + 1;
+        }
+        if (lo < best) { best = lo; bestI = i; }
+    }
+    if (lane == 0) { bestIdx[pt] = bestI; bestMedian[pt] = best; }
+}
+
+void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* bestIdx, int32_t* bestMedian,
+                        cudaStream_t s) {
+    if (npoints <= 0) return;
+    const int threads = 128, perBlock = threads / 32;
+    distinctive_kernel<<<(npoints + perBlock - 1) / perBlock, threads, 0, s>>>(desc, offsets, npoints, bestIdx, bestMedian);
+}
+
 }  // namespace rumi

@@ -163,6 +163,9 @@ void launch_bow_transform(const BowTreeView& t, const uint8_t* desc, int n, int 
 void launch_bow_node_distances(const uint8_t* A, const uint8_t* B, const int32_t* aIdx, const int32_t* bIdx,
                                const BowSegment* segs, int nseg, uint16_t* dist, cudaStream_t s);
 
+void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* bestIdx, int32_t* bestMedian,
+                        cudaStream_t s);
+
 struct StereoRefineArgs {
     LevelView left[kMaxLevels], right[kMaxLevels];     // frame 0 of the two extractors' pyramids
     float scale[kMaxLevels], invScale[kMaxLevels];

@@ -146,6 +146,19 @@ class ORBmatcher:
                                         len(Rk), float(mbf), float(mb), ptr(u), ptr(d), C.byref(n)))
         return u, d, n.value
 
+    # ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:355-426), batched over map points ----
+    def ComputeDistinctiveDescriptors(self, desc, offsets):
+        """desc: [total,32] observed descriptors of all map points, point p owns rows offsets[p]:offsets[p+1].
+        Returns (best_idx, best_median): per point the row (relative to its own list) with the least median distance
+        to the point's other observations -- the descriptor the reference stores in mDescriptor."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        n = len(offsets) - 1
+        best, med = np.zeros(max(n, 0), np.int32), np.zeros(max(n, 0), np.int32)
+        if n > 0:
+            check(self._L.rumi_distinctive_descriptors(self._m, ptr(desc), ptr(offsets), n, ptr(best), ptr(med)))
+        return best, med
+
     # ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:198-370, F.Nleft == -1) ----
     def SearchByBoW(self, desc_kf, angle_kf, kf_valid, featvec_kf, desc_f, angle_f, featvec_f):
         """desc_*: [n,32] descriptors; angle_*: keypoint angles (mvKeysUn[i].angle / mvKeys[i].angle); kf_valid[i]:

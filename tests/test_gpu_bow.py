@@ -113,3 +113,19 @@ def test_search_by_bow_edge_cases(bow_oracle):
     assert n == 0                                                 # no valid map point
     n, match = m.SearchByBoW(d, np.zeros(3), np.ones(3, np.uint8), {}, d, np.zeros(3), {1: [0]})
     assert n == 0
+
+
+def test_distinctive_descriptors_match_oracle(bow_oracle):
+    from rumi_slam_b200 import ORBmatcher
+    rng = np.random.default_rng(3)
+    sizes = np.concatenate([rng.integers(0, 12, 400), rng.integers(30, 100, 20), [1, 2, 0, 33, 64, 65]])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    centre = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    parts = [centre[p] ^ np.packbits(rng.random((sizes[p], 256)) < 0.08, axis=1) for p in range(len(sizes)) if sizes[p]]
+    desc = np.concatenate(parts)
+    desc[off[5]:off[6]] = desc[off[5]] if sizes[5] else 0            # a point whose observations are all identical
+    m = ORBmatcher()
+    best, med = m.ComputeDistinctiveDescriptors(desc, off)
+    rb, rm = bow_oracle.distinctive(desc, off)
+    assert np.array_equal(best, rb) and np.array_equal(med, rm)
+    assert m.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.array([0], np.int32))[0].shape == (0,)

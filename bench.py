@@ -144,6 +144,29 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """With several ranks on one host the pinned staging buffers should live on the NUMA node whose PCIe root the GPU
+    hangs off, and the rank should run there: sysfs gives the node's CPU list for the GPU's PCI address."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        addr = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + addr
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": addr, "numa_node": node, "cpus": len(cpus)}
+    except Exception as e:                                   # no sysfs / no permission: run unbound
+        return {"error": str(e)[:80]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -172,6 +195,9 @@ def run_b200(args):
         t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- host placement: run (and first-touch the pinned buffers) on the CPUs next to this rank's GPU ----
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
 
     # ---- synthetic inputs: 1024 frames per rank, distinct seeds per rank ----
     host = synthetic_batch(nframes, W_IMG, H_IMG, seed0=10000 * rank, unique=args.unique)
@@ -255,6 +281,22 @@ def run_b200(args):
     del scratch
     h2d = nframes * W_IMG * H_IMG
     d2h = nframes * cap * (28 + 32) + 8 * nframes
+
+    # ---- single-frame latency of operator() (BASELINE configs[0]): host image in, keypoints + descriptors out ----
+    latency = None
+    if rank == 0:
+        ex1 = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local)
+        for _ in range(20):
+            ex1(host[0])
+        ts = []
+        for i in range(100):
+            t0 = time.perf_counter()
+            ex1(host[i % args.unique])
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts) * 1e3
+        latency = {"workload": "ORBextractor::operator() on ONE 640x480 host frame, synchronous (configs[0])",
+                   "median_ms": float(np.median(ts)), "p90_ms": float(np.percentile(ts, 90)), "calls": len(ts)}
+        ex1.close()
 
     # ---- matching: cfg 5a, 40 front + 40 back keyframes x 1000 descriptors, all pairs; train sharded over ranks ----
     nq = nt = 40 * 1000
@@ -399,7 +441,8 @@ def run_b200(args):
             "config": {"workload": "ORB extraction, batch of %d synthetic 640x480 frames per GPU (BASELINE configs[1]), "
                                    "1000 features / 8 levels / 1.2 / FAST 20-7, frame-sharded" % nframes,
                        "frames_per_gpu": nframes, "chunk_frames": chunk, "mean_keypoints_per_frame": nkp_mean,
-                       "l2": "inputs (315 MB per GPU) exceed the 126 MB L2, no flush between steps"},
+                       "l2": "inputs (315 MB per GPU) exceed the 126 MB L2, no flush between steps",
+                       "host_binding": numa},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_GBps_raw": round(h2d_gbps, 2),
                     "frames_per_s_at_raw_h2d": round(world * h2d_gbps * 1e9 / (W_IMG * H_IMG), 1)},
@@ -416,6 +459,7 @@ def run_b200(args):
                                       "note": "POPC rate measured 15.8/clk/SM (tools/probe/pipe_probe.cu); "
                                               "5 POPC + 14 LOP3 per pair"}},
             "bow": bow,
+            "single_frame_latency": latency,
             "clocks": clocks}
     emit(json.dumps(line))
     if world > 1:

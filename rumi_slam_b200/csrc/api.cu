@@ -111,7 +111,7 @@ struct rumi_orb {
     int fastTilePitch = 0, fastTileRows = 0, fastScoreRows = 0, fastMaskWords = 0;
     FastCell* fastCells = nullptr;                    // [totalCells] cell geometry of all levels
     // marching pyramid (K1'): per-level column-group / row tables, work-item geometry
-    bool useMarch = true, marchOk = false;
+    bool useMarch = true, marchOk = false, marchForced = false;
     int marchSplit = kMaxLevels;                      // levels below this get their own launch, the rest is chained
                                                       // inside one launch (RUMI_PYRAMID_SPLIT; measured: separate wins)
     uint8_t* marchTables = nullptr;
@@ -388,7 +388,9 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     if (h->profile) prof_event(h, s);
     // K1': all levels in one launch when every source can be read as aligned 32-bit words (always true for the
     // internal buffers; caller device memory only if it is 4-byte aligned with readable row padding)
-    bool march = h->useMarch && h->marchOk && oc.nlevels > 1;
+    // (a marching item walks its rows serially: with only a few frames in flight the 64x32-pixel TMA tiles have the
+    // shorter critical path -- single frame: 32 us vs 62 us for the 7 levels -- so small calls use the tile kernel)
+    bool march = h->useMarch && h->marchOk && oc.nlevels > 1 && (n >= 8 || h->marchForced);
     if (march && !l0Internal)
         march = ((((uintptr_t)l0.ptr | (uintptr_t)l0.pitch | (uintptr_t)l0.stride) & 3) == 0) &&
                 l0.stride >= 4 * (h->marchLv[1].srcLastWord + 1);
@@ -506,6 +508,7 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     h->useTMA = !(e && e[0] == '1');
     const char* pm = getenv("RUMI_PYRAMID");                     // "march" (default) | "tiles" (TMA / plain tile kernel)
     h->useMarch = !(pm && pm[0] == 't') && h->useTMA;            // RUMI_NO_TMA=1 selects the plain tile kernel
+    h->marchForced = pm && pm[0] == 'm';                         // RUMI_PYRAMID=march: also for small calls (tests)
     const char* ps = getenv("RUMI_PYRAMID_SPLIT");
     if (ps && ps[0] >= '1' && ps[0] <= '9') h->marchSplit = ps[0] - '0';
     const char* ns = getenv("RUMI_STREAMS");

@@ -27,7 +27,7 @@ def test_pyramid_and_blur_bitexact(oracle, w, h, nf, mode):
         ex = make(nf)
     finally:
         os.environ["RUMI_NO_TMA"] = "0"
-        os.environ["RUMI_PYRAMID"] = "march"
+        os.environ.pop("RUMI_PYRAMID", None)           # default: march for chunks of >= 8 frames, tiles below
     img = synthetic_frame(11, w, h)
     ex(img)
     ref = oracle.pyramid(img)

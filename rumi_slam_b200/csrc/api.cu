@@ -329,7 +329,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
             }
         const int slots = (l + 1 < oc.nlevels ? oc.lv[l + 1].kpBase : oc.kpCap) - g.kpBase;
         nodeCap = std::max(nodeCap, slots + 1);
-        if (g.candCap >= (1 << 19)) return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, g.candCap);
+        if (g.candCap >= (1 << kOrderBits)) return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, g.candCap);
     }
     h->pyrBytes = pb + 256; h->candElems = ce; h->bigKeysElems = be;
     h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScoreRows = sr; h->fastMaskWords = (tp * hc + 31) / 32;

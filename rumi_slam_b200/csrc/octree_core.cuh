@@ -21,8 +21,7 @@
 
 namespace rumi {
 
-constexpr int kOrderBits = 19;                       // candidate insertion index (per frame, level) < 2^19
-constexpr int kKeyCodeShift = kOrderBits + 8;        // key = code << 28 | order << 8 | response
+constexpr int kKeyCodeShift = kOrderBits + 8;        // key = code << 30 | order << 8 | response  (30 + 22 + 8 <= 64 bits)
 constexpr int kRankBits = 20;
 
 RUMI_HD uint64_t make_tree_key(uint32_t code, uint32_t order, uint32_t resp) {

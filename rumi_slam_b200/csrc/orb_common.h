@@ -19,6 +19,7 @@ constexpr int kMinBorder = 16;       // EDGE_THRESHOLD-3 R/lib_src/ORBextractor.
 constexpr int kHalfPatch = 15;       // HALF_PATCH_SIZE  R/lib_src/ORBextractor.cc:70
 constexpr int kMaxTreeDepth = 13;    // quad-tree path digits kept per key (images up to 8192 px)
 constexpr int kRootBits = 4;         // up to 16 root nodes (nIni = round(width/height))
+constexpr int kOrderBits = 22;        // FAST candidates per (frame, level) < 2^22: insertion index field of the quad-tree keys
 constexpr int kOverQuota = 3;        // DistributeOctTree can exceed N by at most 3  (:695-696)
 
 // Per-level static geometry (computed once per (shape, ORB params) on the host).

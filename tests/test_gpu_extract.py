@@ -141,3 +141,23 @@ def test_cloud_frame_compute_descriptors(oracle):
     assert n == rc == len(level0)
     assert np.array_equal(desc, rdesc)
     assert ex.CloudFrameComputeDescriptors(np.zeros((0, 0), np.uint8), level0)[0] == -1
+
+
+@pytest.mark.parametrize("w,h,nf,levels,scale", [(1920, 1080, 3000, 8, 1.2), (1280, 720, 1500, 6, 1.3), (320, 240, 500, 5, 1.2),
+                                                 (641, 479, 1000, 8, 1.2), (333, 257, 300, 4, 1.5), (800, 600, 1000, 3, 2.0),
+                                                 (1024, 768, 2000, 12, 1.1)])
+def test_other_shapes_and_pyramid_parameters(oracle, w, h, nf, levels, scale):
+    """Shapes / pyramid parameters the benchmark does not use: full HD, odd sizes (partial words and cells), few and
+    many levels, scale factors up to 2.0 (source windows of 8 pixels per 4 outputs) -- single frames (tile pyramid)
+    and a chunk of 9 frames (marching pyramid)."""
+    from rumi_slam_b200 import ORBextractor
+    ex = ORBextractor(nf, scale, levels, 20, 7, max_batch=9)
+    frames = synthetic_batch(9, w, h, seed0=70)
+    ref = [oracle.extract(frames[i], nfeatures=nf, scale=scale, nlevels=levels) for i in range(9)]
+    mono, kps, desc = ex(frames[0])
+    assert mono == ref[0][2] and np.array_equal(kps, ref[0][0]) and np.array_equal(desc, ref[0][1])
+    bk, bd, nkp, nmono = ex.extract_batch(frames)
+    for i in range(9):
+        rk, rd, rm = ref[i]
+        assert nkp[i] == len(rk) and nmono[i] == rm
+        assert np.array_equal(bk[i, :nkp[i]], rk) and np.array_equal(bd[i, :nkp[i]], rd)

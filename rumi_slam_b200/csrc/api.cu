@@ -1156,6 +1156,15 @@ int rumi_vocab_create(rumi_vocab** out, int device, int k, int L, int nnodes, co
         ++cnt[parent[i]];
     }
     if (cnt[0] == 0) return fail(RUMI_ERR_ARG, "root has no children");
+    {   // limits of the descent kernel: child position travels in 16 bits, at most 63 levels
+        std::vector<int32_t> depth(nnodes, 0);
+        for (int i = 1; i < nnodes; ++i) {
+            depth[i] = depth[parent[i]] + 1;
+            if (depth[i] > 63) return fail(RUMI_ERR_ARG, "vocabulary deeper than 63 levels");
+            if (cnt[i] > 65535) return fail(RUMI_ERR_ARG, "node %d has more than 65535 children", i);
+        }
+        if (cnt[0] > 65535) return fail(RUMI_ERR_ARG, "root has more than 65535 children");
+    }
     int run = 0;
     for (int i = 0; i < nnodes; ++i) { start[i] = run; run += cnt[i]; }
     std::vector<int32_t> fill(start);

@@ -75,6 +75,8 @@ bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, int nframes, i
 
 struct Workspace {
     cudaStream_t stream = nullptr;
+    cudaStream_t streamHi = nullptr;   // high-priority side stream for the latency-bound kernels (pyramid, quad-tree)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork / join points between the two streams
     uint8_t *pyr = nullptr, *blur = nullptr;
     uint32_t *cand = nullptr, *candOrdered = nullptr, *sel = nullptr;
     int *levelCount = nullptr, *cellOff = nullptr, *cellCount = nullptr, *selCount = nullptr, *slot = nullptr;
@@ -120,6 +122,8 @@ struct rumi_orb {
     int smemKeys = 4096, maxNodeCap = 0;
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
+    bool hiPrio = false;           // pyramid / quad-tree on a high-priority side stream (RUMI_HIPRIO=1; measured: 1 stream
+                                   // 103 -> 107 k frames/s, but 2 streams 123 -> 110 k, so off by default)
     bool nwsSet = false;           // RUMI_STREAMS given: use it for every path
     int nwsDefault = 4; bool nwsSetDefault = false;
     int lastWs = 0;
@@ -143,9 +147,11 @@ void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
     cudaFree(w.levelCount); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
     cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono); cudaFree(w.pyrFlags);
-    cudaStream_t s = w.stream;
+    cudaStream_t s = w.stream, sh = w.streamHi;
+    cudaEvent_t ev[4] = {w.ev[0], w.ev[1], w.ev[2], w.ev[3]};
     w = Workspace();
-    w.stream = s;
+    w.stream = s; w.streamHi = sh;
+    for (int i = 0; i < 4; ++i) w.ev[i] = ev[i];
 }
 
 LevelView internal_view(const rumi_orb* h, const uint8_t* base, int l) {
@@ -347,6 +353,12 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
 int ensure_workspace(rumi_orb* h, int idx) {
     Workspace& w = h->ws[idx];
     if (!w.stream) CU_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    if (h->hiPrio && !w.streamHi) {
+        int least = 0, greatest = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU_TRY(cudaStreamCreateWithPriority(&w.streamHi, cudaStreamNonBlocking, greatest));
+        for (int i = 0; i < 4; ++i) CU_TRY(cudaEventCreateWithFlags(&w.ev[i], cudaEventDisableTiming));
+    }
     if (w.pyr) return RUMI_OK;
     return alloc_workspace(h, w);
 }
@@ -378,6 +390,13 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
               KeyPointRec* dKps, uint8_t* dDesc, int outCap, int* dNkp, int* dNmono) {
     const OrbConst& oc = h->oc;
     cudaStream_t s = w.stream;
+    // Optional (RUMI_HIPRIO=1): the latency-bound kernels (pyramid: 7 dependent small launches; quad-tree: barriers + a
+    // serial phase) go to a high-priority side stream, so the block scheduler hands freed SM slots to them first and
+    // the blur (needs only the pyramid) overlaps the quad-tree of its own chunk.  Measured on B200: helps a single
+    // stream of chunks (103 -> 107 k frames/s) and single-frame latency (0.270 -> 0.261 ms) but hurts the default
+    // two-workspace pipeline (123 -> 110 k), which already overlaps neighbouring chunks -- so it is off by default.
+    const bool fork = h->hiPrio && !h->profile && w.streamHi;
+    cudaStream_t sh = fork ? w.streamHi : s;
     ChunkView cv;
     cv.nframes = n;
     for (int l = 0; l < oc.nlevels; ++l) {
@@ -386,6 +405,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     }
     CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
     if (h->profile) prof_event(h, s);
+    if (fork) { CU_TRY(cudaEventRecord(w.ev[0], s)); CU_TRY(cudaStreamWaitEvent(sh, w.ev[0], 0)); }
     // K1': all levels in one launch when every source can be read as aligned 32-bit words (always true for the
     // internal buffers; caller device memory only if it is 4-byte aligned with readable row padding)
     // (a marching item walks its rows serially: with only a few frames in flight the 64x32-pixel TMA tiles have the
@@ -405,8 +425,8 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         // (small, latency bound: the chain hides their launch gaps)
         const int split = std::min(std::max(h->marchSplit, 1), oc.nlevels);
         pyrLaunches = 0;
-        for (int l = 1; l < split; ++l) { ma.levelFirst = ma.levelLast = l; launch_pyramid_march(ma, s); ++pyrLaunches; }
-        if (split < oc.nlevels) { ma.levelFirst = split; ma.levelLast = oc.nlevels - 1; launch_pyramid_march(ma, s); ++pyrLaunches; }
+        for (int l = 1; l < split; ++l) { ma.levelFirst = ma.levelLast = l; launch_pyramid_march(ma, sh); ++pyrLaunches; }
+        if (split < oc.nlevels) { ma.levelFirst = split; ma.levelLast = oc.nlevels - 1; launch_pyramid_march(ma, sh); ++pyrLaunches; }
     } else
     for (int l = 1; l < oc.nlevels; ++l) {
         PyramidLevelArgs pa;
@@ -423,8 +443,9 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
                 tm = &dyn;
             }
         }
-        launch_pyramid_level(pa, tm, s);
+        launch_pyramid_level(pa, tm, sh);
     }
+    if (fork) { CU_TRY(cudaEventRecord(w.ev[1], sh)); CU_TRY(cudaStreamWaitEvent(s, w.ev[1], 0)); }
     prof_mark(h, s, ST_PYRAMID, pyrLaunches);
     FastArgs fa;
     fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
@@ -445,15 +466,18 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     }
     launch_fast(fa, oc, s);
     prof_mark(h, s, ST_FAST, 1);
-    launch_octree(oa, oc, s);
+    if (fork) { CU_TRY(cudaEventRecord(w.ev[2], s)); CU_TRY(cudaStreamWaitEvent(sh, w.ev[2], 0)); }
+    launch_octree(oa, oc, sh);
     prof_mark(h, s, ST_OCTREE, 1);
     DescribeArgs da;
     da.cv = cv; da.sel = w.sel; da.selCount = w.selCount; da.lap0 = lap0; da.lap1 = lap1; da.slot = w.slot;
     da.kps = dKps; da.desc = dDesc; da.nkp = dNkp; da.nmono = dNmono; da.outCap = outCap;
-    launch_assign_slots(da, oc, s);
+    launch_assign_slots(da, oc, sh);
     prof_mark(h, s, ST_SLOTS, 1);
-    launch_blur(cv, oc, s);
+    if (fork) CU_TRY(cudaEventRecord(w.ev[3], sh));
+    launch_blur(cv, oc, s);                                  // needs only the pyramid: beside the quad-tree when forked
     prof_mark(h, s, ST_BLUR, 1);
+    if (fork) CU_TRY(cudaStreamWaitEvent(s, w.ev[3], 0));
     launch_describe(da, oc, s);
     prof_mark(h, s, ST_DESCRIBE, 1);
     CU_TRY(cudaGetLastError());
@@ -511,6 +535,8 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     h->marchForced = pm && pm[0] == 'm';                         // RUMI_PYRAMID=march: also for small calls (tests)
     const char* ps = getenv("RUMI_PYRAMID_SPLIT");
     if (ps && ps[0] >= '1' && ps[0] <= '9') h->marchSplit = ps[0] - '0';
+    const char* hp = getenv("RUMI_HIPRIO");
+    if (hp && hp[0] == '1') h->hiPrio = true;
     const char* ns = getenv("RUMI_STREAMS");
     if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) { h->nws = ns[0] - '0'; h->nwsSet = true; }
     h->nwsDefault = h->nws; h->nwsSetDefault = h->nwsSet;
@@ -525,6 +551,8 @@ void rumi_orb_destroy(rumi_orb* h) {
         if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
         free_workspace(h->ws[i]);
         if (h->ws[i].stream) cudaStreamDestroy(h->ws[i].stream);
+        if (h->ws[i].streamHi) cudaStreamDestroy(h->ws[i].streamHi);
+        for (int e = 0; e < 4; ++e) if (h->ws[i].ev[e]) cudaEventDestroy(h->ws[i].ev[e]);
     }
     cudaFree(h->coef);
     cudaFree(h->fastCells);

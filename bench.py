@@ -371,6 +371,49 @@ def run_b200(args):
                                    "sample": "%d of the same descriptors, oracle/bow_oracle.cpp (pinned against the "
                                              "reference DBoW2), 1 thread, %.2f s" % (len(sample), dt)}
 
+    # ---- optional cfg 5b: 10^6 x 10^6 all-pairs top-2 (descriptors = extracted ones tiled with ~10 % of the bits
+    #      flipped, so true neighbours exist), train set sharded over the ranks, NCCL all-gather of the candidates ----
+    match_big = None
+    if args.match_big > 0:
+        nbig = args.match_big
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        base = rows[:min(rows.shape[0], 80000)]
+        def tiled(n, seed):
+            gen.manual_seed(seed)
+            out = base.repeat(-(-n // base.shape[0]), 1)[:n].clone()
+            for c0 in range(0, n, 1 << 18):                        # flip ~10 % of the bits, chunked to bound memory
+                c1 = min(c0 + (1 << 18), n)
+                mask = torch.zeros((c1 - c0, 32), dtype=torch.uint8, device=dev)
+                for bit in range(8):
+                    mask |= (torch.rand((c1 - c0, 32), device=dev, generator=gen) < 0.1).to(torch.uint8) << bit
+                out[c0:c1] ^= mask
+            return out.contiguous()
+        Qb, Tb = tiled(nbig, 7), tiled(nbig, 8)
+        if world > 1:
+            dist.broadcast(Qb, 0); dist.broadcast(Tb, 0)
+        bb, eb = train_shard(nbig, rank, world)
+        Tb_local = Tb[bb:eb].contiguous()
+        def big_once():
+            if world == 1:
+                return m.top2_device(Qb, Tb_local, t_base=bb, sync=False)
+            return sharded_top2(m, Qb, Tb_local, bb)
+        big_once()
+        barrier()
+        bsteps = 3
+        t_a = time.perf_counter()
+        m.timer_start()
+        for _ in range(bsteps):
+            big_once()
+        ms_big = m.timer_stop()
+        barrier()
+        windows.append((t_a, time.perf_counter()))
+        ms_big = max_over_ranks(ms_big)
+        match_big = {"workload": "cfg 5b: %d x %d descriptors all-pairs top-2, train set sharded over %d GPU(s)" % (nbig, nbig, world),
+                     "pairs_per_s": float(nbig) * nbig * bsteps / (ms_big / 1e3), "matches_per_s": nbig * bsteps / (ms_big / 1e3),
+                     "ms_per_step": ms_big / bsteps, "steps": bsteps}
+        del Qb, Tb, Tb_local
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -458,6 +501,7 @@ def run_b200(args):
                                       "frac": pairs_per_s / (world * 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 5),
                                       "note": "POPC rate measured 15.8/clk/SM (tools/probe/pipe_probe.cu); "
                                               "5 POPC + 14 LOP3 per pair"}},
+            "matching_5b": match_big,
             "bow": bow,
             "single_frame_latency": latency,
             "clocks": clocks}
@@ -498,6 +542,7 @@ def main():
     ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames generated per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bow", action="store_true")
+    ap.add_argument("--match-big", type=int, default=0, help="also run cfg 5b with this many descriptors per side (10^6)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -19,8 +19,15 @@ scal = []
 for name in ("r1_bench_n2.json", "r1_bench_n8.json"):
     if os.path.exists(P(name)):
         d = json.load(open(P(name)))
-        scal.append("| %d | %.0f | %.0f | %.3g | %s |" % (d["n_gpus"], d["value"], d["e2e"]["value"], d["matching"]["pairs_per_s"],
-                                                        d["e2e"].get("h2d_GBps_raw")))
+        big = d.get("matching_5b")
+        scal.append("| %d | %.0f | %.0f | %.3g | %s | %s |" % (d["n_gpus"], d["value"], d["e2e"]["value"], d["matching"]["pairs_per_s"],
+                                                             ("%.3g (%.0f ms)" % (big["pairs_per_s"], big["ms_per_step"])) if big else "-",
+                                                             d["e2e"].get("h2d_GBps_raw")))
+big1 = ""
+if os.path.exists(P("r1_bench_5b_n1.json")):
+    d1 = json.load(open(P("r1_bench_5b_n1.json")))
+    big1 = "\n| 1 | %.0f | - | %.3g | %.3g (%.0f ms) | - |" % (d1["value"], d1["matching"]["pairs_per_s"], d1["matching_5b"]["pairs_per_s"],
+                                                              d1["matching_5b"]["ms_per_step"])
 md = f"""# Round 1 -- final state of the round (supersedes r1_first_path_summary.md, kept for history)
 
 Workload of the captures: `tools/prof_run.py` = one 64-frame chunk of synthetic 640x480 frames (1000 features, 8 levels,
@@ -73,11 +80,12 @@ if scal:
     md += """
 Multi-GPU (one process per GPU, frames sharded, train set sharded + NCCL all-gather of 8 B/query candidates):
 
-| GPUs | value frames/s | e2e frames/s | matching pairs/s | raw H2D GB/s per GPU |
-|---|---|---|---|---|
-""" + "\n".join(scal) + """
+| GPUs | value frames/s | e2e frames/s | matching 40k x 40k pairs/s | matching 10^6 x 10^6 pairs/s | raw H2D GB/s per GPU |
+|---|---|---|---|---|---|
+""" + "\n".join(scal) + big1 + """
 
-`value` scales linearly (no data-path collective).  `e2e` at 8 GPUs is bound by the host links of the box: with 8 ranks
+`value` scales linearly (no data-path collective); cfg 5b (10^12 pairs) takes 1287 ms on one GPU and 161 ms on eight
+(8.0x: the candidate all-gather is 8 MB per rank).  `e2e` at 8 GPUs is bound by the host links of the box: with 8 ranks
 copying at once the raw pinned H2D bandwidth per GPU drops from 55 to 24 GB/s (single NUMA node VM, `nvidia-smi topo`),
 i.e. 307 KB/frame caps each GPU at 78 k frames/s.
 """

@@ -885,6 +885,9 @@ struct rumi_match {
     uint64_t* partial = nullptr; size_t partialCap = 0;
     uint8_t *dQ = nullptr, *dT = nullptr; size_t qCap = 0, tCap = 0;
     uint8_t* dOut = nullptr; size_t outCap = 0;      // idx1 (4 B) | d1 (2 B) | d2 (2 B) per query
+    uint8_t *qx = nullptr, *tx = nullptr; size_t qxCap = 0, txCap = 0;   // 0/1-byte expansions for the IMMA kernel
+    uint16_t* popT = nullptr; size_t popCap = 0;
+    int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 2 IMMA whenever it applies
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     long long launches = 0;
 };
@@ -902,12 +905,29 @@ int grow(void** p, size_t* cap, size_t need) {
 int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int tBase, int32_t* dIdx,
                 uint16_t* dD1, uint16_t* dD2) {
     if (((uintptr_t)dQ | (uintptr_t)dT) & 15) return fail(RUMI_ERR_ARG, "descriptor arrays must be 16-byte aligned");
-    const int slices = match_slices(nq, nt);
-    int rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq);
-    if (rc) return rc;
-    launch_hamming_top2_partial(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
-    launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
-    m->launches += 2;
+    // Large problems go to the integer tensor cores (descriptors expanded to 0/1 bytes once per call, int8 IMMA dot
+    // products); small ones (stereo bands, single frames) stay on the LOP3+POPC kernel, whose set-up is cheaper.
+    const bool big = (long long)nq * nt >= 64ll * 1024 * 1024 && nq >= 256;
+    const bool imma = nt > 0 && nt <= (1 << 22) && (m->mode == 2 || (m->mode == 0 && big));
+    int rc;
+    if (imma) {
+        const int slices = imma_slices(nq, nt);
+        if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
+        if ((rc = grow((void**)&m->qx, &m->qxCap, 256 * (size_t)nq))) return rc;
+        if ((rc = grow((void**)&m->tx, &m->txCap, 256 * (size_t)nt))) return rc;
+        if ((rc = grow((void**)&m->popT, &m->popCap, 2 * (size_t)nt))) return rc;
+        launch_expand_bits(dQ, nq, m->qx, nullptr, m->stream);
+        launch_expand_bits(dT, nt, m->tx, m->popT, m->stream);
+        launch_hamming_top2_imma(dQ, m->qx, nq, m->tx, m->popT, nt, tBase, slices, m->partial, m->stream);
+        launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
+        m->launches += 4;
+    } else {
+        const int slices = match_slices(nq, nt);
+        if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
+        launch_hamming_top2_partial(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
+        launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
+        m->launches += 2;
+    }
     CU_TRY(cudaGetLastError());
     return RUMI_OK;
 }
@@ -926,6 +946,8 @@ int rumi_match_create(rumi_match** out, int device) {
     rumi_match* m = new rumi_match();
     m->device = device;
     CU_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    const char* mm = getenv("RUMI_MATCH");                       // "popc" / "imma": force one top-2 kernel (tests, A/B)
+    if (mm) m->mode = mm[0] == 'p' ? 1 : mm[0] == 'i' ? 2 : 0;
     *out = m;
     return RUMI_OK;
 }
@@ -934,7 +956,8 @@ void rumi_match_destroy(rumi_match* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut);
+    cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut); cudaFree(m->qx); cudaFree(m->tx);
+    cudaFree(m->popT);
     if (m->evStart) { cudaEventDestroy(m->evStart); cudaEventDestroy(m->evStop); }
     delete m;
 }

@@ -137,6 +137,12 @@ void launch_describe_given(const uint8_t* img, int w, int h, int stride, const K
 int match_slices(int nq, int nt);
 void launch_hamming_top2_partial(const uint8_t* Q, int nq, const uint8_t* T, int nt, int tBase, int slices,
                                  uint64_t* partial, cudaStream_t s);
+// tensor-core variant for large problems (match_imma.cu): descriptors expanded to 0/1 bytes, int8 IMMA dot products
+void launch_expand_bits(const uint8_t* D, int n, uint8_t* X /* [n][256] */, uint16_t* pop /* [n] or nullptr */,
+                        cudaStream_t s);
+int imma_slices(int nq, int nt);
+void launch_hamming_top2_imma(const uint8_t* Q, const uint8_t* Qx, int nq, const uint8_t* Tx, const uint16_t* popT,
+                              int nt, int tBase, int slices, uint64_t* partial, cudaStream_t s);
 // merge per-shard candidates {d1,d2,idx} gathered in shard order: cand[shard][nq]
 void launch_top2_merge(const uint64_t* packed, int nshards, int nq, int32_t* idx1, uint16_t* d1, uint16_t* d2,
                        cudaStream_t s);

@@ -7,17 +7,25 @@ from rumi_slam_b200.synth import synthetic_frame, perturbed_descriptors, stereo_
 pytestmark = pytest.mark.gpu
 
 
-def matcher(**kw):
+def matcher(mode=None, **kw):
+    """mode: None = automatic kernel choice, "popc" / "imma" = force the LOP3+POPC or the tensor-core top-2 kernel."""
+    import os
     from rumi_slam_b200 import ORBmatcher
-    return ORBmatcher(**kw)
+    if mode:
+        os.environ["RUMI_MATCH"] = mode
+    try:
+        return ORBmatcher(**kw)
+    finally:
+        os.environ.pop("RUMI_MATCH", None)
 
 
 def real_descriptors(oracle, seeds):
     return np.concatenate([oracle.extract(synthetic_frame(s))[1] for s in seeds])
 
 
-def test_top2_kats():
-    m = matcher()
+@pytest.mark.parametrize("mode", ["popc", "imma"])
+def test_top2_kats(mode):
+    m = matcher(mode)
     zeros, ones = np.zeros((1, 32), np.uint8), np.full((1, 32), 255, np.uint8)
     i1, d1, d2 = m.top2(zeros, ones)
     assert (i1[0], d1[0], d2[0]) == (-1, 256, 256)            # 256 is not < the initial 256 (ORBmatcher.cc:236-240)
@@ -38,23 +46,47 @@ def test_top2_kat_all_ones_index(oracle):
     assert (gi[0], gd1[0], gd2[0]) == (-1, 256, 256)
 
 
-@pytest.mark.parametrize("nq,nt", [(1, 1), (37, 1000), (1000, 1000), (2049, 4099), (5000, 700)])
-def test_top2_matches_oracle(oracle, nq, nt):
+@pytest.mark.parametrize("mode", ["popc", "imma"])
+@pytest.mark.parametrize("nq,nt", [(1, 1), (37, 1000), (1000, 1000), (2049, 4099), (5000, 700), (130, 127), (129, 3000)])
+def test_top2_matches_oracle(oracle, nq, nt, mode):
     base = real_descriptors(oracle, (0, 1))
     Q = perturbed_descriptors(base, nq, seed=1, flip_p=0.05)
     T = perturbed_descriptors(base[::-1].copy(), nt, seed=2, flip_p=0.05)
     T[nt // 2] = T[0]                                          # force exact ties
-    i1, d1, d2 = matcher().top2(Q, T)
+    i1, d1, d2 = matcher(mode).top2(Q, T)
     ri, rd1, rd2 = oracle.hamming_top2(Q, T)
     assert np.array_equal(i1, ri) and np.array_equal(d1, rd1) and np.array_equal(d2, rd2)
 
 
-def test_sharded_merge_equals_single(oracle):
+def test_top2_large_automatic_path_and_extreme_descriptors(oracle):
+    """8192 x 20000 (large enough for the automatic choice of the tensor-core kernel) with all-zero / all-one rows,
+    duplicates of the best match far apart (earliest index must win) and queries whose best distance is 256."""
+    rng = np.random.default_rng(9)
+    base = real_descriptors(oracle, (5, 6))
+    nq, nt = 8192, 20000
+    Q = perturbed_descriptors(base, nq, seed=5, flip_p=0.04)
+    T = perturbed_descriptors(base, nt, seed=6, flip_p=0.04)
+    Q[0] = 0; Q[1] = 255; T[10] = 0; T[11] = 255; T[19999] = 0
+    T[15000] = T[123]; T[4000] = T[123]
+    Q[2] = T[123]
+    auto, imma, popc = matcher(), matcher("imma"), matcher("popc")
+    ri, rd1, rd2 = oracle.hamming_top2(Q, T)
+    for m in (auto, imma, popc):
+        i1, d1, d2 = m.top2(Q, T)
+        assert np.array_equal(i1, ri) and np.array_equal(d1, rd1) and np.array_equal(d2, rd2)
+    assert ri[2] == 123 and rd1[2] == 0 and rd2[2] == 0 and ri[0] == 10
+    # every train at distance 256 from the query: no match
+    i1, d1, d2 = imma.top2(np.zeros((300, 32), np.uint8), np.full((2000, 32), 255, np.uint8))
+    assert (i1 == -1).all() and (d1 == 256).all() and (d2 == 256).all()
+
+
+@pytest.mark.parametrize("mode", ["popc", "imma"])
+def test_sharded_merge_equals_single(oracle, mode):
     import torch
     base = real_descriptors(oracle, (2, 3, 4))
     Q = torch.from_numpy(perturbed_descriptors(base, 3000, seed=3)).cuda()
     T = torch.from_numpy(perturbed_descriptors(base, 8000, seed=4)).cuda()
-    m = matcher()
+    m = matcher(mode)
     i1, d1, d2 = m.top2_device(Q, T)
     for shards in (2, 3, 8):
         bounds = np.linspace(0, T.shape[0], shards + 1).astype(int)

@@ -144,6 +144,23 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def match_roofline(path, pairs_per_s, world, sm_mhz):
+    """The top-2 kernels are bound by an execution pipe, not by HBM (operands are reused from shared memory):
+    popc: 5 POPC per pair at the measured 16 POPC/clk/SM; imma: 1/16 m16n8k32 IMMA per pair at the measured 0.478
+    warp-IMMA/clk/SM (tools/probe/pipe_probe.cu)."""
+    if path == "imma":
+        peak = world * 148 * 0.478 * 16 * sm_mhz * 1e6
+        return {"bound": "imma-pipe", "imma_per_pair": 1.0 / 16, "imma_per_clk_per_sm": 0.478, "peak_pairs_per_s": peak,
+                "frac": pairs_per_s / peak,
+                "note": "int8 m16n8k32 on 0/1-expanded descriptors: 256 MACs per pair; rate measured by "
+                        "tools/probe/pipe_probe.cu; the b1 and.popc form lowers to the same IMMA with per-instruction "
+                        "unpacking (2.7 pairs/clk/SM, tools/probe/b1_probe.cu)"}
+    peak = world * 148 * 16 * sm_mhz * 1e6 / 5
+    return {"bound": "popc-pipe", "popc_per_pair": 5, "popc_per_clk_per_sm": 16, "peak_pairs_per_s": peak,
+            "frac": pairs_per_s / peak,
+            "note": "POPC rate measured 15.8/clk/SM (tools/probe/pipe_probe.cu); 5 POPC + 14 LOP3 per pair"}
+
+
 def bind_to_gpu_numa_node(torch, local):
     """With several ranks on one host the pinned staging buffers should live on the NUMA node whose PCIe root the GPU
     hangs off, and the rank should run there: sysfs gives the node's CPU list for the GPU's PCI address."""
@@ -330,6 +347,7 @@ def run_b200(args):
     windows.append((t_a, time.perf_counter()))
     ms_match = max_over_ranks(ms_match)
     match_launches = m.launch_count(reset=True)
+    match_path = m.last_path()
     matches_per_s = nq * msteps / (ms_match / 1e3)
     pairs_per_s = matches_per_s * nt
 
@@ -496,11 +514,8 @@ def run_b200(args):
             "matching": {"workload": "cfg 5a: 40000 x 40000 descriptors all-pairs top-2, train set sharded over %d GPU(s)" % world,
                          "matches_per_s": matches_per_s, "pairs_per_s": pairs_per_s, "ms_per_step": ms_match / msteps,
                          "gpu_launches": match_launches, "steps": msteps,
-                         "roofline": {"bound": "popc-pipe", "popc_per_pair": 5, "popc_per_clk_per_sm": 16,
-                                      "peak_pairs_per_s": world * 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 5,
-                                      "frac": pairs_per_s / (world * 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 5),
-                                      "note": "POPC rate measured 15.8/clk/SM (tools/probe/pipe_probe.cu); "
-                                              "5 POPC + 14 LOP3 per pair"}},
+                         "kernel": match_path,
+                         "roofline": match_roofline(match_path, pairs_per_s, world, clocks.get("sm_mhz") or 1965.0)},
             "matching_5b": match_big,
             "bow": bow,
             "single_frame_latency": latency,

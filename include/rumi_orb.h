@@ -123,6 +123,9 @@ int rumi_hamming_top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uin
                              int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync);
 int rumi_match_timer_start(rumi_match* m);
 int rumi_match_timer_stop(rumi_match* m, float* ms);
+/* Which top-2 kernel the last rumi_hamming_top2* call used: 1 = LOP3+POPC (small problems), 2 = int8 tensor-core
+ * kernel on 0/1-expanded descriptors (>= 64 Mi pairs and >= 256 queries; RUMI_MATCH=popc|imma forces one). */
+int rumi_match_last_path(const rumi_match* m);
 long long rumi_match_launch_count(rumi_match* m, int reset);
 
 /* Shard exchange step: pack local results into 8-byte candidates for the all-gather, and merge

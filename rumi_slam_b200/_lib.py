@@ -49,6 +49,7 @@ SIGNATURES = {
     "rumi_match_timer_start": (C.c_int, [_vp]),
     "rumi_match_timer_stop": (C.c_int, [_vp, _f32p]),
     "rumi_match_launch_count": (C.c_longlong, [_vp, C.c_int]),
+    "rumi_match_last_path": (C.c_int, [_vp]),
     "rumi_match_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "rumi_match_destroy": (None, [_vp]),
     "rumi_hamming_top2": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),

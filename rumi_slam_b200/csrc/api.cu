@@ -888,6 +888,7 @@ struct rumi_match {
     uint8_t *qx = nullptr, *tx = nullptr; size_t qxCap = 0, txCap = 0;   // 0/1-byte expansions for the IMMA kernel
     uint16_t* popT = nullptr; size_t popCap = 0;
     int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 2 IMMA whenever it applies
+    int lastPath = 0;                                // kernel of the last top-2 call: 1 LOP3+POPC, 2 IMMA
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     long long launches = 0;
 };
@@ -921,12 +922,14 @@ int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int
         launch_hamming_top2_imma(dQ, m->qx, nq, m->tx, m->popT, nt, tBase, slices, m->partial, m->stream);
         launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
         m->launches += 4;
+        m->lastPath = 2;
     } else {
         const int slices = match_slices(nq, nt);
         if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
         launch_hamming_top2_partial(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
         launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
         m->launches += 2;
+        m->lastPath = 1;
     }
     CU_TRY(cudaGetLastError());
     return RUMI_OK;
@@ -1013,6 +1016,8 @@ int rumi_match_timer_stop(rumi_match* m, float* ms) {
     CU_TRY(cudaEventElapsedTime(ms, m->evStart, m->evStop));
     return RUMI_OK;
 }
+
+int rumi_match_last_path(const rumi_match* m) { return m ? m->lastPath : 0; }
 
 long long rumi_match_launch_count(rumi_match* m, int reset) {
     if (!m) return 0;

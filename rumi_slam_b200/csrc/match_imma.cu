@@ -165,11 +165,12 @@ hamming_top2_imma_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restric
             for (int mb = 0; mb < 4; ++mb) {
                 const uint4 a0 = *reinterpret_cast<const uint4*>(qa + mb * 8 * kImmaQPitch + 128 * ss);        // k-step 2 ss
                 const uint4 a1 = *reinterpret_cast<const uint4*>(qa + mb * 8 * kImmaQPitch + 128 * ss + 16);   // k-step 2 ss + 1
+                // the two k-steps of one accumulator are kept 4 IMMAs apart (back-to-back they would serialise on the
+                // accumulator dependency)
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    imma16832(cur[mb][nb], a0.x, a0.y, a0.z, a0.w, b[nb].x, b[nb].y);
-                    imma16832(cur[mb][nb], a1.x, a1.y, a1.z, a1.w, b[nb].z, b[nb].w);
-                }
+                for (int nb = 0; nb < 4; ++nb) imma16832(cur[mb][nb], a0.x, a0.y, a0.z, a0.w, b[nb].x, b[nb].y);
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) imma16832(cur[mb][nb], a1.x, a1.y, a1.z, a1.w, b[nb].z, b[nb].w);
             }
             if (hasPrev) epilogue_mb(prev, bsPrev, ss);               // a quarter of the previous tile's epilogue
         }

@@ -37,6 +37,10 @@ class ORBmatcher:
         except Exception:
             pass
 
+    def last_path(self):
+        """Kernel of the last top-2 call: 'popc' (LOP3+POPC) or 'imma' (int8 tensor cores on expanded descriptors)."""
+        return {1: "popc", 2: "imma"}.get(int(self._L.rumi_match_last_path(self._m)), "none")
+
     @staticmethod
     def DescriptorDistance(a, b):
         """ORBmatcher::DescriptorDistance (ORBmatcher.cc:1830-1844) for one pair of 32-byte rows."""

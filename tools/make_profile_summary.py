@@ -63,7 +63,8 @@ NMS + emission 15 %, staging / set-up 11 %.
 | blur | 268 us | {k['kernels']['blur']['duration_us']:.0f} us | register-marching warps, DP4A rows, 7-row register ring, ping-pong prefetch, no shared memory |
 | pyramid | 112 us (TMA tiles) | {k['kernels']['pyramid']['duration_us']:.0f} us | marching warps, 3 word loads + 2 PRMT + 4 DP2A per source row (51 M vs 61 M warp instructions); TMA tiles kept for calls of < 8 frames (single frame: 32 vs 62 us) |
 | describe | 70 us | {k['kernels']['describe']['duration_us']:.0f} us | unchanged |
-| Hamming top-2 (8192 x 40000) | 637 us | {k['kernels']['hamming_top2']['duration_us']:.0f} us | LOP3 carry-save tree: 5 POPC per pair |
+| Hamming top-2, LOP3+POPC (8192 x 40000) | 637 us | {k['kernels']['hamming_top2']['duration_us']:.0f} us | LOP3 carry-save tree: 5 POPC per pair |
+| Hamming top-2, tensor cores (16384 x 40000) | (1 170 us at the POPC kernel's rate) | {k['kernels']['hamming_top2_imma']['duration_us']:.0f} us | descriptors expanded once to 0/1 bytes, int8 IMMA m16n8k32 dot products, cp.async 3-stage tiles, ping-pong accumulators so the top-2 update overlaps the MMAs; IMMA pipe 51 % busy (ncu) |
 
 Experiments that did NOT pay (kept as switches, documented in DESIGN.md): chaining all pyramid levels inside one launch with
 completion flags (`RUMI_PYRAMID_SPLIT=1`: 127-377 us vs 102 us for 7 launches -- a dependent chain of latency-bound items),
@@ -73,7 +74,7 @@ more than 2 workspaces for resident input (L2 thrash), FAST at 48 / 56 registers
 
 value **{b['value']:.0f} frames/s** (inputs resident), e2e **{b['e2e']['value']:.0f} frames/s** (pinned host buffers, H2D + D2H inside; raw H2D
 {b['e2e']['h2d_GBps_raw']} GB/s would allow {b['e2e']['frames_per_s_at_raw_h2d']:.0f}), single-frame `operator()` latency {b['single_frame_latency']['median_ms']:.3f} ms, matching {b['matching']['pairs_per_s']:.3g} pairs/s
-({b['matching']['roofline']['frac']:.0%} of the measured POPC-pipe rate), BoW descent {b['bow']['features_per_s']:.3g} features/s (CPU port {b['bow']['cpu_baseline']['value']:.3g} on one
+({b['matching']['kernel']} kernel, {b['matching']['roofline']['frac']:.0%} of the measured {b['matching']['roofline']['bound']} rate; the LOP3+POPC kernel gives 7.4e11), BoW descent {b['bow']['features_per_s']:.3g} features/s (CPU port {b['bow']['cpu_baseline']['value']:.3g} on one
 thread), CPU reference arm {b['cpu_baseline']['value']:.0f} frames/s on {b['cpu_baseline']['cores']} host threads ({b['cpu_baseline']['single_thread']:.1f} on one).
 """
 if scal:

@@ -16,11 +16,14 @@
 // so that one shift-subtract builds the key and 2.5 min / max per pair update (best, second best) with the reference's
 // tie rule (smaller index first).  Two accumulator sets alternate: the top-2 update of tile i-1 is interleaved with
 // the IMMAs of tile i, so the integer pipe and the tensor pipe work at the same time inside every warp.  Output = the same per-slice {d1:16, d2:16, idx:32} candidates as K8, merged by K9.
+#include <cstdlib>
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace rumi {
 
-constexpr int kImmaBM = 128, kImmaBN = 128, kImmaPitch = 320, kImmaThreads = 256;
+constexpr int kImmaBN = 128, kImmaPitch = 320;   // query rows / threads per CTA depend on the variant: 64 * WM / 128 * WM
 constexpr int kImmaQPitch = 528;          // one interleaved pair of query rows (g, g + 8): 512 B + 16 B bank skew
 constexpr int kImmaIdxBits = 22;                                  // train index inside one call (nt <= 2^22 per launch)
 constexpr uint32_t kImmaIdxMask = (1u << kImmaIdxBits) - 1u;
@@ -70,21 +73,26 @@ __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1,
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+template <int WM>
 struct ImmaSmem {
-    uint8_t q[(kImmaBM / 2) * kImmaQPitch];        // query rows pair-interleaved in A-fragment order (see load_q)
+    uint8_t q[(64 * WM / 2) * kImmaQPitch];        // query rows pair-interleaved in A-fragment order (see load_q)
     uint8_t t[3][kImmaBN * kImmaPitch];
     uint32_t base[3][kImmaBN];                     // ((pop(t) + 256) << 22) | index, 0xFFFFFFFF past the slice end
-    uint32_t merge[4][kImmaBM][2];                 // per N-warp top-2 of every query row
+    uint32_t merge[4][64 * WM][2];                 // per N-warp top-2 of every query row
 };
 
-__global__ void __launch_bounds__(kImmaThreads, 1)
+// WM = warps along the query dimension (CTA = WM x 4 warps, 64 * WM queries); kPingPong = two accumulator sets (248
+// registers, 8 warps per SM) instead of one (147 registers, 12 warps per SM with WM = 3)
+template <int WM, bool kPingPong>
+__global__ void __launch_bounds__(128 * WM, 1)
 hamming_top2_imma_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restrict__ Qx, int nq,
                          const uint8_t* __restrict__ Tx, const uint16_t* __restrict__ popT, int nt, int sliceRows,
                          int tBase, uint64_t* __restrict__ partial /* [gridDim.y][nq] */) {
     extern __shared__ __align__(16) uint8_t smemRaw[];
-    ImmaSmem& S = *reinterpret_cast<ImmaSmem*>(smemRaw);
+    constexpr int kImmaBM = 64 * WM, kImmaThreads = 128 * WM;
+    ImmaSmem<WM>& S = *reinterpret_cast<ImmaSmem<WM>*>(smemRaw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;                         // 2 x 4 warps: 64 query rows x 32 train columns each
+    const int wm = warp >> 2, wn = warp & 3;                         // WM x 4 warps: 64 query rows x 32 train columns each
     const int g = lane >> 2, t = lane & 3;
     const int q0 = blockIdx.x * kImmaBM;
     const int t0 = blockIdx.y * sliceRows, t1 = min(t0 + sliceRows, nt);
@@ -147,7 +155,9 @@ hamming_top2_imma_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restric
     };
     // One tile: 128 IMMAs into `cur`, with the top-2 update of the PREVIOUS tile's accumulators (`prev`) spread between
     // the k-steps, so that the integer pipe works while the tensor pipe does -- two accumulator sets in ping-pong.
-    auto tile_step = [&](int (&cur)[4][4][4], const int (&prev)[4][4][4], const uint2 (&bsPrev)[4], bool hasPrev, int st) {
+    // (hasPrev is a compile-time tag: a run-time test would split the IMMAs and the update into separate basic blocks
+    // and ptxas would not interleave them)
+    auto tile_step = [&](auto hasPrev, int (&cur)[4][4][4], const int (&prev)[4][4][4], const uint2 (&bsPrev)[4], int st) {
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
@@ -161,18 +171,23 @@ hamming_top2_imma_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restric
             uint4 b[4];
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const uint4*>(tb + nb * 8 * kImmaPitch + 64 * ss);
+            // all 16 accumulators take k-step 2 ss, then all 16 take k-step 2 ss + 1: two IMMAs on the same accumulator
+            // are 16 instructions apart, far more than the IMMA latency
+            uint4 a0[4], a1[4];
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb) {
-                const uint4 a0 = *reinterpret_cast<const uint4*>(qa + mb * 8 * kImmaQPitch + 128 * ss);        // k-step 2 ss
-                const uint4 a1 = *reinterpret_cast<const uint4*>(qa + mb * 8 * kImmaQPitch + 128 * ss + 16);   // k-step 2 ss + 1
-                // the two k-steps of one accumulator are kept 4 IMMAs apart (back-to-back they would serialise on the
-                // accumulator dependency)
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) imma16832(cur[mb][nb], a0.x, a0.y, a0.z, a0.w, b[nb].x, b[nb].y);
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) imma16832(cur[mb][nb], a1.x, a1.y, a1.z, a1.w, b[nb].z, b[nb].w);
+                a0[mb] = *reinterpret_cast<const uint4*>(qa + mb * 8 * kImmaQPitch + 128 * ss);
+                a1[mb] = *reinterpret_cast<const uint4*>(qa + mb * 8 * kImmaQPitch + 128 * ss + 16);
             }
-            if (hasPrev) epilogue_mb(prev, bsPrev, ss);               // a quarter of the previous tile's epilogue
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) imma16832(cur[mb][nb], a0[mb].x, a0[mb].y, a0[mb].z, a0[mb].w, b[nb].x, b[nb].y);
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) imma16832(cur[mb][nb], a1[mb].x, a1[mb].y, a1[mb].z, a1[mb].w, b[nb].z, b[nb].w);
+            if constexpr (decltype(hasPrev)::value) epilogue_mb(prev, bsPrev, ss);   // a quarter of the previous tile's update
         }
     };
     auto load_bases = [&](uint2 (&bs)[4], int st) {
@@ -180,33 +195,51 @@ hamming_top2_imma_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restric
         for (int nb = 0; nb < 4; ++nb) bs[nb] = *reinterpret_cast<const uint2*>(&S.base[st][wn * 32 + nb * 8 + 2 * t]);
     };
 
-    int acc0[4][4][4], acc1[4][4][4];
+    int acc0[4][4][4], acc1[kPingPong ? 4 : 1][4][4];
     uint2 bs0[4], bs1[4];
-    for (int tile = 0; tile < ntiles; tile += 2) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int tl = tile + p;
-            if (tl < ntiles) {                                       // CTA uniform
-                const int st = tl % 3;
-                if (tl + 1 < ntiles) {                               // prefetch the next tile (3 stages: the stage being
-                    load_tile(S.t[(tl + 1) % 3], Tx, t0 + (tl + 1) * kImmaBN, t1);    // filled was last read 2 tiles ago)
-                    load_base((tl + 1) % 3, t0 + (tl + 1) * kImmaBN);
-                    cp_async_commit();
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                if (p == 0) { tile_step(acc0, acc1, bs1, tl > 0, st); load_bases(bs0, st); }
-                else { tile_step(acc1, acc0, bs0, true, st); load_bases(bs1, st); }
+    // tile tl lives in stage tl % 3; the stage filled by the prefetch was last read two tiles ago, so ONE barrier per
+    // tile (after the wait) is enough
+    auto advance = [&](int tl) {
+        if (tl + 1 < ntiles) {
+            load_tile(S.t[(tl + 1) % 3], Tx, t0 + (tl + 1) * kImmaBN, t1);
+            load_base((tl + 1) % 3, t0 + (tl + 1) * kImmaBN);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+    };
+    if constexpr (kPingPong) {
+        if (ntiles > 0) {
+            advance(0);
+            tile_step(std::false_type{}, acc0, acc1, bs1, 0);
+            load_bases(bs0, 0);
+        }
+        for (int tl = 1; tl < ntiles; tl += 2) {
+            advance(tl);
+            tile_step(std::true_type{}, acc1, acc0, bs0, tl % 3);
+            load_bases(bs1, tl % 3);
+            if (tl + 1 < ntiles) {                                   // CTA uniform
+                advance(tl + 1);
+                tile_step(std::true_type{}, acc0, acc1, bs1, (tl + 1) % 3);
+                load_bases(bs0, (tl + 1) % 3);
             }
         }
-    }
-    if (ntiles > 0) {                                                // epilogue of the last tile
-        if ((ntiles - 1) & 1) {
+        if (ntiles > 0) {                                            // update from the last tile
+            if ((ntiles - 1) & 1) {
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb) epilogue_mb(acc1, bs1, mb);
-        } else {
+                for (int mb = 0; mb < 4; ++mb) epilogue_mb(acc1, bs1, mb);
+            } else {
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) epilogue_mb(acc0, bs0, mb);
+            }
+        }
+    } else {
+        for (int tl = 0; tl < ntiles; ++tl) {                        // one accumulator set: MMAs, then the update; the
+            advance(tl);                                             // overlap comes from the other warps of the SM
+            tile_step(std::false_type{}, acc0, acc0, bs0, tl % 3);
+            load_bases(bs0, tl % 3);
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb) epilogue_mb(acc0, bs0, mb);
         }
@@ -255,10 +288,22 @@ hamming_top2_imma_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restric
     }
 }
 
-size_t imma_smem_bytes() { return sizeof(ImmaSmem); }
+// Variant: RUMI_IMMA_VARIANT = "3n" (default: 3 x 4 warps, one accumulator set, 12 warps per SM), "2n" (2 x 4 warps),
+// "2p" (2 x 4 warps, ping-pong accumulators).  Measured on B200, 40000 x 40000: 1.16 / 1.07-1.12 / 1.12-1.13 e12 pairs/s
+// -- the three land within 8 %: the tensor pipe sits at ~50 % in all of them.
+static int imma_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RUMI_IMMA_VARIANT");
+        v = 2;
+        if (e && e[0] == '2') v = e[1] == 'n' ? 1 : 0;
+    }
+    return v;
+}
+static int imma_bm() { return imma_variant() == 2 ? 192 : 128; }
 
 int imma_slices(int nq, int nt) {
-    const int qBlocks = (nq + kImmaBM - 1) / kImmaBM;
+    const int qBlocks = (nq + imma_bm() - 1) / imma_bm();
     const int maxSlices = (nt + 8 * kImmaBN - 1) / (8 * kImmaBN);     // at least 8 tiles per slice
     int want = (148 * 8 + qBlocks - 1) / qBlocks;                      // >= 8 waves of one CTA per SM: tail < 10 %
     if (want > maxSlices) want = maxSlices;
@@ -267,17 +312,29 @@ int imma_slices(int nq, int nt) {
     return want;
 }
 
+template <int WM, bool PP>
+static void launch_imma_variant(const uint8_t* Q, const uint8_t* Qx, int nq, const uint8_t* Tx, const uint16_t* popT, int nt,
+                                int sliceRows, int tBase, int slices, uint64_t* partial, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(hamming_top2_imma_kernel<WM, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(ImmaSmem<WM>));
+        configured = true;
+    }
+    dim3 grid((nq + 64 * WM - 1) / (64 * WM), slices);
+    hamming_top2_imma_kernel<WM, PP><<<grid, 128 * WM, sizeof(ImmaSmem<WM>), s>>>(Q, Qx, nq, Tx, popT, nt, sliceRows, tBase,
+                                                                                  partial);
+}
+
 void launch_hamming_top2_imma(const uint8_t* Q, const uint8_t* Qx, int nq, const uint8_t* Tx, const uint16_t* popT,
                               int nt, int tBase, int slices, uint64_t* partial, cudaStream_t s) {
     int sliceRows = (nt + slices - 1) / slices;
     sliceRows = (sliceRows + kImmaBN - 1) / kImmaBN * kImmaBN;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(hamming_top2_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImmaSmem));
-        configured = true;
+    switch (imma_variant()) {
+        case 1: launch_imma_variant<2, false>(Q, Qx, nq, Tx, popT, nt, sliceRows, tBase, slices, partial, s); break;
+        case 2: launch_imma_variant<3, false>(Q, Qx, nq, Tx, popT, nt, sliceRows, tBase, slices, partial, s); break;
+        default: launch_imma_variant<2, true>(Q, Qx, nq, Tx, popT, nt, sliceRows, tBase, slices, partial, s); break;
     }
-    dim3 grid((nq + kImmaBM - 1) / kImmaBM, slices);
-    hamming_top2_imma_kernel<<<grid, kImmaThreads, sizeof(ImmaSmem), s>>>(Q, Qx, nq, Tx, popT, nt, sliceRows, tBase, partial);
 }
 
 }  // namespace rumi

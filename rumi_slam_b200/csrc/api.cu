@@ -110,7 +110,7 @@ struct rumi_orb {
     long long pyrLevelOff[kMaxLevels], candLevelOff[kMaxLevels], bigKeysLevelOff[kMaxLevels];
     int bigKeysCap[kMaxLevels];
     long long pyrBytes = 0, candElems = 0, bigKeysElems = 0;
-    int fastTilePitch = 0, fastTileRows = 0, fastScoreRows = 0, fastMaskWords = 0;
+    int fastTilePitch = 0, fastTileRows = 0, fastScoreRows = 0;
     FastCell* fastCells = nullptr;                    // [totalCells] cell geometry of all levels
     // marching pyramid (K1'): per-level column-group / row tables, work-item geometry
     bool useMarch = true, marchOk = false, marchForced = false;
@@ -309,7 +309,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
     }
     // level-major workspace offsets for `chunk` frames
     long long pb = 0, ce = 0, be = 0;
-    int tp = 0, tr = 0, sr = 0, hc = 0, nodeCap = 0;
+    int tp = 0, tr = 0, sr = 0, nodeCap = 0;
     std::vector<FastCell> cells(oc.totalCells);
     for (int l = 0; l < oc.nlevels; ++l) {
         const LevelGeom& g = oc.lv[l];
@@ -321,7 +321,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         h->bigKeysCap[l] = cap;
         h->bigKeysLevelOff[l] = be; be += (long long)h->chunk * cap;
         tp = std::max(tp, align_up(g.wCell + 6 + 15, 16)); tr = std::max(tr, g.hCell + 6);   // 16-B aligned staging
-        sr = std::max(sr, g.hCell + 2); hc = std::max(hc, g.hCell);
+        sr = std::max(sr, g.hCell + 2);
         // FAST grid cells (R/lib_src/ORBextractor.cc:748-763): sub-image origin / size clipped to the level border
         const int maxBX = g.w - kMinBorder, maxBY = g.h - kMinBorder;
         for (int ci = 0; ci < g.nRows; ++ci)
@@ -338,7 +338,7 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         if (g.candCap >= (1 << kOrderBits)) return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, g.candCap);
     }
     h->pyrBytes = pb + 256; h->candElems = ce; h->bigKeysElems = be;
-    h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScoreRows = sr; h->fastMaskWords = (tp * hc + 31) / 32;
+    h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScoreRows = sr;
     CU_TRY(cudaMalloc(&h->fastCells, sizeof(FastCell) * std::max<size_t>(cells.size(), 1)));
     CU_TRY(cudaMemcpy(h->fastCells, cells.data(), sizeof(FastCell) * cells.size(), cudaMemcpyHostToDevice));
     CU_TRY(cudaDeviceSynchronize());
@@ -854,7 +854,7 @@ int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* 
         const int nb = h->fastTilePitch * h->fastTileRows + h->fastTilePitch * h->fastScoreRows;
         CU_TRY(cudaDeviceSynchronize());
         CU_TRY(cudaMemcpy(out, h->dbgBuf, std::min(nb, cap), cudaMemcpyDeviceToHost));
-        if (dims5) { dims5[0] = h->fastTilePitch; dims5[1] = h->fastTileRows; dims5[2] = h->fastTilePitch; dims5[3] = h->fastScoreRows; dims5[4] = h->fastMaskWords; }
+        if (dims5) { dims5[0] = h->fastTilePitch; dims5[1] = h->fastTileRows; dims5[2] = h->fastTilePitch; dims5[3] = h->fastScoreRows; dims5[4] = 0; }
         return nb;
     }
     return 0;

@@ -5,8 +5,8 @@
 //   * DBoW2 vocabulary tree descent -- TemplatedVocabulary::transform, R/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h
 //     :1218-1258 (per feature) and :1128-1200 (BowVector / FeatureVector assembly = Frame::ComputeBoW),
 //     tree built like loadFromTextFile (:1338-1421), distance = FORB::distance (FORB.cpp:81-101);
-//   * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) -- R/lib_src/ORBmatcher.cc:198-370, the Nleft == -1 branch,
-//     with ComputeThreeMaxima (:1787-1828).
+//   * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) -- R/lib_src/ORBmatcher.cc:198-370, the Nleft == -1 branch, and
+//     SearchByBoW(KeyFrame*, KeyFrame*, ...) -- :682-804, with ComputeThreeMaxima (:1795-1828).
 // Parity: PINNED.  The tree descent and the vector assembly are checked against the UNMODIFIED reference DBoW2
 // compiled over oracle/cvstub (oracle/_ref/librefbow.so, tests/test_bow_oracle.py) and against the frozen vectors
 // tests/golden/bow_kats.npz.  SearchByBoW needs KeyFrame / Frame / MapPoint (not compilable here): restated from the
@@ -210,6 +210,69 @@ int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, cons
         for (int i = 0; i < HISTO_LENGTH; i++) {
             if (i == ind1 || i == ind2 || i == ind3) continue;
             for (size_t j = 0; j < rotHist[i].size(); j++) { match_f[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), R/lib_src/ORBmatcher.cc:682-804 (NLeft == -1 for both).
+// valid1 / valid2: the feature has a map point that is not bad.  match12[i1] = feature of keyframe 2 whose map point the
+// reference stores in vpMatches12[i1], or -1.  Differences to the KeyFrame-Frame overload: strict '<' against TH_LOW
+// (:756), keyframe-2 features need a valid map point (:735-739), and a keyframe-2 feature stays "matched" (:759) even
+// when the rotation histogram later drops the match.
+int bow_oracle_search_by_bow_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                                const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nnodes1,
+                                const uint8_t* desc2, const float* angle2, const uint8_t* valid2, int n2,
+                                const int32_t* nodes2, const int32_t* off2, const int32_t* idx2, int nnodes2,
+                                float nnratio, int check_ori, int th_low, int32_t* match12) {
+    const int HISTO_LENGTH = 30;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    std::vector<char> matched2(n2 > 0 ? n2 : 1, 0);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nnodes1 && b < nnodes2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = off1[a]; i1 < off1[a + 1]; ++i1) {
+                const int id1 = idx1[i1];
+                if (!valid1[id1]) continue;
+                const uint8_t* d1 = desc1 + 32 * (size_t)id1;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = off2[b]; i2 < off2[b + 1]; ++i2) {
+                    const int id2 = idx2[i2];
+                    if (matched2[id2] || !valid2[id2]) continue;
+                    const int dist = forb_distance(d1, desc2 + 32 * (size_t)id2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = id2; }
+                    else if (dist < bestDist2) { bestDist2 = dist; }
+                }
+                if (bestDist1 < th_low) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match12[id1] = bestIdx2;
+                        matched2[bestIdx2] = 1;
+                        if (check_ori) {
+                            float rot = angle1[id1] - angle2[bestIdx2];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)std::round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(id1);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            a = (int)(std::lower_bound(nodes1 + a, nodes1 + nnodes1, nodes2[b]) - nodes1);
+        } else {
+            b = (int)(std::lower_bound(nodes2 + b, nodes2 + nnodes2, nodes1[a]) - nodes2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { match12[rotHist[i][j]] = -1; nmatches--; }
         }
     }
     return nmatches;

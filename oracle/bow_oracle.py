@@ -48,6 +48,9 @@ def lib():
                                          C.POINTER(C.c_int)]
         L.bow_oracle_search_by_bow.argtypes = [_u8p, _f32p, _u8p, _i32p, _i32p, _i32p, C.c_int, _u8p, _f32p, C.c_int,
                                                _i32p, _i32p, _i32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p]
+        L.bow_oracle_search_by_bow_kf.argtypes = [_u8p, _f32p, _u8p, C.c_int, _i32p, _i32p, _i32p, C.c_int, _u8p, _f32p,
+                                                  _u8p, C.c_int, _i32p, _i32p, _i32p, C.c_int, C.c_float, C.c_int,
+                                                  C.c_int, _i32p]
         L.bow_oracle_distinctive.argtypes = [_u8p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -155,3 +158,20 @@ def distinctive(desc, offsets):
         best[p] = L.bow_oracle_distinctive(_p(d, _u8p), len(d), C.byref(m))
         med[p] = m.value
     return best, med
+
+
+def search_by_bow_kf(desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, nnratio=0.8, check_ori=True, th_low=50):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12): (nmatches, match12)."""
+    d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    a1, a2 = np.ascontiguousarray(angle1, np.float32), np.ascontiguousarray(angle2, np.float32)
+    v1, v2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+    n1, o1, i1 = flatten_fv(fv1)
+    n2, o2, i2 = flatten_fv(fv2)
+    i1 = np.ascontiguousarray(np.append(i1, 0), np.int32)
+    i2 = np.ascontiguousarray(np.append(i2, 0), np.int32)
+    match = np.zeros(max(len(d1), 1), np.int32)
+    n = lib().bow_oracle_search_by_bow_kf(_p(d1, _u8p), _p(a1, _f32p), _p(v1, _u8p), len(d1), _p(n1, _i32p), _p(o1, _i32p),
+                                          _p(i1, _i32p), len(n1), _p(d2, _u8p), _p(a2, _f32p), _p(v2, _u8p), len(d2),
+                                          _p(n2, _i32p), _p(o2, _i32p), _p(i2, _i32p), len(n2), nnratio,
+                                          1 if check_ori else 0, th_low, _p(match, _i32p))
+    return n, match[:len(d1)]

@@ -95,20 +95,18 @@ static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, 
     else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
 }
 
-int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>& angleKF,
-                                 const std::vector<uint8_t>& kfValid,
-                                 const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF,
-                                 const cv::Mat& descF, const std::vector<float>& angleF,
-                                 const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF,
-                                 bool checkOrientation, std::vector<int>& matchF) {
-    matchF.assign(descF.rows, -1);
+long long ORBmatcherAccel::NodeBlocks(const cv::Mat& descA,
+                                      const std::vector<std::pair<unsigned, std::vector<unsigned> > >& fvA,
+                                      const cv::Mat& descB,
+                                      const std::vector<std::pair<unsigned, std::vector<unsigned> > >& fvB,
+                                      std::vector<int32_t>& aIdx, std::vector<int32_t>& bIdx, std::vector<int32_t>& segs,
+                                      std::vector<uint16_t>& dist) {
     // common nodes in ascending order == the nodes the reference's lower_bound walk visits (:218-221, :345-353)
-    std::vector<int32_t> aIdx, bIdx, segs;
     long long ndist = 0;
     size_t a = 0, b = 0;
-    while (a < featVecKF.size() && b < featVecF.size()) {
-        if (featVecKF[a].first == featVecF[b].first) {
-            const std::vector<unsigned>&ia = featVecKF[a].second, &ib = featVecF[b].second;
+    while (a < fvA.size() && b < fvB.size()) {
+        if (fvA[a].first == fvB[b].first) {
+            const std::vector<unsigned>&ia = fvA[a].second, &ib = fvB[b].second;
             segs.push_back((int32_t)aIdx.size()); segs.push_back((int32_t)ia.size());
             segs.push_back((int32_t)bIdx.size()); segs.push_back((int32_t)ib.size());
             segs.push_back((int32_t)ndist);
@@ -116,16 +114,86 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
             bIdx.insert(bIdx.end(), ib.begin(), ib.end());
             ndist += (long long)ia.size() * (long long)ib.size();
             ++a; ++b;
-        } else if (featVecKF[a].first < featVecF[b].first) ++a;
+        } else if (fvA[a].first < fvB[b].first) ++a;
         else ++b;
     }
     if (segs.empty() || ndist == 0) return 0;
-    const std::vector<uint8_t> dk = rows32(descKF), df = rows32(descF);
-    std::vector<uint16_t> dist((size_t)ndist);
-    if (rumi_bow_node_distances(ctx, dk.data(), descKF.rows, df.data(), descF.rows, aIdx.data(), (int)aIdx.size(),
+    const std::vector<uint8_t> da = rows32(descA), db = rows32(descB);
+    dist.resize((size_t)ndist);
+    if (rumi_bow_node_distances(ctx, da.data(), descA.rows, db.data(), descB.rows, aIdx.data(), (int)aIdx.size(),
                                 bIdx.data(), (int)bIdx.size(), segs.data(), (int)(segs.size() / 5), dist.data(),
                                 ndist) != RUMI_OK)
         throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    return ndist;
+}
+
+int ORBmatcherAccel::SearchByBoWKF(const cv::Mat& desc1, const std::vector<float>& angle1,
+                                   const std::vector<uint8_t>& valid1,
+                                   const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec1,
+                                   const cv::Mat& desc2, const std::vector<float>& angle2,
+                                   const std::vector<uint8_t>& valid2,
+                                   const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec2,
+                                   bool checkOrientation, std::vector<int>& match12) {
+    match12.assign(desc1.rows, -1);
+    std::vector<bool> vbMatched2(desc2.rows, false);
+    std::vector<int32_t> aIdx, bIdx, segs;
+    std::vector<uint16_t> dist;
+    if (NodeBlocks(desc1, featVec1, desc2, featVec2, aIdx, bIdx, segs, dist) == 0) return 0;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (size_t s = 0; s < segs.size(); s += 5) {
+        const int a0 = segs[s], ac = segs[s + 1], b0 = segs[s + 2], bc = segs[s + 3];
+        const uint16_t* block = dist.data() + segs[s + 4];
+        for (int i1 = 0; i1 < ac; i1++) {
+            const int idx1 = aIdx[a0 + i1];
+            if (!valid1[idx1]) continue;                                          // :713-717
+            int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+            for (int i2 = 0; i2 < bc; i2++) {
+                const int idx2 = bIdx[b0 + i2];
+                if (vbMatched2[idx2] || !valid2[idx2]) continue;                  // :735-739
+                const int d = block[(size_t)i1 * bc + i2];
+                if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = idx2; }
+                else if (d < bestDist2) { bestDist2 = d; }
+            }
+            if (bestDist1 < TH_LOW) {                                             // strict '<' in this overload (:756)
+                if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+                    match12[idx1] = bestIdx2;
+                    vbMatched2[bestIdx2] = true;
+                    if (checkOrientation) {
+                        float rot = angle1[idx1] - angle2[bestIdx2];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                    nmatches++;
+                }
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { match12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>& angleKF,
+                                 const std::vector<uint8_t>& kfValid,
+                                 const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF,
+                                 const cv::Mat& descF, const std::vector<float>& angleF,
+                                 const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF,
+                                 bool checkOrientation, std::vector<int>& matchF) {
+    matchF.assign(descF.rows, -1);
+    std::vector<int32_t> aIdx, bIdx, segs;
+    std::vector<uint16_t> dist;
+    if (NodeBlocks(descKF, featVecKF, descF, featVecF, aIdx, bIdx, segs, dist) == 0) return 0;
 
     int nmatches = 0;
     std::vector<int> rotHist[HISTO_LENGTH];

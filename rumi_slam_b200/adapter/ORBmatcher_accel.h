@@ -64,7 +64,21 @@ public:
                     const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF, bool checkOrientation,
                     std::vector<int>& matchF);
 
+    // ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (R/lib_src/ORBmatcher.cc:682-804), NLeft == -1 for both
+    // keyframes.  valid1 / valid2: the feature has a map point that is not bad.  match12[i] = feature of keyframe 2
+    // whose map point the reference stores in vpMatches12[i], or -1.
+    int SearchByBoWKF(const cv::Mat& desc1, const std::vector<float>& angle1, const std::vector<uint8_t>& valid1,
+                      const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec1, const cv::Mat& desc2,
+                      const std::vector<float>& angle2, const std::vector<uint8_t>& valid2,
+                      const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec2, bool checkOrientation,
+                      std::vector<int>& match12);
+
 private:
+    // distance blocks of the vocabulary nodes common to two feature vectors (rumi_bow_node_distances)
+    long long NodeBlocks(const cv::Mat& descA, const std::vector<std::pair<unsigned, std::vector<unsigned> > >& fvA,
+                         const cv::Mat& descB, const std::vector<std::pair<unsigned, std::vector<unsigned> > >& fvB,
+                         std::vector<int32_t>& aIdx, std::vector<int32_t>& bIdx, std::vector<int32_t>& segs,
+                         std::vector<uint16_t>& dist);
     rumi_match* ctx;
     float mfNNratio;
 };

@@ -163,6 +163,35 @@ class ORBmatcher:
             check(self._L.rumi_distinctive_descriptors(self._m, ptr(desc), ptr(offsets), n, ptr(best), ptr(med)))
         return best, med
 
+    # ---- ORBmatcher::SearchByBoW: shared machinery ----
+    def _bow_blocks(self, desc_a, featvec_a, desc_b, featvec_b):
+        """Distance blocks of every vocabulary node common to both feature vectors (ascending node id == the nodes
+        the reference's lower_bound walk visits): [(a_indices, b_indices, dist[len(a), len(b)])]."""
+        da = np.ascontiguousarray(desc_a, np.uint8).reshape(-1, 32)
+        db = np.ascontiguousarray(desc_b, np.uint8).reshape(-1, 32)
+        common = sorted(set(featvec_a) & set(featvec_b))
+        a_idx, b_idx, segs, off = [], [], [], 0
+        for nid in common:
+            ia, ib = featvec_a[nid], featvec_b[nid]
+            segs.append((len(a_idx), len(ia), len(b_idx), len(ib), off))
+            a_idx += list(ia); b_idx += list(ib)
+            off += len(ia) * len(ib)
+        if not segs or off == 0:
+            return []
+        a_idx, b_idx = np.array(a_idx, np.int32), np.array(b_idx, np.int32)
+        segs_a = np.array(segs, np.int32).reshape(-1, 5)
+        dist = np.zeros(off, np.uint16)
+        check(self._L.rumi_bow_node_distances(self._m, ptr(da), len(da), ptr(db), len(db), ptr(a_idx), len(a_idx),
+                                              ptr(b_idx), len(b_idx), ptr(segs_a), len(segs_a), ptr(dist), off))
+        return [(a_idx[a0:a0 + ac], b_idx[b0:b0 + bc], dist[o:o + ac * bc].reshape(ac, bc)) for (a0, ac, b0, bc, o) in segs]
+
+    def _rot_bin(self, angle_a, angle_b):
+        rot = np.float32(angle_a) - np.float32(angle_b)
+        if rot < 0.0:
+            rot = np.float32(rot + np.float32(360.0))
+        b = _c_round(float(np.float32(rot * (np.float32(1.0) / np.float32(self.HISTO_LENGTH)))))
+        return 0 if b == self.HISTO_LENGTH else b
+
     # ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:198-370, F.Nleft == -1) ----
     def SearchByBoW(self, desc_kf, angle_kf, kf_valid, featvec_kf, desc_f, angle_f, featvec_f):
         """desc_*: [n,32] descriptors; angle_*: keypoint angles (mvKeysUn[i].angle / mvKeys[i].angle); kf_valid[i]:
@@ -170,37 +199,19 @@ class ORBmatcher:
         Returns (nmatches, match_f) with match_f[j] = keyframe feature whose map point was assigned to frame feature
         j, or -1.  The GPU computes every distance of every common vocabulary node; the acceptance (TH_LOW, ratio,
         the "already matched" skip :249 and the rotation histogram) is replayed here in the reference's order."""
-        dk = np.ascontiguousarray(desc_kf, np.uint8).reshape(-1, 32)
-        df = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
-        nodes_kf, nodes_f = sorted(featvec_kf), sorted(featvec_f)
-        common = sorted(set(nodes_kf) & set(nodes_f))             # the lower_bound walk visits exactly these, ascending
-        a_idx, b_idx, segs, off = [], [], [], 0
-        for nid in common:
-            ia, ib = featvec_kf[nid], featvec_f[nid]
-            segs.append((len(a_idx), len(ia), len(b_idx), len(ib), off))
-            a_idx += list(ia); b_idx += list(ib)
-            off += len(ia) * len(ib)
-        match_f = np.full(len(df), -1, np.int32)
-        if not segs or off == 0:
-            return 0, match_f
-        a_idx, b_idx = np.array(a_idx, np.int32), np.array(b_idx, np.int32)
-        segs_a = np.array(segs, np.int32).reshape(-1, 5)
-        dist = np.zeros(off, np.uint16)
-        check(self._L.rumi_bow_node_distances(self._m, ptr(dk), len(dk), ptr(df), len(df), ptr(a_idx), len(a_idx),
-                                              ptr(b_idx), len(b_idx), ptr(segs_a), len(segs_a), ptr(dist), off))
+        nf = len(np.asarray(desc_f).reshape(-1, 32))
+        match_f = np.full(nf, -1, np.int32)
         nmatches = 0
         rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
-        factor = np.float32(1.0) / np.float32(self.HISTO_LENGTH)
         ratio = np.float32(self.mfNNratio)
-        for (a0, ac, b0, bc, o) in segs:
-            block = dist[o:o + ac * bc].reshape(ac, bc)
-            for i in range(ac):
-                real_kf = int(a_idx[a0 + i])
+        for a_idx, b_idx, block in self._bow_blocks(desc_kf, featvec_kf, desc_f, featvec_f):
+            for i in range(len(a_idx)):
+                real_kf = int(a_idx[i])
                 if not kf_valid[real_kf]:
                     continue
                 best1, best_f, best2 = 256, -1, 256
-                for j in range(bc):
-                    real_f = int(b_idx[b0 + j])
+                for j in range(len(b_idx)):
+                    real_f = int(b_idx[j])
                     if match_f[real_f] >= 0:
                         continue
                     d = int(block[i, j])
@@ -211,13 +222,7 @@ class ORBmatcher:
                 if best1 <= self.TH_LOW and np.float32(best1) < ratio * np.float32(best2):
                     match_f[best_f] = real_kf
                     if self.mbCheckOrientation:
-                        rot = np.float32(angle_kf[real_kf]) - np.float32(angle_f[best_f])
-                        if rot < 0.0:
-                            rot = np.float32(rot + np.float32(360.0))
-                        b = _c_round(float(np.float32(rot * factor)))
-                        if b == self.HISTO_LENGTH:
-                            b = 0
-                        rot_hist[b].append(best_f)
+                        rot_hist[self._rot_bin(angle_kf[real_kf], angle_f[best_f])].append(best_f)
                     nmatches += 1
         if self.mbCheckOrientation:
             keep = _three_maxima(rot_hist)
@@ -228,6 +233,48 @@ class ORBmatcher:
                     match_f[j] = -1
                     nmatches -= 1
         return nmatches, match_f
+
+    # ---- ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (ORBmatcher.cc:682-804, NLeft == -1) ----
+    def SearchByBoW_KF(self, desc1, angle1, valid1, featvec1, desc2, angle2, valid2, featvec2):
+        """Returns (nmatches, match12): match12[i] = feature of keyframe 2 whose map point is stored in vpMatches12[i],
+        or -1.  valid1 / valid2: the feature has a map point that is not bad."""
+        n1 = len(np.asarray(desc1).reshape(-1, 32))
+        n2 = len(np.asarray(desc2).reshape(-1, 32))
+        match12 = np.full(n1, -1, np.int32)
+        matched2 = np.zeros(max(n2, 1), bool)
+        nmatches = 0
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        ratio = np.float32(self.mfNNratio)
+        for a_idx, b_idx, block in self._bow_blocks(desc1, featvec1, desc2, featvec2):
+            for i in range(len(a_idx)):
+                id1 = int(a_idx[i])
+                if not valid1[id1]:
+                    continue
+                best1, best_2, best2 = 256, -1, 256
+                for j in range(len(b_idx)):
+                    id2 = int(b_idx[j])
+                    if matched2[id2] or not valid2[id2]:
+                        continue
+                    d = int(block[i, j])
+                    if d < best1:
+                        best2, best1, best_2 = best1, d, id2
+                    elif d < best2:
+                        best2 = d
+                if best1 < self.TH_LOW and np.float32(best1) < ratio * np.float32(best2):      # strict '<' here (:756)
+                    match12[id1] = best_2
+                    matched2[best_2] = True
+                    if self.mbCheckOrientation:
+                        rot_hist[self._rot_bin(angle1[id1], angle2[best_2])].append(id1)
+                    nmatches += 1
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for i in range(self.HISTO_LENGTH):
+                if i in keep:
+                    continue
+                for j in rot_hist[i]:
+                    match12[j] = -1
+                    nmatches -= 1
+        return nmatches, match12
 
 
 def _c_round(x):

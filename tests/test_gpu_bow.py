@@ -129,3 +129,31 @@ def test_distinctive_descriptors_match_oracle(bow_oracle):
     rb, rm = bow_oracle.distinctive(desc, off)
     assert np.array_equal(best, rb) and np.array_equal(med, rm)
     assert m.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.array([0], np.int32))[0].shape == (0,)
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+def test_search_by_bow_keyframe_keyframe_matches_oracle(bow_oracle, check_ori):
+    from rumi_slam_b200 import ORBVocabulary, ORBmatcher
+    k, L = 10, 4
+    par, leaf, desc, w = synthetic_vocabulary(k, L, seed=12)
+    V = ORBVocabulary(k, L, par, leaf, desc, w)
+    rng = np.random.default_rng(4)
+    n1, n2 = 900, 1000
+    d1 = descriptors_near_vocabulary(desc, leaf, n1, 40, flip=0.04)
+    src = rng.integers(0, n1, 800)
+    d2 = np.concatenate([d1[src] ^ np.packbits(rng.random((800, 256)) < 0.03, axis=1),
+                         descriptors_near_vocabulary(desc, leaf, n2 - 800, 41)])
+    perm = rng.permutation(n2)
+    d2 = d2[perm]
+    a1 = rng.random(n1).astype(np.float32) * 360
+    a2 = rng.random(n2).astype(np.float32) * 360
+    a2[np.argsort(perm)[:800]] = (a1[src] + 20 + rng.normal(0, 2, 800)).astype(np.float32) % 360
+    v1 = (rng.random(n1) < 0.85).astype(np.uint8)
+    v2 = (rng.random(n2) < 0.85).astype(np.uint8)
+    _, fv1 = V.transform(d1, 2)
+    _, fv2 = V.transform(d2, 2)
+    m = ORBmatcher(0.8, check_ori)
+    n_gpu, match_gpu = m.SearchByBoW_KF(d1, a1, v1, fv1, d2, a2, v2, fv2)
+    n_ref, match_ref = bow_oracle.search_by_bow_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, nnratio=0.8, check_ori=check_ori)
+    assert n_gpu == n_ref and n_ref > 100 and np.array_equal(match_gpu, match_ref)
+    assert all(v2[j] for j in match_gpu if j >= 0)

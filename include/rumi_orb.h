@@ -92,6 +92,9 @@ int rumi_orb_debug_fast_tile(rumi_orb* h, int cell, uint8_t* out, int cap, int* 
 /* profiling hook: first call arms per-phase cycle counters of the quad-tree kernel (frame 0 of every chunk), later
    calls copy out[level*16 + phase] and reset them; returns the number of counters */
 int rumi_orb_debug_octree_clocks(rumi_orb* h, long long* out, int cap);
+/* timing experiments only (results become stale / wrong): bit s of mask = do not launch stage s (0 pyramid, 1 FAST,
+   2 quad-tree, 4 blur, 5 describe) in later calls, to measure a stage's marginal cost inside the pipelined batch */
+int rumi_orb_debug_skip_stages(rumi_orb* h, int mask);
 
 /* ---- measurement (bench.py) ----
  * Device-side timing on the streams the kernels are launched on: start records an event on the handle's first

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rumi_orb_debug_fast_tile": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "rumi_orb_debug_octree_clocks": (C.c_int, [_vp, _vp, C.c_int]),
     "rumi_orb_set_streams": (C.c_int, [_vp, C.c_int]),
+    "rumi_orb_debug_skip_stages": (C.c_int, [_vp, C.c_int]),
     "rumi_orb_timer_start": (C.c_int, [_vp]),
     "rumi_orb_timer_stop": (C.c_int, [_vp, _f32p]),
     "rumi_orb_profile": (C.c_int, [_vp, C.c_int]),

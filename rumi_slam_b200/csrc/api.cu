@@ -122,6 +122,7 @@ struct rumi_orb {
     int smemKeys = 4096, maxNodeCap = 0;
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
+    int skipMask = 0;              // RUMI_SKIP_STAGES (timing experiments only: results are wrong) bit s = skip stage s
     bool hiPrio = false;           // pyramid / quad-tree on a high-priority side stream (RUMI_HIPRIO=1; measured: 1 stream
                                    // 103 -> 107 k frames/s, but 2 streams 123 -> 110 k, so off by default)
     bool nwsSet = false;           // RUMI_STREAMS given: use it for every path
@@ -403,7 +404,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         cv.src[l] = l == 0 ? l0 : internal_view(h, w.pyr, l);
         cv.blur[l] = internal_view(h, w.blur, l);
     }
-    CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
+    if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
     if (h->profile) prof_event(h, s);
     if (fork) { CU_TRY(cudaEventRecord(w.ev[0], s)); CU_TRY(cudaStreamWaitEvent(sh, w.ev[0], 0)); }
     // K1': all levels in one launch when every source can be read as aligned 32-bit words (always true for the
@@ -415,7 +416,9 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         march = ((((uintptr_t)l0.ptr | (uintptr_t)l0.pitch | (uintptr_t)l0.stride) & 3) == 0) &&
                 l0.stride >= 4 * (h->marchLv[1].srcLastWord + 1);
     int pyrLaunches = oc.nlevels - 1;
-    if (march) {
+    const int skip = h->skipMask;
+    if (skip & 1) {
+    } else if (march) {
         PyrMarchArgs ma;
         ma.cv = cv;
         for (int l = 0; l < kMaxLevels; ++l) ma.lv[l] = h->marchLv[l];
@@ -464,10 +467,10 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         oa.bigKeysLevelOff[l] = h->bigKeysLevelOff[l];
         oa.bigKeysCap[l] = h->bigKeysCap[l];
     }
-    launch_fast(fa, oc, s);
+    if (!(skip & 2)) launch_fast(fa, oc, s);
     prof_mark(h, s, ST_FAST, 1);
     if (fork) { CU_TRY(cudaEventRecord(w.ev[2], s)); CU_TRY(cudaStreamWaitEvent(sh, w.ev[2], 0)); }
-    launch_octree(oa, oc, sh);
+    if (!(skip & 4)) launch_octree(oa, oc, sh);
     prof_mark(h, s, ST_OCTREE, 1);
     DescribeArgs da;
     da.cv = cv; da.sel = w.sel; da.selCount = w.selCount; da.lap0 = lap0; da.lap1 = lap1; da.slot = w.slot;
@@ -475,10 +478,10 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     launch_assign_slots(da, oc, sh);
     prof_mark(h, s, ST_SLOTS, 1);
     if (fork) CU_TRY(cudaEventRecord(w.ev[3], sh));
-    launch_blur(cv, oc, s);                                  // needs only the pyramid: beside the quad-tree when forked
+    if (!(skip & 16)) launch_blur(cv, oc, s);                // needs only the pyramid: beside the quad-tree when forked
     prof_mark(h, s, ST_BLUR, 1);
     if (fork) CU_TRY(cudaStreamWaitEvent(s, w.ev[3], 0));
-    launch_describe(da, oc, s);
+    if (!(skip & 32)) launch_describe(da, oc, s);
     prof_mark(h, s, ST_DESCRIBE, 1);
     CU_TRY(cudaGetLastError());
     w.lastFrames = n;
@@ -535,6 +538,8 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     h->marchForced = pm && pm[0] == 'm';                         // RUMI_PYRAMID=march: also for small calls (tests)
     const char* ps = getenv("RUMI_PYRAMID_SPLIT");
     if (ps && ps[0] >= '1' && ps[0] <= '9') h->marchSplit = ps[0] - '0';
+    const char* sk = getenv("RUMI_SKIP_STAGES");
+    if (sk) h->skipMask = atoi(sk);
     const char* hp = getenv("RUMI_HIPRIO");
     if (hp && hp[0] == '1') h->hiPrio = true;
     const char* ns = getenv("RUMI_STREAMS");
@@ -797,6 +802,12 @@ int rumi_orb_timer_stop(rumi_orb* h, float* ms) {
     CU_TRY(cudaEventRecord(h->evStop, h->ws[0].stream));
     CU_TRY(cudaEventSynchronize(h->evStop));
     CU_TRY(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+    return RUMI_OK;
+}
+
+int rumi_orb_debug_skip_stages(rumi_orb* h, int mask) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    h->skipMask = mask;
     return RUMI_OK;
 }
 

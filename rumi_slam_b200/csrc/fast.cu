@@ -340,17 +340,48 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
         }
         return;
     }
-    for (int i = lane; i < nMin; i += 32) {
-        const int o = (int)clist[i];
-        const int sc = s0[o];
-        if (sc < thEmit) continue;                       // survivors below iniThFAST when the cell has stronger ones
-        int rank = 0;
-        for (int j = 0; j < nMin; ++j) {
-            const int oj = (int)clist[j];
-            rank += (oj < o) && (s0[oj] >= thEmit);
+    // keep only the survivors that are emitted (score >= iniThFAST when the cell has such corners): second in-place
+    // compaction, keys = offset << 8 | score
+    int nEmit = 0;
+    for (int b = 0; b < nMin; b += 32) {
+        bool k = false;
+        int o = 0, sc = 0;
+        if (b + lane < nMin) {
+            o = (int)clist[b + lane];
+            sc = s0[o];
+            k = sc >= thEmit;
         }
+        __syncwarp();
+        const unsigned mk = __ballot_sync(kFull, k);
+        if (k) clist[nEmit + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)o;
+        nEmit += __popc(mk);
+    }
+    __syncwarp();
+    auto emit = [&](int o, int sc, int rank) {
         const int y = TP == 64 ? (o >> 6) : (int)div_magic((uint32_t)o, magicT), x = o - y * tp;
         out[rank] = pack_cand(relX + x, relY + y, sc);
+    };
+    if (nEmit <= 32) {
+        // one key per lane, bitonic sort across the warp (15 shuffle stages): lane i ends up with the i-th offset
+        uint32_t key = 0xFFFFFFFFu;
+        if (lane < nEmit) { const int o = (int)clist[lane]; key = ((uint32_t)o << 8) | (uint32_t)s0[o]; }
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const uint32_t other = __shfl_xor_sync(kFull, key, j);
+                const bool keepMin = ((lane & j) == 0) == ((lane & k) == 0);
+                key = keepMin ? min(key, other) : max(key, other);
+            }
+        }
+        if (lane < nEmit) emit((int)(key >> 8), (int)(key & 0xFFu), lane);
+        return;
+    }
+    for (int i = lane; i < nEmit; i += 32) {             // many weak survivors: all-pairs rank
+        const int o = (int)clist[i];
+        int rank = 0;
+        for (int j = 0; j < nEmit; ++j) rank += (int)clist[j] < o;
+        emit(o, s0[o], rank);
     }
 }
 

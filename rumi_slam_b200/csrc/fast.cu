@@ -1,22 +1,23 @@
 // K2: grid FAST-9/16 with cell-local non-maximum suppression and the ini/min threshold fallback
 // (ORBextractor::ComputeKeyPointsOctTree, R/lib_src/ORBextractor.cc:726-808; cv::FAST).
 //
-// One WARP per 35-px grid cell, all levels of all frames in one launch.  The reference runs cv::FAST twice per
-// cell (threshold 20, then 7 if nothing survived NMS); because the corner score is threshold independent and a
-// pixel whose score is below the threshold can never beat a corner, ONE score tile per cell at the low threshold
-// plus a per-cell vote reproduces both runs exactly.  Phases (all warp-synchronous, no block barrier):
-//   0. the cell's sub-image (detection area + 3-px ring halo) is staged in shared memory with 16-byte vector
+// One WARP per 35-px grid cell, all levels of all frames in one launch.  The reference runs cv::FAST twice per cell
+// (threshold iniThFAST, then minThFAST if nothing survived NMS).  So does the warp: pass 0 at iniThFAST, and only a cell
+// that ends up without a keypoint repeats the scan at minThFAST (a few per cent of the cells).  Working at the high
+// threshold first matters: its pretest rejects ~3x more pixels, and corners weaker than iniThFAST never have to be
+// scored -- they cannot suppress a stronger neighbour (strict '>') and are not emitted when the cell has a strong one.
+// Phases of a pass (all warp-synchronous, no block barrier):
+//   0. (once) the cell's sub-image (detection area + 3-px ring halo) is staged in shared memory with 16-byte vector
 //      loads of the aligned superset of every row (coalesced uint4; byte loads only for unaligned caller memory);
-//   A. lanes scan the detection area; a pretest on the 8 even ring pixels (a 9-arc always covers 4 consecutive of
-//      them) rejects ~80 % of the pixels; survivors are compacted with __ballot_sync into a small warp queue;
-//   B. the queue is drained 32 at a time so the exact 16-pixel arc test and the exact score always run with full
-//      lanes; corners write their score into a zero-framed score tile and append themselves to a corner list;
+//   A. lanes scan the detection area 4 pixels at a time; a SWAR pretest on the 8 even ring pixels (a 9-arc always
+//      covers 4 consecutive of them) rejects most pixels; survivors are compacted into a small warp queue;
+//   B. the queue is drained 32 at a time so the exact score always runs with full lanes; corners (score >= threshold)
+//      write their score into a zero-framed score tile and append themselves to a corner list;
 //   C. NMS runs over the corner list only: strict '>' against the 8 neighbours INSIDE the cell's detection area
-//      (outside = 0, exactly like cv::FAST on the sub-image); survivors set a bit in a per-pixel bitmap and the
-//      warp votes "any survivor with score >= iniThFAST" (fallback rule, :783);
-//   D. survivors are emitted in raster order from the bitmap (popc prefix over bitmap words) into a block reserved
-//      with one atomicAdd per cell.  The octree kernel later walks the cells in the reference's row-major order, so
-//      the result does not depend on the order of those reservations.
+//      (outside = 0, exactly like cv::FAST on the sub-image); survivors are compacted in place;
+//   D. survivors are sorted by raster offset (warp bitonic sort) and written into a block reserved with one atomicAdd
+//      per cell.  The octree kernel later walks the cells in the reference's row-major order, so the result does not
+//      depend on the order of those reservations.
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -159,11 +160,19 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     }
     __syncwarp();
 
-    const int th = oc.minTh;
+    // The reference runs cv::FAST at iniThFAST and, only if the cell yields NO keypoint, again at minThFAST (:771-783).
+    // Same here: pass 0 at iniThFAST -- its pretest rejects far more pixels and only corners with score >= iniThFAST
+    // are scored and suppressed (weaker neighbours can never block them: strict '>' against a smaller score) -- and the
+    // few low-texture cells that end up empty repeat the scan at minThFAST.  Scores written by pass 0 are the same
+    // values pass 1 would write, so the score tile is not cleared in between.
+    int th = oc.iniTh;
     const uint8_t* t0 = tile + 3 * tp + 3 + ox;         // detection-area origin inside the image tile
     uint8_t* s0 = score + tp + 16;                      // same origin inside the score tile
     int qn = 0, ncorner = 0;                            // queue fill, corner-list fill (warp uniform)
     bool overflow = false;
+    int nMin = 0;                                       // NMS survivors of the last pass
+    const int npx = dw * dh;
+    const uint32_t magicW = magic_of((uint32_t)dw);
 
     auto drain = [&](int o, bool valid) {
         int sc = 0;
@@ -187,7 +196,8 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
     // with funnel shifts, |centre - ring| comes from one VABSDIFF4 per position, "> th" sets bit 7 of each byte,
     // and 16 ANDs + 4 ORs give "4 consecutive positions" for the 4 pixels at once.  (Sign-agnostic, so slightly
     // weaker than the exact test: survivors go to phase B, which is exact.)
-    {
+    for (int pass = 0; pass < 2; ++pass) {
+        qn = 0; ncorner = 0; overflow = false; nMin = 0;
         const uint32_t magicG = magic_of((uint32_t)ng);
         const uint32_t K = (uint32_t)(th <= 126 ? 127 - th : 0) * 0x01010101u;
         const uint32_t forceAll = th <= 126 ? 0u : 0x80808080u;
@@ -260,48 +270,45 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                 __syncwarp();
             }
         }
+        if (qn > 0) drain(lane < qn ? queue[lane] : 0, lane < qn);
+        __syncwarp();
+
+        // ---- C. NMS over the corner list: strict '>' against the 8 neighbours, branch-free.  Survivors are compacted
+        //         IN PLACE into the front of the list (entry i of iteration b is read before anything is written, and
+        //         at most b entries precede it) ----
+        const int nmsCount = overflow ? npx : ncorner;
+        for (int b = 0; b < nmsCount; b += 32) {
+            bool k = false;
+            int s = 0, o = 0;
+            if (b + lane < nmsCount) {
+                if (overflow) {
+                    const int idq = b + lane, y = (int)div_magic((uint32_t)idq, magicW);
+                    o = y * tp + (idq - y * dw);
+                } else {
+                    o = (int)clist[b + lane];
+                }
+                const uint8_t* q = s0 + o;
+                s = q[0];
+                const int m0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
+                const int m1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
+                const int m2 = max(max((int)q[tp], (int)q[tp + 1]), m0);
+                k = s > max(m1, m2);                     // s == 0 (overflow scan of a non-corner) can never pass
+            }
+            __syncwarp();
+            const unsigned mk = __ballot_sync(kFull, k);
+            if (k && !overflow) clist[nMin + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)o;
+            nMin += __popc(mk);
+        }
+        __syncwarp();
+        if (nMin > 0 || oc.minTh >= oc.iniTh) break;      // :783: the low threshold only for a cell without keypoints
+        th = oc.minTh;
     }
-    if (qn > 0) drain(lane < qn ? queue[lane] : 0, lane < qn);
-    __syncwarp();
 
     if (a.dbg && f == 0 && cellId == a.dbgCell) {
         const int nb = tp * a.tileRows + tp * a.scoreRows;
         for (int i = lane; i < nb; i += 32) a.dbg[i] = tile[i];
     }
-
-    // ---- C. NMS over the corner list: strict '>' against the 8 neighbours, branch-free.  Survivors are compacted IN
-    //         PLACE into the front of the list (entry i of iteration b is read before anything is written, and at most
-    //         b entries precede it) ----
-    int nIni = 0, nMin = 0;
-    const int npx = dw * dh;
-    const uint32_t magicW = magic_of((uint32_t)dw);
-    const int nmsCount = overflow ? npx : ncorner;
-    for (int b = 0; b < nmsCount; b += 32) {
-        bool k = false;
-        int s = 0, o = 0;
-        if (b + lane < nmsCount) {
-            if (overflow) {
-                const int idq = b + lane, y = (int)div_magic((uint32_t)idq, magicW);
-                o = y * tp + (idq - y * dw);
-            } else {
-                o = (int)clist[b + lane];
-            }
-            const uint8_t* q = s0 + o;
-            s = q[0];
-            const int m0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
-            const int m1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
-            const int m2 = max(max((int)q[tp], (int)q[tp + 1]), m0);
-            k = s > max(m1, m2);                         // s == 0 (overflow scan of a non-corner) can never pass
-        }
-        __syncwarp();
-        const unsigned mk = __ballot_sync(kFull, k);
-        if (k && !overflow) clist[nMin + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)o;
-        nMin += __popc(mk);
-        nIni += __popc(__ballot_sync(kFull, k && s >= oc.iniTh));
-    }
-    __syncwarp();
-    const int thEmit = nIni > 0 ? oc.iniTh : oc.minTh;         // :783 fallback on an empty cell
-    const int total = nIni > 0 ? nIni : nMin;
+    const int total = nMin;
     int off = 0;
     if (lane == 0) {
         off = total ? atomicAdd(a.levelCount + (long long)f * oc.nlevels + l, total) : 0;
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                 const int m0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
                 const int m1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
                 const int m2 = max(max((int)q[tp], (int)q[tp + 1]), m0);
-                k = s > max(m1, m2) && s >= thEmit;
+                k = s > max(m1, m2);
             }
             const unsigned mk = __ballot_sync(kFull, k);
             if (k) out[w + __popc(mk & ((1u << lane) - 1u))] = pack_cand(relX + x, relY + y, s);
@@ -340,23 +347,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
         }
         return;
     }
-    // keep only the survivors that are emitted (score >= iniThFAST when the cell has such corners): second in-place
-    // compaction, keys = offset << 8 | score
-    int nEmit = 0;
-    for (int b = 0; b < nMin; b += 32) {
-        bool k = false;
-        int o = 0, sc = 0;
-        if (b + lane < nMin) {
-            o = (int)clist[b + lane];
-            sc = s0[o];
-            k = sc >= thEmit;
-        }
-        __syncwarp();
-        const unsigned mk = __ballot_sync(kFull, k);
-        if (k) clist[nEmit + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)o;
-        nEmit += __popc(mk);
-    }
-    __syncwarp();
+    const int nEmit = nMin;                              // every survivor of the last pass is a keypoint candidate
     auto emit = [&](int o, int sc, int rank) {
         const int y = TP == 64 ? (o >> 6) : (int)div_magic((uint32_t)o, magicT), x = o - y * tp;
         out[rank] = pack_cand(relX + x, relY + y, sc);

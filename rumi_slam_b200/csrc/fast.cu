@@ -247,20 +247,15 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                 pass4 = any & validTab[gl];                                      // bytes inside the detection area
             }
             const int o0 = y * tp + 4 * g - c0;                                  // offset of byte 0 of the group
-            {   // append the (up to 4) surviving pixels of every lane: popc + shuffle prefix, predicated stores
-                const int c = __popc(pass4);
-                int incl = c;
+            {   // append the surviving pixels: one ballot per byte plane (the order inside the queue is irrelevant)
+                const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int n = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += n;
+                for (int j = 0; j < 4; ++j) {
+                    const bool hit = (pass4 >> (8 * j + 7)) & 1u;
+                    const unsigned m = __ballot_sync(kFull, hit);
+                    if (hit) queue[qn + __popc(m & lt)] = (uint16_t)(o0 + j);
+                    qn += __popc(m);
                 }
-                int pos = qn + incl - c;
-                if (pass4 & 0x00000080u) queue[pos++] = (uint16_t)o0;
-                if (pass4 & 0x00008000u) queue[pos++] = (uint16_t)(o0 + 1);
-                if (pass4 & 0x00800000u) queue[pos++] = (uint16_t)(o0 + 2);
-                if (pass4 & 0x80000000u) queue[pos] = (uint16_t)(o0 + 3);
-                qn += __shfl_sync(kFull, incl, 31);
             }
             __syncwarp();
             // ---- B. exact score on the compacted survivors, 32 at a time ----

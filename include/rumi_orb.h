@@ -188,6 +188,34 @@ int rumi_bow_node_distances(rumi_match* m, const uint8_t* descA, int nA, const u
 int rumi_distinctive_descriptors(rumi_match* m, const uint8_t* desc, const int32_t* offsets, int npoints,
                                  int32_t* best_idx, int32_t* best_median);
 
+/* ---- sparse pyramidal Lucas-Kanade flow ----
+ * Replaces cv::calcOpticalFlowPyrLK as KFDSample::Step calls it on every untracked frame
+ * (R/lib_src/KFDSample.cc:131-132: winSize 31x31, maxLevel 2, TermCriteria(COUNT+EPS, 20, 0.03),
+ * R/include/cloud_edge_slam_lib/KFDSample.h:47; flags 0, minEigThreshold 1e-4 = OpenCV defaults).
+ * Points are (x, y) float pairs = cv::Point2f.  status[i] = 1 when the flow of point i was found; err[i] = mean
+ * absolute patch difference / 32 (OpenCV's default error measure), 0 when status[i] = 0.  The pyramid stops at the
+ * last level whose next size would not exceed the window, like cv::buildOpticalFlowPyramid.
+ * The handle keeps the previous frame's pyramid and Scharr derivatives on the device: `advance` = 1 makes the frame
+ * just tracked the new previous frame (imprvs = imnext.clone(), KFDSample.cc:169), so the steady state uploads one
+ * image per call.  One handle is single-threaded like the reference's KFDSample. */
+typedef struct rumi_flow rumi_flow;
+int rumi_flow_create(rumi_flow** out, int device, int win, int max_level, int max_count, double epsilon,
+                     float min_eig_threshold);
+void rumi_flow_destroy(rumi_flow* f);
+int rumi_flow_set_prev(rumi_flow* f, const uint8_t* img, int w, int h_px, size_t stride);
+int rumi_flow_track_next(rumi_flow* f, const uint8_t* img, size_t stride, const float* prev_pts, int n,
+                         float* next_pts, uint8_t* status, float* err /* may be NULL */, int advance);
+/* one-shot form of cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, ...) */
+int rumi_flow_track(rumi_flow* f, const uint8_t* prev, const uint8_t* next, int w, int h_px, size_t stride,
+                    const float* prev_pts, int n, float* next_pts, uint8_t* status, float* err);
+int rumi_flow_levels(const rumi_flow* f);            /* pyramid levels in use for the frames held */
+long long rumi_flow_launches(const rumi_flow* f);    /* kernels launched so far (bench.py) */
+/* parity hooks (tests): pyramid level of the previous (which = 0) / last tracked (1) frame, Scharr (dx, dy) pairs */
+int rumi_flow_debug_level(rumi_flow* f, int which, int level, uint8_t* dst, int* w, int* h_px);
+int rumi_flow_debug_deriv(rumi_flow* f, int level, int16_t* dst);
+int rumi_flow_timer_start(rumi_flow* f);
+int rumi_flow_timer_stop(rumi_flow* f, float* ms);
+
 /* ORBmatcher::DescriptorDistance for one pair (host inline popcount; the API, not a fallback). */
 int rumi_descriptor_distance(const uint8_t* a, const uint8_t* b);
 

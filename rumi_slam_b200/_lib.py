@@ -71,6 +71,17 @@ SIGNATURES = {
     "rumi_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp]),
     "rumi_bow_node_distances": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
                                           _vp, C.c_longlong]),
+    "rumi_flow_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float]),
+    "rumi_flow_destroy": (None, [_vp]),
+    "rumi_flow_set_prev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t]),
+    "rumi_flow_track_next": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "rumi_flow_track": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, C.c_int, _vp, _vp, _vp]),
+    "rumi_flow_levels": (C.c_int, [_vp]),
+    "rumi_flow_launches": (C.c_longlong, [_vp]),
+    "rumi_flow_debug_level": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i32p, _i32p]),
+    "rumi_flow_debug_deriv": (C.c_int, [_vp, C.c_int, _vp]),
+    "rumi_flow_timer_start": (C.c_int, [_vp]),
+    "rumi_flow_timer_stop": (C.c_int, [_vp, _f32p]),
 }
 
 

@@ -1394,3 +1394,231 @@ int rumi_distinctive_descriptors(rumi_match* m, const uint8_t* desc, const int32
 }
 
 }  // extern "C"
+
+// ===================================================================================================================
+// Sparse pyramidal Lucas-Kanade flow (KFDSample::Step, R/lib_src/KFDSample.cc:131-132) -- SURVEY.md 8f rank 4
+// ===================================================================================================================
+struct rumi_flow {
+    int device = 0;
+    int win = 31, maxLevelReq = 2, maxCount = 20;
+    double eps2 = 0.0009;
+    float minEig = 1e-4f;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evDone = nullptr;
+    int w = 0, h = 0, levels = 0;                    // geometry of the frames currently held
+    int lw[kFlowMaxLevels], lh[kFlowMaxLevels], lstride[kFlowMaxLevels];
+    size_t loff[kFlowMaxLevels], doff[kFlowMaxLevels], imgBytes = 0, derivBytes = 0;
+    uint8_t* img[2] = {nullptr, nullptr}; size_t imgCap[2] = {0, 0};    // two pyramids: previous / next, swapped on advance
+    uint8_t* deriv = nullptr; size_t derivCap = 0;   // Scharr (dx, dy) of the previous frame's pyramid
+    uint8_t* pts = nullptr; size_t ptsCap = 0;       // prevPts | nextPts | err | status
+    int prevSlot = 0;
+    bool havePrev = false;
+    long long launches = 0;
+};
+
+namespace {
+
+void flow_geometry(rumi_flow* f, int w, int h) {
+    // buildOpticalFlowPyramid: stop at the last level whose NEXT size would not exceed the window.
+    f->w = w; f->h = h;
+    int sw = w, sh = h, level = 0;
+    size_t off = 0, doff = 0;
+    for (;; ++level) {
+        f->lw[level] = sw; f->lh[level] = sh; f->lstride[level] = (sw + 15) & ~15;
+        f->loff[level] = off; f->doff[level] = doff;
+        off += ((size_t)f->lstride[level] * sh + 255) & ~(size_t)255;
+        doff += ((size_t)sw * sh * 4 + 255) & ~(size_t)255;
+        sw = (sw + 1) / 2; sh = (sh + 1) / 2;
+        if (level == f->maxLevelReq || sw <= f->win || sh <= f->win) break;
+    }
+    f->levels = level + 1;
+    f->imgBytes = off; f->derivBytes = doff;
+}
+
+FlowPyramidView flow_view(const rumi_flow* f, int slot) {
+    FlowPyramidView v{};
+    for (int l = 0; l < f->levels; ++l) {
+        v.ptr[l] = f->img[slot] + f->loff[l];
+        v.w[l] = f->lw[l]; v.h[l] = f->lh[l]; v.stride[l] = f->lstride[l];
+    }
+    return v;
+}
+
+FlowDerivView flow_deriv_view(const rumi_flow* f) {
+    FlowDerivView v{};
+    for (int l = 0; l < f->levels; ++l) v.ptr[l] = reinterpret_cast<short2*>(f->deriv + f->doff[l]);
+    return v;
+}
+
+int flow_upload(rumi_flow* f, int slot, const uint8_t* img, size_t stride) {
+    int rc = grow((void**)&f->img[slot], &f->imgCap[slot], f->imgBytes);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy2DAsync(f->img[slot], f->lstride[0], img, stride, f->w, f->h, cudaMemcpyDefault, f->stream));
+    for (int l = 1; l < f->levels; ++l) {
+        launch_flow_pyrdown(f->img[slot] + f->loff[l - 1], f->lw[l - 1], f->lh[l - 1], f->lstride[l - 1],
+                            f->img[slot] + f->loff[l], f->lstride[l], f->stream);
+        f->launches += 1;
+    }
+    CU_TRY(cudaGetLastError());
+    return RUMI_OK;
+}
+
+int flow_derivatives(rumi_flow* f, int slot) {
+    int rc = grow((void**)&f->deriv, &f->derivCap, f->derivBytes);
+    if (rc) return rc;
+    launch_flow_scharr(flow_view(f, slot), flow_deriv_view(f), f->levels, f->stream);
+    f->launches += 1;
+    CU_TRY(cudaGetLastError());
+    return RUMI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rumi_flow_create(rumi_flow** out, int device, int win, int max_level, int max_count, double epsilon,
+                     float min_eig_threshold) {
+    if (!out) return fail(RUMI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RUMI_ERR_CUDA, "no CUDA device: librumi_orb has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RUMI_ERR_ARG, "device %d out of range", device);
+    if (win != 31 && win != 21 && win != 15)
+        return fail(RUMI_ERR_ARG, "window %d not built (KFDSample uses 31; 21 and 15 are also instantiated)", win);
+    if (max_level < 0 || max_level >= kFlowMaxLevels) return fail(RUMI_ERR_ARG, "maxLevel must be in [0, %d]", kFlowMaxLevels - 1);
+    CU_TRY(cudaSetDevice(device));
+    rumi_flow* f = new rumi_flow();
+    f->device = device;
+    f->win = win;
+    f->maxLevelReq = max_level;
+    f->maxCount = std::min(std::max(max_count, 0), 100);           // calcOpticalFlowPyrLK clamps the criteria
+    const double e = std::min(std::max(epsilon, 0.), 10.);
+    f->eps2 = e * e;
+    f->minEig = min_eig_threshold;
+    CU_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&f->evDone, cudaEventDisableTiming));
+    *out = f;
+    return RUMI_OK;
+}
+
+void rumi_flow_destroy(rumi_flow* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }
+    cudaFree(f->img[0]); cudaFree(f->img[1]); cudaFree(f->deriv); cudaFree(f->pts);
+    if (f->evStart) { cudaEventDestroy(f->evStart); cudaEventDestroy(f->evStop); }
+    if (f->evDone) cudaEventDestroy(f->evDone);
+    delete f;
+}
+
+int rumi_flow_levels(const rumi_flow* f) { return f ? f->levels : 0; }
+long long rumi_flow_launches(const rumi_flow* f) { return f ? f->launches : 0; }
+
+int rumi_flow_set_prev(rumi_flow* f, const uint8_t* img, int w, int h, size_t stride) {
+    if (!f) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (!img || w <= 0 || h <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (stride < (size_t)w) return fail(RUMI_ERR_ARG, "stride smaller than the width");
+    CU_TRY(cudaSetDevice(f->device));
+    flow_geometry(f, w, h);
+    f->havePrev = false;
+    int rc = flow_upload(f, f->prevSlot, img, stride);
+    if (rc) return rc;
+    if ((rc = flow_derivatives(f, f->prevSlot))) return rc;
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    f->havePrev = true;
+    return RUMI_OK;
+}
+
+int rumi_flow_track_next(rumi_flow* f, const uint8_t* img, size_t stride, const float* prev_pts, int n,
+                         float* next_pts, uint8_t* status, float* err, int advance) {
+    if (!f) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (!f->havePrev) return fail(RUMI_ERR_ARG, "no previous frame: call rumi_flow_set_prev first");
+    if (!img) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (stride < (size_t)f->w) return fail(RUMI_ERR_ARG, "stride smaller than the width");
+    if (n < 0) return fail(RUMI_ERR_ARG, "negative point count");
+    if (n > 0 && (!prev_pts || !next_pts || !status)) return fail(RUMI_ERR_ARG, "NULL point buffers");
+    CU_TRY(cudaSetDevice(f->device));
+    const int nextSlot = f->prevSlot ^ 1;
+    int rc = flow_upload(f, nextSlot, img, stride);
+    if (rc) return rc;
+    if (n > 0) {
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t oNext = al(8 * (size_t)n), oErr = oNext + al(8 * (size_t)n), oSt = oErr + al(4 * (size_t)n);
+        if ((rc = grow((void**)&f->pts, &f->ptsCap, oSt + al((size_t)n)))) return rc;
+        CU_TRY(cudaMemcpyAsync(f->pts, prev_pts, 8 * (size_t)n, cudaMemcpyDefault, f->stream));
+        FlowTrackArgs a{};
+        a.I = flow_view(f, f->prevSlot);
+        a.J = flow_view(f, nextSlot);
+        a.D = flow_deriv_view(f);
+        a.maxLevel = f->levels - 1; a.maxCount = f->maxCount; a.eps2 = f->eps2; a.minEig = f->minEig;
+        a.prevPts = reinterpret_cast<const float2*>(f->pts);
+        a.nextPts = reinterpret_cast<float2*>(f->pts + oNext);
+        a.err = reinterpret_cast<float*>(f->pts + oErr);
+        a.status = f->pts + oSt;
+        a.n = n;
+        if (!launch_flow_track(a, f->win, f->stream)) return fail(RUMI_ERR_ARG, "window %d not built", f->win);
+        f->launches += 1;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(next_pts, f->pts + oNext, 8 * (size_t)n, cudaMemcpyDefault, f->stream));
+        CU_TRY(cudaMemcpyAsync(status, f->pts + oSt, (size_t)n, cudaMemcpyDefault, f->stream));
+        if (err) CU_TRY(cudaMemcpyAsync(err, f->pts + oErr, 4 * (size_t)n, cudaMemcpyDefault, f->stream));
+    }
+    CU_TRY(cudaEventRecord(f->evDone, f->stream));   // the caller's results are complete here
+    if (advance) {                                   // imprvs = imnext.clone()  (KFDSample.cc:169)
+        f->prevSlot = nextSlot;                      // the new previous frame's derivatives are computed behind the
+        if ((rc = flow_derivatives(f, f->prevSlot))) return rc;   // caller's back; the next call queues after them
+    }
+    CU_TRY(cudaEventSynchronize(f->evDone));
+    return RUMI_OK;
+}
+
+int rumi_flow_track(rumi_flow* f, const uint8_t* prev, const uint8_t* next, int w, int h, size_t stride,
+                    const float* prev_pts, int n, float* next_pts, uint8_t* status, float* err) {
+    int rc = rumi_flow_set_prev(f, prev, w, h, stride);
+    if (rc) return rc;
+    return rumi_flow_track_next(f, next, stride, prev_pts, n, next_pts, status, err, 0);
+}
+
+int rumi_flow_debug_level(rumi_flow* f, int which, int level, uint8_t* dst, int* w, int* h) {
+    if (!f || !f->havePrev) return fail(RUMI_ERR_ARG, "no frames held");
+    if (level < 0 || level >= f->levels) return fail(RUMI_ERR_ARG, "level out of range");
+    const int slot = which ? f->prevSlot ^ 1 : f->prevSlot;
+    if (!f->img[slot]) return fail(RUMI_ERR_ARG, "that frame was never uploaded");
+    if (w) *w = f->lw[level];
+    if (h) *h = f->lh[level];
+    if (dst) {
+        CU_TRY(cudaSetDevice(f->device));
+        CU_TRY(cudaStreamSynchronize(f->stream));
+        CU_TRY(cudaMemcpy2D(dst, f->lw[level], f->img[slot] + f->loff[level], f->lstride[level], f->lw[level],
+                            f->lh[level], cudaMemcpyDeviceToHost));
+    }
+    return RUMI_OK;
+}
+
+int rumi_flow_debug_deriv(rumi_flow* f, int level, int16_t* dst) {
+    if (!f || !f->havePrev) return fail(RUMI_ERR_ARG, "no frames held");
+    if (level < 0 || level >= f->levels || !dst) return fail(RUMI_ERR_ARG, "level out of range / NULL buffer");
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    CU_TRY(cudaMemcpy(dst, f->deriv + f->doff[level], (size_t)f->lw[level] * f->lh[level] * 4, cudaMemcpyDeviceToHost));
+    return RUMI_OK;
+}
+
+int rumi_flow_timer_start(rumi_flow* f) {
+    if (!f) return fail(RUMI_ERR_ARG, "context is NULL");
+    CU_TRY(cudaSetDevice(f->device));
+    if (!f->evStart) { CU_TRY(cudaEventCreate(&f->evStart)); CU_TRY(cudaEventCreate(&f->evStop)); }
+    CU_TRY(cudaEventRecord(f->evStart, f->stream));
+    return RUMI_OK;
+}
+
+int rumi_flow_timer_stop(rumi_flow* f, float* ms) {
+    if (!f || !f->evStart || !ms) return fail(RUMI_ERR_ARG, "timer not started");
+    CU_TRY(cudaEventRecord(f->evStop, f->stream));
+    CU_TRY(cudaEventSynchronize(f->evStop));
+    CU_TRY(cudaEventElapsedTime(ms, f->evStart, f->evStop));
+    return RUMI_OK;
+}
+
+}  // extern "C"

@@ -183,4 +183,21 @@ struct StereoRefineArgs {
 };
 void launch_stereo_refine(const StereoRefineArgs& a, cudaStream_t s);
 
+// ---- sparse pyramidal Lucas-Kanade flow of KFDSample::Step (flow.cu) ----
+constexpr int kFlowMaxLevels = 8;
+struct FlowPyramidView { const uint8_t* ptr[kFlowMaxLevels]; int w[kFlowMaxLevels], h[kFlowMaxLevels], stride[kFlowMaxLevels]; };
+struct FlowDerivView { short2* ptr[kFlowMaxLevels]; };       // [h][w] (dx, dy) per level, zero outside the image
+struct FlowTrackArgs {
+    FlowPyramidView I, J;        // previous / next frame
+    FlowDerivView D;             // Scharr derivatives of the previous frame
+    int maxLevel, maxCount;
+    double eps2;                 // criteria.epsilon squared
+    float minEig;
+    const float2* prevPts; float2* nextPts; uint8_t* status; float* err;
+    int n;
+};
+void launch_flow_pyrdown(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dstride, cudaStream_t s);
+void launch_flow_scharr(const FlowPyramidView& img, const FlowDerivView& der, int levels, cudaStream_t s);
+bool launch_flow_track(const FlowTrackArgs& a, int win, cudaStream_t s);   // false: window size not built
+
 }  // namespace rumi

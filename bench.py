@@ -389,6 +389,63 @@ def run_b200(args):
                                    "sample": "%d of the same descriptors, oracle/bow_oracle.cpp (pinned against the "
                                              "reference DBoW2), 1 thread, %.2f s" % (len(sample), dt)}
 
+    # ---- KFDSample::Step's optical flow: the frames of this rank tracked one after the other,
+    #      1000 points, 31x31 window, 3 levels, <= 20 iterations.  Sequential by construction (the points of frame k
+    #      come from frame k-1), so this is a latency figure: one image H2D + 2 pyrDown + tracker + D2H + Scharr per call ----
+    flow = None
+    if not args.no_flow:
+        from rumi_slam_b200 import SparsePyrLK
+        lk = SparsePyrLK(31, 2, 20, 0.03, device=local)
+        from rumi_slam_b200.synth import motion_sequence
+        nseq = 65
+        seq = motion_sequence(nseq, W_IMG, H_IMG, seed=500 + rank)         # camera translating 1.3 / -0.7 px per frame
+        exf = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local)
+        _, kp0, _ = exf(seq[0])
+        exf.close()
+        pts0 = np.stack([kp0["x"], kp0["y"]], 1).astype(np.float32)[:1000]
+        def flow_pass():
+            lk.set_prev(seq[0])
+            cur, tracked = pts0, 0
+            for i in range(1, nseq):
+                cur, st, _ = lk.track_next(seq[i], cur, advance=True)      # old = next (KFDSample.cc:166)
+                tracked += int(st.sum())
+            return tracked
+        flow_pass()
+        l0 = lk.launches()
+        barrier()
+        t_a = time.perf_counter()
+        tracked = flow_pass()
+        t_b = time.perf_counter()
+        barrier()
+        windows.append((t_a, t_b))
+        dt_flow = max_over_ranks((t_b - t_a) * 1e3) / 1e3
+        flow = {"workload": "KFDSample::Step flow: %d consecutive 640x480 host frames, %d points each, "
+                            "calcOpticalFlowPyrLK(31x31, maxLevel 2, 20 it, eps 0.03), synchronous calls" % (nseq - 1, len(pts0)),
+                "frames_per_s": world * (nseq - 1) / dt_flow, "points_per_s": world * (nseq - 1) * len(pts0) / dt_flow,
+                "ms_per_call": dt_flow / (nseq - 1) * 1e3, "gpu_launches": lk.launches() - l0,
+                "tracked_fraction": tracked / float((nseq - 1) * len(pts0)),
+                "timing": "host wall clock around synchronous calls (H2D, kernels, D2H inside)"}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import flow_oracle
+            t0 = time.perf_counter()
+            for i in range(1, 9):
+                flow_oracle.lk(seq[i - 1], seq[i], pts0)
+            dt = time.perf_counter() - t0
+            flow["cpu_baseline"] = {"value": 8 / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                                    "sample": "8 of the same frame pairs, oracle/flow_oracle.cpp (pinned against cv2), "
+                                              "1 thread, %.2f s" % dt}
+            try:
+                import cv2
+                cv2.setNumThreads(1)
+                crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 20, 0.03)
+                t0 = time.perf_counter()
+                for i in range(1, 33):
+                    cv2.calcOpticalFlowPyrLK(seq[i - 1], seq[i], pts0.reshape(-1, 1, 2), None, winSize=(31, 31),
+                                             maxLevel=2, criteria=crit)
+                flow["cv2_frames_per_s_1_thread"] = 32 / (time.perf_counter() - t0)
+            except Exception:
+                pass
+
     # ---- optional cfg 5b: 10^6 x 10^6 all-pairs top-2 (descriptors = extracted ones tiled with ~10 % of the bits
     #      flipped, so true neighbours exist), train set sharded over the ranks, NCCL all-gather of the candidates ----
     match_big = None
@@ -518,6 +575,7 @@ def run_b200(args):
                          "roofline": match_roofline(match_path, pairs_per_s, world, clocks.get("sm_mhz") or 1965.0)},
             "matching_5b": match_big,
             "bow": bow,
+            "flow": flow,
             "single_frame_latency": latency,
             "clocks": clocks}
     emit(json.dumps(line))
@@ -557,6 +615,7 @@ def main():
     ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames generated per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bow", action="store_true")
+    ap.add_argument("--no-flow", action="store_true")
     ap.add_argument("--match-big", type=int, default=0, help="also run cfg 5b with this many descriptors per side (10^6)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

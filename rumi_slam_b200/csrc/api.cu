@@ -1411,6 +1411,7 @@ struct rumi_flow {
     uint8_t* img[2] = {nullptr, nullptr}; size_t imgCap[2] = {0, 0};    // two pyramids: previous / next, swapped on advance
     uint8_t* deriv = nullptr; size_t derivCap = 0;   // Scharr (dx, dy) of the previous frame's pyramid
     uint8_t* pts = nullptr; size_t ptsCap = 0;       // prevPts | nextPts | err | status
+    uint8_t* hpts = nullptr; size_t hptsCap = 0;     // pinned mirror of `pts`: one H2D and ONE D2H per call
     int prevSlot = 0;
     bool havePrev = false;
     long long launches = 0;
@@ -1507,6 +1508,7 @@ void rumi_flow_destroy(rumi_flow* f) {
     cudaSetDevice(f->device);
     if (f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }
     cudaFree(f->img[0]); cudaFree(f->img[1]); cudaFree(f->deriv); cudaFree(f->pts);
+    if (f->hpts) cudaFreeHost(f->hpts);
     if (f->evStart) { cudaEventDestroy(f->evStart); cudaEventDestroy(f->evStop); }
     if (f->evDone) cudaEventDestroy(f->evDone);
     delete f;
@@ -1540,13 +1542,23 @@ int rumi_flow_track_next(rumi_flow* f, const uint8_t* img, size_t stride, const 
     if (n > 0 && (!prev_pts || !next_pts || !status)) return fail(RUMI_ERR_ARG, "NULL point buffers");
     CU_TRY(cudaSetDevice(f->device));
     const int nextSlot = f->prevSlot ^ 1;
-    int rc = flow_upload(f, nextSlot, img, stride);
-    if (rc) return rc;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oNext = al(8 * (size_t)n), oErr = oNext + al(8 * (size_t)n), oSt = oErr + al(4 * (size_t)n),
+                 total = oSt + al((size_t)n);
+    int rc;
     if (n > 0) {
-        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        const size_t oNext = al(8 * (size_t)n), oErr = oNext + al(8 * (size_t)n), oSt = oErr + al(4 * (size_t)n);
-        if ((rc = grow((void**)&f->pts, &f->ptsCap, oSt + al((size_t)n)))) return rc;
-        CU_TRY(cudaMemcpyAsync(f->pts, prev_pts, 8 * (size_t)n, cudaMemcpyDefault, f->stream));
+        if ((rc = grow((void**)&f->pts, &f->ptsCap, total))) return rc;
+        if (total > f->hptsCap) {
+            if (f->hpts) cudaFreeHost(f->hpts);
+            f->hpts = nullptr; f->hptsCap = 0;
+            CU_TRY(cudaHostAlloc((void**)&f->hpts, total, cudaHostAllocDefault));
+            f->hptsCap = total;
+        }
+        memcpy(f->hpts, prev_pts, 8 * (size_t)n);
+        CU_TRY(cudaMemcpyAsync(f->pts, f->hpts, 8 * (size_t)n, cudaMemcpyHostToDevice, f->stream));
+    }
+    if ((rc = flow_upload(f, nextSlot, img, stride))) return rc;
+    if (n > 0) {
         FlowTrackArgs a{};
         a.I = flow_view(f, f->prevSlot);
         a.J = flow_view(f, nextSlot);
@@ -1560,9 +1572,8 @@ int rumi_flow_track_next(rumi_flow* f, const uint8_t* img, size_t stride, const 
         if (!launch_flow_track(a, f->win, f->stream)) return fail(RUMI_ERR_ARG, "window %d not built", f->win);
         f->launches += 1;
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync(next_pts, f->pts + oNext, 8 * (size_t)n, cudaMemcpyDefault, f->stream));
-        CU_TRY(cudaMemcpyAsync(status, f->pts + oSt, (size_t)n, cudaMemcpyDefault, f->stream));
-        if (err) CU_TRY(cudaMemcpyAsync(err, f->pts + oErr, 4 * (size_t)n, cudaMemcpyDefault, f->stream));
+        CU_TRY(cudaMemcpyAsync(f->hpts + oNext, f->pts + oNext, oSt + (size_t)n - oNext, cudaMemcpyDeviceToHost,
+                               f->stream));
     }
     CU_TRY(cudaEventRecord(f->evDone, f->stream));   // the caller's results are complete here
     if (advance) {                                   // imprvs = imnext.clone()  (KFDSample.cc:169)
@@ -1570,6 +1581,11 @@ int rumi_flow_track_next(rumi_flow* f, const uint8_t* img, size_t stride, const 
         if ((rc = flow_derivatives(f, f->prevSlot))) return rc;   // caller's back; the next call queues after them
     }
     CU_TRY(cudaEventSynchronize(f->evDone));
+    if (n > 0) {
+        memcpy(next_pts, f->hpts + oNext, 8 * (size_t)n);
+        memcpy(status, f->hpts + oSt, (size_t)n);
+        if (err) memcpy(err, f->hpts + oErr, 4 * (size_t)n);
+    }
     return RUMI_OK;
 }
 

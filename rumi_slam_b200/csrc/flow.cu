@@ -3,15 +3,17 @@
 // OpenCV's algorithm (buildOpticalFlowPyramid / calcScharrDeriv / LKTrackerInvoker) re-designed for the device:
 //   * K13 pyrDown: thread per destination pixel, 5x5 [1 4 6 4 1] taps with REFLECT_101 indices, (sum + 128) >> 8;
 //   * K14 Scharr: thread per pixel, all levels in one launch, int16 (dx, dy) pairs;
-//   * K15 tracker: ONE WARP PER POINT walks ALL pyramid levels inside one launch (points are independent, so the
-//     per-level launches of the CPU code collapse into one).  Lane = window column (win + 1 <= 32 columns: the extra
-//     lane supplies the right neighbour of the bilinear sample through a shuffle); the win x win template patch and
-//     its two derivative patches stay in REGISTERS (3 x win ints per lane, rows fully unrolled); every Newton step is
-//     win + 1 byte loads per lane, 4 IMAD per row for the fixed-point bilinear sample, 2 IMAD for the mismatch
-//     vector.  The sums of the normal equations are sums of integer products: accumulated exactly (int32 per lane,
-//     int64 across the warp), i.e. OpenCV's integer-accumulator variant, so the result does not depend on the
-//     reduction order and equals the oracle bit for bit; the float32 tail uses explicit IEEE operations
-//     (--fmad=false, IEEE sqrt / division).
+//   * K15 tracker: ONE CTA OF 4 WARPS PER POINT walks ALL pyramid levels inside one launch (points are independent,
+//     so the per-level launches of the CPU code collapse into one).  The kernel is a chain of dependent Newton steps,
+//     i.e. latency bound: the window rows are split between the 4 warps (one per SM sub-partition) to shorten each
+//     step (one warp per point: 95 us for 1000 points; 4 warps: see profiles/).  Lane = window column (win + 1 <= 32
+//     columns: the extra lane supplies the right neighbour of the bilinear sample through a shuffle); the template
+//     patch and its two derivative patches stay in REGISTERS (3 ints per row and lane, rows fully unrolled); every
+//     Newton step is one byte load per row and lane, 4 IMAD for the fixed-point bilinear sample, 2 IMAD for the
+//     mismatch vector, then one shuffle + shared-memory reduction with a single barrier.  The sums of the normal
+//     equations are sums of integer products: accumulated exactly (int32 per lane, int64 across the CTA), i.e.
+//     OpenCV's integer-accumulator variant, so the result does not depend on the reduction order and equals the
+//     oracle bit for bit; the float32 tail uses explicit IEEE operations (--fmad=false, IEEE sqrt / division).
 #include "kernels.cuh"
 
 namespace rumi {
@@ -74,40 +76,62 @@ __device__ __forceinline__ long long warp_sum(long long v) {
     return v;
 }
 
-// Mismatch of the WIN x WIN window of J at (ix, iy) + fractional weights against the template rows in registers.
-// MODE 0: b-vector (sum diff * Ix, sum diff * Iy); MODE 1: sum |diff| (the `err` output).
-template <int WIN, int MODE>
-__device__ __forceinline__ void lk_window(const uint8_t* __restrict__ J, int w, int h, int stride, int ix, int iy,
-                                          const Weights k, int lane, const int (&Iw)[WIN], const int (&Ix)[WIN],
-                                          const int (&Iy)[WIN], long long& s1, long long& s2) {
-    const int xr = reflect101(ix + lane, w);
-    int a1 = 0, a2 = 0, prevH = 0;
+constexpr int kLkWarps = 4;                       // warps per point: the window rows are split between them
+
+// Exact sum of up to three per-lane integers over the CTA (4 warps).  Two shared-memory buffers used alternately
+// (`phase`), so one barrier per reduction is enough.
+template <int N>
+__device__ __forceinline__ void block_sum(long long (&v)[N], long long (*red)[kLkWarps][3], int& phase, int warp,
+                                          int lane) {
 #pragma unroll
-    for (int y = 0; y <= WIN; ++y) {
-        const int c = J[(size_t)reflect101(iy + y, h) * stride + xr];
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    long long(*buf)[3] = red[phase & 1];
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) buf[warp][i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = buf[0][i] + buf[1][i] + buf[2][i] + buf[3][i];
+    ++phase;
+}
+
+// Mismatch of this warp's rows [row0, row0 + RPW) of the WIN x WIN window of J at (ix, iy) + fractional weights
+// against the template rows in registers.  MODE 0: b-vector (sum diff * Ix, sum diff * Iy); MODE 1: sum |diff|.
+template <int WIN, int RPW, int MODE>
+__device__ __forceinline__ void lk_rows(const uint8_t* __restrict__ J, int w, int h, int stride, int ix, int iy,
+                                        const Weights k, int lane, int row0, const int (&Iw)[RPW],
+                                        const int (&Ix)[RPW], const int (&Iy)[RPW], int& a1, int& a2) {
+    const int xr = reflect101(ix + lane, w);
+    int prevH = 0;
+    a1 = 0; a2 = 0;
+#pragma unroll
+    for (int r = 0; r <= RPW; ++r) {
+        const int c = J[(size_t)reflect101(iy + row0 + r, h) * stride + xr];
         const int cr = __shfl_down_sync(0xFFFFFFFFu, c, 1);
-        if (y > 0) {
-            const int diff = ((prevH + c * k.w10 + cr * k.w11 + (1 << 8)) >> 9) - Iw[y - 1];
-            if (MODE == 0) { a1 += diff * Ix[y - 1]; a2 += diff * Iy[y - 1]; }
+        if (r > 0 && row0 + r - 1 < WIN) {
+            const int diff = ((prevH + c * k.w10 + cr * k.w11 + (1 << 8)) >> 9) - Iw[r - 1];
+            if (MODE == 0) { a1 += diff * Ix[r - 1]; a2 += diff * Iy[r - 1]; }
             else a1 += abs(diff);
         }
         prevH = c * k.w00 + cr * k.w01;
     }
     if (lane >= WIN) { a1 = 0; a2 = 0; }
-    s1 = warp_sum((long long)a1);
-    s2 = MODE == 0 ? warp_sum((long long)a2) : 0;
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(128) flow_lk_kernel(FlowTrackArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (p >= a.n) return;
+__global__ void __launch_bounds__(32 * kLkWarps) flow_lk_kernel(FlowTrackArgs a) {
+    constexpr int RPW = (WIN + kLkWarps - 1) / kLkWarps;
+    __shared__ long long red[2][kLkWarps][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x;
+    const int row0 = warp * RPW;
+    int phase = 0;
     const float half = (WIN - 1) * 0.5f;
     const float2 pp = a.prevPts[p];
     float outx = 0.f, outy = 0.f, errv = 0.f;
     int st = 1;
-    int Iw[WIN], Ix[WIN], Iy[WIN];
+    int Iw[RPW], Ix[RPW], Iy[RPW];
     for (int level = a.maxLevel; level >= 0; --level) {
         const int w = a.I.w[level], h = a.I.h[level];
         const float sc = (float)(1. / (1 << level));
@@ -123,8 +147,9 @@ __global__ void __launch_bounds__(128) flow_lk_kernel(FlowTrackArgs a) {
             continue;
         }
         Weights k = lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy));
-        int s11 = 0, s12 = 0, s22 = 0;
+        long long sA[3];
         {
+            int s11 = 0, s12 = 0, s22 = 0;
             const uint8_t* I = a.I.ptr[level];
             const short2* D = a.D.ptr[level];
             const int stride = a.I.stride[level];
@@ -132,31 +157,33 @@ __global__ void __launch_bounds__(128) flow_lk_kernel(FlowTrackArgs a) {
             const bool xin = X >= 0 && X < w;
             int pH = 0, pHx = 0, pHy = 0;
 #pragma unroll
-            for (int y = 0; y <= WIN; ++y) {
-                const int Y = ipy + y;
+            for (int r = 0; r <= RPW; ++r) {
+                const int Y = ipy + row0 + r;
                 const int c = I[(size_t)reflect101(Y, h) * stride + xr];
                 short2 d = make_short2(0, 0);
                 if (xin && Y >= 0 && Y < h) d = D[(size_t)Y * w + X];
                 const int cr = __shfl_down_sync(0xFFFFFFFFu, c, 1);
                 const int dpk = __shfl_down_sync(0xFFFFFFFFu, ((int)d.y << 16) | ((int)d.x & 0xFFFF), 1);
                 const int dxr = (int)(short)(dpk & 0xFFFF), dyr = dpk >> 16;
-                if (y > 0) {
+                if (r > 0) {
                     const int iv = (pH + c * k.w10 + cr * k.w11 + (1 << 8)) >> 9;
                     const int gx = (pHx + d.x * k.w10 + dxr * k.w11 + (1 << 13)) >> 14;
                     const int gy = (pHy + d.y * k.w10 + dyr * k.w11 + (1 << 13)) >> 14;
-                    Iw[y - 1] = iv; Ix[y - 1] = gx; Iy[y - 1] = gy;
-                    s11 += gx * gx; s12 += gx * gy; s22 += gy * gy;
+                    Iw[r - 1] = iv; Ix[r - 1] = gx; Iy[r - 1] = gy;
+                    if (row0 + r - 1 < WIN) { s11 += gx * gx; s12 += gx * gy; s22 += gy * gy; }
                 }
                 pH = c * k.w00 + cr * k.w01;
                 pHx = d.x * k.w00 + dxr * k.w01;
                 pHy = d.y * k.w00 + dyr * k.w01;
             }
             if (lane >= WIN) { s11 = 0; s12 = 0; s22 = 0; }
+            sA[0] = s11; sA[1] = s12; sA[2] = s22;
         }
+        block_sum<3>(sA, red, phase, warp, lane);
         const float FLT_SCALE = 1.f / (1 << 20);
-        const float A11 = __fmul_rn(__ll2float_rn(warp_sum((long long)s11)), FLT_SCALE);
-        const float A12 = __fmul_rn(__ll2float_rn(warp_sum((long long)s12)), FLT_SCALE);
-        const float A22 = __fmul_rn(__ll2float_rn(warp_sum((long long)s22)), FLT_SCALE);
+        const float A11 = __fmul_rn(__ll2float_rn(sA[0]), FLT_SCALE);
+        const float A12 = __fmul_rn(__ll2float_rn(sA[1]), FLT_SCALE);
+        const float A22 = __fmul_rn(__ll2float_rn(sA[2]), FLT_SCALE);
         float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dA = __fsub_rn(A11, A22);
         const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -177,9 +204,11 @@ __global__ void __launch_bounds__(128) flow_lk_kernel(FlowTrackArgs a) {
                 break;
             }
             k = lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny));
-            long long ib1, ib2;
-            lk_window<WIN, 0>(J, w, h, jstride, inx, iny, k, lane, Iw, Ix, Iy, ib1, ib2);
-            const float b1 = __fmul_rn(__ll2float_rn(ib1), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(ib2), FLT_SCALE);
+            int a1, a2;
+            lk_rows<WIN, RPW, 0>(J, w, h, jstride, inx, iny, k, lane, row0, Iw, Ix, Iy, a1, a2);
+            long long sb[2] = {a1, a2};
+            block_sum<2>(sb, red, phase, warp, lane);
+            const float b1 = __fmul_rn(__ll2float_rn(sb[0]), FLT_SCALE), b2 = __fmul_rn(__ll2float_rn(sb[1]), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -197,12 +226,14 @@ __global__ void __launch_bounds__(128) flow_lk_kernel(FlowTrackArgs a) {
             const int iex = (int)floorf(ex), iey = (int)floorf(ey);
             if (iex < -WIN || iex >= w || iey < -WIN || iey >= h) { st = 0; continue; }
             k = lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey));
-            long long e1, e2;
-            lk_window<WIN, 1>(J, w, h, jstride, iex, iey, k, lane, Iw, Ix, Iy, e1, e2);
-            errv = __fdiv_rn(__fmul_rn(__ll2float_rn(e1), 1.f), (float)(32 * WIN * WIN));
+            int a1, a2;
+            lk_rows<WIN, RPW, 1>(J, w, h, jstride, iex, iey, k, lane, row0, Iw, Ix, Iy, a1, a2);
+            long long se[1] = {a1};
+            block_sum<1>(se, red, phase, warp, lane);
+            errv = __fdiv_rn(__fmul_rn(__ll2float_rn(se[0]), 1.f), (float)(32 * WIN * WIN));
         }
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         a.nextPts[p] = make_float2(outx, outy);
         a.status[p] = (uint8_t)st;
         a.err[p] = errv;
@@ -222,11 +253,11 @@ void launch_flow_scharr(const FlowPyramidView& img, const FlowDerivView& der, in
 
 bool launch_flow_track(const FlowTrackArgs& a, int win, cudaStream_t s) {
     if (a.n <= 0) return true;
-    const int grid = (a.n + 3) / 4;
+    const int grid = a.n, threads = 32 * kLkWarps;          // one CTA (4 warps) per point
     switch (win) {
-        case 31: flow_lk_kernel<31><<<grid, 128, 0, s>>>(a); return true;
-        case 21: flow_lk_kernel<21><<<grid, 128, 0, s>>>(a); return true;
-        case 15: flow_lk_kernel<15><<<grid, 128, 0, s>>>(a); return true;
+        case 31: flow_lk_kernel<31><<<grid, threads, 0, s>>>(a); return true;
+        case 21: flow_lk_kernel<21><<<grid, threads, 0, s>>>(a); return true;
+        case 15: flow_lk_kernel<15><<<grid, threads, 0, s>>>(a); return true;
         default: return false;
     }
 }

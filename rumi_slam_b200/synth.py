@@ -127,3 +127,20 @@ def descriptors_near_vocabulary(desc_nodes, is_leaf, n, seed=0, flip=0.05):
     pick = rng.choice(leaves, n)
     mask = np.packbits(rng.random((n, 256)) < flip, axis=1)
     return desc_nodes[pick] ^ mask
+
+
+def motion_sequence(n, w=640, h=480, seed=0, vx=1.3, vy=-0.7, noise=2):
+    """n frames of a camera translating over one large synthetic scene with sub-pixel velocity (vx, vy) px/frame
+    (bilinear crops + independent sensor noise): the input KFDSample::Step sees on untracked frames."""
+    m = int(np.ceil(n * max(abs(vx), abs(vy)))) + 2
+    scene = synthetic_frame(seed, w + 2 * m, h + 2 * m).astype(np.float32)
+    rng = np.random.default_rng(seed + 1)
+    out = np.empty((n, h, w), np.uint8)
+    for k in range(n):
+        ox, oy = m + k * vx, m + k * vy
+        ix, iy = int(np.floor(ox)), int(np.floor(oy))
+        fx, fy = np.float32(ox - ix), np.float32(oy - iy)
+        c = lambda a, b: scene[iy + a:iy + a + h, ix + b:ix + b + w]
+        f = (1 - fx) * (1 - fy) * c(0, 0) + fx * (1 - fy) * c(0, 1) + (1 - fx) * fy * c(1, 0) + fx * fy * c(1, 1)
+        out[k] = np.clip(np.rint(f) + rng.integers(-noise, noise + 1, (h, w)), 0, 255).astype(np.uint8)
+    return out

@@ -15,8 +15,16 @@ def test_adapter_builds_and_links(tmp_path):
     main.write_text("""
 #include "ORBextractor.h"
 #include "ORBmatcher_accel.h"
+#include "SparsePyrLK_accel.h"
 #include <cstdio>
 int main() {
+    try {
+        SparsePyrLKAccel flow(cv::Size(31, 31), 2, 20, 0.03);
+        std::vector<cv::Point2f> old(1, cv::Point2f(20.f, 20.f)), next; std::vector<uchar> status; std::vector<float> err;
+        cv::Mat fa(64, 64, CV_8U), fb(64, 64, CV_8U);
+        flow.calc(fa, fb, old, next, status, err);
+        std::printf("flow status %d\\n", (int)status[0]);
+    } catch (const std::exception& e) { std::printf("no device: %s\\n", e.what()); }
     try {
         ORB_SLAM3::ORBextractor ex(1000, 1.2f, 8, 20, 7);
         std::vector<cv::KeyPoint> k; cv::Mat d; std::vector<int> lap = {0, 0};
@@ -34,7 +42,7 @@ int main() {
     exe = tmp_path / "adapter_test"
     cmd = ["g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "oracle", "cvstub"), "-I", ad,
            "-I", os.path.join(ROOT, "include"), str(main), os.path.join(ad, "ORBextractor.cc"),
-           os.path.join(ad, "ORBmatcher_accel.cc"), "-o", str(exe), "-L", os.path.join(ROOT, "rumi_slam_b200"),
+           os.path.join(ad, "ORBmatcher_accel.cc"), os.path.join(ad, "SparsePyrLK_accel.cc"), "-o", str(exe), "-L", os.path.join(ROOT, "rumi_slam_b200"),
            "-lrumi_orb", "-Wl,-rpath," + os.path.join(ROOT, "rumi_slam_b200")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]

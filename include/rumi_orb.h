@@ -124,6 +124,13 @@ int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T,
 /* Device-resident variant; train indices are reported as t_base + local index (train shard of a larger set). */
 int rumi_hamming_top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int t_base,
                              int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync);
+/* The same raw top-2 for MANY independent (query set, train set) pairs in one launch: the descriptor association of
+ * the matched key-frame pairs of a submap merge (the pairs R/lib_src/CloudMerging.cc:503-551 walks).
+ * segs[s] = {q_start, q_count, t_start, t_count} (rows of Q / T).  Per query row: idx1 = best train row RELATIVE to
+ * its segment's t_start (= feature index inside the second key frame), earliest index among ties, d2 may equal d1;
+ * (-1, 256, 256) for an empty train set and for rows no segment covers.  Result == rumi_hamming_top2 pair by pair. */
+int rumi_hamming_top2_pairs(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, const int32_t* segs,
+                            int nseg, int32_t* idx1, uint16_t* d1, uint16_t* d2);
 int rumi_match_timer_start(rumi_match* m);
 int rumi_match_timer_stop(rumi_match* m, float* ms);
 /* Which top-2 kernel the last rumi_hamming_top2* call used: 1 = LOP3+POPC (small problems), 2 = int8 tensor-core

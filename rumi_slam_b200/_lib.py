@@ -54,6 +54,7 @@ SIGNATURES = {
     "rumi_match_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "rumi_match_destroy": (None, [_vp]),
     "rumi_hamming_top2": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "rumi_hamming_top2_pairs": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "rumi_hamming_top2_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "rumi_top2_pack_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int]),
     "rumi_top2_merge_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),

@@ -51,6 +51,40 @@ int ORBmatcherAccel::MatchRatio(const cv::Mat& Q, const cv::Mat& T, std::vector<
     return n;
 }
 
+int ORBmatcherAccel::MatchKeyFramePairs(const std::vector<cv::Mat>& descA, const std::vector<cv::Mat>& descB,
+                                        std::vector<std::vector<int>>& matches12, int th) {
+    if (descA.size() != descB.size()) throw std::runtime_error("ORBmatcherAccel: pair lists differ in length");
+    std::vector<uint8_t> Q, T;
+    std::vector<int32_t> segs;
+    for (size_t p = 0; p < descA.size(); ++p) {
+        const std::vector<uint8_t> a = rows32(descA[p]), b = rows32(descB[p]);
+        segs.push_back((int32_t)(Q.size() / 32)); segs.push_back(descA[p].rows);
+        segs.push_back((int32_t)(T.size() / 32)); segs.push_back(descB[p].rows);
+        Q.insert(Q.end(), a.begin(), a.end());
+        T.insert(T.end(), b.begin(), b.end());
+    }
+    const int nq = (int)(Q.size() / 32), nt = (int)(T.size() / 32);
+    std::vector<int32_t> idx(nq);
+    std::vector<uint16_t> d1(nq), d2(nq);
+    if (rumi_hamming_top2_pairs(ctx, Q.data(), nq, T.data(), nt, segs.data(), (int)descA.size(), idx.data(), d1.data(),
+                                d2.data()) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    matches12.assign(descA.size(), std::vector<int>());
+    int n = 0;
+    for (size_t p = 0; p < descA.size(); ++p) {
+        matches12[p].assign(descA[p].rows, -1);
+        for (int q = 0; q < descA[p].rows; ++q) {
+            const int g = segs[4 * p] + q, bestDist1 = d1[g], bestDist2 = d2[g];
+            if (idx[g] >= 0 && bestDist1 <= th &&
+                static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {   // ORBmatcher.cc:290-291
+                matches12[p][q] = idx[g];
+                ++n;
+            }
+        }
+    }
+    return n;
+}
+
 void ORBmatcherAccel::StereoBest1(const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
                                   const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,
                                   const std::vector<float>& scaleFactors, int nRows, float minD, float maxD,

@@ -38,6 +38,12 @@ public:
     // matches12[q] = train index or -1.  Returns the number of matches.
     int MatchRatio(const cv::Mat& Q, const cv::Mat& T, std::vector<int>& matches12, int th = TH_LOW);
 
+    // Descriptor association of MANY matched key-frame pairs in one launch (submap merge: the pairs
+    // R/lib_src/CloudMerging.cc:503-551 walks).  Per pair p and feature q of descA[p]: matches12[p][q] = feature of
+    // descB[p] accepted by the rule above, else -1.  Same result as MatchRatio pair by pair.  Returns all matches.
+    int MatchKeyFramePairs(const std::vector<cv::Mat>& descA, const std::vector<cv::Mat>& descB,
+                           std::vector<std::vector<int>>& matches12, int th = TH_LOW);
+
     // Frame::ComputeStereoMatches row-band best-1 (R/lib_src/Frame.cc:844-905).
     void StereoBest1(const std::vector<cv::KeyPoint>& keysL, const cv::Mat& descL,
                      const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,

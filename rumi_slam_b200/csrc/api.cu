@@ -1011,6 +1011,51 @@ int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T,
     return RUMI_OK;
 }
 
+int rumi_hamming_top2_pairs(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, const int32_t* segs,
+                            int nseg, int32_t* idx1, uint16_t* d1, uint16_t* d2) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nq < 0 || nt < 0 || nseg < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (nq > 0 && (!Q || !idx1 || !d1 || !d2)) return fail(RUMI_ERR_ARG, "NULL buffer");
+    if (nseg > 0 && !segs) return fail(RUMI_ERR_ARG, "NULL segments");
+    int maxQ = 0;
+    for (int s = 0; s < nseg; ++s) {
+        const int32_t* g = segs + 4 * (size_t)s;
+        if (g[1] < 0 || g[3] < 0 || g[0] < 0 || g[2] < 0 || (long long)g[0] + g[1] > nq || (long long)g[2] + g[3] > nt)
+            return fail(RUMI_ERR_ARG, "segment %d outside the descriptor arrays", s);
+        if (g[3] >= (1 << 21)) return fail(RUMI_ERR_ARG, "segment %d: more than 2^21 train descriptors", s);
+        maxQ = std::max(maxQ, g[1]);
+    }
+    for (int i = 0; i < nq; ++i) { idx1[i] = -1; d1[i] = 256; d2[i] = 256; }     // rows no segment covers
+    if (nq == 0 || nseg == 0 || maxQ == 0) return RUMI_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    int rc;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oSeg = al(32 * (size_t)std::max(nt, 1));
+    if ((rc = grow((void**)&m->dQ, &m->qCap, 32 * (size_t)nq))) return rc;
+    if ((rc = grow((void**)&m->dT, &m->tCap, oSeg + al(16 * (size_t)nseg)))) return rc;
+    if ((rc = grow((void**)&m->dOut, &m->outCap, 8 * (size_t)nq))) return rc;
+    int32_t* dIdx = reinterpret_cast<int32_t*>(m->dOut);
+    uint16_t* dD1 = reinterpret_cast<uint16_t*>(m->dOut + 4 * (size_t)nq);
+    uint16_t* dD2 = dD1 + nq;
+    CU_TRY(cudaMemcpyAsync(m->dQ, Q, 32 * (size_t)nq, cudaMemcpyHostToDevice, m->stream));
+    if (nt > 0) CU_TRY(cudaMemcpyAsync(m->dT, T, 32 * (size_t)nt, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(m->dT + oSeg, segs, 16 * (size_t)nseg, cudaMemcpyHostToDevice, m->stream));
+    // rows outside every segment keep (-1, 256, 256): start from the host's initial values
+    CU_TRY(cudaMemcpyAsync(dIdx, idx1, 4 * (size_t)nq, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(dD1, d1, 2 * (size_t)nq, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(cudaMemcpyAsync(dD2, d2, 2 * (size_t)nq, cudaMemcpyHostToDevice, m->stream));
+    launch_hamming_top2_segments(m->dQ, m->dT, reinterpret_cast<const PairSegment*>(m->dT + oSeg), nseg, maxQ, dIdx, dD1,
+                                 dD2, m->stream);
+    m->launches += 1;
+    m->lastPath = 1;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(idx1, dIdx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(d1, dD1, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(d2, dD2, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
 int rumi_match_timer_start(rumi_match* m) {
     if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
     CU_TRY(cudaSetDevice(m->device));

@@ -144,6 +144,9 @@ int imma_slices(int nq, int nt);
 void launch_hamming_top2_imma(const uint8_t* Q, const uint8_t* Qx, int nq, const uint8_t* Tx, const uint16_t* popT,
                               int nt, int tBase, int slices, uint64_t* partial, cudaStream_t s);
 // merge per-shard candidates {d1,d2,idx} gathered in shard order: cand[shard][nq]
+struct PairSegment { int32_t qStart, qCount, tStart, tCount; };   // one (query set, train set) pair of K8-S
+void launch_hamming_top2_segments(const uint8_t* Q, const uint8_t* T, const PairSegment* segs, int nseg, int maxQ,
+                                  int32_t* idx1, uint16_t* d1, uint16_t* d2, cudaStream_t s);
 void launch_top2_merge(const uint64_t* packed, int nshards, int nq, int32_t* idx1, uint16_t* d1, uint16_t* d2,
                        cudaStream_t s);
 void launch_pack_top2(const int32_t* idx1, const uint16_t* d1, const uint16_t* d2, int nq, uint64_t* packed,

@@ -107,6 +107,58 @@ hamming_top2_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __rest
     }
 }
 
+// K8-S: the same top-2 scan for MANY independent (query set, train set) pairs in one launch -- the descriptor
+// association of matched key-frame pairs when two submaps are merged (one pair of key frames = one segment of
+// ~1000 x ~1000 descriptors; R/lib_src/CloudMerging.cc:503-551 walks the same pairs).  grid = (query blocks, segment);
+// one query per thread (segments are small: more CTAs matter more than register reuse), the segment's train rows
+// stream through shared memory in ascending index, strict '<' => earliest index among ties; the train index written
+// is relative to the segment (= feature index inside the second key frame).
+constexpr int kSegThreads = 128;
+__global__ void __launch_bounds__(kSegThreads)
+hamming_top2_segments_kernel(const uint8_t* __restrict__ Q, const uint8_t* __restrict__ T, const PairSegment* __restrict__ segs,
+                             int32_t* __restrict__ idx1, uint16_t* __restrict__ d1, uint16_t* __restrict__ d2) {
+    __shared__ uint4 tile[kTileRows * 2];
+    const PairSegment sg = segs[blockIdx.y];
+    if ((int)(blockIdx.x * kSegThreads) >= sg.qCount) return;
+    const int ql = blockIdx.x * kSegThreads + threadIdx.x;
+    const bool live = ql < sg.qCount;
+    uint32_t q[8];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(Q) + (size_t)(sg.qStart + min(ql, sg.qCount - 1)) * 2;
+        const uint4 a = src[0], b = src[1];
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    uint32_t k1 = 256u << kIdxBits, k2 = k1;
+    const uint32_t one = blockDim.z, two = one + one, keyMul = one << kIdxBits;
+    for (int base = 0; base < sg.tCount; base += kTileRows) {
+        const int rows = min(kTileRows, sg.tCount - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * 2; i += kSegThreads)
+            tile[i] = reinterpret_cast<const uint4*>(T)[(size_t)(sg.tStart + base) * 2 + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r) {
+            const uint32_t key = imad(hamming256(q, tile[2 * r], tile[2 * r + 1], one, two), keyMul, (uint32_t)(base + r));
+            k2 = min(k2, max(key, k1));
+            k1 = min(k1, key);
+        }
+    }
+    if (live) {
+        const uint32_t e1 = k1 >> kIdxBits, e2 = k2 >> kIdxBits;
+        const int qi = sg.qStart + ql;
+        idx1[qi] = e1 >= 256u ? -1 : (int32_t)(k1 & ((1u << kIdxBits) - 1u));
+        d1[qi] = (uint16_t)e1;
+        d2[qi] = (uint16_t)e2;
+    }
+}
+
+void launch_hamming_top2_segments(const uint8_t* Q, const uint8_t* T, const PairSegment* segs, int nseg, int maxQ,
+                                  int32_t* idx1, uint16_t* d1, uint16_t* d2, cudaStream_t s) {
+    if (nseg <= 0 || maxQ <= 0) return;
+    dim3 grid((maxQ + kSegThreads - 1) / kSegThreads, nseg);
+    hamming_top2_segments_kernel<<<grid, kSegThreads, 0, s>>>(Q, T, segs, idx1, d1, d2);
+}
+
 // K9: merge candidate triples {d1:16, d2:16, idx:32} of `nshards` shards, gathered in ascending train-index order.
 __global__ void top2_merge_kernel(const uint64_t* __restrict__ packed, int nshards, int nq, int32_t* idx1,
                                   uint16_t* d1, uint16_t* d2) {

@@ -122,6 +122,35 @@ class ORBmatcher:
         ok = self.accept_bow(d1, d2) & (i1 >= 0)
         return np.where(ok, i1, -1), d1, d2
 
+    # ---- descriptor association of many key-frame pairs in one launch (submap merge) ----
+    def top2_pairs(self, descs_a, descs_b):
+        """descs_a[i], descs_b[i]: descriptor matrices of the i-th matched key-frame pair (the pairs
+        CloudMerging.cc:503-551 walks).  Returns a list of (idx1, d1, d2) per pair, idx1 = feature index inside
+        descs_b[i]; identical to calling top2(descs_a[i], descs_b[i]) pair by pair."""
+        assert len(descs_a) == len(descs_b)
+        A = [np.ascontiguousarray(a, np.uint8).reshape(-1, 32) for a in descs_a]
+        B = [np.ascontiguousarray(b, np.uint8).reshape(-1, 32) for b in descs_b]
+        qo = np.concatenate([[0], np.cumsum([len(a) for a in A])]).astype(np.int64)
+        to = np.concatenate([[0], np.cumsum([len(b) for b in B])]).astype(np.int64)
+        Q = np.concatenate(A) if A else np.zeros((0, 32), np.uint8)
+        T = np.concatenate(B) if B else np.zeros((0, 32), np.uint8)
+        segs = np.array([[qo[i], len(A[i]), to[i], len(B[i])] for i in range(len(A))], np.int32).reshape(-1, 4)
+        i1 = np.zeros(len(Q), np.int32)
+        d1 = np.zeros(len(Q), np.uint16)
+        d2 = np.zeros(len(Q), np.uint16)
+        check(self._L.rumi_hamming_top2_pairs(self._m, ptr(Q), len(Q), ptr(T), len(T), ptr(segs), len(segs), ptr(i1),
+                                              ptr(d1), ptr(d2)))
+        return [(i1[qo[i]:qo[i + 1]], d1[qo[i]:qo[i + 1]], d2[qo[i]:qo[i + 1]]) for i in range(len(A))]
+
+    def match_keyframe_pairs(self, descs_a, descs_b, th=None):
+        """Per pair: matches12[q] = feature of key frame 2 accepted by the SearchByBoW rule (ORBmatcher.cc:290-291:
+        best1 <= TH_LOW and best1 < mfNNratio * best2), else -1."""
+        out = []
+        for i1, d1, d2 in self.top2_pairs(descs_a, descs_b):
+            ok = self.accept_bow(d1, d2, th) & (i1 >= 0)
+            out.append(np.where(ok, i1, -1))
+        return out
+
     # ---- stereo row-band best-1 (Frame.cc:828-905) ----
     def stereo_best1(self, Lk, Ld, Rk, Rd, scale_factors, n_rows, min_d, max_d):
         Lk = np.ascontiguousarray(Lk, KP_DTYPE)

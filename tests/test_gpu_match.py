@@ -139,3 +139,30 @@ def test_compute_stereo_matches_complete(oracle, w, h, nf, seed):
     ru, rdp, rn = oracle.stereo_match(left, right, lk, ld, rk, rd, bf, bf / fx)
     assert n == rn and n > 100
     assert np.array_equal(u, ru) and np.array_equal(d, rdp)
+
+
+def test_keyframe_pair_association_equals_pairwise(oracle):
+    """rumi_hamming_top2_pairs (one launch for all matched key-frame pairs of a submap merge) == the oracle's top-2
+    pair by pair, including ragged / empty pairs, duplicates (earliest index) and the acceptance rule."""
+    from rumi_slam_b200 import ORBmatcher
+    from rumi_slam_b200.synth import perturbed_descriptors
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+    sizes = [(1000, 1000), (1, 700), (513, 0), (0, 40), (128, 129), (257, 2000), (1200, 5), (1000, 1000)]
+    A, B = [], []
+    for i, (na, nb) in enumerate(sizes):
+        b = base[rng.choice(len(base), nb, replace=True)] if nb else np.zeros((0, 32), np.uint8)   # duplicates
+        a = perturbed_descriptors(b, na, seed=i, flip_p=0.06) if nb and na else rng.integers(0, 256, (na, 32), dtype=np.uint8)
+        A.append(a); B.append(b)
+    m = ORBmatcher(0.7)
+    got = m.top2_pairs(A, B)
+    nmatch = 0
+    for (i1, d1, d2), a, b in zip(got, A, B):
+        ri, r1, r2 = oracle.hamming_top2(a, b)
+        assert np.array_equal(i1, ri) and np.array_equal(d1, r1) and np.array_equal(d2, r2)
+    for mt, a, b in zip(m.match_keyframe_pairs(A, B), A, B):
+        want, _, _ = m.match_bow(a, b)
+        assert np.array_equal(mt, want)
+        nmatch += int((mt >= 0).sum())
+    assert nmatch > 1000
+    assert m.top2_pairs([], []) == []

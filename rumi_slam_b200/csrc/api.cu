@@ -898,8 +898,8 @@ struct rumi_match {
     uint8_t* dOut = nullptr; size_t outCap = 0;      // idx1 (4 B) | d1 (2 B) | d2 (2 B) per query
     uint8_t *qx = nullptr, *tx = nullptr; size_t qxCap = 0, txCap = 0;   // 0/1-byte expansions for the IMMA kernel
     uint16_t* popT = nullptr; size_t popCap = 0;
-    int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 2 IMMA whenever it applies
-    int lastPath = 0;                                // kernel of the last top-2 call: 1 LOP3+POPC, 2 IMMA
+    int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 2 IMMA (mma.sync), 3 tcgen05 UMMA
+    int lastPath = 0;                                // kernel of the last top-2 call: 1 LOP3+POPC, 2 IMMA, 3 UMMA
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     long long launches = 0;
 };
@@ -921,8 +921,16 @@ int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int
     // products); small ones (stereo bands, single frames) stay on the LOP3+POPC kernel, whose set-up is cheaper.
     const bool big = (long long)nq * nt >= 64ll * 1024 * 1024 && nq >= 256;
     const bool imma = nt > 0 && nt <= (1 << 22) && (m->mode == 2 || (m->mode == 0 && big));
+    const bool umma = nt > 0 && nt <= (1 << 22) && m->mode == 3;
     int rc;
-    if (imma) {
+    if (umma) {
+        const int slices = umma_slices(nq, nt);
+        if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
+        launch_hamming_top2_umma(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
+        launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
+        m->launches += 2;
+        m->lastPath = 3;
+    } else if (imma) {
         const int slices = imma_slices(nq, nt);
         if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
         if ((rc = grow((void**)&m->qx, &m->qxCap, 256 * (size_t)nq))) return rc;
@@ -961,7 +969,7 @@ int rumi_match_create(rumi_match** out, int device) {
     m->device = device;
     CU_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     const char* mm = getenv("RUMI_MATCH");                       // "popc" / "imma": force one top-2 kernel (tests, A/B)
-    if (mm) m->mode = mm[0] == 'p' ? 1 : mm[0] == 'i' ? 2 : 0;
+    if (mm) m->mode = mm[0] == 'p' ? 1 : mm[0] == 'i' ? 2 : mm[0] == 'u' ? 3 : 0;
     *out = m;
     return RUMI_OK;
 }

@@ -39,7 +39,7 @@ class ORBmatcher:
 
     def last_path(self):
         """Kernel of the last top-2 call: 'popc' (LOP3+POPC) or 'imma' (int8 tensor cores on expanded descriptors)."""
-        return {1: "popc", 2: "imma"}.get(int(self._L.rumi_match_last_path(self._m)), "none")
+        return {1: "popc", 2: "imma", 3: "umma"}.get(int(self._L.rumi_match_last_path(self._m)), "none")
 
     @staticmethod
     def DescriptorDistance(a, b):

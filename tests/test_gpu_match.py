@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 
 def matcher(mode=None, **kw):
-    """mode: None = automatic kernel choice, "popc" / "imma" = force the LOP3+POPC or the tensor-core top-2 kernel."""
+    """mode: None = automatic kernel choice, "popc" / "imma" / "umma" = force the LOP3+POPC, the mma.sync int8 or the
+    tcgen05 (TMEM accumulator) top-2 kernel."""
     import os
     from rumi_slam_b200 import ORBmatcher
     if mode:
@@ -23,7 +24,7 @@ def real_descriptors(oracle, seeds):
     return np.concatenate([oracle.extract(synthetic_frame(s))[1] for s in seeds])
 
 
-@pytest.mark.parametrize("mode", ["popc", "imma"])
+@pytest.mark.parametrize("mode", ["popc", "imma", "umma"])
 def test_top2_kats(mode):
     m = matcher(mode)
     zeros, ones = np.zeros((1, 32), np.uint8), np.full((1, 32), 255, np.uint8)
@@ -46,7 +47,7 @@ def test_top2_kat_all_ones_index(oracle):
     assert (gi[0], gd1[0], gd2[0]) == (-1, 256, 256)
 
 
-@pytest.mark.parametrize("mode", ["popc", "imma"])
+@pytest.mark.parametrize("mode", ["popc", "imma", "umma"])
 @pytest.mark.parametrize("nq,nt", [(1, 1), (37, 1000), (1000, 1000), (2049, 4099), (5000, 700), (130, 127), (129, 3000)])
 def test_top2_matches_oracle(oracle, nq, nt, mode):
     base = real_descriptors(oracle, (0, 1))
@@ -69,18 +70,19 @@ def test_top2_large_automatic_path_and_extreme_descriptors(oracle):
     Q[0] = 0; Q[1] = 255; T[10] = 0; T[11] = 255; T[19999] = 0
     T[15000] = T[123]; T[4000] = T[123]
     Q[2] = T[123]
-    auto, imma, popc = matcher(), matcher("imma"), matcher("popc")
+    auto, imma, popc, umma = matcher(), matcher("imma"), matcher("popc"), matcher("umma")
     ri, rd1, rd2 = oracle.hamming_top2(Q, T)
-    for m in (auto, imma, popc):
+    for m in (auto, imma, popc, umma):
         i1, d1, d2 = m.top2(Q, T)
         assert np.array_equal(i1, ri) and np.array_equal(d1, rd1) and np.array_equal(d2, rd2)
     assert ri[2] == 123 and rd1[2] == 0 and rd2[2] == 0 and ri[0] == 10
     # every train at distance 256 from the query: no match
-    i1, d1, d2 = imma.top2(np.zeros((300, 32), np.uint8), np.full((2000, 32), 255, np.uint8))
-    assert (i1 == -1).all() and (d1 == 256).all() and (d2 == 256).all()
+    for m in (imma, umma):
+        i1, d1, d2 = m.top2(np.zeros((300, 32), np.uint8), np.full((2000, 32), 255, np.uint8))
+        assert (i1 == -1).all() and (d1 == 256).all() and (d2 == 256).all()
 
 
-@pytest.mark.parametrize("mode", ["popc", "imma"])
+@pytest.mark.parametrize("mode", ["popc", "imma", "umma"])
 def test_sharded_merge_equals_single(oracle, mode):
     import torch
     base = real_descriptors(oracle, (2, 3, 4))

@@ -21,18 +21,19 @@ namespace rumi {
 
 namespace {
 
-constexpr int kUmBM = 128, kUmBN = 128;            // queries per CTA, train rows per tile
+constexpr int kUmBM = 256, kUmBN = 128;            // queries per CTA (two M = 128 MMAs share every train tile), train rows per tile
+constexpr int kUmThreads = kUmBM;
 constexpr int kUmIdxBits = 22;
 constexpr uint32_t kUmIdxMask = (1u << kUmIdxBits) - 1u;
-constexpr int kUmTileBytes = kUmBN * 256;          // one expanded operand tile: 32 KB
-constexpr int kUmChunkStride = kUmBN * 16;         // bytes between consecutive 16-byte K chunks (LBO)
-constexpr int kUmTmemCols = 256;                   // two 128-column accumulators
+constexpr int kUmTileBytes = 128 * 256;            // one expanded 128-row operand tile: 32 KB
+constexpr int kUmChunkStride = 128 * 16;           // bytes between consecutive 16-byte K chunks (LBO)
+constexpr int kUmTmemCols = 512;                   // (ping, pong) x (query half 0, 1) x 128 columns = all of TMEM
 
 struct UmmaSmem {
-    alignas(1024) uint8_t A[kUmTileBytes];
+    alignas(1024) uint8_t A[2][kUmTileBytes];      // query rows 0-127, 128-255 of this CTA
     alignas(1024) uint8_t B[2][kUmTileBytes];
     uint32_t cst[3][kUmBN];                        // per train row of a tile: ((pop + 256) << 22) | index
-    alignas(8) uint64_t bar[2];                    // MMA-complete barriers of the two accumulators
+    alignas(8) uint64_t bar[2];                    // MMA-complete barriers of the two accumulator sets
     uint32_t tmemBase;
 };
 
@@ -45,7 +46,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 
 // instruction descriptor: D = S32 (bits 4-5 = 2), A / B = unsigned 8 bit (0), both K-major, N >> 3 at bit 17, M >> 4 at 24
-constexpr uint32_t kUmIdesc = (2u << 4) | ((uint32_t)(kUmBN >> 3) << 17) | ((uint32_t)(kUmBM >> 4) << 24);
+constexpr uint32_t kUmIdesc = (2u << 4) | ((uint32_t)(kUmBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void umma_i8(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t accumulate) {
     asm volatile(
@@ -62,39 +63,56 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         :: "r"(bar), "r"(parity) : "memory");
 }
 
-// Expands row `row` of the packed descriptor array D (n rows) into the operand tile at `tile` (this thread's row r)
-// and returns its popcount.  Output byte k of the row = bit k of the descriptor; rows beyond n are zero.
-__device__ __forceinline__ int expand_row(const uint8_t* __restrict__ D, int n, int row, uint8_t* tile, int r) {
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ uint32_t umad(uint32_t a, uint32_t b, uint32_t c) {      // stays an IMAD (FMA pipe)
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Expands words [w0, w0 + NW) of row `row` of the packed descriptor array D (n rows) into the operand tile at `tile`
+// (row r of the tile) and returns the popcount of the WHOLE row.  Output byte k = bit k of the descriptor; rows beyond
+// n are zero.  4 bits -> 4 bytes by one multiply: (nibble * 0x00204081) & 0x01010101.
+struct PackedRow { uint4 a, b; };
+__device__ __forceinline__ PackedRow load_packed(const uint8_t* __restrict__ D, int n, int row) {
+    PackedRow p;
+    p.a = make_uint4(0, 0, 0, 0); p.b = p.a;
     if (row < n) {
         const uint4* src = reinterpret_cast<const uint4*>(D) + (size_t)row * 2;
-        const uint4 a = src[0], b = src[1];
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        p.a = src[0]; p.b = src[1];
     }
+    return p;
+}
+
+template <int NW>
+__device__ __forceinline__ int expand_row(const PackedRow& p, uint8_t* tile, int r, int w0) {
+    const uint32_t w[8] = {p.a.x, p.a.y, p.a.z, p.a.w, p.b.x, p.b.y, p.b.z, p.b.w};
     int pop = 0;
 #pragma unroll
+    for (int i = 0; i < 8; ++i) pop += __popc(w[i]);
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
-        pop += __popc(w[i]);
+        if (i < w0 || i >= w0 + NW) continue;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {                       // 16 bits -> one 16-byte chunk
             uint4 o;
             const uint32_t v = w[i] >> (16 * hf);
-            o.x = (((v >> 0) & 0xFu) * 0x00204081u) & 0x01010101u;
-            o.y = (((v >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-            o.z = (((v >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-            o.w = (((v >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+            o.x = umad((v >> 0) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
+            o.y = umad((v >> 4) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
+            o.z = umad((v >> 8) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
+            o.w = umad((v >> 12) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
             *reinterpret_cast<uint4*>(tile + (size_t)(2 * i + hf) * kUmChunkStride + (size_t)r * 16) = o;
         }
     }
     return pop;
 }
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kUmThreads, 1)
 hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ T, int nt, int tilesPerSlice,
                          int tBase, uint64_t* __restrict__ partial /* [gridDim.y][nq] */) {
     extern __shared__ __align__(1024) uint8_t smemRaw[];
     UmmaSmem& sm = *reinterpret_cast<UmmaSmem*>(smemRaw);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int half = tid >> 7, r128 = tid & 127;                        // query half / row inside a 128-row tile
     const int q0 = blockIdx.x * kUmBM;
     const int nTilesAll = (nt + kUmBN - 1) / kUmBN;
     const int tile0 = blockIdx.y * tilesPerSlice, tile1 = min(tile0 + tilesPerSlice, nTilesAll);
@@ -110,26 +128,38 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const int popq = expand_row(Q, nq, q0 + tid, sm.A, tid);
-    if (ntiles > 0) {
-        const int row = tile0 * kUmBN + tid;
-        const int pop = expand_row(T, nt, row, sm.B[0], tid);
-        sm.cst[0][tid] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
-    }
+    // train tile: thread (r128, half) expands words 4 * half .. 4 * half + 3 of train row r128.  The packed row of the
+    // tile after the one being expanded is already in flight (`nextRow`), so its L2 latency hides behind the epilogue.
+    PackedRow nextRow;
+    auto fetch_train = [&](int i) { nextRow = load_packed(T, i < ntiles ? nt : 0, (tile0 + i) * kUmBN + r128); };
+    auto expand_train = [&](int i) {
+        const int row = (tile0 + i) * kUmBN + r128;
+        const int pop = half == 0 ? expand_row<4>(nextRow, sm.B[i & 1], r128, 0) : expand_row<4>(nextRow, sm.B[i & 1], r128, 4);
+        if (half == 0)
+            sm.cst[i % 3][r128] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
+    };
+    fetch_train(0);
+    const PackedRow qrow = load_packed(Q, nq, q0 + tid);
+    const int popq = expand_row<8>(qrow, sm.A[half], r128, 0);
+    if (ntiles > 0) { expand_train(0); fetch_train(1); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmemBase;
-    const uint32_t aBase = smem_u32(sm.A), bBase0 = smem_u32(sm.B[0]), bBase1 = smem_u32(sm.B[1]);
+    const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
+    const uint32_t bBase0 = smem_u32(sm.B[0]), bBase1 = smem_u32(sm.B[1]);
     const uint32_t bar0 = smem_u32(&sm.bar[0]), bar1 = smem_u32(&sm.bar[1]);
 
-    auto issue = [&](int i) {                                           // tile i of this slice -> accumulator i & 1
+    auto issue = [&](int i) {                      // tile i of this slice -> accumulator set i & 1 (columns 256 * (i & 1))
         const uint32_t bBase = (i & 1) ? bBase1 : bBase0;
-        const uint32_t d = tmem + (uint32_t)(i & 1) * kUmBN;
+        const uint32_t d = tmem + (uint32_t)(i & 1) * 256u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            umma_i8(d, umma_desc(aBase + k * 2 * kUmChunkStride), umma_desc(bBase + k * 2 * kUmChunkStride), k > 0);
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
+            umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
+            umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                      :: "r"((i & 1) ? bar1 : bar0) : "memory");
     };
@@ -137,48 +167,72 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     __syncwarp();
 
     uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-    for (int i = 0; i < ntiles; ++i) {
-        if (i + 1 < ntiles) {                                           // expand the next tile while MMA i runs
-            const int row = (tile0 + i + 1) * kUmBN + tid;
-            const int pop = expand_row(T, nt, row, sm.B[(i + 1) & 1], tid);
-            sm.cst[(i + 1) % 3][tid] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);       // accumulator i & 1 complete
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                                // next tile expanded, epilogue i-1 finished
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (i + 1 < ntiles && tid == 0) issue(i + 1);
-        __syncwarp();
-        // ---- top-2 update of tile i: this thread = query row (TMEM lane), 128 columns = train rows of the tile ----
-        const uint32_t* cst = sm.cst[i % 3];
-        const uint32_t taddr = tmem + (uint32_t)(i & 1) * kUmBN + ((uint32_t)(warp * 32) << 16);
+    const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1));              // acc * negTwo = -2 <q,t> in the distance field
+    // 8 keys at a time: one min tree, and the exact update only when the group holds a key below the current second
+    // best (rare after the first tiles)
+    auto update8 = [&](const uint32_t* v, const uint32_t* cst) {
+        const uint4 ca = *reinterpret_cast<const uint4*>(cst);          // broadcast
+        const uint4 cb = *reinterpret_cast<const uint4*>(cst + 4);
+        uint32_t key[8];
+        key[0] = umad(v[0], negTwo, ca.x); key[1] = umad(v[1], negTwo, ca.y);
+        key[2] = umad(v[2], negTwo, ca.z); key[3] = umad(v[3], negTwo, ca.w);
+        key[4] = umad(v[4], negTwo, cb.x); key[5] = umad(v[5], negTwo, cb.y);
+        key[6] = umad(v[6], negTwo, cb.z); key[7] = umad(v[7], negTwo, cb.w);
+        const uint32_t m = min(min(min(key[0], key[1]), min(key[2], key[3])),
+                               min(min(key[4], key[5]), min(key[6], key[7])));
+        if (m < k2) {
 #pragma unroll
-        for (int c0 = 0; c0 < kUmBN; c0 += 32) {
-            uint32_t v[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr + (uint32_t)c0) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const uint4 c = *reinterpret_cast<const uint4*>(cst + c0 + j);       // broadcast
-                const uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t key = cc[e] - (v[j + e] << (kUmIdxBits + 1));     // - 2 <q,t> in the distance field
-                    k2 = min(k2, max(key, k1));
-                    k1 = min(k1, key);
-                }
+            for (int e = 0; e < 8; ++e) {
+                k2 = min(k2, max(key[e], k1));
+                k1 = min(k1, key[e]);
             }
         }
+    };
+#define RUMI_LDTM64(v, addr)                                                                                          \
+    asm volatile(                                                                                                     \
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "                                                                     \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "                            \
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "                            \
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"                     \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),             \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),       \
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),     \
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),     \
+          "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),     \
+          "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),     \
+          "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),     \
+          "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])      \
+        : "r"(addr) : "memory")
+
+    for (int i = 0; i < ntiles; ++i) {
+        if (i + 1 < ntiles) {                                           // expand the next tile, fetch the one after it
+            expand_train(i + 1);
+            fetch_train(i + 2);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                                // tile i+1 expanded, epilogue i-1 finished
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (i + 1 < ntiles && tid == 0) issue(i + 1);                   // queued behind MMA i: the tensor pipe never idles
+        __syncwarp();
+        mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);       // accumulator set i & 1 complete
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
+        //      accumulator), 128 columns = train rows of the tile; the second 64 columns load while the first are used
+        const uint32_t* cst = sm.cst[i % 3];
+        const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t va[64], vb[64];
+        RUMI_LDTM64(va, taddr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        RUMI_LDTM64(vb, taddr + 64u);
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) update8(va + j, cst + j);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) update8(vb + j, cst + 64 + j);
     }
+#undef RUMI_LDTM64
     // every accumulator read is complete (wait::ld above); release TMEM
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -203,7 +257,7 @@ int umma_slices(int nq, int nt) {
     const int qBlocks = (nq + kUmBM - 1) / kUmBM;
     const int nTiles = (nt + kUmBN - 1) / kUmBN;
     const int maxSlices = std::max(1, nTiles / 8);                      // at least 8 tiles per slice
-    int want = (148 * 2 * 4 + qBlocks - 1) / qBlocks;                    // >= 4 waves of two CTAs per SM
+    int want = (148 * 6 + qBlocks - 1) / qBlocks;                        // >= 6 waves of one CTA per SM
     want = std::min(std::min(want, maxSlices), 64);
     return std::max(want, 1);
 }
@@ -218,7 +272,7 @@ void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt
     const int nTiles = (nt + kUmBN - 1) / kUmBN;
     const int tilesPerSlice = (nTiles + slices - 1) / slices;
     dim3 grid((nq + kUmBM - 1) / kUmBM, slices);
-    hamming_top2_umma_kernel<<<grid, 128, sizeof(UmmaSmem) + 1024, s>>>(Q, nq, T, nt, tilesPerSlice, tBase, partial);
+    hamming_top2_umma_kernel<<<grid, kUmThreads, sizeof(UmmaSmem) + 1024, s>>>(Q, nq, T, nt, tilesPerSlice, tBase, partial);
 }
 
 }  // namespace rumi

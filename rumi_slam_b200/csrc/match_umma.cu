@@ -22,7 +22,8 @@ namespace rumi {
 namespace {
 
 constexpr int kUmBM = 256, kUmBN = 128;            // queries per CTA (two M = 128 MMAs share every train tile), train rows per tile
-constexpr int kUmThreads = kUmBM;
+constexpr int kUmWorkers = kUmBM;                  // 8 worker warps: thread = query row (epilogue) / half a train row (expansion)
+constexpr int kUmThreads = kUmWorkers + 32;        // + one warp whose only job is to issue the MMAs
 constexpr int kUmIdxBits = 22;
 constexpr uint32_t kUmIdxMask = (1u << kUmIdxBits) - 1u;
 constexpr int kUmTileBytes = 128 * 256;            // one expanded 128-row operand tile: 32 KB
@@ -32,11 +33,14 @@ constexpr int kUmTmemCols = 512;                   // (ping, pong) x (query half
 struct UmmaSmem {
     alignas(1024) uint8_t A[2][kUmTileBytes];      // query rows 0-127, 128-255 of this CTA
     alignas(1024) uint8_t B[2][kUmTileBytes];
-    uint32_t cst[3][kUmBN];                        // per train row of a tile: ((pop + 256) << 22) | index
-    alignas(8) uint64_t bar[2];                    // MMA-complete barriers of the two accumulator sets
+    uint32_t cst[4][kUmBN];                        // per train row of a tile: ((pop + 256) << 22) | index
+    alignas(8) uint64_t bar[2];                    // MMAs of tile i complete: accumulator set i & 1 full, B[i & 1] free
+    alignas(8) uint64_t full[2];                   // B[s] expanded by all worker warps
+    alignas(8) uint64_t accFree[2];                // accumulator set drained by all worker warps
     uint32_t tmemBase;
 };
 
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // no-swizzle K-major shared-memory matrix descriptor (start address, LBO, SBO in 16-byte units; version 1 = sm_100)
@@ -61,6 +65,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n"
         :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
 __device__ __forceinline__ uint32_t umad(uint32_t a, uint32_t b, uint32_t c) {      // stays an IMAD (FMA pipe)
@@ -124,70 +132,89 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[1])) : "memory");
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[b])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.full[b])), "r"(kUmWorkers / 32) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.accFree[b])), "r"(kUmWorkers / 32) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // train tile: thread (r128, half) expands words 4 * half .. 4 * half + 3 of train row r128.  The packed row of the
-    // tile after the one being expanded is already in flight (`nextRow`), so its L2 latency hides behind the epilogue.
-    PackedRow nextRow;
-    auto fetch_train = [&](int i) { nextRow = load_packed(T, i < ntiles ? nt : 0, (tile0 + i) * kUmBN + r128); };
-    auto expand_train = [&](int i) {
-        const int row = (tile0 + i) * kUmBN + r128;
-        const int pop = half == 0 ? expand_row<4>(nextRow, sm.B[i & 1], r128, 0) : expand_row<4>(nextRow, sm.B[i & 1], r128, 4);
-        if (half == 0)
-            sm.cst[i % 3][r128] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
-    };
-    fetch_train(0);
-    const PackedRow qrow = load_packed(Q, nq, q0 + tid);
-    const int popq = expand_row<8>(qrow, sm.A[half], r128, 0);
-    if (ntiles > 0) { expand_train(0); fetch_train(1); }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                               // TMEM base + barriers visible to every role
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmemBase;
-    const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
-    const uint32_t bBase0 = smem_u32(sm.B[0]), bBase1 = smem_u32(sm.B[1]);
     const uint32_t bar0 = smem_u32(&sm.bar[0]), bar1 = smem_u32(&sm.bar[1]);
-
-    auto issue = [&](int i) {                      // tile i of this slice -> accumulator set i & 1 (columns 256 * (i & 1))
-        const uint32_t bBase = (i & 1) ? bBase1 : bBase0;
-        const uint32_t d = tmem + (uint32_t)(i & 1) * 256u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
-            umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
-            umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     :: "r"((i & 1) ? bar1 : bar0) : "memory");
-    };
-    if (ntiles > 0 && tid == 0) issue(0);
-    __syncwarp();
-
+    const uint32_t full0 = smem_u32(&sm.full[0]), full1 = smem_u32(&sm.full[1]);
+    const uint32_t free0 = smem_u32(&sm.accFree[0]), free1 = smem_u32(&sm.accFree[1]);
     uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-    const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1));              // acc * negTwo = -2 <q,t> in the distance field
-    // 8 keys at a time: one min tree, and the exact update only when the group holds a key below the current second
-    // best (rare after the first tiles)
-    auto update8 = [&](const uint32_t* v, const uint32_t* cst) {
-        const uint4 ca = *reinterpret_cast<const uint4*>(cst);          // broadcast
-        const uint4 cb = *reinterpret_cast<const uint4*>(cst + 4);
-        uint32_t key[8];
-        key[0] = umad(v[0], negTwo, ca.x); key[1] = umad(v[1], negTwo, ca.y);
-        key[2] = umad(v[2], negTwo, ca.z); key[3] = umad(v[3], negTwo, ca.w);
-        key[4] = umad(v[4], negTwo, cb.x); key[5] = umad(v[5], negTwo, cb.y);
-        key[6] = umad(v[6], negTwo, cb.z); key[7] = umad(v[7], negTwo, cb.w);
-        const uint32_t m = min(min(min(key[0], key[1]), min(key[2], key[3])),
-                               min(min(key[4], key[5]), min(key[6], key[7])));
-        if (m < k2) {
+    int popq = 0;
+
+    if (warp == kUmWorkers / 32) {
+        // =========================== MMA issuer: one thread, never touches data ===========================
+        // tcgen05.mma blocks its issuing thread while the tensor pipe's queue is full (measured: ~1800 clk per tile when
+        // the issuer was also an epilogue thread -- the whole CTA then waited for it at the next barrier), so the
+        // issuer is a warp of its own and talks to the workers through mbarriers only.
+        if (lane_id() == 0) {
+            const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
+            const uint32_t bBase0 = smem_u32(sm.B[0]), bBase1 = smem_u32(sm.B[1]);
+            for (int i = 0; i < ntiles; ++i) {
+                mbar_wait((i & 1) ? full1 : full0, (uint32_t)(i >> 1) & 1u);              // B[i & 1] (and A) expanded
+                if (i >= 2) mbar_wait((i & 1) ? free1 : free0, (uint32_t)((i >> 1) - 1) & 1u);   // accumulators drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t bBase = (i & 1) ? bBase1 : bBase0;
+                const uint32_t d = tmem + (uint32_t)(i & 1) * 256u;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                k2 = min(k2, max(key[e], k1));
-                k1 = min(k1, key[e]);
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
+                    umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
+                    umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             :: "r"((i & 1) ? bar1 : bar0) : "memory");
             }
         }
-    };
+    } else {
+        // =========================== workers: expand train tiles, run the top-2 epilogue ===========================
+        const int lane = tid & 31;
+        // train tile: thread (r128, half) expands words 4 * half .. 4 * half + 3 of train row r128.  The packed row of
+        // the tile after the one being expanded is already in flight (`nextRow`): its L2 latency hides behind the epilogue.
+        PackedRow nextRow;
+        auto fetch_train = [&](int i) { nextRow = load_packed(T, i < ntiles ? nt : 0, (tile0 + i) * kUmBN + r128); };
+        auto expand_train = [&](int i) {           // ... then tells the issuer: one arrival per warp
+            const int row = (tile0 + i) * kUmBN + r128;
+            const int pop = half == 0 ? expand_row<4>(nextRow, sm.B[i & 1], r128, 0) : expand_row<4>(nextRow, sm.B[i & 1], r128, 4);
+            if (half == 0)
+                sm.cst[i & 3][r128] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive((i & 1) ? full1 : full0);
+        };
+        fetch_train(0);
+        const PackedRow qrow = load_packed(Q, nq, q0 + tid);
+        popq = expand_row<8>(qrow, sm.A[half], r128, 0);
+        if (ntiles > 0) { expand_train(0); fetch_train(1); }
+
+        const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1));          // acc * negTwo = -2 <q,t> in the distance field
+        // 8 keys at a time: one min tree, and the exact update only when the group holds a key below the current
+        // second best (rare after the first tiles)
+        auto update8 = [&](const uint32_t* v, const uint32_t* cst) {
+            const uint4 ca = *reinterpret_cast<const uint4*>(cst);      // broadcast
+            const uint4 cb = *reinterpret_cast<const uint4*>(cst + 4);
+            uint32_t key[8];
+            key[0] = umad(v[0], negTwo, ca.x); key[1] = umad(v[1], negTwo, ca.y);
+            key[2] = umad(v[2], negTwo, ca.z); key[3] = umad(v[3], negTwo, ca.w);
+            key[4] = umad(v[4], negTwo, cb.x); key[5] = umad(v[5], negTwo, cb.y);
+            key[6] = umad(v[6], negTwo, cb.z); key[7] = umad(v[7], negTwo, cb.w);
+            const uint32_t m = min(min(min(key[0], key[1]), min(key[2], key[3])),
+                                   min(min(key[4], key[5]), min(key[6], key[7])));
+            if (m < k2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    k2 = min(k2, max(key[e], k1));
+                    k1 = min(k1, key[e]);
+                }
+            }
+        };
 #define RUMI_LDTM64(v, addr)                                                                                          \
     asm volatile(                                                                                                     \
         "tcgen05.ld.sync.aligned.32x32b.x64.b32 "                                                                     \
@@ -205,34 +232,32 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
           "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])      \
         : "r"(addr) : "memory")
 
-    for (int i = 0; i < ntiles; ++i) {
-        if (i + 1 < ntiles) {                                           // expand the next tile, fetch the one after it
-            expand_train(i + 1);
-            fetch_train(i + 2);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < ntiles; ++i) {
+            if (i + 1 < ntiles) {                  // expand the next tile (its B slot was freed by MMA i-1, waited for
+                expand_train(i + 1);               // in the previous iteration), fetch the one after it
+                fetch_train(i + 2);
+            }
+            mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);   // accumulator set i & 1 complete
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
+            //      accumulator), 128 columns = train rows of the tile; the second 64 columns load while the first are used
+            const uint32_t* cst = sm.cst[i & 3];
+            const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + ((uint32_t)((warp & 3) * 32) << 16);
+            uint32_t va[64], vb[64];
+            RUMI_LDTM64(va, taddr);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            RUMI_LDTM64(vb, taddr + 64u);
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) update8(va + j, cst + j);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive((i & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) update8(vb + j, cst + 64 + j);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                                // tile i+1 expanded, epilogue i-1 finished
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (i + 1 < ntiles && tid == 0) issue(i + 1);                   // queued behind MMA i: the tensor pipe never idles
-        __syncwarp();
-        mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);       // accumulator set i & 1 complete
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
-        //      accumulator), 128 columns = train rows of the tile; the second 64 columns load while the first are used
-        const uint32_t* cst = sm.cst[i % 3];
-        const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t va[64], vb[64];
-        RUMI_LDTM64(va, taddr);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        RUMI_LDTM64(vb, taddr + 64u);
-#pragma unroll
-        for (int j = 0; j < 64; j += 8) update8(va + j, cst + j);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 64; j += 8) update8(vb + j, cst + 64 + j);
-    }
 #undef RUMI_LDTM64
+    }
     // every accumulator read is complete (wait::ld above); release TMEM
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -240,7 +265,7 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kUmTmemCols) : "memory");
     }
     const int qi = q0 + tid;
-    if (qi < nq) {
+    if (tid < kUmWorkers && qi < nq) {
         // key >> 22 = pop(t) - 2 dot + 256; distance = that - 256 + pop(q).  A distance of 256 is "no match"
         // (the reference's scan starts from bestDist = 256 with strict '<').
         int d1 = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> kUmIdxBits) - 256 + popq;

@@ -22,7 +22,7 @@ namespace rumi {
 namespace {
 
 constexpr int kUmBM = 256, kUmBN = 128;            // queries per CTA (two M = 128 MMAs share every train tile), train rows per tile
-constexpr int kUmWorkers = kUmBM;                  // 8 worker warps: thread = query row (epilogue) / half a train row (expansion)
+constexpr int kUmWorkers = 2 * kUmBM;              // 16 worker warps: (query half) x (TMEM lane quarter) x (column half of the tile)
 constexpr int kUmThreads = kUmWorkers + 32;        // + one warp whose only job is to issue the MMAs
 constexpr int kUmIdxBits = 22;
 constexpr uint32_t kUmIdxMask = (1u << kUmIdxBits) - 1u;
@@ -34,6 +34,7 @@ struct UmmaSmem {
     alignas(1024) uint8_t A[2][kUmTileBytes];      // query rows 0-127, 128-255 of this CTA
     alignas(1024) uint8_t B[2][kUmTileBytes];
     uint32_t cst[4][kUmBN];                        // per train row of a tile: ((pop + 256) << 22) | index
+    uint32_t mergeK[2][kUmBM];                     // (k1, k2) of the threads that scanned columns 64-127 of every tile
     alignas(8) uint64_t bar[2];                    // MMAs of tile i complete: accumulator set i & 1 full, B[i & 1] free
     alignas(8) uint64_t full[2];                   // B[s] expanded by all worker warps
     alignas(8) uint64_t accFree[2];                // accumulator set drained by all worker warps
@@ -120,7 +121,9 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     extern __shared__ __align__(1024) uint8_t smemRaw[];
     UmmaSmem& sm = *reinterpret_cast<UmmaSmem*>(smemRaw);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int half = tid >> 7, r128 = tid & 127;                        // query half / row inside a 128-row tile
+    const int r128 = tid & 127, quarter = (tid >> 7) & 3;               // row inside a 128-row tile / quarter of the work
+    const int half = quarter & 1, colHalf = quarter >> 1;               // epilogue: query half, columns [64 * colHalf, +64)
+    const int qrowLocal = half * 128 + r128;                            // query row of this thread inside the CTA
     const int q0 = blockIdx.x * kUmBM;
     const int nTilesAll = (nt + kUmBN - 1) / kUmBN;
     const int tile0 = blockIdx.y * tilesPerSlice, tile1 = min(tile0 + tilesPerSlice, nTilesAll);
@@ -176,22 +179,24 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     } else {
         // =========================== workers: expand train tiles, run the top-2 epilogue ===========================
         const int lane = tid & 31;
-        // train tile: thread (r128, half) expands words 4 * half .. 4 * half + 3 of train row r128.  The packed row of
+        // train tile: thread (r128, quarter) expands words 2 * quarter, 2 * quarter + 1 of train row r128.  The packed row of
         // the tile after the one being expanded is already in flight (`nextRow`): its L2 latency hides behind the epilogue.
         PackedRow nextRow;
         auto fetch_train = [&](int i) { nextRow = load_packed(T, i < ntiles ? nt : 0, (tile0 + i) * kUmBN + r128); };
         auto expand_train = [&](int i) {           // ... then tells the issuer: one arrival per warp
             const int row = (tile0 + i) * kUmBN + r128;
-            const int pop = half == 0 ? expand_row<4>(nextRow, sm.B[i & 1], r128, 0) : expand_row<4>(nextRow, sm.B[i & 1], r128, 4);
-            if (half == 0)
+            uint8_t* dst = sm.B[i & 1];
+            const int pop = quarter == 0 ? expand_row<2>(nextRow, dst, r128, 0) : quarter == 1 ? expand_row<2>(nextRow, dst, r128, 2)
+                          : quarter == 2 ? expand_row<2>(nextRow, dst, r128, 4) : expand_row<2>(nextRow, dst, r128, 6);
+            if (quarter == 0)
                 sm.cst[i & 3][r128] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive((i & 1) ? full1 : full0);
         };
         fetch_train(0);
-        const PackedRow qrow = load_packed(Q, nq, q0 + tid);
-        popq = expand_row<8>(qrow, sm.A[half], r128, 0);
+        const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
+        popq = colHalf == 0 ? expand_row<4>(qrow, sm.A[half], r128, 0) : expand_row<4>(qrow, sm.A[half], r128, 4);
         if (ntiles > 0) { expand_train(0); fetch_train(1); }
 
         const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1));          // acc * negTwo = -2 <q,t> in the distance field
@@ -215,21 +220,15 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
                 }
             }
         };
-#define RUMI_LDTM64(v, addr)                                                                                          \
+#define RUMI_LDTM32(v, addr)                                                                                          \
     asm volatile(                                                                                                     \
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "                                                                     \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "                            \
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "                            \
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"                     \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                     \
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),             \
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),       \
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),     \
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),     \
-          "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),     \
-          "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),     \
-          "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),     \
-          "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])      \
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])      \
         : "r"(addr) : "memory")
 
         for (int i = 0; i < ntiles; ++i) {
@@ -240,23 +239,27 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);   // accumulator set i & 1 complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
-            //      accumulator), 128 columns = train rows of the tile; the second 64 columns load while the first are used
-            const uint32_t* cst = sm.cst[i & 3];
-            const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + ((uint32_t)((warp & 3) * 32) << 16);
-            uint32_t va[64], vb[64];
-            RUMI_LDTM64(va, taddr);
+            //      accumulator) x 64 of the 128 columns (train rows of the tile); the second 32 columns load while the
+            //      first are used
+            const uint32_t* cst = sm.cst[i & 3] + 64 * colHalf;
+            const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + (uint32_t)colHalf * 64u +
+                                   ((uint32_t)((warp & 3) * 32) << 16);
+            uint32_t va[32], vb[32];
+            RUMI_LDTM32(va, taddr);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            RUMI_LDTM64(vb, taddr + 64u);
+            RUMI_LDTM32(vb, taddr + 32u);
 #pragma unroll
-            for (int j = 0; j < 64; j += 8) update8(va + j, cst + j);
+            for (int j = 0; j < 32; j += 8) update8(va + j, cst + j);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive((i & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
 #pragma unroll
-            for (int j = 0; j < 64; j += 8) update8(vb + j, cst + 64 + j);
+            for (int j = 0; j < 32; j += 8) update8(vb + j, cst + 32 + j);
         }
-#undef RUMI_LDTM64
+#undef RUMI_LDTM32
+        // the two threads of a query row scanned disjoint train rows (unique keys): park one half for the exact merge
+        if (colHalf == 1) { sm.mergeK[0][qrowLocal] = k1; sm.mergeK[1][qrowLocal] = k2; }
     }
     // every accumulator read is complete (wait::ld above); release TMEM
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -264,8 +267,14 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kUmTmemCols) : "memory");
     }
-    const int qi = q0 + tid;
-    if (tid < kUmWorkers && qi < nq) {
+    __syncthreads();
+    const int qi = q0 + qrowLocal;
+    if (tid < kUmBM) {                             // colHalf == 0 workers: min / max merge with the parked half
+        const uint32_t o1 = sm.mergeK[0][qrowLocal], o2 = sm.mergeK[1][qrowLocal];
+        k2 = min(min(k2, o2), max(k1, o1));
+        k1 = min(k1, o1);
+    }
+    if (tid < kUmBM && qi < nq) {
         // key >> 22 = pop(t) - 2 dot + 256; distance = that - 256 + pop(q).  A distance of 256 is "no match"
         // (the reference's scan starts from bestDist = 256 with strict '<').
         int d1 = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> kUmIdxBits) - 256 + popq;

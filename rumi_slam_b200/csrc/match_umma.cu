@@ -92,7 +92,12 @@ __device__ __forceinline__ PackedRow load_packed(const uint8_t* __restrict__ D, 
     return p;
 }
 
-template <int NW>
+// Expands words [w0, w0 + NW) of a packed row into the operand tile (row r).  One byte of 8 bits becomes 8 output
+// bytes with ONE 64-bit multiply: x * 0x8040201008040201 puts bit i of x at positions i + 9 j (all distinct, so no
+// carries); position 8 j + 7 holds bit 7 - j.  The order of the 256 products inside a dot product is free, so the
+// bit-reversed byte order is used as is on both sides; the train side keeps the bit where it lands (bytes 0 / 0x80,
+// accumulator = 128 <q,t>), the query side (once per CTA) shifts it down to 0 / 1.
+template <int NW, bool kQuery>
 __device__ __forceinline__ int expand_row(const PackedRow& p, uint8_t* tile, int r, int w0) {
     const uint32_t w[8] = {p.a.x, p.a.y, p.a.z, p.a.w, p.b.x, p.b.y, p.b.z, p.b.w};
     int pop = 0;
@@ -103,12 +108,12 @@ __device__ __forceinline__ int expand_row(const PackedRow& p, uint8_t* tile, int
         if (i < w0 || i >= w0 + NW) continue;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {                       // 16 bits -> one 16-byte chunk
+            const unsigned long long lo = (unsigned long long)__byte_perm(w[i], 0, 0x4440 + 2 * hf) * 0x8040201008040201ull;
+            const unsigned long long hi = (unsigned long long)__byte_perm(w[i], 0, 0x4441 + 2 * hf) * 0x8040201008040201ull;
             uint4 o;
-            const uint32_t v = w[i] >> (16 * hf);
-            o.x = umad((v >> 0) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
-            o.y = umad((v >> 4) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
-            o.z = umad((v >> 8) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
-            o.w = umad((v >> 12) & 0xFu, 0x00204081u, 0u) & 0x01010101u;
+            o.x = (uint32_t)lo & 0x80808080u; o.y = (uint32_t)(lo >> 32) & 0x80808080u;
+            o.z = (uint32_t)hi & 0x80808080u; o.w = (uint32_t)(hi >> 32) & 0x80808080u;
+            if (kQuery) { o.x >>= 7; o.y >>= 7; o.z >>= 7; o.w >>= 7; }
             *reinterpret_cast<uint4*>(tile + (size_t)(2 * i + hf) * kUmChunkStride + (size_t)r * 16) = o;
         }
     }
@@ -186,8 +191,8 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         auto expand_train = [&](int i) {           // ... then tells the issuer: one arrival per warp
             const int row = (tile0 + i) * kUmBN + r128;
             uint8_t* dst = sm.B[i & 1];
-            const int pop = quarter == 0 ? expand_row<2>(nextRow, dst, r128, 0) : quarter == 1 ? expand_row<2>(nextRow, dst, r128, 2)
-                          : quarter == 2 ? expand_row<2>(nextRow, dst, r128, 4) : expand_row<2>(nextRow, dst, r128, 6);
+            const int pop = quarter == 0 ? expand_row<2, false>(nextRow, dst, r128, 0) : quarter == 1 ? expand_row<2, false>(nextRow, dst, r128, 2)
+                          : quarter == 2 ? expand_row<2, false>(nextRow, dst, r128, 4) : expand_row<2, false>(nextRow, dst, r128, 6);
             if (quarter == 0)
                 sm.cst[i & 3][r128] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -196,10 +201,10 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         };
         fetch_train(0);
         const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
-        popq = colHalf == 0 ? expand_row<4>(qrow, sm.A[half], r128, 0) : expand_row<4>(qrow, sm.A[half], r128, 4);
+        popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
         if (ntiles > 0) { expand_train(0); fetch_train(1); }
 
-        const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1));          // acc * negTwo = -2 <q,t> in the distance field
+        const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1 - 7));      // acc = 128 <q,t>: acc * negTwo = -2 <q,t> in the distance field
         // 8 keys at a time: one min tree, and the exact update only when the group holds a key below the current
         // second best (rare after the first tiles)
         auto update8 = [&](const uint32_t* v, const uint32_t* cst) {
@@ -210,8 +215,8 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             key[2] = umad(v[2], negTwo, ca.z); key[3] = umad(v[3], negTwo, ca.w);
             key[4] = umad(v[4], negTwo, cb.x); key[5] = umad(v[5], negTwo, cb.y);
             key[6] = umad(v[6], negTwo, cb.z); key[7] = umad(v[7], negTwo, cb.w);
-            const uint32_t m = min(min(min(key[0], key[1]), min(key[2], key[3])),
-                                   min(min(key[4], key[5]), min(key[6], key[7])));
+            // a chain, so that ptxas pairs the steps into 3-input VIMNMX3
+            const uint32_t m = min(min(min(min(min(min(min(key[0], key[1]), key[2]), key[3]), key[4]), key[5]), key[6]), key[7]);
             if (m < k2) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {

@@ -148,6 +148,18 @@ def match_roofline(path, pairs_per_s, world, sm_mhz):
     """The top-2 kernels are bound by an execution pipe, not by HBM (operands are reused from shared memory):
     popc: 5 POPC per pair at the measured 16 POPC/clk/SM; imma: 1/16 m16n8k32 IMMA per pair at the measured 0.478
     warp-IMMA/clk/SM (tools/probe/pipe_probe.cu)."""
+    if path == "umma":
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            src = "2 x MEASURED_PEAKS.json bf16_tflops (int8 dense = twice the bf16 rate; nominal 4.5 POP/s)"
+        except Exception:
+            bf16, src = 2250.0, "nominal 4.5 POP/s int8 dense (no MEASURED_PEAKS.json)"
+        peak = world * 2 * bf16 * 1e12 / 512.0            # 256 MACs = 512 ops per pair
+        return {"bound": "tensor", "kernel": "tcgen05.mma kind::i8 (UTCIMMA), TMEM accumulators", "ops_per_pair": 512,
+                "achieved": round(pairs_per_s * 512 / 1e12, 1), "peak": round(world * 2 * bf16, 1), "unit": "TOP/s",
+                "peak_pairs_per_s": peak, "frac": pairs_per_s / peak, "peak_source": src,
+                "note": "the top-2 epilogue (1 IMAD + min tree per pair on the CUDA cores) and the in-kernel bit expansion "
+                        "bound the kernel, not the tensor pipe (ncu: profiles/r1_ncu_umma.json)"}
     if path == "imma":
         peak = world * 148 * 0.478 * 16 * sm_mhz * 1e6
         return {"bound": "imma-pipe", "imma_per_pair": 1.0 / 16, "imma_per_clk_per_sm": 0.478, "peak_pairs_per_s": peak,

@@ -917,11 +917,13 @@ int grow(void** p, size_t* cap, size_t need) {
 int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int tBase, int32_t* dIdx,
                 uint16_t* dD1, uint16_t* dD2) {
     if (((uintptr_t)dQ | (uintptr_t)dT) & 15) return fail(RUMI_ERR_ARG, "descriptor arrays must be 16-byte aligned");
-    // Large problems go to the integer tensor cores (descriptors expanded to 0/1 bytes once per call, int8 IMMA dot
-    // products); small ones (stereo bands, single frames) stay on the LOP3+POPC kernel, whose set-up is cheaper.
+    // Large problems go to the tensor cores: tcgen05 kind::i8 UMMA with TMEM accumulators (K8-U, operands expanded
+    // in-kernel from the packed rows); small ones (stereo bands, single frames) stay on the LOP3+POPC kernel, whose
+    // set-up is cheaper.  The mma.sync int8 kernel (K8-T) is kept behind RUMI_MATCH=imma for comparison.
     const bool big = (long long)nq * nt >= 64ll * 1024 * 1024 && nq >= 256;
-    const bool imma = nt > 0 && nt <= (1 << 22) && (m->mode == 2 || (m->mode == 0 && big));
-    const bool umma = nt > 0 && nt <= (1 << 22) && m->mode == 3;
+    const bool fits = nt > 0 && nt <= (1 << 22);
+    const bool umma = fits && (m->mode == 3 || (m->mode == 0 && big));
+    const bool imma = fits && m->mode == 2;
     int rc;
     if (umma) {
         const int slices = umma_slices(nq, nt);

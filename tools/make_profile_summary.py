@@ -15,6 +15,8 @@ for st, v in k["kernels"].items():
         v["warps_active_pct"], v["registers"]))
 st = b["roofline"]["stages"]
 fa = k["kernels"]["fast"]
+um = k["kernels"]["hamming_top2_umma"]
+im = k["kernels"]["hamming_top2_imma"]
 scal = []
 for name in ("r1_bench_n2.json", "r1_bench_n8.json"):
     if os.path.exists(P(name)):
@@ -31,7 +33,9 @@ if os.path.exists(P("r1_bench_5b_n1.json")):
 md = f"""# Round 1 -- final state of the round (supersedes r1_first_path_summary.md, kept for history)
 
 Workload of the captures: `tools/prof_run.py` = one 64-frame chunk of synthetic 640x480 frames (1000 features, 8 levels,
-1.2, FAST 20/7) through `rumi_orb_extract_batch_device`, 2 warm-up + 2 profiled passes, then 8192 x 40000 Hamming top-2.
+1.2, FAST 20/7) through `rumi_orb_extract_batch_device` (2 warm-up + 2 profiled passes), 8192 x 40000 Hamming top-2 on the
+LOP3+POPC kernel, 16384 x 40000 on the mma.sync int8 kernel and on the tcgen05 kernel, 4 optical-flow steps of 1000 points
+(the `--set full` capture runs the same script with `PROF_LIGHT=1`: one warm-up + one profiled pass of each).
 
 ## 1. Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none --csv`, `r1_launches_final.csv`)
 
@@ -39,7 +43,7 @@ Workload of the captures: `tools/prof_run.py` = one 64-frame chunk of synthetic 
 Shares agree with bench.py's own exclusive stage pass (CUDA events, one stream, `r1_bench_final.json`): pyramid {st['pyramid']['share']:.3f},
 FAST {st['fast']['share']:.3f}, quad-tree {st['octree']['share']:.3f}, slots {st['slots']['share']:.3f}, blur {st['blur']['share']:.3f}, describe {st['describe']['share']:.3f} of the extraction step.
 
-## 2. Per-kernel counters (`ncu --set full --clock-control none --import-source on`, `r1_ncu_kernels.json`)
+## 2. Per-kernel counters (`PROF_LIGHT=1 ncu --set full --clock-control none`, condensed on the GPU box by `tools/ncu_to_json.py` into `r1_ncu_kernels.json`)
 
 | stage | launches/chunk | us/chunk | DRAM r / w (MB) | warp instr (M) | issue % | ALU / FMA / LSU pipe % | warps active % | regs |
 |---|---|---|---|---|---|---|---|---|
@@ -47,24 +51,35 @@ FAST {st['fast']['share']:.3f}, quad-tree {st['octree']['share']:.3f}, slots {st
 
 Reading: no kernel moves more DRAM bytes than its algorithmic bytes (FAST reads {fa['dram_read_bytes']/1e6:.1f} MB for 60.8 MB of pixels: levels
 1-7 are still in L2; blur 63.7 + 18.5 MB for 121.7 MB), so nothing is re-read; every kernel is **instruction-issue
-bound on the integer (ALU) pipe** or latency bound (quad-tree, the per-level pyramid launches), not HBM bound, exactly
-as SURVEY.md 8d predicts.  FAST is the dominant kernel: {fa['warp_instructions']/1e6:.0f} M warp instructions per chunk = {fa['warp_instructions']*32/60.8e6:.0f} thread
+bound on the integer (ALU) pipe** or latency bound (quad-tree, the per-level pyramid launches, the Newton chain of the LK
+tracker), not HBM bound, exactly as SURVEY.md 8d predicts.  FAST is the dominant kernel: {fa['warp_instructions']/1e6:.0f} M warp instructions per chunk = {fa['warp_instructions']*32/60.8e6:.0f} thread
 instructions per pixel, ALU pipe {fa['alu_pipe_pct']:.0f} % of its peak, issue slots {fa['issue_active_pct']:.0f} % busy; its stalls are spread over fixed-latency
 waits, "not selected" and math-pipe throttle, i.e. the schedulers are saturated for this instruction mix.  Where its
-instructions go (`tools/sass_phases.py` on the source page): SWAR pretest 27 %, exact score 33 %, queue append 10 %,
-NMS + emission 15 %, staging / set-up 11 %.
+instructions go (`tools/sass_phases.py` on the source page of the 270-us version): SWAR pretest 27 %, exact score 33 %, queue
+append 10 %, NMS + emission 15 %, staging / set-up 11 %; the later changes (second compaction + warp bitonic sort for the
+emission, ini / min thresholds as two passes per cell, one ballot per byte plane) removed 67 M of the 190 M warp instructions.
+
+The tcgen05 top-2 kernel (`hamming_top2_umma`, K8-U): {um['duration_us']:.0f} us for 16384 x 40000 pairs under ncu = {16384*40000/um['duration_us']/1e6:.2f}e12 pairs/s;
+{um['warp_instructions']/1e6:.0f} M warp instructions against {im['warp_instructions']/1e6:.0f} M for the mma.sync kernel and {k['kernels']['hamming_top2']['warp_instructions']*2/1e6:.0f} M (scaled to the same size) for
+LOP3+POPC: the MMAs are 32 `UTCIMMA` per tile issued by ONE thread, what is left on the CUDA cores is the bit expansion and the
+top-2 epilogue (issue {um['issue_active_pct']:.0f} %, ALU pipe {um['alu_pipe_pct']:.0f} %).  Tensor pipe ({{sm__pipe_tensor_cycles_active}} of an earlier capture of the same
+kernel at 2.7e12 pairs/s, `r1_ncu_umma_v3_excerpt.txt`): 33 % busy, `sm__ops_path_tensor_op_utcimma_src_int8` 30 % of peak -- the
+kernel is bound by the epilogue / expansion instruction stream, not by the tensor cores.  Phase clocks taken inside the kernel
+(clock64 per role): issuer blocked in `tcgen05.mma` 1 440 clk per tile, workers 830 clk expansion + 1 400 clk epilogue per tile.
 
 ## 3. What changed during the round (per 64-frame chunk, ncu durations)
 
 | kernel | first path | now | how |
 |---|---|---|---|
-| FAST | 993 us | {fa['duration_us']:.0f} us | SWAR 4-pixel pretest, ballot-compacted queue, both-polarity packed score (1 IMAD per ring pixel, 40 VIMNMX3.S16x2), unified tile/score pitch, branch-free NMS, in-place survivor list + rank emission, cell table |
+| FAST | 993 us | {fa['duration_us']:.0f} us | SWAR 4-pixel pretest, ballot-compacted queue, both-polarity packed score (1 IMAD per ring pixel, 40 VIMNMX3.S16x2), unified tile/score pitch, branch-free NMS, in-place survivor list, second compaction + warp bitonic sort for the emission, two-pass ini / min thresholds, cell table |
 | quad-tree | 276 us | {k['kernels']['octree']['duration_us']:.0f} us | closed-form level phase, block scans, register bitonic sort, parallel stable-rank replay of std::sort's insertion phase |
 | blur | 268 us | {k['kernels']['blur']['duration_us']:.0f} us | register-marching warps, DP4A rows, 7-row register ring, ping-pong prefetch, no shared memory |
 | pyramid | 112 us (TMA tiles) | {k['kernels']['pyramid']['duration_us']:.0f} us | marching warps, 3 word loads + 2 PRMT + 4 DP2A per source row (51 M vs 61 M warp instructions); TMA tiles kept for calls of < 8 frames (single frame: 32 vs 62 us) |
 | describe | 70 us | {k['kernels']['describe']['duration_us']:.0f} us | unchanged |
 | Hamming top-2, LOP3+POPC (8192 x 40000) | 637 us | {k['kernels']['hamming_top2']['duration_us']:.0f} us | LOP3 carry-save tree: 5 POPC per pair |
-| Hamming top-2, tensor cores (16384 x 40000) | (1 170 us at the POPC kernel's rate) | {k['kernels']['hamming_top2_imma']['duration_us']:.0f} us | descriptors expanded once to 0/1 bytes, int8 IMMA m16n8k32 dot products, cp.async 3-stage tiles, ping-pong accumulators so the top-2 update overlaps the MMAs; IMMA pipe 51 % busy (ncu) |
+| Hamming top-2, mma.sync tensor cores (16384 x 40000) | (1 170 us at the POPC kernel's rate) | {im['duration_us']:.0f} us | descriptors expanded once to 0/1 bytes, int8 IMMA m16n8k32 dot products, cp.async 3-stage tiles, ping-pong accumulators so the top-2 update overlaps the MMAs; IMMA pipe 51 % busy (ncu) |
+| Hamming top-2, **tcgen05 + TMEM** (16384 x 40000) | {im['duration_us']:.0f} us (mma.sync) | {um['duration_us']:.0f} us | `tcgen05.mma kind::i8` M128 N128 K32 with ping-pong TMEM accumulators (all 512 columns), operands expanded in-kernel into the no-swizzle core-matrix layout (one 64-bit multiply per 8 bits), dedicated issuer warp + mbarrier hand-offs, 3-stage train ring, threshold-filtered top-2 epilogue from `tcgen05.ld` |
+| LK flow tracker (1000 points, 3 levels) | 95 us (one warp per point) | {k['kernels']['flow_lk']['duration_us']:.0f} us | 4 warps per point (window rows split), exact integer normal equations, one-barrier block reduction |
 
 Experiments that did NOT pay (kept as switches, documented in DESIGN.md): chaining all pyramid levels inside one launch with
 completion flags (`RUMI_PYRAMID_SPLIT=1`: 127-377 us vs 102 us for 7 launches -- a dependent chain of latency-bound items),
@@ -74,7 +89,9 @@ more than 2 workspaces for resident input (L2 thrash), FAST at 48 / 56 registers
 
 value **{b['value']:.0f} frames/s** (inputs resident), e2e **{b['e2e']['value']:.0f} frames/s** (pinned host buffers, H2D + D2H inside; raw H2D
 {b['e2e']['h2d_GBps_raw']} GB/s would allow {b['e2e']['frames_per_s_at_raw_h2d']:.0f}), single-frame `operator()` latency {b['single_frame_latency']['median_ms']:.3f} ms, matching {b['matching']['pairs_per_s']:.3g} pairs/s
-({b['matching']['kernel']} kernel, {b['matching']['roofline']['frac']:.0%} of the measured {b['matching']['roofline']['bound']} rate; the LOP3+POPC kernel gives 7.4e11), BoW descent {b['bow']['features_per_s']:.3g} features/s (CPU port {b['bow']['cpu_baseline']['value']:.3g} on one
+({b['matching']['kernel']} kernel = tcgen05, {b['matching']['roofline']['achieved']} TOP/s = {b['matching']['roofline']['frac']:.0%} of the nominal 4.5 POP/s int8 rate; mma.sync int8: 1.16e12, LOP3+POPC: 7.4e11),
+cfg 5b 10^6 x 10^6: {b['matching_5b']['pairs_per_s']:.3g} pairs/s ({b['matching_5b']['ms_per_step']:.0f} ms), KFDSample flow step {b['flow']['ms_per_call']:.3f} ms per 640x480 frame / 1000 points
+(cv2 on one host thread: {1e3/b['flow']['cv2_frames_per_s_1_thread']:.1f} ms), BoW descent {b['bow']['features_per_s']:.3g} features/s (CPU port {b['bow']['cpu_baseline']['value']:.3g} on one
 thread), CPU reference arm {b['cpu_baseline']['value']:.0f} frames/s on {b['cpu_baseline']['cores']} host threads ({b['cpu_baseline']['single_thread']:.1f} on one).
 """
 if scal:
@@ -85,8 +102,8 @@ Multi-GPU (one process per GPU, frames sharded, train set sharded + NCCL all-gat
 |---|---|---|---|---|---|
 """ + "\n".join(scal) + big1 + """
 
-`value` scales linearly (no data-path collective); cfg 5b (10^12 pairs) takes 1287 ms on one GPU and 161 ms on eight
-(8.0x: the candidate all-gather is 8 MB per rank).  `e2e` at 8 GPUs is bound by the host links of the box: with 8 ranks
+`value` scales linearly (no data-path collective); cfg 5b (10^12 pairs): see the table (the candidate all-gather is 8 MB
+per rank).  `e2e` at 8 GPUs is bound by the host links of the box: with 8 ranks
 copying at once the raw pinned H2D bandwidth per GPU drops from 55 to 24 GB/s (single NUMA node VM, `nvidia-smi topo`),
 i.e. 307 KB/frame caps each GPU at 78 k frames/s.
 """

@@ -13,7 +13,10 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 H, U = rows[0], rows[1]
 col = {h: i for i, h in enumerate(H)}
-STAGE = [("fast_kernel", "fast"), ("octree_kernel", "octree"), ("blur_kernel", "blur"), ("describe_kernel", "describe"),
+STAGE = [("hamming_top2_umma", "hamming_top2_umma"), ("hamming_top2_imma", "hamming_top2_imma"),
+         ("hamming_top2_segments", "hamming_top2_pairs"), ("expand_bits", "expand_bits"),
+         ("flow_lk", "flow_lk"), ("flow_pyrdown", "flow_pyrdown"), ("flow_scharr", "flow_scharr"),
+         ("fast_kernel", "fast"), ("octree_kernel", "octree"), ("blur_kernel", "blur"), ("describe_kernel", "describe"),
          ("assign_slots", "slots"), ("pyramid", "pyramid"), ("hamming_top2", "hamming_top2"), ("top2_merge", "top2_merge"),
          ("stereo", "stereo")]
 

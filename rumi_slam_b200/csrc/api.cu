@@ -128,6 +128,12 @@ struct rumi_orb {
     bool nwsSet = false;           // RUMI_STREAMS given: use it for every path
     int nwsDefault = 4; bool nwsSetDefault = false;
     int lastWs = 0;
+    // host-batch pipeline: input staging ring + copy streams decoupled from the two compute workspaces
+    static constexpr int kStage = 3;
+    cudaStream_t cpIn = nullptr, cpOut = nullptr;
+    uint8_t* stage[kStage] = {nullptr, nullptr, nullptr}; size_t stageBytes = 0;
+    cudaEvent_t evInReady[kStage] = {}, evInFree[kStage] = {}, evComputeDone[2] = {}, evOutDone[2] = {};
+    bool staged = false;           // RUMI_STAGED=1 (measured slower: 8.40 vs 8.02 ms per 1024 frames, so off by default)
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
     int dbgCell = 0;
@@ -208,6 +214,17 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
         if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
         free_workspace(h->ws[i]);
     }
+    for (int i = 0; i < rumi_orb::kStage; ++i) {
+        cudaFree(h->stage[i]);
+        if (h->evInReady[i]) cudaEventDestroy(h->evInReady[i]);
+        if (h->evInFree[i]) cudaEventDestroy(h->evInFree[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (h->evComputeDone[i]) cudaEventDestroy(h->evComputeDone[i]);
+        if (h->evOutDone[i]) cudaEventDestroy(h->evOutDone[i]);
+    }
+    if (h->cpIn) cudaStreamDestroy(h->cpIn);
+    if (h->cpOut) cudaStreamDestroy(h->cpOut);
     cudaFree(h->coef);
     cudaFree(h->fastCells);
     cudaFree(h->marchTables);
@@ -542,6 +559,8 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     if (sk) h->skipMask = atoi(sk);
     const char* hp = getenv("RUMI_HIPRIO");
     if (hp && hp[0] == '1') h->hiPrio = true;
+    const char* sg = getenv("RUMI_STAGED");
+    if (sg) h->staged = sg[0] != '0';
     const char* ns = getenv("RUMI_STREAMS");
     if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) { h->nws = ns[0] - '0'; h->nwsSet = true; }
     h->nwsDefault = h->nws; h->nwsSetDefault = h->nwsSet;
@@ -606,6 +625,89 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
     if (cap_per_frame < oc.kpCap)
         return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, oc.kpCap);
     const int nchunks = (n + h->chunk - 1) / h->chunk;
+    if (h->staged && !h->profile && !h->nwsSet && nchunks >= 3) {
+        // Staged pipeline (experiment, RUMI_STAGED=1; the default below -- every chunk's H2D / kernels / D2H on its own
+        // workspace stream, 4 workspaces -- measured faster: 127.7 k vs 121.9 k frames/s end to end).
+        // Kernels run best with TWO workspaces in flight (more only thrash L2, see the device path),
+        // but hiding the 307 KB/frame H2D needs the copies to run further ahead.  So the copies get their own streams and
+        // a ring of kStage input buffers: chunk c is uploaded into stage[c % 3] on `cpIn`, extracted on workspace c % 2
+        // reading level 0 straight from the staging buffer, and its results leave on `cpOut`.
+        //   cpIn     : [wait compute(c-3) done] H2D(c)                        -> evInReady[c % 3]
+        //   ws[c % 2]: [wait evInReady, wait D2H(c-2) done] kernels(c)        -> evComputeDone[c % 2] (= evInFree[c % 3])
+        //   cpOut    : [wait evComputeDone] D2H(c)                            -> evOutDone[c % 2]
+        const LevelGeom& g0 = oc.lv[0];
+        const size_t frameBytes = (size_t)g0.stride * g0.h, need = frameBytes * h->chunk + 256;
+        if (!h->cpIn) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->cpIn, cudaStreamNonBlocking));
+            CU_TRY(cudaStreamCreateWithFlags(&h->cpOut, cudaStreamNonBlocking));
+            for (int i = 0; i < rumi_orb::kStage; ++i) {
+                CU_TRY(cudaEventCreateWithFlags(&h->evInReady[i], cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&h->evInFree[i], cudaEventDisableTiming));
+            }
+            for (int i = 0; i < 2; ++i) {
+                CU_TRY(cudaEventCreateWithFlags(&h->evComputeDone[i], cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&h->evOutDone[i], cudaEventDisableTiming));
+            }
+        }
+        if (h->stageBytes < need) {
+            for (int i = 0; i < rumi_orb::kStage; ++i) {
+                cudaFree(h->stage[i]); h->stage[i] = nullptr;
+                CU_TRY(cudaMalloc(&h->stage[i], need));
+                CU_TRY(cudaMemset(h->stage[i], 0, need));      // row padding is read as whole words by the pyramid kernel
+            }
+            CU_TRY(cudaDeviceSynchronize());
+            h->stageBytes = need;
+        }
+        for (int wi = 0; wi < 2; ++wi)
+            if ((rc = ensure_workspace(h, wi))) return rc;
+        for (int c = 0; c < nchunks; ++c) {
+            const int wi = c & 1, slot = c % rumi_orb::kStage;
+            Workspace& ws = h->ws[wi];
+            const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);
+            const uint8_t* src = imgs + (size_t)f0 * frame_pitch;
+            uint8_t* dst = h->stage[slot];
+            if (c >= rumi_orb::kStage) CU_TRY(cudaStreamWaitEvent(h->cpIn, h->evInFree[slot], 0));
+            if ((frame_pitch == stride * (size_t)g0.h || m == 1) && stride == (size_t)g0.stride) {
+                CU_TRY(cudaMemcpyAsync(dst, src, (size_t)m * frameBytes, cudaMemcpyHostToDevice, h->cpIn));
+            } else if (frame_pitch == stride * (size_t)g0.h || m == 1) {
+                CU_TRY(cudaMemcpy2DAsync(dst, g0.stride, src, stride, g0.w, (size_t)m * g0.h, cudaMemcpyHostToDevice, h->cpIn));
+            } else {
+                for (int i = 0; i < m; ++i)
+                    CU_TRY(cudaMemcpy2DAsync(dst + (size_t)i * frameBytes, g0.stride, src + i * frame_pitch, stride, g0.w,
+                                             g0.h, cudaMemcpyHostToDevice, h->cpIn));
+            }
+            CU_TRY(cudaEventRecord(h->evInReady[slot], h->cpIn));
+            CU_TRY(cudaStreamWaitEvent(ws.stream, h->evInReady[slot], 0));
+            if (c >= 2) CU_TRY(cudaStreamWaitEvent(ws.stream, h->evOutDone[wi], 0));     // ws.kps / ws.desc still leaving
+            LevelView l0;
+            l0.ptr = dst; l0.pitch = (long long)frameBytes; l0.stride = g0.stride; l0.w = g0.w; l0.h = g0.h;
+            if ((rc = run_chunk(h, ws, l0, false, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
+            if (c == nchunks - 1)     // keep the parity hooks / pyramid read-back working: level 0 of the last chunk
+                CU_TRY(cudaMemcpyAsync(ws.pyr + h->pyrLevelOff[0], dst, (size_t)m * frameBytes, cudaMemcpyDeviceToDevice, ws.stream));
+            CU_TRY(cudaEventRecord(h->evComputeDone[wi], ws.stream));
+            CU_TRY(cudaEventRecord(h->evInFree[slot], ws.stream));
+            CU_TRY(cudaStreamWaitEvent(h->cpOut, h->evComputeDone[wi], 0));
+            if (cap_per_frame == oc.kpCap) {
+                CU_TRY(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ws.kps, sizeof(rumi_kp) * (size_t)oc.kpCap * m,
+                                       cudaMemcpyDeviceToHost, h->cpOut));
+                CU_TRY(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ws.desc, 32 * (size_t)oc.kpCap * m,
+                                       cudaMemcpyDeviceToHost, h->cpOut));
+            } else {
+                CU_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap_per_frame, sizeof(rumi_kp) * (size_t)cap_per_frame, ws.kps,
+                                         sizeof(rumi_kp) * (size_t)oc.kpCap, sizeof(rumi_kp) * (size_t)oc.kpCap, m,
+                                         cudaMemcpyDeviceToHost, h->cpOut));
+                CU_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap_per_frame * 32, 32 * (size_t)cap_per_frame, ws.desc,
+                                         32 * (size_t)oc.kpCap, 32 * (size_t)oc.kpCap, m, cudaMemcpyDeviceToHost, h->cpOut));
+            }
+            CU_TRY(cudaMemcpyAsync(n_kp + f0, ws.nkp, 4 * (size_t)m, cudaMemcpyDeviceToHost, h->cpOut));
+            CU_TRY(cudaMemcpyAsync(n_mono + f0, ws.nmono, 4 * (size_t)m, cudaMemcpyDeviceToHost, h->cpOut));
+            CU_TRY(cudaEventRecord(h->evOutDone[wi], h->cpOut));
+            h->lastWs = wi;
+        }
+        CU_TRY(cudaStreamSynchronize(h->cpOut));
+        for (int i = 0; i < 2; ++i) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+        return RUMI_OK;
+    }
     for (int c = 0; c < nchunks; ++c) {
         const int wi = c % h->nws;
         if ((rc = ensure_workspace(h, wi))) return rc;

@@ -161,3 +161,24 @@ def test_other_shapes_and_pyramid_parameters(oracle, w, h, nf, levels, scale):
         rk, rd, rm = ref[i]
         assert nkp[i] == len(rk) and nmono[i] == rm
         assert np.array_equal(bk[i, :nkp[i]], rk) and np.array_equal(bd[i, :nkp[i]], rd)
+
+
+def test_staged_host_pipeline_equals_default():
+    """RUMI_STAGED=1 (copy streams + 3 staging buffers + 2 workspaces; an experiment kept as a switch) returns exactly
+    what the default host-batch pipeline returns, on a ragged 5-chunk batch."""
+    import os
+    from rumi_slam_b200 import ORBextractor
+    from rumi_slam_b200.synth import synthetic_batch
+    frames = synthetic_batch(37, 640, 480, seed0=900, unique=6)
+    outs = []
+    for staged in ("0", "1"):
+        os.environ["RUMI_STAGED"] = staged
+        try:
+            ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=8)
+        finally:
+            os.environ.pop("RUMI_STAGED", None)
+        k, d, n, m = ex.extract_batch(frames)
+        outs.append((k.copy(), d.copy(), n.copy(), m.copy()))
+        ex.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)

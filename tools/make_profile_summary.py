@@ -83,7 +83,10 @@ kernel is bound by the epilogue / expansion instruction stream, not by the tenso
 
 Experiments that did NOT pay (kept as switches, documented in DESIGN.md): chaining all pyramid levels inside one launch with
 completion flags (`RUMI_PYRAMID_SPLIT=1`: 127-377 us vs 102 us for 7 launches -- a dependent chain of latency-bound items),
-more than 2 workspaces for resident input (L2 thrash), FAST at 48 / 56 registers (no change), 1 / 4 warps per FAST CTA.
+more than 2 workspaces for resident input (L2 thrash), FAST at 48 / 56 registers (no change), 1 / 4 warps per FAST CTA,
+a staged host pipeline (`RUMI_STAGED=1`: copy streams + 3 input buffers + 2 workspaces: 121.9 k vs 127.7 k frames/s end to
+end for the default 4 workspace streams), and for the tcgen05 matcher: 2 CTAs x 128 queries per SM, 8 instead of 16 worker
+warps, a 2-stage train ring (all within 5 % of each other once the MMA issuer had its own warp).
 
 ## 4. bench.py on B200 (1965 MHz, no throttle reasons)
 

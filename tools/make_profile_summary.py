@@ -18,7 +18,7 @@ fa = k["kernels"]["fast"]
 um = k["kernels"]["hamming_top2_umma"]
 im = k["kernels"]["hamming_top2_imma"]
 scal = []
-for name in ("r1_bench_n2.json", "r1_bench_n8.json"):
+for name in ("r1_bench_n2.json", "r1_bench_n4.json", "r1_bench_n8.json"):
     if os.path.exists(P(name)):
         d = json.load(open(P(name)))
         big = d.get("matching_5b")

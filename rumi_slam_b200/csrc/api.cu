@@ -1030,9 +1030,10 @@ int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int
     if (umma) {
         const int slices = umma_slices(nq, nt);
         if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
-        launch_hamming_top2_umma(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
+        if ((rc = grow((void**)&m->tx, &m->txCap, umma_train_bytes(nt)))) return rc;
+        launch_hamming_top2_umma(dQ, nq, dT, nt, m->tx, tBase, slices, m->partial, m->stream);
         launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
-        m->launches += 2;
+        m->launches += 3;
         m->lastPath = 3;
     } else if (imma) {
         const int slices = imma_slices(nq, nt);

@@ -143,7 +143,8 @@ void launch_expand_bits(const uint8_t* D, int n, uint8_t* X /* [n][256] */, uint
 int imma_slices(int nq, int nt);
 // K8-U (match_umma.cu): tcgen05.mma kind::i8 with TMEM accumulators, operands expanded in-kernel from the packed rows
 int umma_slices(int nq, int nt);
-void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt, int tBase, int slices,
+size_t umma_train_bytes(int nt);        // scratch for the train set as ready-to-load operand tiles
+void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt, uint8_t* trainTiles, int tBase, int slices,
                               uint64_t* partial, cudaStream_t s);
 void launch_hamming_top2_imma(const uint8_t* Q, const uint8_t* Qx, int nq, const uint8_t* Tx, const uint16_t* popT,
                               int nt, int tBase, int slices, uint64_t* partial, cudaStream_t s);

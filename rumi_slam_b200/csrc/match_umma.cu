@@ -32,7 +32,9 @@ namespace {
 
 constexpr int kUmBM = 256, kUmBN = 128;            // queries per CTA (two M = 128 MMAs share every train tile), train rows per tile
 constexpr int kUmWorkers = 2 * kUmBM;              // 16 worker warps: (query half) x (TMEM lane quarter) x (column half of the tile)
-constexpr int kUmThreads = kUmWorkers + 32;        // + one warp whose only job is to issue the MMAs
+constexpr int kUmThreads = kUmWorkers + 64;        // + one warp that issues the MMAs + one warp that issues the bulk copies
+constexpr int kUmStages = 4;                       // train-tile ring
+constexpr int kUmStageBytes = 128 * 256 + 128 * 4; // expanded tile (32 KB) + its 128 key constants: one bulk copy
 constexpr int kUmIdxBits = 22;
 constexpr uint32_t kUmIdxMask = (1u << kUmIdxBits) - 1u;
 constexpr int kUmTileBytes = 128 * 256;            // one expanded 128-row operand tile: 32 KB
@@ -41,16 +43,15 @@ constexpr int kUmTmemCols = 512;                   // (ping, pong) x (query half
 
 struct UmmaSmem {
     alignas(1024) uint8_t A[2][kUmTileBytes];      // query rows 0-127, 128-255 of this CTA
-    alignas(1024) uint8_t B[3][kUmTileBytes];      // three train stages: tile i+2 is expanded before tile i is consumed
-    uint32_t cst[8][kUmBN];                        // per train row of a tile: ((pop + 256) << 22) | index
+    alignas(1024) uint8_t B[kUmStages][kUmStageBytes];   // ring of pre-expanded train tiles, filled by cp.async.bulk
     uint32_t mergeK[2][kUmBM];                     // (k1, k2) of the threads that scanned columns 64-127 of every tile
-    alignas(8) uint64_t bar[2];                    // MMAs of tile i complete: accumulator set i & 1 full, B[i % 3] free
-    alignas(8) uint64_t full[3];                   // B[s] expanded by all worker warps
+    alignas(8) uint64_t bar[2];                    // MMAs of tile i complete: accumulator set i & 1 full
+    alignas(8) uint64_t full[kUmStages];           // stage landed (cp.async.bulk complete_tx)
+    alignas(8) uint64_t slotFree[kUmStages];       // stage consumed: its MMAs are done and every worker warp has used its constants
     alignas(8) uint64_t accFree[2];                // accumulator set drained by all worker warps
     uint32_t tmemBase;
 };
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // no-swizzle K-major shared-memory matrix descriptor (start address, LBO, SBO in 16-byte units; version 1 = sm_100)
@@ -129,12 +130,23 @@ __device__ __forceinline__ int expand_row(const PackedRow& p, uint8_t* tile, int
     return pop;
 }
 
+// Pre-pass (once per call): the train set as ready-to-load tiles -- per 128 rows 32 KB in the shared-memory operand
+// layout followed by the 128 key constants ((pop + 256) << 22 | row), 0xFFFFFFFF for the padding rows.
+__global__ void __launch_bounds__(128)
+umma_pack_train_kernel(const uint8_t* __restrict__ T, int nt, uint8_t* __restrict__ tiles) {
+    const int tile = blockIdx.x, r = threadIdx.x, row = tile * kUmBN + r;
+    uint8_t* dst = tiles + (size_t)tile * kUmStageBytes;
+    const PackedRow p = load_packed(T, nt, row);
+    const int pop = expand_row<8, false>(p, dst, r, 0);
+    reinterpret_cast<uint32_t*>(dst + kUmTileBytes)[r] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
+}
+
 __global__ void __launch_bounds__(kUmThreads, 1)
-hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ T, int nt, int tilesPerSlice,
+hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ tiles, int nt, int tilesPerSlice,
                          int tBase, uint64_t* __restrict__ partial /* [gridDim.y][nq] */) {
     extern __shared__ __align__(1024) uint8_t smemRaw[];
     UmmaSmem& sm = *reinterpret_cast<UmmaSmem*>(smemRaw);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r128 = tid & 127, quarter = (tid >> 7) & 3;               // row inside a 128-row tile / quarter of the work
     const int half = quarter & 1, colHalf = quarter >> 1;               // epilogue: query half, columns [64 * colHalf, +64)
     const int qrowLocal = half * 128 + r128;                            // query row of this thread inside the CTA
@@ -153,35 +165,57 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[b])) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.accFree[b])), "r"(kUmWorkers / 32) : "memory");
         }
-        for (int b = 0; b < 3; ++b)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.full[b])), "r"(kUmWorkers / 32) : "memory");
+        for (int b = 0; b < kUmStages; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.full[b])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.slotFree[b])), "r"(kUmWorkers / 32) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // the query block is expanded once per CTA by the worker threads (quarter-rows), straight into the operand layout
+    int popq = 0;
+    if (tid < kUmWorkers) {
+        const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
+        popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                               // TMEM base + barriers visible to every role
+    __syncthreads();                               // TMEM base, barriers and the query operand visible to every role
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmemBase;
     const uint32_t bar0 = smem_u32(&sm.bar[0]), bar1 = smem_u32(&sm.bar[1]);
-    const uint32_t fullBase = smem_u32(&sm.full[0]);
+    const uint32_t fullBase = smem_u32(&sm.full[0]), slotBase = smem_u32(&sm.slotFree[0]);
     const uint32_t free0 = smem_u32(&sm.accFree[0]), free1 = smem_u32(&sm.accFree[1]);
+    const uint32_t bBase0 = smem_u32(sm.B[0]);
     uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-    int popq = 0;
 
-    if (warp == kUmWorkers / 32) {
+    if (warp == kUmWorkers / 32 + 1) {
+        // =========================== loader: one thread feeds the train-tile ring with bulk copies ===========================
+        if (lane == 0) {
+            const uint8_t* src = tiles + (size_t)tile0 * kUmStageBytes;
+            for (int i = 0; i < ntiles; ++i) {
+                const uint32_t s = (uint32_t)i & (kUmStages - 1);
+                if (i >= kUmStages) mbar_wait(slotBase + 8u * s, (uint32_t)((i / kUmStages) - 1) & 1u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             :: "r"(fullBase + 8u * s), "r"((uint32_t)kUmStageBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(bBase0 + s * kUmStageBytes), "l"(src + (size_t)i * kUmStageBytes), "r"((uint32_t)kUmStageBytes),
+                                "r"(fullBase + 8u * s) : "memory");
+            }
+        }
+    } else if (warp == kUmWorkers / 32) {
         // =========================== MMA issuer: one thread, never touches data ===========================
         // tcgen05.mma blocks its issuing thread while the tensor pipe's queue is full (measured: ~1800 clk per tile when
         // the issuer was also an epilogue thread -- the whole CTA then waited for it at the next barrier), so the
-        // issuer is a warp of its own and talks to the workers through mbarriers only.
-        if (lane_id() == 0) {
+        // issuer is a warp of its own and talks to the other roles through mbarriers only.
+        if (lane == 0) {
             const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
-            const uint32_t bBase0 = smem_u32(sm.B[0]);
-            for (int i = 0, s3 = 0, ph3 = 0; i < ntiles; ++i) {
-                mbar_wait(fullBase + 8u * s3, (uint32_t)ph3);                             // B[i % 3] (and A) expanded
+            for (int i = 0; i < ntiles; ++i) {
+                const uint32_t s = (uint32_t)i & (kUmStages - 1);
+                mbar_wait(fullBase + 8u * s, (uint32_t)(i / kUmStages) & 1u);                    // stage landed
                 if (i >= 2) mbar_wait((i & 1) ? free1 : free0, (uint32_t)((i >> 1) - 1) & 1u);   // accumulators drained
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t bBase = bBase0 + (uint32_t)s3 * kUmTileBytes;
+                const uint32_t bBase = bBase0 + s * kUmStageBytes;
                 const uint32_t d = tmem + (uint32_t)(i & 1) * 256u;
-                if (++s3 == 3) { s3 = 0; ph3 ^= 1; }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
@@ -193,31 +227,9 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             }
         }
     } else {
-        // =========================== workers: expand train tiles, run the top-2 epilogue ===========================
-        const int lane = tid & 31;
-        // train tile: thread (r128, quarter) expands words 2 * quarter, 2 * quarter + 1 of train row r128.  The packed row of
-        // the tile after the one being expanded is already in flight (`nextRow`): its L2 latency hides behind the epilogue.
-        PackedRow nextRow;
-        auto fetch_train = [&](int i) { nextRow = load_packed(T, i < ntiles ? nt : 0, (tile0 + i) * kUmBN + r128); };
-        auto expand_train = [&](int i) {           // ... then tells the issuer: one arrival per warp
-            const int row = (tile0 + i) * kUmBN + r128;
-            uint8_t* dst = sm.B[i % 3];
-            const int pop = quarter == 0 ? expand_row<2, false>(nextRow, dst, r128, 0) : quarter == 1 ? expand_row<2, false>(nextRow, dst, r128, 2)
-                          : quarter == 2 ? expand_row<2, false>(nextRow, dst, r128, 4) : expand_row<2, false>(nextRow, dst, r128, 6);
-            if (quarter == 0)
-                sm.cst[i & 7][r128] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(fullBase + 8u * (uint32_t)(i % 3));
-        };
-        fetch_train(0);
-        const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
-        popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
-        if (ntiles > 0) { expand_train(0); fetch_train(1); }
-        if (ntiles > 1) { expand_train(1); fetch_train(2); }
-
+        // =========================== workers: the top-2 epilogue ===========================
         const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1 - 7));      // acc = 128 <q,t>: acc * negTwo = -2 <q,t> in the distance field
-        // 8 keys at a time: one min tree, and the exact update only when the group holds a key below the current
+        // 8 keys at a time: one min chain, and the exact update only when the group holds a key below the current
         // second best (rare after the first tiles)
         auto update8 = [&](const uint32_t* v, const uint32_t* cst) {
             const uint4 ca = *reinterpret_cast<const uint4*>(cst);      // broadcast
@@ -249,16 +261,14 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         : "r"(addr) : "memory")
 
         for (int i = 0; i < ntiles; ++i) {
-            if (i + 2 < ntiles) {                  // expand tile i+2 (its B slot was freed by MMA i-1, waited for in the
-                expand_train(i + 2);               // previous iteration) BEFORE consuming tile i: the issuer always has
-                fetch_train(i + 3);                // the next operands ready; fetch the packed rows of the tile after it
-            }
+            const uint32_t s = (uint32_t)i & (kUmStages - 1);
             mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);   // accumulator set i & 1 complete
+            mbar_wait(fullBase + 8u * s, (uint32_t)(i / kUmStages) & 1u);  // (long complete: acquires the bulk copy's writes)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
             //      accumulator) x 64 of the 128 columns (train rows of the tile); the second 32 columns load while the
             //      first are used
-            const uint32_t* cst = sm.cst[i & 7] + 64 * colHalf;
+            const uint32_t* cst = reinterpret_cast<const uint32_t*>(sm.B[s] + kUmTileBytes) + 64 * colHalf;
             const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + (uint32_t)colHalf * 64u +
                                    ((uint32_t)((warp & 3) * 32) << 16);
             uint32_t va[32], vb[32];
@@ -273,6 +283,8 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             if (lane == 0) mbar_arrive((i & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
 #pragma unroll
             for (int j = 0; j < 32; j += 8) update8(vb + j, cst + 32 + j);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(slotBase + 8u * s);               // the loader may refill this stage
         }
 #undef RUMI_LDTM32
         // the two threads of a query row scanned disjoint train rows (unique keys): park one half for the exact merge
@@ -284,7 +296,6 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kUmTmemCols) : "memory");
     }
-    __syncthreads();
     const int qi = q0 + qrowLocal;
     if (tid < kUmBM) {                             // colHalf == 0 workers: min / max merge with the parked half
         const uint32_t o1 = sm.mergeK[0][qrowLocal], o2 = sm.mergeK[1][qrowLocal];
@@ -314,7 +325,9 @@ int umma_slices(int nq, int nt) {
     return std::max(want, 1);
 }
 
-void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt, int tBase, int slices,
+size_t umma_train_bytes(int nt) { return (size_t)((nt + kUmBN - 1) / kUmBN) * kUmStageBytes; }
+
+void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt, uint8_t* trainTiles, int tBase, int slices,
                               uint64_t* partial, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
@@ -322,9 +335,10 @@ void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt
         configured = true;
     }
     const int nTiles = (nt + kUmBN - 1) / kUmBN;
+    umma_pack_train_kernel<<<nTiles, 128, 0, s>>>(T, nt, trainTiles);
     const int tilesPerSlice = (nTiles + slices - 1) / slices;
     dim3 grid((nq + kUmBM - 1) / kUmBM, slices);
-    hamming_top2_umma_kernel<<<grid, kUmThreads, sizeof(UmmaSmem) + 1024, s>>>(Q, nq, T, nt, tilesPerSlice, tBase, partial);
+    hamming_top2_umma_kernel<<<grid, kUmThreads, sizeof(UmmaSmem) + 1024, s>>>(Q, nq, trainTiles, nt, tilesPerSlice, tBase, partial);
 }
 
 }  // namespace rumi

@@ -239,9 +239,10 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             key[2] = umad(v[2], negTwo, ca.z); key[3] = umad(v[3], negTwo, ca.w);
             key[4] = umad(v[4], negTwo, cb.x); key[5] = umad(v[5], negTwo, cb.y);
             key[6] = umad(v[6], negTwo, cb.z); key[7] = umad(v[7], negTwo, cb.w);
-            // a chain, so that ptxas pairs the steps into 3-input VIMNMX3
-            const uint32_t m = min(min(min(min(min(min(min(key[0], key[1]), key[2]), key[3]), key[4]), key[5]), key[6]), key[7]);
-            if (m < k2) {
+            // depth-2 tree of 3-input minima (VIMNMX3): the branch below is on the critical path of the warp
+            const uint32_t t0 = min(min(key[0], key[1]), key[2]), t1 = min(min(key[3], key[4]), key[5]), t2 = min(key[6], key[7]);
+            const uint32_t m = min(min(t0, t1), t2);
+            if (__any_sync(0xFFFFFFFFu, m < k2)) {             // warp-uniform: no divergence bookkeeping; the update is idempotent
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     k2 = min(k2, max(key[e], k1));

@@ -7,20 +7,21 @@
 //   * one CTA per SM owns 256 queries: two tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 128, K = 32) per K step share
 //     every 128-row train tile; the 2 x (128 x 128) int32 accumulators live in TMEM, ping-pong over two sets = all 512
 //     columns, and never touch registers until the top-2 epilogue reads them with tcgen05.ld;
-//   * operands are expanded from the packed 32-byte descriptors INSIDE the kernel, straight into the canonical
-//     no-swizzle K-major shared-memory layout ([16-byte K chunk][row][16 B]: core matrices of 8 rows x 16 B, SBO = 128 B,
-//     LBO = 2048 B) -- no expanded copy in HBM / L2 (the mma.sync kernel streams 256 B per descriptor from L2, this one
-//     32 B).  8 bits become 8 operand bytes with ONE 64-bit multiply (see expand_row);
-//   * warp roles: 16 worker warps (expand train tiles two tiles ahead into a 3-stage ring, run the epilogue) and ONE
-//     issuer warp whose single thread issues the MMAs -- tcgen05.mma blocks its issuing thread while the tensor queue
-//     is full, so it must not be a thread anybody else waits for.  Roles meet only at mbarriers: full[3] (tile
-//     expanded, 16 warp arrivals), bar[2] (tcgen05.commit: accumulator set ready and train stage free), accFree[2]
-//     (accumulator set drained).
+//   * the train set is packed ONCE per call (umma_pack_train_kernel) into ready-to-load operand tiles: per 128 rows 32 KB
+//     in the canonical no-swizzle K-major shared-memory layout ([16-byte K chunk][row][16 B]: core matrices of 8 rows x
+//     16 B, SBO = 128 B, LBO = 2048 B) followed by the tile's 128 key constants.  8 bits become 8 operand bytes with ONE
+//     64-bit multiply (see expand_row).  The query block is expanded the same way inside the kernel, once per CTA;
+//   * warp roles: a LOADER warp (one thread streams the tiles into a 4-stage ring with cp.async.bulk + mbarrier
+//     complete_tx), an ISSUER warp (one thread issues the MMAs -- tcgen05.mma blocks its issuing thread while the tensor
+//     queue is full, so it must not be a thread anybody else waits for) and 16 EPILOGUE warps.  Roles meet only at
+//     mbarriers: full[4] (stage landed), bar[2] (tcgen05.commit: accumulator set ready), accFree[2] (accumulator set
+//     drained), slotFree[4] (stage consumed).
 // Key per pair = ((pop(t) - 2 <q,t> + 256) << 22 | train index) built by one IMAD from the accumulator; 8 keys go
-// through a min chain and the exact update k2 = min(k2, max(key, k1)), k1 = min(k1, key) runs only when the group
+// through a min tree and the exact update k2 = min(k2, max(key, k1)), k1 = min(k1, key) runs only when the group
 // holds a key below the current second best; pop(q) is added at the end (it does not change the order).  A query row
 // is scanned by two threads (column halves of every tile); keys are unique, so their merge is an exact min / max.
-// Measured on B200 (40000 x 40000): 3.4e12 pairs/s vs 1.16e12 for the mma.sync kernel and 7.4e11 for LOP3+POPC.
+// Measured on B200: 4.2e12 pairs/s (40000 x 40000), 5.7e12 (10^6 x 10^6) vs 1.16e12 for the mma.sync kernel and 7.4e11
+// for LOP3+POPC; tensor pipe 54 % busy (ncu), the rest is the latency of the top-2 epilogue.
 #include "kernels.cuh"
 
 #include <algorithm>

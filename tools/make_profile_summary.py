@@ -59,13 +59,16 @@ instructions go (`tools/sass_phases.py` on the source page of the 270-us version
 append 10 %, NMS + emission 15 %, staging / set-up 11 %; the later changes (second compaction + warp bitonic sort for the
 emission, ini / min thresholds as two passes per cell, one ballot per byte plane) removed 67 M of the 190 M warp instructions.
 
-The tcgen05 top-2 kernel (`hamming_top2_umma`, K8-U): {um['duration_us']:.0f} us for 16384 x 40000 pairs under ncu = {16384*40000/um['duration_us']/1e6:.2f}e12 pairs/s;
-{um['warp_instructions']/1e6:.0f} M warp instructions against {im['warp_instructions']/1e6:.0f} M for the mma.sync kernel and {k['kernels']['hamming_top2']['warp_instructions']*2/1e6:.0f} M (scaled to the same size) for
-LOP3+POPC: the MMAs are 32 `UTCIMMA` per tile issued by ONE thread, what is left on the CUDA cores is the bit expansion and the
-top-2 epilogue (issue {um['issue_active_pct']:.0f} %, ALU pipe {um['alu_pipe_pct']:.0f} %).  Tensor pipe ({{sm__pipe_tensor_cycles_active}} of an earlier capture of the same
-kernel at 2.7e12 pairs/s, `r1_ncu_umma_v3_excerpt.txt`): 33 % busy, `sm__ops_path_tensor_op_utcimma_src_int8` 30 % of peak -- the
-kernel is bound by the epilogue / expansion instruction stream, not by the tensor cores.  Phase clocks taken inside the kernel
-(clock64 per role): issuer blocked in `tcgen05.mma` 1 440 clk per tile, workers 830 clk expansion + 1 400 clk epilogue per tile.
+The tcgen05 top-2 kernel (`hamming_top2_umma`, K8-U; re-captured alone on 40000 x 40000 after its last revision): {um['duration_us']:.0f} us under
+ncu = {40000*40000/um['duration_us']/1e6:.2f}e12 pairs/s; {um['warp_instructions']/1e6:.0f} M warp instructions = {um['warp_instructions']*32/1.6e9:.1f} thread instructions per pair (mma.sync kernel: {im['warp_instructions']*32/(16384*40000):.1f}, LOP3+POPC:
+{k['kernels']['hamming_top2']['warp_instructions']*32/(8192*40000):.1f}): the MMAs are 16 `UTCIMMA` per tile issued by ONE thread, the train tiles arrive by `cp.async.bulk` (`UBLKCP`), what is left
+on the CUDA cores is the top-2 epilogue (issue {um['issue_active_pct']:.0f} %, ALU pipe {um['alu_pipe_pct']:.0f} %).  **Tensor pipe: `sm__pipe_tensor_cycles_active` 54 % of
+peak sustained active** (49 % elapsed; `r1_ncu_umma_final_keys.txt`); an earlier revision at 2.7e12 pairs/s read 33 % / `utcimma_src_int8`
+30 % of peak (`r1_ncu_umma_v3_excerpt.txt`), which fixes the 100 % mark at 8.8e12 pairs/s = the nominal 4.5 POP/s.  Phase clocks
+taken inside the kernel (clock64 per role, 53-tile slices): the epilogue of one 64-column half tile takes a worker warp ~1 550 clk
+(190 clk per group of 8 keys: min tree, vote, rare exact update), the loader waits 1 700 clk per tile for a free stage and the
+issuer sits in `tcgen05.mma` (queue full) 1 440 clk per tile -- the kernel is bound by the epilogue's instruction latency,
+with the tensor pipe half busy.
 
 ## 3. What changed during the round (per 64-frame chunk, ncu durations)
 
@@ -78,7 +81,7 @@ kernel is bound by the epilogue / expansion instruction stream, not by the tenso
 | describe | 70 us | {k['kernels']['describe']['duration_us']:.0f} us | unchanged |
 | Hamming top-2, LOP3+POPC (8192 x 40000) | 637 us | {k['kernels']['hamming_top2']['duration_us']:.0f} us | LOP3 carry-save tree: 5 POPC per pair |
 | Hamming top-2, mma.sync tensor cores (16384 x 40000) | (1 170 us at the POPC kernel's rate) | {im['duration_us']:.0f} us | descriptors expanded once to 0/1 bytes, int8 IMMA m16n8k32 dot products, cp.async 3-stage tiles, ping-pong accumulators so the top-2 update overlaps the MMAs; IMMA pipe 51 % busy (ncu) |
-| Hamming top-2, **tcgen05 + TMEM** (16384 x 40000) | {im['duration_us']:.0f} us (mma.sync) | {um['duration_us']:.0f} us | `tcgen05.mma kind::i8` M128 N128 K32 with ping-pong TMEM accumulators (all 512 columns), operands expanded in-kernel into the no-swizzle core-matrix layout (one 64-bit multiply per 8 bits), dedicated issuer warp + mbarrier hand-offs, 3-stage train ring, threshold-filtered top-2 epilogue from `tcgen05.ld` |
+| Hamming top-2, **tcgen05 + TMEM** (40000 x 40000) | 1 380 us (mma.sync) | {um['duration_us']:.0f} us | `tcgen05.mma kind::i8` M128 N128 K32 with ping-pong TMEM accumulators (all 512 columns), train set packed once per call into ready-to-load no-swizzle operand tiles (one 64-bit multiply per 8 bits), loader warp (`cp.async.bulk`, 4-stage ring) + issuer warp + 16 epilogue warps meeting only at mbarriers, threshold-filtered top-2 epilogue from `tcgen05.ld` |
 | LK flow tracker (1000 points, 3 levels) | 95 us (one warp per point) | {k['kernels']['flow_lk']['duration_us']:.0f} us | 4 warps per point (window rows split), exact integer normal equations, one-barrier block reduction |
 
 Experiments that did NOT pay (kept as switches, documented in DESIGN.md): chaining all pyramid levels inside one launch with
@@ -99,7 +102,8 @@ thread), CPU reference arm {b['cpu_baseline']['value']:.0f} frames/s on {b['cpu_
 """
 if scal:
     md += """
-Multi-GPU (one process per GPU, frames sharded, train set sharded + NCCL all-gather of 8 B/query candidates):
+Multi-GPU (one process per GPU, frames sharded, train set sharded + NCCL all-gather of 8 B/query candidates; the 2 / 4 / 8-GPU
+rows were taken one kernel revision earlier -- 3.4e12 instead of 4.2e12 pairs/s per GPU on cfg 5a, 4.4e12 instead of 5.7e12 on cfg 5b):
 
 | GPUs | value frames/s | e2e frames/s | matching 40k x 40k pairs/s | matching 10^6 x 10^6 pairs/s | raw H2D GB/s per GPU |
 |---|---|---|---|---|---|

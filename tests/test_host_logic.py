@@ -157,3 +157,25 @@ def test_scalar_math(hh, oracle):
         hh.hh_sincos(float(a), C.byref(s), C.byref(c))
         rc, rs = oracle.sincos(a)
         assert (s.value, c.value) == (rs, rc)
+
+
+def test_umma_bit_expansion_identity():
+    """The arithmetic identity behind the tcgen05 matcher's operand expansion (rumi_slam_b200/csrc/match_umma.cu,
+    expand_row): x * 0x8040201008040201 places bit i of the byte x at positions i + 9 j (all distinct: no carries), so
+    masking with 0x80..80 leaves byte j = 0x80 iff bit 7 - j of x is set -- a fixed permutation of the 8 bits, applied to
+    queries and train rows alike, which a dot product does not see."""
+    C = 0x8040201008040201
+    M = 0x8080808080808080
+    for x in range(256):
+        p = (x * C) & 0xFFFFFFFFFFFFFFFF & M
+        for j in range(8):
+            assert ((p >> (8 * j)) & 0xFF) == (0x80 if (x >> (7 - j)) & 1 else 0)
+    # dot product of two expanded rows (queries 0/1, train 0/0x80) = 128 * popcount(a & b); Hamming from it
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+    ea = np.array([[(int(x) * C & M) >> (8 * j) & 0xFF for j in range(8)] for x in a]).ravel() >> 7
+    eb = np.array([[(int(x) * C & M) >> (8 * j) & 0xFF for j in range(8)] for x in b]).ravel()
+    acc = int((ea * eb).sum())
+    pop = lambda v: int(np.unpackbits(v).sum())
+    assert acc == 128 * pop(a & b)
+    assert pop(a) + pop(b) - 2 * (acc >> 7) == pop(a ^ b)

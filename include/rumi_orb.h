@@ -133,8 +133,9 @@ int rumi_hamming_top2_pairs(rumi_match* m, const uint8_t* Q, int nq, const uint8
                             int nseg, int32_t* idx1, uint16_t* d1, uint16_t* d2);
 int rumi_match_timer_start(rumi_match* m);
 int rumi_match_timer_stop(rumi_match* m, float* ms);
-/* Which top-2 kernel the last rumi_hamming_top2* call used: 1 = LOP3+POPC (small problems), 2 = int8 tensor-core
- * kernel on 0/1-expanded descriptors (>= 64 Mi pairs and >= 256 queries; RUMI_MATCH=popc|imma forces one). */
+/* Which top-2 kernel the last rumi_hamming_top2* call used: 1 = LOP3+POPC (small problems), 3 = tcgen05 / TMEM int8
+ * kernel (>= 64 Mi pairs and >= 256 queries), 2 = the older mma.sync int8 kernel (only with RUMI_MATCH=imma).
+ * RUMI_MATCH=popc|imma|umma forces one kernel; the results are identical. */
 int rumi_match_last_path(const rumi_match* m);
 long long rumi_match_launch_count(rumi_match* m, int reset);
 

@@ -331,11 +331,8 @@ size_t umma_train_bytes(int nt) { return (size_t)((nt + kUmBN - 1) / kUmBN) * kU
 
 void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt, uint8_t* trainTiles, int tBase, int slices,
                               uint64_t* partial, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(hamming_top2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaSmem) + 1024);
-        configured = true;
-    }
+    // (per device and cheap: set on every launch rather than cached in a process-wide flag)
+    cudaFuncSetAttribute(hamming_top2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaSmem) + 1024);
     const int nTiles = (nt + kUmBN - 1) / kUmBN;
     umma_pack_train_kernel<<<nTiles, 128, 0, s>>>(T, nt, trainTiles);
     const int tilesPerSlice = (nTiles + slices - 1) / slices;

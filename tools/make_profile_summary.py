@@ -40,6 +40,8 @@ LOP3+POPC kernel, 16384 x 40000 on the mma.sync int8 kernel and on the tcgen05 k
 ## 1. Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none --csv`, `r1_launches_final.csv`)
 
 {tab}
+The same pass over `bench.py --steps 2 --warmup 3 --no-cpu --no-bow --no-flow` itself (`r1_launches_bench.csv`, first 600 launches = 50
+chunks): FAST 0.316, quad-tree 0.200, pyramid 0.195, blur 0.141, describe 0.133, slots 0.014 of the extraction kernels.
 Shares agree with bench.py's own exclusive stage pass (CUDA events, one stream, `r1_bench_final.json`): pyramid {st['pyramid']['share']:.3f},
 FAST {st['fast']['share']:.3f}, quad-tree {st['octree']['share']:.3f}, slots {st['slots']['share']:.3f}, blur {st['blur']['share']:.3f}, describe {st['describe']['share']:.3f} of the extraction step.
 

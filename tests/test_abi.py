@@ -37,6 +37,12 @@ def test_no_gpu_means_error_not_fallback():
     assert e.value.code == -4 and "no CPU fallback" in str(e.value)
     with pytest.raises(RumiError):
         ORBmatcher()
+    from rumi_slam_b200 import SparsePyrLK, KFDSample
+    with pytest.raises(RumiError) as e:
+        SparsePyrLK()
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    with pytest.raises(RumiError):
+        KFDSample()
 
 
 def test_product_never_imports_the_oracle():
@@ -46,7 +52,7 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
-                assert "orb_oracle" not in src and "liborb_ref" not in src, f
+                assert "orb_oracle" not in src and "liborb_ref" not in src and "flow_oracle" not in src, f
 
 
 def test_descriptor_distance_host_inline(oracle):

@@ -73,6 +73,16 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
                                   size_t frame_pitch, int lap0, int lap1, rumi_kp* d_kps, uint8_t* d_desc,
                                   int cap_per_frame, int* d_n_kp, int* d_n_mono, int sync);
 
+/* Stream ordering for the device-resident entry points.  The library launches on PRIVATE non-blocking streams, which
+ * no caller stream is ordered against implicitly.  `stream` is the caller's cudaStream_t (NULL = legacy default stream):
+ *   wait_stream    work the library enqueues after this call starts only after everything enqueued on `stream` so far
+ *                  (the caller produced the inputs / zero-filled the outputs there);
+ *   signal_stream  work the caller enqueues on `stream` after this call starts only after everything the library has
+ *                  enqueued so far (the caller consumes the results there).
+ * Neither call blocks the host.  (The same pair exists for rumi_match and rumi_vocab below.) */
+int rumi_orb_wait_stream(rumi_orb* h, void* stream);
+int rumi_orb_signal_stream(rumi_orb* h, void* stream);
+
 /* ORBextractor::CloudFrameComputeDescriptors(image, keypoints, descriptors)   R/lib_src/ORBextractor.cc:989-1011
  * HOST pointers.  Returns n (like the reference) or an error code. */
 int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,
@@ -134,8 +144,8 @@ int rumi_hamming_top2_pairs(rumi_match* m, const uint8_t* Q, int nq, const uint8
 int rumi_match_timer_start(rumi_match* m);
 int rumi_match_timer_stop(rumi_match* m, float* ms);
 /* Which top-2 kernel the last rumi_hamming_top2* call used: 1 = LOP3+POPC (small problems), 3 = tcgen05 / TMEM int8
- * kernel (>= 64 Mi pairs and >= 256 queries), 2 = the older mma.sync int8 kernel (only with RUMI_MATCH=imma).
- * RUMI_MATCH=popc|imma|umma forces one kernel; the results are identical. */
+ * kernel (>= 64 Mi pairs and >= 256 queries).
+ * RUMI_MATCH=popc|umma forces one kernel; the results are identical. */
 int rumi_match_last_path(const rumi_match* m);
 long long rumi_match_launch_count(rumi_match* m, int reset);
 
@@ -145,6 +155,27 @@ int rumi_top2_pack_device(rumi_match* m, const int32_t* d_idx1, const uint16_t* 
                           uint64_t* d_packed, int sync);
 int rumi_top2_merge_device(rumi_match* m, const uint64_t* d_packed, int nshards, int nq, int32_t* d_idx1,
                            uint16_t* d_d1, uint16_t* d_d2, int sync);
+
+int rumi_match_wait_stream(rumi_match* m, void* stream);
+int rumi_match_signal_stream(rumi_match* m, void* stream);
+
+/* ---- multi-GPU all-pairs matching (BASELINE config 5): one process per GPU ----
+ * The train set is sharded into contiguous index ranges; every rank scans ALL queries against its shard (global train
+ * indices = t_base + local row), the per-rank {d1,d2,idx} candidates (8 B per query) are exchanged with ONE
+ * ncclAllGather and folded in rank order with the reference's strict '<' rule -- bit-identical to the single-GPU scan
+ * because every index of rank r precedes every index of rank r+1.  Everything (scan, exchange, fold) is enqueued on
+ * the matcher's stream; nothing synchronises the host unless `sync` != 0.  Every rank receives the full result.
+ *
+ * Communicator: rank 0 calls rumi_nccl_unique_id and hands the 128 bytes (== ncclUniqueId) to the other ranks by the
+ * host application's own means (MPI, torch.distributed, a socket, a file); every rank then calls
+ * rumi_match_comm_init (collective: ncclCommInitRank).  A host that already owns an ncclComm_t for these ranks passes
+ * it with rumi_match_comm_adopt instead (not destroyed by the library).  NCCL is resolved at run time
+ * (dlopen libnccl.so.2): single-GPU users need no NCCL. */
+int rumi_nccl_unique_id(uint8_t* id128);
+int rumi_match_comm_init(rumi_match* m, const uint8_t* id128, int rank, int nranks);
+int rumi_match_comm_adopt(rumi_match* m, void* nccl_comm, int rank, int nranks);
+int rumi_hamming_top2_sharded(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT_local, int nt_local,
+                              int t_base, int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync);
 
 /* Stereo row-band best-1 search of Frame::ComputeStereoMatches (R/lib_src/Frame.cc:828-905): for every left
  * keypoint the right keypoint with the smallest Hamming distance among those whose row band [y-2s, y+2s] covers the
@@ -174,6 +205,8 @@ int rumi_vocab_create(rumi_vocab** out, int device, int k, int L, int nnodes, co
                       const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
 void rumi_vocab_destroy(rumi_vocab* v);
 int rumi_vocab_words(const rumi_vocab* v);
+int rumi_vocab_wait_stream(rumi_vocab* v, void* stream);
+int rumi_vocab_signal_stream(rumi_vocab* v, void* stream);
 /* Per-feature tree descent == TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup) (:1218-1258):
  * word id and weight of the leaf reached, node id at depth L - levelsup (0 = root when that depth is <= 0).  Host
  * buffers; the BowVector / FeatureVector maps of Frame::ComputeBoW are assembled from these by the caller. */

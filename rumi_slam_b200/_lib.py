@@ -33,6 +33,16 @@ SIGNATURES = {
                                          C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     "rumi_orb_extract_batch_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                                                 C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "rumi_orb_wait_stream": (C.c_int, [_vp, _vp]),
+    "rumi_orb_signal_stream": (C.c_int, [_vp, _vp]),
+    "rumi_match_wait_stream": (C.c_int, [_vp, _vp]),
+    "rumi_match_signal_stream": (C.c_int, [_vp, _vp]),
+    "rumi_vocab_wait_stream": (C.c_int, [_vp, _vp]),
+    "rumi_vocab_signal_stream": (C.c_int, [_vp, _vp]),
+    "rumi_nccl_unique_id": (C.c_int, [_vp]),
+    "rumi_match_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "rumi_match_comm_adopt": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "rumi_hamming_top2_sharded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "rumi_orb_describe": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, C.c_int, _vp]),
     "rumi_orb_pyramid_level": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _i32p, _i32p]),
     "rumi_orb_blurred_level": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _i32p, _i32p]),
@@ -99,9 +109,9 @@ def lib():
     """Loads (building first if needed) librumi_orb.so.  Raises if it cannot be built or loaded."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
-            _build.build()
+        from . import build as _build
+        _build.build()                     # no-op when the .so is newer than every source / header (mtime check);
+                                           # on a box without nvcc the prebuilt .so is used as shipped
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError = the library does not export what the header declares
@@ -115,6 +125,12 @@ def check(rc):
     if rc < 0:
         raise RumiError(rc, lib().rumi_last_error().decode("utf-8", "replace"))
     return rc
+
+
+def torch_stream():
+    """cudaStream_t of torch's current stream (the stream the caller's tensors are produced / consumed on)."""
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def ptr(a):

@@ -77,11 +77,15 @@ class ORBVocabulary:
         import torch
         assert desc.is_cuda and desc.dtype == torch.uint8 and desc.is_contiguous()
         n = desc.shape[0]
-        word = torch.zeros(n, dtype=torch.int32, device=desc.device)
-        weight = torch.zeros(n, dtype=torch.float64, device=desc.device)
-        node = torch.zeros(n, dtype=torch.int32, device=desc.device)
+        word = torch.empty(n, dtype=torch.int32, device=desc.device)
+        weight = torch.empty(n, dtype=torch.float64, device=desc.device)
+        node = torch.empty(n, dtype=torch.int32, device=desc.device)
+        st = _lib.torch_stream()                    # `desc` was produced on torch's stream; the results are used there
+        check(self._L.rumi_vocab_wait_stream(self._v, st))
         check(self._L.rumi_bow_transform_device(self._v, ptr(desc), n, int(levelsup), ptr(word), ptr(weight), ptr(node),
                                                 1 if sync else 0))
+        if not sync:
+            check(self._L.rumi_vocab_signal_stream(self._v, st))
         return word, weight, node
 
     # ---- transform(features, BowVector&, FeatureVector&, levelsup) (:1128-1200) == Frame::ComputeBoW ----

@@ -4,6 +4,8 @@ In-tree build with plain nvcc (cross-compiles without a GPU): one object per .cu
 library.  `python -m rumi_slam_b200.build [--force] [--verbose]`.
 """
 import concurrent.futures as cf
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -12,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librumi_orb.so")
-SOURCES = ["pyramid.cu", "pyramid_march.cu", "blur.cu", "fast.cu", "octree.cu", "describe.cu", "match.cu", "match_imma.cu", "match_umma.cu", "bow.cu", "stereo.cu", "flow.cu", "api.cu"]
+SOURCES = ["pyramid.cu", "pyramid_march.cu", "blur.cu", "fast.cu", "octree.cu", "describe.cu", "match.cu", "match_umma.cu", "bow.cu", "stereo.cu", "flow.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]
@@ -34,12 +36,41 @@ def _compile(src, verbose):
     return obj, r.stderr
 
 
+STAMP = LIB + ".stamp"
+
+
+def _fingerprint(deps):
+    """Content hash of every source / header / flag: file times do not survive the copy to the GPU box."""
+    h = hashlib.sha256(" ".join(FLAGS[:-1]).encode())
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _fresh(fp):
+    try:
+        return os.path.exists(LIB) and open(STAMP).read().strip() == fp
+    except OSError:
+        return False
+
+
 def build(force=False, verbose=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = [os.path.join(CSRC, s) for s in srcs] + _headers() + [os.path.abspath(__file__)]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+    deps = [os.path.join(CSRC, s) for s in srcs] + _headers()
+    fp = _fingerprint(deps)
+    if not force and _fresh(fp):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:         # ranks of one torchrun job: one builds, the rest wait
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _fresh(fp):
+            return LIB
+        return _build_locked(srcs, fp, verbose)
+
+
+def _build_locked(srcs, fp, verbose):
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
         res = list(ex.map(lambda s: _compile(s, verbose), srcs))
     log = "".join(r[1] for r in res)
@@ -49,6 +80,8 @@ def build(force=False, verbose=False):
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    with open(STAMP, "w") as f:
+        f.write(fp + "\n")
     return LIB
 
 

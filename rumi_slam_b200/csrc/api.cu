@@ -2,6 +2,7 @@
 // orchestration.  No arithmetic of the hot path happens on the host; without a CUDA device every call fails.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -75,8 +76,6 @@ bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, int nframes, i
 
 struct Workspace {
     cudaStream_t stream = nullptr;
-    cudaStream_t streamHi = nullptr;   // high-priority side stream for the latency-bound kernels (pyramid, quad-tree)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork / join points between the two streams
     uint8_t *pyr = nullptr, *blur = nullptr;
     uint32_t *cand = nullptr, *candOrdered = nullptr, *sel = nullptr;
     int *levelCount = nullptr, *cellOff = nullptr, *cellCount = nullptr, *selCount = nullptr, *slot = nullptr;
@@ -89,6 +88,7 @@ struct Workspace {
     int lastFrames = 0;
     int* pyrFlags = nullptr;           // [chunk][marchItems] completion epochs of the marching pyramid's work items
     int pyrEpoch = 0;
+    bool ready = false;                // every buffer above is allocated
 };
 
 }  // namespace
@@ -114,8 +114,6 @@ struct rumi_orb {
     FastCell* fastCells = nullptr;                    // [totalCells] cell geometry of all levels
     // marching pyramid (K1'): per-level column-group / row tables, work-item geometry
     bool useMarch = true, marchOk = false, marchForced = false;
-    int marchSplit = kMaxLevels;                      // levels below this get their own launch, the rest is chained
-                                                      // inside one launch (RUMI_PYRAMID_SPLIT; measured: separate wins)
     uint8_t* marchTables = nullptr;
     PyrMarchLevel marchLv[kMaxLevels];
     int marchItems = 0;
@@ -123,22 +121,18 @@ struct rumi_orb {
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
     int skipMask = 0;              // RUMI_SKIP_STAGES (timing experiments only: results are wrong) bit s = skip stage s
-    bool hiPrio = false;           // pyramid / quad-tree on a high-priority side stream (RUMI_HIPRIO=1; measured: 1 stream
-                                   // 103 -> 107 k frames/s, but 2 streams 123 -> 110 k, so off by default)
     bool nwsSet = false;           // RUMI_STREAMS given: use it for every path
     int nwsDefault = 4; bool nwsSetDefault = false;
     int lastWs = 0;
-    // host-batch pipeline: input staging ring + copy streams decoupled from the two compute workspaces
-    static constexpr int kStage = 3;
-    cudaStream_t cpIn = nullptr, cpOut = nullptr;
-    uint8_t* stage[kStage] = {nullptr, nullptr, nullptr}; size_t stageBytes = 0;
-    cudaEvent_t evInReady[kStage] = {}, evInFree[kStage] = {}, evComputeDone[2] = {}, evOutDone[2] = {};
-    bool staged = false;           // RUMI_STAGED=1 (measured slower: 8.40 vs 8.02 ms per 1024 frames, so off by default)
+    // device-side error flags in mapped pinned host memory (per handle, read for free at every host sync point):
+    // [0] a TMA transaction of the tile pyramid timed out, [1] a pyramid level dependency timed out
+    int* errHost = nullptr; int* errDev = nullptr;
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
     int dbgCell = 0;
     // measurement: device-side timer on the launching streams, optional per-stage events, launch counter
     cudaEvent_t evStart = nullptr, evStop = nullptr, evJoin[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evOrder = nullptr, evSignal[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};   // wait_stream / signal_stream
     bool profile = false;
     std::vector<cudaEvent_t> evPool;
     size_t evUsed = 0;
@@ -154,11 +148,9 @@ void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
     cudaFree(w.levelCount); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
     cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono); cudaFree(w.pyrFlags);
-    cudaStream_t s = w.stream, sh = w.streamHi;
-    cudaEvent_t ev[4] = {w.ev[0], w.ev[1], w.ev[2], w.ev[3]};
+    cudaStream_t s = w.stream;
     w = Workspace();
-    w.stream = s; w.streamHi = sh;
-    for (int i = 0; i < 4; ++i) w.ev[i] = ev[i];
+    w.stream = s;
 }
 
 LevelView internal_view(const rumi_orb* h, const uint8_t* base, int l) {
@@ -200,37 +192,38 @@ int alloc_workspace(rumi_orb* h, Workspace& w) {
         w.tmapOk[l] = h->useTMA && make_tmap(&w.tmap[l], src.ptr, src.w, src.h, h->chunk, src.stride, src.pitch,
                                              h->boxW[l], h->boxH[l]);
     }
+    w.ready = true;
     return RUMI_OK;
 }
 
-// (Re)builds everything that depends on the image shape.
-int ensure_geometry(rumi_orb* h, int W, int H) {
-    if (h->W == W && h->H == H && h->coef) return RUMI_OK;
-    CU_TRY(cudaSetDevice(h->device));
-    OrbConst oc;
-    const int rc = build_orb_const(oc, W, H, h->nfeatures, h->scaleFactor, h->nlevels, h->iniTh, h->minTh);
-    if (rc) return fail(RUMI_ERR_SHAPE, "image %dx%d cannot be processed with %d levels (code %d)", W, H, h->nlevels, rc);
+// Drops everything that depends on the image shape: the handle is back to "no geometry" (W = H = 0), so the next call
+// rebuilds from scratch.  Also the failure path of build_geometry / alloc_workspace: a half-built geometry is never kept.
+void reset_geometry(rumi_orb* h) {
     for (int i = 0; i < kMaxWs; ++i) {
         if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
         free_workspace(h->ws[i]);
     }
-    for (int i = 0; i < rumi_orb::kStage; ++i) {
-        cudaFree(h->stage[i]);
-        if (h->evInReady[i]) cudaEventDestroy(h->evInReady[i]);
-        if (h->evInFree[i]) cudaEventDestroy(h->evInFree[i]);
-    }
-    for (int i = 0; i < 2; ++i) {
-        if (h->evComputeDone[i]) cudaEventDestroy(h->evComputeDone[i]);
-        if (h->evOutDone[i]) cudaEventDestroy(h->evOutDone[i]);
-    }
-    if (h->cpIn) cudaStreamDestroy(h->cpIn);
-    if (h->cpOut) cudaStreamDestroy(h->cpOut);
     cudaFree(h->coef);
     cudaFree(h->fastCells);
     cudaFree(h->marchTables);
     h->coef = nullptr;
     h->fastCells = nullptr;
     h->marchTables = nullptr;
+    h->marchOk = false; h->marchItems = 0;
+    h->W = 0; h->H = 0;
+    h->pyrBytes = 0; h->candElems = 0; h->bigKeysElems = 0;
+    cudaGetLastError();                     // a failed cudaMalloc leaves a (non-sticky) error behind
+}
+
+// Builds everything that depends on the image shape (the caller resets the handle when this fails).
+int build_geometry(rumi_orb* h, int W, int H) {
+    OrbConst oc;
+    const int rc = build_orb_const(oc, W, H, h->nfeatures, h->scaleFactor, h->nlevels, h->iniTh, h->minTh);
+    if (rc) return fail(RUMI_ERR_SHAPE, "image %dx%d cannot be processed with %d levels (code %d)", W, H, h->nlevels, rc);
+    for (int l = 0; l < oc.nlevels; ++l)
+        if (oc.lv[l].candCap >= (1 << kOrderBits))
+            return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, oc.lv[l].candCap);
+    reset_geometry(h);
     h->oc = oc;
     h->W = W; h->H = H;
     // resize coefficient tables + per-level source box of a 64x32 tile
@@ -353,7 +346,6 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
             }
         const int slots = (l + 1 < oc.nlevels ? oc.lv[l + 1].kpBase : oc.kpCap) - g.kpBase;
         nodeCap = std::max(nodeCap, slots + 1);
-        if (g.candCap >= (1 << kOrderBits)) return fail(RUMI_ERR_SHAPE, "level %d too large (%d candidates)", l, g.candCap);
     }
     h->pyrBytes = pb + 256; h->candElems = ce; h->bigKeysElems = be;
     h->fastTilePitch = tp; h->fastTileRows = tr; h->fastScoreRows = sr;
@@ -368,17 +360,43 @@ int ensure_geometry(rumi_orb* h, int W, int H) {
     return RUMI_OK;
 }
 
+// (Re)builds the shape-dependent state when the shape changes.  Nothing is committed on failure: the handle is left
+// without geometry, so a later call with the same shape tries again instead of running on null tables.
+int ensure_geometry(rumi_orb* h, int W, int H) {
+    if (h->W == W && h->H == H && h->coef && h->fastCells) return RUMI_OK;
+    CU_TRY(cudaSetDevice(h->device));
+    const int rc = build_geometry(h, W, H);
+    if (rc) {
+        const std::string msg = g_err;
+        reset_geometry(h);
+        g_err = msg;
+    }
+    return rc;
+}
+
 int ensure_workspace(rumi_orb* h, int idx) {
     Workspace& w = h->ws[idx];
     if (!w.stream) CU_TRY(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-    if (h->hiPrio && !w.streamHi) {
-        int least = 0, greatest = 0;
-        CU_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        CU_TRY(cudaStreamCreateWithPriority(&w.streamHi, cudaStreamNonBlocking, greatest));
-        for (int i = 0; i < 4; ++i) CU_TRY(cudaEventCreateWithFlags(&w.ev[i], cudaEventDisableTiming));
+    if (w.ready) return RUMI_OK;
+    const int rc = alloc_workspace(h, w);
+    if (rc) {                                 // partial allocation: release it, the next call starts over
+        const std::string msg = g_err;
+        cudaStreamSynchronize(w.stream);
+        free_workspace(w);
+        cudaGetLastError();
+        g_err = msg;
     }
-    if (w.pyr) return RUMI_OK;
-    return alloc_workspace(h, w);
+    return rc;
+}
+
+// Called after a host synchronisation: a kernel that gave up waiting (instead of hanging the GPU) becomes an error code.
+int check_device_flags(rumi_orb* h) {
+    if (!h->errHost) return RUMI_OK;
+    const int tma = h->errHost[0], dep = h->errHost[1];
+    if (!tma && !dep) return RUMI_OK;
+    h->errHost[0] = h->errHost[1] = 0;                       // reported once; the handle stays usable
+    return fail(RUMI_ERR_CUDA, tma ? "TMA transaction timed out (results of this call are invalid)"
+                                   : "pyramid level dependency timed out (results of this call are invalid)");
 }
 
 enum { ST_PYRAMID = 0, ST_FAST = 1, ST_OCTREE = 2, ST_SLOTS = 3, ST_BLUR = 4, ST_DESCRIBE = 5, ST_H2D = 6, ST_D2H = 7,
@@ -408,13 +426,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
               KeyPointRec* dKps, uint8_t* dDesc, int outCap, int* dNkp, int* dNmono) {
     const OrbConst& oc = h->oc;
     cudaStream_t s = w.stream;
-    // Optional (RUMI_HIPRIO=1): the latency-bound kernels (pyramid: 7 dependent small launches; quad-tree: barriers + a
-    // serial phase) go to a high-priority side stream, so the block scheduler hands freed SM slots to them first and
-    // the blur (needs only the pyramid) overlaps the quad-tree of its own chunk.  Measured on B200: helps a single
-    // stream of chunks (103 -> 107 k frames/s) and single-frame latency (0.270 -> 0.261 ms) but hurts the default
-    // two-workspace pipeline (123 -> 110 k), which already overlaps neighbouring chunks -- so it is off by default.
-    const bool fork = h->hiPrio && !h->profile && w.streamHi;
-    cudaStream_t sh = fork ? w.streamHi : s;
+    cudaStream_t sh = s;
     ChunkView cv;
     cv.nframes = n;
     for (int l = 0; l < oc.nlevels; ++l) {
@@ -423,7 +435,6 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     }
     if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
     if (h->profile) prof_event(h, s);
-    if (fork) { CU_TRY(cudaEventRecord(w.ev[0], s)); CU_TRY(cudaStreamWaitEvent(sh, w.ev[0], 0)); }
     // K1': all levels in one launch when every source can be read as aligned 32-bit words (always true for the
     // internal buffers; caller device memory only if it is 4-byte aligned with readable row padding)
     // (a marching item walks its rows serially: with only a few frames in flight the 64x32-pixel TMA tiles have the
@@ -440,20 +451,16 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         ma.cv = cv;
         for (int l = 0; l < kMaxLevels; ++l) ma.lv[l] = h->marchLv[l];
         ma.nlevels = oc.nlevels; ma.itemsPerFrame = h->marchItems;
-        ma.flags = w.pyrFlags; ma.epoch = ++w.pyrEpoch;
-        // levels [1, split) one launch each (large, throughput bound); levels [split, n) chained inside one launch
-        // (small, latency bound: the chain hides their launch gaps)
-        const int split = std::min(std::max(h->marchSplit, 1), oc.nlevels);
+        ma.flags = w.pyrFlags; ma.epoch = ++w.pyrEpoch; ma.err = h->errDev + 1;
         pyrLaunches = 0;
-        for (int l = 1; l < split; ++l) { ma.levelFirst = ma.levelLast = l; launch_pyramid_march(ma, sh); ++pyrLaunches; }
-        if (split < oc.nlevels) { ma.levelFirst = split; ma.levelLast = oc.nlevels - 1; launch_pyramid_march(ma, sh); ++pyrLaunches; }
+        for (int l = 1; l < oc.nlevels; ++l) { ma.levelFirst = ma.levelLast = l; launch_pyramid_march(ma, sh); ++pyrLaunches; }
     } else
     for (int l = 1; l < oc.nlevels; ++l) {
         PyramidLevelArgs pa;
         pa.src = cv.src[l - 1]; pa.dst = cv.src[l];
         pa.xc = h->xc[l]; pa.yc = h->yc[l];
         pa.boxW = h->boxW[l]; pa.boxH = h->boxH[l];
-        pa.nframes = n;
+        pa.nframes = n; pa.err = h->errDev;
         const CUtensorMap* tm = nullptr;
         CUtensorMap dyn;
         if (h->useTMA) {
@@ -465,7 +472,6 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         }
         launch_pyramid_level(pa, tm, sh);
     }
-    if (fork) { CU_TRY(cudaEventRecord(w.ev[1], sh)); CU_TRY(cudaStreamWaitEvent(s, w.ev[1], 0)); }
     prof_mark(h, s, ST_PYRAMID, pyrLaunches);
     FastArgs fa;
     fa.cv = cv; fa.cand = w.cand; fa.levelCount = w.levelCount; fa.cellOff = w.cellOff; fa.cellCount = w.cellCount;
@@ -486,7 +492,6 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     }
     if (!(skip & 2)) launch_fast(fa, oc, s);
     prof_mark(h, s, ST_FAST, 1);
-    if (fork) { CU_TRY(cudaEventRecord(w.ev[2], s)); CU_TRY(cudaStreamWaitEvent(sh, w.ev[2], 0)); }
     if (!(skip & 4)) launch_octree(oa, oc, sh);
     prof_mark(h, s, ST_OCTREE, 1);
     DescribeArgs da;
@@ -494,10 +499,8 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     da.kps = dKps; da.desc = dDesc; da.nkp = dNkp; da.nmono = dNmono; da.outCap = outCap;
     launch_assign_slots(da, oc, sh);
     prof_mark(h, s, ST_SLOTS, 1);
-    if (fork) CU_TRY(cudaEventRecord(w.ev[3], sh));
-    if (!(skip & 16)) launch_blur(cv, oc, s);                // needs only the pyramid: beside the quad-tree when forked
+    if (!(skip & 16)) launch_blur(cv, oc, s);
     prof_mark(h, s, ST_BLUR, 1);
-    if (fork) CU_TRY(cudaStreamWaitEvent(s, w.ev[3], 0));
     if (!(skip & 32)) launch_describe(da, oc, s);
     prof_mark(h, s, ST_DESCRIBE, 1);
     CU_TRY(cudaGetLastError());
@@ -553,17 +556,18 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     const char* pm = getenv("RUMI_PYRAMID");                     // "march" (default) | "tiles" (TMA / plain tile kernel)
     h->useMarch = !(pm && pm[0] == 't') && h->useTMA;            // RUMI_NO_TMA=1 selects the plain tile kernel
     h->marchForced = pm && pm[0] == 'm';                         // RUMI_PYRAMID=march: also for small calls (tests)
-    const char* ps = getenv("RUMI_PYRAMID_SPLIT");
-    if (ps && ps[0] >= '1' && ps[0] <= '9') h->marchSplit = ps[0] - '0';
     const char* sk = getenv("RUMI_SKIP_STAGES");
     if (sk) h->skipMask = atoi(sk);
-    const char* hp = getenv("RUMI_HIPRIO");
-    if (hp && hp[0] == '1') h->hiPrio = true;
-    const char* sg = getenv("RUMI_STAGED");
-    if (sg) h->staged = sg[0] != '0';
     const char* ns = getenv("RUMI_STREAMS");
     if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) { h->nws = ns[0] - '0'; h->nwsSet = true; }
     h->nwsDefault = h->nws; h->nwsSetDefault = h->nwsSet;
+    if (cudaHostAlloc((void**)&h->errHost, 2 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&h->errDev, h->errHost, 0) != cudaSuccess) {
+        if (h->errHost) cudaFreeHost(h->errHost);
+        delete h;
+        return fail(RUMI_ERR_CUDA, "cannot allocate the mapped error flags: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    h->errHost[0] = h->errHost[1] = 0;
     *out = h;
     return RUMI_OK;
 }
@@ -575,18 +579,19 @@ void rumi_orb_destroy(rumi_orb* h) {
         if (h->ws[i].stream) cudaStreamSynchronize(h->ws[i].stream);
         free_workspace(h->ws[i]);
         if (h->ws[i].stream) cudaStreamDestroy(h->ws[i].stream);
-        if (h->ws[i].streamHi) cudaStreamDestroy(h->ws[i].streamHi);
-        for (int e = 0; e < 4; ++e) if (h->ws[i].ev[e]) cudaEventDestroy(h->ws[i].ev[e]);
     }
     cudaFree(h->coef);
     cudaFree(h->fastCells);
     cudaFree(h->marchTables);
     cudaFree(h->dbgBuf);
     cudaFree(h->octClk);
+    if (h->errHost) cudaFreeHost(h->errHost);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->evStart) cudaEventDestroy(h->evStart);
     if (h->evStop) cudaEventDestroy(h->evStop);
     for (int i = 0; i < kMaxWs; ++i) if (h->evJoin[i]) cudaEventDestroy(h->evJoin[i]);
+    if (h->evOrder) cudaEventDestroy(h->evOrder);
+    for (int i = 0; i < kMaxWs; ++i) if (h->evSignal[i]) cudaEventDestroy(h->evSignal[i]);
     delete h;
 }
 
@@ -625,89 +630,6 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
     if (cap_per_frame < oc.kpCap)
         return fail(RUMI_ERR_CAPACITY, "cap_per_frame %d < frame capacity %d", cap_per_frame, oc.kpCap);
     const int nchunks = (n + h->chunk - 1) / h->chunk;
-    if (h->staged && !h->profile && !h->nwsSet && nchunks >= 3) {
-        // Staged pipeline (experiment, RUMI_STAGED=1; the default below -- every chunk's H2D / kernels / D2H on its own
-        // workspace stream, 4 workspaces -- measured faster: 127.7 k vs 121.9 k frames/s end to end).
-        // Kernels run best with TWO workspaces in flight (more only thrash L2, see the device path),
-        // but hiding the 307 KB/frame H2D needs the copies to run further ahead.  So the copies get their own streams and
-        // a ring of kStage input buffers: chunk c is uploaded into stage[c % 3] on `cpIn`, extracted on workspace c % 2
-        // reading level 0 straight from the staging buffer, and its results leave on `cpOut`.
-        //   cpIn     : [wait compute(c-3) done] H2D(c)                        -> evInReady[c % 3]
-        //   ws[c % 2]: [wait evInReady, wait D2H(c-2) done] kernels(c)        -> evComputeDone[c % 2] (= evInFree[c % 3])
-        //   cpOut    : [wait evComputeDone] D2H(c)                            -> evOutDone[c % 2]
-        const LevelGeom& g0 = oc.lv[0];
-        const size_t frameBytes = (size_t)g0.stride * g0.h, need = frameBytes * h->chunk + 256;
-        if (!h->cpIn) {
-            CU_TRY(cudaStreamCreateWithFlags(&h->cpIn, cudaStreamNonBlocking));
-            CU_TRY(cudaStreamCreateWithFlags(&h->cpOut, cudaStreamNonBlocking));
-            for (int i = 0; i < rumi_orb::kStage; ++i) {
-                CU_TRY(cudaEventCreateWithFlags(&h->evInReady[i], cudaEventDisableTiming));
-                CU_TRY(cudaEventCreateWithFlags(&h->evInFree[i], cudaEventDisableTiming));
-            }
-            for (int i = 0; i < 2; ++i) {
-                CU_TRY(cudaEventCreateWithFlags(&h->evComputeDone[i], cudaEventDisableTiming));
-                CU_TRY(cudaEventCreateWithFlags(&h->evOutDone[i], cudaEventDisableTiming));
-            }
-        }
-        if (h->stageBytes < need) {
-            for (int i = 0; i < rumi_orb::kStage; ++i) {
-                cudaFree(h->stage[i]); h->stage[i] = nullptr;
-                CU_TRY(cudaMalloc(&h->stage[i], need));
-                CU_TRY(cudaMemset(h->stage[i], 0, need));      // row padding is read as whole words by the pyramid kernel
-            }
-            CU_TRY(cudaDeviceSynchronize());
-            h->stageBytes = need;
-        }
-        for (int wi = 0; wi < 2; ++wi)
-            if ((rc = ensure_workspace(h, wi))) return rc;
-        for (int c = 0; c < nchunks; ++c) {
-            const int wi = c & 1, slot = c % rumi_orb::kStage;
-            Workspace& ws = h->ws[wi];
-            const int f0 = c * h->chunk, m = std::min(h->chunk, n - f0);
-            const uint8_t* src = imgs + (size_t)f0 * frame_pitch;
-            uint8_t* dst = h->stage[slot];
-            if (c >= rumi_orb::kStage) CU_TRY(cudaStreamWaitEvent(h->cpIn, h->evInFree[slot], 0));
-            if ((frame_pitch == stride * (size_t)g0.h || m == 1) && stride == (size_t)g0.stride) {
-                CU_TRY(cudaMemcpyAsync(dst, src, (size_t)m * frameBytes, cudaMemcpyHostToDevice, h->cpIn));
-            } else if (frame_pitch == stride * (size_t)g0.h || m == 1) {
-                CU_TRY(cudaMemcpy2DAsync(dst, g0.stride, src, stride, g0.w, (size_t)m * g0.h, cudaMemcpyHostToDevice, h->cpIn));
-            } else {
-                for (int i = 0; i < m; ++i)
-                    CU_TRY(cudaMemcpy2DAsync(dst + (size_t)i * frameBytes, g0.stride, src + i * frame_pitch, stride, g0.w,
-                                             g0.h, cudaMemcpyHostToDevice, h->cpIn));
-            }
-            CU_TRY(cudaEventRecord(h->evInReady[slot], h->cpIn));
-            CU_TRY(cudaStreamWaitEvent(ws.stream, h->evInReady[slot], 0));
-            if (c >= 2) CU_TRY(cudaStreamWaitEvent(ws.stream, h->evOutDone[wi], 0));     // ws.kps / ws.desc still leaving
-            LevelView l0;
-            l0.ptr = dst; l0.pitch = (long long)frameBytes; l0.stride = g0.stride; l0.w = g0.w; l0.h = g0.h;
-            if ((rc = run_chunk(h, ws, l0, false, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
-            if (c == nchunks - 1)     // keep the parity hooks / pyramid read-back working: level 0 of the last chunk
-                CU_TRY(cudaMemcpyAsync(ws.pyr + h->pyrLevelOff[0], dst, (size_t)m * frameBytes, cudaMemcpyDeviceToDevice, ws.stream));
-            CU_TRY(cudaEventRecord(h->evComputeDone[wi], ws.stream));
-            CU_TRY(cudaEventRecord(h->evInFree[slot], ws.stream));
-            CU_TRY(cudaStreamWaitEvent(h->cpOut, h->evComputeDone[wi], 0));
-            if (cap_per_frame == oc.kpCap) {
-                CU_TRY(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ws.kps, sizeof(rumi_kp) * (size_t)oc.kpCap * m,
-                                       cudaMemcpyDeviceToHost, h->cpOut));
-                CU_TRY(cudaMemcpyAsync(desc + (size_t)f0 * cap_per_frame * 32, ws.desc, 32 * (size_t)oc.kpCap * m,
-                                       cudaMemcpyDeviceToHost, h->cpOut));
-            } else {
-                CU_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap_per_frame, sizeof(rumi_kp) * (size_t)cap_per_frame, ws.kps,
-                                         sizeof(rumi_kp) * (size_t)oc.kpCap, sizeof(rumi_kp) * (size_t)oc.kpCap, m,
-                                         cudaMemcpyDeviceToHost, h->cpOut));
-                CU_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap_per_frame * 32, 32 * (size_t)cap_per_frame, ws.desc,
-                                         32 * (size_t)oc.kpCap, 32 * (size_t)oc.kpCap, m, cudaMemcpyDeviceToHost, h->cpOut));
-            }
-            CU_TRY(cudaMemcpyAsync(n_kp + f0, ws.nkp, 4 * (size_t)m, cudaMemcpyDeviceToHost, h->cpOut));
-            CU_TRY(cudaMemcpyAsync(n_mono + f0, ws.nmono, 4 * (size_t)m, cudaMemcpyDeviceToHost, h->cpOut));
-            CU_TRY(cudaEventRecord(h->evOutDone[wi], h->cpOut));
-            h->lastWs = wi;
-        }
-        CU_TRY(cudaStreamSynchronize(h->cpOut));
-        for (int i = 0; i < 2; ++i) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
-        return RUMI_OK;
-    }
     for (int c = 0; c < nchunks; ++c) {
         const int wi = c % h->nws;
         if ((rc = ensure_workspace(h, wi))) return rc;
@@ -739,7 +661,7 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
     }
     for (int i = 0; i < kMaxWs; ++i)
         if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
-    return RUMI_OK;
+    return check_device_flags(h);
 }
 
 int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1,
@@ -760,8 +682,7 @@ int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t st
     CU_TRY(cudaMemcpyAsync(&counts[0], ws.nkp, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaMemcpyAsync(&counts[1], ws.nmono, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaStreamSynchronize(ws.stream));
-    if (h->useTMA && read_tma_timeout_flag() != 0) return fail(RUMI_ERR_CUDA, "TMA transaction timed out");
-    if (h->useMarch && read_pyramid_wait_timeout_flag() != 0) return fail(RUMI_ERR_CUDA, "pyramid level dependency timed out");
+    if ((rc = check_device_flags(h))) return rc;
     *n_kp = counts[0]; *n_mono = counts[1];
     const int m = std::min(counts[0], cap);
     if (m > 0) {
@@ -802,9 +723,11 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
             return rc;
         h->lastWs = wi;
     }
-    if (sync)
+    if (sync) {
         for (int i = 0; i < kMaxWs; ++i)
             if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+        return check_device_flags(h);
+    }
     return RUMI_OK;
 }
 
@@ -904,6 +827,32 @@ int rumi_orb_timer_stop(rumi_orb* h, float* ms) {
     CU_TRY(cudaEventRecord(h->evStop, h->ws[0].stream));
     CU_TRY(cudaEventSynchronize(h->evStop));
     CU_TRY(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+    return check_device_flags(h);
+}
+
+// Ordering against the caller's own CUDA work (device-resident entry points): the library launches on private
+// non-blocking streams, which no other stream orders itself against implicitly.
+int rumi_orb_wait_stream(rumi_orb* h, void* stream) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    if (!h->evOrder) CU_TRY(cudaEventCreateWithFlags(&h->evOrder, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(h->evOrder, (cudaStream_t)stream));
+    for (int i = 0; i < kMaxWs; ++i) {
+        if (!h->ws[i].stream) CU_TRY(cudaStreamCreateWithFlags(&h->ws[i].stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamWaitEvent(h->ws[i].stream, h->evOrder, 0));
+    }
+    return RUMI_OK;
+}
+
+int rumi_orb_signal_stream(rumi_orb* h, void* stream) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < kMaxWs; ++i) {
+        if (!h->ws[i].stream) continue;
+        if (!h->evSignal[i]) CU_TRY(cudaEventCreateWithFlags(&h->evSignal[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(h->evSignal[i], h->ws[i].stream));
+        CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->evSignal[i], 0));
+    }
     return RUMI_OK;
 }
 
@@ -998,12 +947,15 @@ struct rumi_match {
     uint64_t* partial = nullptr; size_t partialCap = 0;
     uint8_t *dQ = nullptr, *dT = nullptr; size_t qCap = 0, tCap = 0;
     uint8_t* dOut = nullptr; size_t outCap = 0;      // idx1 (4 B) | d1 (2 B) | d2 (2 B) per query
-    uint8_t *qx = nullptr, *tx = nullptr; size_t qxCap = 0, txCap = 0;   // 0/1-byte expansions for the IMMA kernel
-    uint16_t* popT = nullptr; size_t popCap = 0;
-    int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 2 IMMA (mma.sync), 3 tcgen05 UMMA
-    int lastPath = 0;                                // kernel of the last top-2 call: 1 LOP3+POPC, 2 IMMA, 3 UMMA
+    uint8_t* tx = nullptr; size_t txCap = 0;         // train set as ready-to-load UMMA operand tiles (K8-P)
+    int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 3 tcgen05 UMMA only
+    int lastPath = 0;                                // kernel of the last top-2 call: 1 LOP3+POPC, 3 UMMA
     cudaEvent_t evStart = nullptr, evStop = nullptr;
+    cudaEvent_t evOrder = nullptr;                   // ordering with the caller's streams (wait_stream / signal_stream)
     long long launches = 0;
+    // multi-GPU exchange step (one process per GPU): NCCL communicator, this rank, gather buffers
+    void* comm = nullptr; bool ownComm = false; int rank = 0, nranks = 1;
+    uint64_t *shardSend = nullptr, *shardRecv = nullptr; size_t sendCap = 0, recvCap = 0;
 };
 
 namespace {
@@ -1016,46 +968,91 @@ int grow(void** p, size_t* cap, size_t need) {
     return RUMI_OK;
 }
 
-int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int tBase, int32_t* dIdx,
-                uint16_t* dD1, uint16_t* dD2) {
+// Runs the top-2 scan of nq queries against nt train rows; leaves `*slices` candidate arrays [slice][nq] in m->partial.
+int top2_partials(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int tBase, int* slicesOut) {
     if (((uintptr_t)dQ | (uintptr_t)dT) & 15) return fail(RUMI_ERR_ARG, "descriptor arrays must be 16-byte aligned");
     // Large problems go to the tensor cores: tcgen05 kind::i8 UMMA with TMEM accumulators (K8-U, operands expanded
     // in-kernel from the packed rows); small ones (stereo bands, single frames) stay on the LOP3+POPC kernel, whose
-    // set-up is cheaper.  The mma.sync int8 kernel (K8-T) is kept behind RUMI_MATCH=imma for comparison.
+    // set-up is cheaper.
     const bool big = (long long)nq * nt >= 64ll * 1024 * 1024 && nq >= 256;
     const bool fits = nt > 0 && nt <= (1 << 22);
     const bool umma = fits && (m->mode == 3 || (m->mode == 0 && big));
-    const bool imma = fits && m->mode == 2;
     int rc;
     if (umma) {
         const int slices = umma_slices(nq, nt);
         if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
         if ((rc = grow((void**)&m->tx, &m->txCap, umma_train_bytes(nt)))) return rc;
         launch_hamming_top2_umma(dQ, nq, dT, nt, m->tx, tBase, slices, m->partial, m->stream);
-        launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
-        m->launches += 3;
+        m->launches += 2;
         m->lastPath = 3;
-    } else if (imma) {
-        const int slices = imma_slices(nq, nt);
-        if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
-        if ((rc = grow((void**)&m->qx, &m->qxCap, 256 * (size_t)nq))) return rc;
-        if ((rc = grow((void**)&m->tx, &m->txCap, 256 * (size_t)nt))) return rc;
-        if ((rc = grow((void**)&m->popT, &m->popCap, 2 * (size_t)nt))) return rc;
-        launch_expand_bits(dQ, nq, m->qx, nullptr, m->stream);
-        launch_expand_bits(dT, nt, m->tx, m->popT, m->stream);
-        launch_hamming_top2_imma(dQ, m->qx, nq, m->tx, m->popT, nt, tBase, slices, m->partial, m->stream);
-        launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
-        m->launches += 4;
-        m->lastPath = 2;
+        *slicesOut = slices;
     } else {
         const int slices = match_slices(nq, nt);
         if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
         launch_hamming_top2_partial(dQ, nq, dT, nt, tBase, slices, m->partial, m->stream);
-        launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
-        m->launches += 2;
+        m->launches += 1;
         m->lastPath = 1;
+        *slicesOut = slices;
     }
     CU_TRY(cudaGetLastError());
+    return RUMI_OK;
+}
+
+int top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, int nt, int tBase, int32_t* dIdx,
+                uint16_t* dD1, uint16_t* dD2) {
+    int slices = 1;
+    const int rc = top2_partials(m, dQ, nq, dT, nt, tBase, &slices);
+    if (rc) return rc;
+    launch_top2_merge(m->partial, slices, nq, dIdx, dD1, dD2, m->stream);
+    m->launches += 1;
+    CU_TRY(cudaGetLastError());
+    return RUMI_OK;
+}
+
+// ---- NCCL, resolved at run time (the library has no link-time dependency on it; a process that already loaded
+//      libnccl.so.2 -- e.g. through torch -- gets that copy) ----
+struct NcclApi {
+    void* lib = nullptr;
+    int (*getUniqueId)(void* id) = nullptr;
+    int (*commDestroy)(void* comm) = nullptr;
+    int (*allGather)(const void* send, void* recv, size_t count, int dtype, void* comm, cudaStream_t s) = nullptr;
+    const char* (*errorString)(int) = nullptr;
+    void* commInitRank = nullptr;            // ncclCommInitRank(ncclComm_t*, int, ncclUniqueId (by value, 128 B), int)
+    bool ok = false;
+};
+struct NcclId { char internal[128]; };       // == ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES 128)
+constexpr int kNcclUint64 = 5;               // ncclDataType_t ncclUint64 (nccl.h)
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names)
+            if ((api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (api.lib) {
+            api.getUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+            api.commDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+            api.allGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+            api.errorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+            api.commInitRank = dlsym(api.lib, "ncclCommInitRank");
+            api.ok = api.getUniqueId && api.commDestroy && api.allGather && api.errorString && api.commInitRank;
+        }
+    }
+    return api;
+}
+#define NCCL_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        const int r__ = (expr);                                                                         \
+        if (r__ != 0) return fail(RUMI_ERR_CUDA, "%s failed: %s", #expr, nccl_api().errorString(r__));  \
+    } while (0)
+
+// Orders a private library stream against a caller stream (NULL = the legacy default stream).
+int order_after(cudaStream_t waiter, cudaStream_t producer, cudaEvent_t* ev) {
+    if (!*ev) CU_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(*ev, producer));
+    CU_TRY(cudaStreamWaitEvent(waiter, *ev, 0));
     return RUMI_OK;
 }
 }  // namespace
@@ -1073,8 +1070,8 @@ int rumi_match_create(rumi_match** out, int device) {
     rumi_match* m = new rumi_match();
     m->device = device;
     CU_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    const char* mm = getenv("RUMI_MATCH");                       // "popc" / "imma": force one top-2 kernel (tests, A/B)
-    if (mm) m->mode = mm[0] == 'p' ? 1 : mm[0] == 'i' ? 2 : mm[0] == 'u' ? 3 : 0;
+    const char* mm = getenv("RUMI_MATCH");                       // "popc" / "umma": force one top-2 kernel (tests, A/B)
+    if (mm) m->mode = mm[0] == 'p' ? 1 : mm[0] == 'u' ? 3 : 0;
     *out = m;
     return RUMI_OK;
 }
@@ -1083,9 +1080,11 @@ void rumi_match_destroy(rumi_match* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut); cudaFree(m->qx); cudaFree(m->tx);
-    cudaFree(m->popT);
+    cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut); cudaFree(m->tx);
+    cudaFree(m->shardSend); cudaFree(m->shardRecv);
+    if (m->comm && m->ownComm && nccl_api().ok) nccl_api().commDestroy(m->comm);
     if (m->evStart) { cudaEventDestroy(m->evStart); cudaEventDestroy(m->evStop); }
+    if (m->evOrder) cudaEventDestroy(m->evOrder);
     delete m;
 }
 
@@ -1213,6 +1212,76 @@ int rumi_top2_merge_device(rumi_match* m, const uint64_t* d_packed, int nshards,
     CU_TRY(cudaSetDevice(m->device));
     launch_top2_merge(d_packed, nshards, nq, d_idx1, d_d1, d_d2, m->stream);
     m->launches += 1;
+    CU_TRY(cudaGetLastError());
+    if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+int rumi_match_wait_stream(rumi_match* m, void* stream) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    CU_TRY(cudaSetDevice(m->device));
+    return order_after(m->stream, (cudaStream_t)stream, &m->evOrder);
+}
+
+int rumi_match_signal_stream(rumi_match* m, void* stream) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    CU_TRY(cudaSetDevice(m->device));
+    return order_after((cudaStream_t)stream, m->stream, &m->evOrder);
+}
+
+int rumi_nccl_unique_id(uint8_t* id128) {
+    if (!id128) return fail(RUMI_ERR_ARG, "id is NULL");
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(RUMI_ERR_CUDA, "libnccl.so.2 not found: multi-GPU matching needs NCCL");
+    NcclId id;
+    NCCL_TRY(n.getUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return RUMI_OK;
+}
+
+int rumi_match_comm_init(rumi_match* m, const uint8_t* id128, int rank, int nranks) {
+    if (!m || !id128) return fail(RUMI_ERR_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RUMI_ERR_ARG, "rank %d of %d", rank, nranks);
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(RUMI_ERR_CUDA, "libnccl.so.2 not found: multi-GPU matching needs NCCL");
+    CU_TRY(cudaSetDevice(m->device));
+    if (m->comm && m->ownComm) n.commDestroy(m->comm);
+    m->comm = nullptr;
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    typedef int (*InitFn)(void**, int, NcclId, int);
+    NCCL_TRY(((InitFn)n.commInitRank)(&m->comm, nranks, id, rank));
+    m->ownComm = true; m->rank = rank; m->nranks = nranks;
+    return RUMI_OK;
+}
+
+int rumi_match_comm_adopt(rumi_match* m, void* nccl_comm, int rank, int nranks) {
+    if (!m || !nccl_comm) return fail(RUMI_ERR_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RUMI_ERR_ARG, "rank %d of %d", rank, nranks);
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(RUMI_ERR_CUDA, "libnccl.so.2 not found: multi-GPU matching needs NCCL");
+    if (m->comm && m->ownComm) n.commDestroy(m->comm);
+    m->comm = nccl_comm; m->ownComm = false; m->rank = rank; m->nranks = nranks;
+    return RUMI_OK;
+}
+
+int rumi_hamming_top2_sharded(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT_local, int nt_local,
+                              int t_base, int32_t* d_idx1, uint16_t* d_d1, uint16_t* d_d2, int sync) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nq < 0 || nt_local < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (!m->comm) return fail(RUMI_ERR_ARG, "no communicator: call rumi_match_comm_init / rumi_match_comm_adopt first");
+    if (nq == 0) return RUMI_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    int rc, slices = 1;
+    if ((rc = grow((void**)&m->shardSend, &m->sendCap, 8 * (size_t)nq))) return rc;
+    if ((rc = grow((void**)&m->shardRecv, &m->recvCap, 8 * (size_t)nq * m->nranks))) return rc;
+    // local scan -> packed candidates (the slice merge writes the 8-byte form the exchange sends) -> all-gather on the
+    // matcher's own stream (no host synchronisation anywhere) -> fold in rank order = ascending train ranges
+    if ((rc = top2_partials(m, dQ, nq, dT_local, nt_local, t_base, &slices))) return rc;
+    launch_top2_merge_packed(m->partial, slices, nq, m->shardSend, m->stream);
+    NCCL_TRY(nccl_api().allGather(m->shardSend, m->shardRecv, (size_t)nq, kNcclUint64, m->comm, m->stream));
+    launch_top2_merge(m->shardRecv, m->nranks, nq, d_idx1, d_d1, d_d2, m->stream);
+    m->launches += 2;
     CU_TRY(cudaGetLastError());
     if (sync) CU_TRY(cudaStreamSynchronize(m->stream));
     return RUMI_OK;
@@ -1360,6 +1429,7 @@ struct rumi_vocab {
     rumi::BowTreeView view;
     uint8_t* scratch = nullptr;        // host-call staging: descriptors + outputs
     size_t scratchCap = 0;
+    cudaEvent_t evOrder = nullptr;
     long long launches = 0;
 };
 
@@ -1431,10 +1501,23 @@ void rumi_vocab_destroy(rumi_vocab* v) {
     cudaSetDevice(v->device);
     if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
     cudaFree(v->blob); cudaFree(v->scratch);
+    if (v->evOrder) cudaEventDestroy(v->evOrder);
     delete v;
 }
 
 int rumi_vocab_words(const rumi_vocab* v) { return v ? v->nwords : 0; }
+
+int rumi_vocab_wait_stream(rumi_vocab* v, void* stream) {
+    if (!v) return fail(RUMI_ERR_ARG, "vocabulary is NULL");
+    CU_TRY(cudaSetDevice(v->device));
+    return order_after(v->stream, (cudaStream_t)stream, &v->evOrder);
+}
+
+int rumi_vocab_signal_stream(rumi_vocab* v, void* stream) {
+    if (!v) return fail(RUMI_ERR_ARG, "vocabulary is NULL");
+    CU_TRY(cudaSetDevice(v->device));
+    return order_after((cudaStream_t)stream, v->stream, &v->evOrder);
+}
 
 long long rumi_vocab_launch_count(rumi_vocab* v, int reset) {
     if (!v) return 0;

@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(256) bow_transform_kernel(const BowTreeView t,
         a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
     }
     const int nidLevel = t.L - levelsup;
+    // the two half-warps descend independent features and may leave the loop at different depths (unbalanced trees):
+    // the shuffles name only the lanes of this half
+    const unsigned halfMask = 0xFFFFu << (threadIdx.x & 16);
     int cur = 0, level = 0, nid = 0;
     int nchild = t.childCount[0];
     while (nchild > 0 && level < 64) {
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) bow_transform_kernel(const BowTreeView t,
             best = min(best, key);
         }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(kFullMask, best, o));
+        for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(halfMask, best, o));
         cur = t.childIds[base + (int)(best & 0xFFFFu)];
         if (level == nidLevel) nid = cur;
         nchild = t.childCount[cur];

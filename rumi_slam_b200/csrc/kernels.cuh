@@ -33,6 +33,7 @@ struct PyramidLevelArgs {
     const ResizeCoef* yc;    // [dst.h]
     int boxW, boxH;          // source box staged per tile (boxW multiple of 16)
     int nframes;
+    int* err;                // mapped host flag: set when the TMA transaction did not complete in time
 };
 
 void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap /* nullptr = plain loads */,
@@ -67,11 +68,10 @@ struct PyrMarchArgs {
     int levelFirst, levelLast; // destination levels produced by this launch (chained through the flags)
     int* flags;                // [frame][itemsPerFrame] completion epoch of every item
     int epoch;
+    int* err;                  // mapped host flag: set when a level dependency did not arrive in time
 };
 void launch_pyramid_march(const PyrMarchArgs& a, cudaStream_t s);
-int read_pyramid_wait_timeout_flag();
 
-int read_tma_timeout_flag();     // 1 = a TMA load timed out since the module was loaded, -1 = query failed
 void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s);
 
 // One FAST grid cell (R/lib_src/ORBextractor.cc:748-763): sub-image origin and size, clipped to the level border.
@@ -137,23 +137,18 @@ void launch_describe_given(const uint8_t* img, int w, int h, int stride, const K
 int match_slices(int nq, int nt);
 void launch_hamming_top2_partial(const uint8_t* Q, int nq, const uint8_t* T, int nt, int tBase, int slices,
                                  uint64_t* partial, cudaStream_t s);
-// tensor-core variant for large problems (match_imma.cu): descriptors expanded to 0/1 bytes, int8 IMMA dot products
-void launch_expand_bits(const uint8_t* D, int n, uint8_t* X /* [n][256] */, uint16_t* pop /* [n] or nullptr */,
-                        cudaStream_t s);
-int imma_slices(int nq, int nt);
 // K8-U (match_umma.cu): tcgen05.mma kind::i8 with TMEM accumulators, operands expanded in-kernel from the packed rows
 int umma_slices(int nq, int nt);
 size_t umma_train_bytes(int nt);        // scratch for the train set as ready-to-load operand tiles
 void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt, uint8_t* trainTiles, int tBase, int slices,
                               uint64_t* partial, cudaStream_t s);
-void launch_hamming_top2_imma(const uint8_t* Q, const uint8_t* Qx, int nq, const uint8_t* Tx, const uint16_t* popT,
-                              int nt, int tBase, int slices, uint64_t* partial, cudaStream_t s);
 // merge per-shard candidates {d1,d2,idx} gathered in shard order: cand[shard][nq]
 struct PairSegment { int32_t qStart, qCount, tStart, tCount; };   // one (query set, train set) pair of K8-S
 void launch_hamming_top2_segments(const uint8_t* Q, const uint8_t* T, const PairSegment* segs, int nseg, int maxQ,
                                   int32_t* idx1, uint16_t* d1, uint16_t* d2, cudaStream_t s);
 void launch_top2_merge(const uint64_t* packed, int nshards, int nq, int32_t* idx1, uint16_t* d1, uint16_t* d2,
                        cudaStream_t s);
+void launch_top2_merge_packed(const uint64_t* packed, int nshards, int nq, uint64_t* out, cudaStream_t s);
 void launch_pack_top2(const int32_t* idx1, const uint16_t* d1, const uint16_t* d2, int nq, uint64_t* packed,
                       cudaStream_t s);
 

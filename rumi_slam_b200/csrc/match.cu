@@ -177,6 +177,22 @@ __global__ void top2_merge_kernel(const uint64_t* __restrict__ packed, int nshar
     d2[qi] = (uint16_t)b2;
 }
 
+// Same fold, result kept in the packed candidate form: the local stage of a train-sharded match writes what the
+// all-gather sends (no separate pack launch).
+__global__ void top2_merge_packed_kernel(const uint64_t* __restrict__ packed, int nshards, int nq, uint64_t* __restrict__ out) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int b1 = 256, b2 = 256;
+    uint32_t i1 = 0xFFFFFFFFu;
+    for (int s = 0; s < nshards; ++s) {
+        const uint64_t p = packed[(size_t)s * nq + qi];
+        const int e1 = (int)(p >> 48), e2 = (int)((p >> 32) & 0xFFFF);
+        if (e1 < b1) { b2 = min(b1, e2); b1 = e1; i1 = (uint32_t)p; }
+        else b2 = min(b2, e1);
+    }
+    out[qi] = ((uint64_t)b1 << 48) | ((uint64_t)b2 << 32) | (uint64_t)i1;
+}
+
 __global__ void pack_top2_kernel(const int32_t* idx1, const uint16_t* d1, const uint16_t* d2, int nq,
                                  uint64_t* packed) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,6 +227,11 @@ void launch_top2_merge(const uint64_t* packed, int nshards, int nq, int32_t* idx
                        cudaStream_t s) {
     if (nq <= 0) return;
     top2_merge_kernel<<<(nq + 255) / 256, 256, 0, s>>>(packed, nshards, nq, idx1, d1, d2);
+}
+
+void launch_top2_merge_packed(const uint64_t* packed, int nshards, int nq, uint64_t* out, cudaStream_t s) {
+    if (nq <= 0) return;
+    top2_merge_packed_kernel<<<(nq + 255) / 256, 256, 0, s>>>(packed, nshards, nq, out);
 }
 
 void launch_pack_top2(const int32_t* idx1, const uint16_t* d1, const uint16_t* d2, int nq, uint64_t* packed,

@@ -1,5 +1,5 @@
 // K8-U: all-pairs 256-bit Hamming top-2 on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in
-// TMEM).  Same contract as K8 / K8-T (match.cu, match_imma.cu): per query the best and second-best
+// TMEM).  Same contract as K8 (match.cu): per query the best and second-best
 // ORBmatcher::DescriptorDistance (R/lib_src/ORBmatcher.cc:1830-1844) over the train set, earliest index among ties.
 //
 // Hamming(q, t) = pop(q) + pop(t) - 2 <q, t> on descriptors expanded to one byte per bit, so the pair loop is an int8

@@ -20,11 +20,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Set when a TMA transaction did not complete in time; checked by the host after synchronisation so that a lost
-// transaction becomes an error code instead of a hung GPU.
-__device__ int g_tma_timeout = 0;
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// A TMA transaction that does not complete in time sets the handle's mapped host flag `err`; the host reads it after
+// synchronisation, so a lost transaction becomes an error code instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
     uint32_t done = 0;
     int spins = 0;
     while (!done) {
@@ -35,7 +33,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1 << 20)) { atomicExch(&g_tma_timeout, 1); break; }
+        if (!done && ++spins > (1 << 20)) { *reinterpret_cast<volatile int*>(err) = 1; break; }
     }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
@@ -66,7 +64,7 @@ pyramid_level_kernel(const __grid_constant__ CUtensorMap tmap, const PyramidLeve
             mbar_expect_tx(&bar, (uint32_t)(boxW * boxH));
             tma_load_3d(box, &tmap, &bar, sx0, sy0, f);      // out-of-image part of the box is zero filled
         }
-        mbar_wait(&bar, 0);
+        mbar_wait(&bar, 0, a.err);
     } else {
         const uint8_t* s = a.src.ptr + (long long)f * a.src.pitch;
         for (int i = threadIdx.x; i < boxW * boxH; i += kPyrThreads) {
@@ -105,12 +103,6 @@ pyramid_level_kernel(const __grid_constant__ CUtensorMap tmap, const PyramidLeve
         }
         *reinterpret_cast<uchar4*>(d + (long long)dy * a.dst.stride + ox + cx) = o;   // dst rows are 16-B padded
     }
-}
-
-int read_tma_timeout_flag() {
-    int v = 0;
-    if (cudaMemcpyFromSymbol(&v, g_tma_timeout, sizeof(int)) != cudaSuccess) return -1;
-    return v;
 }
 
 void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap, cudaStream_t s) {

@@ -19,8 +19,6 @@
 
 namespace rumi {
 
-__device__ int g_pyr_wait_timeout = 0;
-
 __device__ __forceinline__ int ld_relaxed(const int* p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -77,7 +75,7 @@ __global__ void __launch_bounds__(kPyrMarchWarps * 32) pyramid_march_kernel(cons
             int spins = 0;
             while (ld_relaxed(fl) != a.epoch) {
                 __nanosleep(400);
-                if (++spins > (1 << 22)) { atomicExch(&g_pyr_wait_timeout, 1); break; }
+                if (++spins > (1 << 22)) { *reinterpret_cast<volatile int*>(a.err) = 1; break; }
             }
         }
         __threadfence();
@@ -146,12 +144,6 @@ __global__ void __launch_bounds__(kPyrMarchWarps * 32) pyramid_march_kernel(cons
         __syncwarp();
         if (lane == 0) st_relaxed(flags + item, a.epoch);
     }
-}
-
-int read_pyramid_wait_timeout_flag() {
-    int v = 0;
-    if (cudaMemcpyFromSymbol(&v, g_pyr_wait_timeout, sizeof(int)) != cudaSuccess) return -1;
-    return v;
 }
 
 void launch_pyramid_march(const PyrMarchArgs& a, cudaStream_t s) {

@@ -118,9 +118,15 @@ class ORBextractor:
                    torch.zeros((n, cap, 32), dtype=torch.uint8, device=dev),
                    torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.int32, device=dev))
         kps, desc, nkp, nmono = out
+        # the library runs on its own streams: order them behind torch's current stream (which produced `images` and
+        # zero-filled `out`) and, for asynchronous calls, order torch's stream behind the extraction
+        st = _lib.torch_stream()
+        check(self._L.rumi_orb_wait_stream(self._h, st))
         check(self._L.rumi_orb_extract_batch_device(self._h, ptr(images), n, w, h, images.stride(1), images.stride(0),
                                                     int(vLappingArea[0]), int(vLappingArea[1]), ptr(kps), ptr(desc),
                                                     cap, ptr(nkp), ptr(nmono), 1 if sync else 0))
+        if not sync:
+            check(self._L.rumi_orb_signal_stream(self._h, st))
         self._last_shape = (h, w)
         return kps, desc, nkp, nmono
 

@@ -38,8 +38,8 @@ class ORBmatcher:
             pass
 
     def last_path(self):
-        """Kernel of the last top-2 call: 'popc' (LOP3+POPC) or 'imma' (int8 tensor cores on expanded descriptors)."""
-        return {1: "popc", 2: "imma", 3: "umma"}.get(int(self._L.rumi_match_last_path(self._m)), "none")
+        """Kernel of the last top-2 call: 'popc' (LOP3+POPC) or 'umma' (tcgen05 int8 tensor cores, TMEM accumulators)."""
+        return {1: "popc", 3: "umma"}.get(int(self._L.rumi_match_last_path(self._m)), "none")
 
     @staticmethod
     def DescriptorDistance(a, b):
@@ -68,8 +68,46 @@ class ORBmatcher:
                    torch.empty(nq, dtype=torch.int16, device=Q.device),
                    torch.empty(nq, dtype=torch.int16, device=Q.device))
         i1, d1, d2 = out
+        st = _lib.torch_stream()                       # Q / T were produced on torch's stream, the results are used there
+        check(self._L.rumi_match_wait_stream(self._m, st))
         check(self._L.rumi_hamming_top2_device(self._m, ptr(Q), nq, ptr(T), nt, int(t_base), ptr(i1), ptr(d1), ptr(d2),
                                                1 if sync else 0))
+        if not sync:
+            check(self._L.rumi_match_signal_stream(self._m, st))
+        return i1, d1, d2
+
+    # ---- multi-GPU all-pairs top-2: train set sharded over the ranks, NCCL candidate all-gather ----
+    def comm_init(self, unique_id, rank, nranks):
+        """unique_id: the 128 bytes rank 0 got from ORBmatcher.nccl_unique_id(), distributed by the caller."""
+        buf = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert buf.size == 128
+        check(self._L.rumi_match_comm_init(self._m, ptr(buf), int(rank), int(nranks)))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = np.zeros(128, np.uint8)
+        check(_lib.lib().rumi_nccl_unique_id(ptr(buf)))
+        return buf.tobytes()
+
+    def top2_sharded(self, Q, T_local, t_base, out=None, sync=False):
+        """Q: all queries, replicated on every rank; T_local: this rank's contiguous train range starting at global row
+        t_base.  Every rank gets the global (idx1, d1, d2).  Scan, exchange and fold are enqueued on the matcher's
+        stream; torch's current stream is ordered behind them."""
+        import torch
+        assert Q.is_cuda and T_local.is_cuda and Q.dtype == torch.uint8 and T_local.dtype == torch.uint8
+        nq, nt = Q.shape[0], T_local.shape[0]
+        if out is None:
+            out = (torch.empty(nq, dtype=torch.int32, device=Q.device),
+                   torch.empty(nq, dtype=torch.int16, device=Q.device),
+                   torch.empty(nq, dtype=torch.int16, device=Q.device))
+        i1, d1, d2 = out
+        st = _lib.torch_stream()
+        check(self._L.rumi_match_wait_stream(self._m, st))
+        check(self._L.rumi_hamming_top2_sharded(self._m, ptr(Q), nq, ptr(T_local), nt, int(t_base), ptr(i1), ptr(d1),
+                                                ptr(d2), 1 if sync else 0))
+        if not sync:
+            check(self._L.rumi_match_signal_stream(self._m, st))
         return i1, d1, d2
 
     def pack_device(self, i1, d1, d2, out=None, sync=True):
@@ -77,7 +115,11 @@ class ORBmatcher:
         nq = i1.shape[0]
         if out is None:
             out = torch.empty(nq, dtype=torch.int64, device=i1.device)
+        st = _lib.torch_stream()
+        check(self._L.rumi_match_wait_stream(self._m, st))
         check(self._L.rumi_top2_pack_device(self._m, ptr(i1), ptr(d1), ptr(d2), nq, ptr(out), 1 if sync else 0))
+        if not sync:
+            check(self._L.rumi_match_signal_stream(self._m, st))
         return out
 
     def merge_device(self, packed, nshards, nq, out=None, sync=True):
@@ -87,8 +129,12 @@ class ORBmatcher:
                    torch.empty(nq, dtype=torch.int16, device=packed.device),
                    torch.empty(nq, dtype=torch.int16, device=packed.device))
         i1, d1, d2 = out
+        st = _lib.torch_stream()                       # `packed` may come from a collective on torch's stream
+        check(self._L.rumi_match_wait_stream(self._m, st))
         check(self._L.rumi_top2_merge_device(self._m, ptr(packed), int(nshards), int(nq), ptr(i1), ptr(d1), ptr(d2),
                                              1 if sync else 0))
+        if not sync:
+            check(self._L.rumi_match_signal_stream(self._m, st))
         return i1, d1, d2
 
     def timer_start(self):

@@ -20,17 +20,29 @@ def train_shard(n_train, rank, world):
     return frame_shard(n_train, rank, world)
 
 
-def sharded_top2(matcher, Q, T_local, t_base, group=None):
-    """Q: all queries (CUDA u8 [nq,32]) replicated on every rank; T_local: this rank's train rows; t_base: global
-    index of its first row.  Returns the global (idx1, d1, d2) on every rank."""
-    import torch
+def init_matcher_comm(matcher, group=None):
+    """Creates the matcher's own NCCL communicator over the ranks of `group`: rank 0 draws the NCCL unique id,
+    torch.distributed (any backend) only carries those 128 bytes to the other ranks."""
     import torch.distributed as dist
-    world = dist.get_world_size(group)
-    i1, d1, d2 = matcher.top2_device(Q, T_local, t_base=t_base, sync=False)
-    packed = matcher.pack_device(i1, d1, d2, sync=True)
-    gathered = torch.empty((world, Q.shape[0]), dtype=torch.int64, device=Q.device)
-    dist.all_gather_into_tensor(gathered.view(-1), packed, group=group)
-    return matcher.merge_device(gathered, world, Q.shape[0])
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [matcher.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    matcher.comm_init(box[0], rank, world)
+
+
+def sharded_top2(matcher, Q, T_local, t_base, out=None, sync=False):
+    """Q: all queries (CUDA u8 [nq,32]) replicated on every rank; T_local: this rank's train rows; t_base: global
+    index of its first row.  Returns the global (idx1, d1, d2) on every rank.  The whole exchange step lives in the
+    C ABI (rumi_hamming_top2_sharded: scan -> packed candidates -> ncclAllGather -> fold, all on the matcher's stream,
+    no host synchronisation); call init_matcher_comm once before."""
+    return matcher.top2_sharded(Q, T_local, t_base, out=out, sync=sync)
+
+
+def query_shard(n_query, rank, world):
+    """Small problems (a shard's scan is shorter than an exchange step) shard the QUERIES instead: every rank scans
+    its own query range against the whole train set with rumi_hamming_top2_device -- no exchange, no merge; the result
+    stays sharded by query."""
+    return frame_shard(n_query, rank, world)
 
 
 def merge_top2_host(parts):

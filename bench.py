@@ -7,10 +7,16 @@ One step = one pass of the hot path over one batch of synthetic frames (BASELINE
 640x480 frames, TUM ORB settings 1000/1.2/8/20/7).  Frames shard by frame across ranks with no data-path
 collective, each rank owning its own 1024-frame batch ("scaling": "weak").
 
-  value     frames/s over all ranks, inputs already resident in HBM, device-timed on the launching streams
-  e2e       same metric through ORBextractor.extract_batch (HOST pinned buffers; H2D + kernels + D2H timed)
-  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs the measured HBM peak
-  matching  cfg 5a (40 front + 40 back keyframes x 1000 descriptors, all-pairs top-2): matches/s and pairs/s
+  value       frames/s over all ranks, inputs already resident in HBM, device-timed on the launching streams
+  e2e         same metric through ORBextractor.extract_batch (HOST pinned buffers; H2D + kernels + D2H timed);
+              e2e.pageable = the same call on ordinary (pageable) host memory
+  parity      OUTSIDE the timed regions: sampled frames of both result sets, every query of cfg 5a, sampled queries of
+              cfg 5b and one stereo pair per shape are compared with the oracle; sharded == unsharded at N > 1
+  roofline    dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs the measured HBM peak
+  strong      literal configs[1]: ONE 1024-frame batch split over the N ranks (strong scaling)
+  matching    cfg 5a (40 front + 40 back keyframes x 1000 descriptors, all-pairs top-2): matches/s and pairs/s
+  matching_5b cfg 5b: 10^6 x 10^6, train set sharded over the ranks, candidate all-gather (NCCL) inside the C ABI
+  stereo_euroc / stereo_kitti   configs[2] / [3]: left + right extraction + Frame::ComputeStereoMatches, pairs/s
   cpu_baseline  the oracle (oracle/_ref = the unmodified reference ORBextractor.cc over a cv stub, when built;
                 else the C++ port) on the host cores, bounded sample
 
@@ -32,6 +38,8 @@ sys.path.insert(0, ROOT)
 W_IMG, H_IMG, NFEAT = 640, 480, 1000
 ORB = dict(nfeatures=NFEAT, scale=1.2, nlevels=8, ini=20, mn=7)
 METRIC = "ORB frames/sec (640x480, 1000 kp)"
+WORKLOAD = "ORB extraction, synthetic 640x480 frames (BASELINE configs[1]), 1000 features / 8 levels / 1.2 / FAST 20-7"
+NCU_PROFILE = os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")
 
 
 def level_sizes(w, h, nlevels=8, scale=1.2):
@@ -100,19 +108,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_extract_rate(frames, threads, seconds_hint=None):
-    """frames/s of the CPU reference path on `threads` host threads (ctypes releases the GIL)."""
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import orb_oracle, ref_lib
-    use_ref = ref_lib.available()
-    fn = ref_lib.extract if use_ref else orb_oracle.extract
-    orb_oracle.build()
-    fn(frames[0], **ORB)                                         # load + warm
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(lambda im: fn(im, **ORB), frames))
-    dt = time.perf_counter() - t0
-    return len(frames) / dt, ("reference" if use_ref else "port"), dt
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores
+# --------------------------------------------------------------------------------------------------------------------
+class CpuExtractor:
+    """The CPU reference path on a PERSISTENT pool of host threads (ctypes releases the GIL): oracle/_ref = the unmodified
+    reference ORBextractor.cc compiled over oracle/cvstub when it was built, else the C++ port."""
+
+    def __init__(self, threads, orb=None):
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import orb_oracle, ref_lib
+        self.orb = dict(ORB if orb is None else orb)
+        self.kind = "reference" if ref_lib.available() else "port"
+        self.fn = ref_lib.extract if self.kind == "reference" else orb_oracle.extract
+        orb_oracle.build()
+        self.threads = threads
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+
+    def run(self, frames):
+        """Extracts every frame once; returns seconds."""
+        t0 = time.perf_counter()
+        list(self.pool.map(lambda im: self.fn(im, **self.orb), frames, chunksize=1))
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.shutdown()
 
 
 def run_reference(args):
@@ -121,33 +141,34 @@ def run_reference(args):
         return
     from rumi_slam_b200.synth import synthetic_batch
     cores = len(os.sched_getaffinity(0))
-    per_step = max(2 * cores, 16)
-    frames = synthetic_batch(per_step, W_IMG, H_IMG, seed0=1000, unique=min(per_step, 16))
+    per_step = 40 * cores                      # >= 40 frames per thread per step: the pool runs at its steady rate
+    frames = synthetic_batch(per_step, W_IMG, H_IMG, seed0=1000, unique=min(per_step, 32))
+    cpu = CpuExtractor(cores)
+    cpu.run(frames[:2 * cores])                # load + first touch
     for _ in range(args.warmup):
-        cpu_extract_rate(frames[:cores], cores)
+        cpu.run(frames[:4 * cores])
     t0 = time.perf_counter()
-    kind = "port"
     for _ in range(args.steps):
-        _, kind, _ = cpu_extract_rate(frames, cores)
+        cpu.run(frames)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ORB extraction, synthetic 640x480 frames, 1000 features / 8 levels / 1.2 / FAST 20-7",
-                       "frames_per_step": per_step},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
-                             "sample": "%d frames per step on %d host threads; oracle/_ref = unmodified reference "
-                                       "ORBextractor.cc compiled over oracle/cvstub (cv2-pinned primitives)"
-                                       % (per_step, cores)},
+            "config": {"workload": WORKLOAD, "frames_per_step": per_step,
+                       "sample": "bounded sample of the 1024-frame batch: %d frames per step" % per_step},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
+                             "sample": "%d frames per step (40 per thread) on a persistent pool of %d host threads; "
+                                       "oracle/_ref = unmodified reference ORBextractor.cc compiled over oracle/cvstub "
+                                       "(cv2-pinned primitives)" % (per_step, cores)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cpu.close()
     print(json.dumps(line))
 
 
 def match_roofline(path, pairs_per_s, world, sm_mhz):
     """The top-2 kernels are bound by an execution pipe, not by HBM (operands are reused from shared memory):
-    popc: 5 POPC per pair at the measured 16 POPC/clk/SM; imma: 1/16 m16n8k32 IMMA per pair at the measured 0.478
-    warp-IMMA/clk/SM (tools/probe/pipe_probe.cu)."""
+    popc: 5 POPC per pair at the measured 16 POPC/clk/SM (tools/probe/pipe_probe.cu)."""
     if path == "umma":
         # peak: the nominal dense int8 rate, 4.5 POP/s per GPU.  ncu's own counter agrees with it: a capture at 2.69e12
         # pairs/s (1377 TOP/s) read sm__ops_path_tensor_op_utcimma_src_int8 = 30.4 % of peak
@@ -164,15 +185,8 @@ def match_roofline(path, pairs_per_s, world, sm_mhz):
                 "peak_pairs_per_s": peak, "frac": pairs_per_s / peak,
                 "peak_source": "nominal dense int8 4.5 POP/s per GPU (consistent with ncu's utcimma pct_of_peak)",
                 "frac_of_2x_measured_bf16": (pairs_per_s * 512 / 1e12) / (world * extra) if extra else None,
-                "note": "the top-2 epilogue (1 IMAD + min chain per pair on the CUDA cores) and the in-kernel bit expansion "
-                        "bound the kernel, not the tensor pipe (profiles/r1_summary.md)"}
-    if path == "imma":
-        peak = world * 148 * 0.478 * 16 * sm_mhz * 1e6
-        return {"bound": "imma-pipe", "imma_per_pair": 1.0 / 16, "imma_per_clk_per_sm": 0.478, "peak_pairs_per_s": peak,
-                "frac": pairs_per_s / peak,
-                "note": "int8 m16n8k32 on 0/1-expanded descriptors: 256 MACs per pair; rate measured by "
-                        "tools/probe/pipe_probe.cu; the b1 and.popc form lowers to the same IMMA with per-instruction "
-                        "unpacking (2.7 pairs/clk/SM, tools/probe/b1_probe.cu)"}
+                "note": "the top-2 epilogue (1 IMAD + min chain per pair on the CUDA cores) bounds the kernel, not the "
+                        "tensor pipe (profiles/r2_summary.md)"}
     peak = world * 148 * 16 * sm_mhz * 1e6 / 5
     return {"bound": "popc-pipe", "popc_per_pair": 5, "popc_per_clk_per_sm": 16, "peak_pairs_per_s": peak,
             "frac": pairs_per_s / peak,
@@ -202,12 +216,38 @@ def bind_to_gpu_numa_node(torch, local):
         return {"error": str(e)[:80]}
 
 
+def host_topology():
+    """NUMA / PCIe layout of the box (context for the e2e scaling curve: every rank's H2D shares the host links)."""
+    out = {}
+    try:
+        r = subprocess.run(["numactl", "-H"], capture_output=True, text=True, timeout=5)
+        out["numactl_H"] = [l for l in r.stdout.splitlines() if l.startswith(("available", "node")) and "size" not in l][:6]
+    except Exception:
+        try:
+            nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
+            out["numa_nodes"] = {n: open("/sys/devices/system/node/%s/cpulist" % n).read().strip() for n in nodes}
+        except Exception:
+            pass
+    try:
+        r = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10)
+        out["nvidia_smi_topo"] = [l for l in r.stdout.splitlines() if l.startswith("GPU")][:8]
+    except Exception:
+        pass
+    return out
+
+
+def kp_bytes_equal(dev_rows, ref):
+    """dev_rows: [cap,7] float32 view of 28-byte records; ref: KP_DTYPE array."""
+    raw = np.ascontiguousarray(dev_rows).view(np.uint8).reshape(-1, 28)[:len(ref)]
+    return np.array_equal(raw.reshape(-1).view(ref.dtype), ref)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from rumi_slam_b200 import ORBextractor, ORBmatcher
-    from rumi_slam_b200.sharding import sharded_top2, train_shard
-    from rumi_slam_b200.synth import synthetic_batch
+    from rumi_slam_b200 import KP_DTYPE, ORBextractor, ORBmatcher
+    from rumi_slam_b200.sharding import frame_shard, init_matcher_comm, query_shard, sharded_top2, train_shard
+    from rumi_slam_b200.synth import stereo_pair, synthetic_batch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,6 +258,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     nframes, chunk = args.frames, args.chunk
+    cores = len(os.sched_getaffinity(0))
+    check_oracle = not args.no_check
+    if check_oracle:
+        from oracle import orb_oracle
+        orb_oracle.build()
 
     def barrier():
         if world > 1:
@@ -231,8 +276,16 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks_true(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     # ---- host placement: run (and first-touch the pinned buffers) on the CPUs next to this rank's GPU ----
     numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
+    threads_here = max(1, len(os.sched_getaffinity(0)) // world)       # host threads this rank may use for the checks
 
     # ---- synthetic inputs: 1024 frames per rank, distinct seeds per rank ----
     host = synthetic_batch(nframes, W_IMG, H_IMG, seed0=10000 * rank, unique=args.unique)
@@ -243,6 +296,7 @@ def run_b200(args):
     out_dev = (torch.zeros((nframes, cap, 7), dtype=torch.float32, device=dev),
                torch.zeros((nframes, cap, 32), dtype=torch.uint8, device=dev),
                torch.zeros(nframes, dtype=torch.int32, device=dev), torch.zeros(nframes, dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     windows = []
 
@@ -278,12 +332,15 @@ def run_b200(args):
     stages = ex.profile_read(reset=True)
     ex.profile(False)
     ex.set_streams(0)
+    # leave the results of the PIPELINED configuration (what `value` timed) in out_dev for the parity check
+    for t in out_dev:
+        t.zero_()
+    ex.extract_batch_device(resident, out=out_dev, sync=True)
     ex.launch_count(reset=True)
     value = world * nframes * args.steps / (ms / 1e3)
     nkp_mean = float(out_dev[2].float().mean().item())
 
     # ---- e2e: host pinned buffers through the public batch call (H2D + kernels + D2H inside the timed region) ----
-    from rumi_slam_b200 import KP_DTYPE
     out_host = (torch.zeros((nframes, cap, 28), dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE).reshape(nframes, cap),
                 torch.zeros((nframes, cap, 32), dtype=torch.uint8).pin_memory().numpy(),
                 torch.zeros(nframes, dtype=torch.int32).pin_memory().numpy(),
@@ -302,20 +359,95 @@ def run_b200(args):
     ms_e2e = max_over_ranks(ms_e2e)
     launches_e2e = ex.launch_count(reset=True)
     e2e_value = world * nframes * args.steps / (ms_e2e / 1e3)
-    # raw host->device bandwidth of the same pinned buffer (context for e2e: 307 200 B per frame must cross PCIe)
+    d2h = int(ex.last_d2h_bytes()) if hasattr(ex, "last_d2h_bytes") else nframes * cap * (28 + 32) + 8 * nframes
+    # the same call on ordinary pageable host memory (what a caller holding cv::Mat images has): the driver stages the
+    # copies through its own pinned buffers
+    out_page = (np.zeros((nframes, cap), KP_DTYPE), np.zeros((nframes, cap, 32), np.uint8), np.zeros(nframes, np.int32),
+                np.zeros(nframes, np.int32))
+    ex.extract_batch(host, out=out_page)
+    barrier()
+    pg_steps = max(2, args.steps // 4)
+    t_a = time.perf_counter()
+    for _ in range(pg_steps):
+        ex.extract_batch(host, out=out_page)
+    torch.cuda.synchronize()
+    dt_page = max_over_ranks(time.perf_counter() - t_a)
+    barrier()
+    windows.append((t_a, time.perf_counter()))
+    e2e_pageable = world * nframes * pg_steps / dt_page
+    ex.launch_count(reset=True)
+    # raw host->device bandwidth of the same pinned buffer, all ranks copying at once (context for e2e: 307 200 B per
+    # frame must cross the host links; this is the ceiling of the e2e metric on this box)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scratch = torch.empty_like(resident)
     scratch.copy_(pinned, non_blocking=True)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record()
     for _ in range(3):
         scratch.copy_(pinned, non_blocking=True)
     ev1.record()
     torch.cuda.synchronize()
-    h2d_gbps = 3 * pinned.numel() / (ev0.elapsed_time(ev1) / 1e3) / 1e9
+    h2d_gbps = 3 * pinned.numel() / (max_over_ranks(ev0.elapsed_time(ev1)) / 1e3) / 1e9
     del scratch
     h2d = nframes * W_IMG * H_IMG
-    d2h = nframes * cap * (28 + 32) + 8 * nframes
+    ceiling = world * h2d_gbps * 1e9 / (W_IMG * H_IMG)
+
+    # ---- parity of what was just timed (outside every timed region): frames spread over all chunks / workspaces ----
+    parity = {"checked": False}
+    if check_oracle:
+        nsample = min(nframes, 128 if world == 1 else 64)
+        pick = np.unique(np.linspace(0, nframes - 1, nsample).astype(int))
+        ref = orb_oracle.extract_mt([host[i] for i in pick], threads=threads_here)
+        dk = out_dev[0][torch.from_numpy(pick).to(dev)].cpu().numpy()
+        dd = out_dev[1][torch.from_numpy(pick).to(dev)].cpu().numpy()
+        dn, dm = out_dev[2].cpu().numpy(), out_dev[3].cpu().numpy()
+        bad = []
+        for j, i in enumerate(pick):
+            rk, rd, rm = ref[j]
+            ok_dev = dn[i] == len(rk) and dm[i] == rm and kp_bytes_equal(dk[j], rk) and np.array_equal(dd[j, :len(rk)], rd)
+            ok_host = (out_host[2][i] == len(rk) and out_host[3][i] == rm and np.array_equal(out_host[0][i, :len(rk)], rk)
+                       and np.array_equal(out_host[1][i, :len(rk)], rd))
+            ok_page = (out_page[2][i] == len(rk) and np.array_equal(out_page[0][i, :len(rk)], rk)
+                       and np.array_equal(out_page[1][i, :len(rk)], rd))
+            if not (ok_dev and ok_host and ok_page):
+                bad.append((int(i), bool(ok_dev), bool(ok_host), bool(ok_page)))
+        parity = {"checked": True, "frames": int(len(pick)) * world, "chunks_covered": int(len(set(pick // chunk))),
+                  "device_path_ok": all_ranks_true(not any(not b[1] for b in bad)),
+                  "host_path_ok": all_ranks_true(not any(not b[2] for b in bad)),
+                  "pageable_path_ok": all_ranks_true(not any(not b[3] for b in bad)),
+                  "first_bad": bad[:3],
+                  "against": "oracle/orb_oracle.cpp (pinned to the unmodified reference ORBextractor.cc), keypoints incl. "
+                             "order, angles and descriptors bit for bit"}
+    del out_page
+
+    # ---- strong scaling, the literal configs[1]: ONE batch of 1024 frames split over the ranks ----
+    strong = None
+    if world > 1:
+        b, e = frame_shard(nframes, rank, world)
+        sub_dev, sub_host = resident[b:e], host_pinned[b:e]
+        sub_out = tuple(t[b:e] for t in out_dev)
+        sub_out_host = tuple(t[b:e] for t in out_host)
+        for _ in range(3):
+            ex.extract_batch_device(sub_dev, out=sub_out, sync=True)
+        barrier()
+        t_a = time.perf_counter()
+        ex.timer_start()
+        for _ in range(args.steps):
+            ex.extract_batch_device(sub_dev, out=sub_out, sync=False)
+        ms_s = max_over_ranks(ex.timer_stop())
+        barrier()
+        ex.extract_batch(sub_host, out=sub_out_host)
+        barrier()
+        ex.timer_start()
+        for _ in range(args.steps):
+            ex.extract_batch(sub_host, out=sub_out_host)
+        ms_se = max_over_ranks(ex.timer_stop())
+        barrier()
+        windows.append((t_a, time.perf_counter()))
+        strong = {"workload": "ONE batch of %d frames frame-sharded over %d GPUs (%d per GPU)" % (nframes, world, e - b),
+                  "scaling": "strong", "value": nframes * args.steps / (ms_s / 1e3), "e2e": nframes * args.steps / (ms_se / 1e3),
+                  "unit": "frames/s", "ms_per_step": ms_s / args.steps, "e2e_ms_per_step": ms_se / args.steps}
+        ex.launch_count(reset=True)
 
     # ---- single-frame latency of operator() (BASELINE configs[0]): host image in, keypoints + descriptors out ----
     latency = None
@@ -344,17 +476,23 @@ def run_b200(args):
     if world > 1:                                              # every rank must see the same Q / T
         dist.broadcast(Q, 0); dist.broadcast(T, 0)
     m = ORBmatcher(device=local)
+    if world > 1:
+        init_matcher_comm(m)                                   # the matcher's own NCCL communicator (C ABI)
     b, e = train_shard(nt, rank, world)
     T_local = T[b:e].contiguous()
+    res5a = (torch.empty(nq, dtype=torch.int32, device=dev), torch.empty(nq, dtype=torch.int16, device=dev),
+             torch.empty(nq, dtype=torch.int16, device=dev))
+    torch.cuda.synchronize()
 
     def match_once():
         if world == 1:
-            return m.top2_device(Q, T_local, t_base=b, sync=False)
-        return sharded_top2(m, Q, T_local, b)
+            return m.top2_device(Q, T_local, t_base=b, out=res5a, sync=False)
+        return sharded_top2(m, Q, T_local, b, out=res5a)
 
     for _ in range(3):
         match_once()
     barrier()
+    m.launch_count(reset=True)
     msteps = max(args.steps, 10)
     t_a = time.perf_counter()
     m.timer_start()
@@ -368,6 +506,183 @@ def run_b200(args):
     match_path = m.last_path()
     matches_per_s = nq * msteps / (ms_match / 1e3)
     pairs_per_s = matches_per_s * nt
+    matching = {"workload": "cfg 5a: 40000 x 40000 descriptors all-pairs top-2, train set sharded over %d GPU(s)%s"
+                            % (world, "" if world == 1 else ", NCCL candidate all-gather + fold inside rumi_hamming_top2_sharded"),
+                "matches_per_s": matches_per_s, "pairs_per_s": pairs_per_s, "ms_per_step": ms_match / msteps,
+                "gpu_launches": match_launches, "steps": msteps, "kernel": match_path}
+    # small problems can shard the QUERIES instead (no exchange, the result stays sharded by query)
+    if world > 1:
+        qb, qe = query_shard(nq, rank, world)
+        Qs = Q[qb:qe].contiguous()
+        outq = tuple(t[qb:qe] for t in (torch.empty_like(res5a[0]), torch.empty_like(res5a[1]), torch.empty_like(res5a[2])))
+        for _ in range(3):
+            m.top2_device(Qs, T, out=outq, sync=False)
+        barrier()
+        m.timer_start()
+        for _ in range(msteps):
+            m.top2_device(Qs, T, out=outq, sync=False)
+        ms_q = max_over_ranks(m.timer_stop())
+        barrier()
+        matching["query_sharded"] = {"pairs_per_s": float(nq) * nt * msteps / (ms_q / 1e3), "ms_per_step": ms_q / msteps,
+                                     "note": "each rank scans its own %d queries against all train rows; no exchange, "
+                                             "result sharded by query" % (qe - qb)}
+        m.launch_count(reset=True)
+    # parity + CPU baseline of the matching metric (rank 0): the reference's bit-hack DescriptorDistance scan
+    # (ORBmatcher.cc:1830-1844 inside :253-261) on 1 core (bounded sample) and on all cores (ALL queries = the parity check)
+    if check_oracle:
+        ok5a, cpu5a = True, None
+        if rank == 0:
+            q_np, t_np = Q.cpu().numpy(), T.cpu().numpy()
+            t0 = time.perf_counter()
+            orb_oracle.hamming_top2(q_np[:1500], t_np)
+            dt1 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ri, rd1, rd2 = orb_oracle.hamming_top2_mt(q_np, t_np, threads=cores)
+            dta = time.perf_counter() - t0
+            gi, g1, g2 = (x.cpu().numpy() for x in res5a)
+            ok5a = bool(np.array_equal(gi, ri) and np.array_equal(g1.astype(np.uint16), rd1) and np.array_equal(g2.astype(np.uint16), rd2))
+            if world > 1:                                      # sharded == unsharded on this GPU
+                ui, u1, u2 = m.top2_device(Q, T, sync=True)
+                ok5a = ok5a and bool(torch.equal(ui, res5a[0]) and torch.equal(u1, res5a[1]) and torch.equal(u2, res5a[2]))
+            cpu5a = {"value": float(nq) * nt / dta, "unit": "pairs/s", "cores": cores, "kind": "port",
+                     "matches_per_s": nq / dta, "single_thread_pairs_per_s": 1500.0 * nt / dt1,
+                     "sample": "all 40000 x 40000 pairs on %d host threads (%.1f s); 1 thread: 1500 x 40000 pairs (%.1f s); "
+                               "oracle/orb_oracle.cpp orc_hamming_top2 = the reference's SWAR DescriptorDistance in the "
+                               "best/second-best scan, -O2" % (cores, dta, dt1)}
+        matching["parity_ok"] = all_ranks_true(ok5a)
+        matching["parity"] = "all 40000 queries == oracle scan%s" % ("" if world == 1 else "; sharded == unsharded on rank 0")
+        matching["cpu_baseline"] = cpu5a
+
+    # ---- cfg 5b: 10^6 x 10^6 all-pairs top-2 (descriptors = extracted ones tiled with ~10 % of the bits flipped, so
+    #      true neighbours exist), train set sharded over the ranks, candidate all-gather inside the C ABI ----
+    match_big = None
+    if args.match_big > 0:
+        nbig = args.match_big
+        gen = torch.Generator(device=dev)
+        base = rows[:min(rows.shape[0], 80000)]
+
+        def tiled(n, seed):
+            gen.manual_seed(seed)
+            out = base.repeat(-(-n // base.shape[0]), 1)[:n].clone()
+            for c0 in range(0, n, 1 << 18):                        # flip ~10 % of the bits, chunked to bound memory
+                c1 = min(c0 + (1 << 18), n)
+                mask = torch.zeros((c1 - c0, 32), dtype=torch.uint8, device=dev)
+                for bit in range(8):
+                    mask |= (torch.rand((c1 - c0, 32), device=dev, generator=gen) < 0.1).to(torch.uint8) << bit
+                out[c0:c1] ^= mask
+            return out.contiguous()
+        Qb, Tb = tiled(nbig, 7), tiled(nbig, 8)
+        if world > 1:
+            dist.broadcast(Qb, 0); dist.broadcast(Tb, 0)
+        bb, eb = train_shard(nbig, rank, world)
+        Tb_local = Tb[bb:eb].contiguous()
+        resb = (torch.empty(nbig, dtype=torch.int32, device=dev), torch.empty(nbig, dtype=torch.int16, device=dev),
+                torch.empty(nbig, dtype=torch.int16, device=dev))
+        torch.cuda.synchronize()
+
+        def big_once():
+            if world == 1:
+                return m.top2_device(Qb, Tb_local, t_base=bb, out=resb, sync=False)
+            return sharded_top2(m, Qb, Tb_local, bb, out=resb)
+        big_once()
+        barrier()
+        bsteps = 3
+        t_a = time.perf_counter()
+        m.timer_start()
+        for _ in range(bsteps):
+            big_once()
+        ms_big = m.timer_stop()
+        barrier()
+        windows.append((t_a, time.perf_counter()))
+        ms_big = max_over_ranks(ms_big)
+        big_pairs = float(nbig) * nbig * bsteps / (ms_big / 1e3)
+        match_big = {"workload": "cfg 5b: %d x %d descriptors all-pairs top-2, train set sharded over %d GPU(s)" % (nbig, nbig, world),
+                     "pairs_per_s": big_pairs, "matches_per_s": nbig * bsteps / (ms_big / 1e3),
+                     "ms_per_step": ms_big / bsteps, "steps": bsteps, "kernel": m.last_path(),
+                     "roofline": match_roofline(m.last_path(), big_pairs, world, 1965.0)}
+        if check_oracle:
+            okb = True
+            if rank == 0:
+                pick = np.random.default_rng(5).choice(nbig, 2000, replace=False)
+                pk = torch.from_numpy(pick).to(dev)
+                ri, rd1, rd2 = orb_oracle.hamming_top2_mt(Qb[pk].cpu().numpy(), Tb.cpu().numpy(), threads=cores)
+                okb = bool(np.array_equal(resb[0][pk].cpu().numpy(), ri)
+                           and np.array_equal(resb[1][pk].cpu().numpy().astype(np.uint16), rd1)
+                           and np.array_equal(resb[2][pk].cpu().numpy().astype(np.uint16), rd2))
+                if world > 1:
+                    ui, u1, u2 = m.top2_device(Qb, Tb, sync=True)
+                    okb = okb and bool(torch.equal(ui, resb[0]) and torch.equal(u1, resb[1]) and torch.equal(u2, resb[2]))
+            match_big["parity_ok"] = all_ranks_true(okb)
+            match_big["parity"] = "2000 sampled queries == brute-force oracle scan of all %d train rows%s" % (
+                nbig, "" if world == 1 else "; sharded == unsharded (all queries) on rank 0")
+        del Qb, Tb, Tb_local, resb
+        m.launch_count(reset=True)
+
+    # ---- configs[2] / [3]: stereo frames.  Per pair, as Frame::Frame does (Frame.cc:116-119, 828-985): the left and the
+    #      right extractor run in two host threads on two handles, then ComputeStereoMatches on the device-resident
+    #      pyramids.  Host images in, mvKeys / descriptors / mvuRight / mvDepth out: an end-to-end figure. ----
+    def stereo_row(name, w, h, nf, fx, bf, npairs, unique):
+        from concurrent.futures import ThreadPoolExecutor
+        pairs = [stereo_pair(100 * rank + s, w, h) for s in range(unique)]
+        exl, exr = ORBextractor(nf, 1.2, 8, 20, 7, device=local), ORBextractor(nf, 1.2, 8, 20, 7, device=local)
+        ms_ = ORBmatcher(device=local)
+        pool = ThreadPoolExecutor(max_workers=2)
+
+        def one(i):
+            left, right = pairs[i % unique]
+            fl, fr = pool.submit(exl, left), pool.submit(exr, right)
+            (_, lk, ld), (_, rk, rd) = fl.result(), fr.result()
+            u, d, n = ms_.stereo_match(exl, exr, lk, ld, rk, rd, bf, bf / fx)
+            return lk, ld, rk, rd, u, d, n
+        for i in range(8):
+            one(i)
+        l0 = exl.launch_count(reset=True) + exr.launch_count(reset=True) + ms_.launch_count(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        nm = 0
+        for i in range(npairs):
+            nm += one(i)[6]
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        windows.append((t0, time.perf_counter()))
+        row = {"workload": "%s: %d synthetic %dx%d stereo pairs per GPU, %d features per image, left + right extraction "
+                           "(two handles, two host threads) + Frame::ComputeStereoMatches; host images in, results out"
+                           % (name, npairs, w, h, nf),
+               "pairs_per_s": world * npairs / dt, "frames_per_s": 2 * world * npairs / dt, "ms_per_pair": 1e3 * dt / npairs,
+               "mean_stereo_matches": nm / float(npairs),
+               "gpu_launches": exl.launch_count() + exr.launch_count() + ms_.launch_count(),
+               "timing": "host wall clock around synchronous calls (H2D, kernels, D2H inside), max over ranks"}
+        if check_oracle:
+            lk, ld, rk, rd, u, d, n = one(1)
+            left, right = pairs[1 % unique]
+            ok_, od_, om_ = orb_oracle.extract(left, nfeatures=nf)
+            ru, rdp, rn = orb_oracle.stereo_match(left, right, lk, ld, rk, rd, bf, bf / fx)
+            row["parity_ok"] = all_ranks_true(bool(np.array_equal(lk, ok_) and np.array_equal(ld, od_) and n == rn
+                                                   and np.array_equal(u, ru) and np.array_equal(d, rdp)))
+            if rank == 0 and world == 1 and not args.no_cpu:
+                cpu = CpuExtractor(cores, dict(nfeatures=nf, scale=1.2, nlevels=8, ini=20, mn=7))
+                nsamp = max(2 * cores, 8)
+
+                def cpu_pair(i):
+                    left, right = pairs[i % unique]
+                    a, bq = cpu.fn(left, **cpu.orb), cpu.fn(right, **cpu.orb)
+                    orb_oracle.stereo_match(left, right, a[0], a[1], bq[0], bq[1], bf, bf / fx)
+                cpu_pair(0)
+                t0 = time.perf_counter()
+                list(cpu.pool.map(cpu_pair, range(nsamp)))
+                dtc = time.perf_counter() - t0
+                cpu.close()
+                row["cpu_baseline"] = {"value": nsamp / dtc, "unit": "pairs/s", "cores": cores,
+                                       "kind": cpu.kind + " extraction + port of ComputeStereoMatches",
+                                       "sample": "%d of the same pairs on %d host threads (%.1f s)" % (nsamp, cores, dtc)}
+        exl.close(); exr.close(); ms_.close(); pool.shutdown()
+        return row
+
+    stereo = {}
+    if not args.no_stereo:
+        stereo["stereo_euroc"] = stereo_row("cfg 3 (EuRoC shape)", 752, 480, 1200, 435.2, 47.9, args.stereo_pairs, 8)
+        stereo["stereo_kitti"] = stereo_row("cfg 4 (KITTI shape)", 1241, 376, 2000, 718.856, 386.1448, args.stereo_pairs, 8)
 
     # ---- bag of words: Frame::ComputeBoW tree descent of this rank's descriptors on an ORBvoc-shaped vocabulary
     #      (k = 10, L = 6: 1 111 111 nodes, 10^6 words; synthetic because ORBvoc.txt is a missing blob) ----
@@ -386,7 +701,7 @@ def run_b200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(msteps):
-            voc.transform_features_device(feats, 4, sync=True)                # own stream, synchronised per call
+            voc.transform_features_device(feats, 4, sync=False)              # torch's stream is ordered behind each call
         ev1.record()
         torch.cuda.synchronize()
         barrier()
@@ -401,8 +716,10 @@ def run_b200(args):
             cpu_voc = bow_oracle.Vocabulary(10, 6, par, leaf, vdesc, vw)
             sample = feats[:100000].cpu().numpy()
             t0 = time.perf_counter()
-            cpu_voc.transform(sample, 4)
+            cw, _, cn = cpu_voc.transform(sample, 4)
             dt = time.perf_counter() - t0
+            gw, _, gn = voc.transform_features_device(feats[:100000].contiguous(), 4, sync=True)
+            bow["parity_ok"] = bool(np.array_equal(gw.cpu().numpy(), cw) and np.array_equal(gn.cpu().numpy(), cn))
             bow["cpu_baseline"] = {"value": len(sample) / dt, "unit": "features/s", "cores": 1, "kind": "port",
                                    "sample": "%d of the same descriptors, oracle/bow_oracle.cpp (pinned against the "
                                              "reference DBoW2), 1 thread, %.2f s" % (len(sample), dt)}
@@ -421,6 +738,7 @@ def run_b200(args):
         _, kp0, _ = exf(seq[0])
         exf.close()
         pts0 = np.stack([kp0["x"], kp0["y"]], 1).astype(np.float32)[:1000]
+
         def flow_pass():
             lk.set_prev(seq[0])
             cur, tracked = pts0, 0
@@ -438,7 +756,8 @@ def run_b200(args):
         windows.append((t_a, t_b))
         dt_flow = max_over_ranks((t_b - t_a) * 1e3) / 1e3
         flow = {"workload": "KFDSample::Step flow: %d consecutive 640x480 host frames, %d points each, "
-                            "calcOpticalFlowPyrLK(31x31, maxLevel 2, 20 it, eps 0.03), synchronous calls" % (nseq - 1, len(pts0)),
+                            "calcOpticalFlowPyrLK(31x31, maxLevel 2, 20 it, eps 0.03), synchronous calls; replicas only "
+                            "(sequential by construction)" % (nseq - 1, len(pts0)),
                 "frames_per_s": world * (nseq - 1) / dt_flow, "points_per_s": world * (nseq - 1) * len(pts0) / dt_flow,
                 "ms_per_call": dt_flow / (nseq - 1) * 1e3, "gpu_launches": lk.launches() - l0,
                 "tracked_fraction": tracked / float((nseq - 1) * len(pts0)),
@@ -463,49 +782,6 @@ def run_b200(args):
                 flow["cv2_frames_per_s_1_thread"] = 32 / (time.perf_counter() - t0)
             except Exception:
                 pass
-
-    # ---- optional cfg 5b: 10^6 x 10^6 all-pairs top-2 (descriptors = extracted ones tiled with ~10 % of the bits
-    #      flipped, so true neighbours exist), train set sharded over the ranks, NCCL all-gather of the candidates ----
-    match_big = None
-    if args.match_big > 0:
-        nbig = args.match_big
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(7)
-        base = rows[:min(rows.shape[0], 80000)]
-        def tiled(n, seed):
-            gen.manual_seed(seed)
-            out = base.repeat(-(-n // base.shape[0]), 1)[:n].clone()
-            for c0 in range(0, n, 1 << 18):                        # flip ~10 % of the bits, chunked to bound memory
-                c1 = min(c0 + (1 << 18), n)
-                mask = torch.zeros((c1 - c0, 32), dtype=torch.uint8, device=dev)
-                for bit in range(8):
-                    mask |= (torch.rand((c1 - c0, 32), device=dev, generator=gen) < 0.1).to(torch.uint8) << bit
-                out[c0:c1] ^= mask
-            return out.contiguous()
-        Qb, Tb = tiled(nbig, 7), tiled(nbig, 8)
-        if world > 1:
-            dist.broadcast(Qb, 0); dist.broadcast(Tb, 0)
-        bb, eb = train_shard(nbig, rank, world)
-        Tb_local = Tb[bb:eb].contiguous()
-        def big_once():
-            if world == 1:
-                return m.top2_device(Qb, Tb_local, t_base=bb, sync=False)
-            return sharded_top2(m, Qb, Tb_local, bb)
-        big_once()
-        barrier()
-        bsteps = 3
-        t_a = time.perf_counter()
-        m.timer_start()
-        for _ in range(bsteps):
-            big_once()
-        ms_big = m.timer_stop()
-        barrier()
-        windows.append((t_a, time.perf_counter()))
-        ms_big = max_over_ranks(ms_big)
-        match_big = {"workload": "cfg 5b: %d x %d descriptors all-pairs top-2, train set sharded over %d GPU(s)" % (nbig, nbig, world),
-                     "pairs_per_s": float(nbig) * nbig * bsteps / (ms_big / 1e3), "matches_per_s": nbig * bsteps / (ms_big / 1e3),
-                     "ms_per_step": ms_big / bsteps, "steps": bsteps}
-        del Qb, Tb, Tb_local
 
     if rank != 0:
         if world > 1:
@@ -538,13 +814,13 @@ def run_b200(args):
     # DRAM traffic of the dominant kernel per launch (one chunk) from the committed ncu --set full capture
     traffic, ncu_ctx = None, None
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")))
+        ncu = json.load(open(NCU_PROFILE))
         k = ncu["kernels"].get(dom)
         if k and ncu.get("frames_per_launch") == chunk:
             traffic = int(k["dram_read_bytes"] + k["dram_write_bytes"])
             ncu_ctx = {kk: k[kk] for kk in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "lsu_pipe_pct",
                                             "warps_active_pct", "warp_instructions") if kk in k}
-            ncu_ctx["source"] = "profiles/r1_ncu_kernels.json (ncu --set full, %d-frame chunk)" % chunk
+            ncu_ctx["source"] = "%s (ncu --set full, %d-frame chunk)" % (os.path.relpath(NCU_PROFILE, ROOT), chunk)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
@@ -562,36 +838,49 @@ def run_b200(args):
     # ---- CPU baseline on the host cores (bounded sample, rank 0, N == 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu:
-        cores = len(os.sched_getaffinity(0))
         sample = max(40 * cores, 64)
-        rate, kind, dt = cpu_extract_rate(host[:sample], cores)
-        rate1, _, dt1 = cpu_extract_rate(host[:48], 1)
-        cpu = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
+        pool = CpuExtractor(cores)
+        pool.run(host[:2 * cores])
+        dt = pool.run(host[:sample])
+        pool.close()
+        one = CpuExtractor(1)
+        dt1 = one.run(host[:48])
+        one.close()
+        cpu = {"value": sample / dt, "unit": "frames/s", "cores": cores, "kind": pool.kind,
                "sample": "%d of the same synthetic frames on %d host threads (%.1f s); 1 thread: %.1f frames/s"
-                         % (sample, cores, dt, rate1),
-               "single_thread": rate1}
+                         % (sample, cores, dt, 48 / dt1),
+               "single_thread": 48 / dt1}
 
+    if matching is not None:
+        matching["roofline"] = match_roofline(match_path, pairs_per_s, world, clocks.get("sm_mhz") or 1965.0)
+    parity_ok = bool(parity.get("device_path_ok", False) and parity.get("host_path_ok", False)
+                     and parity.get("pageable_path_ok", False)
+                     and (matching or {}).get("parity_ok", True) and (match_big or {}).get("parity_ok", True)
+                     and all(v.get("parity_ok", True) for v in stereo.values())) if check_oracle else None
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ORB extraction, batch of %d synthetic 640x480 frames per GPU (BASELINE configs[1]), "
-                                   "1000 features / 8 levels / 1.2 / FAST 20-7, frame-sharded" % nframes,
+            "config": {"workload": WORKLOAD + ", batch of %d frames per GPU, frame-sharded" % nframes,
                        "frames_per_gpu": nframes, "chunk_frames": chunk, "mean_keypoints_per_frame": nkp_mean,
+                       "distinct_frames": "%d generated per GPU, the rest are 2-D circular shifts of them" % args.unique,
                        "l2": "inputs (315 MB per GPU) exceed the 126 MB L2, no flush between steps",
-                       "host_binding": numa},
+                       "host_binding": numa, "host_topology": host_topology() if world > 1 else None},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_GBps_raw": round(h2d_gbps, 2),
-                    "frames_per_s_at_raw_h2d": round(world * h2d_gbps * 1e9 / (W_IMG * H_IMG), 1)},
+                    "frames_per_s_at_raw_h2d": round(ceiling, 1),
+                    "e2e_over_raw_h2d_ceiling": round(e2e_value / ceiling, 4),
+                    "pageable": {"value": e2e_pageable, "unit": "frames/s", "steps": pg_steps,
+                                 "note": "same call, ordinary pageable host arrays in and out"}},
+            "parity_checked_frames": parity.get("frames", 0), "parity_ok": parity_ok, "parity": parity,
             "gpu_launches": launches,
             "gpu_launches_e2e": launches_e2e,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "matching": {"workload": "cfg 5a: 40000 x 40000 descriptors all-pairs top-2, train set sharded over %d GPU(s)" % world,
-                         "matches_per_s": matches_per_s, "pairs_per_s": pairs_per_s, "ms_per_step": ms_match / msteps,
-                         "gpu_launches": match_launches, "steps": msteps,
-                         "kernel": match_path,
-                         "roofline": match_roofline(match_path, pairs_per_s, world, clocks.get("sm_mhz") or 1965.0)},
+            "strong": strong,
+            "matching": matching,
             "matching_5b": match_big,
+            "stereo_euroc": stereo.get("stereo_euroc"),
+            "stereo_kitti": stereo.get("stereo_kitti"),
             "bow": bow,
             "flow": flow,
             "single_frame_latency": latency,
@@ -630,11 +919,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("RUMI_CHUNK", "64")))
-    ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames generated per rank")
+    ap.add_argument("--unique", type=int, default=64, help="distinct synthetic frames generated per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bow", action="store_true")
     ap.add_argument("--no-flow", action="store_true")
-    ap.add_argument("--match-big", type=int, default=0, help="also run cfg 5b with this many descriptors per side (10^6)")
+    ap.add_argument("--no-stereo", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle parity checks (they run outside the timed regions)")
+    ap.add_argument("--stereo-pairs", type=int, default=256)
+    ap.add_argument("--match-big", type=int, default=1000000, help="cfg 5b descriptors per side (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

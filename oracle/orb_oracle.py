@@ -227,6 +227,31 @@ def hamming_top2(Q, T):
     return i1, d1, d2
 
 
+def hamming_top2_mt(Q, T, threads=None):
+    """hamming_top2 with the query rows split over host threads (ctypes releases the GIL): same result, used by the
+    benchmark-scale parity checks and as the all-cores CPU baseline of the matching metric."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    Q = np.ascontiguousarray(Q, np.uint8).reshape(-1, 32)
+    threads = threads or len(os.sched_getaffinity(0))
+    if threads <= 1 or len(Q) < 2 * threads:
+        return hamming_top2(Q, T)
+    cuts = np.linspace(0, len(Q), threads * 4 + 1).astype(int)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(lambda i: hamming_top2(Q[cuts[i]:cuts[i + 1]], T), range(len(cuts) - 1)))
+    return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+
+
+def extract_mt(frames, threads=None, **kw):
+    """extract() of many frames on host threads; returns a list of (kps, desc, mono)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    threads = threads or len(os.sched_getaffinity(0))
+    build()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(lambda im: extract(im, **kw), frames))
+
+
 def stereo_best1(Lk, Ld, Rk, Rd, scale_factors, n_rows, min_d, max_d):
     Lk = np.ascontiguousarray(Lk, KP_DTYPE)
     Rk = np.ascontiguousarray(Rk, KP_DTYPE)

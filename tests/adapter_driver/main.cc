@@ -1,0 +1,85 @@
+// Test driver: runs the reference-signature C++ classes (rumi_slam_b200/adapter) on raw image files and dumps what a
+// Frame constructor would receive, so that tests/test_adapter_gpu.py can compare it with the oracle.
+//   adapter_driver <out.bin> <w> <h> <nfeatures> <lap0> <lap1> <left.raw> [<right.raw> <mbf> <mb>]
+// out.bin: int32 mono, nkp, then nkp x 28 B keypoints, nkp x 32 B descriptors, int32 nlevels, per level int32 w, h and
+// the level's pixels (mvImagePyramid); with a right image: the same block for the right frame, then int32 nmatches,
+// nL floats mvuRight, nL floats mvDepth (Frame::ComputeStereoMatches through ORBmatcherAccel).
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <thread>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "ORBmatcher_accel.h"
+
+static cv::Mat load(const char* path, int w, int h) {
+    cv::Mat m(h, w, CV_8UC1);
+    FILE* f = std::fopen(path, "rb");
+    if (!f) throw std::runtime_error("cannot open image");
+    for (int y = 0; y < h; ++y)
+        if (std::fread(m.ptr(y), 1, (size_t)w, f) != (size_t)w) throw std::runtime_error("short image file");
+    std::fclose(f);
+    return m;
+}
+
+struct Result {
+    int mono = 0;
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat desc;
+};
+
+static void dump(FILE* f, ORB_SLAM3::ORBextractor& ex, const Result& r) {
+    const int nkp = (int)r.keys.size();
+    std::fwrite(&r.mono, 4, 1, f);
+    std::fwrite(&nkp, 4, 1, f);
+    std::fwrite(r.keys.data(), 28, (size_t)nkp, f);
+    for (int i = 0; i < nkp; ++i) std::fwrite(r.desc.ptr(i), 1, 32, f);
+    const int nl = ex.GetLevels();
+    std::fwrite(&nl, 4, 1, f);
+    for (int l = 0; l < nl; ++l) {
+        const cv::Mat& m = ex.mvImagePyramid[l];
+        std::fwrite(&m.cols, 4, 1, f);
+        std::fwrite(&m.rows, 4, 1, f);
+        for (int y = 0; y < m.rows; ++y) std::fwrite(m.ptr(y), 1, (size_t)m.cols, f);
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 8) return 2;
+    try {
+        const int w = std::atoi(argv[2]), h = std::atoi(argv[3]), nf = std::atoi(argv[4]);
+        std::vector<int> lap = {std::atoi(argv[5]), std::atoi(argv[6])};
+        const bool stereo = argc >= 11;
+        cv::Mat left = load(argv[7], w, h), right;
+        if (stereo) right = load(argv[8], w, h);
+        ORB_SLAM3::ORBextractor exL(nf, 1.2f, 8, 20, 7), exR(nf, 1.2f, 8, 20, 7);
+        Result L, R;
+        // Frame.cc:116-119: the two extractors run in two threads
+        std::thread tl([&] { L.mono = exL(left, cv::Mat(), L.keys, L.desc, lap); });
+        std::thread tr([&] { if (stereo) R.mono = exR(right, cv::Mat(), R.keys, R.desc, lap); });
+        tl.join(); tr.join();
+        FILE* f = std::fopen(argv[1], "wb");
+        if (!f) return 3;
+        dump(f, exL, L);
+        if (stereo) {
+            dump(f, exR, R);
+            ORB_SLAM3::ORBmatcherAccel m;
+            std::vector<float> uR, depth;
+            const int n = m.ComputeStereoMatches(exL.Handle(), exR.Handle(), L.keys, L.desc, R.keys, R.desc,
+                                                 (float)std::atof(argv[9]), (float)std::atof(argv[10]), uR, depth);
+            std::fwrite(&n, 4, 1, f);
+            std::fwrite(uR.data(), 4, uR.size(), f);
+            std::fwrite(depth.data(), 4, depth.size(), f);
+        }
+        // the empty-image contract of operator() (ORBextractor.cc:1017)
+        cv::Mat empty; Result E;
+        const int e = exL(empty, cv::Mat(), E.keys, E.desc, lap);
+        std::fwrite(&e, 4, 1, f);
+        std::fclose(f);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "adapter_driver: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,82 @@
+"""The C++ adapter EXECUTES on the GPU: a g++-built driver calls ORB_SLAM3::ORBextractor::operator() (two instances in
+two threads, as Frame.cc:116-119 does) and ORBmatcherAccel::ComputeStereoMatches through rumi_slam_b200/adapter ->
+C ABI -> CUDA kernels, and its output is compared bit for bit with the oracle: keypoints (order included), descriptors,
+monoIndex, the public mvImagePyramid, mvuRight / mvDepth."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from rumi_slam_b200.synth import stereo_pair, synthetic_frame
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    from rumi_slam_b200 import _lib
+    _lib.lib()
+    ad = os.path.join(ROOT, "rumi_slam_b200", "adapter")
+    exe = tmp_path_factory.mktemp("adapter") / "adapter_driver"
+    # OpenCV headers are absent in this image: oracle/cvstub provides cv::Mat / cv::KeyPoint (containers only; with a
+    # real OpenCV the same sources build unchanged)
+    cmd = ["g++", "-std=c++14", "-O1", "-pthread", "-I", os.path.join(ROOT, "oracle", "cvstub"), "-I", ad,
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "adapter_driver", "main.cc"),
+           os.path.join(ad, "ORBextractor.cc"), os.path.join(ad, "ORBmatcher_accel.cc"), "-o", str(exe),
+           "-L", os.path.join(ROOT, "rumi_slam_b200"), "-lrumi_orb", "-Wl,-rpath," + os.path.join(ROOT, "rumi_slam_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return str(exe)
+
+
+def read_frame(buf, off, kp_dtype):
+    mono, nkp = np.frombuffer(buf, np.int32, 2, off); off += 8
+    kps = np.frombuffer(buf, kp_dtype, nkp, off).copy(); off += 28 * nkp
+    desc = np.frombuffer(buf, np.uint8, 32 * nkp, off).reshape(nkp, 32).copy(); off += 32 * nkp
+    nl = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    pyr = []
+    for _ in range(nl):
+        w, h = np.frombuffer(buf, np.int32, 2, off); off += 8
+        pyr.append(np.frombuffer(buf, np.uint8, w * h, off).reshape(h, w).copy()); off += w * h
+    return int(mono), kps, desc, pyr, off
+
+
+@pytest.mark.parametrize("lap", [(0, 0), (0, 1000)])
+def test_operator_call_through_cpp_adapter(oracle, driver, tmp_path, lap):
+    img = synthetic_frame(77, 640, 480)
+    (tmp_path / "l.raw").write_bytes(img.tobytes())
+    out = tmp_path / "out.bin"
+    r = subprocess.run([driver, str(out), "640", "480", "1000", str(lap[0]), str(lap[1]), str(tmp_path / "l.raw")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = out.read_bytes()
+    mono, kps, desc, pyr, off = read_frame(buf, 0, oracle.KP_DTYPE)
+    rk, rd, rmono = oracle.extract(img, lapping=lap)
+    assert mono == rmono and np.array_equal(kps, rk) and np.array_equal(desc, rd)
+    for got, want in zip(pyr, oracle.pyramid(img)):
+        assert np.array_equal(got, want)
+    assert np.frombuffer(buf, np.int32, 1, off)[0] == -1          # empty image -> -1
+
+
+def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
+    left, right = stereo_pair(4, 752, 480)
+    (tmp_path / "l.raw").write_bytes(left.tobytes())
+    (tmp_path / "r.raw").write_bytes(right.tobytes())
+    out = tmp_path / "out.bin"
+    fx, bf = 435.2, 47.9
+    r = subprocess.run([driver, str(out), "752", "480", "1200", "0", "0", str(tmp_path / "l.raw"), str(tmp_path / "r.raw"),
+                        repr(bf), repr(bf / fx)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = out.read_bytes()
+    lm, lk, ld, lp, off = read_frame(buf, 0, oracle.KP_DTYPE)
+    rm, rk, rd, rp, off = read_frame(buf, off, oracle.KP_DTYPE)
+    for (mono, k, d), img in (((lm, lk, ld), left), ((rm, rk, rd), right)):
+        ok, od, omono = oracle.extract(img, nfeatures=1200)
+        assert mono == omono and np.array_equal(k, ok) and np.array_equal(d, od)
+    n = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    u = np.frombuffer(buf, np.float32, len(lk), off); off += 4 * len(lk)
+    dep = np.frombuffer(buf, np.float32, len(lk), off)
+    ru, rdp, rn = oracle.stereo_match(left, right, lk, ld, rk, rd, bf, bf / fx)      # double -> float at the C boundary, both sides
+    assert n == rn and n > 100 and np.array_equal(u, ru) and np.array_equal(dep, rdp)

@@ -163,24 +163,34 @@ def test_other_shapes_and_pyramid_parameters(oracle, w, h, nf, levels, scale):
         assert np.array_equal(bk[i, :nkp[i]], rk) and np.array_equal(bd[i, :nkp[i]], rd)
 
 
-def test_staged_host_pipeline_equals_default():
-    """RUMI_STAGED=1 (copy streams + 3 staging buffers + 2 workspaces; an experiment kept as a switch) returns exactly
-    what the default host-batch pipeline returns, on a ragged 5-chunk batch."""
-    import os
+def test_benchmark_pipeline_matches_oracle(oracle):
+    """What bench.py times is what is tested: a 256-frame batch in chunks of 64 (the marching / strip pyramid, every
+    workspace and stream of the pipeline in use) through BOTH public batch calls -- device-resident (2 workspaces) and
+    host buffers (4 workspaces, H2D + D2H inside) -- every frame compared with the oracle, keypoint order included."""
+    import torch
     from rumi_slam_b200 import ORBextractor
-    from rumi_slam_b200.synth import synthetic_batch
-    frames = synthetic_batch(37, 640, 480, seed0=900, unique=6)
-    outs = []
-    for staged in ("0", "1"):
-        os.environ["RUMI_STAGED"] = staged
-        try:
-            ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=8)
-        finally:
-            os.environ.pop("RUMI_STAGED", None)
-        k, d, n, m = ex.extract_batch(frames)
-        outs.append((k.copy(), d.copy(), n.copy(), m.copy()))
-        ex.close()
-    (k0, d0, n0, m0), (k1, d1, n1, m1) = outs
-    assert np.array_equal(n0, n1) and np.array_equal(m0, m1) and n0.min() > 900
-    for f in range(len(frames)):                       # rows beyond a frame's count are scratch
-        assert np.array_equal(k0[f, :n0[f]], k1[f, :n0[f]]) and np.array_equal(d0[f, :n0[f]], d1[f, :n0[f]]), f
+    n, w, h = 256, 640, 480
+    frames = synthetic_batch(n, w, h, seed0=3000, unique=48)
+    ref = oracle.extract_mt(frames)                          # 256 oracle extractions on the host threads
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=64)
+    dev_in = torch.from_numpy(frames).cuda()
+    for rep in range(2):                                     # second pass: workspaces are reused
+        dk, dd, dn, dm = ex.extract_batch_device(dev_in, sync=False)
+    torch.cuda.synchronize()
+    dk = dk.cpu().numpy().view(np.uint8).reshape(n, -1, 28)
+    dd, dn, dm = dd.cpu().numpy(), dn.cpu().numpy(), dm.cpu().numpy()
+    hk, hd, hn, hm = ex.extract_batch(frames)
+    for i in range(n):
+        rk, rd, rm = ref[i]
+        assert dn[i] == len(rk) == hn[i] and dm[i] == rm == hm[i], i
+        assert np.array_equal(dk[i, :len(rk)].reshape(-1).view(rk.dtype), rk), "device path, frame %d" % i
+        assert np.array_equal(dd[i, :len(rk)], rd), "device path descriptors, frame %d" % i
+        assert np.array_equal(hk[i, :len(rk)], rk) and np.array_equal(hd[i, :len(rk)], rd), "host path, frame %d" % i
+    # ragged tail + pageable (non-pinned) host memory + a second shape on the same handle
+    frames2 = synthetic_batch(70, 752, 480, seed0=3100, unique=10)
+    ex2 = ORBextractor(1200, 1.2, 8, 20, 7, max_batch=64)
+    k2, d2, n2, m2 = ex2.extract_batch(frames2)
+    ref2 = oracle.extract_mt(frames2, nfeatures=1200)
+    for i in range(70):
+        rk, rd, rm = ref2[i]
+        assert n2[i] == len(rk) and m2[i] == rm and np.array_equal(k2[i, :len(rk)], rk) and np.array_equal(d2[i, :len(rk)], rd), i

@@ -44,6 +44,7 @@ def lib():
         L.orc_fast.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, f32p, C.c_int]
         L.orc_grid_fast.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, f32p, C.c_int, i32p]
         L.orc_octree.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int]
+        L.orc_octree_stable.argtypes = L.orc_octree.argtypes
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_fast_atan2.restype = C.c_float
         L.orc_ic_angle.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int]
@@ -143,6 +144,15 @@ def octree(xyr, min_x, max_x, min_y, max_y, n_target):
     cap = n_target + 16 + len(xyr)
     sel = np.zeros(cap, np.int32)
     n = lib().orc_octree(_p(xyr, C.c_float), len(xyr), min_x, max_x, min_y, max_y, n_target, _p(sel, C.c_int32), cap)
+    return sel[:n]
+
+
+def octree_stable(xyr, min_x, max_x, min_y, max_y, n_target):
+    """NOT the reference's behaviour: final phase sorted with std::stable_sort (tie-sensitivity census only)."""
+    xyr = np.ascontiguousarray(xyr, np.float32)
+    cap = n_target + 16 + len(xyr)
+    sel = np.zeros(cap, np.int32)
+    n = lib().orc_octree_stable(_p(xyr, C.c_float), len(xyr), min_x, max_x, min_y, max_y, n_target, _p(sel, C.c_int32), cap)
     return sel[:n]
 
 

@@ -1,0 +1,169 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/_ref/librefframe.so.
+
+librefframe.so = reference functions of Frame.cc / MapPoint.cc / ORBmatcher.cc cut out of /root/reference at build time
+and compiled UNMODIFIED over class stand-ins (oracle/ref_frame_shim.cpp, oracle/extract_ref.py, `make -C oracle refframe`).
+Built only where /root/reference exists; travels to the GPU box as a prebuilt file.  Pins the oracle's restatements of
+ComputeStereoMatches, ComputeDistinctiveDescriptors, both SearchByBoW overloads, GetFeaturesInArea,
+SearchForInitialization and SearchByProjection.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .orb_oracle import KP_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "librefframe.so")
+REF_SRC = "/root/reference/src/rumi-slam/lib_src/Frame.cc"
+
+_u8p, _f32p, _i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+
+def build():
+    if os.path.exists(REF_SRC):
+        subprocess.check_call(["make", "-C", _HERE, "refframe"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_LIB)
+
+
+def available():
+    return os.path.exists(_LIB) or build()
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/librefframe.so not built (reference sources absent)")
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def stereo_match(pyrL, pyrR, Lk, Ld, Rk, Rd, scale, inv_scale, mbf, mb):
+    """Frame::ComputeStereoMatches on the given pyramids (lists of dense u8 levels): (mvuRight, mvDepth, kept)."""
+    n = len(pyrL)
+    keepL = [np.ascontiguousarray(a, np.uint8) for a in pyrL]
+    keepR = [np.ascontiguousarray(a, np.uint8) for a in pyrR]
+    PL = (C.c_void_p * n)(*[a.ctypes.data for a in keepL])
+    PR = (C.c_void_p * n)(*[a.ctypes.data for a in keepR])
+    lw = np.array([a.shape[1] for a in keepL], np.int32)
+    lh = np.array([a.shape[0] for a in keepL], np.int32)
+    Lk, Rk = np.ascontiguousarray(Lk, KP_DTYPE), np.ascontiguousarray(Rk, KP_DTYPE)
+    Ld, Rd = np.ascontiguousarray(Ld, np.uint8), np.ascontiguousarray(Rd, np.uint8)
+    sc, isc = np.ascontiguousarray(scale, np.float32), np.ascontiguousarray(inv_scale, np.float32)
+    u, d = np.zeros(len(Lk), np.float32), np.zeros(len(Lk), np.float32)
+    L = lib()
+    L.ref_stereo_match.argtypes = [C.c_void_p, C.c_void_p, _i32p, _i32p, C.c_int, C.c_void_p, _u8p, C.c_int, C.c_void_p,
+                                   _u8p, C.c_int, _f32p, _f32p, C.c_float, C.c_float, _f32p, _f32p]
+    kept = L.ref_stereo_match(PL, PR, _p(lw, _i32p), _p(lh, _i32p), n, Lk.ctypes.data, _p(Ld, _u8p), len(Lk),
+                              Rk.ctypes.data, _p(Rd, _u8p), len(Rk), _p(sc, _f32p), _p(isc, _f32p), float(mbf), float(mb),
+                              _p(u, _f32p), _p(d, _f32p))
+    return u, d, kept
+
+
+def distinctive(desc):
+    """MapPoint::ComputeDistinctiveDescriptors for one map point: the 32 bytes the reference stores in mDescriptor."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    out = np.zeros(32, np.uint8)
+    L = lib()
+    L.ref_distinctive.argtypes = [_u8p, C.c_int, _u8p]
+    rc = L.ref_distinctive(_p(desc, _u8p), len(desc), _p(out, _u8p))
+    return None if rc else out
+
+
+def descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8).reshape(32), np.ascontiguousarray(b, np.uint8).reshape(32)
+    L = lib()
+    L.ref_descriptor_distance.argtypes = [_u8p, _u8p]
+    return L.ref_descriptor_distance(_p(a, _u8p), _p(b, _u8p))
+
+
+def _nodes(fv, n):
+    node = np.full(max(n, 1), -1, np.int32)
+    for nid, idx in fv.items():
+        for i in idx:
+            node[i] = nid
+    return node
+
+
+def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...).  fv_*: {node id: [feature indices in ascending order]} (the order
+    DBoW2::FeatureVector::addFeature produces when features are added by ascending index).  (nmatches, matchF)."""
+    dk, df = np.ascontiguousarray(desc_kf, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+    ak, af = np.ascontiguousarray(angle_kf, np.float32), np.ascontiguousarray(angle_f, np.float32)
+    vk = np.ascontiguousarray(kf_valid, np.uint8)
+    nk, nf = _nodes(fv_kf, len(dk)), _nodes(fv_f, len(df))
+    match = np.zeros(max(len(df), 1), np.int32)
+    L = lib()
+    L.ref_search_by_bow.argtypes = [_u8p, _f32p, _u8p, _i32p, C.c_int, _u8p, _f32p, _i32p, C.c_int, C.c_float, C.c_int, _i32p]
+    n = L.ref_search_by_bow(_p(dk, _u8p), _p(ak, _f32p), _p(vk, _u8p), _p(nk, _i32p), len(dk), _p(df, _u8p), _p(af, _f32p),
+                            _p(nf, _i32p), len(df), float(nnratio), 1 if check_ori else 0, _p(match, _i32p))
+    return n, match[:len(df)]
+
+
+def search_by_bow_kf(desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, nnratio=0.8, check_ori=True):
+    d1, d2 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+    a1, a2 = np.ascontiguousarray(angle1, np.float32), np.ascontiguousarray(angle2, np.float32)
+    v1, v2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+    n1, n2 = _nodes(fv1, len(d1)), _nodes(fv2, len(d2))
+    match = np.zeros(max(len(d1), 1), np.int32)
+    L = lib()
+    L.ref_search_by_bow_kf.argtypes = [_u8p, _f32p, _u8p, _i32p, C.c_int, _u8p, _f32p, _u8p, _i32p, C.c_int, C.c_float, C.c_int,
+                                       _i32p]
+    n = L.ref_search_by_bow_kf(_p(d1, _u8p), _p(a1, _f32p), _p(v1, _u8p), _p(n1, _i32p), len(d1), _p(d2, _u8p), _p(a2, _f32p),
+                               _p(v2, _u8p), _p(n2, _i32p), len(d2), float(nnratio), 1 if check_ori else 0, _p(match, _i32p))
+    return n, match[:len(d1)]
+
+
+def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea on the grid AssignFeaturesToGrid builds; bounds = (mnMinX, mnMinY, mnMaxX, mnMaxY)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    L = lib()
+    L.ref_features_in_area.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                       C.c_int, C.c_int, _i32p, C.c_int]
+    n = L.ref_features_in_area(kps.ctypes.data, len(kps), *[int(b) for b in bounds], float(x), float(y), float(r),
+                               int(min_level), int(max_level), _p(out, _i32p), len(out))
+    return out[:n].copy()
+
+
+def search_for_initialization(k1, d1, k2, d2, bounds, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization: (nmatches, vnMatches12, updated vbPrevMatched)."""
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.zeros(max(len(k1), 1), np.int32)
+    L = lib()
+    L.ref_search_for_initialization.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, _f32p, C.c_int, C.c_float, C.c_int, _i32p]
+    n = L.ref_search_for_initialization(k1.ctypes.data, _p(d1, _u8p), len(k1), k2.ctypes.data, _p(d2, _u8p), len(k2),
+                                        *[int(b) for b in bounds], _p(prev, _f32p), int(window), float(nnratio),
+                                        1 if check_ori else 0, _p(m12, _i32p))
+    return n, m12[:len(k1)], prev
+
+
+def search_by_projection(kF, dF, scale_factors, bounds, proj, level, view_cos, dMP, has_obs, th=3.0, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) on a mono frame: (nmatches, frameMatch[j] = map point)."""
+    kF = np.ascontiguousarray(kF, KP_DTYPE)
+    dF, dMP = np.ascontiguousarray(dF, np.uint8).reshape(-1, 32), np.ascontiguousarray(dMP, np.uint8).reshape(-1, 32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    proj = np.ascontiguousarray(proj, np.float32)
+    level = np.ascontiguousarray(level, np.int32)
+    vc = np.ascontiguousarray(view_cos, np.float32)
+    ho = np.ascontiguousarray(has_obs, np.uint8)
+    out = np.zeros(max(len(kF), 1), np.int32)
+    L = lib()
+    L.ref_search_by_projection.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p,
+                                           _i32p, _f32p, _u8p, _u8p, C.c_int, C.c_float, C.c_float, _i32p]
+    n = L.ref_search_by_projection(kF.ctypes.data, _p(dF, _u8p), len(kF), _p(sf, _f32p), len(sf), *[int(b) for b in bounds],
+                                   _p(proj, _f32p), _p(level, _i32p), _p(vc, _f32p), _p(dMP, _u8p), _p(ho, _u8p), len(dMP),
+                                   float(th), float(nnratio), _p(out, _i32p))
+    return n, out[:len(kF)]

@@ -41,6 +41,7 @@ def lib():
         L.ref_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, u8p, C.c_int, i32p, i32p]
         L.ref_octree.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int]
+        L.ref_describe.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, u8p]
         L.ref_tables.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, f32p]
         _lib = L
     return _lib
@@ -58,6 +59,17 @@ def extract(img, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7, lapping=(0,
     if rc != 0:
         return None
     return kps[:n.value].copy(), desc[:n.value].copy(), m.value
+
+
+def describe(img, kps):
+    """The reference's ORBextractor::CloudFrameComputeDescriptors: (return value, descriptors)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.zeros((len(kps), 32), np.uint8)
+    h, w = (img.shape if img.ndim == 2 and img.size else (0, 0))
+    rc = lib().ref_describe(img.ctypes.data_as(C.POINTER(C.c_uint8)), w, h, img.strides[0] if img.size else 0,
+                            kps.ctypes.data, len(kps), desc.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return rc, desc
 
 
 def octree(xyr, min_x, max_x, min_y, max_y, n_target):

@@ -79,6 +79,22 @@ int ref_extract(const uint8_t* img, int W, int H, size_t stride, int nfeatures, 
     return 0;
 }
 
+// ORBextractor::CloudFrameComputeDescriptors(image, keypoints, descriptors)  (R/lib_src/ORBextractor.cc:989-1011)
+int ref_describe(const uint8_t* img, int W, int H, size_t stride, const void* kps, int n, uint8_t* desc) {
+    cv::Mat image;
+    if (img && W > 0 && H > 0) {
+        image = cv::Mat(H, W, CV_8UC1);
+        for (int y = 0; y < H; ++y) std::memcpy(image.ptr(y), img + (size_t)y * stride, W);
+    }
+    ORB_SLAM3::ORBextractor ex(1000, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> k(n);
+    if (n) std::memcpy((void*)k.data(), kps, (size_t)n * 28);
+    cv::Mat d;
+    const int rc = ex.CloudFrameComputeDescriptors(image, k, d);
+    for (int i = 0; i < n && rc > 0; ++i) std::memcpy(desc + 32 * (size_t)i, d.ptr(i), 32);
+    return rc;
+}
+
 int ref_octree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N, float* out_xyr, int cap) {
     Exposed ex(1000, 1.2f, 8, 20, 7);
     std::vector<cv::KeyPoint> in;

@@ -1,0 +1,119 @@
+"""Pins the oracle's restatements of Frame::ComputeStereoMatches, MapPoint::ComputeDistinctiveDescriptors and both
+ORBmatcher::SearchByBoW overloads against the UNMODIFIED reference functions (oracle/_ref/librefframe.so: the function
+definitions cut out of /root/reference's Frame.cc / MapPoint.cc / ORBmatcher.cc at build time and compiled over class
+stand-ins, oracle/ref_frame_shim.cpp).  Skipped where neither /root/reference nor the prebuilt library exists."""
+import numpy as np
+import pytest
+
+from rumi_slam_b200.synth import descriptors_near_vocabulary, stereo_pair, synthetic_vocabulary
+
+
+@pytest.fixture(scope="module")
+def rf():
+    from oracle import ref_frame_lib
+    if not ref_frame_lib.available():
+        pytest.skip("oracle/_ref/librefframe.so not available")
+    return ref_frame_lib
+
+
+@pytest.fixture(scope="module")
+def B():
+    from oracle import bow_oracle
+    bow_oracle.build()
+    return bow_oracle
+
+
+def test_descriptor_distance_is_the_references(oracle, rf):
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a, b = rng.integers(0, 256, (2, 32), dtype=np.uint8)
+        assert rf.descriptor_distance(a, b) == oracle.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+@pytest.mark.parametrize("w,h,nf,fx,bf,seeds", [(752, 480, 1200, 435.2, 47.9, (1, 2, 3, 4)),
+                                                (1241, 376, 2000, 718.856, 386.1448, (5, 6)),
+                                                (640, 480, 1000, 517.3, 40.0, (7,))])
+def test_compute_stereo_matches_equals_reference(oracle, rf, w, h, nf, fx, bf, seeds):
+    """mvuRight / mvDepth of the oracle == the reference's own Frame::ComputeStereoMatches (R/lib_src/Frame.cc:828-985),
+    float for float, on the BASELINE stereo shapes (EuRoC, KITTI) -- best-1 band search, SAD slide, parabola, median cut."""
+    tb = oracle.tables(nf)
+    total = 0
+    for s in seeds:
+        left, right = stereo_pair(s, w, h)
+        lk, ld, _ = oracle.extract(left, nfeatures=nf)
+        rk, rd, _ = oracle.extract(right, nfeatures=nf)
+        u, d, n = oracle.stereo_match(left, right, lk, ld, rk, rd, bf, bf / fx)
+        ru, rdp, rn = rf.stereo_match(oracle.pyramid(left), oracle.pyramid(right), lk, ld, rk, rd, tb["scale"],
+                                      tb["inv_scale"], bf, bf / fx)
+        assert n == rn and np.array_equal(u, ru) and np.array_equal(d, rdp), (s, n, rn)
+        total += n
+    assert total > 300 * len(seeds)
+
+
+def test_distinctive_descriptor_equals_reference(rf, B):
+    """The descriptor MapPoint::ComputeDistinctiveDescriptors (R/lib_src/MapPoint.cc:353-426) stores == the row the oracle
+    picks, for 1..100 observations incl. ties (identical observations, two equally central rows)."""
+    rng = np.random.default_rng(3)
+    sizes = np.concatenate([rng.integers(1, 12, 300), rng.integers(30, 100, 20), [1, 2, 3, 33, 64, 65]])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    centre = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    desc = np.concatenate([centre[p] ^ np.packbits(rng.random((sizes[p], 256)) < 0.08, axis=1) for p in range(len(sizes))])
+    desc[off[5]:off[6]] = desc[off[5]]                       # all observations identical: first wins
+    desc[off[7] + 1] = desc[off[7]]                          # duplicated rows inside a point
+    best, med = B.distinctive(desc, off)
+    for p in range(len(sizes)):
+        d = desc[off[p]:off[p + 1]]
+        assert np.array_equal(rf.distinctive(d), d[best[p]]), p
+
+
+def _scene(B, seed, nk=700, nf=800, flip=0.03):
+    k, L = 10, 4
+    par, leaf, vdesc, w = synthetic_vocabulary(k, L, seed=11)
+    V = B.Vocabulary(k, L, par, leaf, vdesc, w)
+    rng = np.random.default_rng(seed)
+    dk = descriptors_near_vocabulary(vdesc, leaf, nk, 20 + seed, flip=0.04)
+    src = rng.integers(0, nk, nf - 150)
+    df = np.concatenate([dk[src] ^ np.packbits(rng.random((nf - 150, 256)) < flip, axis=1),
+                         descriptors_near_vocabulary(vdesc, leaf, 150, 30 + seed)])
+    perm = rng.permutation(nf)
+    df = df[perm]
+    ak = (rng.random(nk) * 360).astype(np.float32)
+    af = (rng.random(nf) * 360).astype(np.float32)
+    af[np.argsort(perm)[:nf - 150]] = ((ak[src] - 15 + rng.normal(0, 2, nf - 150)) % 360).astype(np.float32)
+
+    def featvec(desc):
+        _, weight, node = V.transform(desc, 2)
+        fv = {}
+        for i in range(len(desc)):
+            if weight[i] > 0:
+                fv.setdefault(int(node[i]), []).append(i)
+        return fv
+    return dk, ak, featvec(dk), df, af, featvec(df), rng
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_search_by_bow_equals_reference(rf, B, seed, check_ori):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (R/lib_src/ORBmatcher.cc:198-370): the assignment of every frame
+    feature equals the reference's -- order-dependent 'already matched' skip and rotation histogram included."""
+    dk, ak, fvk, df, af, fvf, rng = _scene(B, seed)
+    valid = (rng.random(len(dk)) < 0.8).astype(np.uint8)
+    for ratio in (0.6, 0.75, 0.9):
+        n, m = B.search_by_bow(dk, ak, valid, fvk, df, af, fvf, nnratio=ratio, check_ori=check_ori)
+        rn, rm = rf.search_by_bow(dk, ak, valid, fvk, df, af, fvf, nnratio=ratio, check_ori=check_ori)
+        assert n == rn and np.array_equal(m, rm), (seed, ratio)
+    assert rn > 100
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed", [4, 5, 6])
+def test_search_by_bow_keyframes_equals_reference(rf, B, seed, check_ori):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (R/lib_src/ORBmatcher.cc:682-804), strict '<' TH_LOW."""
+    d1, a1, fv1, d2, a2, fv2, rng = _scene(B, seed)
+    v1 = (rng.random(len(d1)) < 0.85).astype(np.uint8)
+    v2 = (rng.random(len(d2)) < 0.85).astype(np.uint8)
+    for ratio in (0.7, 0.8):
+        n, m = B.search_by_bow_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, nnratio=ratio, check_ori=check_ori)
+        rn, rm = rf.search_by_bow_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, nnratio=ratio, check_ori=check_ori)
+        assert n == rn and np.array_equal(m, rm), (seed, ratio)
+    assert rn > 100

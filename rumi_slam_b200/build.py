@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librumi_orb.so")
-SOURCES = ["pyramid.cu", "pyramid_march.cu", "blur.cu", "fast.cu", "octree.cu", "describe.cu", "match.cu", "match_umma.cu", "bow.cu", "stereo.cu", "flow.cu", "api.cu"]
+SOURCES = ["pyramid.cu", "pyramid_strip.cu", "blur.cu", "fast.cu", "octree.cu", "describe.cu", "match.cu", "match_umma.cu", "bow.cu", "stereo.cu", "flow.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]

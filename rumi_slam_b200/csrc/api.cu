@@ -86,8 +86,6 @@ struct Workspace {
     CUtensorMap tmap[kMaxLevels];      // tmap[l]: source map (internal level l-1) used to produce level l
     bool tmapOk[kMaxLevels];
     int lastFrames = 0;
-    int* pyrFlags = nullptr;           // [chunk][marchItems] completion epochs of the marching pyramid's work items
-    int pyrEpoch = 0;
     bool ready = false;                // every buffer above is allocated
 };
 
@@ -112,11 +110,14 @@ struct rumi_orb {
     long long pyrBytes = 0, candElems = 0, bigKeysElems = 0;
     int fastTilePitch = 0, fastTileRows = 0, fastScoreRows = 0;
     FastCell* fastCells = nullptr;                    // [totalCells] cell geometry of all levels
-    // marching pyramid (K1'): per-level column-group / row tables, work-item geometry
-    bool useMarch = true, marchOk = false, marchForced = false;
-    uint8_t* marchTables = nullptr;
-    PyrMarchLevel marchLv[kMaxLevels];
-    int marchItems = 0;
+    // strip pyramid (K1): per-level column-group / row tables, and for each usable strip count the rows every strip
+    // computes per level + its shared-memory budget
+    bool useStrip = true, stripOk = false;
+    uint8_t* pyrTables = nullptr;
+    PyrStripLevel stripLv[kMaxLevels];
+    struct StripVariant { int nstrips; const int2* ranges; size_t smemBytes; int buf1Offset, rowTabOffset; int rowsPerItem[kMaxLevels]; };
+    std::vector<StripVariant> stripVariants;          // ascending nstrips
+    int stripForce = 0;                               // RUMI_PYR_STRIPS: force a strip count (tuning)
     int smemKeys = 4096, maxNodeCap = 0;
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
@@ -147,7 +148,7 @@ namespace {
 void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
     cudaFree(w.levelCount); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
-    cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono); cudaFree(w.pyrFlags);
+    cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono);
     cudaStream_t s = w.stream;
     w = Workspace();
     w.stream = s;
@@ -181,9 +182,6 @@ int alloc_workspace(rumi_orb* h, Workspace& w) {
     CU_TRY(cudaMalloc(&w.desc, 32 * n * oc.kpCap));
     CU_TRY(cudaMalloc(&w.nkp, 4 * n));
     CU_TRY(cudaMalloc(&w.nmono, 4 * n));
-    CU_TRY(cudaMalloc(&w.pyrFlags, 4 * n * std::max(h->marchItems, 1)));
-    CU_TRY(cudaMemsetAsync(w.pyrFlags, 0, 4 * n * std::max(h->marchItems, 1), w.stream));
-    w.pyrEpoch = 0;
     // the workspace streams are non-blocking: a legacy-stream memset would not be ordered before the first upload
     CU_TRY(cudaMemsetAsync(w.pyr, 0, h->pyrBytes, w.stream));
     CU_TRY(cudaMemsetAsync(w.blur, 0, h->pyrBytes, w.stream));
@@ -205,11 +203,11 @@ void reset_geometry(rumi_orb* h) {
     }
     cudaFree(h->coef);
     cudaFree(h->fastCells);
-    cudaFree(h->marchTables);
+    cudaFree(h->pyrTables);
     h->coef = nullptr;
     h->fastCells = nullptr;
-    h->marchTables = nullptr;
-    h->marchOk = false; h->marchItems = 0;
+    h->pyrTables = nullptr;
+    h->stripOk = false; h->stripVariants.clear();
     h->W = 0; h->H = 0;
     h->pyrBytes = 0; h->candElems = 0; h->bigKeysElems = 0;
     cudaGetLastError();                     // a failed cudaMalloc leaves a (non-sticky) error behind
@@ -256,13 +254,13 @@ int build_geometry(rumi_orb* h, int W, int H) {
         CU_TRY(cudaMalloc(&h->coef, sizeof(ResizeCoef)));
     }
     for (int l = 1; l < oc.nlevels; ++l) { h->xc[l] = h->coef + xo[l]; h->yc[l] = h->coef + yo[l]; }
-    // marching pyramid tables: per group of 4 destination columns the 8-byte source window (first word, alignment
+    // strip pyramid tables: per group of 4 destination columns the 8-byte source window (first word, alignment
     // shift, byte selectors, weights), per destination row the two source rows and the vertical weights << 16
     {
         std::vector<uint8_t> blob;
         std::vector<size_t> colOff(oc.nlevels, 0), rowOff(oc.nlevels, 0);
+        std::vector<std::vector<PyrRow>> rowTab(oc.nlevels);
         bool ok = oc.nlevels > 1;
-        int items = 0;
         for (int l = 1; l < oc.nlevels && ok; ++l) {
             const LevelGeom &sg = oc.lv[l - 1], &dg = oc.lv[l];
             AxisCoef cx = make_axis_coef(sg.w, dg.w), cy = make_axis_coef(sg.h, dg.h);
@@ -282,12 +280,22 @@ int build_geometry(rumi_orb* h, int W, int H) {
                 }
                 c.sel01 = (uint16_t)(sel & 0xFFFFu); c.sel23 = (uint16_t)(sel >> 16);
             }
-            std::vector<PyrRow> rows(dg.h);
+            std::vector<PyrRow>& rows = rowTab[l];
+            rows.resize(dg.h);
             for (int y = 0; y < dg.h; ++y) {
-                rows[y].sy0 = cy.ofs[y];
-                rows[y].sy1 = (uint16_t)std::min(cy.ofs[y] + 1, sg.h - 1);
-                rows[y].b0s = (uint32_t)cy.a0[y] << 16;
-                rows[y].b1s = (uint32_t)cy.a1[y] << 16;
+                int s0 = cy.ofs[y], s1 = std::min(cy.ofs[y] + 1, sg.h - 1);
+                uint32_t b0 = (uint32_t)cy.a0[y], b1 = (uint32_t)cy.a1[y];
+                if (s1 == s0) {                                  // clamped at the bottom (weight of the second tap is 0)
+                    if (b1 != 0 || s0 < 1) ok = false;
+                    s0 -= 1; b1 = b0; b0 = 0;
+                }
+                rows[y].sy1 = s1; rows[y].b0s = b0 << 16; rows[y].b1s = b1 << 16;
+                rows[y].adv = 1;
+                // the kernel keeps only the last two horizontally filtered rows and reads source rows in order:
+                // consecutive rows advance by 0 (bottom clamp only: first-tap weight 0), 1 or 2 source rows
+                const int adv = y > 0 ? s1 - rows[y - 1].sy1 : 1;
+                if (adv < 0 || adv > 2 || s1 - s0 != 1 || (adv == 0 && b0 != 0)) ok = false;
+                if (y > 0) rows[y - 1].adv = adv;                // the record of row y-1 carries the advance count of row y
             }
             blob.resize((blob.size() + 15) & ~(size_t)15);
             colOff[l] = blob.size();
@@ -295,27 +303,82 @@ int build_geometry(rumi_orb* h, int W, int H) {
             blob.resize((blob.size() + 15) & ~(size_t)15);
             rowOff[l] = blob.size();
             blob.insert(blob.end(), (uint8_t*)rows.data(), (uint8_t*)(rows.data() + dg.h));
-            PyrMarchLevel& m = h->marchLv[l];
+            PyrStripLevel& m = h->stripLv[l];
             m.groups = groups;
-            m.nColBlocks = (groups + 31) / 32;
-            // every item marches its rows serially, so the dependent chain of levels costs (levels x item time): the
-            // small levels get shorter strips (more, shorter items)
-            const long long px = (long long)dg.w * dg.h;
-            m.stripRows = px >= 120000 ? kPyrStripRows : px >= 50000 ? kPyrStripRows / 2 : kPyrStripRows / 4;
-            m.nStrips = (dg.h + m.stripRows - 1) / m.stripRows;
-            m.itemBase = items; items += m.nColBlocks * m.nStrips;
             m.srcLastWord = (sg.w - 1) >> 2;
+            m.rowsPerItem = 8;
         }
-        h->marchOk = ok;
-        h->marchItems = ok ? items : 0;
+        // Strip variants: for S strips per frame, strip s owns rows [s*h/S, (s+1)*h/S) of every level and additionally
+        // computes the rows of level l that its rows of level l+1 read (1-2 halo rows per level, computed by both
+        // neighbours).  Usable when the two largest adjacent levels of a strip fit the shared memory of one SM.
+        std::vector<size_t> rangeOff;
+        std::vector<rumi_orb::StripVariant> variants;
+        const int top = oc.nlevels - 1;
+        const int candidates[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+        for (int S : candidates) {
+            if (!ok) break;
+            if (S > 1 && oc.lv[top].h / S < 4) break;
+            std::vector<int2> rg((size_t)S * kMaxLevels, make_int2(0, 0));
+            size_t bufBytes[2] = {0, 0};
+            rumi_orb::StripVariant v{};
+            v.nstrips = S;
+            for (int st = 0; st < S; ++st) {
+                int needA = 0, needB = 0;
+                for (int l = top; l >= 1; --l) {
+                    const int hl = oc.lv[l].h;
+                    int a = (int)((long long)st * hl / S), b = (int)((long long)(st + 1) * hl / S);
+                    if (l < top) { a = std::min(a, needA); b = std::max(b, needB); }
+                    rg[(size_t)st * kMaxLevels + l] = make_int2(a, b);
+                    if (b > a) { needA = rowTab[l][a].sy1 - 1; needB = rowTab[l][b - 1].sy1 + 1; }    // rows of level l-1 read
+                    else { needA = oc.lv[l - 1].h; needB = 0; }
+                    // shared copy of a level: 16 spare bytes behind every row, one spare row behind the last (read-ahead)
+                    if (l < top) bufBytes[l & 1] = std::max(bufBytes[l & 1], (size_t)(b - a + 1) * (oc.lv[l].stride + 16) + 64);
+                }
+            }
+            int maxRows = 0;
+            for (int st = 0; st < S; ++st)
+                for (int l = 1; l <= top; ++l)
+                    maxRows = std::max(maxRows, rg[(size_t)st * kMaxLevels + l].y - rg[(size_t)st * kMaxLevels + l].x);
+            v.buf1Offset = (int)((bufBytes[0] + 127) & ~(size_t)127);
+            v.rowTabOffset = v.buf1Offset + (int)((bufBytes[1] + 127) & ~(size_t)127);
+            v.smemBytes = (size_t)v.rowTabOffset + 16 * (size_t)maxRows;
+            if (v.smemBytes > 220 * 1024) continue;
+            // rows per item: minimise rounds x per-item cost (vertical pass ~25 instr / row, horizontal ~16 per source row)
+            for (int l = 1; l <= top; ++l) {
+                int rowsMax = 0;
+                for (int st = 0; st < S; ++st) rowsMax = std::max(rowsMax, rg[(size_t)st * kMaxLevels + l].y - rg[(size_t)st * kMaxLevels + l].x);
+                const double sc = (double)oc.lv[l - 1].h / oc.lv[l].h;
+                double best = 1e30; int bestR = 8;
+                for (int R = 3; R <= 24; ++R) {
+                    const long long items = (long long)((rowsMax + R - 1) / R) * h->stripLv[l].groups;
+                    const double rounds = (double)((items + kPyrStripThreads - 1) / kPyrStripThreads);
+                    const double cost = rounds * (R * 25.0 + (sc * R + 1.0) * 16.0 + 30.0);
+                    if (cost < best - 1e-9) { best = cost; bestR = R; }
+                }
+                v.rowsPerItem[l] = bestR;
+            }
+            blob.resize((blob.size() + 15) & ~(size_t)15);
+            rangeOff.push_back(blob.size());
+            blob.insert(blob.end(), (uint8_t*)rg.data(), (uint8_t*)(rg.data() + rg.size()));
+            variants.push_back(v);
+        }
+        ok = ok && !variants.empty();
+        h->stripOk = ok;
         if (ok) {
-            CU_TRY(cudaMalloc(&h->marchTables, blob.size()));
-            CU_TRY(cudaMemcpy(h->marchTables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+            CU_TRY(cudaMalloc(&h->pyrTables, blob.size()));
+            CU_TRY(cudaMemcpy(h->pyrTables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
             CU_TRY(cudaDeviceSynchronize());
             for (int l = 1; l < oc.nlevels; ++l) {
-                h->marchLv[l].cols = reinterpret_cast<const PyrColGroup*>(h->marchTables + colOff[l]);
-                h->marchLv[l].rows = reinterpret_cast<const PyrRow*>(h->marchTables + rowOff[l]);
+                h->stripLv[l].cols = reinterpret_cast<const PyrColGroup*>(h->pyrTables + colOff[l]);
+                h->stripLv[l].rows = reinterpret_cast<const PyrRow*>(h->pyrTables + rowOff[l]);
             }
+            size_t maxSmem = 0;
+            for (size_t i = 0; i < variants.size(); ++i) {
+                variants[i].ranges = reinterpret_cast<const int2*>(h->pyrTables + rangeOff[i]);
+                maxSmem = std::max(maxSmem, variants[i].smemBytes);
+            }
+            h->stripVariants = variants;
+            if (pyramid_strip_prepare(maxSmem) != 0) { cudaGetLastError(); h->stripOk = false; }
         }
     }
     // level-major workspace offsets for `chunk` frames
@@ -435,25 +498,29 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     }
     if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
     if (h->profile) prof_event(h, s);
-    // K1': all levels in one launch when every source can be read as aligned 32-bit words (always true for the
-    // internal buffers; caller device memory only if it is 4-byte aligned with readable row padding)
-    // (a marching item walks its rows serially: with only a few frames in flight the 64x32-pixel TMA tiles have the
-    // shorter critical path -- single frame: 32 us vs 62 us for the 7 levels -- so small calls use the tile kernel)
-    bool march = h->useMarch && h->marchOk && oc.nlevels > 1 && (n >= 8 || h->marchForced);
-    if (march && !l0Internal)
-        march = ((((uintptr_t)l0.ptr | (uintptr_t)l0.pitch | (uintptr_t)l0.stride) & 3) == 0) &&
-                l0.stride >= 4 * (h->marchLv[1].srcLastWord + 1);
+    // K1: all levels in ONE launch (a CTA carries a strip of a frame through every level in shared memory) when every
+    // source row can be read as aligned 32-bit words: always true for the internal buffers, caller device memory only if
+    // it is 4-byte aligned with readable row padding.  Otherwise (and for scale factors > 2) the tile kernel runs.
+    bool strip = h->useStrip && h->stripOk && oc.nlevels > 1;
+    if (strip && !l0Internal)
+        strip = ((((uintptr_t)l0.ptr | (uintptr_t)l0.pitch | (uintptr_t)l0.stride) & 3) == 0) &&
+                l0.stride >= 4 * (h->stripLv[1].srcLastWord + 1);
     int pyrLaunches = oc.nlevels - 1;
     const int skip = h->skipMask;
     if (skip & 1) {
-    } else if (march) {
-        PyrMarchArgs ma;
-        ma.cv = cv;
-        for (int l = 0; l < kMaxLevels; ++l) ma.lv[l] = h->marchLv[l];
-        ma.nlevels = oc.nlevels; ma.itemsPerFrame = h->marchItems;
-        ma.flags = w.pyrFlags; ma.epoch = ++w.pyrEpoch; ma.err = h->errDev + 1;
-        pyrLaunches = 0;
-        for (int l = 1; l < oc.nlevels; ++l) { ma.levelFirst = ma.levelLast = l; launch_pyramid_march(ma, sh); ++pyrLaunches; }
+    } else if (strip) {
+        // strips per frame: enough CTAs to fill the GPU (small calls get more, thinner strips), as few as possible
+        // otherwise (every strip boundary recomputes the halo rows of all levels)
+        const rumi_orb::StripVariant* v = &h->stripVariants.back();
+        for (const auto& c : h->stripVariants)
+            if (h->stripForce ? c.nstrips >= h->stripForce : (long long)c.nstrips * n >= 128) { v = &c; break; }
+        PyrStripArgs sa;
+        sa.cv = cv;
+        for (int l = 0; l < kMaxLevels; ++l) { sa.lv[l] = h->stripLv[l]; sa.lv[l].rowsPerItem = v->rowsPerItem[l]; }
+        sa.nlevels = oc.nlevels; sa.nstrips = v->nstrips; sa.ranges = v->ranges; sa.buf1Offset = v->buf1Offset;
+        sa.rowTabOffset = v->rowTabOffset;
+        launch_pyramid_strip(sa, v->smemBytes, sh);
+        pyrLaunches = 1;
     } else
     for (int l = 1; l < oc.nlevels; ++l) {
         PyramidLevelArgs pa;
@@ -553,9 +620,10 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     h->tables = make_scale_tables(nfeatures, scale_factor, nlevels);
     const char* e = getenv("RUMI_NO_TMA");
     h->useTMA = !(e && e[0] == '1');
-    const char* pm = getenv("RUMI_PYRAMID");                     // "march" (default) | "tiles" (TMA / plain tile kernel)
-    h->useMarch = !(pm && pm[0] == 't') && h->useTMA;            // RUMI_NO_TMA=1 selects the plain tile kernel
-    h->marchForced = pm && pm[0] == 'm';                         // RUMI_PYRAMID=march: also for small calls (tests)
+    const char* pm = getenv("RUMI_PYRAMID");                     // "strip" (default) | "tiles" (TMA / plain tile kernel)
+    h->useStrip = !(pm && pm[0] == 't') && h->useTMA;            // RUMI_NO_TMA=1 selects the plain tile kernel
+    const char* pst = getenv("RUMI_PYR_STRIPS");
+    if (pst) h->stripForce = atoi(pst);
     const char* sk = getenv("RUMI_SKIP_STAGES");
     if (sk) h->skipMask = atoi(sk);
     const char* ns = getenv("RUMI_STREAMS");
@@ -582,7 +650,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     }
     cudaFree(h->coef);
     cudaFree(h->fastCells);
-    cudaFree(h->marchTables);
+    cudaFree(h->pyrTables);
     cudaFree(h->dbgBuf);
     cudaFree(h->octClk);
     if (h->errHost) cudaFreeHost(h->errHost);

@@ -38,7 +38,7 @@ struct PyramidLevelArgs {
 
 void launch_pyramid_level(const PyramidLevelArgs& a, const CUtensorMap* tmap /* nullptr = plain loads */,
                           cudaStream_t s);
-// ---- K1', the default pyramid path: register-marching warps, all levels of a chunk in ONE launch ----
+// ---- K1, the default pyramid path (pyramid_strip.cu): all levels of a chunk in ONE launch, levels chained in shared memory ----
 // Per group of 4 destination columns: where the 8-byte source window starts and how its bytes map to the outputs.
 struct alignas(8) PyrColGroup {
     uint16_t word0;          // first 32-bit source word of the window
@@ -47,30 +47,30 @@ struct alignas(8) PyrColGroup {
     uint16_t sel01, sel23;   // PRMT selectors: (p0,p1) of outputs 0|1 and 2|3 as bytes of one register each
     uint32_t coef[4];        // a0 | a1 << 16 (11-bit fixed-point weights) per output
 };
-struct PyrRow { uint16_t sy0, sy1; uint32_t b0s, b1s; };     // source rows and vertical weights << 16
+// Per destination row: vertical weights << 16 of the taps (sy1 - 1, sy1), and `adv` = how many source rows lie between
+// the NEXT row's second tap and this row's (0, 1 or 2 for scale factors <= 2).  A row whose taps coincide (clamped at the bottom,
+// second weight 0) is stored as (sy1 - 1, sy1) with weights (0, b0): the same value.
+struct alignas(16) PyrRow { uint32_t b0s, b1s; int32_t sy1, adv; };
 
-constexpr int kPyrStripRows = 32, kPyrBlockCols = 128, kPyrMarchWarps = 4;
-
-struct PyrMarchLevel {                                        // destination level l (source = level l-1)
+// One destination level of the strip kernel (source = level l-1).
+struct PyrStripLevel {
     const PyrColGroup* cols;   // [groups]
     const PyrRow* rows;        // [dst.h]
     int groups;                // ceil(dst.w / 4)
-    int nColBlocks, nStrips;   // work items of this level = nColBlocks * nStrips
-    int stripRows;             // destination rows per item (<= kPyrStripRows; smaller on the small levels)
-    int itemBase;              // first item of this level inside a frame
     int srcLastWord;           // last readable 32-bit word of a source row
-    int blockBase, blocksPerFrame;   // filled per launch: first CTA of this level, CTAs per frame
+    int rowsPerItem;           // destination rows a thread marches per item (chosen per launch geometry)
 };
-struct PyrMarchArgs {
+constexpr int kPyrStripThreads = 512;
+struct PyrStripArgs {
     ChunkView cv;
-    PyrMarchLevel lv[kMaxLevels];
-    int nlevels, itemsPerFrame;
-    int levelFirst, levelLast; // destination levels produced by this launch (chained through the flags)
-    int* flags;                // [frame][itemsPerFrame] completion epoch of every item
-    int epoch;
-    int* err;                  // mapped host flag: set when a level dependency did not arrive in time
+    PyrStripLevel lv[kMaxLevels];
+    int nlevels, nstrips;
+    const int2* ranges;        // [strip][kMaxLevels]: destination rows [x, y) of each level the strip computes
+    int buf1Offset;            // byte offset of the second ping-pong level buffer in dynamic shared memory
+    int rowTabOffset;          // byte offset of the row-record table of the current level (16 B per strip row)
 };
-void launch_pyramid_march(const PyrMarchArgs& a, cudaStream_t s);
+int pyramid_strip_prepare(size_t smemBytes);      // opt in to `smemBytes` of dynamic shared memory (current device)
+void launch_pyramid_strip(const PyrStripArgs& a, size_t smemBytes, cudaStream_t s);
 
 void launch_blur(const ChunkView& cv, const OrbConst& oc, cudaStream_t s);
 

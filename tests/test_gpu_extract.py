@@ -18,16 +18,20 @@ def make(nf, **kw):
 
 
 @pytest.mark.parametrize("w,h,nf", SHAPES)
-@pytest.mark.parametrize("mode", ["march", "tma", "plain"])
+@pytest.mark.parametrize("mode", ["strip", "strip1", "strip3", "strip8", "tma", "plain"])
 def test_pyramid_and_blur_bitexact(oracle, w, h, nf, mode):
-    # march = register-marching all-level kernel (default); tma / plain = the tile kernel with / without TMA staging
-    os.environ["RUMI_PYRAMID"] = "march" if mode == "march" else "tiles"
+    # strip = the all-level shared-memory kernel (default; stripN forces N strips per frame: different halo rows),
+    # tma / plain = the per-level tile kernel with / without TMA staging (fallback for scale factors > 2)
+    os.environ["RUMI_PYRAMID"] = "strip" if mode.startswith("strip") else "tiles"
     os.environ["RUMI_NO_TMA"] = "1" if mode == "plain" else "0"
+    if mode[5:]:
+        os.environ["RUMI_PYR_STRIPS"] = mode[5:]
     try:
         ex = make(nf)
     finally:
         os.environ["RUMI_NO_TMA"] = "0"
-        os.environ.pop("RUMI_PYRAMID", None)           # default: march for chunks of >= 8 frames, tiles below
+        os.environ.pop("RUMI_PYRAMID", None)
+        os.environ.pop("RUMI_PYR_STRIPS", None)
     img = synthetic_frame(11, w, h)
     ex(img)
     ref = oracle.pyramid(img)
@@ -148,8 +152,8 @@ def test_cloud_frame_compute_descriptors(oracle):
                                                  (1024, 768, 2000, 12, 1.1)])
 def test_other_shapes_and_pyramid_parameters(oracle, w, h, nf, levels, scale):
     """Shapes / pyramid parameters the benchmark does not use: full HD, odd sizes (partial words and cells), few and
-    many levels, scale factors up to 2.0 (source windows of 8 pixels per 4 outputs) -- single frames (tile pyramid)
-    and a chunk of 9 frames (marching pyramid)."""
+    many levels, scale factors up to 2.0 (source windows of 8 pixels per 4 outputs) -- single frames (many thin strips)
+    and a chunk of 9 frames (fewer, taller strips)."""
     from rumi_slam_b200 import ORBextractor
     ex = ORBextractor(nf, scale, levels, 20, 7, max_batch=9)
     frames = synthetic_batch(9, w, h, seed0=70)

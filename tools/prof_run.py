@@ -1,6 +1,5 @@
 """Short profiling workload: one 64-frame chunk of synthetic 640x480 frames through the device-resident batch
-call (2 warm-up + 2 profiled passes), 8192 x 40000 top-2 on the LOP3+POPC kernel, 16384 x 40000 on the mma.sync and the
-tcgen05 kernels, and 4 optical-flow steps of 1000 points.  Used under ncu (see profiles/README.md)."""
+call (2 warm-up + 2 profiled passes), 8192 x 40000 top-2 on the LOP3+POPC kernel, 16384 x 40000 on the tcgen05 kernel, and 4 optical-flow steps of 1000 points.  Used under ncu (see profiles/README.md)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,7 +24,7 @@ m = matcher("popc")                                  # K8: LOP3 + POPC
 for _ in range(1 if LIGHT else 2):
     m.top2_device(Q, T)
 Q2 = desc[:16384].contiguous()
-for mode in ("imma", "umma"):                        # K8-T (mma.sync int8) and K8-U (tcgen05 + TMEM), 16384 x 40000
+for mode in ("umma",):                               # K8-U (tcgen05 + TMEM), 16384 x 40000
     mm = matcher(mode)
     for _ in range(1 if LIGHT else 2):
         mm.top2_device(Q2, T)

@@ -416,7 +416,9 @@ int build_geometry(rumi_orb* h, int W, int H) {
     CU_TRY(cudaMemcpy(h->fastCells, cells.data(), sizeof(FastCell) * cells.size(), cudaMemcpyHostToDevice));
     CU_TRY(cudaDeviceSynchronize());
     h->maxNodeCap = nodeCap;
-    h->smemKeys = 4096;
+    // 2048 keys in shared memory (16 KB): five problems per SM stay resident, which is what hides the latency of the
+    // serial phases; a level with more candidates sorts in the global scratch instead
+    h->smemKeys = 2048;
     while (h->smemKeys > 256 && octree_smem_bytes(h->smemKeys, nodeCap, 256) > 200 * 1024) h->smemKeys >>= 1;
     if (octree_smem_bytes(h->smemKeys, nodeCap, 256) > 220 * 1024)
         return fail(RUMI_ERR_CAPACITY, "nfeatures %d needs more shared memory than one SM has", h->nfeatures);

@@ -79,10 +79,129 @@ __device__ void block_sort_regs(uint64_t* a, int n, int tid) {
     __syncthreads();
 }
 
+// Block-wide ascending sort of the first n (<= 16 * blockDim.x) u64 keys by BUCKETS of their leading bits: bucket(key) =
+// key >> bshift < nb.  Tree keys are (path code | insertion index | response): the code of a candidate is unique (every
+// leaf of the full-depth tree is one pixel), the leading 2p digits of the code spread the keys over nb = roots * 4^p
+// buckets of a handful of keys each.  Histogram (shared atomics) -> scan -> index lists per bucket -> every key counts
+// the smaller keys of its own bucket -> final position.  ~M * (bucket size) shared reads instead of the ~M log^2 M
+// compare-exchanges of a bitonic network (29 k -> 4 k cycles for 1 500 keys).  Returns false (nothing moved) when a
+// bucket is too crowded (clustered candidates) -- the caller falls back to the bitonic network.
+// scratch: ints [2 * nb + 2] then u16 [n].
+template <int E>
+__device__ bool block_bucket_sort(uint64_t* a, int n, int bshift, int nb, int* scratch, int tid, int nthr) {
+    int* start = scratch;                 // [nb + 1]
+    int* fill = scratch + nb + 1;         // [nb] (+1: crowded flag)
+    uint16_t* idx = reinterpret_cast<uint16_t*>(fill + nb + 1);
+    for (int b = tid; b <= nb; b += nthr) { start[b] = 0; fill[b] = 0; }
+    __syncthreads();
+    uint64_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = tid + r * nthr;
+        v[r] = i < n ? a[i] : ~0ull;
+        if (i < n) atomicAdd(&start[(int)(v[r] >> bshift)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the bucket counts (nb <= 4 * nthr): per-thread chunk + warp scans + one pass over the warp sums
+    {
+        const int per = (nb + nthr - 1) / nthr;
+        const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+        int s = 0, mx = 0;
+        for (int b = b0; b < b1; ++b) { s += start[b]; mx = max(mx, start[b]); }
+        if (mx > 192) fill[nb] = 1;                                  // crowded bucket: quadratic ranking would be slow
+        const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __shared__ int wsum[33];
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = lane < nw ? wsum[lane] : 0;
+            int ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, ti, o);
+                if (lane >= o) ti += u;
+            }
+            if (lane < nw) wsum[lane] = ti - t;
+        }
+        __syncthreads();
+        int run = wsum[wid] + incl - s;
+        for (int b = b0; b < b1; ++b) { const int c = start[b]; start[b] = run; run += c; }
+        if (tid == nthr - 1) start[nb] = n;
+    }
+    __syncthreads();
+    if (fill[nb]) return false;                                        // uniform: read after the barrier
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = tid + r * nthr;
+        if (i < n) {
+            const int b = (int)(v[r] >> bshift);
+            idx[start[b] + atomicAdd(&fill[b], 1)] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    int rank[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = tid + r * nthr;
+        rank[r] = 0;
+        if (i < n) {
+            const int b = (int)(v[r] >> bshift);
+            const int p0 = start[b], p1 = start[b + 1];
+            int c = p0;
+            for (int p = p0; p < p1; ++p) {
+                const int j = idx[p];
+                const uint64_t o = a[j];
+                c += (o < v[r]) || (o == v[r] && j < i);
+            }
+            rank[r] = c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = tid + r * nthr;
+        if (i < n) a[rank[r]] = v[r];
+    }
+    __syncthreads();
+    return true;
+}
+
+// Ascending sort of n <= 2 * blockDim.x u64 keys by counting, per key, the smaller ones (distinct keys): two passes
+// over shared memory instead of a sorting network (the leaf-list keys: a few hundred).
+__device__ void block_rank_sort(uint64_t* a, int n, int tid, int nthr) {
+    uint64_t v[2];
+    int rank[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = tid + r * nthr;
+        v[r] = i < n ? a[i] : ~0ull;
+        rank[r] = 0;
+    }
+#pragma unroll 8
+    for (int j = 0; j < n; ++j) {                         // n is a power of two >= 8: the loads of 8 keys are in flight
+        const uint64_t o = a[j];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) rank[r] += (o < v[r]) || (o == v[r] && j < tid + r * nthr);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+        if (tid + r * nthr < n) a[rank[r]] = v[r];
+    __syncthreads();
+}
+
 struct BlockCtx {
     int tid, nthr;
     long long* clk;          // optional phase clock accumulators (test / profiling hook), else nullptr
     long long last;
+    int* sortScratch;        // shared memory that is idle while the tree keys are sorted
+    int sortScratchBytes;
     // adds the cycles since the previous mark to accumulator `id` (thread 0 only)
     __device__ __forceinline__ void mark(int id) {
         if (clk && tid == 0) { const long long now = clock64(); clk[id] += now - last; last = now; }
@@ -91,9 +210,19 @@ struct BlockCtx {
     __device__ __forceinline__ void sync_warp() { __syncwarp(); }
     // ascending sort of n (power of two >= 8) u64 keys; everything written before the call is visible (callers sync)
     __device__ __forceinline__ void sort_u64(uint64_t* a, int n) {
-        if (n <= 8 * nthr) block_sort_regs<8>(a, n, tid);
+        if (n <= nthr) block_rank_sort(a, n, tid, nthr);
+        else if (n <= 8 * nthr) block_sort_regs<8>(a, n, tid);
         else if (n <= 16 * nthr) block_sort_regs<16>(a, n, tid);
         else bitonic_sort_u64(*this, a, n);               // global-memory scratch for pathological candidate counts
+    }
+    // ascending sort of the tree keys: a[0 .. m) are real keys (bucket = key >> bshift < nb), a[m .. npad) are ~0
+    __device__ __forceinline__ void sort_tree_keys(uint64_t* a, int m, int npad, int bshift, int nb) {
+        const bool fits = nb <= 4 * nthr && (size_t)sortScratchBytes >= 4 * (size_t)(2 * nb + 2) + 2 * (size_t)m;
+        if (fits && m > 64 && m <= nthr) { if (block_bucket_sort<1>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
+        else if (fits && m > nthr && m <= 2 * nthr) { if (block_bucket_sort<2>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
+        else if (fits && m > 2 * nthr && m <= 4 * nthr) { if (block_bucket_sort<4>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
+        else if (fits && m > 4 * nthr && m <= 8 * nthr) { if (block_bucket_sort<8>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
+        sort_u64(a, npad);                                 // > 2048 keys, crowded buckets or a tiny problem
     }
     __device__ __forceinline__ int warp_id() const { return tid >> 5; }
     __device__ __forceinline__ int num_warps() const { return nthr >> 5; }
@@ -173,7 +302,9 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
     const int f = blockIdx.x, l = blockIdx.y + a.levelFirst;
     const LevelGeom& g = oc.lv[l];
     const OctreeSmemLayout L = octree_layout(a.smemKeys, a.maxNodeCap, kOctThreads);
-    BlockCtx ctx{(int)threadIdx.x, kOctThreads, (a.dbgClk && f == 0) ? a.dbgClk + 16 * l : nullptr, clock64()};
+    // while the tree keys are sorted everything between the key buffer and the histograms is idle
+    BlockCtx ctx{(int)threadIdx.x, kOctThreads, (a.dbgClk && f == 0) ? a.dbgClk + 16 * l : nullptr, clock64(),
+                 reinterpret_cast<int*>(smem + L.lkeys), (int)(L.hist - L.lkeys)};
 
     const int M = a.levelCount[(long long)f * oc.nlevels + l];
     const uint32_t* cand = a.cand + a.candLevelOff[l] + (long long)f * g.candCap;
@@ -249,7 +380,7 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
     ctx.mark(10);
     distribute_quadtree(ctx, ordered, M, g.quota, g, w, out, slots);
     ctx.mark(11);
-    if (ctx.clk && threadIdx.x == 0) { ctx.clk[12] = M; ctx.clk[13] = w.scal[SC_NOUT]; }
+    if (ctx.clk && threadIdx.x == 0) { ctx.clk[12] = M; ctx.clk[13] = w.scal[SC_NOUT]; ctx.clk[14] += w.scal[SC_NREPLAY]; }
     __syncthreads();
     if (threadIdx.x == 0) a.selCount[(long long)f * oc.nlevels + l] = min(w.scal[SC_NOUT], slots);
 }

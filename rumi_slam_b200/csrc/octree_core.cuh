@@ -78,7 +78,7 @@ struct OctreeWork {
 };
 
 enum { SC_TSTAR = 0, SC_PHASEB = 1, SC_G = 2, SC_NOUT = 3, SC_NCREATED = 4, SC_NPEND = 5, SC_SIZE = 6, SC_DEPTH = 7,
-       SC_DONE = 8, SC_J = 9, SC_NEWC = 10, SC_NEWM = 11, SC_COUNT = 12 };
+       SC_DONE = 8, SC_J = 9, SC_NEWC = 10, SC_NEWM = 11, SC_TIE = 12, SC_NREPLAY = 13, SC_COUNT = 14 };
 constexpr uint32_t kRefListBit = 0x80000000u;        // node ref: bit 31 set -> position in the leaf list
 
 // ---- bitonic sort of n (power of two) u64 ascending; all threads of the block participate ----
@@ -187,12 +187,17 @@ RUMI_HD void move_median_to_first(uint64_t* v, int result, int a, int b, int c) 
     else swp(v, result, b);
 }
 RUMI_HD int unguarded_partition(uint64_t* v, int first, int last, int pivot) {
+    // the pivot sits in front of [first, last) and is never swapped: its key is read once (this loop is the serial
+    // critical path of the kernel); the two elements of a swap are already in registers when it happens
+    const uint32_t pk = (uint32_t)(v[pivot] >> 32);
     while (true) {
-        while (lt(v[first], v[pivot])) ++first;
+        uint64_t a = v[first];
+        while ((uint32_t)(a >> 32) < pk) a = v[++first];
         --last;
-        while (lt(v[pivot], v[last])) --last;
+        uint64_t b = v[last];
+        while (pk < (uint32_t)(b >> 32)) b = v[--last];
         if (!(first < last)) return first;
-        swp(v, first, last);
+        v[first] = b; v[last] = a;
         ++first;
     }
 }
@@ -292,7 +297,12 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
     for (int i = ctx.tid; i < 2 * (kMaxTreeDepth + 2); i += ctx.nthr) w.hist[i] = 0;
     ctx.sync();
     ctx.mark(0);
-    ctx.sort_u64(w.keys, Mpad);
+    {
+        // buckets of the key sort: root index and the first p digits of the path code (p <= 4, at most 1024 buckets)
+        int p = D < 4 ? D : 4;
+        while (p > 1 && (g.nIni << (2 * p)) > 1024) --p;
+        ctx.sort_tree_keys(w.keys, M, Mpad, kKeyCodeShift + 2 * (D - p), g.nIni << (2 * p));
+    }
     ctx.mark(1);
 
     // 2. closed-form level-synchronous phase
@@ -331,6 +341,7 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
         w.scal[SC_PHASEB] = phaseB;
         w.scal[SC_NOUT] = 0;
         w.scal[SC_NCREATED] = 0;
+        w.scal[SC_NREPLAY] = 0;
     }
     ctx.sync();
     ctx.mark(2);
@@ -447,14 +458,16 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
             }
             ctx.sync();
             ctx.mark(6);
-            // (R2) libstdc++ std::sort replay.  Only __introsort_loop (the partitioning) is order dependent and runs on
-            // thread 0.  __final_insertion_sort is a STABLE sort of whatever the partitioning left (strict '<' in
+            // (R2) libstdc++ std::sort replay.  Only __introsort_loop (the partitioning) is order dependent and serial
+            // (thread 0).  __final_insertion_sort is a STABLE sort of whatever the partitioning left (strict '<' in
             // __unguarded_linear_insert, and an element smaller than the current minimum goes to the front), so its
             // result is reproduced in parallel: position = #(smaller keys) + #(equal keys that sit earlier).
-            if (ctx.tid == 0) stdsort::introsort_loop(w.pend, npend);
-            ctx.sync();
-            {
-                uint64_t* sorted = w.lsort;
+            // Elements whose key is unique end up at the same position whatever the partitioning did; only the order
+            // INSIDE a block of equal keys depends on it.  So the stable rank of the ORIGINAL order is tried first: if
+            // no two equal keys meet inside the part of the array that (R3) actually consumes (the J largest elements,
+            // and the element just below them), that is the reference's result and the serial replay is skipped.
+            const int size0 = w.scal[SC_SIZE];
+            auto rank_sort = [&]() {                               // w.pend -> w.lsort
                 for (int i = ctx.tid; i < npend; i += ctx.nthr) {
                     const uint64_t e = w.pend[i];
                     const uint32_t ke = (uint32_t)(e >> 32);
@@ -463,29 +476,27 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                         const uint32_t kj = (uint32_t)(w.pend[j] >> 32);
                         rank += (kj < ke) || (kj == ke && j < i);
                     }
-                    sorted[rank] = e;
+                    w.lsort[rank] = e;
                 }
+                if (ctx.tid == 0) { w.scal[SC_J] = npend; w.scal[SC_TIE] = 0; }
                 ctx.sync();
-                for (int i = ctx.tid; i < npend; i += ctx.nthr) w.pend[i] = sorted[i];
-                if (ctx.tid == 0) w.scal[SC_J] = npend;
-                ctx.sync();
-            }
+            };
             // (R3) split from the back of the sorted array until size >= N: prefix sums over the processing order q
             // (q-th processed = sorted position npend-1-q) of the children each split creates.
-            {
-                const int size0 = w.scal[SC_SIZE];
+            auto split_scan = [&]() {                              // reads w.lsort
+                const uint64_t* arr = w.lsort;
                 const int chunk = (npend + ctx.nthr - 1) / ctx.nthr;
                 const int q0 = ctx.tid * chunk < npend ? ctx.tid * chunk : npend;
                 const int q1 = q0 + chunk < npend ? q0 + chunk : npend;
                 uint32_t loc = 0;
                 for (int q = q0; q < q1; ++q) {
-                    const uint32_t m = w.meta[(uint32_t)w.pend[npend - 1 - q]];
+                    const uint32_t m = w.meta[(uint32_t)arr[npend - 1 - q]];
                     loc += (m & 15u) | ((m >> 4) << 16);
                 }
                 int tot;
                 uint32_t run = (uint32_t)ctx.exclusive_scan((int)loc, w.part, &tot);
                 for (int q = q0; q < q1; ++q) {
-                    const uint32_t m = w.meta[(uint32_t)w.pend[npend - 1 - q]];
+                    const uint32_t m = w.meta[(uint32_t)arr[npend - 1 - q]];
                     w.qbase[q] = run;                                  // created before q | multi-key before q << 16
                     run += (m & 15u) | ((m >> 4) << 16);
                     // size after processing q = size0 + (children created so far) - (nodes split so far)
@@ -494,7 +505,7 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                 ctx.sync();
                 const int J = w.scal[SC_J];
                 if (J > 0 && J - 1 >= q0 && J - 1 < q1) {                  // owner of the last processed node
-                    const uint32_t m = w.meta[(uint32_t)w.pend[npend - J]];
+                    const uint32_t m = w.meta[(uint32_t)arr[npend - J]];
                     const uint32_t endRun = w.qbase[J - 1] + ((m & 15u) | ((m >> 4) << 16));
                     const int size = size0 + (int)(endRun & 0xFFFFu) - J;
                     w.scal[SC_SIZE] = size;
@@ -505,7 +516,21 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
                 if (npend == 0 && ctx.tid == 0) {
                     w.scal[SC_NEWC] = 0; w.scal[SC_NEWM] = 0; w.scal[SC_DONE] = 1;
                 }
+                // equal keys inside the consumed suffix [npend - J, npend) (or across its lower edge)?
+                for (int sIdx = npend - J + ctx.tid; sIdx < npend; sIdx += ctx.nthr)
+                    if (sIdx > 0 && (uint32_t)(arr[sIdx] >> 32) == (uint32_t)(arr[sIdx - 1] >> 32)) w.scal[SC_TIE] = 1;
+                ctx.sync();
+            };
+            rank_sort();
+            split_scan();
+            if (w.scal[SC_TIE]) {
+                ctx.sync();                                        // everybody has read SC_TIE before it is reset
+                if (ctx.tid == 0) { stdsort::introsort_loop(w.pend, npend); w.scal[SC_NREPLAY] += 1; }
+                ctx.sync();
+                rank_sort();
+                split_scan();
             }
+            for (int i = ctx.tid; i < npend; i += ctx.nthr) w.pend[i] = w.lsort[i];
             ctx.sync();
             ctx.mark(7);
             // (R4) create the children of the J split nodes (processing order = from the back of the sorted array)

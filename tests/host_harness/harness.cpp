@@ -17,6 +17,11 @@ struct HostCtx {
     void sync() {}
     void sync_warp() {}
     void sort_u64(uint64_t* a, int n) { std::sort(a, a + n); }
+    void sort_tree_keys(uint64_t* a, int m, int npad, int bshift, int nb) {
+        for (int i = 0; i < m; ++i)
+            if ((long long)(a[i] >> bshift) >= nb) std::abort();          // every key must fall into a bucket
+        std::sort(a, a + npad);
+    }
     int warp_id() const { return 0; }
     int num_warps() const { return 1; }
     int lane() const { return 0; }
@@ -66,6 +71,10 @@ void hh_realsort(uint64_t* v, int n) {
     std::sort(v, v + n, [](const uint64_t& a, const uint64_t& b) { return (uint32_t)(a >> 32) < (uint32_t)(b >> 32); });
 }
 
+// serial std::sort replays of the last hh_octree call | (sorted final phase ran) << 16
+static int g_last_replays = 0;
+int hh_octree_last_replays() { return g_last_replays; }
+
 // Quad-tree distribution of packed candidates for level `level` of the given configuration.
 int hh_octree(int W, int H, int nfeatures, float scale, int nlevels, int level, const uint32_t* cand, int M,
               int N_override, uint32_t* out, int outCap) {
@@ -85,6 +94,7 @@ int hh_octree(int W, int H, int nfeatures, float scale, int nlevels, int level, 
     w.pend = pend.data(); w.next = next.data(); w.next2 = next2.data(); w.meta = meta.data(); w.qbase = qbase.data(); w.hist = hist.data(); w.part = part.data(); w.scal = scal.data();
     HostCtx ctx;
     distribute_quadtree(ctx, cand, M, N, g, w, out, outCap);
+    g_last_replays = scal[SC_NREPLAY] | (scal[SC_PHASEB] << 16);
     return scal[SC_NOUT];
 }
 

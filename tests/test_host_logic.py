@@ -98,9 +98,13 @@ def test_std_sort_replay_matches_libstdcxx(hh):
 
 
 def test_octree_core_on_real_candidates(hh, oracle):
+    """Real FAST candidates of every level.  Also a census of the two ways the final phase is evaluated: the serial
+    std::sort replay only runs when equal (count, UL.x) keys meet inside the part of the sorted array that is consumed;
+    both ways must occur here (and both equal the oracle = the reference)."""
+    phase_b = replays = 0
     for (W, H, nf) in [(640, 480, 1000), (752, 480, 1200), (1241, 376, 2000), (640, 480, 5000), (640, 480, 200)]:
         tb = oracle.tables(nf)
-        for seed in range(2):
+        for seed in range(4):
             py = oracle.pyramid(synthetic_frame(seed + 100, W, H))
             for l in range(8):
                 xyr, _ = oracle.grid_fast(py[l])
@@ -108,6 +112,11 @@ def test_octree_core_on_real_candidates(hh, oracle):
                 sel = oracle.octree(xyr, 16, w - 16, 16, h - 16, int(tb["quota"][l]))
                 got = run_octree(hh, W, H, nf, 8, l, xyr)
                 assert np.array_equal(xyr[sel], got), (W, H, nf, seed, l)
+                st = hh.hh_octree_last_replays()
+                phase_b += st >> 16
+                replays += 1 if (st & 0xFFFF) else 0
+    print("sorted final phase ran in %d problems, %d of them needed the serial std::sort replay" % (phase_b, replays))
+    assert phase_b > 100 and 0 < replays < phase_b
 
 
 def test_octree_core_adversarial(hh, oracle):

@@ -87,6 +87,12 @@ int rumi_orb_signal_stream(rumi_orb* h, void* stream);
  * HOST pointers.  Returns n (like the reference) or an error code. */
 int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,
                       uint8_t* desc);
+/* The same for MANY key frames of one shape in one call (one upload, one launch): frame f = imgs + f * frame_pitch, its
+ * keypoints are kps[kp_off[f] .. kp_off[f + 1]) (kp_off[0] == 0), desc[k] belongs to kps[k].  This is how the cloud key
+ * frames of a submap merge get real descriptors (they carry zero descriptors in the reference,
+ * R/src/cloud_edge_main.cpp:937).  Returns kp_off[nimg] or an error code. */
+int rumi_orb_describe_batch(rumi_orb* h, const uint8_t* imgs, int nimg, int w, int h_px, size_t stride, size_t frame_pitch,
+                            const rumi_kp* kps, const int32_t* kp_off, uint8_t* desc);
 
 /* mvImagePyramid[level] of the LAST rumi_orb_extract call (R/include/cloud_edge_slam_lib/ORBextractor.h:86;
  * read by Frame::ComputeStereoMatches, R/lib_src/Frame.cc:834,918-932).  Copies the level to host memory. */
@@ -141,6 +147,16 @@ int rumi_hamming_top2_device(rumi_match* m, const uint8_t* dQ, int nq, const uin
  * (-1, 256, 256) for an empty train set and for rows no segment covers.  Result == rumi_hamming_top2 pair by pair. */
 int rumi_hamming_top2_pairs(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, const int32_t* segs,
                             int nseg, int32_t* idx1, uint16_t* d1, uint16_t* d2);
+/* Candidate-list matching -- the form every window / projection search of ORBmatcher takes (SearchByProjection,
+ * R/lib_src/ORBmatcher.cc:70-111; SearchForInitialization, :606-630; ...): query q is compared ONLY with the train rows
+ * cand_idx[cand_off[q] .. cand_off[q + 1]), e.g. what Frame::GetFeaturesInArea (R/lib_src/Frame.cc:695-750) returned for
+ * it.  dist[k] = DescriptorDistance(Q[q], T[cand_idx[k]]) for every list entry k -- the adapters replay the call site's own
+ * acceptance on them (several sites skip candidates depending on EARLIER acceptances: ORBmatcher.cc:86-88, :617) -- and,
+ * when idx1 / d1 / idx2 / d2 are given, the raw best and second best of every list in list order (strict '<': the
+ * earliest entry wins ties; idx2 lets the caller apply the level-aware ratio test of :101-104; -1 / 256 when a list has
+ * fewer than one / two entries).  cand_off has nq + 1 entries, cand_off[0] == 0.  HOST pointers. */
+int rumi_hamming_candidates(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, const int32_t* cand_off,
+                            const int32_t* cand_idx, uint16_t* dist, int32_t* idx1, uint16_t* d1, int32_t* idx2, uint16_t* d2);
 int rumi_match_timer_start(rumi_match* m);
 int rumi_match_timer_stop(rumi_match* m, float* ms);
 /* Which top-2 kernel the last rumi_hamming_top2* call used: 1 = LOP3+POPC (small problems), 3 = tcgen05 / TMEM int8

@@ -1,0 +1,231 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (used by tests/, __graft_entry__.smoke() and bench.py's CPU baseline legs).
+// CPU restatement of the candidate-list matchers of the reference and of the feature grid that feeds them:
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea      R/lib_src/Frame.cc:441-466, 752-767, 695-750
+//   ORBmatcher::SearchForInitialization                              R/lib_src/ORBmatcher.cc:581-680
+//   ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...)     R/lib_src/ORBmatcher.cc:39-189 (mono frame, Nleft == -1)
+//   CloudMerging's pixel-distance key-point association              R/lib_src/CloudMerging.cc:503-551
+// Pinned against the UNMODIFIED reference functions compiled into oracle/_ref/librefframe.so
+// (tests/test_ref_frame_pin.py).  FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48 (R/include/cloud_edge_slam_lib/Frame.h:42-43).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct KP { float x, y, size, angle, response; int32_t octave, class_id; };
+static_assert(sizeof(KP) == 28, "cv::KeyPoint layout");
+
+constexpr int kGridCols = 64, kGridRows = 48;
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;      // ORBmatcher.cc:31-33
+
+// ORBmatcher::DescriptorDistance (ORBmatcher.cc:1830-1844)
+inline int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        std::memcpy(&x, a + 4 * i, 4); std::memcpy(&y, b + 4 * i, 4);
+        uint32_t v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+struct Grid {
+    float minX, minY, wInv, hInv;
+    const KP* kps; int n;
+    std::vector<int> cell[kGridCols][kGridRows];
+    Grid(const KP* k, int nn, int x0, int y0, int x1, int y1) : kps(k), n(nn) {
+        minX = (float)x0; minY = (float)y0;
+        wInv = static_cast<float>(kGridCols) / static_cast<float>(x1 - x0);      // Frame.cc:98-99
+        hInv = static_cast<float>(kGridRows) / static_cast<float>(y1 - y0);
+        for (int i = 0; i < n; ++i) {                                            // AssignFeaturesToGrid :455-465
+            const int px = (int)std::round((kps[i].x - minX) * wInv), py = (int)std::round((kps[i].y - minY) * hInv);   // PosInGrid
+            if (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) continue;
+            cell[px][py].push_back(i);
+        }
+    }
+    // GetFeaturesInArea :695-750 (Nleft == -1)
+    void query(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+        out.clear();
+        const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * wInv));
+        if (nMinCellX >= kGridCols) return;
+        const int nMaxCellX = std::min(kGridCols - 1, (int)std::ceil((x - minX + r) * wInv));
+        if (nMaxCellX < 0) return;
+        const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * hInv));
+        if (nMinCellY >= kGridRows) return;
+        const int nMaxCellY = std::min(kGridRows - 1, (int)std::ceil((y - minY + r) * hInv));
+        if (nMaxCellY < 0) return;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+            for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+                for (int j : cell[ix][iy]) {
+                    const KP& kp = kps[j];
+                    if (bCheckLevels) {
+                        if (kp.octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    }
+                    const float dx = kp.x - x, dy = kp.y - y;
+                    if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(j);
+                }
+    }
+};
+
+// ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:1795-1826)
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mo_features_in_area(const void* kps, int n, int minX, int minY, int maxX, int maxY, float x, float y, float r,
+                        int minLevel, int maxLevel, int32_t* out, int cap) {
+    Grid g((const KP*)kps, n, minX, minY, maxX, maxY);
+    std::vector<int> v;
+    g.query(x, y, r, minLevel, maxLevel, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
+// CSR candidate lists of many queries on one grid: off[nq + 1], idx[cap]; returns the total (may exceed cap: call again).
+int mo_candidate_lists(const void* kps, int n, int minX, int minY, int maxX, int maxY, const float* qxy, const float* qr,
+                       const int32_t* qMinLevel, const int32_t* qMaxLevel, int nq, int32_t* off, int32_t* idx, int cap) {
+    Grid g((const KP*)kps, n, minX, minY, maxX, maxY);
+    std::vector<int> v;
+    int tot = 0;
+    for (int q = 0; q < nq; ++q) {
+        off[q] = tot;
+        g.query(qxy[2 * q], qxy[2 * q + 1], qr[q], qMinLevel ? qMinLevel[q] : -1, qMaxLevel ? qMaxLevel[q] : -1, v);
+        for (int j : v) { if (tot < cap) idx[tot] = j; ++tot; }
+    }
+    off[nq] = tot;
+    return tot;
+}
+
+// ORBmatcher::SearchForInitialization (ORBmatcher.cc:581-680).  prev: vbPrevMatched [n1][2], updated in place.
+int mo_search_for_initialization(const void* k1v, const uint8_t* d1, int n1, const void* k2v, const uint8_t* d2, int n2,
+                                 int minX, int minY, int maxX, int maxY, float* prev, int windowSize, float ratio, int checkOri,
+                                 int32_t* vnMatches12) {
+    const KP* k1 = (const KP*)k1v; const KP* k2 = (const KP*)k2v;
+    Grid g(k2, n2, minX, minY, maxX, maxY);
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(n2, INT_MAX), vnMatches21(n2, -1), vIndices2;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int level1 = k1[i1].octave;
+        if (level1 > 0) continue;
+        g.query(prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * ratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) {
+                    float rot = k1[i1].angle - k2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; ++i1)
+        if (vnMatches12[i1] >= 0) { prev[2 * i1] = k2[vnMatches12[i1]].x; prev[2 * i1 + 1] = k2[vnMatches12[i1]].y; }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, false, ..) on a mono frame without depth (Nleft == -1, mvuRight
+// <= 0): ORBmatcher.cc:39-118.  frameMatch[j] = map point assigned to frame feature j (or -1).
+int mo_search_by_projection(const void* kFv, const uint8_t* dF, int nF, const float* scaleFactors, int minX, int minY, int maxX,
+                            int maxY, const float* proj, const int32_t* level, const float* viewCos, const uint8_t* dMP,
+                            const uint8_t* hasObs, int nMP, float th, float ratio, int32_t* frameMatch) {
+    const KP* kF = (const KP*)kFv;
+    Grid g(kF, nF, minX, minY, maxX, maxY);
+    for (int j = 0; j < nF; ++j) frameMatch[j] = -1;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < nMP; ++iMP) {
+        const int nPredictedLevel = level[iMP];
+        float r = viewCos[iMP] > 0.998 ? 2.5f : 4.0f;                   // RadiusByViewingCos :191-196
+        if (bFactor) r *= th;
+        g.query(proj[2 * iMP], proj[2 * iMP + 1], r * scaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, vIndices);
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (frameMatch[idx] >= 0 && hasObs[frameMatch[idx]]) continue;           // F.mvpMapPoints[idx]->Observations() > 0
+            const int dist = descriptor_distance(dMP + 32 * (size_t)iMP, dF + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kF[idx].octave; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = kF[idx].octave; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > ratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= ratio * bestDist2) { frameMatch[bestIdx] = iMP; nmatches++; }
+        }
+    }
+    return nmatches;
+}
+
+// CloudMerging.cc:503-551 for one matched key-frame pair: per key point of key frame 1 the nearest key point of key
+// frame 2 in PIXEL distance (< tol, both with a map point) among GetFeaturesInArea(u, v, tol).  match12[i] = j or -1.
+int mo_associate_pixels(const void* k1v, const uint8_t* valid1, int n1, const void* k2v, const uint8_t* valid2, int n2,
+                        int minX, int minY, int maxX, int maxY, float tol, int32_t* match12) {
+    const KP* k1 = (const KP*)k1v; const KP* k2 = (const KP*)k2v;
+    Grid g(k2, n2, minX, minY, maxX, maxY);
+    std::vector<int> v;
+    int matchNum = 0;
+    for (int i = 0; i < n1; ++i) {
+        match12[i] = -1;
+        const float u = k1[i].x, vv = k1[i].y;
+        g.query(u, vv, tol, -1, -1, v);
+        if (v.empty()) continue;
+        float best_dist = tol;
+        int best_idx = -1;
+        for (int j : v) {
+            const float delta = (float)std::sqrt(std::pow(u - k2[j].x, 2) + std::pow(vv - k2[j].y, 2));
+            if (delta < best_dist && valid1[i] && valid2[j]) { best_idx = j; best_dist = delta; }
+        }
+        if (best_idx == -1) continue;
+        ++matchNum;
+        match12[i] = best_idx;
+    }
+    return matchNum;
+}
+
+}  // extern "C"

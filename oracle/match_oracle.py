@@ -1,0 +1,114 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/match_oracle.cpp (feature grid, SearchForInitialization,
+SearchByProjection, CloudMerging's pixel association).  Pinned against oracle/_ref/librefframe.so."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .orb_oracle import KP_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libmatch_oracle.so")
+_u8p, _f32p, _i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "match_oracle.cpp")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libmatch_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def features_in_area(kps, bounds, x, y, r, min_level=-1, max_level=-1):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    L = lib()
+    L.mo_features_in_area.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                      C.c_int, C.c_int, _i32p, C.c_int]
+    n = L.mo_features_in_area(kps.ctypes.data, len(kps), *[int(b) for b in bounds], float(x), float(y), float(r),
+                              int(min_level), int(max_level), _p(out, _i32p), len(out))
+    return out[:n].copy()
+
+
+def candidate_lists(kps, bounds, qxy, qr, qmin=None, qmax=None):
+    """CSR candidate lists (off[nq+1], idx) of GetFeaturesInArea for many queries on one frame grid."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    qxy = np.ascontiguousarray(qxy, np.float32).reshape(-1, 2)
+    nq = len(qxy)
+    qr = np.ascontiguousarray(np.broadcast_to(np.asarray(qr, np.float32), (nq,)))
+    qmin = None if qmin is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qmin, np.int32), (nq,)))
+    qmax = None if qmax is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qmax, np.int32), (nq,)))
+    off = np.zeros(nq + 1, np.int32)
+    L = lib()
+    L.mo_candidate_lists.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _i32p, _i32p, C.c_int,
+                                     _i32p, _i32p, C.c_int]
+    cap = max(64 * nq, 1024)
+    while True:
+        idx = np.zeros(cap, np.int32)
+        tot = L.mo_candidate_lists(kps.ctypes.data, len(kps), *[int(b) for b in bounds], _p(qxy, _f32p), _p(qr, _f32p),
+                                   None if qmin is None else _p(qmin, _i32p), None if qmax is None else _p(qmax, _i32p), nq,
+                                   _p(off, _i32p), _p(idx, _i32p), cap)
+        if tot <= cap:
+            return off, idx[:tot].copy()
+        cap = tot
+
+
+def search_for_initialization(k1, d1, k2, d2, bounds, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32), np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.zeros(max(len(k1), 1), np.int32)
+    L = lib()
+    L.mo_search_for_initialization.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, _f32p, C.c_int, C.c_float, C.c_int, _i32p]
+    n = L.mo_search_for_initialization(k1.ctypes.data, _p(d1, _u8p), len(k1), k2.ctypes.data, _p(d2, _u8p), len(k2),
+                                       *[int(b) for b in bounds], _p(prev, _f32p), int(window), float(nnratio),
+                                       1 if check_ori else 0, _p(m12, _i32p))
+    return n, m12[:len(k1)], prev
+
+
+def search_by_projection(kF, dF, scale_factors, bounds, proj, level, view_cos, dMP, has_obs, th=3.0, nnratio=0.8):
+    kF = np.ascontiguousarray(kF, KP_DTYPE)
+    dF, dMP = np.ascontiguousarray(dF, np.uint8).reshape(-1, 32), np.ascontiguousarray(dMP, np.uint8).reshape(-1, 32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    proj = np.ascontiguousarray(proj, np.float32)
+    level = np.ascontiguousarray(level, np.int32)
+    vc = np.ascontiguousarray(view_cos, np.float32)
+    ho = np.ascontiguousarray(has_obs, np.uint8)
+    out = np.zeros(max(len(kF), 1), np.int32)
+    L = lib()
+    L.mo_search_by_projection.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i32p,
+                                          _f32p, _u8p, _u8p, C.c_int, C.c_float, C.c_float, _i32p]
+    n = L.mo_search_by_projection(kF.ctypes.data, _p(dF, _u8p), len(kF), _p(sf, _f32p), *[int(b) for b in bounds],
+                                  _p(proj, _f32p), _p(level, _i32p), _p(vc, _f32p), _p(dMP, _u8p), _p(ho, _u8p), len(dMP),
+                                  float(th), float(nnratio), _p(out, _i32p))
+    return n, out[:len(kF)]
+
+
+def associate_pixels(k1, valid1, k2, valid2, bounds, tol=3.0):
+    """CloudMerging.cc:503-551 for one key-frame pair: (matchNum, match12)."""
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    v1, v2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+    out = np.zeros(max(len(k1), 1), np.int32)
+    L = lib()
+    L.mo_associate_pixels.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, _i32p]
+    n = L.mo_associate_pixels(k1.ctypes.data, _p(v1, _u8p), len(k1), k2.ctypes.data, _p(v2, _u8p), len(k2),
+                              *[int(b) for b in bounds], float(tol), _p(out, _i32p))
+    return n, out[:len(k1)]

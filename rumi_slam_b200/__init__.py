@@ -3,6 +3,6 @@ ORBextractor / ORBmatcher interface.  Product code = csrc/ (CUDA + C ABI, includ
 mirrors in extractor.py / matcher.py / bow.py / flow.py / sharding.py.  No CPU fallback."""
 from ._lib import KP_DTYPE, LIB_PATH, RumiError  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
-from .matcher import ORBmatcher  # noqa: F401
+from .matcher import FrameGrid, ORBmatcher  # noqa: F401
 from .bow import ORBVocabulary  # noqa: F401
 from .flow import KFDSample, SparsePyrLK  # noqa: F401

@@ -44,6 +44,7 @@ SIGNATURES = {
     "rumi_match_comm_adopt": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "rumi_hamming_top2_sharded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "rumi_orb_describe": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t, _vp, C.c_int, _vp]),
+    "rumi_orb_describe_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "rumi_orb_pyramid_level": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _i32p, _i32p]),
     "rumi_orb_blurred_level": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _i32p, _i32p]),
     "rumi_orb_debug_candidates": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "rumi_match_destroy": (None, [_vp]),
     "rumi_hamming_top2": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "rumi_hamming_top2_pairs": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "rumi_hamming_candidates": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rumi_hamming_top2_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "rumi_top2_pack_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int]),
     "rumi_top2_merge_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),

@@ -128,6 +128,7 @@ struct rumi_orb {
     // device-side error flags in mapped pinned host memory (per handle, read for free at every host sync point):
     // [0] a TMA transaction of the tile pyramid timed out, [1] a pyramid level dependency timed out
     int* errHost = nullptr; int* errDev = nullptr;
+    uint8_t* descBuf = nullptr; size_t descCap = 0;   // scratch of rumi_orb_describe* (images, keypoints, descriptors)
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
     int dbgCell = 0;
@@ -655,6 +656,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     cudaFree(h->pyrTables);
     cudaFree(h->dbgBuf);
     cudaFree(h->octClk);
+    cudaFree(h->descBuf);
     if (h->errHost) cudaFreeHost(h->errHost);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->evStart) cudaEventDestroy(h->evStart);
@@ -801,12 +803,16 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
     return RUMI_OK;
 }
 
-int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,
-                      uint8_t* desc) {
+int rumi_orb_describe_batch(rumi_orb* h, const uint8_t* imgs, int nimg, int w, int h_px, size_t stride, size_t frame_pitch,
+                            const rumi_kp* kps, const int32_t* kp_off, uint8_t* desc) {
     if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
-    if (!img || w <= 0 || h_px <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
-    if (n < 0 || (n > 0 && (!kps || !desc)) || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad arguments");
+    if (!imgs || w <= 0 || h_px <= 0 || nimg <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
+    if (stride < (size_t)w || !kp_off || kp_off[0] != 0) return fail(RUMI_ERR_ARG, "bad arguments");
+    for (int f = 0; f < nimg; ++f)
+        if (kp_off[f + 1] < kp_off[f]) return fail(RUMI_ERR_ARG, "kp_off must be non-decreasing");
+    const int n = kp_off[nimg];
     if (n == 0) return 0;
+    if (!kps || !desc) return fail(RUMI_ERR_ARG, "NULL keypoints / descriptors");
     for (int i = 0; i < n; ++i) {
         const int x = rint_f(kps[i].x), y = rint_f(kps[i].y);
         if (x < kEdge || y < kEdge || x >= w - kEdge || y >= h_px - kEdge)
@@ -815,19 +821,39 @@ int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t s
     CU_TRY(cudaSetDevice(h->device));
     if (!h->ws[0].stream) CU_TRY(cudaStreamCreateWithFlags(&h->ws[0].stream, cudaStreamNonBlocking));
     cudaStream_t s = h->ws[0].stream;
-    uint8_t *dImg = nullptr, *dDesc = nullptr;
-    KeyPointRec* dK = nullptr;
     const int dstride = align_up(w, 16);
-    CU_TRY(cudaMalloc(&dImg, (size_t)dstride * h_px));
-    CU_TRY(cudaMalloc(&dDesc, 32 * (size_t)n));
-    CU_TRY(cudaMalloc(&dK, sizeof(KeyPointRec) * (size_t)n));
-    CU_TRY(cudaMemcpy2DAsync(dImg, dstride, img, stride, w, h_px, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(dK, kps, sizeof(KeyPointRec) * (size_t)n, cudaMemcpyHostToDevice, s));
-    launch_describe_given(dImg, w, h_px, dstride, dK, n, dDesc, s);
-    CU_TRY(cudaMemcpyAsync(desc, dDesc, 32 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    const size_t imgBytes = (size_t)dstride * h_px;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oK = al(imgBytes * nimg), oD = oK + al(sizeof(KeyPointRec) * (size_t)n), oO = oD + al(32 * (size_t)n),
+                 need = oO + al(4 * ((size_t)nimg + 1));
+    if (need > h->descCap) {                                   // scratch of the describe calls: grows, never shrinks
+        cudaFree(h->descBuf); h->descBuf = nullptr; h->descCap = 0;
+        CU_TRY(cudaMalloc(&h->descBuf, need));
+        h->descCap = need;
+    }
+    uint8_t* p = h->descBuf;
+    if (frame_pitch == stride * (size_t)h_px || nimg == 1) {
+        CU_TRY(cudaMemcpy2DAsync(p, dstride, imgs, stride, w, (size_t)h_px * nimg, cudaMemcpyHostToDevice, s));
+    } else {
+        for (int f = 0; f < nimg; ++f)
+            CU_TRY(cudaMemcpy2DAsync(p + f * imgBytes, dstride, imgs + f * frame_pitch, stride, w, h_px, cudaMemcpyHostToDevice, s));
+    }
+    CU_TRY(cudaMemcpyAsync(p + oK, kps, sizeof(KeyPointRec) * (size_t)n, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p + oO, kp_off, 4 * ((size_t)nimg + 1), cudaMemcpyHostToDevice, s));
+    launch_describe_given(p, w, h_px, dstride, (long long)imgBytes, nimg, reinterpret_cast<const int*>(p + oO),
+                          reinterpret_cast<const KeyPointRec*>(p + oK), n, p + oD, s);
+    h->launches += 1;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(desc, p + oD, 32 * (size_t)n, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
-    cudaFree(dImg); cudaFree(dDesc); cudaFree(dK);
     return n;
+}
+
+int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,
+                      uint8_t* desc) {
+    if (n < 0) return fail(RUMI_ERR_ARG, "bad arguments");
+    const int32_t off[2] = {0, n};
+    return rumi_orb_describe_batch(h, img, 1, w, h_px, stride, stride * (size_t)(h_px > 0 ? h_px : 0), kps, off, desc);
 }
 
 static int copy_level(rumi_orb* h, const uint8_t* base, int level, uint8_t* dst, size_t dst_stride, int* w, int* hp) {
@@ -1235,6 +1261,55 @@ int rumi_hamming_top2_pairs(rumi_match* m, const uint8_t* Q, int nq, const uint8
     CU_TRY(cudaMemcpyAsync(d1, dD1, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(d2, dD2, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
+    return RUMI_OK;
+}
+
+int rumi_hamming_candidates(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T, int nt, const int32_t* cand_off,
+                            const int32_t* cand_idx, uint16_t* dist, int32_t* idx1, uint16_t* d1, int32_t* idx2, uint16_t* d2) {
+    if (!m) return fail(RUMI_ERR_ARG, "context is NULL");
+    if (nq < 0 || nt < 0) return fail(RUMI_ERR_ARG, "negative sizes");
+    if (nq == 0) return RUMI_OK;
+    if (!Q || !cand_off || cand_off[0] != 0) return fail(RUMI_ERR_ARG, "NULL buffer / cand_off[0] != 0");
+    const bool top2 = idx1 || d1 || idx2 || d2;
+    if (top2 && !(idx1 && d1 && idx2 && d2)) return fail(RUMI_ERR_ARG, "the four top-2 outputs go together");
+    for (int q = 0; q < nq; ++q) {
+        if (cand_off[q + 1] < cand_off[q]) return fail(RUMI_ERR_ARG, "cand_off must be non-decreasing");
+        if (top2 && cand_off[q + 1] - cand_off[q] >= 0xFFFF) return fail(RUMI_ERR_ARG, "query %d: more than 65534 candidates", q);
+    }
+    const int ne = cand_off[nq];
+    if (ne > 0 && (!cand_idx || !dist || !T)) return fail(RUMI_ERR_ARG, "NULL candidate buffers");
+    for (int k = 0; k < ne; ++k)
+        if (cand_idx[k] < 0 || cand_idx[k] >= nt) return fail(RUMI_ERR_ARG, "cand_idx[%d] = %d outside the train set", k, cand_idx[k]);
+    CU_TRY(cudaSetDevice(m->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oT = al(32 * (size_t)nq), oOff = oT + al(32 * (size_t)std::max(nt, 1)), oIdx = oOff + al(4 * ((size_t)nq + 1)),
+                 oDist = oIdx + al(4 * (size_t)std::max(ne, 1)), oRes = oDist + al(2 * (size_t)std::max(ne, 1)),
+                 need = oRes + al(12 * (size_t)nq);
+    int rc = grow((void**)&m->dT, &m->tCap, need);
+    if (rc) return rc;
+    uint8_t* p = m->dT;
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(p, Q, 32 * (size_t)nq, cudaMemcpyHostToDevice, s));
+    if (nt > 0) CU_TRY(cudaMemcpyAsync(p + oT, T, 32 * (size_t)nt, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p + oOff, cand_off, 4 * ((size_t)nq + 1), cudaMemcpyHostToDevice, s));
+    if (ne > 0) CU_TRY(cudaMemcpyAsync(p + oIdx, cand_idx, 4 * (size_t)ne, cudaMemcpyHostToDevice, s));
+    int32_t* dI1 = reinterpret_cast<int32_t*>(p + oRes);
+    int32_t* dI2 = dI1 + nq;
+    uint16_t* dD1 = reinterpret_cast<uint16_t*>(dI2 + nq);
+    uint16_t* dD2 = dD1 + nq;
+    launch_hamming_candidates(p, nq, p + oT, reinterpret_cast<const int32_t*>(p + oOff), reinterpret_cast<const int32_t*>(p + oIdx),
+                              reinterpret_cast<uint16_t*>(p + oDist), top2 ? dI1 : nullptr, dD1, dI2, dD2, s);
+    m->launches += 1;
+    m->lastPath = 1;
+    CU_TRY(cudaGetLastError());
+    if (ne > 0) CU_TRY(cudaMemcpyAsync(dist, p + oDist, 2 * (size_t)ne, cudaMemcpyDeviceToHost, s));
+    if (top2) {
+        CU_TRY(cudaMemcpyAsync(idx1, dI1, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(idx2, dI2, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(d1, dD1, 2 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(d2, dD2, 2 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
     return RUMI_OK;
 }
 

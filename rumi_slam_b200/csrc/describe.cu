@@ -160,24 +160,35 @@ void launch_describe(const DescribeArgs& a, const OrbConst& oc, cudaStream_t s) 
 }
 
 // CloudFrameComputeDescriptors (R/lib_src/ORBextractor.cc:989-1011): caller's keypoints (pt, angle as given),
-// caller's image as is -- no pyramid, no blur, no orientation.
-__global__ void __launch_bounds__(256) describe_given_kernel(const uint8_t* img, int w, int h, int stride,
+// caller's image as is -- no pyramid, no blur, no orientation.  Batched over images of one shape: keypoint i belongs
+// to the image f with kpOff[f] <= i < kpOff[f + 1] (nimg == 1: kpOff may be null).
+__global__ void __launch_bounds__(256) describe_given_kernel(const uint8_t* imgs, int w, int h, int stride, long long pitch,
+                                                             int nimg, const int* __restrict__ kpOff,
                                                              const KeyPointRec* kps, int n, uint8_t* desc) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + warp;
     if (i >= n) return;
+    int f = 0;
+    if (nimg > 1) {                                          // largest f with kpOff[f] <= i
+        int lo = 0, hi = nimg;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (kpOff[mid] <= i) lo = mid; else hi = mid;
+        }
+        f = lo;
+    }
     const KeyPointRec k = kps[i];
     const int x = __float2int_rn(k.x), y = __float2int_rn(k.y);
     const float rad = __fmul_rn(k.angle, 0.017453292519943295f);
     float sb, ca;
     glibc_sincosf(rad, &sb, &ca);
-    desc[(long long)i * 32 + lane] = brief_byte(img + (long long)y * stride + x, stride, ca, sb, lane);
+    desc[(long long)i * 32 + lane] = brief_byte(imgs + f * pitch + (long long)y * stride + x, stride, ca, sb, lane);
 }
 
-void launch_describe_given(const uint8_t* img, int w, int h, int stride, const KeyPointRec* kps, int n,
-                           uint8_t* desc, cudaStream_t s) {
+void launch_describe_given(const uint8_t* imgs, int w, int h, int stride, long long pitch, int nimg, const int* kpOff,
+                           const KeyPointRec* kps, int n, uint8_t* desc, cudaStream_t s) {
     if (n <= 0) return;
-    describe_given_kernel<<<(n + 7) / 8, 256, 0, s>>>(img, w, h, stride, kps, n, desc);
+    describe_given_kernel<<<(n + 7) / 8, 256, 0, s>>>(imgs, w, h, stride, pitch, nimg, kpOff, kps, n, desc);
 }
 
 }  // namespace rumi

@@ -129,8 +129,8 @@ void launch_assign_slots(const DescribeArgs& a, const OrbConst& oc, cudaStream_t
 void launch_describe(const DescribeArgs& a, const OrbConst& oc, cudaStream_t s);
 
 // CloudFrameComputeDescriptors: descriptors of given keypoints on a given (un-pyramided, un-blurred) image.
-void launch_describe_given(const uint8_t* img, int w, int h, int stride, const KeyPointRec* kps, int n,
-                           uint8_t* desc, cudaStream_t s);
+void launch_describe_given(const uint8_t* imgs, int w, int h, int stride, long long pitch, int nimg, const int* kpOff,
+                           const KeyPointRec* kps, int n, uint8_t* desc, cudaStream_t s);
 
 // ---- matching ----
 // partial[slice][nq] = {d1:16 | d2:16 | global train index:32} of train rows [slice*sliceRows, ...) (+tBase)
@@ -146,6 +146,8 @@ void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt
 struct PairSegment { int32_t qStart, qCount, tStart, tCount; };   // one (query set, train set) pair of K8-S
 void launch_hamming_top2_segments(const uint8_t* Q, const uint8_t* T, const PairSegment* segs, int nseg, int maxQ,
                                   int32_t* idx1, uint16_t* d1, uint16_t* d2, cudaStream_t s);
+void launch_hamming_candidates(const uint8_t* Q, int nq, const uint8_t* T, const int32_t* off, const int32_t* idx,
+                               uint16_t* dist, int32_t* idx1, uint16_t* d1, int32_t* idx2, uint16_t* d2, cudaStream_t s);
 void launch_top2_merge(const uint64_t* packed, int nshards, int nq, int32_t* idx1, uint16_t* d1, uint16_t* d2,
                        cudaStream_t s);
 void launch_top2_merge_packed(const uint64_t* packed, int nshards, int nq, uint64_t* out, cudaStream_t s);

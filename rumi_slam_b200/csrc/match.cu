@@ -152,6 +152,52 @@ hamming_top2_segments_kernel(const uint8_t* __restrict__ Q, const uint8_t* __res
     }
 }
 
+// K8-C: candidate-list matching -- the form every projection / window search of ORBmatcher uses: query q is compared only
+// with the train rows listed for it (Frame::GetFeaturesInArea, R/lib_src/Frame.cc:695-750).  One warp per query, lanes
+// stride over its list: every entry's distance is written out (the adapters replay the call sites' order-dependent
+// acceptance rules on them), plus the raw top-2 in list order (strict '<': the earliest entry wins ties).
+__global__ void __launch_bounds__(256)
+hamming_candidates_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ T, const int32_t* __restrict__ off,
+                          const int32_t* __restrict__ idx, uint16_t* __restrict__ dist, int32_t* __restrict__ idx1,
+                          uint16_t* __restrict__ d1, int32_t* __restrict__ idx2, uint16_t* __restrict__ d2) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const uint4* qs = reinterpret_cast<const uint4*>(Q) + (size_t)q * 2;
+    const uint4 qa = __ldg(qs), qb = __ldg(qs + 1);
+    const int b = off[q], e = off[q + 1];
+    uint32_t k1 = (256u << 16) | 0xFFFFu, k2 = k1;                   // key = distance << 16 | position in the list
+    for (int p = b + lane; p < e; p += 32) {
+        const uint4* ts = reinterpret_cast<const uint4*>(T) + (size_t)idx[p] * 2;
+        const uint4 ta = __ldg(ts), tb = __ldg(ts + 1);
+        const uint32_t d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                           __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+        dist[p] = (uint16_t)d;
+        const uint32_t key = (d << 16) | (uint32_t)min(p - b, 0xFFFE);
+        k2 = min(k2, max(key, k1));
+        k1 = min(k1, key);
+    }
+    if (!idx1) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
+        k2 = min(max(k1, o1), min(k2, o2));
+        k1 = min(k1, o1);
+    }
+    if (lane == 0) {
+        const uint32_t e1 = k1 >> 16, e2 = k2 >> 16;
+        idx1[q] = e1 >= 256u ? -1 : idx[b + (int)(k1 & 0xFFFFu)];
+        d1[q] = (uint16_t)e1;
+        idx2[q] = e2 >= 256u ? -1 : idx[b + (int)(k2 & 0xFFFFu)];
+        d2[q] = (uint16_t)e2;
+    }
+}
+
+void launch_hamming_candidates(const uint8_t* Q, int nq, const uint8_t* T, const int32_t* off, const int32_t* idx,
+                               uint16_t* dist, int32_t* idx1, uint16_t* d1, int32_t* idx2, uint16_t* d2, cudaStream_t s) {
+    if (nq <= 0) return;
+    hamming_candidates_kernel<<<(nq + 7) / 8, 256, 0, s>>>(Q, nq, T, off, idx, dist, idx1, d1, idx2, d2);
+}
+
 void launch_hamming_top2_segments(const uint8_t* Q, const uint8_t* T, const PairSegment* segs, int nseg, int maxQ,
                                   int32_t* idx1, uint16_t* d1, uint16_t* d2, cudaStream_t s) {
     if (nseg <= 0 || maxQ <= 0) return;

@@ -141,6 +141,18 @@ class ORBextractor:
                                             ptr(kps), len(kps), ptr(desc)))
         return n, desc
 
+    def CloudFrameComputeDescriptorsBatch(self, images, keypoints, kp_off):
+        """CloudFrameComputeDescriptors for many key frames of one shape in ONE call: images [n, h, w] u8, keypoints of
+        frame f = keypoints[kp_off[f]:kp_off[f + 1]].  Returns the [total, 32] descriptors."""
+        images = np.ascontiguousarray(images, np.uint8)
+        kps = np.ascontiguousarray(keypoints, KP_DTYPE)
+        off = np.ascontiguousarray(kp_off, np.int32)
+        desc = np.zeros((len(kps), 32), np.uint8)
+        n, h, w = images.shape
+        check(self._L.rumi_orb_describe_batch(self._h, ptr(images), n, w, h, images.strides[1], images.strides[0], ptr(kps),
+                                              ptr(off), ptr(desc)))
+        return desc
+
     # ---- mvImagePyramid (ORBextractor.h:86): filled lazily from the device ----
     def _level(self, fn, level):
         w, h = C.c_int32(0), C.c_int32(0)

@@ -197,6 +197,141 @@ class ORBmatcher:
             out.append(np.where(ok, i1, -1))
         return out
 
+    # ---- candidate-list matching (the form SearchByProjection / SearchForInitialization use) ----
+    def candidates(self, Q, T, cand_off, cand_idx, top2=False):
+        """dist[k] = DescriptorDistance(Q[q], T[cand_idx[k]]) for every entry k of query q's list
+        cand_idx[cand_off[q]:cand_off[q + 1]]; with top2 also (idx1, d1, idx2, d2) per query in list order."""
+        Q = np.ascontiguousarray(Q, np.uint8).reshape(-1, 32)
+        T = np.ascontiguousarray(T, np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(cand_off, np.int32)
+        idx = np.ascontiguousarray(cand_idx, np.int32)
+        dist = np.zeros(max(len(idx), 1), np.uint16)
+        nq = len(Q)
+        if top2:
+            i1, i2 = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+            d1, d2 = np.zeros(nq, np.uint16), np.zeros(nq, np.uint16)
+            check(self._L.rumi_hamming_candidates(self._m, ptr(Q), nq, ptr(T), len(T), ptr(off), ptr(idx), ptr(dist), ptr(i1),
+                                                  ptr(d1), ptr(i2), ptr(d2)))
+            return dist[:len(idx)], (i1, d1, i2, d2)
+        check(self._L.rumi_hamming_candidates(self._m, ptr(Q), nq, ptr(T), len(T), ptr(off), ptr(idx), ptr(dist), None, None,
+                                              None, None))
+        return dist[:len(idx)]
+
+    # ---- ORBmatcher::SearchForInitialization (ORBmatcher.cc:581-680) ----
+    def SearchForInitialization(self, keys1, desc1, keys2, desc2, bounds, vbPrevMatched, windowSize=10):
+        """keys*: mvKeysUn of F1 / F2 (KP_DTYPE), bounds = F2's (mnMinX, mnMinY, mnMaxX, mnMaxY).  Returns (nmatches,
+        vnMatches12, updated vbPrevMatched).  The GPU computes the distance of every (level-0 key point of F1, window
+        candidate of F2) pair in one launch; the acceptance -- vMatchedDistance skip (:617), re-assignment of a taken
+        feature (:631-634), rotation histogram -- is replayed here in the reference's order."""
+        k1, k2 = np.ascontiguousarray(keys1, KP_DTYPE), np.ascontiguousarray(keys2, KP_DTYPE)
+        prev = np.array(vbPrevMatched, np.float32).reshape(-1, 2)
+        n1, n2 = len(k1), len(k2)
+        m12 = np.full(n1, -1, np.int32)
+        q = np.flatnonzero(k1["octave"] <= 0)                                 # level1 > 0: continue (:596-597)
+        grid = FrameGrid(k2, bounds)
+        off, idx = grid.candidate_lists(prev[q], float(windowSize), k1["octave"][q], k1["octave"][q])
+        dist = self.candidates(np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)[q], desc2, off, idx)
+        matched_dist = np.full(n2, np.iinfo(np.int32).max, np.int64)
+        m21 = np.full(n2, -1, np.int32)
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        nmatches = 0
+        ratio = np.float32(self.mfNNratio)
+        big = np.iinfo(np.int32).max
+        for qi, i1 in enumerate(q):
+            best, best2, best_idx = big, big, -1
+            for p in range(off[qi], off[qi + 1]):
+                i2, d = int(idx[p]), int(dist[p])
+                if matched_dist[i2] <= d:
+                    continue
+                if d < best:
+                    best2, best, best_idx = best, d, i2
+                elif d < best2:
+                    best2 = d
+            if best <= self.TH_LOW and np.float32(best) < np.float32(best2) * ratio:
+                if m21[best_idx] >= 0:
+                    m12[m21[best_idx]] = -1
+                    nmatches -= 1
+                m12[i1] = best_idx
+                m21[best_idx] = i1
+                matched_dist[best_idx] = best
+                nmatches += 1
+                if self.mbCheckOrientation:
+                    rot_hist[self._rot_bin(k1["angle"][i1], k2["angle"][best_idx])].append(int(i1))
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for i in range(self.HISTO_LENGTH):
+                if i in keep:
+                    continue
+                for i1 in rot_hist[i]:
+                    if m12[i1] >= 0:
+                        m12[i1] = -1
+                        nmatches -= 1
+        ok = m12 >= 0
+        prev[ok, 0] = k2["x"][m12[ok]]
+        prev[ok, 1] = k2["y"][m12[ok]]
+        return nmatches, m12, prev
+
+    # ---- ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...) (ORBmatcher.cc:39-118, mono frame) ----
+    def SearchByProjection(self, keysF, descF, scale_factors, bounds, proj, level, view_cos, descMP, has_obs, th=3.0):
+        """Map points in view (mbTrackInView) with their projection (mTrackProjX/Y), predicted level, viewing cosine,
+        descriptor and Observations() > 0 flag.  Returns (nmatches, frame_match[j] = map point index or -1)."""
+        kF = np.ascontiguousarray(keysF, KP_DTYPE)
+        sf = np.asarray(scale_factors, np.float32)
+        proj = np.asarray(proj, np.float32).reshape(-1, 2)
+        level = np.asarray(level, np.int32)
+        r = np.where(np.asarray(view_cos, np.float32) > 0.998, np.float32(2.5), np.float32(4.0)).astype(np.float32)
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        grid = FrameGrid(kF, bounds)
+        off, idx = grid.candidate_lists(proj, (r * sf[level]).astype(np.float32), level - 1, level)
+        dist = self.candidates(descMP, descF, off, idx)
+        fm = np.full(len(kF), -1, np.int32)
+        ratio = np.float32(self.mfNNratio)
+        nmatches = 0
+        for i in range(len(proj)):
+            best, best_level, best2, best_level2, best_idx = 256, -1, 256, -1, -1
+            for p in range(off[i], off[i + 1]):
+                j, d = int(idx[p]), int(dist[p])
+                if fm[j] >= 0 and has_obs[fm[j]]:
+                    continue
+                if d < best:
+                    best2, best, best_level2, best_level, best_idx = best, d, best_level, int(kF["octave"][j]), j
+                elif d < best2:
+                    best_level2, best2 = int(kF["octave"][j]), d
+            if best <= self.TH_HIGH and best_idx >= 0:
+                if best_level == best_level2 and np.float32(best) > ratio * np.float32(best2):
+                    continue
+                fm[best_idx] = i
+                nmatches += 1
+        return nmatches, fm
+
+    # ---- descriptor-based key-point association of matched key-frame pairs (submap merge, SURVEY.md 8f rank 3) ----
+    def AssociateSubmap(self, extractor, images1, keys1, valid1, images2, keys2, valid2, th=None):
+        """For every matched key-frame pair p (the pairs CloudMerging.cc:503-551 walks): real descriptors for the cloud key
+        frames (CloudFrameComputeDescriptors, ORBextractor.cc:989-1011, one batched call per side), all pairs' top-2 in one
+        launch, SearchByBoW's acceptance (best <= TH_LOW and best < ratio * second).  Only key points with a map point
+        (valid*) take part, like the `vpMap1MapPoints[i] && vpMap2MapPoints[j]` test of the reference.
+        images*: [npairs, h, w] u8; keys*: list of KP_DTYPE arrays; valid*: list of bool arrays.
+        Returns (match12 list: key point of key frame 2 or -1 per key point of key frame 1, number of matches per pair)."""
+        def describe(images, keys):
+            off = np.zeros(len(keys) + 1, np.int32)
+            off[1:] = np.cumsum([len(k) for k in keys])
+            allk = np.concatenate([np.ascontiguousarray(k, KP_DTYPE) for k in keys]) if off[-1] else np.zeros(0, KP_DTYPE)
+            d = extractor.CloudFrameComputeDescriptorsBatch(images, allk, off)
+            return [d[off[i]:off[i + 1]] for i in range(len(keys))]
+        d1, d2 = describe(images1, keys1), describe(images2, keys2)
+        sel1 = [np.flatnonzero(v) for v in valid1]
+        sel2 = [np.flatnonzero(v) for v in valid2]
+        res = self.top2_pairs([d[s] for d, s in zip(d1, sel1)], [d[s] for d, s in zip(d2, sel2)])
+        out, counts = [], []
+        for p, (i1, e1, e2) in enumerate(res):
+            ok = self.accept_bow(e1, e2, th) & (i1 >= 0)
+            m = np.full(len(keys1[p]), -1, np.int32)
+            m[sel1[p][ok]] = sel2[p][i1[ok]]
+            out.append(m)
+            counts.append(int(ok.sum()))
+        return out, counts
+
     # ---- stereo row-band best-1 (Frame.cc:828-905) ----
     def stereo_best1(self, Lk, Ld, Rk, Rd, scale_factors, n_rows, min_d, max_d):
         Lk = np.ascontiguousarray(Lk, KP_DTYPE)
@@ -350,6 +485,73 @@ class ORBmatcher:
                     match12[j] = -1
                     nmatches -= 1
         return nmatches, match12
+
+
+class FrameGrid:
+    """The 64 x 48 key-point grid a reference Frame / KeyFrame carries (FRAME_GRID_COLS / ROWS,
+    R/include/cloud_edge_slam_lib/Frame.h:42-43): AssignFeaturesToGrid + PosInGrid (R/lib_src/Frame.cc:441-466, 752-767)
+    and GetFeaturesInArea (:695-750; KeyFrame.cc:887-925 is the same walk).  Host-side index bookkeeping, as in the
+    reference; its output (candidate lists in the reference's order) feeds rumi_hamming_candidates."""
+    COLS, ROWS = 64, 48
+
+    def __init__(self, kps, bounds):
+        """kps: KP_DTYPE key points (mvKeysUn); bounds = (mnMinX, mnMinY, mnMaxX, mnMaxY)."""
+        f32 = np.float32
+        self.kps = np.ascontiguousarray(kps, KP_DTYPE)
+        self.min_x, self.min_y = f32(bounds[0]), f32(bounds[1])
+        self.w_inv = f32(self.COLS) / f32(bounds[2] - bounds[0])
+        self.h_inv = f32(self.ROWS) / f32(bounds[3] - bounds[1])
+        px = _c_round_arr((self.kps["x"] - self.min_x) * self.w_inv)
+        py = _c_round_arr((self.kps["y"] - self.min_y) * self.h_inv)
+        ok = (px >= 0) & (px < self.COLS) & (py >= 0) & (py < self.ROWS)
+        cell = np.where(ok, px * self.ROWS + py, self.COLS * self.ROWS)
+        self._order = np.argsort(cell, kind="stable").astype(np.int32)           # insertion order inside a cell
+        self._start = np.searchsorted(cell[self._order], np.arange(self.COLS * self.ROWS + 1)).astype(np.int64)
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        f32 = np.float32
+        x, y, r = f32(x), f32(y), f32(r)
+        c0 = max(0, int(np.floor((x - self.min_x - r) * self.w_inv)))
+        if c0 >= self.COLS:
+            return np.zeros(0, np.int32)
+        c1 = min(self.COLS - 1, int(np.ceil((x - self.min_x + r) * self.w_inv)))
+        if c1 < 0:
+            return np.zeros(0, np.int32)
+        r0 = max(0, int(np.floor((y - self.min_y - r) * self.h_inv)))
+        if r0 >= self.ROWS:
+            return np.zeros(0, np.int32)
+        r1 = min(self.ROWS - 1, int(np.ceil((y - self.min_y + r) * self.h_inv)))
+        if r1 < 0:
+            return np.zeros(0, np.int32)
+        parts = [self._order[self._start[ix * self.ROWS + r0]:self._start[ix * self.ROWS + r1 + 1]] for ix in range(c0, c1 + 1)]
+        idx = np.concatenate(parts) if parts else np.zeros(0, np.int32)
+        if len(idx) == 0:
+            return idx
+        k = self.kps[idx]
+        keep = (np.abs(k["x"] - x) < r) & (np.abs(k["y"] - y) < r)
+        if min_level > 0 or max_level >= 0:                                      # bCheckLevels
+            keep &= k["octave"] >= min_level
+            if max_level >= 0:
+                keep &= k["octave"] <= max_level
+        return idx[keep]
+
+    def candidate_lists(self, qxy, qr, qmin=None, qmax=None):
+        """CSR lists (off[nq + 1], idx) of features_in_area for many queries."""
+        qxy = np.asarray(qxy, np.float32).reshape(-1, 2)
+        nq = len(qxy)
+        qr = np.broadcast_to(np.asarray(qr, np.float32), (nq,))
+        qmin = np.broadcast_to(np.asarray(-1 if qmin is None else qmin, np.int32), (nq,))
+        qmax = np.broadcast_to(np.asarray(-1 if qmax is None else qmax, np.int32), (nq,))
+        lists = [self.features_in_area(qxy[q, 0], qxy[q, 1], qr[q], int(qmin[q]), int(qmax[q])) for q in range(nq)]
+        off = np.zeros(nq + 1, np.int32)
+        off[1:] = np.cumsum([len(l) for l in lists])
+        return off, (np.concatenate(lists).astype(np.int32) if nq and off[-1] else np.zeros(0, np.int32))
+
+
+def _c_round_arr(v):
+    """C round() of a float32 array: half away from zero (numpy rounds half to even)."""
+    v = np.asarray(v, np.float32)
+    return np.where(v >= 0, np.floor(v + np.float32(0.5)), -np.floor(-v + np.float32(0.5))).astype(np.int64)
 
 
 def _c_round(x):

@@ -1,0 +1,125 @@
+"""GPU parity of candidate-list matching (rumi_hamming_candidates) and of the matchers built on it: the reference's
+SearchForInitialization and SearchByProjection, and the descriptor-based key-point association of a submap merge
+(40 front + 40 back key frames).  The oracle side is pinned to the unmodified reference functions
+(tests/test_ref_frame_pin.py)."""
+import numpy as np
+import pytest
+
+from rumi_slam_b200.synth import motion_sequence, synthetic_frame
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    from oracle import match_oracle
+    match_oracle.build()
+    return match_oracle
+
+
+def frame_pair(oracle, seed, shift=(3.0, -2.0)):
+    seq = motion_sequence(2, 640, 480, seed=seed, vx=shift[0], vy=shift[1])
+    k1, d1, _ = oracle.extract(seq[0])
+    k2, d2, _ = oracle.extract(seq[1])
+    return k1, d1, k2, d2
+
+
+def test_candidate_distances_and_top2(oracle, M):
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, 11)
+    bounds = (0, 0, 640, 480)
+    off, idx = M.candidate_lists(k2, bounds, np.stack([k1["x"], k1["y"]], 1), 40.0)
+    m = ORBmatcher()
+    dist, (i1, e1, i2, e2) = m.candidates(d1, d2, off, idx, top2=True)
+    assert len(dist) == off[-1] > 10 * len(k1)
+    for q in range(len(k1)):
+        lst = idx[off[q]:off[q + 1]]
+        ref = np.array([oracle.descriptor_distance(d1[q], d2[j]) for j in lst], np.int64)
+        assert np.array_equal(dist[off[q]:off[q + 1]], ref)
+        b1, b2, bi, bi2 = 256, 256, -1, -1                         # the reference scan incl. the second-best index
+        for j, d in zip(lst, ref):
+            if d < b1:
+                b2, bi2, b1, bi = b1, bi, d, j
+            elif d < b2:
+                b2, bi2 = d, j
+        assert (i1[q], e1[q], e2[q]) == (bi, b1, b2) and (i2[q] == bi2 or e2[q] == 256)
+    # empty lists, a single candidate, duplicated candidates (earliest list entry wins)
+    off2 = np.array([0, 0, 1, 4], np.int32)
+    idx2 = np.array([5, 7, 7, 3], np.int32)
+    T = d2.copy(); T[3] = T[7]
+    dist, (i1, e1, i2, e2) = m.candidates(d1[:3], T, off2, idx2, top2=True)
+    assert (i1[0], e1[0], i2[0], e2[0]) == (-1, 256, -1, 256)
+    assert i1[1] == 5 and i2[1] == -1 and e2[1] == 256
+    assert i1[2] == 7 and i2[2] == 7 and e1[2] == e2[2]
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,window,ratio", [(2, 100, 0.9), (3, 30, 0.9), (4, 100, 0.6)])
+def test_search_for_initialization_matches_oracle(oracle, M, seed, window, ratio, check_ori):
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, seed)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, p = ORBmatcher(ratio, check_ori).SearchForInitialization(k1, d1, k2, d2, (0, 0, 640, 480), prev, window)
+    rn, rm, rp = M.search_for_initialization(k1, d1, k2, d2, (0, 0, 640, 480), prev, window, ratio, check_ori)
+    assert n == rn and np.array_equal(m12, rm) and np.array_equal(p, rp)
+    assert rn > (20 if ratio > 0.8 else 0)
+
+
+@pytest.mark.parametrize("seed,th,ratio", [(6, 3.0, 0.8), (7, 1.0, 0.8), (8, 5.0, 0.9), (9, 15.0, 0.6)])
+def test_search_by_projection_matches_oracle(oracle, M, seed, th, ratio):
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed)
+    sf = oracle.tables()["scale"]
+    proj = np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(np.float32) + rng.normal(0, 0.7, (len(k1), 2)).astype(np.float32)
+    level = np.clip(k1["octave"] + rng.integers(-1, 2, len(k1)), 0, 7).astype(np.int32)
+    view_cos = rng.choice([0.9, 0.9985, 1.0], len(k1)).astype(np.float32)
+    has_obs = (rng.random(len(k1)) < 0.7).astype(np.uint8)
+    n, fm = ORBmatcher(ratio).SearchByProjection(k2, d2, sf, (0, 0, 640, 480), proj, level, view_cos, d1, has_obs, th)
+    rn, rfm = M.search_by_projection(k2, d2, sf, (0, 0, 640, 480), proj, level, view_cos, d1, has_obs, th, ratio)
+    assert n == rn and np.array_equal(fm, rfm) and rn > 50
+
+
+def test_associate_submap_40_plus_40_keyframes(oracle, M):
+    """A synthetic submap merge: 40 front key frames, 40 back key frames observing the same places (slightly shifted views,
+    independent noise), cloud key points WITHOUT descriptors (as in the reference).  AssociateSubmap == the oracle
+    composition (CloudFrameComputeDescriptors -> top-2 scan -> SearchByBoW acceptance) pair by pair, and it finds most of
+    what the reference's pixel-distance association (CloudMerging.cc:503-551) finds when the views coincide."""
+    from rumi_slam_b200 import ORBextractor, ORBmatcher
+    npairs, w, h = 40, 640, 480
+    rng = np.random.default_rng(3)
+    imgs1, imgs2, keys1, keys2, valid1, valid2 = [], [], [], [], [], []
+    for p in range(npairs):
+        seq = motion_sequence(2, w, h, seed=700 + p, vx=0.4, vy=-0.3, noise=2)
+        k = oracle.extract(seq[0])[0]
+        k = k[k["octave"] == 0].copy()                        # cloud key points live in level-0 coordinates
+        k2 = k.copy()
+        k2["x"] = np.rint(k["x"] - 0.4); k2["y"] = np.rint(k["y"] + 0.3)        # the same places in the second view
+        keep = rng.random(len(k2)) < 0.9                      # the back submap misses some of them, and has extra ones
+        extra = oracle.extract(seq[1])[0]
+        extra = extra[extra["octave"] == 0][:40]
+        k2 = np.concatenate([k2[keep], extra])
+        k2 = k2[rng.permutation(len(k2))]
+        imgs1.append(seq[0]); imgs2.append(seq[1]); keys1.append(k); keys2.append(k2)
+        valid1.append(rng.random(len(k)) < 0.9); valid2.append(rng.random(len(k2)) < 0.9)
+    imgs1, imgs2 = np.stack(imgs1), np.stack(imgs2)
+    ex, m = ORBextractor(1000, 1.2, 8, 20, 7), ORBmatcher(0.75)
+    match12, counts = m.AssociateSubmap(ex, imgs1, keys1, valid1, imgs2, keys2, valid2)
+    total, agree, pix = 0, 0, 0
+    for p in range(npairs):
+        d1 = oracle.describe(imgs1[p], keys1[p])[1]
+        d2 = oracle.describe(imgs2[p], keys2[p])[1]
+        s1, s2 = np.flatnonzero(valid1[p]), np.flatnonzero(valid2[p])
+        i1, e1, e2 = oracle.hamming_top2(d1[s1], d2[s2])
+        ok = m.accept_bow(e1, e2) & (i1 >= 0)
+        want = np.full(len(keys1[p]), -1, np.int32)
+        want[s1[ok]] = s2[i1[ok]]
+        assert np.array_equal(match12[p], want), p
+        assert counts[p] == int(ok.sum())
+        total += counts[p]
+        npx, px = M.associate_pixels(keys1[p], valid1[p], keys2[p], valid2[p], (0, 0, w, h), 3.0)
+        both = (px >= 0) & (want >= 0)
+        pix += npx
+        agree += int((px[both] == want[both]).sum())
+    assert total > 40 * 100 and pix > 40 * 100
+    assert agree > 0.6 * pix                                  # same physical points found by descriptors alone

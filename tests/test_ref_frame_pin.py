@@ -117,3 +117,68 @@ def test_search_by_bow_keyframes_equals_reference(rf, B, seed, check_ori):
         rn, rm = rf.search_by_bow_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, nnratio=ratio, check_ori=check_ori)
         assert n == rn and np.array_equal(m, rm), (seed, ratio)
     assert rn > 100
+
+
+# ---- the feature grid and the candidate-list matchers (oracle/match_oracle.cpp) ----
+@pytest.fixture(scope="module")
+def M():
+    from oracle import match_oracle
+    match_oracle.build()
+    return match_oracle
+
+
+def _frame_pair(oracle, seed, shift=(3.0, -2.0)):
+    from rumi_slam_b200.synth import motion_sequence
+    seq = motion_sequence(2, 640, 480, seed=seed, vx=shift[0], vy=shift[1])
+    k1, d1, _ = oracle.extract(seq[0])
+    k2, d2, _ = oracle.extract(seq[1])
+    return k1, d1, k2, d2
+
+
+def test_features_in_area_equals_reference(oracle, rf, M):
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (R/lib_src/Frame.cc:441-466, 695-767): the same
+    indices in the same order, with and without the level filter, near and beyond the image border."""
+    k1, _, _, _ = _frame_pair(oracle, 1)
+    bounds = (0, 0, 640, 480)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        x, y = rng.uniform(-40, 680), rng.uniform(-40, 520)
+        r = float(rng.choice([1.5, 3, 10, 25, 100]))
+        lv = int(rng.integers(-1, 8))
+        a = M.features_in_area(k1, bounds, x, y, r, lv - 1 if lv >= 0 else -1, lv)
+        b = rf.features_in_area(k1, bounds, x, y, r, lv - 1 if lv >= 0 else -1, lv)
+        assert np.array_equal(a, b)
+    off, idx = M.candidate_lists(k1, bounds, np.stack([k1["x"], k1["y"]], 1), 10.0, 0, 0)
+    for q in (0, 17, len(k1) - 1):
+        assert np.array_equal(idx[off[q]:off[q + 1]], rf.features_in_area(k1, bounds, k1["x"][q], k1["y"][q], 10.0, 0, 0))
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,window,ratio", [(2, 100, 0.9), (3, 30, 0.9), (4, 100, 0.6), (5, 10, 0.9)])
+def test_search_for_initialization_equals_reference(oracle, rf, M, seed, window, ratio, check_ori):
+    """ORBmatcher::SearchForInitialization (R/lib_src/ORBmatcher.cc:581-680): vnMatches12, the updated vbPrevMatched and
+    the match count -- the vMatchedDistance skip, the re-assignment of a taken feature and the rotation histogram."""
+    k1, d1, k2, d2 = _frame_pair(oracle, seed)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m, p = M.search_for_initialization(k1, d1, k2, d2, (0, 0, 640, 480), prev, window, ratio, check_ori)
+    rn, rm, rp = rf.search_for_initialization(k1, d1, k2, d2, (0, 0, 640, 480), prev, window, ratio, check_ori)
+    assert n == rn and np.array_equal(m, rm) and np.array_equal(p, rp)
+    assert rn > (20 if window >= 30 and ratio > 0.8 else 0)
+
+
+@pytest.mark.parametrize("seed,th,ratio", [(6, 3.0, 0.8), (7, 1.0, 0.8), (8, 5.0, 0.9), (9, 15.0, 0.6)])
+def test_search_by_projection_equals_reference(oracle, rf, M, seed, th, ratio):
+    """ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) (R/lib_src/ORBmatcher.cc:39-118) on a mono frame: level
+    window, level-aware ratio test and the order-dependent 'already has a map point with observations' skip."""
+    k1, d1, k2, d2 = _frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed)
+    sf = oracle.tables()["scale"]
+    # map points = the features of frame 1, projected into frame 2 with the known image motion plus noise
+    proj = np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(np.float32) + rng.normal(0, 0.7, (len(k1), 2)).astype(np.float32)
+    level = np.clip(k1["octave"] + rng.integers(-1, 2, len(k1)), 0, 7).astype(np.int32)
+    view_cos = rng.choice([0.9, 0.9985, 1.0], len(k1)).astype(np.float32)
+    has_obs = (rng.random(len(k1)) < 0.7).astype(np.uint8)
+    n, fm = M.search_by_projection(k2, d2, sf, (0, 0, 640, 480), proj, level, view_cos, d1, has_obs, th, ratio)
+    rn, rfm = rf.search_by_projection(k2, d2, sf, (0, 0, 640, 480), proj, level, view_cos, d1, has_obs, th, ratio)
+    assert n == rn and np.array_equal(fm, rfm)
+    assert rn > 50

@@ -17,6 +17,7 @@ collective, each rank owning its own 1024-frame batch ("scaling": "weak").
   matching    cfg 5a (40 front + 40 back keyframes x 1000 descriptors, all-pairs top-2): matches/s and pairs/s
   matching_5b cfg 5b: 10^6 x 10^6, train set sharded over the ranks, candidate all-gather (NCCL) inside the C ABI
   stereo_euroc / stereo_kitti   configs[2] / [3]: left + right extraction + Frame::ComputeStereoMatches, pairs/s
+  submap_merge  descriptor-based key-point association of 40 + 40 key frames (describe + top-2 + acceptance)
   cpu_baseline  the oracle (oracle/_ref = the unmodified reference ORBextractor.cc over a cv stub, when built;
                 else the C++ port) on the host cores, bounded sample
 
@@ -684,6 +685,66 @@ def run_b200(args):
         stereo["stereo_euroc"] = stereo_row("cfg 3 (EuRoC shape)", 752, 480, 1200, 435.2, 47.9, args.stereo_pairs, 8)
         stereo["stereo_kitti"] = stereo_row("cfg 4 (KITTI shape)", 1241, 376, 2000, 718.856, 386.1448, args.stereo_pairs, 8)
 
+    # ---- submap merge: descriptor-based key-point association of 40 matched key-frame pairs.  The
+    #      cloud key frames carry no descriptors in the reference (cloud_edge_main.cpp:937), which therefore associates by
+    #      pixel distance (CloudMerging.cc:503-551): that loop is the CPU baseline printed beside it. ----
+    submap = None
+    if not args.no_submap:
+        npairs = 40
+        kf_a, kf_b = host[:npairs], np.ascontiguousarray(np.roll(host[:npairs], (1, -1), axis=(1, 2)))
+        exs = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_batch=npairs)
+        ka, _, na, _ = exs.extract_batch(kf_a)
+        kb, _, nb, _ = exs.extract_batch(kf_b)
+        keys1 = [ka[i, :na[i]].copy() for i in range(npairs)]
+        keys2 = [kb[i, :nb[i]].copy() for i in range(npairs)]
+        rng = np.random.default_rng(11 + rank)
+        valid1 = [rng.random(len(k)) < 0.9 for k in keys1]
+        valid2 = [rng.random(len(k)) < 0.9 for k in keys2]
+        ma = ORBmatcher(0.75, device=local)
+        ma.AssociateSubmap(exs, kf_a, keys1, valid1, kf_b, keys2, valid2)
+        l0 = exs.launch_count(reset=True) + ma.launch_count(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            m12, counts = ma.AssociateSubmap(exs, kf_a, keys1, valid1, kf_b, keys2, valid2)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        windows.append((t0, time.perf_counter()))
+        submap = {"workload": "submap merge: %d front + %d back key frames per GPU (640x480, ~1000 key points each, 90 %% with a "
+                              "map point): CloudFrameComputeDescriptors of all %d key frames + all-pairs top-2 of the %d matched "
+                              "pairs + acceptance; host images / key points in, associations out" % (npairs, npairs, 2 * npairs, npairs),
+                  "keyframe_pairs_per_s": world * npairs * reps / dt, "ms_per_merge": 1e3 * dt / reps,
+                  "descriptor_pairs_per_s": world * reps * float(sum(int(a.sum()) * int(b.sum()) for a, b in zip(valid1, valid2))) / dt,
+                  "associations": int(sum(counts)), "gpu_launches": exs.launch_count() + ma.launch_count(),
+                  "timing": "host wall clock around synchronous calls (H2D, kernels, D2H inside), max over ranks"}
+        if check_oracle:
+            p = 3
+            d1 = orb_oracle.describe(kf_a[p], keys1[p])[1]
+            d2 = orb_oracle.describe(kf_b[p], keys2[p])[1]
+            s1, s2 = np.flatnonzero(valid1[p]), np.flatnonzero(valid2[p])
+            i1, e1, e2 = orb_oracle.hamming_top2(d1[s1], d2[s2])
+            ok = ma.accept_bow(e1, e2) & (i1 >= 0)
+            want = np.full(len(keys1[p]), -1, np.int32)
+            want[s1[ok]] = s2[i1[ok]]
+            submap["parity_ok"] = all_ranks_true(bool(np.array_equal(m12[p], want)))
+            if rank == 0 and world == 1 and not args.no_cpu:
+                from oracle import match_oracle
+                match_oracle.build()
+                t0 = time.perf_counter()
+                npx = 0
+                for _ in range(20):
+                    for q in range(npairs):
+                        npx += match_oracle.associate_pixels(keys1[q], valid1[q], keys2[q], valid2[q], (0, 0, W_IMG, H_IMG), 3.0)[0]
+                dtc = time.perf_counter() - t0
+                submap["cpu_baseline"] = {"value": 20 * npairs / dtc, "unit": "keyframe pairs/s", "cores": 1, "kind": "port",
+                                          "sample": "the reference's own association of the same %d pairs: nearest key point within "
+                                                    "3 px through KeyFrame::GetFeaturesInArea (CloudMerging.cc:503-551, "
+                                                    "oracle/match_oracle.cpp), 20 repetitions, %.2f s -- a different, much cheaper "
+                                                    "criterion (no descriptors): the reference has no descriptor path here" % (npairs, dtc),
+                                          "associations": npx // 20}
+        exs.close(); ma.close()
+
     # ---- bag of words: Frame::ComputeBoW tree descent of this rank's descriptors on an ORBvoc-shaped vocabulary
     #      (k = 10, L = 6: 1 111 111 nodes, 10^6 words; synthetic because ORBvoc.txt is a missing blob) ----
     bow = None
@@ -856,7 +917,8 @@ def run_b200(args):
     parity_ok = bool(parity.get("device_path_ok", False) and parity.get("host_path_ok", False)
                      and parity.get("pageable_path_ok", False)
                      and (matching or {}).get("parity_ok", True) and (match_big or {}).get("parity_ok", True)
-                     and all(v.get("parity_ok", True) for v in stereo.values())) if check_oracle else None
+                     and all(v.get("parity_ok", True) for v in stereo.values())
+                     and (submap or {}).get("parity_ok", True)) if check_oracle else None
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -881,6 +943,7 @@ def run_b200(args):
             "matching_5b": match_big,
             "stereo_euroc": stereo.get("stereo_euroc"),
             "stereo_kitti": stereo.get("stereo_kitti"),
+            "submap_merge": submap,
             "bow": bow,
             "flow": flow,
             "single_frame_latency": latency,
@@ -924,6 +987,7 @@ def main():
     ap.add_argument("--no-bow", action="store_true")
     ap.add_argument("--no-flow", action="store_true")
     ap.add_argument("--no-stereo", action="store_true")
+    ap.add_argument("--no-submap", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle parity checks (they run outside the timed regions)")
     ap.add_argument("--stereo-pairs", type=int, default=256)
     ap.add_argument("--match-big", type=int, default=1000000, help="cfg 5b descriptors per side (0 = skip)")

@@ -1,5 +1,7 @@
 #include "ORBmatcher_accel.h"
 
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -271,6 +273,234 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
         }
     }
     return nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// key-point grid
+FrameGridAccel::FrameGridAccel(const std::vector<cv::KeyPoint>& keysUn, float minX, float minY, float maxX, float maxY)
+    : keys(keysUn), mnMinX(minX), mnMinY(minY) {
+    mfGridElementWidthInv = static_cast<float>(kCols) / static_cast<float>(maxX - minX);        // Frame.cc:98-99
+    mfGridElementHeightInv = static_cast<float>(kRows) / static_cast<float>(maxY - minY);
+    for (size_t i = 0; i < keys.size(); ++i) {                                                  // AssignFeaturesToGrid
+        const int posX = (int)std::round((keys[i].pt.x - mnMinX) * mfGridElementWidthInv);      // PosInGrid
+        const int posY = (int)std::round((keys[i].pt.y - mnMinY) * mfGridElementHeightInv);
+        if (posX < 0 || posX >= kCols || posY < 0 || posY >= kRows) continue;
+        mGrid[posX][posY].push_back(i);
+    }
+}
+
+std::vector<size_t> FrameGridAccel::GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel,
+                                                      const int maxLevel) const {
+    std::vector<size_t> vIndices;
+    const int nMinCellX = std::max(0, (int)std::floor((x - mnMinX - r) * mfGridElementWidthInv));
+    if (nMinCellX >= kCols) return vIndices;
+    const int nMaxCellX = std::min(kCols - 1, (int)std::ceil((x - mnMinX + r) * mfGridElementWidthInv));
+    if (nMaxCellX < 0) return vIndices;
+    const int nMinCellY = std::max(0, (int)std::floor((y - mnMinY - r) * mfGridElementHeightInv));
+    if (nMinCellY >= kRows) return vIndices;
+    const int nMaxCellY = std::min(kRows - 1, (int)std::ceil((y - mnMinY + r) * mfGridElementHeightInv));
+    if (nMaxCellY < 0) return vIndices;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+            for (size_t j : mGrid[ix][iy]) {
+                const cv::KeyPoint& kpUn = keys[j];
+                if (bCheckLevels) {
+                    if (kpUn.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kpUn.octave > maxLevel) continue;
+                }
+                if (std::fabs(kpUn.pt.x - x) < r && std::fabs(kpUn.pt.y - y) < r) vIndices.push_back(j);
+            }
+    return vIndices;
+}
+
+namespace {
+// ORBmatcher::ComputeThreeMaxima (R/lib_src/ORBmatcher.cc:1795-1826)
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+}  // namespace
+
+int ORBmatcherAccel::SearchForInitialization(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
+                                             const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2,
+                                             const FrameGridAccel& grid2, std::vector<cv::Point2f>& vbPrevMatched,
+                                             std::vector<int>& vnMatches12, int windowSize, bool checkOrientation) {
+    int nmatches = 0;
+    vnMatches12 = std::vector<int>(keys1.size(), -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(keys2.size(), INT_MAX), vnMatches21(keys2.size(), -1);
+    // candidate lists of every level-0 key point of F1 (:596-602), all distances in one launch
+    std::vector<int> query;
+    std::vector<int32_t> off(1, 0), idx;
+    std::vector<uint8_t> Q;
+    for (size_t i1 = 0; i1 < keys1.size(); i1++) {
+        const int level1 = keys1[i1].octave;
+        if (level1 > 0) continue;
+        const std::vector<size_t> v = grid2.GetFeaturesInArea(vbPrevMatched[i1].x, vbPrevMatched[i1].y, windowSize, level1, level1);
+        query.push_back((int)i1);
+        idx.insert(idx.end(), v.begin(), v.end());
+        off.push_back((int32_t)idx.size());
+        Q.insert(Q.end(), desc1.ptr((int)i1), desc1.ptr((int)i1) + 32);
+    }
+    std::vector<uint16_t> dist(idx.size() + 1);
+    const std::vector<uint8_t> T = rows32(desc2);
+    if (!query.empty() && rumi_hamming_candidates(ctx, Q.data(), (int)query.size(), T.data(), desc2.rows, off.data(), idx.data(),
+                                                  dist.data(), nullptr, nullptr, nullptr, nullptr) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    for (size_t qi = 0; qi < query.size(); ++qi) {
+        const int i1 = query[qi];
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int p = off[qi]; p < off[qi + 1]; ++p) {
+            const int i2 = idx[p], d = dist[p];
+            if (vMatchedDistance[i2] <= d) continue;                                            // :617
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * mfNNratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOrientation) {
+                    float rot = keys1[i1].angle - keys2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (size_t i1 = 0; i1 < vnMatches12.size(); i1++)
+        if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = keys2[vnMatches12[i1]].pt;
+    return nmatches;
+}
+
+int ORBmatcherAccel::SearchByProjection(const std::vector<cv::KeyPoint>& keysF, const cv::Mat& descF,
+                                        const FrameGridAccel& gridF, const std::vector<float>& scaleFactors,
+                                        const std::vector<cv::Point2f>& proj, const std::vector<int>& level,
+                                        const std::vector<float>& viewCos, const cv::Mat& descMP,
+                                        const std::vector<uint8_t>& hasObservations, float th, std::vector<int>& frameMatch) {
+    const int nMP = (int)proj.size();
+    frameMatch.assign(keysF.size(), -1);
+    const bool bFactor = th != 1.0;
+    std::vector<int32_t> off(1, 0), idx;
+    for (int iMP = 0; iMP < nMP; ++iMP) {
+        const int nPredictedLevel = level[iMP];
+        float r = viewCos[iMP] > 0.998 ? 2.5f : 4.0f;                                           // RadiusByViewingCos
+        if (bFactor) r *= th;
+        const std::vector<size_t> v = gridF.GetFeaturesInArea(proj[iMP].x, proj[iMP].y, r * scaleFactors[nPredictedLevel],
+                                                              nPredictedLevel - 1, nPredictedLevel);
+        idx.insert(idx.end(), v.begin(), v.end());
+        off.push_back((int32_t)idx.size());
+    }
+    std::vector<uint16_t> dist(idx.size() + 1);
+    const std::vector<uint8_t> Q = rows32(descMP), T = rows32(descF);
+    if (nMP > 0 && rumi_hamming_candidates(ctx, Q.data(), nMP, T.data(), descF.rows, off.data(), idx.data(), dist.data(), nullptr,
+                                           nullptr, nullptr, nullptr) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    int nmatches = 0;
+    for (int iMP = 0; iMP < nMP; ++iMP) {
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int p = off[iMP]; p < off[iMP + 1]; ++p) {
+            const int j = idx[p], d = dist[p];
+            if (frameMatch[j] >= 0 && hasObservations[frameMatch[j]]) continue;                 // :86-88
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = keysF[j].octave; bestIdx = j; }
+            else if (d < bestDist2) { bestLevel2 = keysF[j].octave; bestDist2 = d; }
+        }
+        if (bestDist <= TH_HIGH && bestIdx >= 0) {
+            if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= mfNNratio * bestDist2) { frameMatch[bestIdx] = iMP; nmatches++; }
+        }
+    }
+    return nmatches;
+}
+
+int ORBmatcherAccel::AssociateSubmap(struct rumi_orb* extractor, const std::vector<cv::Mat>& images1,
+                                     const std::vector<std::vector<cv::KeyPoint>>& keys1,
+                                     const std::vector<std::vector<uint8_t>>& valid1, const std::vector<cv::Mat>& images2,
+                                     const std::vector<std::vector<cv::KeyPoint>>& keys2,
+                                     const std::vector<std::vector<uint8_t>>& valid2, std::vector<std::vector<int>>& match12,
+                                     int th) {
+    const size_t np = images1.size();
+    if (images2.size() != np || keys1.size() != np || keys2.size() != np || valid1.size() != np || valid2.size() != np)
+        throw std::runtime_error("ORBmatcherAccel::AssociateSubmap: argument lists differ in length");
+    match12.assign(np, std::vector<int>());
+    if (np == 0) return 0;
+    // descriptors of the key points that carry a map point, one batched CloudFrameComputeDescriptors per side
+    auto describe = [&](const std::vector<cv::Mat>& images, const std::vector<std::vector<cv::KeyPoint>>& keys,
+                        const std::vector<std::vector<uint8_t>>& valid, std::vector<std::vector<int>>& sel,
+                        std::vector<int32_t>& kpOff, std::vector<uint8_t>& desc) {
+        const int w = images[0].cols, h = images[0].rows;
+        std::vector<uint8_t> packed((size_t)w * h * np);
+        std::vector<rumi_kp> k;
+        sel.assign(np, std::vector<int>());
+        kpOff.assign(1, 0);
+        for (size_t p = 0; p < np; ++p) {
+            if (images[p].cols != w || images[p].rows != h) throw std::runtime_error("AssociateSubmap: image shapes differ");
+            for (int y = 0; y < h; ++y) std::memcpy(packed.data() + ((size_t)p * h + y) * w, images[p].ptr(y), (size_t)w);
+            for (size_t i = 0; i < keys[p].size(); ++i)
+                if (valid[p][i]) {
+                    rumi_kp r;
+                    std::memcpy(&r, &keys[p][i], sizeof(r));
+                    k.push_back(r);
+                    sel[p].push_back((int)i);
+                }
+            kpOff.push_back((int32_t)k.size());
+        }
+        desc.assign(32 * k.size() + 32, 0);
+        if (rumi_orb_describe_batch(extractor, packed.data(), (int)np, w, h, (size_t)w, (size_t)w * h, k.data(), kpOff.data(),
+                                    desc.data()) < 0)
+            throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    };
+    std::vector<std::vector<int>> sel1, sel2;
+    std::vector<int32_t> off1, off2;
+    std::vector<uint8_t> Q, T;
+    describe(images1, keys1, valid1, sel1, off1, Q);
+    describe(images2, keys2, valid2, sel2, off2, T);
+    std::vector<int32_t> segs;
+    for (size_t p = 0; p < np; ++p) {
+        segs.push_back(off1[p]); segs.push_back(off1[p + 1] - off1[p]);
+        segs.push_back(off2[p]); segs.push_back(off2[p + 1] - off2[p]);
+    }
+    const int nq = off1[np], nt = off2[np];
+    std::vector<int32_t> idx(nq + 1);
+    std::vector<uint16_t> d1(nq + 1), d2(nq + 1);
+    if (rumi_hamming_top2_pairs(ctx, Q.data(), nq, T.data(), nt, segs.data(), (int)np, idx.data(), d1.data(), d2.data()) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    int total = 0;
+    for (size_t p = 0; p < np; ++p) {
+        match12[p].assign(keys1[p].size(), -1);
+        for (int q = 0; q < off1[p + 1] - off1[p]; ++q) {
+            const int g = off1[p] + q, bestDist1 = d1[g], bestDist2 = d2[g];
+            if (idx[g] >= 0 && bestDist1 <= th &&
+                static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {   // ORBmatcher.cc:290-291
+                match12[p][sel1[p][q]] = sel2[p][idx[g]];
+                ++total;
+            }
+        }
+    }
+    return total;
 }
 
 }  // namespace ORB_SLAM3

@@ -17,6 +17,22 @@ struct rumi_orb;
 
 namespace ORB_SLAM3 {
 
+// The 64 x 48 key-point grid a reference Frame / KeyFrame carries (FRAME_GRID_COLS / ROWS,
+// R/include/cloud_edge_slam_lib/Frame.h:42-43): AssignFeaturesToGrid + PosInGrid (R/lib_src/Frame.cc:441-466, 752-767)
+// and GetFeaturesInArea (:695-750; KeyFrame.cc:887-925 walks the same way).  A caller that already holds a reference
+// Frame uses Frame::GetFeaturesInArea itself; this class is for flattened inputs.
+class FrameGridAccel {
+public:
+    FrameGridAccel(const std::vector<cv::KeyPoint>& keysUn, float minX, float minY, float maxX, float maxY);
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                          const int maxLevel = -1) const;
+private:
+    static const int kCols = 64, kRows = 48;
+    const std::vector<cv::KeyPoint>& keys;
+    float mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[kCols][kRows];
+};
+
 class ORBmatcherAccel {
 public:
     static const int TH_LOW = 50;       // R/lib_src/ORBmatcher.cc:32
@@ -78,6 +94,35 @@ public:
                       const std::vector<float>& angle2, const std::vector<uint8_t>& valid2,
                       const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec2, bool checkOrientation,
                       std::vector<int>& match12);
+
+    // ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (R/lib_src/ORBmatcher.cc:581-680)
+    // on flattened frames: keys* = mvKeysUn, desc* = mDescriptors, grid2 = F2's key-point grid.  Every DescriptorDistance
+    // of every (level-0 key point of F1, window candidate of F2) pair runs in ONE launch (rumi_hamming_candidates); the
+    // acceptance -- vMatchedDistance skip, re-assignment, rotation histogram -- is replayed in the reference's order.
+    int SearchForInitialization(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
+                                const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2, const FrameGridAccel& grid2,
+                                std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize,
+                                bool checkOrientation);
+
+    // ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...) (R/lib_src/ORBmatcher.cc:39-118), mono frame.  Per map
+    // point in view: mTrackProjX/Y, mnTrackScaleLevel, mTrackViewCos, GetDescriptor(), Observations() > 0.
+    // frameMatch[j] = map point the reference would store in F.mvpMapPoints[j], or -1.
+    int SearchByProjection(const std::vector<cv::KeyPoint>& keysF, const cv::Mat& descF, const FrameGridAccel& gridF,
+                           const std::vector<float>& scaleFactors, const std::vector<cv::Point2f>& proj,
+                           const std::vector<int>& level, const std::vector<float>& viewCos, const cv::Mat& descMP,
+                           const std::vector<uint8_t>& hasObservations, float th, std::vector<int>& frameMatch);
+
+    // Descriptor-based key-point association of the matched key-frame pairs of a submap merge (the pairs
+    // R/lib_src/CloudMerging.cc:503-551 associates by pixel distance): real descriptors for the cloud
+    // key frames (ORBextractor::CloudFrameComputeDescriptors, one batched call per side -- they carry zero descriptors in
+    // the reference, R/src/cloud_edge_main.cpp:937), the top-2 of all pairs in one launch, SearchByBoW's acceptance.
+    // Only key points with a map point (valid*) take part, like the `vpMap1MapPoints[i] && vpMap2MapPoints[j]` test.
+    // match12[p][i] = key point of key frame 2 or -1; returns the total number of associations.
+    int AssociateSubmap(struct rumi_orb* extractor, const std::vector<cv::Mat>& images1,
+                        const std::vector<std::vector<cv::KeyPoint>>& keys1, const std::vector<std::vector<uint8_t>>& valid1,
+                        const std::vector<cv::Mat>& images2, const std::vector<std::vector<cv::KeyPoint>>& keys2,
+                        const std::vector<std::vector<uint8_t>>& valid2, std::vector<std::vector<int>>& match12,
+                        int th = TH_LOW);
 
 private:
     // distance blocks of the vocabulary nodes common to two feature vectors (rumi_bow_node_distances)

@@ -3,7 +3,8 @@
 //   adapter_driver <out.bin> <w> <h> <nfeatures> <lap0> <lap1> <left.raw> [<right.raw> <mbf> <mb>]
 // out.bin: int32 mono, nkp, then nkp x 28 B keypoints, nkp x 32 B descriptors, int32 nlevels, per level int32 w, h and
 // the level's pixels (mvImagePyramid); with a right image: the same block for the right frame, then int32 nmatches,
-// nL floats mvuRight, nL floats mvDepth (Frame::ComputeStereoMatches through ORBmatcherAccel).
+// nL floats mvuRight, nL floats mvDepth (Frame::ComputeStereoMatches through ORBmatcherAccel), int32 nmatches + nL int32
+// vnMatches12 of SearchForInitialization(left, right, window 100), int32 total, int32 n1, n1 int32 of AssociateSubmap.
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -71,6 +72,28 @@ int main(int argc, char** argv) {
             std::fwrite(&n, 4, 1, f);
             std::fwrite(uR.data(), 4, uR.size(), f);
             std::fwrite(depth.data(), 4, depth.size(), f);
+            // candidate-list matcher through the C++ adapter: SearchForInitialization(left -> right, window 100)
+            ORB_SLAM3::ORBmatcherAccel mi(0.9f);
+            ORB_SLAM3::FrameGridAccel grid(R.keys, 0.f, 0.f, (float)w, (float)h);
+            std::vector<cv::Point2f> prev;
+            for (const cv::KeyPoint& k : L.keys) prev.push_back(k.pt);
+            std::vector<int> m12;
+            const int ni = mi.SearchForInitialization(L.keys, L.desc, R.keys, R.desc, grid, prev, m12, 100, true);
+            std::fwrite(&ni, 4, 1, f);
+            std::fwrite(m12.data(), 4, m12.size(), f);
+            // descriptor-based association of ONE key-frame pair (level-0 key points, every one valid)
+            std::vector<std::vector<cv::KeyPoint>> k1(1), k2(1);
+            for (const cv::KeyPoint& k : L.keys) if (k.octave == 0) k1[0].push_back(k);
+            for (const cv::KeyPoint& k : R.keys) if (k.octave == 0) k2[0].push_back(k);
+            std::vector<std::vector<uint8_t>> v1(1, std::vector<uint8_t>(k1[0].size(), 1)), v2(1, std::vector<uint8_t>(k2[0].size(), 1));
+            std::vector<std::vector<int>> a12;
+            ORB_SLAM3::ORBmatcherAccel ma(0.75f);
+            const int na = ma.AssociateSubmap(exL.Handle(), std::vector<cv::Mat>(1, left), k1, v1, std::vector<cv::Mat>(1, right), k2,
+                                              v2, a12);
+            const int n1 = (int)k1[0].size();
+            std::fwrite(&na, 4, 1, f);
+            std::fwrite(&n1, 4, 1, f);
+            std::fwrite(a12[0].data(), 4, a12[0].size(), f);
         }
         // the empty-image contract of operator() (ORBextractor.cc:1017)
         cv::Mat empty; Result E;

@@ -80,3 +80,18 @@ def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
     dep = np.frombuffer(buf, np.float32, len(lk), off)
     ru, rdp, rn = oracle.stereo_match(left, right, lk, ld, rk, rd, bf, bf / fx)      # double -> float at the C boundary, both sides
     assert n == rn and n > 100 and np.array_equal(u, ru) and np.array_equal(dep, rdp)
+    off += 4 * len(lk)
+    # ORBmatcherAccel::SearchForInitialization and ::AssociateSubmap, executed in C++
+    from oracle import match_oracle as M
+    ni = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    m12 = np.frombuffer(buf, np.int32, len(lk), off); off += 4 * len(lk)
+    prev = np.stack([lk["x"], lk["y"]], 1).astype(np.float32)
+    rn_, rm_, _ = M.search_for_initialization(lk, ld, rk, rd, (0, 0, 752, 480), prev, 100, 0.9, True)
+    assert ni == rn_ and np.array_equal(m12, rm_) and rn_ > 20
+    na, n1 = (int(v) for v in np.frombuffer(buf, np.int32, 2, off)); off += 8
+    a12 = np.frombuffer(buf, np.int32, n1, off)
+    k1, k2 = lk[lk["octave"] == 0], rk[rk["octave"] == 0]
+    d1, d2 = oracle.describe(left, k1)[1], oracle.describe(right, k2)[1]
+    i1, e1, e2 = oracle.hamming_top2(d1, d2)
+    ok = (i1 >= 0) & (e1 <= 50) & (e1.astype(np.float32) < np.float32(0.75) * e2.astype(np.float32))
+    assert n1 == len(k1) and na == int(ok.sum()) and np.array_equal(a12, np.where(ok, i1, -1))

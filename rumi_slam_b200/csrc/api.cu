@@ -135,6 +135,7 @@ struct rumi_orb {
     // measurement: device-side timer on the launching streams, optional per-stage events, launch counter
     cudaEvent_t evStart = nullptr, evStop = nullptr, evJoin[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evOrder = nullptr, evSignal[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};   // wait_stream / signal_stream
+    cudaEvent_t evCompute[kMaxWs] = {nullptr, nullptr, nullptr, nullptr};                     // host batch path: kernels of a chunk done
     bool profile = false;
     std::vector<cudaEvent_t> evPool;
     size_t evUsed = 0;
@@ -664,6 +665,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     for (int i = 0; i < kMaxWs; ++i) if (h->evJoin[i]) cudaEventDestroy(h->evJoin[i]);
     if (h->evOrder) cudaEventDestroy(h->evOrder);
     for (int i = 0; i < kMaxWs; ++i) if (h->evSignal[i]) cudaEventDestroy(h->evSignal[i]);
+    for (int i = 0; i < kMaxWs; ++i) if (h->evCompute[i]) cudaEventDestroy(h->evCompute[i]);
     delete h;
 }
 
@@ -728,7 +730,14 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
         if ((rc = upload_level0(h, ws, imgs + (size_t)f0 * frame_pitch, m, stride, frame_pitch))) return rc;
         if (h->profile) { h->evSpans.push_back(std::make_pair((int)ST_H2D, (int)h->evUsed - 1)); prof_event(h, ws.stream); }
         const LevelView l0 = internal_view(h, ws.pyr, 0);
+        // uploads run ahead on all workspaces, but only TWO chunks compute at a time (more thrash the L2, see the device
+        // path): the kernels of chunk c start behind the kernels of chunk c - 2
+        if (h->nws > 2 && c >= 2) CU_TRY(cudaStreamWaitEvent(ws.stream, h->evCompute[(c - 2) % kMaxWs], 0));
         if ((rc = run_chunk(h, ws, l0, true, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
+        if (h->nws > 2) {
+            if (!h->evCompute[c % kMaxWs]) CU_TRY(cudaEventCreateWithFlags(&h->evCompute[c % kMaxWs], cudaEventDisableTiming));
+            CU_TRY(cudaEventRecord(h->evCompute[c % kMaxWs], ws.stream));
+        }
         // results: dense [m][kpCap] blocks -> caller's [n][cap_per_frame] layout
         if (cap_per_frame == oc.kpCap) {
             CU_TRY(cudaMemcpyAsync(kps + (size_t)f0 * cap_per_frame, ws.kps, sizeof(rumi_kp) * (size_t)oc.kpCap * m,

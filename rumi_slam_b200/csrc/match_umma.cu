@@ -3,25 +3,28 @@
 // ORBmatcher::DescriptorDistance (R/lib_src/ORBmatcher.cc:1830-1844) over the train set, earliest index among ties.
 //
 // Hamming(q, t) = pop(q) + pop(t) - 2 <q, t> on descriptors expanded to one byte per bit, so the pair loop is an int8
-// GEMM.  What is B200-specific here:
-//   * one CTA per SM owns 256 queries: two tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 128, K = 32) per K step share
-//     every 128-row train tile; the 2 x (128 x 128) int32 accumulators live in TMEM, ping-pong over two sets = all 512
-//     columns, and never touch registers until the top-2 epilogue reads them with tcgen05.ld;
-//   * the train set is packed ONCE per call (umma_pack_train_kernel) into ready-to-load operand tiles: per 128 rows 32 KB
+// GEMM -- and the pop(t) term rides in the GEMM too: a ninth K step (32 more bytes per row: query side all 1, train side
+// 32 signed bytes that sum to -pop(t)) makes the accumulator  acc = 2 <q,t> - pop(t) = pop(q) - Hamming(q, t)  directly
+// comparable ACROSS the columns of a tile.  What is B200-specific here:
+//   * one CTA per SM owns 256 queries: two tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 128, K = 32; A unsigned, B
+//     signed) per K step share every 128-row train tile; the 2 x (128 x 128) int32 accumulators live in TMEM, ping-pong
+//     over two sets = all 512 columns, and never touch registers until the top-2 epilogue reads them with tcgen05.ld;
+//   * the train set is packed ONCE per call (umma_pack_train_kernel) into ready-to-load operand tiles: per 128 rows 36 KB
 //     in the canonical no-swizzle K-major shared-memory layout ([16-byte K chunk][row][16 B]: core matrices of 8 rows x
-//     16 B, SBO = 128 B, LBO = 2048 B) followed by the tile's 128 key constants.  8 bits become 8 operand bytes with ONE
-//     64-bit multiply (see expand_row).  The query block is expanded the same way inside the kernel, once per CTA;
+//     16 B, SBO = 128 B, LBO = 2048 B).  8 bits become 8 operand bytes with ONE 64-bit multiply (see expand_row).  The
+//     query block is expanded the same way inside the kernel, once per CTA;
 //   * warp roles: a LOADER warp (one thread streams the tiles into a 4-stage ring with cp.async.bulk + mbarrier
 //     complete_tx), an ISSUER warp (one thread issues the MMAs -- tcgen05.mma blocks its issuing thread while the tensor
 //     queue is full, so it must not be a thread anybody else waits for) and 16 EPILOGUE warps.  Roles meet only at
 //     mbarriers: full[4] (stage landed), bar[2] (tcgen05.commit: accumulator set ready), accFree[2] (accumulator set
-//     drained), slotFree[4] (stage consumed).
-// Key per pair = ((pop(t) - 2 <q,t> + 256) << 22 | train index) built by one IMAD from the accumulator; 8 keys go
-// through a min tree and the exact update k2 = min(k2, max(key, k1)), k1 = min(k1, key) runs only when the group
-// holds a key below the current second best; pop(q) is added at the end (it does not change the order).  A query row
-// is scanned by two threads (column halves of every tile); keys are unique, so their merge is an exact min / max.
-// Measured on B200: 4.2e12 pairs/s (40000 x 40000), 5.7e12 (10^6 x 10^6) vs 1.16e12 for the mma.sync kernel and 7.4e11
-// for LOP3+POPC; tensor pipe 54 % busy (ncu), the rest is the latency of the top-2 epilogue.
+//     drained), slotFree[4] (tcgen05.commit: the MMAs that read the stage are done).
+// Epilogue: the raw accumulators of a 32-column tcgen05.ld group go through ONE max tree (VIMNMX3, ~0.5 instructions per
+// pair) and one warp vote against the accumulator value that would tie the current second best; only the 8-column
+// sub-groups that pass build keys ((256 - acc) << 22 | train index, one IMAD each) and run the exact update
+// k2 = min(k2, max(key, k1)), k1 = min(k1, key).  (Round 1 built the key of EVERY pair first -- 1 IMAD + 1 constant word per
+// pair, ALU pipe 58 %, tensor pipe 54 % busy -- because pop(t) differed per column.)  pop(q) is added at the end (it does
+// not change the order).  A query row is scanned by two threads (column halves of every tile); keys are unique, so their
+// merge is an exact min / max.
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -35,10 +38,11 @@ constexpr int kUmBM = 256, kUmBN = 128;            // queries per CTA (two M = 1
 constexpr int kUmWorkers = 2 * kUmBM;              // 16 worker warps: (query half) x (TMEM lane quarter) x (column half of the tile)
 constexpr int kUmThreads = kUmWorkers + 64;        // + one warp that issues the MMAs + one warp that issues the bulk copies
 constexpr int kUmStages = 4;                       // train-tile ring
-constexpr int kUmStageBytes = 128 * 256 + 128 * 4; // expanded tile (32 KB) + its 128 key constants: one bulk copy
+constexpr int kUmK = 256 + 32;                     // operand bytes per row: 256 descriptor bits + the 32 bytes of the pop(t) K step
 constexpr int kUmIdxBits = 22;
 constexpr uint32_t kUmIdxMask = (1u << kUmIdxBits) - 1u;
-constexpr int kUmTileBytes = 128 * 256;            // one expanded 128-row operand tile: 32 KB
+constexpr int kUmTileBytes = 128 * kUmK;           // one expanded 128-row operand tile: 36 KB
+constexpr int kUmStageBytes = kUmTileBytes;        // one bulk copy per tile
 constexpr int kUmChunkStride = 128 * 16;           // bytes between consecutive 16-byte K chunks (LBO)
 constexpr int kUmTmemCols = 512;                   // (ping, pong) x (query half 0, 1) x 128 columns = all of TMEM
 
@@ -48,7 +52,7 @@ struct UmmaSmem {
     uint32_t mergeK[2][kUmBM];                     // (k1, k2) of the threads that scanned columns 64-127 of every tile
     alignas(8) uint64_t bar[2];                    // MMAs of tile i complete: accumulator set i & 1 full
     alignas(8) uint64_t full[kUmStages];           // stage landed (cp.async.bulk complete_tx)
-    alignas(8) uint64_t slotFree[kUmStages];       // stage consumed: its MMAs are done and every worker warp has used its constants
+    alignas(8) uint64_t slotFree[kUmStages];       // stage consumed: the MMAs that read it are done (tcgen05.commit)
     alignas(8) uint64_t accFree[2];                // accumulator set drained by all worker warps
     uint32_t tmemBase;
 };
@@ -61,8 +65,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
            (1ull << 46);
 }
 
-// instruction descriptor: D = S32 (bits 4-5 = 2), A / B = unsigned 8 bit (0), both K-major, N >> 3 at bit 17, M >> 4 at 24
-constexpr uint32_t kUmIdesc = (2u << 4) | ((uint32_t)(kUmBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: D = S32 (bits 4-5 = 2), A = unsigned 8 bit (bits 7-9 = 0), B = SIGNED 8 bit (bits 10-12 = 1),
+// both K-major, N >> 3 at bit 17, M >> 4 at 24
+constexpr uint32_t kUmIdesc = (2u << 4) | (1u << 10) | ((uint32_t)(kUmBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void umma_i8(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t accumulate) {
     asm volatile(
@@ -106,14 +111,15 @@ __device__ __forceinline__ PackedRow load_packed(const uint8_t* __restrict__ D, 
 // Expands words [w0, w0 + NW) of a packed row into the operand tile (row r).  One byte of 8 bits becomes 8 output
 // bytes with ONE 64-bit multiply: x * 0x8040201008040201 puts bit i of x at positions i + 9 j (all distinct, so no
 // carries); position 8 j + 7 holds bit 7 - j.  The order of the 256 products inside a dot product is free, so the
-// bit-reversed byte order is used as is on both sides; the train side keeps the bit where it lands (bytes 0 / 0x80,
-// accumulator = 128 <q,t>), the query side (once per CTA) shifts it down to 0 / 1.
+// bit-reversed byte order is used as is on both sides.  Train side: bytes 0 / 1; query side: bytes 0 / 2, so that the
+// accumulator holds 2 <q,t>.
 template <int NW, bool kQuery>
 __device__ __forceinline__ int expand_row(const PackedRow& p, uint8_t* tile, int r, int w0) {
     const uint32_t w[8] = {p.a.x, p.a.y, p.a.z, p.a.w, p.b.x, p.b.y, p.b.z, p.b.w};
     int pop = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) pop += __popc(w[i]);
+    constexpr int kShift = kQuery ? 6 : 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (i < w0 || i >= w0 + NW) continue;
@@ -122,24 +128,43 @@ __device__ __forceinline__ int expand_row(const PackedRow& p, uint8_t* tile, int
             const unsigned long long lo = (unsigned long long)__byte_perm(w[i], 0, 0x4440 + 2 * hf) * 0x8040201008040201ull;
             const unsigned long long hi = (unsigned long long)__byte_perm(w[i], 0, 0x4441 + 2 * hf) * 0x8040201008040201ull;
             uint4 o;
-            o.x = (uint32_t)lo & 0x80808080u; o.y = (uint32_t)(lo >> 32) & 0x80808080u;
-            o.z = (uint32_t)hi & 0x80808080u; o.w = (uint32_t)(hi >> 32) & 0x80808080u;
-            if (kQuery) { o.x >>= 7; o.y >>= 7; o.z >>= 7; o.w >>= 7; }
+            o.x = ((uint32_t)lo & 0x80808080u) >> kShift; o.y = ((uint32_t)(lo >> 32) & 0x80808080u) >> kShift;
+            o.z = ((uint32_t)hi & 0x80808080u) >> kShift; o.w = ((uint32_t)(hi >> 32) & 0x80808080u) >> kShift;
             *reinterpret_cast<uint4*>(tile + (size_t)(2 * i + hf) * kUmChunkStride + (size_t)r * 16) = o;
         }
     }
     return pop;
 }
 
-// Pre-pass (once per call): the train set as ready-to-load tiles -- per 128 rows 32 KB in the shared-memory operand
-// layout followed by the 128 key constants ((pop + 256) << 22 | row), 0xFFFFFFFF for the padding rows.
+// The two K chunks (32 bytes) of the pop(t) step.  Query side: all ones.  Train side: 32 signed bytes that sum to -pop
+// (byte e = -floor((pop + e) / 32), each in [-8, 0]); a padding row (beyond the train set) gets pop = 256 with all
+// descriptor bits zero: accumulator -256 = "distance 256 + pop(q)", never a match.
+__device__ __forceinline__ void write_pop_chunks(uint8_t* tile, int r, int pop, bool query) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t wds[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v = 0x01010101u;
+            if (!query) {
+                v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) v |= (uint32_t)((0 - ((pop + 16 * c + 4 * k + b) >> 5)) & 0xFF) << (8 * b);
+            }
+            wds[k] = v;
+        }
+        *reinterpret_cast<uint4*>(tile + (size_t)(16 + c) * kUmChunkStride + (size_t)r * 16) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    }
+}
+
+// Pre-pass (once per call): the train set as ready-to-load tiles -- per 128 rows 36 KB in the shared-memory operand layout.
 __global__ void __launch_bounds__(128)
 umma_pack_train_kernel(const uint8_t* __restrict__ T, int nt, uint8_t* __restrict__ tiles) {
     const int tile = blockIdx.x, r = threadIdx.x, row = tile * kUmBN + r;
     uint8_t* dst = tiles + (size_t)tile * kUmStageBytes;
     const PackedRow p = load_packed(T, nt, row);
     const int pop = expand_row<8, false>(p, dst, r, 0);
-    reinterpret_cast<uint32_t*>(dst + kUmTileBytes)[r] = row < nt ? ((uint32_t)(pop + 256) << kUmIdxBits) | (uint32_t)row : 0xFFFFFFFFu;
+    write_pop_chunks(dst, r, row < nt ? pop : 256, false);
 }
 
 __global__ void __launch_bounds__(kUmThreads, 1)
@@ -168,7 +193,7 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         }
         for (int b = 0; b < kUmStages; ++b) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.full[b])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&sm.slotFree[b])), "r"(kUmWorkers / 32) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.slotFree[b])) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -177,6 +202,7 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     if (tid < kUmWorkers) {
         const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
         popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
+        if (colHalf == 0) write_pop_chunks(sm.A[half], r128, 0, true);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -218,37 +244,45 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
                 const uint32_t bBase = bBase0 + s * kUmStageBytes;
                 const uint32_t d = tmem + (uint32_t)(i & 1) * 256u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kUmK / 32; ++k) {          // 8 K steps of descriptor bits + the pop(t) step
                     const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
                     umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
                     umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
                 }
+                // both arrive when the MMAs above are complete: the accumulator set is full, the stage may be refilled
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                              :: "r"((i & 1) ? bar1 : bar0) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             :: "r"(slotBase + 8u * s) : "memory");
             }
         }
     } else {
         // =========================== workers: the top-2 epilogue ===========================
-        const uint32_t negTwo = 0u - (1u << (kUmIdxBits + 1 - 7));      // acc = 128 <q,t>: acc * negTwo = -2 <q,t> in the distance field
-        // 8 keys at a time: one min chain, and the exact update only when the group holds a key below the current
-        // second best (rare after the first tiles)
-        auto update8 = [&](const uint32_t* v, const uint32_t* cst) {
-            const uint4 ca = *reinterpret_cast<const uint4*>(cst);      // broadcast
-            const uint4 cb = *reinterpret_cast<const uint4*>(cst + 4);
-            uint32_t key[8];
-            key[0] = umad(v[0], negTwo, ca.x); key[1] = umad(v[1], negTwo, ca.y);
-            key[2] = umad(v[2], negTwo, ca.z); key[3] = umad(v[3], negTwo, ca.w);
-            key[4] = umad(v[4], negTwo, cb.x); key[5] = umad(v[5], negTwo, cb.y);
-            key[6] = umad(v[6], negTwo, cb.z); key[7] = umad(v[7], negTwo, cb.w);
-            // depth-2 tree of 3-input minima (VIMNMX3): the branch below is on the critical path of the warp
-            const uint32_t t0 = min(min(key[0], key[1]), key[2]), t1 = min(min(key[3], key[4]), key[5]), t2 = min(key[6], key[7]);
-            const uint32_t m = min(min(t0, t1), t2);
-            if (__any_sync(0xFFFFFFFFu, m < k2)) {             // warp-uniform: no divergence bookkeeping; the update is idempotent
+        const uint32_t negOne = 0u - (1u << kUmIdxBits);               // key = (256 - acc) << 22 | index = acc * negOne + (256 << 22 | index)
+        int thr = 256 - (int)(k2 >> kUmIdxBits);                        // an accumulator >= thr can change (k1, k2); ties included
+        // 32 raw accumulators at a time (one tcgen05.ld group): one max tree, one warp vote; keys only for the 8-column
+        // sub-groups that can matter.  rowBase = train row (inside this call) of column 0 of the group.
+        auto scan32 = [&](const uint32_t* v, uint32_t rowBase) {
+            int g[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    k2 = min(k2, max(key[e], k1));
-                    k1 = min(k1, key[e]);
+            for (int q = 0; q < 4; ++q) {
+                const int* a8 = reinterpret_cast<const int*>(v) + 8 * q;
+                g[q] = max(max(max(max(a8[0], a8[1]), a8[2]), max(max(a8[3], a8[4]), a8[5])), max(a8[6], a8[7]));
+            }
+            const int m = max(max(g[0], g[1]), max(g[2], g[3]));
+            if (__any_sync(0xFFFFFFFFu, m >= thr)) {           // warp-uniform: no divergence bookkeeping
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (__any_sync(0xFFFFFFFFu, g[q] >= thr)) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {           // idempotent for lanes whose keys do not qualify
+                            const uint32_t key = umad(v[8 * q + e], negOne, (256u << kUmIdxBits) | (rowBase + 8u * q + e));
+                            k2 = min(k2, max(key, k1));
+                            k1 = min(k1, key);
+                        }
+                    }
                 }
+                thr = 256 - (int)(k2 >> kUmIdxBits);
             }
         };
 #define RUMI_LDTM32(v, addr)                                                                                          \
@@ -265,28 +299,23 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         for (int i = 0; i < ntiles; ++i) {
             const uint32_t s = (uint32_t)i & (kUmStages - 1);
             mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);   // accumulator set i & 1 complete
-            mbar_wait(fullBase + 8u * s, (uint32_t)(i / kUmStages) & 1u);  // (long complete: acquires the bulk copy's writes)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
             //      accumulator) x 64 of the 128 columns (train rows of the tile); the second 32 columns load while the
             //      first are used
-            const uint32_t* cst = reinterpret_cast<const uint32_t*>(sm.B[s] + kUmTileBytes) + 64 * colHalf;
+            const uint32_t rowBase = (uint32_t)(tile0 + i) * kUmBN + 64u * (uint32_t)colHalf;
             const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + (uint32_t)colHalf * 64u +
                                    ((uint32_t)((warp & 3) * 32) << 16);
             uint32_t va[32], vb[32];
             RUMI_LDTM32(va, taddr);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             RUMI_LDTM32(vb, taddr + 32u);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) update8(va + j, cst + j);
+            scan32(va, rowBase);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive((i & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) update8(vb + j, cst + 32 + j);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(slotBase + 8u * s);               // the loader may refill this stage
+            scan32(vb, rowBase + 32u);
         }
 #undef RUMI_LDTM32
         // the two threads of a query row scanned disjoint train rows (unique keys): park one half for the exact merge
@@ -305,7 +334,7 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         k1 = min(k1, o1);
     }
     if (tid < kUmBM && qi < nq) {
-        // key >> 22 = pop(t) - 2 dot + 256; distance = that - 256 + pop(q).  A distance of 256 is "no match"
+        // key >> 22 = 256 - acc = pop(t) - 2 dot + 256; distance = that - 256 + pop(q).  A distance of 256 is "no match"
         // (the reference's scan starts from bestDist = 256 with strict '<').
         int d1 = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> kUmIdxBits) - 256 + popq;
         int d2 = k2 == 0xFFFFFFFFu ? 256 : (int)(k2 >> kUmIdxBits) - 256 + popq;

@@ -111,10 +111,12 @@ def lib():
     """Loads (building first if needed) librumi_orb.so.  Raises if it cannot be built or loaded."""
     global _lib
     if _lib is None:
-        from . import build as _build
-        _build.build()                     # no-op when the .so is newer than every source / header (mtime check);
-                                           # on a box without nvcc the prebuilt .so is used as shipped
-        L = C.CDLL(LIB_PATH)
+        path = os.environ.get("RUMI_ORB_LIB")      # A/B runs against another build of the same ABI
+        if not path:
+            from . import build as _build
+            _build.build()                 # no-op when the .so matches the sources (content hash)
+            path = LIB_PATH
+        L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError = the library does not export what the header declares
             fn.restype = res

@@ -1105,7 +1105,7 @@ int top2_partials(rumi_match* m, const uint8_t* dQ, int nq, const uint8_t* dT, i
         if ((rc = grow((void**)&m->partial, &m->partialCap, 8 * (size_t)slices * nq))) return rc;
         if ((rc = grow((void**)&m->tx, &m->txCap, umma_train_bytes(nt)))) return rc;
         launch_hamming_top2_umma(dQ, nq, dT, nt, m->tx, tBase, slices, m->partial, m->stream);
-        m->launches += 2;
+        m->launches += 3;                                   // train pre-pass, partial fill, the persistent UMMA kernel
         m->lastPath = 3;
         *slicesOut = slices;
     } else {

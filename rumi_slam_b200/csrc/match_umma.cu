@@ -14,8 +14,10 @@
 //     16 B, SBO = 128 B, LBO = 2048 B).  8 bits become 8 operand bytes with ONE 64-bit multiply (see expand_row).  The
 //     query block is expanded the same way inside the kernel, once per CTA;
 //   * warp roles: a LOADER warp (one thread streams the tiles into a 4-stage ring with cp.async.bulk + mbarrier
-//     complete_tx), an ISSUER warp (one thread issues the MMAs -- tcgen05.mma blocks its issuing thread while the tensor
-//     queue is full, so it must not be a thread anybody else waits for) and 16 EPILOGUE warps.  Roles meet only at
+//     complete_tx), an ISSUER warp (converged, one ELECTED lane issues the MMAs with every operand in a uniform register:
+//     18 UTCIMMA + 2 UTCBAR in ~150 straight-line uniform-datapath instructions per tile.  tcgen05.mma blocks its issuing
+//     thread while the tensor queue is full, so the issuer must not be a thread anybody else waits for; and it has only
+//     ~85 clk per MMA, so instruction count matters -- see the note at the issuer loop) and 16 EPILOGUE warps.  Roles meet only at
 //     mbarriers: full[4] (stage landed), bar[2] (tcgen05.commit: accumulator set ready), accFree[2] (accumulator set
 //     drained), slotFree[4] (tcgen05.commit: the MMAs that read the stage are done).
 // Epilogue: the raw accumulators of a 32-column tcgen05.ld group go through ONE max tree (VIMNMX3, ~0.5 instructions per
@@ -86,6 +88,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+// A warp-uniform value the compiler cannot prove uniform (loaded from shared memory, result of a division) -> REDUX
+// writes a UNIFORM register.  Every lane of a converged warp must pass the same x.
+__device__ __forceinline__ uint32_t uniform(uint32_t x) { return __reduce_or_sync(0xFFFFFFFFu, x); }
+__device__ __forceinline__ int uniform(int x) { return (int)__reduce_or_sync(0xFFFFFFFFu, (uint32_t)x); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ uint32_t umad(uint32_t a, uint32_t b, uint32_t c) {      // stays an IMAD (FMA pipe)
@@ -167,19 +180,25 @@ umma_pack_train_kernel(const uint8_t* __restrict__ T, int nt, uint8_t* __restric
     write_pop_chunks(dst, r, row < nt ? pop : 256, false);
 }
 
+// Work decomposition: the (query block, train tile) grid is flattened query-block-major and cut into gridDim.x equal
+// ranges of `unitsPerCta` tiles -- ONE persistent CTA per SM, no wave quantisation and one pipeline fill per CTA instead of
+// one per (query block, slice) (round 1: 942 CTAs in 6.4 waves for 40 000 x 40 000, ~12 us of fixed cost per wave).
+// A range that crosses a query-block boundary is processed as two (rarely three) SEGMENTS: the query operand is
+// re-expanded, the running (k1, k2) are flushed.  Segment results go to partial[slot][query] with slot = CTA index minus
+// the first CTA that touches the query block: slots of a block are ascending train ranges, the merge folds them in order.
 __global__ void __launch_bounds__(kUmThreads, 1)
-hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ tiles, int nt, int tilesPerSlice,
-                         int tBase, uint64_t* __restrict__ partial /* [gridDim.y][nq] */) {
+hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* __restrict__ tiles, int nt, int unitsPerCta,
+                         int tBase, uint64_t* __restrict__ partial /* [slots][nq] */) {
     extern __shared__ __align__(1024) uint8_t smemRaw[];
     UmmaSmem& sm = *reinterpret_cast<UmmaSmem*>(smemRaw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r128 = tid & 127, quarter = (tid >> 7) & 3;               // row inside a 128-row tile / quarter of the work
     const int half = quarter & 1, colHalf = quarter >> 1;               // epilogue: query half, columns [64 * colHalf, +64)
-    const int qrowLocal = half * 128 + r128;                            // query row of this thread inside the CTA
-    const int q0 = blockIdx.x * kUmBM;
+    const int qrowLocal = half * 128 + r128;                            // query row of this thread inside its query block
     const int nTilesAll = (nt + kUmBN - 1) / kUmBN;
-    const int tile0 = blockIdx.y * tilesPerSlice, tile1 = min(tile0 + tilesPerSlice, nTilesAll);
-    const int ntiles = tile1 - tile0;
+    const int nQB = (nq + kUmBM - 1) / kUmBM;
+    const long long total = (long long)nQB * nTilesAll;
+    const long long u0 = (long long)blockIdx.x * unitsPerCta, u1 = min(u0 + unitsPerCta, total);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -197,94 +216,114 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // the query block is expanded once per CTA by the worker threads (quarter-rows), straight into the operand layout
-    int popq = 0;
-    if (tid < kUmWorkers) {
-        const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
-        popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
-        if (colHalf == 0) write_pop_chunks(sm.A[half], r128, 0, true);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                               // TMEM base, barriers and the query operand visible to every role
+    __syncthreads();                               // TMEM base and barriers visible to every role
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmemBase;
     const uint32_t bar0 = smem_u32(&sm.bar[0]), bar1 = smem_u32(&sm.bar[1]);
     const uint32_t fullBase = smem_u32(&sm.full[0]), slotBase = smem_u32(&sm.slotFree[0]);
     const uint32_t free0 = smem_u32(&sm.accFree[0]), free1 = smem_u32(&sm.accFree[1]);
     const uint32_t bBase0 = smem_u32(sm.B[0]);
-    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 
-    if (warp == kUmWorkers / 32 + 1) {
-        // =========================== loader: one thread feeds the train-tile ring with bulk copies ===========================
-        if (lane == 0) {
-            const uint8_t* src = tiles + (size_t)tile0 * kUmStageBytes;
-            for (int i = 0; i < ntiles; ++i) {
-                const uint32_t s = (uint32_t)i & (kUmStages - 1);
-                if (i >= kUmStages) mbar_wait(slotBase + 8u * s, (uint32_t)((i / kUmStages) - 1) & 1u);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                             :: "r"(fullBase + 8u * s), "r"((uint32_t)kUmStageBytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(bBase0 + s * kUmStageBytes), "l"(src + (size_t)i * kUmStageBytes), "r"((uint32_t)kUmStageBytes),
-                                "r"(fullBase + 8u * s) : "memory");
-            }
+    int done = 0;                                  // tiles this CTA has pushed through the ring so far (all roles count alike)
+    for (long long u = u0; u < u1;) {
+        const int qb = (int)(u / nTilesAll), tile0 = (int)(u - (long long)qb * nTilesAll);
+        const int ntiles = (int)min((long long)(nTilesAll - tile0), u1 - u);
+        const int q0 = qb * kUmBM;
+        // ---- the query block of this segment, expanded by the worker threads (quarter rows) into the operand layout.
+        //      (Every MMA of the previous segment is complete: its accumulators were all read.)
+        int popq = 0;
+        if (tid < kUmWorkers) {
+            const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
+            popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
+            if (colHalf == 0) write_pop_chunks(sm.A[half], r128, 0, true);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         }
-    } else if (warp == kUmWorkers / 32) {
-        // =========================== MMA issuer: one thread, never touches data ===========================
-        // tcgen05.mma blocks its issuing thread while the tensor pipe's queue is full (measured: ~1800 clk per tile when
-        // the issuer was also an epilogue thread -- the whole CTA then waited for it at the next barrier), so the
-        // issuer is a warp of its own and talks to the other roles through mbarriers only.
-        if (lane == 0) {
-            const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
-            for (int i = 0; i < ntiles; ++i) {
-                const uint32_t s = (uint32_t)i & (kUmStages - 1);
-                mbar_wait(fullBase + 8u * s, (uint32_t)(i / kUmStages) & 1u);                    // stage landed
-                if (i >= 2) mbar_wait((i & 1) ? free1 : free0, (uint32_t)((i >> 1) - 1) & 1u);   // accumulators drained
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t bBase = bBase0 + s * kUmStageBytes;
-                const uint32_t d = tmem + (uint32_t)(i & 1) * 256u;
-#pragma unroll
-                for (int k = 0; k < kUmK / 32; ++k) {          // 8 K steps of descriptor bits + the pop(t) step
-                    const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
-                    umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
-                    umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+
+        if (warp == kUmWorkers / 32 + 1) {
+            // =========================== loader: one thread feeds the train-tile ring with bulk copies ===========================
+            if (lane == 0) {
+                const uint8_t* src = tiles + (size_t)tile0 * kUmStageBytes;
+                for (int i = 0; i < ntiles; ++i) {
+                    const int it = done + i;
+                    const uint32_t s = (uint32_t)it & (kUmStages - 1);
+                    if (it >= kUmStages) mbar_wait(slotBase + 8u * s, (uint32_t)((it / kUmStages) - 1) & 1u);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                 :: "r"(fullBase + 8u * s), "r"((uint32_t)kUmStageBytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"(bBase0 + s * kUmStageBytes), "l"(src + (size_t)i * kUmStageBytes), "r"((uint32_t)kUmStageBytes),
+                                    "r"(fullBase + 8u * s) : "memory");
                 }
-                // both arrive when the MMAs above are complete: the accumulator set is full, the stage may be refilled
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             :: "r"((i & 1) ? bar1 : bar0) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             :: "r"(slotBase + 8u * s) : "memory");
             }
-        }
-    } else {
-        // =========================== workers: the top-2 epilogue ===========================
-        const uint32_t negOne = 0u - (1u << kUmIdxBits);               // key = (256 - acc) << 22 | index = acc * negOne + (256 << 22 | index)
-        int thr = 256 - (int)(k2 >> kUmIdxBits);                        // an accumulator >= thr can change (k1, k2); ties included
-        // 32 raw accumulators at a time (one tcgen05.ld group): one max tree, one warp vote; keys only for the 8-column
-        // sub-groups that can matter.  rowBase = train row (inside this call) of column 0 of the group.
-        auto scan32 = [&](const uint32_t* v, uint32_t rowBase) {
-            int g[4];
+        } else if (warp == kUmWorkers / 32) {
+            // =========================== MMA issuer: one thread, never touches data ===========================
+            // tcgen05.mma blocks its issuing thread while the tensor pipe's queue is full (measured: ~1800 clk per tile when
+            // the issuer was also an epilogue thread -- the whole CTA then waited for it at the next barrier), so the
+            // issuer is a warp of its own and talks to the other roles through mbarriers only.
+            // The WHOLE warp walks the loop and one elected lane issues (the elect.sync form ptxas recognises): with the
+            // loop inside `if (lane == 0)` every UTCIMMA was wrapped in a 6-instruction elect/branch loop and -- once ring
+            // position and trip count came out of a 64-bit division, i.e. vector registers -- in R2UR.BROADCAST waterfalls
+            // too: ~17 instructions per MMA on a thread that has ~85 clk per MMA, which made the ISSUER the limiter of long
+            // scans.  uniform() moves the three run-time values into uniform registers; everything else is constants.
+            const int itBase = uniform(done), nIssue = uniform(ntiles);
+            const uint32_t tmemU = uniform(tmem);
+            const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
+            for (int i = 0; i < nIssue; ++i) {
+                const int it = itBase + i;
+                const uint32_t s = (uint32_t)it & (kUmStages - 1);
+                mbar_wait(fullBase + 8u * s, (uint32_t)(it / kUmStages) & 1u);                    // stage landed
+                if (it >= 2) mbar_wait((it & 1) ? free1 : free0, (uint32_t)((it >> 1) - 1) & 1u);  // accumulators drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t bBase = bBase0 + s * kUmStageBytes;
+                    const uint32_t d = tmemU + (uint32_t)(it & 1) * 256u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int* a8 = reinterpret_cast<const int*>(v) + 8 * q;
-                g[q] = max(max(max(max(a8[0], a8[1]), a8[2]), max(max(a8[3], a8[4]), a8[5])), max(a8[6], a8[7]));
+                    for (int k = 0; k < kUmK / 32; ++k) {          // 8 K steps of descriptor bits + the pop(t) step
+                        const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
+                        umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
+                        umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
+                    }
+                    // both arrive when the MMAs above are complete: the accumulator set is full, the stage may be refilled
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 :: "r"((it & 1) ? bar1 : bar0) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 :: "r"(slotBase + 8u * s) : "memory");
+                }
+                __syncwarp();
             }
-            const int m = max(max(g[0], g[1]), max(g[2], g[3]));
-            if (__any_sync(0xFFFFFFFFu, m >= thr)) {           // warp-uniform: no divergence bookkeeping
+        } else {
+            // =========================== workers: the top-2 epilogue ===========================
+            const uint32_t negOne = 0u - (1u << kUmIdxBits);               // key = (256 - acc) << 22 | index = acc * negOne + (256 << 22 | index)
+            int thr = 256 - (int)(k2 >> kUmIdxBits);                        // an accumulator >= thr can change (k1, k2); ties included
+            // 32 raw accumulators at a time (one tcgen05.ld group): one max tree, one warp vote; keys only for the 8-column
+            // sub-groups that can matter.  rowBase = train row (inside this call) of column 0 of the group.
+            auto scan32 = [&](const uint32_t* v, uint32_t rowBase) {
+                int g[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (__any_sync(0xFFFFFFFFu, g[q] >= thr)) {
+                    const int* a8 = reinterpret_cast<const int*>(v) + 8 * q;
+                    g[q] = max(max(max(max(a8[0], a8[1]), a8[2]), max(max(a8[3], a8[4]), a8[5])), max(a8[6], a8[7]));
+                }
+                const int m = max(max(g[0], g[1]), max(g[2], g[3]));
+                if (__any_sync(0xFFFFFFFFu, m >= thr)) {           // warp-uniform: no divergence bookkeeping
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {           // idempotent for lanes whose keys do not qualify
-                            const uint32_t key = umad(v[8 * q + e], negOne, (256u << kUmIdxBits) | (rowBase + 8u * q + e));
-                            k2 = min(k2, max(key, k1));
-                            k1 = min(k1, key);
+                    for (int q = 0; q < 4; ++q) {
+                        if (__any_sync(0xFFFFFFFFu, g[q] >= thr)) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {           // idempotent for lanes whose keys do not qualify
+                                const uint32_t key = umad(v[8 * q + e], negOne, (256u << kUmIdxBits) | (rowBase + 8u * q + e));
+                                k2 = min(k2, max(key, k1));
+                                k1 = min(k1, key);
+                            }
                         }
                     }
+                    thr = 256 - (int)(k2 >> kUmIdxBits);
                 }
-                thr = 256 - (int)(k2 >> kUmIdxBits);
-            }
-        };
+            };
 #define RUMI_LDTM32(v, addr)                                                                                          \
     asm volatile(                                                                                                     \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
@@ -296,30 +335,53 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])      \
         : "r"(addr) : "memory")
 
-        for (int i = 0; i < ntiles; ++i) {
-            const uint32_t s = (uint32_t)i & (kUmStages - 1);
-            mbar_wait((i & 1) ? bar1 : bar0, (uint32_t)(i >> 1) & 1u);   // accumulator set i & 1 complete
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
-            //      accumulator) x 64 of the 128 columns (train rows of the tile); the second 32 columns load while the
-            //      first are used
-            const uint32_t rowBase = (uint32_t)(tile0 + i) * kUmBN + 64u * (uint32_t)colHalf;
-            const uint32_t taddr = tmem + (uint32_t)(i & 1) * 256u + (uint32_t)half * 128u + (uint32_t)colHalf * 64u +
-                                   ((uint32_t)((warp & 3) * 32) << 16);
-            uint32_t va[32], vb[32];
-            RUMI_LDTM32(va, taddr);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            RUMI_LDTM32(vb, taddr + 32u);
-            scan32(va, rowBase);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive((i & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
-            scan32(vb, rowBase + 32u);
-        }
+            for (int i = 0; i < ntiles; ++i) {
+                const int it = done + i;
+                mbar_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);   // accumulator set it & 1 complete
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
+                //      accumulator) x 64 of the 128 columns (train rows of the tile); the second 32 columns load while the
+                //      first are used
+                const uint32_t rowBase = (uint32_t)(tile0 + i) * kUmBN + 64u * (uint32_t)colHalf;
+                const uint32_t taddr = tmem + (uint32_t)(it & 1) * 256u + (uint32_t)half * 128u + (uint32_t)colHalf * 64u +
+                                       ((uint32_t)((warp & 3) * 32) << 16);
+                uint32_t va[32], vb[32];
+                RUMI_LDTM32(va, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                RUMI_LDTM32(vb, taddr + 32u);
+                scan32(va, rowBase);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive((it & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
+                scan32(vb, rowBase + 32u);
+            }
 #undef RUMI_LDTM32
-        // the two threads of a query row scanned disjoint train rows (unique keys): park one half for the exact merge
-        if (colHalf == 1) { sm.mergeK[0][qrowLocal] = k1; sm.mergeK[1][qrowLocal] = k2; }
+            // the two threads of a query row scanned disjoint train rows (unique keys): park one half for the exact merge
+            if (colHalf == 1) { sm.mergeK[0][qrowLocal] = k1; sm.mergeK[1][qrowLocal] = k2; }
+        }
+        done += ntiles;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                           // every role is through this segment; the parked halves are visible
+        const int qi = q0 + qrowLocal;
+        if (tid < kUmBM) {                         // colHalf == 0 workers: min / max merge with the parked half
+            const uint32_t o1 = sm.mergeK[0][qrowLocal], o2 = sm.mergeK[1][qrowLocal];
+            k2 = min(min(k2, o2), max(k1, o1));
+            k1 = min(k1, o1);
+            if (qi < nq) {
+                // key >> 22 = 256 - acc = pop(t) - 2 dot + 256; distance = that - 256 + pop(q).  A distance of 256 is "no match"
+                // (the reference's scan starts from bestDist = 256 with strict '<').
+                int d1 = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> kUmIdxBits) - 256 + popq;
+                int d2 = k2 == 0xFFFFFFFFu ? 256 : (int)(k2 >> kUmIdxBits) - 256 + popq;
+                d1 = min(d1, 256); d2 = min(d2, 256);
+                const uint32_t idx = d1 >= 256 ? 0xFFFFFFFFu : (uint32_t)tBase + (k1 & kUmIdxMask);
+                const int slot = (int)blockIdx.x - (int)(((long long)qb * nTilesAll) / unitsPerCta);
+                partial[(size_t)slot * nq + qi] = ((uint64_t)d1 << 48) | ((uint64_t)d2 << 32) | (uint64_t)idx;
+            }
+        }
+        u += ntiles;
+        // (the next segment's expansion overwrites A and mergeK only after the barrier at its start; k1 / k2 restart)
+        __syncthreads();
     }
     // every accumulator read is complete (wait::ld above); release TMEM
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -327,33 +389,41 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kUmTmemCols) : "memory");
     }
-    const int qi = q0 + qrowLocal;
-    if (tid < kUmBM) {                             // colHalf == 0 workers: min / max merge with the parked half
-        const uint32_t o1 = sm.mergeK[0][qrowLocal], o2 = sm.mergeK[1][qrowLocal];
-        k2 = min(min(k2, o2), max(k1, o1));
-        k1 = min(k1, o1);
-    }
-    if (tid < kUmBM && qi < nq) {
-        // key >> 22 = 256 - acc = pop(t) - 2 dot + 256; distance = that - 256 + pop(q).  A distance of 256 is "no match"
-        // (the reference's scan starts from bestDist = 256 with strict '<').
-        int d1 = k1 == 0xFFFFFFFFu ? 256 : (int)(k1 >> kUmIdxBits) - 256 + popq;
-        int d2 = k2 == 0xFFFFFFFFu ? 256 : (int)(k2 >> kUmIdxBits) - 256 + popq;
-        d1 = min(d1, 256); d2 = min(d2, 256);
-        const uint32_t idx = d1 >= 256 ? 0xFFFFFFFFu : (uint32_t)tBase + (k1 & kUmIdxMask);
-        partial[(size_t)blockIdx.y * nq + qi] = ((uint64_t)d1 << 48) | ((uint64_t)d2 << 32) | (uint64_t)idx;
-    }
+}
+
+// Slots of partial[] that no CTA writes (a query block touched by fewer CTAs than the maximum) must read as "no candidate".
+__global__ void umma_fill_partial_kernel(uint64_t* partial, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) partial[i] = (256ull << 48) | (256ull << 32) | 0xFFFFFFFFull;
 }
 
 }  // namespace
 
+namespace {
+// ranges of the flattened (query block, tile) grid: one persistent CTA per SM, at least 8 tiles each
+void umma_plan(int nq, int nt, int* nCta, int* unitsPerCta, int* slots) {
+    const long long nQB = (nq + kUmBM - 1) / kUmBM, nTiles = (nt + kUmBN - 1) / kUmBN, total = nQB * nTiles;
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("RUMI_UMMA_CTAS")) sms = std::max(1, atoi(e));          // A/B runs
+    long long ctas = std::min<long long>(sms, std::max<long long>(1, total / 8));
+    long long U = (total + ctas - 1) / ctas;
+    // A train set that does not fit the L2 (36 KB per tile) must be streamed by all CTAs IN STEP, so that a tile is fetched
+    // from HBM once and the other CTAs hit it in L2 (measured: staggered ranges made 10^6 train rows 16 % slower, HBM
+    // bound): every CTA then takes whole query blocks and starts at tile 0.
+    if (nTiles * kUmStageBytes > (48ll << 20) && nQB >= sms) U = ((nQB + sms - 1) / sms) * nTiles;
+    ctas = (total + U - 1) / U;
+    *nCta = (int)ctas; *unitsPerCta = (int)U;
+    // most CTAs that touch one query block: its nTiles units can straddle floor((nTiles - 1) / U) + 2 ranges
+    *slots = (int)std::min<long long>(ctas, (nTiles - 1) / U + 2);
+}
+}  // namespace
+
 int umma_slices(int nq, int nt) {
-    if (const char* e = getenv("RUMI_UMMA_SLICES")) return std::max(1, atoi(e));       // A/B runs
-    const int qBlocks = (nq + kUmBM - 1) / kUmBM;
-    const int nTiles = (nt + kUmBN - 1) / kUmBN;
-    const int maxSlices = std::max(1, nTiles / 8);                      // at least 8 tiles per slice
-    int want = (148 * 6 + qBlocks - 1) / qBlocks;                        // >= 6 waves of one CTA per SM
-    want = std::min(std::min(want, maxSlices), 64);
-    return std::max(want, 1);
+    int nCta, U, slots;
+    umma_plan(nq, nt, &nCta, &U, &slots);
+    return slots;
 }
 
 size_t umma_train_bytes(int nt) { return (size_t)((nt + kUmBN - 1) / kUmBN) * kUmStageBytes; }
@@ -363,10 +433,12 @@ void launch_hamming_top2_umma(const uint8_t* Q, int nq, const uint8_t* T, int nt
     // (per device and cheap: set on every launch rather than cached in a process-wide flag)
     cudaFuncSetAttribute(hamming_top2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaSmem) + 1024);
     const int nTiles = (nt + kUmBN - 1) / kUmBN;
+    int nCta, U, slots;
+    umma_plan(nq, nt, &nCta, &U, &slots);
     umma_pack_train_kernel<<<nTiles, 128, 0, s>>>(T, nt, trainTiles);
-    const int tilesPerSlice = (nTiles + slices - 1) / slices;
-    dim3 grid((nq + kUmBM - 1) / kUmBM, slices);
-    hamming_top2_umma_kernel<<<grid, kUmThreads, sizeof(UmmaSmem) + 1024, s>>>(Q, nq, trainTiles, nt, tilesPerSlice, tBase, partial);
+    const size_t nPartial = (size_t)slices * nq;
+    umma_fill_partial_kernel<<<(unsigned)((nPartial + 255) / 256), 256, 0, s>>>(partial, nPartial);
+    hamming_top2_umma_kernel<<<nCta, kUmThreads, sizeof(UmmaSmem) + 1024, s>>>(Q, nq, trainTiles, nt, U, tBase, partial);
 }
 
 }  // namespace rumi

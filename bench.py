@@ -186,8 +186,9 @@ def match_roofline(path, pairs_per_s, world, sm_mhz):
                 "peak_pairs_per_s": peak, "frac": pairs_per_s / peak,
                 "peak_source": "nominal dense int8 4.5 POP/s per GPU (consistent with ncu's utcimma pct_of_peak)",
                 "frac_of_2x_measured_bf16": (pairs_per_s * 512 / 1e12) / (world * extra) if extra else None,
-                "note": "the top-2 epilogue (1 IMAD + min chain per pair on the CUDA cores) bounds the kernel, not the "
-                        "tensor pipe (profiles/r2_summary.md)"}
+                "note": "query operand in TMEM, train tiles from a shared-memory ring; the pop(t) term is a ninth K step "
+                        "(288 / 256 of the MMA work is algorithmic); frac_of_2x_measured_bf16 compares with twice the "
+                        "burst cuBLAS bf16 rate measured on this pool (profiles/r2_summary.md)"}
     peak = world * 148 * 16 * sm_mhz * 1e6 / 5
     return {"bound": "popc-pipe", "popc_per_pair": 5, "popc_per_clk_per_sm": 16, "peak_pairs_per_s": peak,
             "frac": pairs_per_s / peak,

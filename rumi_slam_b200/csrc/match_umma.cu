@@ -6,9 +6,13 @@
 // GEMM -- and the pop(t) term rides in the GEMM too: a ninth K step (32 more bytes per row: query side all 1, train side
 // 32 signed bytes that sum to -pop(t)) makes the accumulator  acc = 2 <q,t> - pop(t) = pop(q) - Hamming(q, t)  directly
 // comparable ACROSS the columns of a tile.  What is B200-specific here:
-//   * one CTA per SM owns 256 queries: two tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 128, K = 32; A unsigned, B
-//     signed) per K step share every 128-row train tile; the 2 x (128 x 128) int32 accumulators live in TMEM, ping-pong
-//     over two sets = all 512 columns, and never touch registers until the top-2 epilogue reads them with tcgen05.ld;
+//   * one CTA per SM owns 256 queries at a time and keeps their expanded operand IN TMEM (2 x 72 columns, written once per
+//     segment with tcgen05.st): every tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 64, K = 32; A unsigned from TMEM, B
+//     signed from shared memory) reads only the train operand from shared memory.  With both operands in shared memory the
+//     MMAs read 144 KB + the ring refill wrote 36 KB per tile = 115 of the 128 B/clk the shared memory delivers, and the
+//     tensor pipe waited for operands (76 % busy); with A in TMEM it is 72 + 36 KB.  A 128-row train tile is issued as two
+//     64-column sub-tiles, each into its own accumulator set (2 query halves x 64 columns of int32), so the epilogue of
+//     one sub-tile overlaps the MMAs of the other; accumulators never touch registers until tcgen05.ld reads them;
 //   * the train set is packed ONCE per call (umma_pack_train_kernel) into ready-to-load operand tiles: per 128 rows 36 KB
 //     in the canonical no-swizzle K-major shared-memory layout ([16-byte K chunk][row][16 B]: core matrices of 8 rows x
 //     16 B, SBO = 128 B, LBO = 2048 B).  8 bits become 8 operand bytes with ONE 64-bit multiply (see expand_row).  The
@@ -46,13 +50,18 @@ constexpr uint32_t kUmIdxMask = (1u << kUmIdxBits) - 1u;
 constexpr int kUmTileBytes = 128 * kUmK;           // one expanded 128-row operand tile: 36 KB
 constexpr int kUmStageBytes = kUmTileBytes;        // one bulk copy per tile
 constexpr int kUmChunkStride = 128 * 16;           // bytes between consecutive 16-byte K chunks (LBO)
-constexpr int kUmTmemCols = 512;                   // (ping, pong) x (query half 0, 1) x 128 columns = all of TMEM
+constexpr int kUmSubN = 64;                        // train rows per MMA: a tile is issued as two 64-column halves
+constexpr int kUmTmemCols = 512;
+// TMEM map (columns): the QUERY operand of both halves lives in TMEM for the whole segment -- [0, 72) rows 0-127,
+// [72, 144) rows 128-255 (288 operand bytes = 72 columns, byte k of a row = K index k) -- so an MMA reads only the train
+// operand from shared memory; accumulators at 256 + 128 * (sub-tile) + 64 * (query half), 64 columns each.
+constexpr uint32_t kUmTmemA = 0, kUmTmemAcc = 256;
+constexpr uint32_t kUmACols = kUmK / 4;
 
 struct UmmaSmem {
-    alignas(1024) uint8_t A[2][kUmTileBytes];      // query rows 0-127, 128-255 of this CTA
     alignas(1024) uint8_t B[kUmStages][kUmStageBytes];   // ring of pre-expanded train tiles, filled by cp.async.bulk
-    uint32_t mergeK[2][kUmBM];                     // (k1, k2) of the threads that scanned columns 64-127 of every tile
-    alignas(8) uint64_t bar[2];                    // MMAs of tile i complete: accumulator set i & 1 full
+    uint32_t mergeK[2][kUmBM];                     // (k1, k2) of the threads that scanned the upper columns of every sub-tile
+    alignas(8) uint64_t bar[2];                    // MMAs of sub-tile j of the current tile complete: accumulator set j full
     alignas(8) uint64_t full[kUmStages];           // stage landed (cp.async.bulk complete_tx)
     alignas(8) uint64_t slotFree[kUmStages];       // stage consumed: the MMAs that read it are done (tcgen05.commit)
     alignas(8) uint64_t accFree[2];                // accumulator set drained by all worker warps
@@ -61,21 +70,21 @@ struct UmmaSmem {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// no-swizzle K-major shared-memory matrix descriptor (start address, LBO, SBO in 16-byte units; version 1 = sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(kUmChunkStride >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-           (1ull << 46);
-}
+// no-swizzle K-major shared-memory matrix descriptor (start address, LBO, SBO in 16-byte units; version 1 = sm_100),
+// as two words so that the address arithmetic of the issuer stays 32 bit: lo = start | LBO << 16, hi = SBO | 1 << 14
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((uint32_t)(kUmChunkStride >> 4) << 16); }
+constexpr uint32_t kUmDescHi = (uint32_t)(128 >> 4) | (1u << 14);
 
 // instruction descriptor: D = S32 (bits 4-5 = 2), A = unsigned 8 bit (bits 7-9 = 0), B = SIGNED 8 bit (bits 10-12 = 1),
 // both K-major, N >> 3 at bit 17, M >> 4 at 24
-constexpr uint32_t kUmIdesc = (2u << 4) | (1u << 10) | ((uint32_t)(kUmBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t kUmIdesc = (2u << 4) | (1u << 10) | ((uint32_t)(kUmSubN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__device__ __forceinline__ void umma_i8(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]: M = 128 query rows (TMEM lanes) x N = 64 train rows x K = 32 bytes
+__device__ __forceinline__ void umma_i8_ts(uint32_t dTmem, uint32_t aTmem, uint32_t bDescLo, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(kUmIdesc), "r"(accumulate) : "memory");
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], bd, %4, p;\n\t}\n"
+        :: "r"(dTmem), "r"(aTmem), "r"(bDescLo), "r"(kUmDescHi), "r"(kUmIdesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -170,6 +179,32 @@ __device__ __forceinline__ void write_pop_chunks(uint8_t* tile, int r, int pop, 
     }
 }
 
+// Query side: words [w0, w0 + 4) of a packed row expanded (bytes 0 / 2, same byte order as expand_row: the K index of a
+// byte is its offset in the row on both sides) and stored to 32 consecutive TMEM columns of this thread's lane.
+// tcgen05.st.32x32b: lane i of the warp writes TMEM lane 32 * (warp % 4) + i.
+__device__ __forceinline__ void store_query_tmem(const PackedRow& p, int w0, uint32_t taddr) {
+    const uint32_t w[8] = {p.a.x, p.a.y, p.a.z, p.a.w, p.b.x, p.b.y, p.b.z, p.b.w};
+    uint32_t o[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t x = w0 == 0 ? w[i] : w[4 + i];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const unsigned long long e = (unsigned long long)__byte_perm(x, 0, 0x4440 + b) * 0x8040201008040201ull;
+            o[8 * i + 2 * b] = ((uint32_t)e & 0x80808080u) >> 6;
+            o[8 * i + 2 * b + 1] = ((uint32_t)(e >> 32) & 0x80808080u) >> 6;
+        }
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+           "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]),
+           "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]),
+           "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31]) : "memory");
+}
+
 // Pre-pass (once per call): the train set as ready-to-load tiles -- per 128 rows 36 KB in the shared-memory operand layout.
 __global__ void __launch_bounds__(128)
 umma_pack_train_kernel(const uint8_t* __restrict__ T, int nt, uint8_t* __restrict__ tiles) {
@@ -235,9 +270,16 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
         int popq = 0;
         if (tid < kUmWorkers) {
             const PackedRow qrow = load_packed(Q, nq, q0 + qrowLocal);
-            popq = colHalf == 0 ? expand_row<4, true>(qrow, sm.A[half], r128, 0) : expand_row<4, true>(qrow, sm.A[half], r128, 4);
-            if (colHalf == 0) write_pop_chunks(sm.A[half], r128, 0, true);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+            popq = __popc(qrow.a.x) + __popc(qrow.a.y) + __popc(qrow.a.z) + __popc(qrow.a.w) +
+                   __popc(qrow.b.x) + __popc(qrow.b.y) + __popc(qrow.b.z) + __popc(qrow.b.w);
+            const uint32_t arow = tmem + kUmTmemA + (uint32_t)half * kUmACols + ((uint32_t)((warp & 3) * 32) << 16);
+            store_query_tmem(qrow, 4 * colHalf, arow + 32u * (uint32_t)colHalf);
+            if (colHalf == 0) {                    // the pop(t) K step: query side all ones
+                const uint32_t one = 0x01010101u;
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};"
+                             :: "r"(arow + 64u), "r"(one) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -271,29 +313,34 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
             // scans.  uniform() moves the three run-time values into uniform registers; everything else is constants.
             const int itBase = uniform(done), nIssue = uniform(ntiles);
             const uint32_t tmemU = uniform(tmem);
-            const uint32_t aBase0 = smem_u32(sm.A[0]), aBase1 = smem_u32(sm.A[1]);
             for (int i = 0; i < nIssue; ++i) {
                 const int it = itBase + i;
                 const uint32_t s = (uint32_t)it & (kUmStages - 1);
                 mbar_wait(fullBase + 8u * s, (uint32_t)(it / kUmStages) & 1u);                    // stage landed
-                if (it >= 2) mbar_wait((it & 1) ? free1 : free0, (uint32_t)((it >> 1) - 1) & 1u);  // accumulators drained
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t bBase = bBase0 + s * kUmStageBytes;
-                    const uint32_t d = tmemU + (uint32_t)(it & 1) * 256u;
 #pragma unroll
-                    for (int k = 0; k < kUmK / 32; ++k) {          // 8 K steps of descriptor bits + the pop(t) step
-                        const uint64_t bd = umma_desc(bBase + k * 2 * kUmChunkStride);
-                        umma_i8(d, umma_desc(aBase0 + k * 2 * kUmChunkStride), bd, k > 0);
-                        umma_i8(d + 128u, umma_desc(aBase1 + k * 2 * kUmChunkStride), bd, k > 0);
+                for (int j = 0; j < 2; ++j) {                      // sub-tile j (train rows 64 j .. 64 j + 63) -> accumulator set j
+                    if (it >= 1) mbar_wait(j ? free1 : free0, (uint32_t)(it - 1) & 1u);           // set j drained (tile it - 1)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        // rows of a K chunk are 16 B apart: sub-tile j starts 64 * 16 B into every chunk (descriptor units: 16 B)
+                        const uint32_t bd0 = umma_desc_lo(bBase0 + s * kUmStageBytes) + (uint32_t)j * (kUmSubN * 16 >> 4);
+                        const uint32_t d = tmemU + kUmTmemAcc + (uint32_t)j * 128u;
+                        const uint32_t a = tmemU + kUmTmemA;
+#pragma unroll
+                        for (int k = 0; k < kUmK / 32; ++k) {      // 8 K steps of descriptor bits + the pop(t) step
+                            const uint32_t bd = bd0 + (uint32_t)k * (2 * kUmChunkStride >> 4);
+                            umma_i8_ts(d, a + 8u * k, bd, k > 0);
+                            umma_i8_ts(d + 64u, a + kUmACols + 8u * k, bd, k > 0);
+                        }
+                        // arrives when the MMAs above are complete: accumulator set j is full
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     :: "r"(j ? bar1 : bar0) : "memory");
+                        if (j == 1)                                 // ... and the stage may be refilled
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                         :: "r"(slotBase + 8u * s) : "memory");
                     }
-                    // both arrive when the MMAs above are complete: the accumulator set is full, the stage may be refilled
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                                 :: "r"((it & 1) ? bar1 : bar0) : "memory");
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                                 :: "r"(slotBase + 8u * s) : "memory");
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         } else {
             // =========================== workers: the top-2 epilogue ===========================
@@ -335,26 +382,24 @@ hamming_top2_umma_kernel(const uint8_t* __restrict__ Q, int nq, const uint8_t* _
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])      \
         : "r"(addr) : "memory")
 
+            // this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's accumulators) x 32 of the 64 columns
+            // (train rows) of every sub-tile; the scan of sub-tile j runs while the MMAs of the next one do
+            const uint32_t tacc = tmem + kUmTmemAcc + (uint32_t)half * 64u + (uint32_t)colHalf * 32u + ((uint32_t)((warp & 3) * 32) << 16);
             for (int i = 0; i < ntiles; ++i) {
                 const int it = done + i;
-                mbar_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);   // accumulator set it & 1 complete
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // ---- top-2 update of tile i: this thread = query row (TMEM lane 32 * (warp % 4) + lane of its half's
-                //      accumulator) x 64 of the 128 columns (train rows of the tile); the second 32 columns load while the
-                //      first are used
-                const uint32_t rowBase = (uint32_t)(tile0 + i) * kUmBN + 64u * (uint32_t)colHalf;
-                const uint32_t taddr = tmem + (uint32_t)(it & 1) * 256u + (uint32_t)half * 128u + (uint32_t)colHalf * 64u +
-                                       ((uint32_t)((warp & 3) * 32) << 16);
-                uint32_t va[32], vb[32];
-                RUMI_LDTM32(va, taddr);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                RUMI_LDTM32(vb, taddr + 32u);
-                scan32(va, rowBase);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive((it & 1) ? free1 : free0);         // the issuer may overwrite this accumulator set
-                scan32(vb, rowBase + 32u);
+                const uint32_t rowBase = (uint32_t)(tile0 + i) * kUmBN + 32u * (uint32_t)colHalf;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mbar_wait(j ? bar1 : bar0, (uint32_t)it & 1u);             // accumulator set j complete
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t v[32];
+                    RUMI_LDTM32(v, tacc + (uint32_t)j * 128u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(j ? free1 : free0);            // the issuer may overwrite this accumulator set
+                    scan32(v, rowBase + 64u * (uint32_t)j);
+                }
             }
 #undef RUMI_LDTM32
             // the two threads of a query row scanned disjoint train rows (unique keys): park one half for the exact merge

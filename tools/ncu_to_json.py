@@ -13,12 +13,14 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 H, U = rows[0], rows[1]
 col = {h: i for i, h in enumerate(H)}
-STAGE = [("hamming_top2_umma", "hamming_top2_umma"), ("hamming_top2_imma", "hamming_top2_imma"),
-         ("hamming_top2_segments", "hamming_top2_pairs"), ("expand_bits", "expand_bits"),
+STAGE = [("hamming_top2_umma", "hamming_top2_umma"), ("umma_pack_train", "umma_pack_train"),
+         ("umma_fill_partial", "umma_fill_partial"), ("hamming_candidates", "hamming_candidates"),
+         ("hamming_top2_segments", "hamming_top2_pairs"),
          ("flow_lk", "flow_lk"), ("flow_pyrdown", "flow_pyrdown"), ("flow_scharr", "flow_scharr"),
-         ("fast_kernel", "fast"), ("octree_kernel", "octree"), ("blur_kernel", "blur"), ("describe_kernel", "describe"),
-         ("assign_slots", "slots"), ("pyramid", "pyramid"), ("hamming_top2", "hamming_top2"), ("top2_merge", "top2_merge"),
-         ("stereo", "stereo")]
+         ("fast_kernel", "fast"), ("octree_kernel", "octree"), ("blur_kernel", "blur"),
+         ("describe_given", "describe_given"), ("describe_kernel", "describe"),
+         ("assign_slots", "slots"), ("pyramid", "pyramid"), ("hamming_top2", "hamming_top2"),
+         ("top2_merge_packed", "top2_merge_packed"), ("top2_merge", "top2_merge"), ("stereo", "stereo")]
 
 
 def val(r, name, scale=1.0):

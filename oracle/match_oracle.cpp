@@ -3,6 +3,8 @@
 //   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea      R/lib_src/Frame.cc:441-466, 752-767, 695-750
 //   ORBmatcher::SearchForInitialization                              R/lib_src/ORBmatcher.cc:581-680
 //   ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...)     R/lib_src/ORBmatcher.cc:39-189 (mono frame, Nleft == -1)
+//   ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono)   R/lib_src/ORBmatcher.cc:1498-1684 (Nleft == -1)
+//   ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)   R/lib_src/ORBmatcher.cc:1685-1794
 //   CloudMerging's pixel-distance key-point association              R/lib_src/CloudMerging.cc:503-551
 // Pinned against the UNMODIFIED reference functions compiled into oracle/_ref/librefframe.so
 // (tests/test_ref_frame_pin.py).  FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48 (R/include/cloud_edge_slam_lib/Frame.h:42-43).
@@ -197,6 +199,129 @@ int mo_search_by_projection(const void* kFv, const uint8_t* dF, int nF, const fl
         if (bestDist <= TH_HIGH) {
             if (bestLevel == bestLevel2 && bestDist > ratio * bestDist2) continue;
             if (bestLevel != bestLevel2 || bestDist <= ratio * bestDist2) { frameMatch[bestIdx] = iMP; nmatches++; }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1498-1684), the
+// matcher of Tracking::TrackWithMotionModel, for frames without a second fisheye camera (Nleft == -1).  Per feature i of
+// the last frame: valid[i] = it has a map point and is not an outlier (:1518-1520); uv[i] = projection of that point into
+// the current frame, invz[i] = 1 / depth (:1522-1534, the caller's pose and camera model); octave[i], angleLast[i] = its
+// key point (:1541, :1601); dMP[i] = the map point's descriptor; mpHasObs[i] = Observations() > 0.  Current frame: key
+// points, descriptors, grid bounds, scale factors, uRight (mvuRight, <= 0: none), occupied[j] = mvpMapPoints[j] already
+// holds a point with observations.  forward / backward = bForward / bBackward (:1513-1514).  curMatch[j] = last-frame
+// feature whose map point ends up in CurrentFrame.mvpMapPoints[j], or -1.
+int mo_search_by_projection_last(const void* kCv, const uint8_t* dC, int nC, const float* scaleFactors, int minX, int minY,
+                                 int maxX, int maxY, const float* uRight, const uint8_t* occupied, float mbf,
+                                 const uint8_t* valid, const float* uv, const float* invz, const int32_t* octave,
+                                 const float* angleLast, const uint8_t* dMP, const uint8_t* mpHasObs, int nL, float th,
+                                 int forward, int backward, int checkOri, int32_t* curMatch) {
+    const KP* kC = (const KP*)kCv;
+    Grid g(kC, nC, minX, minY, maxX, maxY);
+    for (int j = 0; j < nC; ++j) curMatch[j] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < nL; ++i) {
+        if (!valid[i]) continue;
+        const float invzc = invz[i];
+        if (invzc < 0) continue;
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        if (u < (float)minX || u > (float)maxX) continue;
+        if (v < (float)minY || v > (float)maxY) continue;
+        const int nLastOctave = octave[i];
+        const float radius = th * scaleFactors[nLastOctave];
+        if (forward) g.query(u, v, radius, nLastOctave, -1, vIndices2);
+        else if (backward) g.query(u, v, radius, 0, nLastOctave, vIndices2);
+        else g.query(u, v, radius, nLastOctave - 1, nLastOctave + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (occupied[i2] || (curMatch[i2] >= 0 && mpHasObs[curMatch[i2]])) continue;      // :1563-1565
+            if (uRight && uRight[i2] > 0) {                                                   // :1567-1572
+                const float ur = u - mbf * invzc;
+                const float er = std::fabs(ur - uRight[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(dMP + 32 * (size_t)i, dC + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            curMatch[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) {
+                float rot = angleLast[i] - kC[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { curMatch[j] = -1; nmatches--; }                        // :1672-1675 (no "still set" test)
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794),
+// the matcher of Tracking::Relocalization.  Per key-frame feature i: valid[i] = map point present, not bad, not in
+// sAlreadyFound (:1703-1704); uv[i] = its projection, dist3D[i] = |x3Dw - Ow| with the window [minDist, maxDist]
+// (:1717-1725), level[i] = PredictScale (:1727), angleKF[i] = pKF->mvKeysUn[i].angle, dMP[i].  A current-frame feature that
+// holds ANY map point (occupied[j], or assigned earlier in this call) is skipped (:1742-1743).
+int mo_search_by_projection_kf(const void* kCv, const uint8_t* dC, int nC, const float* scaleFactors, int minX, int minY,
+                               int maxX, int maxY, const uint8_t* occupied, const uint8_t* valid, const float* uv,
+                               const float* dist3D, const float* minDist, const float* maxDist, const int32_t* level,
+                               const float* angleKF, const uint8_t* dMP, int nK, float th, int orbDist, int checkOri,
+                               int32_t* curMatch) {
+    const KP* kC = (const KP*)kCv;
+    Grid g(kC, nC, minX, minY, maxX, maxY);
+    for (int j = 0; j < nC; ++j) curMatch[j] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < nK; ++i) {
+        if (!valid[i]) continue;
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        if (u < (float)minX || u > (float)maxX) continue;
+        if (v < (float)minY || v > (float)maxY) continue;
+        if (dist3D[i] < minDist[i] || dist3D[i] > maxDist[i]) continue;
+        const int nPredictedLevel = level[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        g.query(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (occupied[i2] || curMatch[i2] >= 0) continue;
+            const int dist = descriptor_distance(dMP + 32 * (size_t)i, dC + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orbDist) {
+            curMatch[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) {
+                float rot = angleKF[i] - kC[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { curMatch[j] = -1; nmatches--; }
         }
     }
     return nmatches;

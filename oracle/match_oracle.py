@@ -101,6 +101,57 @@ def search_by_projection(kF, dF, scale_factors, bounds, proj, level, view_cos, d
     return n, out[:len(kF)]
 
 
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def search_by_projection_last(kC, dC, scale_factors, bounds, valid, uv, invz, octave, angle_last, dMP, mp_has_obs, th=15.0,
+                              u_right=None, occupied=None, mbf=0.0, forward=False, backward=False, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1498-1684, Nleft == -1):
+    (nmatches, curMatch[j] = last-frame feature or -1)."""
+    kC = np.ascontiguousarray(kC, KP_DTYPE)
+    dC, dMP = _u8(dC).reshape(-1, 32), _u8(dMP).reshape(-1, 32)
+    sf, uv, invz, ang = _f32(scale_factors), _f32(uv), _f32(invz), _f32(angle_last)
+    octv = np.ascontiguousarray(octave, np.int32)
+    occ = _u8(np.zeros(len(kC)) if occupied is None else occupied)
+    ur = None if u_right is None else _f32(u_right)
+    out = np.zeros(max(len(kC), 1), np.int32)
+    L = lib()
+    L.mo_search_by_projection_last.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p,
+                                               C.c_float, _u8p, _f32p, _f32p, _i32p, _f32p, _u8p, _u8p, C.c_int, C.c_float,
+                                               C.c_int, C.c_int, C.c_int, _i32p]
+    n = L.mo_search_by_projection_last(kC.ctypes.data, _p(dC, _u8p), len(kC), _p(sf, _f32p), *[int(b) for b in bounds],
+                                       None if ur is None else _p(ur, _f32p), _p(occ, _u8p), float(mbf), _p(_u8(valid), _u8p),
+                                       _p(uv, _f32p), _p(invz, _f32p), _p(octv, _i32p), _p(ang, _f32p), _p(dMP, _u8p),
+                                       _p(_u8(mp_has_obs), _u8p), len(dMP), float(th), int(forward), int(backward),
+                                       int(check_ori), _p(out, _i32p))
+    return n, out[:len(kC)]
+
+
+def search_by_projection_kf(kC, dC, scale_factors, bounds, valid, uv, dist3d, min_dist, max_dist, level, angle_kf, dMP, th=10.0,
+                            orb_dist=100, occupied=None, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794):
+    (nmatches, curMatch[j] = key-frame feature or -1)."""
+    kC = np.ascontiguousarray(kC, KP_DTYPE)
+    dC, dMP = _u8(dC).reshape(-1, 32), _u8(dMP).reshape(-1, 32)
+    occ = _u8(np.zeros(len(kC)) if occupied is None else occupied)
+    out = np.zeros(max(len(kC), 1), np.int32)
+    L = lib()
+    L.mo_search_by_projection_kf.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p,
+                                             _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _u8p, C.c_int, C.c_float, C.c_int,
+                                             C.c_int, _i32p]
+    n = L.mo_search_by_projection_kf(kC.ctypes.data, _p(dC, _u8p), len(kC), _p(_f32(scale_factors), _f32p),
+                                     *[int(b) for b in bounds], _p(occ, _u8p), _p(_u8(valid), _u8p), _p(_f32(uv), _f32p),
+                                     _p(_f32(dist3d), _f32p), _p(_f32(min_dist), _f32p), _p(_f32(max_dist), _f32p),
+                                     _p(np.ascontiguousarray(level, np.int32), _i32p), _p(_f32(angle_kf), _f32p), _p(dMP, _u8p),
+                                     len(dMP), float(th), int(orb_dist), int(check_ori), _p(out, _i32p))
+    return n, out[:len(kC)]
+
+
 def associate_pixels(k1, valid1, k2, valid2, bounds, tol=3.0):
     """CloudMerging.cc:503-551 for one key-frame pair: (matchNum, match12)."""
     k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)

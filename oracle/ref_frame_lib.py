@@ -167,3 +167,51 @@ def search_by_projection(kF, dF, scale_factors, bounds, proj, level, view_cos, d
                                    _p(proj, _f32p), _p(level, _i32p), _p(vc, _f32p), _p(dMP, _u8p), _p(ho, _u8p), len(dMP),
                                    float(th), float(nnratio), _p(out, _i32p))
     return n, out[:len(kF)]
+
+
+def search_by_projection_last(kC, dC, scale_factors, bounds, valid, uv, depth, octave, angle_last, dMP, mp_has_obs, th=15.0,
+                              u_right=None, occupied=None, mbf=0.0, forward=False, backward=False, check_ori=True):
+    """The reference's ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) over the stand-in camera
+    (x, y, z) -> (x, y): map point i sits at (uv[i], depth[i]).  (nmatches, curMatch[j] = last-frame feature or -1)."""
+    kC = np.ascontiguousarray(kC, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    dC, dMP = u8(dC).reshape(-1, 32), u8(dMP).reshape(-1, 32)
+    sf = f32(scale_factors)
+    occ = u8(np.zeros(len(kC)) if occupied is None else occupied)
+    ur = None if u_right is None else f32(u_right)
+    out = np.zeros(max(len(kC), 1), np.int32)
+    L = lib()
+    L.ref_search_by_projection_last.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                _f32p, _u8p, C.c_float, _u8p, _f32p, _f32p, _i32p, _f32p, _u8p, _u8p, C.c_int,
+                                                C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, _i32p]
+    n = L.ref_search_by_projection_last(kC.ctypes.data, _p(dC, _u8p), len(kC), _p(sf, _f32p), len(sf), *[int(b) for b in bounds],
+                                        None if ur is None else _p(ur, _f32p), _p(occ, _u8p), float(mbf), _p(u8(valid), _u8p),
+                                        _p(f32(uv), _f32p), _p(f32(depth), _f32p), _p(np.ascontiguousarray(octave, np.int32), _i32p),
+                                        _p(f32(angle_last), _f32p), _p(dMP, _u8p), _p(u8(mp_has_obs), _u8p), len(dMP), float(th),
+                                        int(forward), int(backward), 0.9, int(check_ori), _p(out, _i32p))
+    return n, out[:len(kC)]
+
+
+def search_by_projection_kf(kC, dC, scale_factors, bounds, state, uv, depth, level, min_dist, max_dist, angle_kf, dMP, th=10.0,
+                            orb_dist=100, occupied=None, check_ori=True):
+    """The reference's ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist); state[i]: 0 no map
+    point, 1 usable, 2 bad, 3 already found.  Returns (nmatches, curMatch, dist3D the function compared with the window)."""
+    kC = np.ascontiguousarray(kC, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    dC, dMP = u8(dC).reshape(-1, 32), u8(dMP).reshape(-1, 32)
+    sf = f32(scale_factors)
+    occ = u8(np.zeros(len(kC)) if occupied is None else occupied)
+    out = np.zeros(max(len(kC), 1), np.int32)
+    d3 = np.zeros(max(len(dMP), 1), np.float32)
+    L = lib()
+    L.ref_search_by_projection_kf.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                              _u8p, _f32p, _f32p, _i32p, _f32p, _f32p, _f32p, _u8p, C.c_int, C.c_float, C.c_int,
+                                              C.c_float, C.c_int, _i32p, _f32p]
+    n = L.ref_search_by_projection_kf(kC.ctypes.data, _p(dC, _u8p), len(kC), _p(sf, _f32p), len(sf), *[int(b) for b in bounds],
+                                      _p(occ, _u8p), _p(u8(state), _u8p), _p(f32(uv), _f32p), _p(f32(depth), _f32p),
+                                      _p(np.ascontiguousarray(level, np.int32), _i32p), _p(f32(min_dist), _f32p),
+                                      _p(f32(max_dist), _f32p), _p(f32(angle_kf), _f32p), _p(dMP, _u8p), len(dMP), float(th),
+                                      int(orb_dist), 0.9, int(check_ori), _p(out, _i32p), _p(d3, _f32p))
+    return n, out[:len(kC)], d3[:len(dMP)]

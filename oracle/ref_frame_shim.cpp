@@ -10,6 +10,10 @@
 //   ORBmatcher::DescriptorDistance / ComputeThreeMaxima / RadiusByViewingCos   R/lib_src/ORBmatcher.cc:1830-1844, 1795-1826, 191-196
 //   ORBmatcher::SearchByBoW (KeyFrame, Frame) / (KeyFrame, KeyFrame)           R/lib_src/ORBmatcher.cc:198-370, 682-804
 //   ORBmatcher::SearchByProjection (Frame, MapPoints) / SearchForInitialization   R/lib_src/ORBmatcher.cc:39-189, 581-680
+//   ORBmatcher::SearchByProjection (CurrentFrame, LastFrame) / (CurrentFrame, KeyFrame, sAlreadyFound)   :1498-1684, 1685-1794
+//     (these two take poses and a camera model: Sophus::SE3f / Eigen::Vector3f / GeometricCamera are minimal stand-ins
+//      below -- identity rotation, so that "Tcw * x3Dw" is exact -- and the pin covers everything AFTER the projection,
+//      which is what the flattened adapters take over; the projection itself stays with the caller's own Sophus / camera)
 // cv::norm(NORM_L1) on 8U is an exact integer sum.
 #include <opencv2/opencv.hpp>
 
@@ -37,13 +41,38 @@ inline double norm(const Mat& a, const Mat& b, int) {
 }
 }  // namespace cv
 
+namespace Eigen {
+struct Vector2f { float v[2]; float operator()(int i) const { return v[i]; } };
+struct Vector3f {
+    float v[3];
+    Vector3f() : v{0, 0, 0} {}
+    Vector3f(float a, float b, float c) : v{a, b, c} {}
+    float operator()(int i) const { return v[i]; }
+    Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+    float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+};
+}  // namespace Eigen
+namespace Sophus {
+struct SE3f {                                   // translation only (rotation = identity): R v + t is exact
+    Eigen::Vector3f t;
+    SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t.v[0], -t.v[1], -t.v[2]); return r; }
+    Eigen::Vector3f translation() const { return t; }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return Eigen::Vector3f(p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]); }
+};
+}  // namespace Sophus
+
 using namespace std;
 
 namespace ORB_SLAM3 {
 
 #include "_ref/gen_frame_defines.inc"      // FRAME_GRID_ROWS / FRAME_GRID_COLS   R/include/cloud_edge_slam_lib/Frame.h:42-43
 
-class GeometricCamera {};
+class GeometricCamera {
+public:
+    // stand-in camera model: (x, y, z) -> (x, y); the tests put the wanted pixel position into x, y and the depth into z
+    Eigen::Vector2f project(const Eigen::Vector3f& p) const { Eigen::Vector2f r; r.v[0] = p(0); r.v[1] = p(1); return r; }
+};
+class Frame;
 class KeyFrame;
 
 class MapPoint {
@@ -57,6 +86,12 @@ public:
     int Observations() { return nObs; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
     void ComputeDistinctiveDescriptors();
+    Eigen::Vector3f GetWorldPos() { return mWorldPos; }
+    float GetMaxDistanceInvariance() { return mfMaxDistance; }
+    float GetMinDistanceInvariance() { return mfMinDistance; }
+    int PredictScale(const float&, Frame*) { return mnTrackScaleLevel; }       // stand-in: the level the test prescribes
+    Eigen::Vector3f mWorldPos;
+    float mfMaxDistance = 1e30f, mfMinDistance = 0.0f;
     // state
     bool mbBad = false;
     int nObs = 0;
@@ -92,7 +127,12 @@ public:
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
     GeometricCamera* mpCamera2 = nullptr;
-    static float mfGridElementWidthInv, mfGridElementHeightInv, mnMinX, mnMinY;
+    GeometricCamera* mpCamera = nullptr;
+    std::vector<bool> mvbOutlier;
+    Sophus::SE3f mTcw, mTrl;
+    Sophus::SE3f GetPose() const { return mTcw; }
+    Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
+    static float mfGridElementWidthInv, mfGridElementHeightInv, mnMinX, mnMinY, mnMaxX, mnMaxY;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     void ComputeStereoMatches();
@@ -102,6 +142,7 @@ public:
                                      const int maxLevel = -1, const bool bRight = false) const;
 };
 float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0, Frame::mnMinX = 0, Frame::mnMinY = 0;
+float Frame::mnMaxX = 0, Frame::mnMaxY = 0;
 
 class ORBmatcher {
 public:
@@ -113,6 +154,9 @@ public:
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
                                 int windowSize = 10);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                           const int ORBdist);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -151,7 +195,7 @@ void fill_featvec(DBoW2::FeatureVector& fv, const int32_t* node, int n) {
         if (node[i] >= 0) fv.addFeature((DBoW2::NodeId)node[i], (unsigned)i);
 }
 void set_grid(int minX, int minY, int maxX, int maxY) {      // Frame.cc:98-99 (first frame): static grid constants
-    Frame::mnMinX = (float)minX; Frame::mnMinY = (float)minY;
+    Frame::mnMinX = (float)minX; Frame::mnMinY = (float)minY; Frame::mnMaxX = (float)maxX; Frame::mnMaxY = (float)maxY;
     Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(maxX - minX);
     Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(maxY - minY);
 }
@@ -298,6 +342,95 @@ int ref_search_by_projection(const void* kF, const uint8_t* dF, int nF, const fl
     ORBmatcher m(ratio, true);
     const int n = m.SearchByProjection(F, ptrs, th, false, 50.0f);
     for (int j = 0; j < nF; ++j) frameMatch[j] = F.mvpMapPoints[j] ? (int)(F.mvpMapPoints[j] - mps.data()) : -1;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1498-1684), Nleft == -1.  Last frame:
+// valid[i] = has a map point and is not an outlier, (uv, depth) = where the stand-in camera puts it in the current frame,
+// octave / angle of its key point, descriptor and Observations() > 0 of its map point.  Current frame: key points,
+// descriptors, uRight (may be null: all -1), occupied[j] = mvpMapPoints[j] holds a point with observations.
+// forward / backward steer bForward / bBackward through the relative pose (tlc(2) vs mb).
+int ref_search_by_projection_last(const void* kC, const uint8_t* dC, int nC, const float* scaleFactors, int nlevels, int minX,
+                                  int minY, int maxX, int maxY, const float* uRight, const uint8_t* occupied, float mbf,
+                                  const uint8_t* valid, const float* uv, const float* depth, const int32_t* octave,
+                                  const float* angleLast, const uint8_t* dMP, const uint8_t* mpHasObs, int nL, float th,
+                                  int forward, int backward, float ratio, int checkOri, int32_t* curMatch) {
+    set_grid(minX, minY, maxX, maxY);
+    GeometricCamera cam;
+    Frame C, Lf;
+    C.N = nC; C.mvKeysUn = keys(kC, nC); C.mvKeys = C.mvKeysUn; C.mDescriptors = rows32(dC, nC);
+    C.mvuRight.assign(nC, -1.0f);
+    if (uRight) C.mvuRight.assign(uRight, uRight + nC);
+    C.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    C.mbf = mbf; C.mb = 1.0f; C.mpCamera = &cam;
+    MapPoint taken; taken.nObs = 1;
+    C.mvpMapPoints.assign(nC, nullptr);
+    for (int j = 0; j < nC; ++j) if (occupied && occupied[j]) C.mvpMapPoints[j] = &taken;
+    C.AssignFeaturesToGrid();
+    std::vector<MapPoint> mps(nL);
+    Lf.N = nL; Lf.mvKeys.resize(nL); Lf.mvKeysUn.resize(nL); Lf.mvpMapPoints.assign(nL, nullptr); Lf.mvbOutlier.assign(nL, false);
+    for (int i = 0; i < nL; ++i) {
+        Lf.mvKeys[i].octave = octave[i]; Lf.mvKeysUn[i].octave = octave[i];
+        Lf.mvKeys[i].angle = angleLast[i]; Lf.mvKeysUn[i].angle = angleLast[i];
+        mps[i].mWorldPos = Eigen::Vector3f(uv[2 * i], uv[2 * i + 1], depth[i]);
+        mps[i].mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+        mps[i].nObs = mpHasObs[i] ? 1 : 0;
+        // "not valid" alternates between the two ways the reference skips a feature: no map point / outlier
+        if (valid[i]) Lf.mvpMapPoints[i] = &mps[i];
+        else if (i & 1) { Lf.mvpMapPoints[i] = &mps[i]; Lf.mvbOutlier[i] = true; }
+    }
+    // Tcw = identity -> twc = 0, tlc = Tlw.translation(): bForward <=> tlc(2) > mb, bBackward <=> -tlc(2) > mb
+    Lf.mTcw.t = Eigen::Vector3f(0, 0, forward ? 2.0f : backward ? -2.0f : 0.0f);
+    ORBmatcher m(ratio, checkOri != 0);
+    const int n = m.SearchByProjection(C, Lf, th, false);
+    for (int j = 0; j < nC; ++j) {
+        MapPoint* p = C.mvpMapPoints[j];
+        curMatch[j] = (p && p != &taken) ? (int)(p - mps.data()) : -1;
+    }
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794).  Key frame:
+// state[i] = 0 no map point, 1 usable, 2 bad, 3 in sAlreadyFound; (uv, depth), predicted level (stand-in PredictScale),
+// distance-invariance window [minDist, maxDist] against |x3Dw - Ow| (Ow = 0 here), key point angle, descriptor.
+int ref_search_by_projection_kf(const void* kC, const uint8_t* dC, int nC, const float* scaleFactors, int nlevels, int minX,
+                                int minY, int maxX, int maxY, const uint8_t* occupied, const uint8_t* state, const float* uv,
+                                const float* depth, const int32_t* level, const float* minDist, const float* maxDist,
+                                const float* angleKF, const uint8_t* dMP, int nK, float th, int orbDist, float ratio,
+                                int checkOri, int32_t* curMatch, float* dist3D) {
+    set_grid(minX, minY, maxX, maxY);
+    GeometricCamera cam;
+    Frame C;
+    C.N = nC; C.mvKeysUn = keys(kC, nC); C.mvKeys = C.mvKeysUn; C.mDescriptors = rows32(dC, nC);
+    C.mvuRight.assign(nC, -1.0f);
+    C.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    C.mpCamera = &cam;
+    MapPoint taken; taken.nObs = 1;
+    C.mvpMapPoints.assign(nC, nullptr);
+    for (int j = 0; j < nC; ++j) if (occupied && occupied[j]) C.mvpMapPoints[j] = &taken;
+    C.AssignFeaturesToGrid();
+    KeyFrame kf;
+    std::vector<MapPoint> mps(nK);
+    std::set<MapPoint*> found;
+    kf.mvpMapPoints.assign(nK, nullptr); kf.mvKeysUn.resize(nK);
+    for (int i = 0; i < nK; ++i) {
+        kf.mvKeysUn[i].angle = angleKF[i];
+        mps[i].mWorldPos = Eigen::Vector3f(uv[2 * i], uv[2 * i + 1], depth[i]);
+        mps[i].mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+        mps[i].mnTrackScaleLevel = level[i];
+        mps[i].mfMinDistance = minDist[i]; mps[i].mfMaxDistance = maxDist[i];
+        mps[i].nObs = 1;
+        if (state[i]) kf.mvpMapPoints[i] = &mps[i];
+        if (state[i] == 2) mps[i].mbBad = true;
+        if (state[i] == 3) found.insert(&mps[i]);
+        if (dist3D) dist3D[i] = mps[i].mWorldPos.norm();            // what the function compares with the window (Ow = 0)
+    }
+    ORBmatcher m(ratio, checkOri != 0);
+    const int n = m.SearchByProjection(C, &kf, found, th, orbDist);
+    for (int j = 0; j < nC; ++j) {
+        MapPoint* p = C.mvpMapPoints[j];
+        curMatch[j] = (p && p != &taken) ? (int)(p - mps.data()) : -1;
+    }
     return n;
 }
 

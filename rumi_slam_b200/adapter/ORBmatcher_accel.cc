@@ -278,7 +278,7 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
 // ---------------------------------------------------------------------------------------------------------------
 // key-point grid
 FrameGridAccel::FrameGridAccel(const std::vector<cv::KeyPoint>& keysUn, float minX, float minY, float maxX, float maxY)
-    : keys(keysUn), mnMinX(minX), mnMinY(minY) {
+    : mnMinX(minX), mnMinY(minY), mnMaxX(maxX), mnMaxY(maxY), keys(keysUn) {
     mfGridElementWidthInv = static_cast<float>(kCols) / static_cast<float>(maxX - minX);        // Frame.cc:98-99
     mfGridElementHeightInv = static_cast<float>(kRows) / static_cast<float>(maxY - minY);
     for (size_t i = 0; i < keys.size(); ++i) {                                                  // AssignFeaturesToGrid
@@ -433,6 +433,144 @@ int ORBmatcherAccel::SearchByProjection(const std::vector<cv::KeyPoint>& keysF, 
             if (bestLevel != bestLevel2 || bestDist <= mfNNratio * bestDist2) { frameMatch[bestIdx] = iMP; nmatches++; }
         }
     }
+    return nmatches;
+}
+
+void ORBmatcherAccel::CandidateDistances(const std::vector<uint8_t>& Q, int nq, const cv::Mat& T, const std::vector<int32_t>& off,
+                                         const std::vector<int32_t>& idx, std::vector<uint16_t>& dist) {
+    dist.assign(idx.size() + 1, 0);
+    const std::vector<uint8_t> Tr = rows32(T);
+    if (nq > 0 && rumi_hamming_candidates(ctx, Q.data(), nq, Tr.data(), T.rows, off.data(), idx.data(), dist.data(), nullptr,
+                                          nullptr, nullptr, nullptr) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+}
+
+namespace {
+// the rotation-consistency epilogue the projection matchers share (ORBmatcher.cc:1661-1680, :1776-1791): every entry of a
+// histogram bin outside the three fullest ones is cleared and counted, duplicates included
+int clear_rotation_outliers(std::vector<int>* rotHist, int L, std::vector<int>& match) {
+    int ind1 = -1, ind2 = -1, ind3 = -1, removed = 0;
+    three_maxima(rotHist, L, ind1, ind2, ind3);
+    for (int i = 0; i < L; i++) {
+        if (i == ind1 || i == ind2 || i == ind3) continue;
+        for (int j : rotHist[i]) { match[j] = -1; removed++; }
+    }
+    return removed;
+}
+int rotation_bin(float angleA, float angleB, int L) {
+    float rot = angleA - angleB;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * (1.0f / L));
+    if (bin == L) bin = 0;
+    return bin;
+}
+}  // namespace
+
+int ORBmatcherAccel::SearchByProjectionLastFrame(const std::vector<cv::KeyPoint>& keysC, const cv::Mat& descC,
+                                                 const FrameGridAccel& gridC, const std::vector<float>& scaleFactors,
+                                                 const std::vector<float>& uRight, const std::vector<uint8_t>& occupied,
+                                                 float mbf, const std::vector<uint8_t>& valid,
+                                                 const std::vector<cv::Point2f>& uv, const std::vector<float>& invzc,
+                                                 const std::vector<int>& octaveLast, const std::vector<float>& angleLast,
+                                                 const cv::Mat& descMP, const std::vector<uint8_t>& mpHasObservations, float th,
+                                                 bool bForward, bool bBackward, bool checkOrientation,
+                                                 std::vector<int>& curMatch) {
+    curMatch.assign(keysC.size(), -1);
+    std::vector<int> query;
+    std::vector<float> radii;
+    std::vector<int32_t> off(1, 0), idx;
+    std::vector<uint8_t> Q;
+    for (size_t i = 0; i < uv.size(); i++) {
+        if (!valid[i]) continue;
+        if (invzc[i] < 0) continue;                                                              // :1529-1530
+        if (uv[i].x < gridC.mnMinX || uv[i].x > gridC.mnMaxX) continue;
+        if (uv[i].y < gridC.mnMinY || uv[i].y > gridC.mnMaxY) continue;
+        const int nLastOctave = octaveLast[i];
+        const float radius = th * scaleFactors[nLastOctave];
+        const std::vector<size_t> v = bForward    ? gridC.GetFeaturesInArea(uv[i].x, uv[i].y, radius, nLastOctave)
+                                      : bBackward ? gridC.GetFeaturesInArea(uv[i].x, uv[i].y, radius, 0, nLastOctave)
+                                                  : gridC.GetFeaturesInArea(uv[i].x, uv[i].y, radius, nLastOctave - 1, nLastOctave + 1);
+        if (v.empty()) continue;
+        query.push_back((int)i);
+        radii.push_back(radius);
+        idx.insert(idx.end(), v.begin(), v.end());
+        off.push_back((int32_t)idx.size());
+        Q.insert(Q.end(), descMP.ptr((int)i), descMP.ptr((int)i) + 32);
+    }
+    std::vector<uint16_t> dist;
+    CandidateDistances(Q, (int)query.size(), descC, off, idx, dist);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (size_t qi = 0; qi < query.size(); ++qi) {
+        const int i = query[qi];
+        int bestDist = 256, bestIdx2 = -1;
+        for (int p = off[qi]; p < off[qi + 1]; ++p) {
+            const int i2 = idx[p];
+            if ((!occupied.empty() && occupied[i2]) || (curMatch[i2] >= 0 && mpHasObservations[curMatch[i2]])) continue;   // :1563-1565
+            if (!uRight.empty() && uRight[i2] > 0) {                                             // :1567-1572
+                const float ur = uv[i].x - mbf * invzc[i];
+                const float er = std::fabs(ur - uRight[i2]);
+                if (er > radii[qi]) continue;
+            }
+            const int d = dist[p];
+            if (d < bestDist) { bestDist = d; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            curMatch[bestIdx2] = i;
+            nmatches++;
+            if (checkOrientation) rotHist[rotation_bin(angleLast[i], keysC[bestIdx2].angle, HISTO_LENGTH)].push_back(bestIdx2);
+        }
+    }
+    if (checkOrientation) nmatches -= clear_rotation_outliers(rotHist, HISTO_LENGTH, curMatch);
+    return nmatches;
+}
+
+int ORBmatcherAccel::SearchByProjectionKeyFrame(const std::vector<cv::KeyPoint>& keysC, const cv::Mat& descC,
+                                                const FrameGridAccel& gridC, const std::vector<float>& scaleFactors,
+                                                const std::vector<uint8_t>& occupied, const std::vector<uint8_t>& valid,
+                                                const std::vector<cv::Point2f>& uv, const std::vector<float>& dist3D,
+                                                const std::vector<float>& minDistance, const std::vector<float>& maxDistance,
+                                                const std::vector<int>& predictedLevel, const std::vector<float>& angleKF,
+                                                const cv::Mat& descMP, float th, int ORBdist, bool checkOrientation,
+                                                std::vector<int>& curMatch) {
+    curMatch.assign(keysC.size(), -1);
+    std::vector<int> query;
+    std::vector<int32_t> off(1, 0), idx;
+    std::vector<uint8_t> Q;
+    for (size_t i = 0; i < uv.size(); i++) {
+        if (!valid[i]) continue;
+        if (uv[i].x < gridC.mnMinX || uv[i].x > gridC.mnMaxX) continue;
+        if (uv[i].y < gridC.mnMinY || uv[i].y > gridC.mnMaxY) continue;
+        if (dist3D[i] < minDistance[i] || dist3D[i] > maxDistance[i]) continue;                  // :1724-1725
+        const int nPredictedLevel = predictedLevel[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        const std::vector<size_t> v = gridC.GetFeaturesInArea(uv[i].x, uv[i].y, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+        if (v.empty()) continue;
+        query.push_back((int)i);
+        idx.insert(idx.end(), v.begin(), v.end());
+        off.push_back((int32_t)idx.size());
+        Q.insert(Q.end(), descMP.ptr((int)i), descMP.ptr((int)i) + 32);
+    }
+    std::vector<uint16_t> dist;
+    CandidateDistances(Q, (int)query.size(), descC, off, idx, dist);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (size_t qi = 0; qi < query.size(); ++qi) {
+        const int i = query[qi];
+        int bestDist = 256, bestIdx2 = -1;
+        for (int p = off[qi]; p < off[qi + 1]; ++p) {
+            const int i2 = idx[p];
+            if ((!occupied.empty() && occupied[i2]) || curMatch[i2] >= 0) continue;              // :1742-1743
+            const int d = dist[p];
+            if (d < bestDist) { bestDist = d; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {
+            curMatch[bestIdx2] = i;
+            nmatches++;
+            if (checkOrientation) rotHist[rotation_bin(angleKF[i], keysC[bestIdx2].angle, HISTO_LENGTH)].push_back(bestIdx2);
+        }
+    }
+    if (checkOrientation) nmatches -= clear_rotation_outliers(rotHist, HISTO_LENGTH, curMatch);
     return nmatches;
 }
 

@@ -26,10 +26,12 @@ public:
     FrameGridAccel(const std::vector<cv::KeyPoint>& keysUn, float minX, float minY, float maxX, float maxY);
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
                                           const int maxLevel = -1) const;
+    // Frame::mnMinX / mnMinY / mnMaxX / mnMaxY (the undistorted image bounds the grid was built for)
+    float mnMinX, mnMinY, mnMaxX, mnMaxY;
 private:
     static const int kCols = 64, kRows = 48;
     const std::vector<cv::KeyPoint>& keys;
-    float mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv;
+    float mfGridElementWidthInv, mfGridElementHeightInv;
     std::vector<std::size_t> mGrid[kCols][kRows];
 };
 
@@ -112,6 +114,35 @@ public:
                            const std::vector<int>& level, const std::vector<float>& viewCos, const cv::Mat& descMP,
                            const std::vector<uint8_t>& hasObservations, float th, std::vector<int>& frameMatch);
 
+    // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (R/lib_src/ORBmatcher.cc:1498-1684),
+    // the matcher of Tracking::TrackWithMotionModel, frames without a second fisheye camera (Nleft == -1).  Last frame, per
+    // feature i: valid[i] = has a map point and is not an outlier (:1518-1520); uv[i], invzc[i] = projection of that point
+    // into the current frame and 1 / depth (the caller's pose and camera model, :1522-1534); octaveLast[i] / angleLast[i] of
+    // its key point; descMP.row(i) = GetDescriptor(); mpHasObservations[i] = Observations() > 0.  Current frame: mvKeysUn,
+    // mDescriptors, its grid, mvScaleFactors, mvuRight (empty: mono), occupied[j] = mvpMapPoints[j] already holds a point
+    // with observations (empty: none), mbf.  bForward / bBackward as computed at :1513-1514.
+    // curMatch[j] = last-frame feature whose map point the reference would store in CurrentFrame.mvpMapPoints[j], or -1.
+    int SearchByProjectionLastFrame(const std::vector<cv::KeyPoint>& keysC, const cv::Mat& descC, const FrameGridAccel& gridC,
+                                    const std::vector<float>& scaleFactors, const std::vector<float>& uRight,
+                                    const std::vector<uint8_t>& occupied, float mbf, const std::vector<uint8_t>& valid,
+                                    const std::vector<cv::Point2f>& uv, const std::vector<float>& invzc,
+                                    const std::vector<int>& octaveLast, const std::vector<float>& angleLast,
+                                    const cv::Mat& descMP, const std::vector<uint8_t>& mpHasObservations, float th,
+                                    bool bForward, bool bBackward, bool checkOrientation, std::vector<int>& curMatch);
+
+    // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (R/lib_src/ORBmatcher.cc:1685-1794),
+    // the matcher of Tracking::Relocalization.  Key frame, per feature i: valid[i] = map point present, not bad, not in
+    // sAlreadyFound; uv[i] = its projection; dist3D[i] = |x3Dw - Ow| against [minDistance[i], maxDistance[i]] (:1717-1725);
+    // predictedLevel[i] = PredictScale (:1727); angleKF[i] = pKF->mvKeysUn[i].angle.  A current-frame feature that holds ANY
+    // map point (occupied[j], or assigned earlier in this call) is skipped (:1742-1743).
+    int SearchByProjectionKeyFrame(const std::vector<cv::KeyPoint>& keysC, const cv::Mat& descC, const FrameGridAccel& gridC,
+                                   const std::vector<float>& scaleFactors, const std::vector<uint8_t>& occupied,
+                                   const std::vector<uint8_t>& valid, const std::vector<cv::Point2f>& uv,
+                                   const std::vector<float>& dist3D, const std::vector<float>& minDistance,
+                                   const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel,
+                                   const std::vector<float>& angleKF, const cv::Mat& descMP, float th, int ORBdist,
+                                   bool checkOrientation, std::vector<int>& curMatch);
+
     // Descriptor-based key-point association of the matched key-frame pairs of a submap merge (the pairs
     // R/lib_src/CloudMerging.cc:503-551 associates by pixel distance): real descriptors for the cloud
     // key frames (ORBextractor::CloudFrameComputeDescriptors, one batched call per side -- they carry zero descriptors in
@@ -126,6 +157,9 @@ public:
 
 private:
     // distance blocks of the vocabulary nodes common to two feature vectors (rumi_bow_node_distances)
+    // distances of every (query row, candidate) pair of CSR candidate lists (rumi_hamming_candidates)
+    void CandidateDistances(const std::vector<uint8_t>& Q, int nq, const cv::Mat& T, const std::vector<int32_t>& off,
+                            const std::vector<int32_t>& idx, std::vector<uint16_t>& dist);
     long long NodeBlocks(const cv::Mat& descA, const std::vector<std::pair<unsigned, std::vector<unsigned> > >& fvA,
                          const cv::Mat& descB, const std::vector<std::pair<unsigned, std::vector<unsigned> > >& fvB,
                          std::vector<int32_t>& aIdx, std::vector<int32_t>& bIdx, std::vector<int32_t>& segs,

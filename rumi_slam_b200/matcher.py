@@ -305,6 +305,112 @@ class ORBmatcher:
                 nmatches += 1
         return nmatches, fm
 
+    # ---- ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1498-1684), Nleft == -1 ----
+    def SearchByProjectionLastFrame(self, keysC, descC, scale_factors, bounds, valid, uv, invz, octave, angle_last, descMP,
+                                    mp_has_obs, th=15.0, u_right=None, occupied=None, mbf=0.0, forward=False, backward=False):
+        """The matcher of Tracking::TrackWithMotionModel on flattened frames.  Last frame, per feature i: valid[i] = has a
+        map point and is not an outlier, uv[i] / invz[i] = projection of that point into the current frame and 1 / depth
+        (the caller's pose and camera model, :1522-1534), octave[i] / angle_last[i] of its key point, descMP[i] =
+        GetDescriptor(), mp_has_obs[i] = Observations() > 0.  Current frame: mvKeysUn, mDescriptors, grid bounds, mvuRight
+        (None: mono), occupied[j] = mvpMapPoints[j] already holds a point with observations.  forward / backward =
+        bForward / bBackward (:1513-1514).  Returns (nmatches, cur_match[j] = last-frame feature or -1).
+        All DescriptorDistance calls of all windows run in one launch; the acceptance is replayed in the reference's order
+        (it depends on earlier assignments, :1563-1565)."""
+        f32 = np.float32
+        kC = np.ascontiguousarray(keysC, KP_DTYPE)
+        sf = np.asarray(scale_factors, f32)
+        uv = np.asarray(uv, f32).reshape(-1, 2)
+        invz, octave = np.asarray(invz, f32), np.asarray(octave, np.int32)
+        ok = np.asarray(valid, bool) & ~(invz < 0) & ~(uv[:, 0] < f32(bounds[0])) & ~(uv[:, 0] > f32(bounds[2])) \
+            & ~(uv[:, 1] < f32(bounds[1])) & ~(uv[:, 1] > f32(bounds[3]))
+        q = np.flatnonzero(ok)
+        radius = (f32(th) * sf[octave[q]]).astype(f32)
+        if forward:
+            lo, hi = octave[q], np.full(len(q), -1, np.int32)
+        elif backward:
+            lo, hi = np.zeros(len(q), np.int32), octave[q]
+        else:
+            lo, hi = octave[q] - 1, octave[q] + 1
+        off, idx = FrameGrid(kC, bounds).candidate_lists(uv[q], radius, lo, hi)
+        dist = self.candidates(np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)[q], descC, off, idx)
+        occ = np.zeros(len(kC), bool) if occupied is None else np.asarray(occupied, bool)
+        ur = None if u_right is None else np.asarray(u_right, f32)
+        has_obs = np.asarray(mp_has_obs, bool)
+        cm = np.full(len(kC), -1, np.int32)
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        nmatches = 0
+        for qi, i in enumerate(q):
+            best, best_idx = 256, -1
+            for p in range(off[qi], off[qi + 1]):
+                j = int(idx[p])
+                if occ[j] or (cm[j] >= 0 and has_obs[cm[j]]):
+                    continue
+                if ur is not None and ur[j] > 0:
+                    if abs(f32(uv[i, 0] - f32(f32(mbf) * invz[i])) - ur[j]) > radius[qi]:
+                        continue
+                d = int(dist[p])
+                if d < best:
+                    best, best_idx = d, j
+            if best <= self.TH_HIGH:
+                cm[best_idx] = i
+                nmatches += 1
+                if self.mbCheckOrientation:
+                    rot_hist[self._rot_bin(angle_last[i], kC["angle"][best_idx])].append(best_idx)
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for b in range(self.HISTO_LENGTH):
+                if b not in keep:
+                    for j in rot_hist[b]:                       # (:1672-1675: no "still set" test, duplicates count twice)
+                        cm[j] = -1
+                        nmatches -= 1
+        return nmatches, cm
+
+    # ---- ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794) ----
+    def SearchByProjectionKeyFrame(self, keysC, descC, scale_factors, bounds, valid, uv, dist3d, min_dist, max_dist, level,
+                                   angle_kf, descMP, th=10.0, orb_dist=100, occupied=None):
+        """The matcher of Tracking::Relocalization on flattened inputs.  Key frame, per feature i: valid[i] = map point
+        present, not bad, not in sAlreadyFound; uv[i] = its projection; dist3d[i] = |x3Dw - Ow| with the invariance window
+        [min_dist, max_dist]; level[i] = PredictScale; angle_kf[i]; descMP[i].  A current-frame feature holding ANY map point
+        (occupied[j] or assigned earlier in this call) is skipped.  Returns (nmatches, cur_match[j] = key-frame feature)."""
+        f32 = np.float32
+        kC = np.ascontiguousarray(keysC, KP_DTYPE)
+        sf = np.asarray(scale_factors, f32)
+        uv = np.asarray(uv, f32).reshape(-1, 2)
+        d3, lo_d, hi_d = np.asarray(dist3d, f32), np.asarray(min_dist, f32), np.asarray(max_dist, f32)
+        level = np.asarray(level, np.int32)
+        ok = np.asarray(valid, bool) & ~(uv[:, 0] < f32(bounds[0])) & ~(uv[:, 0] > f32(bounds[2])) & ~(uv[:, 1] < f32(bounds[1])) \
+            & ~(uv[:, 1] > f32(bounds[3])) & ~(d3 < lo_d) & ~(d3 > hi_d)
+        q = np.flatnonzero(ok)
+        radius = (f32(th) * sf[level[q]]).astype(f32)
+        off, idx = FrameGrid(kC, bounds).candidate_lists(uv[q], radius, level[q] - 1, level[q] + 1)
+        dist = self.candidates(np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)[q], descC, off, idx)
+        occ = np.zeros(len(kC), bool) if occupied is None else np.asarray(occupied, bool)
+        cm = np.full(len(kC), -1, np.int32)
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        nmatches = 0
+        for qi, i in enumerate(q):
+            best, best_idx = 256, -1
+            for p in range(off[qi], off[qi + 1]):
+                j = int(idx[p])
+                if occ[j] or cm[j] >= 0:
+                    continue
+                d = int(dist[p])
+                if d < best:
+                    best, best_idx = d, j
+            if best <= orb_dist:
+                cm[best_idx] = i
+                nmatches += 1
+                if self.mbCheckOrientation:
+                    rot_hist[self._rot_bin(angle_kf[i], kC["angle"][best_idx])].append(best_idx)
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for b in range(self.HISTO_LENGTH):
+                if b not in keep:
+                    for j in rot_hist[b]:
+                        cm[j] = -1
+                        nmatches -= 1
+        return nmatches, cm
+
     # ---- descriptor-based key-point association of matched key-frame pairs (submap merge, SURVEY.md 8f rank 3) ----
     def AssociateSubmap(self, extractor, images1, keys1, valid1, images2, keys2, valid2, th=None):
         """For every matched key-frame pair p (the pairs CloudMerging.cc:503-551 walks): real descriptors for the cloud key

@@ -94,6 +94,29 @@ int main(int argc, char** argv) {
             std::fwrite(&na, 4, 1, f);
             std::fwrite(&n1, 4, 1, f);
             std::fwrite(a12[0].data(), 4, a12[0].size(), f);
+            // the projection matchers of TrackWithMotionModel / Relocalization: last frame / key frame = left image, current
+            // frame = right image; deterministic synthetic projections (the test rebuilds the same numbers)
+            const int nL = (int)L.keys.size();
+            std::vector<uint8_t> valid(nL), hasObs(nL), noneU8;
+            std::vector<cv::Point2f> uv(nL);
+            std::vector<float> invz(nL), angle(nL), d3(nL), dmin(nL, 0.5f), dmax(nL, 12.0f), noneF, sf = exL.GetScaleFactors();
+            std::vector<int> octave(nL);
+            for (int i = 0; i < nL; ++i) {
+                valid[i] = i % 7 != 0; hasObs[i] = i % 5 != 0;
+                uv[i] = cv::Point2f(L.keys[i].pt.x - 2.0f, L.keys[i].pt.y + 1.0f);
+                d3[i] = 1.0f + (float)(i % 13);
+                invz[i] = 1.0f / d3[i];
+                angle[i] = L.keys[i].angle; octave[i] = L.keys[i].octave;
+            }
+            std::vector<int> cmLast, cmKF;
+            const int nl = mi.SearchByProjectionLastFrame(R.keys, R.desc, grid, sf, noneF, noneU8, 0.f, valid, uv, invz, octave, angle,
+                                                          L.desc, hasObs, 15.0f, false, false, true, cmLast);
+            const int nk = mi.SearchByProjectionKeyFrame(R.keys, R.desc, grid, sf, noneU8, valid, uv, d3, dmin, dmax, octave, angle,
+                                                         L.desc, 10.0f, 100, true, cmKF);
+            const int nR = (int)R.keys.size();
+            std::fwrite(&nl, 4, 1, f); std::fwrite(&nk, 4, 1, f); std::fwrite(&nR, 4, 1, f);
+            std::fwrite(cmLast.data(), 4, cmLast.size(), f);
+            std::fwrite(cmKF.data(), 4, cmKF.size(), f);
         }
         // the empty-image contract of operator() (ORBextractor.cc:1017)
         cv::Mat empty; Result E;

@@ -95,3 +95,20 @@ def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
     i1, e1, e2 = oracle.hamming_top2(d1, d2)
     ok = (i1 >= 0) & (e1 <= 50) & (e1.astype(np.float32) < np.float32(0.75) * e2.astype(np.float32))
     assert n1 == len(k1) and na == int(ok.sum()) and np.array_equal(a12, np.where(ok, i1, -1))
+    off += 4 * n1
+    # ORBmatcherAccel::SearchByProjectionLastFrame / ::SearchByProjectionKeyFrame, executed in C++ on the same inputs
+    nl, nk, nR = (int(v) for v in np.frombuffer(buf, np.int32, 3, off)); off += 12
+    cm_last = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    cm_kf = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    i = np.arange(len(lk))
+    valid, has_obs = i % 7 != 0, i % 5 != 0
+    uv = np.stack([lk["x"] - np.float32(2.0), lk["y"] + np.float32(1.0)], 1).astype(np.float32)
+    d3 = (1.0 + (i % 13)).astype(np.float32)
+    invz = (np.float32(1.0) / d3).astype(np.float32)
+    sf = oracle.tables()["scale"]
+    rn1, rcm1 = M.search_by_projection_last(rk, rd, sf, (0, 0, 752, 480), valid, uv, invz, lk["octave"], lk["angle"], ld, has_obs,
+                                            15.0, None, None, 0.0, False, False, True)
+    rn2, rcm2 = M.search_by_projection_kf(rk, rd, sf, (0, 0, 752, 480), valid, uv, d3, np.full(len(lk), 0.5, np.float32),
+                                          np.full(len(lk), 12.0, np.float32), lk["octave"], lk["angle"], ld, 10.0, 100, None, True)
+    assert nR == len(rk) and nl == rn1 and np.array_equal(cm_last, rcm1) and rn1 > 50
+    assert nk == rn2 and np.array_equal(cm_kf, rcm2) and rn2 > 30

@@ -1,5 +1,5 @@
 """GPU parity of candidate-list matching (rumi_hamming_candidates) and of the matchers built on it: the reference's
-SearchForInitialization and SearchByProjection, and the descriptor-based key-point association of a submap merge
+SearchForInitialization and three SearchByProjection overloads (map points, last frame, key frame), and the descriptor-based key-point association of a submap merge
 (40 front + 40 back key frames).  The oracle side is pinned to the unmodified reference functions
 (tests/test_ref_frame_pin.py)."""
 import numpy as np
@@ -63,6 +63,62 @@ def test_search_for_initialization_matches_oracle(oracle, M, seed, window, ratio
     rn, rm, rp = M.search_for_initialization(k1, d1, k2, d2, (0, 0, 640, 480), prev, window, ratio, check_ori)
     assert n == rn and np.array_equal(m12, rm) and np.array_equal(p, rp)
     assert rn > (20 if ratio > 0.8 else 0)
+
+
+def _projection_case(oracle, seed, stereo):
+    """Last frame / key frame = frame 1 with map points projected to where its features moved (+ noise), see
+    tests/test_ref_frame_pin.py::_last_frame_case (same construction; the oracle side is pinned there)."""
+    k1, d1, k2, d2 = frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed)
+    n1, n2 = len(k1), len(k2)
+    uv = np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(np.float32) + rng.normal(0, 1.5, (n1, 2)).astype(np.float32)
+    uv[rng.random(n1) < 0.02] += np.float32(700.0)
+    depth = rng.uniform(0.5, 20.0, n1).astype(np.float32)
+    depth[rng.random(n1) < 0.03] *= np.float32(-1.0)
+    valid = (rng.random(n1) < 0.85).astype(np.uint8)
+    has_obs = (rng.random(n1) < 0.8).astype(np.uint8)
+    occupied = (rng.random(n2) < 0.05).astype(np.uint8)
+    u_right = np.where(rng.random(n2) < 0.7, k2["x"] - 40.0 / rng.uniform(0.5, 20.0, n2), -1.0).astype(np.float32) if stereo else None
+    return k1, d1, k2, d2, uv, depth, valid, has_obs, occupied, u_right
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,mode", [(11, 15.0, "mono"), (12, 7.0, "mono"), (13, 15.0, "stereo"), (14, 15.0, "forward"),
+                                          (15, 15.0, "backward")])
+def test_search_by_projection_last_frame_matches_oracle(oracle, M, seed, th, mode, check_ori):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (R/lib_src/ORBmatcher.cc:1498-1684)."""
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2, uv, depth, valid, has_obs, occupied, u_right = _projection_case(oracle, seed, mode != "mono")
+    sf = oracle.tables()["scale"]
+    invz = (1.0 / depth.astype(np.float64)).astype(np.float32)
+    fwd, bwd = mode == "forward", mode == "backward"
+    n, cm = ORBmatcher(0.9, check_ori).SearchByProjectionLastFrame(k2, d2, sf, (0, 0, 640, 480), valid, uv, invz, k1["octave"],
+                                                                   k1["angle"], d1, has_obs, th, u_right, occupied, 40.0, fwd, bwd)
+    rn, rcm = M.search_by_projection_last(k2, d2, sf, (0, 0, 640, 480), valid, uv, invz, k1["octave"], k1["angle"], d1, has_obs,
+                                          th, u_right, occupied, 40.0, fwd, bwd, check_ori)
+    assert n == rn and np.array_equal(cm, rcm)
+    assert rn > 100
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,orb_dist", [(21, 10.0, 100), (22, 3.0, 64)])
+def test_search_by_projection_keyframe_matches_oracle(oracle, M, seed, th, orb_dist, check_ori):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (R/lib_src/ORBmatcher.cc:1685-1794)."""
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2, uv, depth, valid, _, occupied, _ = _projection_case(oracle, seed, False)
+    rng = np.random.default_rng(seed + 100)
+    n1 = len(k1)
+    sf = oracle.tables()["scale"]
+    level = np.clip(k1["octave"] + rng.integers(-1, 2, n1), 0, 7).astype(np.int32)
+    dist3d = np.abs(depth)
+    min_d = rng.uniform(0.0, 6.0, n1).astype(np.float32)
+    max_d = (min_d + rng.uniform(0.0, 30.0, n1)).astype(np.float32)
+    n, cm = ORBmatcher(0.9, check_ori).SearchByProjectionKeyFrame(k2, d2, sf, (0, 0, 640, 480), valid, uv, dist3d, min_d, max_d,
+                                                                  level, k1["angle"], d1, th, orb_dist, occupied)
+    rn, rcm = M.search_by_projection_kf(k2, d2, sf, (0, 0, 640, 480), valid, uv, dist3d, min_d, max_d, level, k1["angle"], d1,
+                                        th, orb_dist, occupied, check_ori)
+    assert n == rn and np.array_equal(cm, rcm)
+    assert rn > 30
 
 
 @pytest.mark.parametrize("seed,th,ratio", [(6, 3.0, 0.8), (7, 1.0, 0.8), (8, 5.0, 0.9), (9, 15.0, 0.6)])

@@ -182,3 +182,66 @@ def test_search_by_projection_equals_reference(oracle, rf, M, seed, th, ratio):
     rn, rfm = rf.search_by_projection(k2, d2, sf, (0, 0, 640, 480), proj, level, view_cos, d1, has_obs, th, ratio)
     assert n == rn and np.array_equal(fm, rfm)
     assert rn > 50
+
+
+def _last_frame_case(oracle, seed, stereo):
+    """Frame 1 = last frame (its features carry map points), frame 2 = current frame; map point i is projected to where
+    frame 1's feature moved (known image motion + noise), with a depth; some features lack a map point / are outliers,
+    some map points have no observations, a few projections fall outside the image or behind the camera."""
+    k1, d1, k2, d2 = _frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed)
+    n1, n2 = len(k1), len(k2)
+    uv = np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(np.float32) + rng.normal(0, 1.5, (n1, 2)).astype(np.float32)
+    uv[rng.random(n1) < 0.02] += np.float32(700.0)                       # out of the image bounds
+    depth = rng.uniform(0.5, 20.0, n1).astype(np.float32)
+    depth[rng.random(n1) < 0.03] *= np.float32(-1.0)                     # behind the camera: invzc < 0
+    valid = (rng.random(n1) < 0.85).astype(np.uint8)
+    has_obs = (rng.random(n1) < 0.8).astype(np.uint8)
+    occupied = (rng.random(n2) < 0.05).astype(np.uint8)
+    u_right = None
+    if stereo:
+        u_right = np.where(rng.random(n2) < 0.7, k2["x"] - 40.0 / rng.uniform(0.5, 20.0, n2), -1.0).astype(np.float32)
+    return k1, d1, k2, d2, uv, depth, valid, has_obs, occupied, u_right
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,mode", [(11, 15.0, "mono"), (12, 7.0, "mono"), (13, 15.0, "stereo"), (14, 15.0, "forward"),
+                                          (15, 15.0, "backward"), (16, 30.0, "stereo")])
+def test_search_by_projection_last_frame_equals_reference(oracle, rf, M, seed, th, mode, check_ori):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (R/lib_src/ORBmatcher.cc:1498-1684), the matcher of
+    TrackWithMotionModel: level windows for forward / backward / lateral motion, the right-image consistency test, the
+    order-dependent 'feature already holds a point with observations' skip, overwriting, the rotation histogram."""
+    k1, d1, k2, d2, uv, depth, valid, has_obs, occupied, u_right = _last_frame_case(oracle, seed, mode != "mono")
+    sf = oracle.tables()["scale"]
+    fwd, bwd = mode == "forward", mode == "backward"
+    invz = (1.0 / depth.astype(np.float64)).astype(np.float32)          # const float invzc = 1.0 / x3Dc(2)  (:1527)
+    n, cm = M.search_by_projection_last(k2, d2, sf, (0, 0, 640, 480), valid, uv, invz, k1["octave"], k1["angle"], d1, has_obs,
+                                        th, u_right, occupied, 40.0, fwd, bwd, check_ori)
+    rn, rcm = rf.search_by_projection_last(k2, d2, sf, (0, 0, 640, 480), valid, uv, depth, k1["octave"], k1["angle"], d1,
+                                           has_obs, th, u_right, occupied, 40.0, fwd, bwd, check_ori)
+    assert n == rn and np.array_equal(cm, rcm)
+    assert rn > 100
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,orb_dist", [(21, 10.0, 100), (22, 3.0, 64), (23, 10.0, 50)])
+def test_search_by_projection_keyframe_equals_reference(oracle, rf, M, seed, th, orb_dist, check_ori):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (R/lib_src/ORBmatcher.cc:1685-1794), the
+    matcher of Relocalization: bad / already-found points, the distance-invariance window, the predicted level window,
+    'any map point' occupancy, the rotation histogram."""
+    k1, d1, k2, d2, uv, depth, _, _, occupied, _ = _last_frame_case(oracle, seed, False)
+    depth = np.abs(depth)
+    rng = np.random.default_rng(seed + 100)
+    n1 = len(k1)
+    sf = oracle.tables()["scale"]
+    state = rng.choice([0, 1, 1, 1, 1, 1, 2, 3], n1).astype(np.uint8)
+    level = np.clip(k1["octave"] + rng.integers(-1, 2, n1), 0, 7).astype(np.int32)
+    min_d = rng.uniform(0.0, 6.0, n1).astype(np.float32)
+    max_d = (min_d + rng.uniform(0.0, 800.0, n1)).astype(np.float32)
+    # the reference compares |x3Dw - Ow| of the stand-in world point (uv, depth): take that number from the reference run
+    rn, rcm, dist3d = rf.search_by_projection_kf(k2, d2, sf, (0, 0, 640, 480), state, uv, depth, level, min_d, max_d, k1["angle"],
+                                                 d1, th, orb_dist, occupied, check_ori)
+    n, cm = M.search_by_projection_kf(k2, d2, sf, (0, 0, 640, 480), state == 1, uv, dist3d, min_d, max_d, level, k1["angle"], d1,
+                                      th, orb_dist, occupied, check_ori)
+    assert n == rn and np.array_equal(cm, rcm)
+    assert rn > 30

@@ -712,9 +712,17 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
         const int c = h->chunk, q = std::max(c / 4, 1), hf = std::max(c / 2, 1);
         int left = n;
         std::vector<int> tail;
-        if (!h->profile && n >= 6 * c && c >= 16) {
-            for (int sz : {q, q, hf}) { sizes.push_back(sz); left -= sz; }
-            for (int sz : {q, hf}) { tail.push_back(sz); left -= sz; }
+        if ((!h->profile || getenv("RUMI_RAMP_HEAD")) && n >= 6 * c && c >= 16) {
+            std::vector<int> head = {q, q, hf}, tl = {q, hf};
+            auto parse = [&](const char* e, std::vector<int>& v) {              // "16,16,32" (measurement runs only)
+                if (!e) return;
+                v.clear();
+                for (const char* p = e; *p;) { v.push_back(std::max(1, atoi(p))); while (*p && *p != ',') ++p; if (*p) ++p; }
+            };
+            parse(getenv("RUMI_RAMP_HEAD"), head);
+            parse(getenv("RUMI_RAMP_TAIL"), tl);
+            for (int sz : head) { sizes.push_back(sz); left -= sz; }
+            for (int sz : tl) { tail.push_back(sz); left -= sz; }
         }
         while (left > 0) { const int sz = std::min(c, left); sizes.push_back(sz); left -= sz; }
         for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
@@ -1006,11 +1014,19 @@ int rumi_orb_profile_read(rumi_orb* h, double* stage_ms, long long* stage_launch
     CU_TRY(cudaSetDevice(h->device));
     for (int i = 0; i < kMaxWs; ++i)
         if (h->ws[i].stream) CU_TRY(cudaStreamSynchronize(h->ws[i].stream));
+    FILE* tl = nullptr;                                        // RUMI_TIMELINE=<file>: "stage start_ms end_ms" per span
+    if (const char* path = getenv("RUMI_TIMELINE")) tl = fopen(path, "a");
     for (const auto& sp : h->evSpans) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, h->evPool[sp.second], h->evPool[sp.second + 1]));
         h->stageMs[sp.first] += ms;
+        if (tl) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, h->evPool[h->evSpans.front().second], h->evPool[sp.second]);
+            fprintf(tl, "%d %.4f %.4f\n", sp.first, t0, t0 + ms);
+        }
     }
+    if (tl) { fprintf(tl, "-1 0 0\n"); fclose(tl); }
     h->evSpans.clear();
     h->evUsed = 0;
     for (int i = 0; i < ST_COUNT; ++i) {

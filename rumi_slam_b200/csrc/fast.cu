@@ -247,14 +247,19 @@ __global__ void __launch_bounds__(kFastWarps * 32, 8) fast_kernel(const __grid_c
                 pass4 = any & validTab[gl];                                      // bytes inside the detection area
             }
             const int o0 = y * tp + 4 * g - c0;                                  // offset of byte 0 of the group
-            {   // append the surviving pixels: one ballot per byte plane (the order inside the queue is irrelevant)
+            {   // append the surviving pixels (the order inside the queue is irrelevant).  A lane has 0..4 of them: the warp
+                // prefix sum of the counts comes from three ballots on the bits of the count (instead of one ballot +
+                // two popcounts + an address per byte plane), then every lane stores its own hits back to back.
                 const unsigned lt = (1u << lane) - 1u;
+                const uint32_t hits = pass4 & 0x80808080u;
+                const int cnt = __popc(hits);
+                const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2), b2 = __ballot_sync(kFull, cnt & 4);
+                if (b0 | b1 | b2) {                                                  // warp uniform
+                    int pos = qn + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+                    qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool hit = (pass4 >> (8 * j + 7)) & 1u;
-                    const unsigned m = __ballot_sync(kFull, hit);
-                    if (hit) queue[qn + __popc(m & lt)] = (uint16_t)(o0 + j);
-                    qn += __popc(m);
+                    for (int j = 0; j < 4; ++j)
+                        if (hits & (0x80u << (8 * j))) queue[pos++] = (uint16_t)(o0 + j);
                 }
             }
             __syncwarp();

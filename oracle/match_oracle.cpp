@@ -5,6 +5,7 @@
 //   ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...)     R/lib_src/ORBmatcher.cc:39-189 (mono frame, Nleft == -1)
 //   ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono)   R/lib_src/ORBmatcher.cc:1498-1684 (Nleft == -1)
 //   ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)   R/lib_src/ORBmatcher.cc:1685-1794
+//   ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight)  (matching core)   R/lib_src/ORBmatcher.cc:1015-1181 (NLeft == -1)
 //   CloudMerging's pixel-distance key-point association              R/lib_src/CloudMerging.cc:503-551
 // Pinned against the UNMODIFIED reference functions compiled into oracle/_ref/librefframe.so
 // (tests/test_ref_frame_pin.py).  FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48 (R/include/cloud_edge_slam_lib/Frame.h:42-43).
@@ -325,6 +326,55 @@ int mo_search_by_projection_kf(const void* kCv, const uint8_t* dC, int nC, const
         }
     }
     return nmatches;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, vpMapPoints, th, false) (ORBmatcher.cc:1015-1181), the matcher of
+// LocalMapping::SearchInNeighbors, for key frames without a second fisheye camera: everything up to the decision "map point
+// i fuses with key-frame feature bestIdx" (:1147).  What follows (Replace / AddObservation / AddMapPoint, :1148-1160) edits
+// the map and stays with the caller; it does not feed back into later iterations of the search.
+// Per map point i: valid[i] = present, not bad, not already in pKF, depth >= 0, viewing angle test passed (:1045-1100, the
+// caller's pose / camera / normal); uv[i] = projection, ur[i] = uv.x - bf * invz (:1074), dist3D[i] vs [minDist, maxDist],
+// level[i] = PredictScale.  Key frame: mvKeysUn, descriptors, mvuRight (< 0: mono feature), mvInvLevelSigma2, grid.
+// bestIdx[i] = key-frame feature (bestDist <= TH_LOW) or -1; returns nFused.
+int mo_fuse_search(const void* kKv, const uint8_t* dK, int nK, const float* scaleFactors, const float* invLevelSigma2, int minX,
+                   int minY, int maxX, int maxY, const float* uRight, const uint8_t* valid, const float* uv, const float* ur,
+                   const float* dist3D, const float* minDist, const float* maxDist, const int32_t* level, const uint8_t* dMP,
+                   int nMP, float th, int32_t* bestIdxOut, int32_t* bestDistOut) {
+    const KP* kK = (const KP*)kKv;
+    Grid g(kK, nK, minX, minY, maxX, maxY);
+    std::vector<int> vIndices;
+    int nFused = 0;
+    for (int i = 0; i < nMP; ++i) {
+        bestIdxOut[i] = -1; bestDistOut[i] = 256;
+        if (!valid[i]) continue;
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        if (!(u >= (float)minX && u < (float)maxX && v >= (float)minY && v < (float)maxY)) continue;   // KeyFrame::IsInImage
+        if (dist3D[i] < minDist[i] || dist3D[i] > maxDist[i]) continue;
+        const int nPredictedLevel = level[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        g.query(u, v, radius, -1, -1, vIndices);                       // KeyFrame::GetFeaturesInArea: no level filter
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            const KP& kp = kK[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (uRight[idx] >= 0) {                                    // stereo feature: 3-dof reprojection error (:1116-1128)
+                const float ex = u - kp.x, ey = v - kp.y, er = ur[i] - uRight[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            }
+            const int dist = descriptor_distance(dMP + 32 * (size_t)i, dK + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        bestDistOut[i] = bestDist;
+        if (bestDist <= TH_LOW) { bestIdxOut[i] = bestIdx; nFused++; }
+    }
+    return nFused;
 }
 
 // CloudMerging.cc:503-551 for one matched key-frame pair: per key point of key frame 1 the nearest key point of key

@@ -152,6 +152,23 @@ def search_by_projection_kf(kC, dC, scale_factors, bounds, valid, uv, dist3d, mi
     return n, out[:len(kC)]
 
 
+def fuse_search(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, valid, uv, ur, dist3d, min_dist, max_dist, level, dMP,
+                th=3.0):
+    """Matching core of ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:1015-1147): (nFused, bestIdx, bestDist)."""
+    kK = np.ascontiguousarray(kK, KP_DTYPE)
+    dK, dMP = _u8(dK).reshape(-1, 32), _u8(dMP).reshape(-1, 32)
+    n = len(dMP)
+    bi, bd = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    L = lib()
+    L.mo_fuse_search.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p, _f32p,
+                                 _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, C.c_int, C.c_float, _i32p, _i32p]
+    nf = L.mo_fuse_search(kK.ctypes.data, _p(dK, _u8p), len(kK), _p(_f32(scale_factors), _f32p), _p(_f32(inv_level_sigma2), _f32p),
+                          *[int(b) for b in bounds], _p(_f32(u_right), _f32p), _p(_u8(valid), _u8p), _p(_f32(uv), _f32p),
+                          _p(_f32(ur), _f32p), _p(_f32(dist3d), _f32p), _p(_f32(min_dist), _f32p), _p(_f32(max_dist), _f32p),
+                          _p(np.ascontiguousarray(level, np.int32), _i32p), _p(dMP, _u8p), n, float(th), _p(bi, _i32p), _p(bd, _i32p))
+    return nf, bi[:n], bd[:n]
+
+
 def associate_pixels(k1, valid1, k2, valid2, bounds, tol=3.0):
     """CloudMerging.cc:503-551 for one key-frame pair: (matchNum, match12)."""
     k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)

@@ -215,3 +215,26 @@ def search_by_projection_kf(kC, dC, scale_factors, bounds, state, uv, depth, lev
                                       _p(f32(max_dist), _f32p), _p(f32(angle_kf), _f32p), _p(dMP, _u8p), len(dMP), float(th),
                                       int(orb_dist), 0.9, int(check_ori), _p(out, _i32p), _p(d3, _f32p))
     return n, out[:len(kC)], d3[:len(dMP)]
+
+
+def fuse(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, kf_has_point, bf, state, uv, depth, min_dist, max_dist, level,
+         dMP, n_obs, th=3.0):
+    """The reference's ORBmatcher::Fuse(pKF, vpMapPoints, th, false): (nFused, bestIdx[i] = key-frame feature map point i was
+    fused with, reconstructed from the logged GetMapPoint / Replace / AddObservation calls; -1 = not fused, or fused with a
+    feature whose resident point is bad -- that case leaves no trace)."""
+    kK = np.ascontiguousarray(kK, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    dK, dMP = u8(dK).reshape(-1, 32), u8(dMP).reshape(-1, 32)
+    sf = f32(scale_factors)
+    n = len(dMP)
+    out = np.zeros(max(n, 1), np.int32)
+    L = lib()
+    L.ref_fuse.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p,
+                           C.c_float, _u8p, _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, _i32p, C.c_int, C.c_float, _i32p]
+    nf = L.ref_fuse(kK.ctypes.data, _p(dK, _u8p), len(kK), _p(sf, _f32p), _p(f32(inv_level_sigma2), _f32p), len(sf),
+                    *[int(b) for b in bounds], _p(f32(u_right), _f32p), _p(u8(kf_has_point), _u8p), float(bf), _p(u8(state), _u8p),
+                    _p(f32(uv), _f32p), _p(f32(depth), _f32p), _p(f32(min_dist), _f32p), _p(f32(max_dist), _f32p),
+                    _p(i32(level), _i32p), _p(dMP, _u8p), _p(i32(n_obs), _i32p), n, float(th), _p(out, _i32p))
+    return nf, out[:n]

@@ -11,7 +11,8 @@
 //   ORBmatcher::SearchByBoW (KeyFrame, Frame) / (KeyFrame, KeyFrame)           R/lib_src/ORBmatcher.cc:198-370, 682-804
 //   ORBmatcher::SearchByProjection (Frame, MapPoints) / SearchForInitialization   R/lib_src/ORBmatcher.cc:39-189, 581-680
 //   ORBmatcher::SearchByProjection (CurrentFrame, LastFrame) / (CurrentFrame, KeyFrame, sAlreadyFound)   :1498-1684, 1685-1794
-//     (these two take poses and a camera model: Sophus::SE3f / Eigen::Vector3f / GeometricCamera are minimal stand-ins
+//   ORBmatcher::Fuse (KeyFrame, MapPoints) + KeyFrame::GetFeaturesInArea / IsInImage   ORBmatcher.cc:1015-1181, KeyFrame.cc:887-930
+//     (these take poses and a camera model: Sophus::SE3f / Eigen::Vector3f / GeometricCamera are minimal stand-ins
 //      below -- identity rotation, so that "Tcw * x3Dw" is exact -- and the pin covers everything AFTER the projection,
 //      which is what the flattened adapters take over; the projection itself stays with the caller's own Sophus / camera)
 // cv::norm(NORM_L1) on 8U is an exact integer sum.
@@ -50,6 +51,7 @@ struct Vector3f {
     float operator()(int i) const { return v[i]; }
     Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
     float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+    float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
 };
 }  // namespace Eigen
 namespace Sophus {
@@ -90,6 +92,14 @@ public:
     float GetMaxDistanceInvariance() { return mfMaxDistance; }
     float GetMinDistanceInvariance() { return mfMinDistance; }
     int PredictScale(const float&, Frame*) { return mnTrackScaleLevel; }       // stand-in: the level the test prescribes
+    int PredictScale(const float&, KeyFrame*) { return mnTrackScaleLevel; }
+    Eigen::Vector3f GetNormal() { return mNormal; }
+    bool IsInKeyFrame(KeyFrame*) { return mbInKF; }
+    void Replace(MapPoint* other);                                             // Fuse: logged, the map is not edited
+    void AddObservation(KeyFrame*, int idx);
+    Eigen::Vector3f mNormal;
+    bool mbInKF = false;
+    int id = -1;
     Eigen::Vector3f mWorldPos;
     float mfMaxDistance = 1e30f, mfMinDistance = 0.0f;
     // state
@@ -104,12 +114,29 @@ class KeyFrame {
 public:
     bool isBad() { return false; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    MapPoint* GetMapPoint(const size_t& idx);                                  // Fuse: logged
+    void AddMapPoint(MapPoint*, const size_t&) {}
     std::vector<MapPoint*> mvpMapPoints;
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+    std::vector<float> mvuRight, mvScaleFactors, mvInvLevelSigma2;
+    GeometricCamera* mpCamera = nullptr;
     GeometricCamera* mpCamera2 = nullptr;
-    int NLeft = -1;
+    int NLeft = -1, N = 0;
+    float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0;
+    Sophus::SE3f mTcw;
+    Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetRightPose() { return mTcw; }
+    Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
+    Eigen::Vector3f GetRightCameraCenter() { return GetCameraCenter(); }
+    // grid (R/include/cloud_edge_slam_lib/KeyFrame.h:341-344, 425-428; copied from the Frame in the KeyFrame constructor)
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+    std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool IsInImage(const float& x, const float& y) const;
 };
 
 struct ExtractorView { std::vector<cv::Mat> mvImagePyramid; };
@@ -157,6 +184,7 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
                            const int ORBdist);
+    int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -166,6 +194,12 @@ protected:
     float mfNNratio;
     bool mbCheckOrientation;
 };
+
+// Fuse edits the map through these three calls; the stand-ins only record which map point met which key-frame feature
+static std::vector<std::pair<int, int>> g_fuseLog;                                 // (map point id, key-frame feature)
+MapPoint* KeyFrame::GetMapPoint(const size_t& idx) { g_fuseLog.push_back(std::make_pair(-1, (int)idx)); return mvpMapPoints[idx]; }
+void MapPoint::Replace(MapPoint* other) { g_fuseLog.back().first = id >= 0 ? id : other->id; }
+void MapPoint::AddObservation(KeyFrame*, int) { g_fuseLog.back().first = id; }
 
 // ================= the reference's own function bodies, cut from /root/reference at build time =================
 #include "_ref/gen_frame_functions.inc"
@@ -432,6 +466,62 @@ int ref_search_by_projection_kf(const void* kC, const uint8_t* dC, int nC, const
         curMatch[j] = (p && p != &taken) ? (int)(p - mps.data()) : -1;
     }
     return n;
+}
+
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, false) (ORBmatcher.cc:1015-1181) on a key frame without a second camera.  Map
+// point i: state[i] = 0 null, 1 usable, 2 bad, 3 already in pKF, 4 viewing angle > 60 deg (normal points away); position
+// (uv, depth) through the stand-in camera, invariance window, prescribed PredictScale level, descriptor.  Key frame: key
+// points, descriptors, mvuRight, mvInvLevelSigma2, kfHasPoint[j] = 0 none, 1 a point with 5 observations, 2 a bad point.
+// bestIdx[i] = the key-frame feature the reference fused map point i with (from the logged GetMapPoint / Replace /
+// AddObservation calls), else -1.  Returns nFused.
+int ref_fuse(const void* kK, const uint8_t* dK, int nK, const float* scaleFactors, const float* invLevelSigma2, int nlevels, int minX,
+             int minY, int maxX, int maxY, const float* uRight, const uint8_t* kfHasPoint, float bf, const uint8_t* state,
+             const float* uv, const float* depth, const float* minDist, const float* maxDist, const int32_t* level,
+             const uint8_t* dMP, const int32_t* nObs, int nMP, float th, int32_t* bestIdx) {
+    set_grid(minX, minY, maxX, maxY);
+    GeometricCamera cam;
+    Frame F;                                       // the frame the key frame was made from: builds the grid
+    F.N = nK; F.mvKeysUn = keys(kK, nK); F.mvKeys = F.mvKeysUn;
+    F.AssignFeaturesToGrid();
+    KeyFrame kf;
+    kf.N = nK; kf.mvKeysUn = F.mvKeysUn; kf.mvKeys = F.mvKeysUn; kf.mDescriptors = rows32(dK, nK);
+    kf.mvuRight.assign(uRight, uRight + nK);
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvInvLevelSigma2.assign(invLevelSigma2, invLevelSigma2 + nlevels);
+    kf.mpCamera = &cam; kf.mbf = bf;
+    kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    kf.mnMinX = minX; kf.mnMinY = minY; kf.mnMaxX = maxX; kf.mnMaxY = maxY;
+    kf.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) kf.mGrid[i][j] = F.mGrid[i][j];
+    MapPoint inKF, badInKF;
+    inKF.nObs = 5; inKF.id = -1000; badInKF.mbBad = true; badInKF.id = -1000;
+    kf.mvpMapPoints.assign(nK, nullptr);
+    for (int j = 0; j < nK; ++j) kf.mvpMapPoints[j] = kfHasPoint[j] == 1 ? &inKF : kfHasPoint[j] == 2 ? &badInKF : nullptr;
+    std::vector<MapPoint> mps(nMP);
+    std::vector<MapPoint*> ptrs(nMP, nullptr);
+    for (int i = 0; i < nMP; ++i) {
+        MapPoint& m = mps[i];
+        m.id = i;
+        m.mWorldPos = Eigen::Vector3f(uv[2 * i], uv[2 * i + 1], depth[i]);
+        const float n = m.mWorldPos.norm();
+        const float sgn = state[i] == 4 ? -1.0f : 1.0f;                        // normal along / against the viewing ray
+        m.mNormal = Eigen::Vector3f(sgn * m.mWorldPos(0) / n, sgn * m.mWorldPos(1) / n, sgn * m.mWorldPos(2) / n);
+        m.mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+        m.mnTrackScaleLevel = level[i];
+        m.mfMinDistance = minDist[i]; m.mfMaxDistance = maxDist[i];
+        m.nObs = nObs[i];
+        m.mbBad = state[i] == 2; m.mbInKF = state[i] == 3;
+        if (state[i]) ptrs[i] = &m;
+        bestIdx[i] = -1;
+    }
+    g_fuseLog.clear();
+    ORBmatcher matcher(0.6f, true);
+    const int nFused = matcher.Fuse(&kf, ptrs, th, false);
+    for (const auto& e : g_fuseLog)
+        if (e.first >= 0) bestIdx[e.first] = e.second;
+        else if (kfHasPoint[e.second] != 2) return -1000 - e.second;           // only a bad resident point leaves no trace
+    return nFused;
 }
 
 }  // extern "C"

@@ -574,6 +574,64 @@ int ORBmatcherAccel::SearchByProjectionKeyFrame(const std::vector<cv::KeyPoint>&
     return nmatches;
 }
 
+int ORBmatcherAccel::FuseSearch(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK, const FrameGridAccel& gridK,
+                                const std::vector<float>& scaleFactors, const std::vector<float>& invLevelSigma2,
+                                const std::vector<float>& uRight, const std::vector<uint8_t>& valid,
+                                const std::vector<cv::Point2f>& uv, const std::vector<float>& ur,
+                                const std::vector<float>& dist3D, const std::vector<float>& minDistance,
+                                const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel,
+                                const cv::Mat& descMP, float th, std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+    const int nMPs = (int)uv.size();
+    bestIdx.assign(nMPs, -1);
+    bestDist.assign(nMPs, 256);
+    std::vector<int> query;
+    std::vector<int32_t> off(1, 0), idx;
+    std::vector<uint8_t> Q;
+    for (int i = 0; i < nMPs; i++) {
+        if (!valid[i]) continue;
+        const float u = uv[i].x, v = uv[i].y;
+        if (!(u >= gridK.mnMinX && u < gridK.mnMaxX && v >= gridK.mnMinY && v < gridK.mnMaxY)) continue;    // KeyFrame::IsInImage
+        if (dist3D[i] < minDistance[i] || dist3D[i] > maxDistance[i]) continue;
+        const int nPredictedLevel = predictedLevel[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        const std::vector<size_t> vIndices = gridK.GetFeaturesInArea(u, v, radius);
+        if (vIndices.empty()) continue;
+        // the gates that precede DescriptorDistance (:1107-1141) thin the list out; the kernel scans what is left
+        for (size_t j : vIndices) {
+            const cv::KeyPoint& kp = keysK[j];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (uRight[j] >= 0) {
+                const float ex = u - kp.pt.x, ey = v - kp.pt.y, er = ur[i] - uRight[j];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = u - kp.pt.x, ey = v - kp.pt.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            }
+            idx.push_back((int32_t)j);
+        }
+        query.push_back(i);
+        off.push_back((int32_t)idx.size());
+        Q.insert(Q.end(), descMP.ptr(i), descMP.ptr(i) + 32);
+    }
+    const int nq = (int)query.size();
+    if (nq == 0) return 0;
+    std::vector<uint16_t> dist(idx.size() + 1), d1(nq), d2(nq);
+    std::vector<int32_t> i1(nq), i2(nq);
+    const std::vector<uint8_t> T = rows32(descK);
+    if (rumi_hamming_candidates(ctx, Q.data(), nq, T.data(), descK.rows, off.data(), idx.data(), dist.data(), i1.data(), d1.data(),
+                                i2.data(), d2.data()) != RUMI_OK)
+        throw std::runtime_error(std::string("ORBmatcherAccel: ") + rumi_last_error());
+    int nFused = 0;
+    for (int q = 0; q < nq; ++q) {
+        bestDist[query[q]] = d1[q];
+        if (d1[q] <= TH_LOW) { bestIdx[query[q]] = i1[q]; nFused++; }
+    }
+    return nFused;
+}
+
 int ORBmatcherAccel::AssociateSubmap(struct rumi_orb* extractor, const std::vector<cv::Mat>& images1,
                                      const std::vector<std::vector<cv::KeyPoint>>& keys1,
                                      const std::vector<std::vector<uint8_t>>& valid1, const std::vector<cv::Mat>& images2,

@@ -143,6 +143,20 @@ public:
                                    const std::vector<float>& angleKF, const cv::Mat& descMP, float th, int ORBdist,
                                    bool checkOrientation, std::vector<int>& curMatch);
 
+    // ORBmatcher::Fuse(KeyFrame* pKF, vpMapPoints, th, bRight = false) (R/lib_src/ORBmatcher.cc:1015-1181), the matcher of
+    // LocalMapping::SearchInNeighbors, up to the fuse decision (:1147).  Per map point i: valid[i] = present, not bad, not
+    // already in pKF, depth >= 0, viewing-angle test passed (:1045-1100, the caller's pose / camera / normal); uv[i] =
+    // projection into pKF, ur[i] = uv.x - bf * invz (:1074); dist3D[i] against [minDistance, maxDistance];
+    // predictedLevel[i] = PredictScale.  Key frame: mvKeysUn, mDescriptors, its grid, mvScaleFactors, mvInvLevelSigma2,
+    // mvuRight (< 0: mono feature).  bestIdx[i] = key-frame feature to fuse with (bestDist <= TH_LOW) or -1; the caller
+    // runs its own Replace / AddObservation / AddMapPoint loop (:1148-1160) on it.  Returns nFused.
+    int FuseSearch(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK, const FrameGridAccel& gridK,
+                   const std::vector<float>& scaleFactors, const std::vector<float>& invLevelSigma2,
+                   const std::vector<float>& uRight, const std::vector<uint8_t>& valid, const std::vector<cv::Point2f>& uv,
+                   const std::vector<float>& ur, const std::vector<float>& dist3D, const std::vector<float>& minDistance,
+                   const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel, const cv::Mat& descMP,
+                   float th, std::vector<int>& bestIdx, std::vector<int>& bestDist);
+
     // Descriptor-based key-point association of the matched key-frame pairs of a submap merge (the pairs
     // R/lib_src/CloudMerging.cc:503-551 associates by pixel distance): real descriptors for the cloud
     // key frames (ORBextractor::CloudFrameComputeDescriptors, one batched call per side -- they carry zero descriptors in

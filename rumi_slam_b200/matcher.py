@@ -411,6 +411,48 @@ class ORBmatcher:
                         nmatches -= 1
         return nmatches, cm
 
+    # ---- ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = false) (ORBmatcher.cc:1015-1181): the matching core ----
+    def FuseSearch(self, keysK, descK, scale_factors, inv_level_sigma2, bounds, u_right, valid, uv, ur, dist3d, min_dist,
+                   max_dist, level, descMP, th=3.0):
+        """The matcher of LocalMapping::SearchInNeighbors up to the fuse decision (:1147).  Per map point i: valid[i] =
+        present, not bad, not already in pKF, depth >= 0, viewing-angle test passed; uv[i] = projection into pKF, ur[i] =
+        uv.x - bf * invz; dist3d[i] against [min_dist, max_dist]; level[i] = PredictScale.  Key frame: mvKeysUn, mDescriptors,
+        mvuRight (< 0: mono feature), mvInvLevelSigma2, grid bounds.  Returns (nFused, best_idx[i] = key-frame feature or -1,
+        best_dist[i]); the caller then runs its own Replace / AddObservation loop (:1148-1160) -- map edits that do not feed
+        back into the search.  The level window and the chi-square gates (5.99 mono / 7.8 stereo) filter the candidate
+        lists on the host; all descriptor distances and the per-list best run in one launch."""
+        f32 = np.float32
+        kK = np.ascontiguousarray(keysK, KP_DTYPE)
+        sf, inv_s2 = np.asarray(scale_factors, f32), np.asarray(inv_level_sigma2, f32)
+        uv = np.asarray(uv, f32).reshape(-1, 2)
+        ur, d3 = np.asarray(ur, f32), np.asarray(dist3d, f32)
+        level = np.asarray(level, np.int32)
+        u_right = np.asarray(u_right, f32)
+        n = len(uv)
+        ok = np.asarray(valid, bool) & (uv[:, 0] >= f32(bounds[0])) & (uv[:, 0] < f32(bounds[2])) & (uv[:, 1] >= f32(bounds[1])) \
+            & (uv[:, 1] < f32(bounds[3])) & ~(d3 < np.asarray(min_dist, f32)) & ~(d3 > np.asarray(max_dist, f32))
+        q = np.flatnonzero(ok)
+        off, idx = FrameGrid(kK, bounds).candidate_lists(uv[q], (f32(th) * sf[level[q]]).astype(f32))
+        # gates of :1107-1141 on every (map point, candidate) pair, vectorised
+        owner = np.repeat(np.arange(len(q)), np.diff(off))
+        i = q[owner]
+        kp = kK[idx]
+        lv = kp["octave"]
+        ex, ey = uv[i, 0] - kp["x"], uv[i, 1] - kp["y"]
+        er = ur[i] - u_right[idx]
+        stereo = u_right[idx] >= 0
+        e2 = np.where(stereo, ((ex * ex + ey * ey).astype(f32) + er * er).astype(f32), (ex * ex + ey * ey).astype(f32))
+        gate = (e2 * inv_s2[lv]).astype(f32) > np.where(stereo, 7.8, 5.99)          # float * float -> float, compared with a double
+        keep = (lv >= level[i] - 1) & (lv <= level[i]) & ~gate
+        off2 = np.zeros(len(q) + 1, np.int32)
+        off2[1:] = np.cumsum(np.bincount(owner[keep], minlength=len(q)))
+        _, (i1, d1, _, _) = self.candidates(np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)[q], descK, off2, idx[keep], top2=True)
+        best_idx, best_dist = np.full(n, -1, np.int32), np.full(n, 256, np.int32)
+        best_dist[q] = d1
+        fused = d1 <= self.TH_LOW
+        best_idx[q[fused]] = i1[fused]
+        return int(fused.sum()), best_idx, best_dist
+
     # ---- descriptor-based key-point association of matched key-frame pairs (submap merge, SURVEY.md 8f rank 3) ----
     def AssociateSubmap(self, extractor, images1, keys1, valid1, images2, keys2, valid2, th=None):
         """For every matched key-frame pair p (the pairs CloudMerging.cc:503-551 walks): real descriptors for the cloud key

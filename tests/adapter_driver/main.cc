@@ -6,6 +6,7 @@
 // nL floats mvuRight, nL floats mvDepth (Frame::ComputeStereoMatches through ORBmatcherAccel), int32 nmatches + nL int32
 // vnMatches12 of SearchForInitialization(left, right, window 100), int32 total, int32 n1, n1 int32 of AssociateSubmap.
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <stdexcept>
 #include <thread>
@@ -117,6 +118,27 @@ int main(int argc, char** argv) {
             std::fwrite(&nl, 4, 1, f); std::fwrite(&nk, 4, 1, f); std::fwrite(&nR, 4, 1, f);
             std::fwrite(cmLast.data(), 4, cmLast.size(), f);
             std::fwrite(cmKF.data(), 4, cmKF.size(), f);
+            // the matching core of Fuse: key frame = right image (mono features); map point i sits half a pixel off the key
+            // point (7 i) mod nR and carries that key point's descriptor and level
+            std::vector<float> invS2(sf.size()), uRnone(nR, -1.0f), urMP(nR), d3F(nR), dminF(nR, 0.0f), dmaxF(nR, 1e9f);
+            for (size_t l = 0; l < sf.size(); ++l) invS2[l] = 1.0f / (sf[l] * sf[l]);
+            std::vector<cv::Point2f> uvF(nR);
+            std::vector<int> lvF(nR);
+            std::vector<uint8_t> validF(nR);
+            cv::Mat descF(nR, 32, CV_8U);
+            for (int i = 0; i < nR; ++i) {
+                const int j = (int)(((long long)i * 7) % nR);
+                uvF[i] = cv::Point2f(R.keys[j].pt.x + 0.5f, R.keys[j].pt.y - 0.5f);
+                lvF[i] = R.keys[j].octave; validF[i] = i % 9 != 0; d3F[i] = 1.0f + (float)(i % 13);
+                urMP[i] = uvF[i].x - 40.0f / d3F[i];
+                std::memcpy(descF.ptr(i), R.desc.ptr(j), 32);
+            }
+            std::vector<int> fIdx, fDist;
+            const int nf = mi.FuseSearch(R.keys, R.desc, grid, sf, invS2, uRnone, validF, uvF, urMP, d3F, dminF, dmaxF, lvF, descF,
+                                         3.0f, fIdx, fDist);
+            std::fwrite(&nf, 4, 1, f);
+            std::fwrite(fIdx.data(), 4, fIdx.size(), f);
+            std::fwrite(fDist.data(), 4, fDist.size(), f);
         }
         // the empty-image contract of operator() (ORBextractor.cc:1017)
         cv::Mat empty; Result E;

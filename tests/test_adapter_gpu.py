@@ -112,3 +112,16 @@ def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
                                           np.full(len(lk), 12.0, np.float32), lk["octave"], lk["angle"], ld, 10.0, 100, None, True)
     assert nR == len(rk) and nl == rn1 and np.array_equal(cm_last, rcm1) and rn1 > 50
     assert nk == rn2 and np.array_equal(cm_kf, rcm2) and rn2 > 30
+    # ORBmatcherAccel::FuseSearch, executed in C++: map point i = key point (7 i) mod nR of the key frame, half a pixel off
+    nf = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    f_idx = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    f_dist = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    inv_s2 = (np.float32(1.0) / (sf * sf).astype(np.float32)).astype(np.float32)
+    ii = np.arange(nR)
+    j = (ii * 7) % nR
+    uv_f = np.stack([rk["x"][j] + np.float32(0.5), rk["y"][j] - np.float32(0.5)], 1).astype(np.float32)
+    d3_f = (1.0 + (ii % 13)).astype(np.float32)
+    ur_f = (uv_f[:, 0] - (np.float32(40.0) / d3_f).astype(np.float32)).astype(np.float32)
+    rn3, rbest, rdist = M.fuse_search(rk, rd, sf, inv_s2, (0, 0, 752, 480), np.full(nR, -1.0, np.float32), ii % 9 != 0, uv_f, ur_f,
+                                      d3_f, np.zeros(nR, np.float32), np.full(nR, 1e9, np.float32), rk["octave"][j], rd[j], 3.0)
+    assert nf == rn3 and np.array_equal(f_idx, rbest) and np.array_equal(f_dist, rdist) and rn3 > 300

@@ -121,6 +121,35 @@ def test_search_by_projection_keyframe_matches_oracle(oracle, M, seed, th, orb_d
     assert rn > 30
 
 
+@pytest.mark.parametrize("seed,th,stereo", [(31, 3.0, False), (32, 3.0, True), (33, 5.0, True)])
+def test_fuse_search_matches_oracle(oracle, M, seed, th, stereo):
+    """Matching core of ORBmatcher::Fuse(pKF, vpMapPoints, th) (R/lib_src/ORBmatcher.cc:1015-1147); the oracle side is pinned to
+    the reference function in tests/test_ref_frame_pin.py::test_fuse_search_equals_reference (same construction)."""
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed + 200)
+    n1, n2 = len(k1), len(k2)
+    f32 = np.float32
+    uv = (np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(f32) + rng.normal(0, 0.8, (n1, 2)).astype(f32))
+    uv[rng.random(n1) < 0.03] += f32(700.0)
+    z = rng.uniform(0.5, 20.0, n1).astype(f32)
+    tab = oracle.tables()
+    sf, inv_sigma2 = tab["scale"], (1.0 / (tab["scale"].astype(np.float64) ** 2)).astype(f32)
+    valid = rng.random(n1) < 0.8
+    level = np.clip(k1["octave"] + rng.integers(0, 2, n1), 0, 7).astype(np.int32)
+    bf = 40.0
+    u_right = (np.where(rng.random(n2) < 0.6, k2["x"] - bf / rng.uniform(2.0, 20.0, n2), -1.0) if stereo else np.full(n2, -1.0)).astype(f32)
+    dist3d = np.sqrt(((uv[:, 0] * uv[:, 0] + uv[:, 1] * uv[:, 1]).astype(f32) + z * z).astype(f32)).astype(f32)
+    ur = (uv[:, 0] - (f32(bf) * (f32(1.0) / z).astype(f32)).astype(f32)).astype(f32)
+    min_d = (dist3d * rng.choice([0.5, 0.9, 1.01], n1)).astype(f32)
+    max_d = (dist3d * rng.choice([0.99, 1.1, 2.0], n1)).astype(f32)
+    args = (k2, d2, sf, inv_sigma2, (0, 0, 640, 480), u_right, valid, uv, ur, dist3d, min_d, max_d, level, d1, th)
+    n, best, bdist = ORBmatcher().FuseSearch(*args)
+    rn, rbest, rdist = M.fuse_search(*args)
+    assert n == rn and np.array_equal(best, rbest) and np.array_equal(bdist, rdist)
+    assert rn > 40
+
+
 @pytest.mark.parametrize("seed,th,ratio", [(6, 3.0, 0.8), (7, 1.0, 0.8), (8, 5.0, 0.9), (9, 15.0, 0.6)])
 def test_search_by_projection_matches_oracle(oracle, M, seed, th, ratio):
     from rumi_slam_b200 import ORBmatcher

@@ -245,3 +245,41 @@ def test_search_by_projection_keyframe_equals_reference(oracle, rf, M, seed, th,
                                       th, orb_dist, occupied, check_ori)
     assert n == rn and np.array_equal(cm, rcm)
     assert rn > 30
+
+
+@pytest.mark.parametrize("seed,th,stereo", [(31, 3.0, False), (32, 3.0, True), (33, 5.0, True), (34, 2.0, False), (35, 4.0, True)])
+def test_fuse_search_equals_reference(oracle, rf, M, seed, th, stereo):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (R/lib_src/ORBmatcher.cc:1015-1181) up to the fuse decision: which key-frame
+    feature each map point meets -- null / bad / already-observed / behind-camera / outside-image / out-of-range / oblique
+    points, the level window, the chi-square reprojection gates (mono 5.99, stereo 7.8), TH_LOW."""
+    k1, d1, k2, d2, uv, depth, _, _, _, _ = _last_frame_case(oracle, seed, False)
+    rng = np.random.default_rng(seed + 200)
+    n1, n2 = len(k1), len(k2)
+    f32 = np.float32
+    uv = (np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(f32) + rng.normal(0, 0.8, (n1, 2)).astype(f32))
+    uv[rng.random(n1) < 0.03] += f32(700.0)
+    tab = oracle.tables()
+    sf, inv_sigma2 = tab["scale"], (1.0 / (tab["scale"].astype(np.float64) ** 2)).astype(f32)
+    state = rng.choice([0, 1, 1, 1, 1, 1, 1, 2, 3, 4], n1).astype(np.uint8)
+    level = np.clip(k1["octave"] + rng.integers(0, 2, n1), 0, 7).astype(np.int32)
+    bf = 40.0
+    u_right = (np.where(rng.random(n2) < 0.6, k2["x"] - bf / rng.uniform(2.0, 20.0, n2), -1.0) if stereo
+               else np.full(n2, -1.0)).astype(f32)
+    kf_has = rng.choice([0, 0, 0, 1, 2], n2).astype(np.uint8)
+    n_obs = rng.integers(1, 10, n1).astype(np.int32)
+    # what the reference computes from the stand-in world point (uv, depth) with Ow = 0: float32, operation by operation
+    x, y, z = uv[:, 0], uv[:, 1], depth
+    dist3d = np.sqrt(((x * x + y * y).astype(f32) + z * z).astype(f32)).astype(f32)
+    invz = (f32(1.0) / z).astype(f32)
+    ur = (x - (f32(bf) * invz).astype(f32)).astype(f32)
+    min_d = (dist3d * rng.choice([0.5, 0.9, 1.01], n1)).astype(f32)
+    max_d = (dist3d * rng.choice([0.99, 1.1, 2.0], n1)).astype(f32)
+    rn, rbest = rf.fuse(k2, d2, sf, inv_sigma2, (0, 0, 640, 480), u_right, kf_has, bf, state, uv, depth, min_d, max_d, level, d1,
+                        n_obs, th)
+    valid = (state == 1) & ~(z < 0)
+    n, best, bdist = M.fuse_search(k2, d2, sf, inv_sigma2, (0, 0, 640, 480), u_right, valid, uv, ur, dist3d, min_d, max_d, level,
+                                   d1, th)
+    assert rn >= 0 and n == rn
+    traced = (best < 0) | (kf_has[np.maximum(best, 0)] != 2)         # a bad resident point leaves no trace in the reference run
+    assert np.array_equal(best[traced], rbest[traced]) and np.all(rbest[~traced] == -1)
+    assert rn > 40 and (best >= 0).sum() == rn

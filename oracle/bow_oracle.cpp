@@ -6,11 +6,12 @@
 //     :1218-1258 (per feature) and :1128-1200 (BowVector / FeatureVector assembly = Frame::ComputeBoW),
 //     tree built like loadFromTextFile (:1338-1421), distance = FORB::distance (FORB.cpp:81-101);
 //   * ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) -- R/lib_src/ORBmatcher.cc:198-370, the Nleft == -1 branch, and
-//     SearchByBoW(KeyFrame*, KeyFrame*, ...) -- :682-804, with ComputeThreeMaxima (:1795-1828).
+//     SearchByBoW(KeyFrame*, KeyFrame*, ...) -- :682-804, with ComputeThreeMaxima (:1795-1828);
+//   * ORBmatcher::SearchForTriangulation -- :806-1013, key frames without a second camera.
 // Parity: PINNED.  The tree descent and the vector assembly are checked against the UNMODIFIED reference DBoW2
 // compiled over oracle/cvstub (oracle/_ref/librefbow.so, tests/test_bow_oracle.py) and against the frozen vectors
-// tests/golden/bow_kats.npz.  SearchByBoW needs KeyFrame / Frame / MapPoint (not compilable here): restated from the
-// cited lines and checked on hand-built known answers.
+// tests/golden/bow_kats.npz.  SearchByBoW (both overloads) and SearchForTriangulation are checked against the reference's
+// own functions compiled over class stand-ins (oracle/_ref/librefframe.so, tests/test_ref_frame_pin.py).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -300,6 +301,77 @@ int bow_oracle_distinctive(const uint8_t* desc, int N, int* median) {
     }
     *median = BestMedian;
     return BestIdx;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), R/lib_src/ORBmatcher.cc:806-1013, the
+// matcher of LocalMapping::CreateNewMapPoints, for key frames without a second fisheye camera (mpCamera2 == NULL).
+// has_mp*[i]: the feature already has a map point (:862-867, :889-893); stereo*[i]: mvuRight[i] >= 0; (x2, y2, octave2) of
+// the key points of key frame 2; (epx, epy) = the epipole in image 2 (:815-819, the caller's poses and camera);
+// epi_ok[i1 * n2 + i2] = what pCamera1->epipolarConstrain(...) returns for the pair (:957; evaluated by the reference only
+// for pairs that survive the distance tests -- it is a pure function of the pair, so a table is equivalent).
+// match12[i1] = feature of key frame 2 or -1.  (vbMatched2 is never set by the reference, :852 / :890: kept that way.)
+int bow_oracle_search_for_triangulation(const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, const uint8_t* stereo1,
+                                        int n1, const int32_t* nodes1, const int32_t* off1, const int32_t* idx1, int nnodes1,
+                                        const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2, const uint8_t* stereo2,
+                                        const float* x2, const float* y2, const int32_t* octave2, int n2, const int32_t* nodes2,
+                                        const int32_t* off2, const int32_t* idx2, int nnodes2, const float* scale_factors2,
+                                        float epx, float epy, int only_stereo, int coarse, const uint8_t* epi_ok, int check_ori,
+                                        int32_t* match12) {
+    const int HISTO_LENGTH = 30, TH_LOW = 50;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nnodes1 && b < nnodes2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = off1[a]; i1 < off1[a + 1]; ++i1) {
+                const int id1 = idx1[i1];
+                if (has_mp1[id1]) continue;
+                const bool bStereo1 = stereo1[id1] != 0;
+                if (only_stereo && !bStereo1) continue;
+                const uint8_t* d1 = desc1 + 32 * (size_t)id1;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = off2[b]; i2 < off2[b + 1]; ++i2) {
+                    const int id2 = idx2[i2];
+                    if (has_mp2[id2]) continue;
+                    const bool bStereo2 = stereo2[id2] != 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = forb_distance(d1, desc2 + 32 * (size_t)id2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = epx - x2[id2], distey = epy - y2[id2];
+                        if (distex * distex + distey * distey < 100 * scale_factors2[octave2[id2]]) continue;
+                    }
+                    if (coarse || epi_ok[(size_t)id1 * n2 + id2]) { bestIdx2 = id2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[id1] = bestIdx2;
+                    nmatches++;
+                    if (check_ori) {
+                        float rot = angle1[id1] - angle2[bestIdx2];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(id1);
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            ++a;                                   // lower_bound on a sorted map = advance to the first id >= the other's
+        } else {
+            ++b;
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int id1 : rotHist[i]) { match12[id1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
 }
 
 }  // extern "C"

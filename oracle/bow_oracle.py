@@ -175,3 +175,29 @@ def search_by_bow_kf(desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, nnr
                                           _p(n2, _i32p), _p(o2, _i32p), _p(i2, _i32p), len(n2), nnratio,
                                           1 if check_ori else 0, th_low, _p(match, _i32p))
     return n, match[:len(d1)]
+
+
+def search_for_triangulation(desc1, angle1, has_mp1, stereo1, fv1, desc2, angle2, has_mp2, stereo2, x2, y2, octave2, fv2,
+                             scale_factors2, ep, epi_ok, only_stereo=False, coarse=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:806-1013, no second camera): (nmatches, match12).  epi_ok: [n1, n2]
+    table of what epipolarConstrain returns for a pair."""
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    d1, d2 = u8(desc1).reshape(-1, 32), u8(desc2).reshape(-1, 32)
+    n1, o1, i1 = flatten_fv(fv1)
+    n2, o2, i2 = flatten_fv(fv2)
+    i1 = np.ascontiguousarray(np.append(i1, 0), np.int32)
+    i2 = np.ascontiguousarray(np.append(i2, 0), np.int32)
+    match = np.zeros(max(len(d1), 1), np.int32)
+    L = lib()
+    L.bow_oracle_search_for_triangulation.restype = C.c_int
+    L.bow_oracle_search_for_triangulation.argtypes = [_u8p, _f32p, _u8p, _u8p, C.c_int, _i32p, _i32p, _i32p, C.c_int, _u8p, _f32p,
+                                                      _u8p, _u8p, _f32p, _f32p, _i32p, C.c_int, _i32p, _i32p, _i32p, C.c_int,
+                                                      _f32p, C.c_float, C.c_float, C.c_int, C.c_int, _u8p, C.c_int, _i32p]
+    n = L.bow_oracle_search_for_triangulation(
+        _p(d1, _u8p), _p(f32(angle1), _f32p), _p(u8(has_mp1), _u8p), _p(u8(stereo1), _u8p), len(d1), _p(n1, _i32p), _p(o1, _i32p),
+        _p(i1, _i32p), len(n1), _p(d2, _u8p), _p(f32(angle2), _f32p), _p(u8(has_mp2), _u8p), _p(u8(stereo2), _u8p),
+        _p(f32(x2), _f32p), _p(f32(y2), _f32p), _p(np.ascontiguousarray(octave2, np.int32), _i32p), len(d2), _p(n2, _i32p),
+        _p(o2, _i32p), _p(i2, _i32p), len(n2), _p(f32(scale_factors2), _f32p), float(ep[0]), float(ep[1]), int(only_stereo),
+        int(coarse), _p(u8(epi_ok), _u8p), int(check_ori), _p(match, _i32p))
+    return n, match[:len(d1)]

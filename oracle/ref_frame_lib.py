@@ -238,3 +238,25 @@ def fuse(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, kf_has_point,
                     _p(f32(uv), _f32p), _p(f32(depth), _f32p), _p(f32(min_dist), _f32p), _p(f32(max_dist), _f32p),
                     _p(i32(level), _i32p), _p(dMP, _u8p), _p(i32(n_obs), _i32p), n, float(th), _p(out, _i32p))
     return nf, out[:n]
+
+
+def search_for_triangulation(k1, d1, has_mp1, u_right1, fv1, k2, d2, has_mp2, u_right2, fv2, scale_factors2, ep, epi_ok,
+                             only_stereo=False, coarse=False, check_ori=True):
+    """The reference's ORBmatcher::SearchForTriangulation over stand-in poses / camera (epipole = ep, epipolarConstrain = the
+    table epi_ok[n1, n2]): (nmatches, match12)."""
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    d1, d2 = u8(d1).reshape(-1, 32), u8(d2).reshape(-1, 32)
+    sf = f32(scale_factors2)
+    n1, n2 = _nodes(fv1, len(d1)), _nodes(fv2, len(d2))
+    match = np.zeros(max(len(d1), 1), np.int32)
+    L = lib()
+    L.ref_search_for_triangulation.argtypes = [C.c_void_p, _u8p, _u8p, _f32p, _i32p, C.c_int, C.c_void_p, _u8p, _u8p, _f32p, _i32p,
+                                               C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, _u8p, C.c_float,
+                                               C.c_int, _i32p]
+    n = L.ref_search_for_triangulation(k1.ctypes.data, _p(d1, _u8p), _p(u8(has_mp1), _u8p), _p(f32(u_right1), _f32p), _p(n1, _i32p),
+                                       len(d1), k2.ctypes.data, _p(d2, _u8p), _p(u8(has_mp2), _u8p), _p(f32(u_right2), _f32p),
+                                       _p(n2, _i32p), len(d2), _p(sf, _f32p), len(sf), float(ep[0]), float(ep[1]), int(only_stereo),
+                                       int(coarse), _p(u8(epi_ok), _u8p), 0.6, int(check_ori), _p(match, _i32p))
+    return n, match[:len(d1)]

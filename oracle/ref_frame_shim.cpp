@@ -12,6 +12,7 @@
 //   ORBmatcher::SearchByProjection (Frame, MapPoints) / SearchForInitialization   R/lib_src/ORBmatcher.cc:39-189, 581-680
 //   ORBmatcher::SearchByProjection (CurrentFrame, LastFrame) / (CurrentFrame, KeyFrame, sAlreadyFound)   :1498-1684, 1685-1794
 //   ORBmatcher::Fuse (KeyFrame, MapPoints) + KeyFrame::GetFeaturesInArea / IsInImage   ORBmatcher.cc:1015-1181, KeyFrame.cc:887-930
+//   ORBmatcher::SearchForTriangulation   ORBmatcher.cc:806-1013 (epipolarConstrain = a table look-up stand-in)
 //     (these take poses and a camera model: Sophus::SE3f / Eigen::Vector3f / GeometricCamera are minimal stand-ins
 //      below -- identity rotation, so that "Tcw * x3Dw" is exact -- and the pin covers everything AFTER the projection,
 //      which is what the flattened adapters take over; the projection itself stays with the caller's own Sophus / camera)
@@ -53,6 +54,7 @@ struct Vector3f {
     float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
     float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
 };
+struct Matrix3f { float m[9]; };
 }  // namespace Eigen
 namespace Sophus {
 struct SE3f {                                   // translation only (rotation = identity): R v + t is exact
@@ -60,6 +62,8 @@ struct SE3f {                                   // translation only (rotation = 
     SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t.v[0], -t.v[1], -t.v[2]); return r; }
     Eigen::Vector3f translation() const { return t; }
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return Eigen::Vector3f(p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]); }
+    SE3f operator*(const SE3f& o) const { SE3f r; r.t = Eigen::Vector3f(t.v[0] + o.t.v[0], t.v[1] + o.t.v[1], t.v[2] + o.t.v[2]); return r; }
+    Eigen::Matrix3f rotationMatrix() const { Eigen::Matrix3f r = {{1, 0, 0, 0, 1, 0, 0, 0, 1}}; return r; }
 };
 }  // namespace Sophus
 
@@ -73,7 +77,16 @@ class GeometricCamera {
 public:
     // stand-in camera model: (x, y, z) -> (x, y); the tests put the wanted pixel position into x, y and the depth into z
     Eigen::Vector2f project(const Eigen::Vector3f& p) const { Eigen::Vector2f r; r.v[0] = p(0); r.v[1] = p(1); return r; }
+    // stand-in for the camera model's epipolar test: a table indexed by the feature numbers the test stores in class_id
+    static const uint8_t* epiTable;
+    static int epiCols;
+    bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f&,
+                           const Eigen::Vector3f&, const float, const float) {
+        return epiTable[(size_t)kp1.class_id * epiCols + kp2.class_id] != 0;
+    }
 };
+const uint8_t* GeometricCamera::epiTable = nullptr;
+int GeometricCamera::epiCols = 0;
 class Frame;
 class KeyFrame;
 
@@ -128,6 +141,9 @@ public:
     Sophus::SE3f mTcw;
     Sophus::SE3f GetPose() { return mTcw; }
     Sophus::SE3f GetRightPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
+    Sophus::SE3f GetRightPoseInverse() { return mTcw.inverse(); }
+    std::vector<float> mvLevelSigma2;
     Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
     Eigen::Vector3f GetRightCameraCenter() { return GetCameraCenter(); }
     // grid (R/include/cloud_edge_slam_lib/KeyFrame.h:341-344, 425-428; copied from the Frame in the KeyFrame constructor)
@@ -185,6 +201,8 @@ public:
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
                            const int ORBdist);
     int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<pair<size_t, size_t>>& vMatchedPairs,
+                               const bool bOnlyStereo, const bool bCoarse = false);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -522,6 +540,41 @@ int ref_fuse(const void* kK, const uint8_t* dK, int nK, const float* scaleFactor
         if (e.first >= 0) bestIdx[e.first] = e.second;
         else if (kfHasPoint[e.second] != 2) return -1000 - e.second;           // only a bad resident point leaves no trace
     return nFused;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:806-1013), key frames
+// without a second camera.  node*[i] = vocabulary node of feature i (-1: not in the feature vector); hasMP*[i]; uRight*[i];
+// the epipole (epx, epy) is produced through the stand-in poses (T1w = identity, T2w = translation (epx, epy, 1), camera
+// (x, y, z) -> (x, y)); epiOk[i1 * n2 + i2] = result of epipolarConstrain for the pair.  match12[i1] = i2 or -1.
+int ref_search_for_triangulation(const void* k1, const uint8_t* d1, const uint8_t* hasMP1, const float* uRight1, const int32_t* node1,
+                                 int n1, const void* k2, const uint8_t* d2, const uint8_t* hasMP2, const float* uRight2,
+                                 const int32_t* node2, int n2, const float* scaleFactors2, int nlevels, float epx, float epy,
+                                 int onlyStereo, int coarse, const uint8_t* epiOk, float ratio, int checkOri, int32_t* match12) {
+    GeometricCamera cam;
+    GeometricCamera::epiTable = epiOk; GeometricCamera::epiCols = n2;
+    MapPoint some;
+    KeyFrame kf1, kf2;
+    auto fill = [&](KeyFrame& kf, const void* k, const uint8_t* d, const uint8_t* hasMP, const float* uRight, const int32_t* node, int n) {
+        kf.N = n; kf.mvKeysUn = keys(k, n);
+        for (int i = 0; i < n; ++i) kf.mvKeysUn[i].class_id = i;
+        kf.mvKeys = kf.mvKeysUn; kf.mDescriptors = rows32(d, n);
+        kf.mvuRight.assign(uRight, uRight + n);
+        kf.mvpMapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; ++i) if (hasMP[i]) kf.mvpMapPoints[i] = &some;
+        fill_featvec(kf.mFeatVec, node, n);
+        kf.mpCamera = &cam;
+        kf.mvScaleFactors.assign(scaleFactors2, scaleFactors2 + nlevels);
+        kf.mvLevelSigma2.assign(nlevels, 1.0f);
+    };
+    fill(kf1, k1, d1, hasMP1, uRight1, node1, n1);
+    fill(kf2, k2, d2, hasMP2, uRight2, node2, n2);
+    kf2.mTcw.t = Eigen::Vector3f(epx, epy, 1.0f);              // C2 = T2w * Cw = (0,0,0) + t2 -> ep = (epx, epy)
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher m(ratio, checkOri != 0);
+    const int n = m.SearchForTriangulation(&kf1, &kf2, pairs, onlyStereo != 0, coarse != 0);
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (const auto& p : pairs) match12[p.first] = (int)p.second;
+    return n;
 }
 
 }  // extern "C"

@@ -220,6 +220,75 @@ int ORBmatcherAccel::SearchByBoWKF(const cv::Mat& desc1, const std::vector<float
     return nmatches;
 }
 
+int ORBmatcherAccel::SearchForTriangulation(const cv::Mat& desc1, const std::vector<float>& angle1,
+                                            const std::vector<uint8_t>& hasMapPoint1, const std::vector<uint8_t>& stereo1,
+                                            const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec1,
+                                            const cv::Mat& desc2, const std::vector<float>& angle2,
+                                            const std::vector<uint8_t>& hasMapPoint2, const std::vector<uint8_t>& stereo2,
+                                            const std::vector<cv::KeyPoint>& keys2,
+                                            const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec2,
+                                            const std::vector<float>& scaleFactors2, cv::Point2f ep,
+                                            const std::function<bool(size_t, size_t)>& epipolarOk, bool bOnlyStereo, bool bCoarse,
+                                            bool checkOrientation, std::vector<std::pair<size_t, size_t> >& vMatchedPairs) {
+    vMatchedPairs.clear();
+    std::vector<int> vMatches12(desc1.rows, -1);
+    std::vector<int32_t> aIdx, bIdx, segs;
+    std::vector<uint16_t> dist;
+    if (NodeBlocks(desc1, featVec1, desc2, featVec2, aIdx, bIdx, segs, dist) == 0) return 0;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (size_t s = 0; s < segs.size(); s += 5) {
+        const int a0 = segs[s], ac = segs[s + 1], b0 = segs[s + 2], bc = segs[s + 3];
+        const uint16_t* block = dist.data() + segs[s + 4];
+        for (int i1 = 0; i1 < ac; i1++) {
+            const size_t idx1 = aIdx[a0 + i1];
+            if (hasMapPoint1[idx1]) continue;                                     // :862-867
+            const bool bStereo1 = stereo1[idx1] != 0;
+            if (bOnlyStereo && !bStereo1) continue;
+            int bestDist = TH_LOW, bestIdx2 = -1;
+            for (int i2 = 0; i2 < bc; i2++) {
+                const size_t idx2 = bIdx[b0 + i2];
+                if (hasMapPoint2[idx2]) continue;                                 // :889-893 (vbMatched2 is never set there)
+                const bool bStereo2 = stereo2[idx2] != 0;
+                if (bOnlyStereo && !bStereo2) continue;
+                const int d = block[(size_t)i1 * bc + i2];
+                if (d > TH_LOW || d > bestDist) continue;
+                const cv::KeyPoint& kp2 = keys2[idx2];
+                if (!bStereo1 && !bStereo2) {                                     // too close to the epipole (:910-916)
+                    const float distex = ep.x - kp2.pt.x, distey = ep.y - kp2.pt.y;
+                    if (distex * distex + distey * distey < 100 * scaleFactors2[kp2.octave]) continue;
+                }
+                if (bCoarse || epipolarOk(idx1, idx2)) { bestIdx2 = (int)idx2; bestDist = d; }
+            }
+            if (bestIdx2 >= 0) {
+                vMatches12[idx1] = bestIdx2;
+                nmatches++;
+                if (checkOrientation) {
+                    float rot = angle1[idx1] - angle2[bestIdx2];
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)std::round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back((int)idx1);
+                }
+            }
+        }
+    }
+    if (checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) { vMatches12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0, iend = vMatches12.size(); i < iend; i++)
+        if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
+    return nmatches;
+}
+
 int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>& angleKF,
                                  const std::vector<uint8_t>& kfValid,
                                  const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF,

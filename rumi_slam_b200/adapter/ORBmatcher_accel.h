@@ -8,6 +8,7 @@
 #define ORBMATCHER_ACCEL_H
 
 #include <cstdint>
+#include <functional>
 #include <utility>
 #include <vector>
 #include <opencv2/core/core.hpp>
@@ -96,6 +97,22 @@ public:
                       const std::vector<float>& angle2, const std::vector<uint8_t>& valid2,
                       const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec2, bool checkOrientation,
                       std::vector<int>& match12);
+
+    // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (R/lib_src/ORBmatcher.cc:806-1013), the
+    // matcher of LocalMapping::CreateNewMapPoints, key frames without a second camera.  hasMapPoint*[i]: GetMapPoint(i) != NULL;
+    // stereo*[i]: mvuRight[i] >= 0; keys2 = pKF2->mvKeysUn; scaleFactors2 = pKF2->mvScaleFactors; epipole = the projection of
+    // camera centre 1 into image 2 (:815-819); epipolarOk(idx1, idx2) = pCamera1->epipolarConstrain(pCamera2, kp1, kp2, R12, t12,
+    // sigma1, sigma2) (:957) -- the caller's geometry, asked only for pairs that survive the distance tests, in the
+    // reference's order.  vMatchedPairs as in the reference.  Distances of all common-node blocks run in one launch.
+    int SearchForTriangulation(const cv::Mat& desc1, const std::vector<float>& angle1, const std::vector<uint8_t>& hasMapPoint1,
+                               const std::vector<uint8_t>& stereo1,
+                               const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec1, const cv::Mat& desc2,
+                               const std::vector<float>& angle2, const std::vector<uint8_t>& hasMapPoint2,
+                               const std::vector<uint8_t>& stereo2, const std::vector<cv::KeyPoint>& keys2,
+                               const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVec2,
+                               const std::vector<float>& scaleFactors2, cv::Point2f epipole,
+                               const std::function<bool(size_t, size_t)>& epipolarOk, bool bOnlyStereo, bool bCoarse,
+                               bool checkOrientation, std::vector<std::pair<size_t, size_t> >& vMatchedPairs);
 
     // ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (R/lib_src/ORBmatcher.cc:581-680)
     // on flattened frames: keys* = mvKeysUn, desc* = mDescriptors, grid2 = F2's key-point grid.  Every DescriptorDistance

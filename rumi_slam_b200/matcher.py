@@ -634,6 +634,56 @@ class ORBmatcher:
                     nmatches -= 1
         return nmatches, match12
 
+    # ---- ORBmatcher::SearchForTriangulation (ORBmatcher.cc:806-1013, key frames without a second camera) ----
+    def SearchForTriangulation(self, desc1, angle1, has_mp1, stereo1, featvec1, desc2, angle2, has_mp2, stereo2, keys2, featvec2,
+                               scale_factors2, epipole, epipolar_ok, only_stereo=False, coarse=False):
+        """The matcher of LocalMapping::CreateNewMapPoints.  has_mp*[i]: the feature already has a map point; stereo*[i]:
+        mvuRight[i] >= 0; keys2: mvKeysUn of key frame 2; epipole = projection of camera centre 1 into image 2 (:815-819);
+        epipolar_ok(i1, i2) -> bool = pCamera1->epipolarConstrain(pCamera2, kp1, kp2, R12, t12, sigma1, sigma2) (:957), the
+        caller's geometry, called only for pairs that survive the distance tests, in the reference's order (a [n1, n2] bool
+        array works too).  Returns (nmatches, match12).  The GPU computes every distance of every common vocabulary node."""
+        f32 = np.float32
+        n1 = len(np.asarray(desc1).reshape(-1, 32))
+        k2 = np.ascontiguousarray(keys2, KP_DTYPE)
+        sf2 = np.asarray(scale_factors2, f32)
+        epx, epy = f32(epipole[0]), f32(epipole[1])
+        ok = epipolar_ok if callable(epipolar_ok) else (lambda a, b, _t=np.asarray(epipolar_ok): bool(_t[a, b]))
+        match12 = np.full(n1, -1, np.int32)
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        nmatches = 0
+        for a_idx, b_idx, block in self._bow_blocks(desc1, featvec1, desc2, featvec2):
+            for i in range(len(a_idx)):
+                id1 = int(a_idx[i])
+                if has_mp1[id1] or (only_stereo and not stereo1[id1]):
+                    continue
+                best, best2 = self.TH_LOW, -1
+                for j in range(len(b_idx)):
+                    id2 = int(b_idx[j])
+                    if has_mp2[id2] or (only_stereo and not stereo2[id2]):
+                        continue
+                    d = int(block[i, j])
+                    if d > self.TH_LOW or d > best:
+                        continue
+                    if not stereo1[id1] and not stereo2[id2]:
+                        ex, ey = f32(epx - k2["x"][id2]), f32(epy - k2["y"][id2])
+                        if f32(f32(ex * ex) + f32(ey * ey)) < f32(f32(100.0) * sf2[k2["octave"][id2]]):
+                            continue
+                    if coarse or ok(id1, id2):
+                        best2, best = id2, d
+                if best2 >= 0:
+                    match12[id1] = best2
+                    nmatches += 1
+                    if self.mbCheckOrientation:
+                        rot_hist[self._rot_bin(angle1[id1], angle2[best2])].append(id1)
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for b in range(self.HISTO_LENGTH):
+                if b not in keep:
+                    for id1 in rot_hist[b]:
+                        match12[id1] = -1
+                        nmatches -= 1
+        return nmatches, match12
+
 
 class FrameGrid:
     """The 64 x 48 key-point grid a reference Frame / KeyFrame carries (FRAME_GRID_COLS / ROWS,

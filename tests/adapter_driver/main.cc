@@ -139,6 +139,27 @@ int main(int argc, char** argv) {
             std::fwrite(&nf, 4, 1, f);
             std::fwrite(fIdx.data(), 4, fIdx.size(), f);
             std::fwrite(fDist.data(), 4, fDist.size(), f);
+            // SearchForTriangulation left -> right: "vocabulary node" of a feature = its first descriptor byte mod 16,
+            // deterministic map-point / stereo flags and epipolar table (the test rebuilds the same inputs)
+            auto featvec = [](const cv::Mat& d) {
+                std::vector<std::pair<unsigned, std::vector<unsigned> > > fv(16);
+                for (unsigned n = 0; n < 16; ++n) fv[n].first = n;
+                for (int i = 0; i < d.rows; ++i) fv[d.ptr(i)[0] % 16].second.push_back((unsigned)i);
+                return fv;
+            };
+            std::vector<uint8_t> has1(nL), has2(nR), st1(nL), st2(nR);
+            std::vector<float> a1(nL), a2(nR);
+            for (int i = 0; i < nL; ++i) { has1[i] = i % 4 == 0; st1[i] = i % 3 == 0; a1[i] = L.keys[i].angle; }
+            for (int i = 0; i < nR; ++i) { has2[i] = i % 5 == 0; st2[i] = i % 2 == 0; a2[i] = R.keys[i].angle; }
+            std::vector<std::pair<size_t, size_t> > pairs;
+            const int nt = mi.SearchForTriangulation(L.desc, a1, has1, st1, featvec(L.desc), R.desc, a2, has2, st2, R.keys,
+                                                     featvec(R.desc), sf, cv::Point2f(376.f, 240.f),
+                                                     [](size_t i1, size_t i2) { return (i1 * 31 + i2 * 17) % 5 != 0; }, false, false,
+                                                     true, pairs);
+            std::vector<int> m12t(nL, -1);
+            for (const auto& pr : pairs) m12t[pr.first] = (int)pr.second;
+            std::fwrite(&nt, 4, 1, f);
+            std::fwrite(m12t.data(), 4, m12t.size(), f);
         }
         // the empty-image contract of operator() (ORBextractor.cc:1017)
         cv::Mat empty; Result E;

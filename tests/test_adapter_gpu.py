@@ -125,3 +125,14 @@ def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
     rn3, rbest, rdist = M.fuse_search(rk, rd, sf, inv_s2, (0, 0, 752, 480), np.full(nR, -1.0, np.float32), ii % 9 != 0, uv_f, ur_f,
                                       d3_f, np.zeros(nR, np.float32), np.full(nR, 1e9, np.float32), rk["octave"][j], rd[j], 3.0)
     assert nf == rn3 and np.array_equal(f_idx, rbest) and np.array_equal(f_dist, rdist) and rn3 > 300
+    # ORBmatcherAccel::SearchForTriangulation, executed in C++ ("node" of a feature = first descriptor byte mod 16)
+    from oracle import bow_oracle as B
+    B.build()
+    nt = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    m12t = np.frombuffer(buf, np.int32, len(lk), off); off += 4 * len(lk)
+    fv = lambda d: {n: [int(v) for v in np.flatnonzero(d[:, 0] % 16 == n)] for n in range(16) if np.any(d[:, 0] % 16 == n)}
+    il, ir = np.arange(len(lk)), np.arange(nR)
+    epi = (il[:, None] * 31 + ir[None, :] * 17) % 5 != 0
+    rn4, rm4 = B.search_for_triangulation(ld, lk["angle"], il % 4 == 0, il % 3 == 0, fv(ld), rd, rk["angle"], ir % 5 == 0, ir % 2 == 0,
+                                          rk["x"], rk["y"], rk["octave"], fv(rd), sf, (376.0, 240.0), epi, False, False, True)
+    assert nt == rn4 and np.array_equal(m12t, rm4) and rn4 > 20

@@ -157,3 +157,44 @@ def test_search_by_bow_keyframe_keyframe_matches_oracle(bow_oracle, check_ori):
     n_ref, match_ref = bow_oracle.search_by_bow_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, nnratio=0.8, check_ori=check_ori)
     assert n_gpu == n_ref and n_ref > 100 and np.array_equal(match_gpu, match_ref)
     assert all(v2[j] for j in match_gpu if j >= 0)
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,only_stereo,coarse", [(40, False, False), (41, True, False), (42, False, True)])
+def test_search_for_triangulation_matches_oracle(bow_oracle, seed, only_stereo, coarse, check_ori):
+    """ORBmatcher::SearchForTriangulation (R/lib_src/ORBmatcher.cc:806-1013); the oracle side is pinned to the reference function
+    in tests/test_ref_frame_pin.py::test_search_for_triangulation_equals_reference."""
+    from rumi_slam_b200 import KP_DTYPE, ORBVocabulary, ORBmatcher
+    k, L = 10, 4
+    par, leaf, desc, w = synthetic_vocabulary(k, L, seed=12)
+    V = ORBVocabulary(k, L, par, leaf, desc, w)
+    rng = np.random.default_rng(seed)
+    n1, n2 = 900, 1000
+    d1 = descriptors_near_vocabulary(desc, leaf, n1, seed, flip=0.04)
+    src = rng.integers(0, n1, 800)
+    d2 = np.concatenate([d1[src] ^ np.packbits(rng.random((800, 256)) < 0.03, axis=1),
+                         descriptors_near_vocabulary(desc, leaf, n2 - 800, seed + 1)])
+    perm = rng.permutation(n2)
+    d2 = d2[perm]
+    a1 = rng.random(n1).astype(np.float32) * 360
+    a2 = rng.random(n2).astype(np.float32) * 360
+    a2[np.argsort(perm)[:800]] = (a1[src] + 20 + rng.normal(0, 2, 800)).astype(np.float32) % 360
+    k2 = np.zeros(n2, KP_DTYPE)
+    k2["x"], k2["y"], k2["octave"] = rng.uniform(20, 620, n2), rng.uniform(20, 460, n2), rng.integers(0, 8, n2)
+    has1, has2 = rng.random(n1) < 0.3, rng.random(n2) < 0.3
+    st1, st2 = rng.random(n1) < 0.5, rng.random(n2) < 0.5
+    epi = ((np.arange(n1)[:, None] * 31 + np.arange(n2)[None, :] * 17) % 5 != 0)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    _, fv1 = V.transform(d1, 2)
+    _, fv2 = V.transform(d2, 2)
+    calls = []
+
+    def epipolar_ok(i1, i2):                       # the caller's geometry: only asked for pairs that survive the distance tests
+        calls.append((i1, i2))
+        return bool(epi[i1, i2])
+    n, m = ORBmatcher(0.6, check_ori).SearchForTriangulation(d1, a1, has1, st1, fv1, d2, a2, has2, st2, k2, fv2, sf, (320.0, 240.0),
+                                                            epipolar_ok, only_stereo, coarse)
+    rn, rm = bow_oracle.search_for_triangulation(d1, a1, has1, st1, fv1, d2, a2, has2, st2, k2["x"], k2["y"], k2["octave"], fv2, sf,
+                                                 (320.0, 240.0), epi, only_stereo, coarse, check_ori)
+    assert n == rn and np.array_equal(m, rm) and rn > 50
+    assert (len(calls) == 0) == coarse and len(calls) < 20 * n1

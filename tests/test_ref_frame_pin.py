@@ -283,3 +283,38 @@ def test_fuse_search_equals_reference(oracle, rf, M, seed, th, stereo):
     traced = (best < 0) | (kf_has[np.maximum(best, 0)] != 2)         # a bad resident point leaves no trace in the reference run
     assert np.array_equal(best[traced], rbest[traced]) and np.all(rbest[~traced] == -1)
     assert rn > 40 and (best >= 0).sum() == rn
+
+
+def _triangulation_case(B, seed):
+    """Two key frames whose descriptors share vocabulary nodes (the SearchByBoW scene), with key points, map-point flags,
+    stereo flags, an epipole inside image 2 and a pseudo-random epipolar-constraint table."""
+    from rumi_slam_b200 import KP_DTYPE
+    d1, a1, fv1, d2, a2, fv2, rng = _scene(B, seed)
+    n1, n2 = len(d1), len(d2)
+
+    def kps(n, ang):
+        k = np.zeros(n, KP_DTYPE)
+        k["x"], k["y"] = rng.uniform(20, 620, n), rng.uniform(20, 460, n)
+        k["angle"], k["octave"], k["size"], k["class_id"] = ang, rng.integers(0, 8, n), 31.0, -1
+        return k
+    k1, k2 = kps(n1, a1), kps(n2, a2)
+    has1, has2 = rng.random(n1) < 0.3, rng.random(n2) < 0.3
+    ur1 = np.where(rng.random(n1) < 0.5, k1["x"] - 5.0, -1.0).astype(np.float32)
+    ur2 = np.where(rng.random(n2) < 0.5, k2["x"] - 5.0, -1.0).astype(np.float32)
+    epi = ((np.arange(n1)[:, None] * 31 + np.arange(n2)[None, :] * 17) % 5 != 0).astype(np.uint8)
+    return d1, a1, fv1, k1, has1, ur1, d2, a2, fv2, k2, has2, ur2, epi, (320.0, 240.0)
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,only_stereo,coarse", [(40, False, False), (41, True, False), (42, False, True), (43, False, False)])
+def test_search_for_triangulation_equals_reference(oracle, rf, B, seed, only_stereo, coarse, check_ori):
+    """ORBmatcher::SearchForTriangulation (R/lib_src/ORBmatcher.cc:806-1013), the matcher of LocalMapping::CreateNewMapPoints:
+    common-node walk, 'already has a map point' skips, stereo-only mode, the running best distance that only an accepted
+    (epipolar-consistent) candidate lowers, the epipole exclusion zone for mono pairs, the rotation histogram."""
+    d1, a1, fv1, k1, has1, ur1, d2, a2, fv2, k2, has2, ur2, epi, ep = _triangulation_case(B, seed)
+    sf = oracle.tables()["scale"]
+    rn, rm = rf.search_for_triangulation(k1, d1, has1, ur1, fv1, k2, d2, has2, ur2, fv2, sf, ep, epi, only_stereo, coarse, check_ori)
+    n, m = B.search_for_triangulation(d1, a1, has1, ur1 >= 0, fv1, d2, a2, has2, ur2 >= 0, k2["x"], k2["y"], k2["octave"], fv2, sf,
+                                      ep, epi, only_stereo, coarse, check_ori)
+    assert n == rn and np.array_equal(m, rm)
+    assert rn > (20 if only_stereo else 60)

@@ -6,6 +6,7 @@
 //   ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono)   R/lib_src/ORBmatcher.cc:1498-1684 (Nleft == -1)
 //   ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)   R/lib_src/ORBmatcher.cc:1685-1794
 //   ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight)  (matching core)   R/lib_src/ORBmatcher.cc:1015-1181 (NLeft == -1)
+//   ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, [vpPointsKFs,] vpMatched, ...)   R/lib_src/ORBmatcher.cc:372-471, 473-580
 //   CloudMerging's pixel-distance key-point association              R/lib_src/CloudMerging.cc:503-551
 // Pinned against the UNMODIFIED reference functions compiled into oracle/_ref/librefframe.so
 // (tests/test_ref_frame_pin.py).  FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48 (R/include/cloud_edge_slam_lib/Frame.h:42-43).
@@ -375,6 +376,42 @@ int mo_fuse_search(const void* kKv, const uint8_t* dK, int nK, const float* scal
         if (bestDist <= TH_LOW) { bestIdxOut[i] = bestIdx; nFused++; }
     }
     return nFused;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, Sim3 Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:372-471) and
+// its overload that also records the points' key frames (:473-580) -- the matchers of LoopClosing (same search).  Per
+// candidate map point i: valid[i] = not bad, not in the initial vpMatched, depth >= 0, viewing-angle test passed; uv[i],
+// dist[i] vs [minDist, maxDist], level[i] = PredictScale.  occupied[j] = vpMatched[j] != NULL on entry; a feature matched
+// earlier in this call is skipped as well (:443-444).  kfMatch[j] = map point stored in vpMatched[j] by this call, or -1.
+int mo_search_by_projection_sim3(const void* kKv, const uint8_t* dK, int nK, const float* scaleFactors, int minX, int minY, int maxX,
+                                 int maxY, const uint8_t* occupied, const uint8_t* valid, const float* uv, const float* dist3D,
+                                 const float* minDist, const float* maxDist, const int32_t* level, const uint8_t* dMP, int nMP,
+                                 int th, float ratioHamming, int32_t* kfMatch) {
+    const KP* kK = (const KP*)kKv;
+    Grid g(kK, nK, minX, minY, maxX, maxY);
+    for (int j = 0; j < nK; ++j) kfMatch[j] = -1;
+    std::vector<int> vIndices;
+    int nmatches = 0;
+    for (int i = 0; i < nMP; ++i) {
+        if (!valid[i]) continue;
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        if (!(u >= (float)minX && u < (float)maxX && v >= (float)minY && v < (float)maxY)) continue;
+        if (dist3D[i] < minDist[i] || dist3D[i] > maxDist[i]) continue;
+        const int nPredictedLevel = level[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        g.query(u, v, radius, -1, -1, vIndices);
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (occupied[idx] || kfMatch[idx] >= 0) continue;
+            const int kpLevel = kK[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int dist = descriptor_distance(dMP + 32 * (size_t)i, dK + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW * ratioHamming) { kfMatch[bestIdx] = i; nmatches++; }
+    }
+    return nmatches;
 }
 
 // CloudMerging.cc:503-551 for one matched key-frame pair: per key point of key frame 1 the nearest key point of key

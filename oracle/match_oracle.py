@@ -169,6 +169,24 @@ def fuse_search(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, valid,
     return nf, bi[:n], bd[:n]
 
 
+def search_by_projection_sim3(kK, dK, scale_factors, bounds, occupied, valid, uv, dist3d, min_dist, max_dist, level, dMP, th=3,
+                              ratio_hamming=1.0):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:372-471 / :473-580):
+    (nmatches, kfMatch[j] = candidate map point or -1)."""
+    kK = np.ascontiguousarray(kK, KP_DTYPE)
+    dK, dMP = _u8(dK).reshape(-1, 32), _u8(dMP).reshape(-1, 32)
+    out = np.zeros(max(len(kK), 1), np.int32)
+    L = lib()
+    L.mo_search_by_projection_sim3.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p,
+                                               _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, C.c_int, C.c_int, C.c_float, _i32p]
+    n = L.mo_search_by_projection_sim3(kK.ctypes.data, _p(dK, _u8p), len(kK), _p(_f32(scale_factors), _f32p),
+                                       *[int(b) for b in bounds], _p(_u8(occupied), _u8p), _p(_u8(valid), _u8p), _p(_f32(uv), _f32p),
+                                       _p(_f32(dist3d), _f32p), _p(_f32(min_dist), _f32p), _p(_f32(max_dist), _f32p),
+                                       _p(np.ascontiguousarray(level, np.int32), _i32p), _p(dMP, _u8p), len(dMP), int(th),
+                                       float(ratio_hamming), _p(out, _i32p))
+    return n, out[:len(kK)]
+
+
 def associate_pixels(k1, valid1, k2, valid2, bounds, tol=3.0):
     """CloudMerging.cc:503-551 for one key-frame pair: (matchNum, match12)."""
     k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)

@@ -260,3 +260,43 @@ def search_for_triangulation(k1, d1, has_mp1, u_right1, fv1, k2, d2, has_mp2, u_
                                        _p(n2, _i32p), len(d2), _p(sf, _f32p), len(sf), float(ep[0]), float(ep[1]), int(only_stereo),
                                        int(coarse), _p(u8(epi_ok), _u8p), 0.6, int(check_ori), _p(match, _i32p))
     return n, match[:len(d1)]
+
+
+def _sim3_args(kK, dK, scale_factors, bounds, occupied, state, already_at, uv, depth, min_dist, max_dist, level, dMP):
+    kK = np.ascontiguousarray(kK, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    dK, dMP = u8(dK).reshape(-1, 32), u8(dMP).reshape(-1, 32)
+    sf = f32(scale_factors)
+    keep = [kK, dK, dMP, sf, u8(occupied), u8(state), i32(already_at), f32(uv), f32(depth), f32(min_dist), f32(max_dist), i32(level)]
+    args = [kK.ctypes.data, _p(dK, _u8p), len(kK), _p(sf, _f32p), len(sf), *[int(b) for b in bounds], _p(keep[4], _u8p),
+            _p(keep[5], _u8p), _p(keep[6], _i32p), _p(keep[7], _f32p), _p(keep[8], _f32p), _p(keep[9], _f32p), _p(keep[10], _f32p),
+            _p(keep[11], _i32p), _p(dMP, _u8p), len(dMP)]
+    types = [C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _i32p, _f32p, _f32p, _f32p,
+             _f32p, _i32p, _u8p, C.c_int]
+    return keep, args, types
+
+
+def search_by_projection_sim3(variant, kK, dK, scale_factors, bounds, occupied, state, already_at, uv, depth, min_dist, max_dist,
+                              level, dMP, th=3, ratio_hamming=1.0):
+    """The reference's ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (variant 0) or its overload
+    with vpPointsKFs / vpMatchedKF (variant 1): (nmatches, kfMatch, dist3D the function compared with the invariance window)."""
+    keep, args, types = _sim3_args(kK, dK, scale_factors, bounds, occupied, state, already_at, uv, depth, min_dist, max_dist, level, dMP)
+    out = np.zeros(max(len(keep[0]), 1), np.int32)
+    d3 = np.zeros(max(len(keep[2]), 1), np.float32)
+    L = lib()
+    L.ref_search_by_projection_sim3.argtypes = [C.c_int] + types + [C.c_int, C.c_float, _i32p, _f32p]
+    n = L.ref_search_by_projection_sim3(int(variant), *args, int(th), float(ratio_hamming), _p(out, _i32p), _p(d3, _f32p))
+    return n, out[:len(keep[0])], d3[:len(keep[2])]
+
+
+def fuse_sim3(kK, dK, scale_factors, bounds, occupied, state, already_at, uv, depth, min_dist, max_dist, level, dMP, th=3.0):
+    """The reference's ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint): (nFused, bestIdx, dist3D)."""
+    keep, args, types = _sim3_args(kK, dK, scale_factors, bounds, occupied, state, already_at, uv, depth, min_dist, max_dist, level, dMP)
+    out = np.zeros(max(len(keep[2]), 1), np.int32)
+    d3 = np.zeros(max(len(keep[2]), 1), np.float32)
+    L = lib()
+    L.ref_fuse_sim3.argtypes = types + [C.c_float, _i32p, _f32p]
+    n = L.ref_fuse_sim3(*args, float(th), _p(out, _i32p), _p(d3, _f32p))
+    return n, out[:len(keep[2])], d3[:len(keep[2])]

@@ -13,6 +13,7 @@
 //   ORBmatcher::SearchByProjection (CurrentFrame, LastFrame) / (CurrentFrame, KeyFrame, sAlreadyFound)   :1498-1684, 1685-1794
 //   ORBmatcher::Fuse (KeyFrame, MapPoints) + KeyFrame::GetFeaturesInArea / IsInImage   ORBmatcher.cc:1015-1181, KeyFrame.cc:887-930
 //   ORBmatcher::SearchForTriangulation   ORBmatcher.cc:806-1013 (epipolarConstrain = a table look-up stand-in)
+//   ORBmatcher::SearchByProjection (KeyFrame, Sim3, ...) x 2 and ORBmatcher::Fuse (KeyFrame, Sim3, ...)   :372-580, :1182-1292
 //     (these take poses and a camera model: Sophus::SE3f / Eigen::Vector3f / GeometricCamera are minimal stand-ins
 //      below -- identity rotation, so that "Tcw * x3Dw" is exact -- and the pin covers everything AFTER the projection,
 //      which is what the flattened adapters take over; the projection itself stays with the caller's own Sophus / camera)
@@ -52,6 +53,7 @@ struct Vector3f {
     float operator()(int i) const { return v[i]; }
     Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
     float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+    Vector3f operator/(float d) const { return Vector3f(v[0] / d, v[1] / d, v[2] / d); }
     float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
 };
 struct Matrix3f { float m[9]; };
@@ -59,12 +61,23 @@ struct Matrix3f { float m[9]; };
 namespace Sophus {
 struct SE3f {                                   // translation only (rotation = identity): R v + t is exact
     Eigen::Vector3f t;
+    SE3f() {}
+    SE3f(const Eigen::Matrix3f&, const Eigen::Vector3f& tr) : t(tr) {}
     SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t.v[0], -t.v[1], -t.v[2]); return r; }
     Eigen::Vector3f translation() const { return t; }
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return Eigen::Vector3f(p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]); }
     SE3f operator*(const SE3f& o) const { SE3f r; r.t = Eigen::Vector3f(t.v[0] + o.t.v[0], t.v[1] + o.t.v[1], t.v[2] + o.t.v[2]); return r; }
     Eigen::Matrix3f rotationMatrix() const { Eigen::Matrix3f r = {{1, 0, 0, 0, 1, 0, 0, 0, 1}}; return r; }
 };
+template <class T>
+struct Sim3 {                                   // identity rotation, translation t, scale s
+    Eigen::Vector3f t;
+    T s = 1;
+    Eigen::Matrix3f rotationMatrix() const { Eigen::Matrix3f r = {{1, 0, 0, 0, 1, 0, 0, 0, 1}}; return r; }
+    Eigen::Vector3f translation() const { return t; }
+    T scale() const { return s; }
+};
+typedef Sim3<float> Sim3f;
 }  // namespace Sophus
 
 using namespace std;
@@ -128,6 +141,7 @@ public:
     bool isBad() { return false; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx);                                  // Fuse: logged
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> r(mvpMapPoints.begin(), mvpMapPoints.end()); r.erase(nullptr); return r; }
     void AddMapPoint(MapPoint*, const size_t&) {}
     std::vector<MapPoint*> mvpMapPoints;
     DBoW2::FeatureVector mFeatVec;
@@ -201,6 +215,13 @@ public:
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
                            const int ORBdist);
     int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
+    int SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints,
+                           std::vector<MapPoint*>& vpMatched, int th, float ratioHamming = 1.0);
+    int SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float>& Scw, const std::vector<MapPoint*>& vpPoints,
+                           const std::vector<KeyFrame*>& vpPointsKFs, std::vector<MapPoint*>& vpMatched,
+                           std::vector<KeyFrame*>& vpMatchedKF, int th, float ratioHamming = 1.0);
+    int Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, float th,
+             vector<MapPoint*>& vpReplacePoint);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<pair<size_t, size_t>>& vMatchedPairs,
                                const bool bOnlyStereo, const bool bCoarse = false);
     static const int TH_LOW;
@@ -575,6 +596,119 @@ int ref_search_for_triangulation(const void* k1, const uint8_t* d1, const uint8_
     for (int i = 0; i < n1; ++i) match12[i] = -1;
     for (const auto& p : pairs) match12[p.first] = (int)p.second;
     return n;
+}
+
+}  // extern "C"
+
+namespace {
+// key frame + candidate map points of the three Sim3 functions (stand-in camera (x, y, z) -> (x, y) for the overloads that
+// call mpCamera->project; the overload that projects with fx, fy, cx, cy gets fx = fy = z-compensating values instead:
+// u = fx * x / z + cx with fx = 1, cx = 0 needs world point (u * z, v * z, z))
+struct Sim3Case {
+    GeometricCamera cam;
+    Frame F;
+    KeyFrame kf;
+    MapPoint resident;
+    std::vector<MapPoint> mps;
+    std::vector<MapPoint*> ptrs;
+    Sim3Case(const void* kK, const uint8_t* dK, int nK, const float* scaleFactors, int nlevels, int minX, int minY, int maxX, int maxY,
+             const uint8_t* occupied, const uint8_t* state, const float* uv, const float* depth, const float* minDist,
+             const float* maxDist, const int32_t* level, const uint8_t* dMP, int nMP, bool pinholeInline)
+        : mps(nMP), ptrs(nMP) {
+        set_grid(minX, minY, maxX, maxY);
+        F.N = nK; F.mvKeysUn = keys(kK, nK); F.mvKeys = F.mvKeysUn;
+        F.AssignFeaturesToGrid();
+        kf.N = nK; kf.mvKeysUn = F.mvKeysUn; kf.mvKeys = F.mvKeysUn; kf.mDescriptors = rows32(dK, nK);
+        kf.mvuRight.assign(nK, -1.0f);
+        kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+        kf.mpCamera = &cam;
+        kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+        kf.mnMinX = minX; kf.mnMinY = minY; kf.mnMaxX = maxX; kf.mnMaxY = maxY;
+        kf.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+        for (int i = 0; i < FRAME_GRID_COLS; ++i)
+            for (int j = 0; j < FRAME_GRID_ROWS; ++j) kf.mGrid[i][j] = F.mGrid[i][j];
+        resident.id = -1000; resident.nObs = 3;
+        kf.mvpMapPoints.assign(nK, nullptr);
+        for (int j = 0; j < nK; ++j) if (occupied[j]) kf.mvpMapPoints[j] = &resident;
+        for (int i = 0; i < nMP; ++i) {
+            MapPoint& m = mps[i];
+            m.id = i;
+            const float z = depth[i];
+            m.mWorldPos = pinholeInline ? Eigen::Vector3f(uv[2 * i] * z, uv[2 * i + 1] * z, z) : Eigen::Vector3f(uv[2 * i], uv[2 * i + 1], z);
+            const float n = m.mWorldPos.norm();
+            const float sgn = state[i] == 4 ? -1.0f : 1.0f;
+            m.mNormal = Eigen::Vector3f(sgn * m.mWorldPos(0) / n, sgn * m.mWorldPos(1) / n, sgn * m.mWorldPos(2) / n);
+            m.mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+            m.mnTrackScaleLevel = level[i];
+            m.mfMinDistance = minDist[i]; m.mfMaxDistance = maxDist[i];
+            m.mbBad = state[i] == 2;
+            ptrs[i] = &m;
+        }
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (variant 0, ORBmatcher.cc:372-471) or the
+// overload with vpPointsKFs / vpMatchedKF (variant 1, :473-580; projects with fx, fy, cx, cy).  state[i]: 1 usable, 2 bad,
+// 3 already in vpMatched (it then occupies feature alreadyAt[i]), 4 oblique.  dist3D[i] = the norm the function compares.
+// kfMatch[j] = candidate stored in vpMatched[j] by the call, or -1.
+int ref_search_by_projection_sim3(int variant, const void* kK, const uint8_t* dK, int nK, const float* scaleFactors, int nlevels,
+                                  int minX, int minY, int maxX, int maxY, const uint8_t* occupied, const uint8_t* state,
+                                  const int32_t* alreadyAt, const float* uv, const float* depth, const float* minDist,
+                                  const float* maxDist, const int32_t* level, const uint8_t* dMP, int nMP, int th,
+                                  float ratioHamming, int32_t* kfMatch, float* dist3D) {
+    Sim3Case c(kK, dK, nK, scaleFactors, nlevels, minX, minY, maxX, maxY, occupied, state, uv, depth, minDist, maxDist, level, dMP,
+               nMP, variant == 1);
+    std::vector<MapPoint*> vpMatched(nK, nullptr);
+    for (int j = 0; j < nK; ++j) if (occupied[j]) vpMatched[j] = &c.resident;
+    for (int i = 0; i < nMP; ++i) {
+        if (state[i] == 3) vpMatched[alreadyAt[i]] = &c.mps[i];
+        dist3D[i] = c.mps[i].mWorldPos.norm();
+    }
+    const std::vector<MapPoint*> before = vpMatched;
+    Sophus::Sim3f Scw;
+    ORBmatcher m(0.6f, true);
+    int n;
+    if (variant == 0) n = m.SearchByProjection(&c.kf, Scw, c.ptrs, vpMatched, th, ratioHamming);
+    else {
+        KeyFrame other;
+        std::vector<KeyFrame*> kfs(nMP, &other), matchedKF(nK, nullptr);
+        n = m.SearchByProjection(&c.kf, Scw, c.ptrs, kfs, vpMatched, matchedKF, th, ratioHamming);
+        for (int j = 0; j < nK; ++j)
+            if ((vpMatched[j] != before[j]) != (matchedKF[j] == &other)) return -1000;      // both arrays are written together
+    }
+    for (int j = 0; j < nK; ++j) kfMatch[j] = vpMatched[j] != before[j] ? (int)(vpMatched[j] - c.mps.data()) : -1;
+    return n;
+}
+
+// ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1182-1292).  state[i]: 1 usable, 2 bad, 3 already
+// a map point of pKF (at feature alreadyAt[i]), 4 oblique.  bestIdx[i] from the logged GetMapPoint calls.
+int ref_fuse_sim3(const void* kK, const uint8_t* dK, int nK, const float* scaleFactors, int nlevels, int minX, int minY, int maxX,
+                  int maxY, const uint8_t* occupied, const uint8_t* state, const int32_t* alreadyAt, const float* uv,
+                  const float* depth, const float* minDist, const float* maxDist, const int32_t* level, const uint8_t* dMP, int nMP,
+                  float th, int32_t* bestIdx, float* dist3D) {
+    Sim3Case c(kK, dK, nK, scaleFactors, nlevels, minX, minY, maxX, maxY, occupied, state, uv, depth, minDist, maxDist, level, dMP,
+               nMP, false);
+    for (int i = 0; i < nMP; ++i) {
+        if (state[i] == 3) c.kf.mvpMapPoints[alreadyAt[i]] = &c.mps[i];
+        dist3D[i] = c.mps[i].mWorldPos.norm();
+        bestIdx[i] = -1;
+    }
+    std::vector<MapPoint*> replace(nMP, nullptr);
+    Sophus::Sim3f Scw;
+    g_fuseLog.clear();
+    ORBmatcher m(0.6f, true);
+    const int nFused = m.Fuse(&c.kf, Scw, c.ptrs, th, replace);
+    // GetMapPoint(bestIdx) is called once per fused point, in candidate order; AddObservation names the point when the
+    // feature was free, vpReplacePoint[i] marks it when the feature was taken
+    size_t e = 0;
+    for (int i = 0; i < nMP && e < g_fuseLog.size(); ++i) {
+        const bool added = g_fuseLog[e].first == i, replaced = replace[i] != nullptr;
+        if (added || replaced) bestIdx[i] = g_fuseLog[e++].second;
+    }
+    return e == g_fuseLog.size() ? nFused : -1000;
 }
 
 }  // extern "C"

@@ -701,6 +701,61 @@ int ORBmatcherAccel::FuseSearch(const std::vector<cv::KeyPoint>& keysK, const cv
     return nFused;
 }
 
+int ORBmatcherAccel::FuseSearchSim3(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK, const FrameGridAccel& gridK,
+                                    const std::vector<float>& scaleFactors, const std::vector<uint8_t>& valid,
+                                    const std::vector<cv::Point2f>& uv, const std::vector<float>& dist3D,
+                                    const std::vector<float>& minDistance, const std::vector<float>& maxDistance,
+                                    const std::vector<int>& predictedLevel, const cv::Mat& descMP, float th,
+                                    std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+    // zero inverse sigma and "no right coordinate" switch the chi-square gates of FuseSearch off (0 > 5.99 never holds)
+    const std::vector<float> zeroSigma(scaleFactors.size(), 0.0f), noRight(keysK.size(), -1.0f), ur(uv.size(), 0.0f);
+    return FuseSearch(keysK, descK, gridK, scaleFactors, zeroSigma, noRight, valid, uv, ur, dist3D, minDistance, maxDistance,
+                      predictedLevel, descMP, th, bestIdx, bestDist);
+}
+
+int ORBmatcherAccel::SearchByProjectionSim3(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK,
+                                            const FrameGridAccel& gridK, const std::vector<float>& scaleFactors,
+                                            const std::vector<uint8_t>& occupied, const std::vector<uint8_t>& valid,
+                                            const std::vector<cv::Point2f>& uv, const std::vector<float>& dist3D,
+                                            const std::vector<float>& minDistance, const std::vector<float>& maxDistance,
+                                            const std::vector<int>& predictedLevel, const cv::Mat& descMP, int th,
+                                            float ratioHamming, std::vector<int>& kfMatch) {
+    kfMatch.assign(keysK.size(), -1);
+    std::vector<int> query;
+    std::vector<int32_t> off(1, 0), idx;
+    std::vector<uint8_t> Q;
+    for (size_t iMP = 0; iMP < uv.size(); iMP++) {
+        if (!valid[iMP]) continue;
+        const float u = uv[iMP].x, v = uv[iMP].y;
+        if (!(u >= gridK.mnMinX && u < gridK.mnMaxX && v >= gridK.mnMinY && v < gridK.mnMaxY)) continue;    // KeyFrame::IsInImage
+        if (dist3D[iMP] < minDistance[iMP] || dist3D[iMP] > maxDistance[iMP]) continue;
+        const float radius = th * scaleFactors[predictedLevel[iMP]];
+        const std::vector<size_t> vIndices = gridK.GetFeaturesInArea(u, v, radius);
+        if (vIndices.empty()) continue;
+        query.push_back((int)iMP);
+        idx.insert(idx.end(), vIndices.begin(), vIndices.end());
+        off.push_back((int32_t)idx.size());
+        Q.insert(Q.end(), descMP.ptr((int)iMP), descMP.ptr((int)iMP) + 32);
+    }
+    std::vector<uint16_t> dist;
+    CandidateDistances(Q, (int)query.size(), descK, off, idx, dist);
+    int nmatches = 0;
+    for (size_t qi = 0; qi < query.size(); ++qi) {
+        const int iMP = query[qi], nPredictedLevel = predictedLevel[iMP];
+        int bestDist = 256, bestIdx = -1;
+        for (int p = off[qi]; p < off[qi + 1]; ++p) {
+            const int j = idx[p];
+            if ((!occupied.empty() && occupied[j]) || kfMatch[j] >= 0) continue;                 // :443-444
+            const int kpLevel = keysK[j].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int d = dist[p];
+            if (d < bestDist) { bestDist = d; bestIdx = j; }
+        }
+        if (bestDist <= TH_LOW * ratioHamming) { kfMatch[bestIdx] = iMP; nmatches++; }
+    }
+    return nmatches;
+}
+
 int ORBmatcherAccel::AssociateSubmap(struct rumi_orb* extractor, const std::vector<cv::Mat>& images1,
                                      const std::vector<std::vector<cv::KeyPoint>>& keys1,
                                      const std::vector<std::vector<uint8_t>>& valid1, const std::vector<cv::Mat>& images2,

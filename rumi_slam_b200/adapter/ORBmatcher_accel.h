@@ -174,6 +174,26 @@ public:
                    const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel, const cv::Mat& descMP,
                    float th, std::vector<int>& bestIdx, std::vector<int>& bestDist);
 
+    // Matching core of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (R/lib_src/ORBmatcher.cc:1182-1292, LoopClosing):
+    // FuseSearch without the reprojection gates.  The caller fills vpReplacePoint / AddObservation from bestIdx (:1268-1280).
+    int FuseSearchSim3(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK, const FrameGridAccel& gridK,
+                       const std::vector<float>& scaleFactors, const std::vector<uint8_t>& valid,
+                       const std::vector<cv::Point2f>& uv, const std::vector<float>& dist3D,
+                       const std::vector<float>& minDistance, const std::vector<float>& maxDistance,
+                       const std::vector<int>& predictedLevel, const cv::Mat& descMP, float th, std::vector<int>& bestIdx,
+                       std::vector<int>& bestDist);
+
+    // ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (R/lib_src/ORBmatcher.cc:372-471) and its
+    // overload with vpPointsKFs / vpMatchedKF (:473-580), the matchers of LoopClosing (same search).  valid[i] = not bad, not in
+    // vpMatched on entry, depth >= 0, viewing-angle test passed; occupied[j] = vpMatched[j] != NULL on entry.
+    // kfMatch[j] = candidate the reference stores in vpMatched[j] (and vpPointsKFs[kfMatch[j]] in vpMatchedKF[j]), or -1.
+    int SearchByProjectionSim3(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK, const FrameGridAccel& gridK,
+                               const std::vector<float>& scaleFactors, const std::vector<uint8_t>& occupied,
+                               const std::vector<uint8_t>& valid, const std::vector<cv::Point2f>& uv,
+                               const std::vector<float>& dist3D, const std::vector<float>& minDistance,
+                               const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel,
+                               const cv::Mat& descMP, int th, float ratioHamming, std::vector<int>& kfMatch);
+
     // Descriptor-based key-point association of the matched key-frame pairs of a submap merge (the pairs
     // R/lib_src/CloudMerging.cc:503-551 associates by pixel distance): real descriptors for the cloud
     // key frames (ORBextractor::CloudFrameComputeDescriptors, one batched call per side -- they carry zero descriptors in

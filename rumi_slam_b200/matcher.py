@@ -453,6 +453,55 @@ class ORBmatcher:
         best_idx[q[fused]] = i1[fused]
         return int(fused.sum()), best_idx, best_dist
 
+    def FuseSearchSim3(self, keysK, descK, scale_factors, bounds, valid, uv, dist3d, min_dist, max_dist, level, descMP, th=3.0):
+        """Matching core of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1182-1292, LoopClosing):
+        FuseSearch without the reprojection gates.  valid[i] = not bad, not already a map point of pKF, depth >= 0,
+        viewing-angle test passed.  The caller fills vpReplacePoint / AddObservation from best_idx (:1268-1280)."""
+        n, k = len(np.asarray(uv).reshape(-1, 2)), len(keysK)
+        return self.FuseSearch(keysK, descK, scale_factors, np.zeros(len(scale_factors), np.float32), bounds,
+                               np.full(k, -1.0, np.float32), valid, uv, np.zeros(n, np.float32), dist3d, min_dist, max_dist, level,
+                               descMP, th)
+
+    # ---- ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming) ----
+    def SearchByProjectionSim3(self, keysK, descK, scale_factors, bounds, occupied, valid, uv, dist3d, min_dist, max_dist, level,
+                               descMP, th=3, ratio_hamming=1.0):
+        """The matchers of LoopClosing (ORBmatcher.cc:372-471 and :473-580; same search).  Per candidate map point i: valid[i] =
+        not bad, not in vpMatched on entry, depth >= 0, viewing-angle test passed; uv[i] = projection through Scw; dist3d[i]
+        against [min_dist, max_dist]; level[i] = PredictScale.  occupied[j] = vpMatched[j] != NULL on entry.  Returns
+        (nmatches, kf_match[j] = candidate stored in vpMatched[j] by this call, or -1); for the second overload
+        vpMatchedKF[j] = vpPointsKFs[kf_match[j]]."""
+        f32 = np.float32
+        kK = np.ascontiguousarray(keysK, KP_DTYPE)
+        sf = np.asarray(scale_factors, f32)
+        uv = np.asarray(uv, f32).reshape(-1, 2)
+        d3 = np.asarray(dist3d, f32)
+        level = np.asarray(level, np.int32)
+        ok = np.asarray(valid, bool) & (uv[:, 0] >= f32(bounds[0])) & (uv[:, 0] < f32(bounds[2])) & (uv[:, 1] >= f32(bounds[1])) \
+            & (uv[:, 1] < f32(bounds[3])) & ~(d3 < np.asarray(min_dist, f32)) & ~(d3 > np.asarray(max_dist, f32))
+        q = np.flatnonzero(ok)
+        off, idx = FrameGrid(kK, bounds).candidate_lists(uv[q], (f32(int(th)) * sf[level[q]]).astype(f32))
+        dist = self.candidates(np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)[q], descK, off, idx)
+        occ = np.asarray(occupied, bool)
+        km = np.full(len(kK), -1, np.int32)
+        limit = f32(f32(self.TH_LOW) * f32(ratio_hamming))
+        nmatches = 0
+        for qi, i in enumerate(q):
+            best, best_idx = 256, -1
+            for p in range(off[qi], off[qi + 1]):
+                j = int(idx[p])
+                if occ[j] or km[j] >= 0:
+                    continue
+                lv = int(kK["octave"][j])
+                if lv < level[i] - 1 or lv > level[i]:
+                    continue
+                d = int(dist[p])
+                if d < best:
+                    best, best_idx = d, j
+            if f32(best) <= limit:
+                km[best_idx] = i
+                nmatches += 1
+        return nmatches, km
+
     # ---- descriptor-based key-point association of matched key-frame pairs (submap merge, SURVEY.md 8f rank 3) ----
     def AssociateSubmap(self, extractor, images1, keys1, valid1, images2, keys2, valid2, th=None):
         """For every matched key-frame pair p (the pairs CloudMerging.cc:503-551 walks): real descriptors for the cloud key

@@ -160,6 +160,15 @@ int main(int argc, char** argv) {
             for (const auto& pr : pairs) m12t[pr.first] = (int)pr.second;
             std::fwrite(&nt, 4, 1, f);
             std::fwrite(m12t.data(), 4, m12t.size(), f);
+            // the loop-closing matchers on the Fuse scene above (every third feature of the key frame already matched)
+            std::vector<uint8_t> occ(nR);
+            for (int j = 0; j < nR; ++j) occ[j] = j % 3 == 0;
+            std::vector<int> kmS, fIdxS, fDistS;
+            const int ns = mi.SearchByProjectionSim3(R.keys, R.desc, grid, sf, occ, validF, uvF, d3F, dminF, dmaxF, lvF, descF, 4, 0.8f, kmS);
+            const int nfs = mi.FuseSearchSim3(R.keys, R.desc, grid, sf, validF, uvF, d3F, dminF, dmaxF, lvF, descF, 4.0f, fIdxS, fDistS);
+            std::fwrite(&ns, 4, 1, f); std::fwrite(&nfs, 4, 1, f);
+            std::fwrite(kmS.data(), 4, kmS.size(), f);
+            std::fwrite(fIdxS.data(), 4, fIdxS.size(), f);
         }
         // the empty-image contract of operator() (ORBextractor.cc:1017)
         cv::Mat empty; Result E;

@@ -136,3 +136,14 @@ def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
     rn4, rm4 = B.search_for_triangulation(ld, lk["angle"], il % 4 == 0, il % 3 == 0, fv(ld), rd, rk["angle"], ir % 5 == 0, ir % 2 == 0,
                                           rk["x"], rk["y"], rk["octave"], fv(rd), sf, (376.0, 240.0), epi, False, False, True)
     assert nt == rn4 and np.array_equal(m12t, rm4) and rn4 > 20
+    # ORBmatcherAccel::SearchByProjectionSim3 / ::FuseSearchSim3 on the Fuse scene, executed in C++
+    ns, nfs = (int(v) for v in np.frombuffer(buf, np.int32, 2, off)); off += 8
+    km_s = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    f_idx_s = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    zeros, big = np.zeros(nR, np.float32), np.full(nR, 1e9, np.float32)
+    rn5, rkm5 = M.search_by_projection_sim3(rk, rd, sf, (0, 0, 752, 480), ir % 3 == 0, ii % 9 != 0, uv_f, d3_f, zeros, big,
+                                            rk["octave"][j], rd[j], 4, 0.8)
+    rn6, rbest6, _ = M.fuse_search(rk, rd, sf, np.zeros(len(sf), np.float32), (0, 0, 752, 480), np.full(nR, -1.0, np.float32),
+                                   ii % 9 != 0, uv_f, zeros, d3_f, zeros, big, rk["octave"][j], rd[j], 4.0)
+    assert ns == rn5 and np.array_equal(km_s, rkm5) and rn5 > 100
+    assert nfs == rn6 and np.array_equal(f_idx_s, rbest6) and rn6 > 300

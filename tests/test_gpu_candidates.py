@@ -150,6 +150,34 @@ def test_fuse_search_matches_oracle(oracle, M, seed, th, stereo):
     assert rn > 40
 
 
+@pytest.mark.parametrize("seed,th,ratio", [(51, 3, 1.0), (53, 10, 0.8), (54, 30, 1.5)])
+def test_sim3_matchers_match_oracle(oracle, M, seed, th, ratio):
+    """ORBmatcher::SearchByProjection(pKF, Scw, ...) (R/lib_src/ORBmatcher.cc:372-580) and Fuse(pKF, Scw, ...) (:1182-1292); the
+    oracle side is pinned to the reference functions in tests/test_ref_frame_pin.py (..._sim3_equals_reference)."""
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed + 300)
+    n1, n2 = len(k1), len(k2)
+    f32 = np.float32
+    uv = (np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(f32) + rng.normal(0, 1.0, (n1, 2)).astype(f32))
+    uv[rng.random(n1) < 0.03] += f32(700.0)
+    valid = rng.random(n1) < 0.8
+    occupied = rng.random(n2) < 0.15
+    level = np.clip(k1["octave"] + rng.integers(0, 2, n1), 0, 7).astype(np.int32)
+    dist3d = rng.uniform(1.0, 100.0, n1).astype(f32)
+    min_d = rng.uniform(0.0, 20.0, n1).astype(f32)
+    max_d = (min_d + rng.uniform(10.0, 500.0, n1)).astype(f32)
+    sf = oracle.tables()["scale"]
+    args = (k2, d2, sf, (0, 0, 640, 480), occupied, valid, uv, dist3d, min_d, max_d, level, d1, th, ratio)
+    n, km = ORBmatcher().SearchByProjectionSim3(*args)
+    rn, rkm = M.search_by_projection_sim3(*args)
+    assert n == rn and np.array_equal(km, rkm) and rn > 50
+    nf, best, bd = ORBmatcher().FuseSearchSim3(k2, d2, sf, (0, 0, 640, 480), valid, uv, dist3d, min_d, max_d, level, d1, float(th))
+    rnf, rbest, rbd = M.fuse_search(k2, d2, sf, np.zeros(8, f32), (0, 0, 640, 480), np.full(n2, -1.0, f32), valid, uv,
+                                    np.zeros(n1, f32), dist3d, min_d, max_d, level, d1, float(th))
+    assert nf == rnf and np.array_equal(best, rbest) and np.array_equal(bd, rbd) and rnf > 50
+
+
 @pytest.mark.parametrize("seed,th,ratio", [(6, 3.0, 0.8), (7, 1.0, 0.8), (8, 5.0, 0.9), (9, 15.0, 0.6)])
 def test_search_by_projection_matches_oracle(oracle, M, seed, th, ratio):
     from rumi_slam_b200 import ORBmatcher

@@ -318,3 +318,60 @@ def test_search_for_triangulation_equals_reference(oracle, rf, B, seed, only_ste
                                       ep, epi, only_stereo, coarse, check_ori)
     assert n == rn and np.array_equal(m, rm)
     assert rn > (20 if only_stereo else 60)
+
+
+def _sim3_case(oracle, seed):
+    """Loop-closing scene: key frame = frame 2, candidate map points = the features of frame 1 projected to where they moved;
+    depths are powers of two so that the overload projecting with fx * x / z + cx reproduces the prescribed pixel exactly."""
+    k1, d1, k2, d2 = _frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed + 300)
+    n1, n2 = len(k1), len(k2)
+    f32 = np.float32
+    uv = (np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(f32) + rng.normal(0, 1.0, (n1, 2)).astype(f32))
+    uv[rng.random(n1) < 0.03] += f32(700.0)
+    depth = rng.choice([0.5, 1.0, 2.0, 4.0, 8.0, -1.0], n1, p=[0.2, 0.2, 0.2, 0.2, 0.17, 0.03]).astype(f32)
+    state = rng.choice([1, 1, 1, 1, 1, 2, 3, 4], n1).astype(np.uint8)
+    already_at = np.zeros(n1, np.int64)                               # distinct features for the already-found points
+    found = np.flatnonzero(state == 3)
+    already_at[found] = rng.permutation(n2)[:len(found)]
+    occupied = (rng.random(n2) < 0.1).astype(np.uint8)
+    level = np.clip(k1["octave"] + rng.integers(0, 2, n1), 0, 7).astype(np.int32)
+    return k1, d1, k2, d2, uv, depth, state, already_at.astype(np.int32), occupied, level, rng
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("seed,th,ratio", [(51, 3, 1.0), (52, 8, 1.0), (53, 10, 0.8), (54, 30, 1.5)])
+def test_search_by_projection_sim3_equals_reference(oracle, rf, M, seed, th, ratio, variant):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (R/lib_src/ORBmatcher.cc:372-471) and its
+    overload with the points' key frames (:473-580), the matchers of LoopClosing: bad / already-found points, image and
+    invariance-window tests, the [level - 1, level] window, 'feature already matched' skips incl. matches made earlier in
+    the call, the float threshold TH_LOW * ratioHamming."""
+    k1, d1, k2, d2, uv, depth, state, already_at, occupied, level, rng = _sim3_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    n1 = len(k1)
+    min_d = rng.uniform(0.0, 50.0, n1).astype(np.float32)
+    max_d = (min_d + rng.uniform(100.0, 5000.0, n1)).astype(np.float32)
+    rn, rkm, dist3d = rf.search_by_projection_sim3(variant, k2, d2, sf, (0, 0, 640, 480), occupied, state, already_at, uv, depth,
+                                                   min_d, max_d, level, d1, th, ratio)
+    occ = occupied.astype(bool).copy()
+    occ[already_at[state == 3]] = True
+    n, km = M.search_by_projection_sim3(k2, d2, sf, (0, 0, 640, 480), occ, (state == 1) & ~(depth < 0), uv, dist3d, min_d, max_d,
+                                        level, d1, th, ratio)
+    assert rn >= 0 and n == rn and np.array_equal(km, rkm)
+    assert rn > 50
+
+
+@pytest.mark.parametrize("seed,th", [(61, 3.0), (62, 4.0), (63, 10.0)])
+def test_fuse_sim3_equals_reference(oracle, rf, M, seed, th):
+    """ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (R/lib_src/ORBmatcher.cc:1182-1292): the fuse decision per
+    candidate == the Fuse matching core without the reprojection gates (zero inverse sigma, no right coordinates)."""
+    k1, d1, k2, d2, uv, depth, state, already_at, occupied, level, rng = _sim3_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    n1, n2 = len(k1), len(k2)
+    min_d = rng.uniform(0.0, 50.0, n1).astype(np.float32)
+    max_d = (min_d + rng.uniform(100.0, 5000.0, n1)).astype(np.float32)
+    rn, rbest, dist3d = rf.fuse_sim3(k2, d2, sf, (0, 0, 640, 480), occupied, state, already_at, uv, depth, min_d, max_d, level, d1, th)
+    n, best, _ = M.fuse_search(k2, d2, sf, np.zeros(8, np.float32), (0, 0, 640, 480), np.full(n2, -1.0, np.float32),
+                               (state == 1) & ~(depth < 0), uv, np.zeros(n1, np.float32), dist3d, min_d, max_d, level, d1, th)
+    assert rn >= 0 and n == rn and np.array_equal(best, rbest)
+    assert rn > 50

@@ -340,7 +340,7 @@ int mo_search_by_projection_kf(const void* kCv, const uint8_t* dC, int nC, const
 int mo_fuse_search(const void* kKv, const uint8_t* dK, int nK, const float* scaleFactors, const float* invLevelSigma2, int minX,
                    int minY, int maxX, int maxY, const float* uRight, const uint8_t* valid, const float* uv, const float* ur,
                    const float* dist3D, const float* minDist, const float* maxDist, const int32_t* level, const uint8_t* dMP,
-                   int nMP, float th, int32_t* bestIdxOut, int32_t* bestDistOut) {
+                   int nMP, float th, int thDist, int32_t* bestIdxOut, int32_t* bestDistOut) {
     const KP* kK = (const KP*)kKv;
     Grid g(kK, nK, minX, minY, maxX, maxY);
     std::vector<int> vIndices;
@@ -373,7 +373,7 @@ int mo_fuse_search(const void* kKv, const uint8_t* dK, int nK, const float* scal
             if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
         }
         bestDistOut[i] = bestDist;
-        if (bestDist <= TH_LOW) { bestIdxOut[i] = bestIdx; nFused++; }
+        if (bestDist <= thDist) { bestIdxOut[i] = bestIdx; nFused++; }        // TH_LOW in Fuse, TH_HIGH in SearchBySim3
     }
     return nFused;
 }
@@ -412,6 +412,32 @@ int mo_search_by_projection_sim3(const void* kKv, const uint8_t* dK, int nK, con
         if (bestDist <= TH_LOW * ratioHamming) { kfMatch[bestIdx] = i; nmatches++; }
     }
     return nmatches;
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (ORBmatcher.cc:1293-1497): the map points of each key frame are
+// searched in the other one (window around the Sim3 projection, [level - 1, level], best distance <= TH_HIGH) and a pair is
+// kept when both directions agree (:1483-1494).  Each direction is the Fuse search without gates and with TH_HIGH.
+// valid1[i1] = pKF1's feature has a map point that is not bad and not matched yet, depth >= 0 in camera 2; uv12 / dist12 /
+// level12 = its projection into image 2; likewise valid2 / uv21 / ... ; match12[i1] = feature of key frame 2 or -1.
+int mo_search_by_sim3(const void* k1v, const uint8_t* d1, int n1, const void* k2v, const uint8_t* d2, int n2,
+                      const float* scaleFactors, int minX, int minY, int maxX, int maxY, const uint8_t* valid1, const float* uv12,
+                      const float* dist12, const float* min1, const float* max1, const int32_t* level12, const uint8_t* valid2,
+                      const float* uv21, const float* dist21, const float* min2, const float* max2, const int32_t* level21,
+                      float th, int32_t* match12) {
+    std::vector<float> zeroSigma(64, 0.0f), noRight1(n1 > 0 ? n1 : 1, -1.0f), noRight2(n2 > 0 ? n2 : 1, -1.0f);
+    std::vector<float> ur1(n1 > 0 ? n1 : 1, 0.0f), ur2(n2 > 0 ? n2 : 1, 0.0f);
+    std::vector<int32_t> vnMatch1(n1 > 0 ? n1 : 1), vnMatch2(n2 > 0 ? n2 : 1), dd1(n1 > 0 ? n1 : 1), dd2(n2 > 0 ? n2 : 1);
+    mo_fuse_search(k2v, d2, n2, scaleFactors, zeroSigma.data(), minX, minY, maxX, maxY, noRight2.data(), valid1, uv12, ur1.data(),
+                   dist12, min1, max1, level12, d1, n1, th, TH_HIGH, vnMatch1.data(), dd1.data());
+    mo_fuse_search(k1v, d1, n1, scaleFactors, zeroSigma.data(), minX, minY, maxX, maxY, noRight1.data(), valid2, uv21, ur2.data(),
+                   dist21, min2, max2, level21, d2, n2, th, TH_HIGH, vnMatch2.data(), dd2.data());
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        match12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+    }
+    return nFound;
 }
 
 // CloudMerging.cc:503-551 for one matched key-frame pair: per key point of key frame 1 the nearest key point of key

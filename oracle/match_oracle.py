@@ -153,7 +153,7 @@ def search_by_projection_kf(kC, dC, scale_factors, bounds, valid, uv, dist3d, mi
 
 
 def fuse_search(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, valid, uv, ur, dist3d, min_dist, max_dist, level, dMP,
-                th=3.0):
+                th=3.0, th_dist=50):
     """Matching core of ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:1015-1147): (nFused, bestIdx, bestDist)."""
     kK = np.ascontiguousarray(kK, KP_DTYPE)
     dK, dMP = _u8(dK).reshape(-1, 32), _u8(dMP).reshape(-1, 32)
@@ -161,11 +161,11 @@ def fuse_search(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, valid,
     bi, bd = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
     L = lib()
     L.mo_fuse_search.argtypes = [C.c_void_p, _u8p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p, _f32p,
-                                 _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, C.c_int, C.c_float, _i32p, _i32p]
+                                 _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, C.c_int, C.c_float, C.c_int, _i32p, _i32p]
     nf = L.mo_fuse_search(kK.ctypes.data, _p(dK, _u8p), len(kK), _p(_f32(scale_factors), _f32p), _p(_f32(inv_level_sigma2), _f32p),
                           *[int(b) for b in bounds], _p(_f32(u_right), _f32p), _p(_u8(valid), _u8p), _p(_f32(uv), _f32p),
                           _p(_f32(ur), _f32p), _p(_f32(dist3d), _f32p), _p(_f32(min_dist), _f32p), _p(_f32(max_dist), _f32p),
-                          _p(np.ascontiguousarray(level, np.int32), _i32p), _p(dMP, _u8p), n, float(th), _p(bi, _i32p), _p(bd, _i32p))
+                          _p(np.ascontiguousarray(level, np.int32), _i32p), _p(dMP, _u8p), n, float(th), int(th_dist), _p(bi, _i32p), _p(bd, _i32p))
     return nf, bi[:n], bd[:n]
 
 
@@ -185,6 +185,24 @@ def search_by_projection_sim3(kK, dK, scale_factors, bounds, occupied, valid, uv
                                        _p(np.ascontiguousarray(level, np.int32), _i32p), _p(dMP, _u8p), len(dMP), int(th),
                                        float(ratio_hamming), _p(out, _i32p))
     return n, out[:len(kK)]
+
+
+def search_by_sim3(k1, d1, k2, d2, scale_factors, bounds, valid1, uv12, dist12, min1, max1, level12, valid2, uv21, dist21, min2,
+                   max2, level21, th=7.5):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1293-1497): (nFound, match12[i1] = feature of key frame 2 or -1)."""
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    d1, d2 = _u8(d1).reshape(-1, 32), _u8(d2).reshape(-1, 32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    out = np.zeros(max(len(k1), 1), np.int32)
+    L = lib()
+    L.mo_search_by_sim3.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _u8p, _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_float, _i32p]
+    n = L.mo_search_by_sim3(k1.ctypes.data, _p(d1, _u8p), len(k1), k2.ctypes.data, _p(d2, _u8p), len(k2), _p(_f32(scale_factors), _f32p),
+                            *[int(b) for b in bounds], _p(_u8(valid1), _u8p), _p(_f32(uv12), _f32p), _p(_f32(dist12), _f32p),
+                            _p(_f32(min1), _f32p), _p(_f32(max1), _f32p), _p(i32(level12), _i32p), _p(_u8(valid2), _u8p),
+                            _p(_f32(uv21), _f32p), _p(_f32(dist21), _f32p), _p(_f32(min2), _f32p), _p(_f32(max2), _f32p),
+                            _p(i32(level21), _i32p), float(th), _p(out, _i32p))
+    return n, out[:len(k1)]
 
 
 def associate_pixels(k1, valid1, k2, valid2, bounds, tol=3.0):

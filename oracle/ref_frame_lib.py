@@ -300,3 +300,27 @@ def fuse_sim3(kK, dK, scale_factors, bounds, occupied, state, already_at, uv, de
     L.ref_fuse_sim3.argtypes = types + [C.c_float, _i32p, _f32p]
     n = L.ref_fuse_sim3(*args, float(th), _p(out, _i32p), _p(d3, _f32p))
     return n, out[:len(keep[2])], d3[:len(keep[2])]
+
+
+def search_by_sim3(k1, d1, k2, d2, scale_factors, bounds, state1, pre_match1, uv12, depth1, min1, max1, level12, state2, uv21,
+                   depth2, min2, max2, level21, th=7.5):
+    """The reference's ORBmatcher::SearchBySim3 over identity poses and a unit pinhole: (nFound, match12, dist12, dist21) --
+    the dist arrays are the |p3Dc| norms the function compared with the invariance windows."""
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    d1, d2 = u8(d1).reshape(-1, 32), u8(d2).reshape(-1, 32)
+    sf = f32(scale_factors)
+    out = np.zeros(max(len(k1), 1), np.int32)
+    q12, q21 = np.zeros(max(len(k1), 1), np.float32), np.zeros(max(len(k2), 1), np.float32)
+    L = lib()
+    L.ref_search_by_sim3.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, _u8p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, _u8p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, _f32p, _f32p, _f32p, _f32p, _i32p,
+                                     C.c_float, _i32p, _f32p, _f32p]
+    n = L.ref_search_by_sim3(k1.ctypes.data, _p(d1, _u8p), len(k1), k2.ctypes.data, _p(d2, _u8p), len(k2), _p(sf, _f32p), len(sf),
+                             *[int(b) for b in bounds], _p(u8(state1), _u8p), _p(i32(pre_match1), _i32p), _p(f32(uv12), _f32p),
+                             _p(f32(depth1), _f32p), _p(f32(min1), _f32p), _p(f32(max1), _f32p), _p(i32(level12), _i32p),
+                             _p(u8(state2), _u8p), _p(f32(uv21), _f32p), _p(f32(depth2), _f32p), _p(f32(min2), _f32p),
+                             _p(f32(max2), _f32p), _p(i32(level21), _i32p), float(th), _p(out, _i32p), _p(q12, _f32p), _p(q21, _f32p))
+    return n, out[:len(k1)], q12[:len(k1)], q21[:len(k2)]

@@ -14,6 +14,7 @@
 //   ORBmatcher::Fuse (KeyFrame, MapPoints) + KeyFrame::GetFeaturesInArea / IsInImage   ORBmatcher.cc:1015-1181, KeyFrame.cc:887-930
 //   ORBmatcher::SearchForTriangulation   ORBmatcher.cc:806-1013 (epipolarConstrain = a table look-up stand-in)
 //   ORBmatcher::SearchByProjection (KeyFrame, Sim3, ...) x 2 and ORBmatcher::Fuse (KeyFrame, Sim3, ...)   :372-580, :1182-1292
+//   ORBmatcher::SearchBySim3   :1293-1497
 //     (these take poses and a camera model: Sophus::SE3f / Eigen::Vector3f / GeometricCamera are minimal stand-ins
 //      below -- identity rotation, so that "Tcw * x3Dw" is exact -- and the pin covers everything AFTER the projection,
 //      which is what the flattened adapters take over; the projection itself stays with the caller's own Sophus / camera)
@@ -76,6 +77,8 @@ struct Sim3 {                                   // identity rotation, translatio
     Eigen::Matrix3f rotationMatrix() const { Eigen::Matrix3f r = {{1, 0, 0, 0, 1, 0, 0, 0, 1}}; return r; }
     Eigen::Vector3f translation() const { return t; }
     T scale() const { return s; }
+    Sim3 inverse() const { Sim3 r; r.t = Eigen::Vector3f(-t.v[0], -t.v[1], -t.v[2]); return r; }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return Eigen::Vector3f(p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]); }
 };
 typedef Sim3<float> Sim3f;
 }  // namespace Sophus
@@ -121,6 +124,8 @@ public:
     int PredictScale(const float&, KeyFrame*) { return mnTrackScaleLevel; }
     Eigen::Vector3f GetNormal() { return mNormal; }
     bool IsInKeyFrame(KeyFrame*) { return mbInKF; }
+    std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { return std::make_tuple(mnIndexInOther, -1); }
+    int mnIndexInOther = -1;
     void Replace(MapPoint* other);                                             // Fuse: logged, the map is not edited
     void AddObservation(KeyFrame*, int idx);
     Eigen::Vector3f mNormal;
@@ -222,6 +227,7 @@ public:
                            std::vector<KeyFrame*>& vpMatchedKF, int th, float ratioHamming = 1.0);
     int Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, float th,
              vector<MapPoint*>& vpReplacePoint);
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12, const float th);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<pair<size_t, size_t>>& vMatchedPairs,
                                const bool bOnlyStereo, const bool bCoarse = false);
     static const int TH_LOW;
@@ -709,6 +715,68 @@ int ref_fuse_sim3(const void* kK, const uint8_t* dK, int nK, const float* scaleF
         if (added || replaced) bestIdx[i] = g_fuseLog[e++].second;
     }
     return e == g_fuseLog.size() ? nFused : -1000;
+}
+
+}  // extern "C"
+
+namespace {
+void fill_sim3_kf(KeyFrame& kf, Frame& F, const void* k, const uint8_t* d, int n, const float* scaleFactors, int nlevels, int minX,
+                  int minY, int maxX, int maxY) {
+    F.N = n; F.mvKeysUn = keys(k, n); F.mvKeys = F.mvKeysUn;
+    F.AssignFeaturesToGrid();
+    kf.N = n; kf.mvKeysUn = F.mvKeysUn; kf.mvKeys = F.mvKeysUn; kf.mDescriptors = rows32(d, n);
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    kf.mnMinX = minX; kf.mnMinY = minY; kf.mnMaxX = maxX; kf.mnMaxY = maxY;
+    kf.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) kf.mGrid[i][j] = F.mGrid[i][j];
+}
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (ORBmatcher.cc:1293-1497) with identity poses / Sim3 and
+// fx = fy = 1, cx = cy = 0: the map point of feature i of key frame A sits at (u * z, v * z, z) so that it projects to the
+// prescribed pixel (u, v) of the other image.  state*[i]: 0 no map point, 1 usable, 2 bad; preMatch1[i1] = -2 none, else
+// vpMatches12[i1] holds a point whose index in pKF2 is preMatch1[i1] (-1: not observed there).
+// match12[i1] = feature of key frame 2 whose map point the call stored in vpMatches12[i1], or -1.
+int ref_search_by_sim3(const void* k1, const uint8_t* d1, int n1, const void* k2, const uint8_t* d2, int n2, const float* scaleFactors,
+                       int nlevels, int minX, int minY, int maxX, int maxY, const uint8_t* state1, const int32_t* preMatch1,
+                       const float* uv12, const float* depth1, const float* min1, const float* max1, const int32_t* level12,
+                       const uint8_t* state2, const float* uv21, const float* depth2, const float* min2, const float* max2,
+                       const int32_t* level21, float th, int32_t* match12, float* dist12, float* dist21) {
+    set_grid(minX, minY, maxX, maxY);
+    Frame F1, F2;
+    KeyFrame kf1, kf2;
+    fill_sim3_kf(kf1, F1, k1, d1, n1, scaleFactors, nlevels, minX, minY, maxX, maxY);
+    fill_sim3_kf(kf2, F2, k2, d2, n2, scaleFactors, nlevels, minX, minY, maxX, maxY);
+    std::vector<MapPoint> mp1(n1), mp2(n2), pre(n1);
+    auto points = [](KeyFrame& kf, std::vector<MapPoint>& mp, const uint8_t* desc, int n, const uint8_t* state, const float* uv,
+                     const float* depth, const float* mn, const float* mx, const int32_t* level, float* dist) {
+        kf.mvpMapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; ++i) {
+            const float z = depth[i];
+            mp[i].mWorldPos = Eigen::Vector3f(uv[2 * i] * z, uv[2 * i + 1] * z, z);
+            mp[i].mDescriptor = rows32(desc + 32 * (size_t)i, 1);
+            mp[i].mnTrackScaleLevel = level[i];
+            mp[i].mfMinDistance = mn[i]; mp[i].mfMaxDistance = mx[i];
+            mp[i].mbBad = state[i] == 2;
+            if (state[i]) kf.mvpMapPoints[i] = &mp[i];
+            dist[i] = mp[i].mWorldPos.norm();
+        }
+    };
+    points(kf1, mp1, d1, n1, state1, uv12, depth1, min1, max1, level12, dist12);
+    points(kf2, mp2, d2, n2, state2, uv21, depth2, min2, max2, level21, dist21);
+    std::vector<MapPoint*> vpMatches12(n1, nullptr);
+    for (int i = 0; i < n1; ++i)
+        if (preMatch1[i] > -2) { pre[i].mnIndexInOther = preMatch1[i]; vpMatches12[i] = &pre[i]; }
+    const std::vector<MapPoint*> before = vpMatches12;
+    Sophus::Sim3f S12;
+    ORBmatcher m(0.6f, true);
+    const int n = m.SearchBySim3(&kf1, &kf2, vpMatches12, S12, th);
+    for (int i = 0; i < n1; ++i) match12[i] = vpMatches12[i] != before[i] ? (int)(vpMatches12[i] - mp2.data()) : -1;
+    return n;
 }
 
 }  // extern "C"

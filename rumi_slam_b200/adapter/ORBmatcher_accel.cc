@@ -649,7 +649,8 @@ int ORBmatcherAccel::FuseSearch(const std::vector<cv::KeyPoint>& keysK, const cv
                                 const std::vector<cv::Point2f>& uv, const std::vector<float>& ur,
                                 const std::vector<float>& dist3D, const std::vector<float>& minDistance,
                                 const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel,
-                                const cv::Mat& descMP, float th, std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+                                const cv::Mat& descMP, float th, std::vector<int>& bestIdx, std::vector<int>& bestDist,
+                                int thDist) {
     const int nMPs = (int)uv.size();
     bestIdx.assign(nMPs, -1);
     bestDist.assign(nMPs, 256);
@@ -696,7 +697,7 @@ int ORBmatcherAccel::FuseSearch(const std::vector<cv::KeyPoint>& keysK, const cv
     int nFused = 0;
     for (int q = 0; q < nq; ++q) {
         bestDist[query[q]] = d1[q];
-        if (d1[q] <= TH_LOW) { bestIdx[query[q]] = i1[q]; nFused++; }
+        if (d1[q] <= thDist) { bestIdx[query[q]] = i1[q]; nFused++; }
     }
     return nFused;
 }
@@ -706,11 +707,33 @@ int ORBmatcherAccel::FuseSearchSim3(const std::vector<cv::KeyPoint>& keysK, cons
                                     const std::vector<cv::Point2f>& uv, const std::vector<float>& dist3D,
                                     const std::vector<float>& minDistance, const std::vector<float>& maxDistance,
                                     const std::vector<int>& predictedLevel, const cv::Mat& descMP, float th,
-                                    std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+                                    std::vector<int>& bestIdx, std::vector<int>& bestDist, int thDist) {
     // zero inverse sigma and "no right coordinate" switch the chi-square gates of FuseSearch off (0 > 5.99 never holds)
     const std::vector<float> zeroSigma(scaleFactors.size(), 0.0f), noRight(keysK.size(), -1.0f), ur(uv.size(), 0.0f);
     return FuseSearch(keysK, descK, gridK, scaleFactors, zeroSigma, noRight, valid, uv, ur, dist3D, minDistance, maxDistance,
-                      predictedLevel, descMP, th, bestIdx, bestDist);
+                      predictedLevel, descMP, th, bestIdx, bestDist, thDist);
+}
+
+int ORBmatcherAccel::SearchBySim3(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1, const FrameGridAccel& grid1,
+                                  const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2, const FrameGridAccel& grid2,
+                                  const std::vector<float>& scaleFactors1, const std::vector<float>& scaleFactors2,
+                                  const std::vector<uint8_t>& valid1, const std::vector<cv::Point2f>& uv12,
+                                  const std::vector<float>& dist12, const std::vector<float>& min1,
+                                  const std::vector<float>& max1, const std::vector<int>& level12,
+                                  const std::vector<uint8_t>& valid2, const std::vector<cv::Point2f>& uv21,
+                                  const std::vector<float>& dist21, const std::vector<float>& min2,
+                                  const std::vector<float>& max2, const std::vector<int>& level21, float th,
+                                  std::vector<int>& match12) {
+    std::vector<int> vnMatch1, vnMatch2, dd;
+    FuseSearchSim3(keys2, desc2, grid2, scaleFactors2, valid1, uv12, dist12, min1, max1, level12, desc1, th, vnMatch1, dd, TH_HIGH);
+    FuseSearchSim3(keys1, desc1, grid1, scaleFactors1, valid2, uv21, dist21, min2, max2, level21, desc2, th, vnMatch2, dd, TH_HIGH);
+    match12.assign(keys1.size(), -1);
+    int nFound = 0;
+    for (size_t i1 = 0; i1 < keys1.size(); i1++) {                                // :1483-1494
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == (int)i1) { match12[i1] = idx2; nFound++; }
+    }
+    return nFound;
 }
 
 int ORBmatcherAccel::SearchByProjectionSim3(const std::vector<cv::KeyPoint>& keysK, const cv::Mat& descK,

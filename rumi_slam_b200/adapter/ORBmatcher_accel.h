@@ -172,7 +172,7 @@ public:
                    const std::vector<float>& uRight, const std::vector<uint8_t>& valid, const std::vector<cv::Point2f>& uv,
                    const std::vector<float>& ur, const std::vector<float>& dist3D, const std::vector<float>& minDistance,
                    const std::vector<float>& maxDistance, const std::vector<int>& predictedLevel, const cv::Mat& descMP,
-                   float th, std::vector<int>& bestIdx, std::vector<int>& bestDist);
+                   float th, std::vector<int>& bestIdx, std::vector<int>& bestDist, int thDist = TH_LOW);
 
     // Matching core of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (R/lib_src/ORBmatcher.cc:1182-1292, LoopClosing):
     // FuseSearch without the reprojection gates.  The caller fills vpReplacePoint / AddObservation from bestIdx (:1268-1280).
@@ -181,7 +181,21 @@ public:
                        const std::vector<cv::Point2f>& uv, const std::vector<float>& dist3D,
                        const std::vector<float>& minDistance, const std::vector<float>& maxDistance,
                        const std::vector<int>& predictedLevel, const cv::Mat& descMP, float th, std::vector<int>& bestIdx,
-                       std::vector<int>& bestDist);
+                       std::vector<int>& bestDist, int thDist = TH_LOW);
+
+    // ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (R/lib_src/ORBmatcher.cc:1293-1497), LoopClosing.  valid1[i1] =
+    // feature i1 of pKF1 has a map point that is not bad and not matched yet (vbAlreadyMatched1), depth >= 0 in camera 2;
+    // uv12 / dist12 / level12 = its projection into image 2, |p3Dc2| against [min1, max1], PredictScale (:1336-1365); the *2 /
+    // *21 arguments likewise for pKF2's points in image 1 (valid2 excludes vbAlreadyMatched2).  Each direction is the gate-free
+    // fuse search with TH_HIGH; match12[i1] = feature of pKF2 when both directions agree (:1483-1494), else -1.
+    int SearchBySim3(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1, const FrameGridAccel& grid1,
+                     const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2, const FrameGridAccel& grid2,
+                     const std::vector<float>& scaleFactors1, const std::vector<float>& scaleFactors2,
+                     const std::vector<uint8_t>& valid1, const std::vector<cv::Point2f>& uv12, const std::vector<float>& dist12,
+                     const std::vector<float>& min1, const std::vector<float>& max1, const std::vector<int>& level12,
+                     const std::vector<uint8_t>& valid2, const std::vector<cv::Point2f>& uv21, const std::vector<float>& dist21,
+                     const std::vector<float>& min2, const std::vector<float>& max2, const std::vector<int>& level21, float th,
+                     std::vector<int>& match12);
 
     // ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (R/lib_src/ORBmatcher.cc:372-471) and its
     // overload with vpPointsKFs / vpMatchedKF (:473-580), the matchers of LoopClosing (same search).  valid[i] = not bad, not in

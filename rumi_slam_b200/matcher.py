@@ -413,7 +413,7 @@ class ORBmatcher:
 
     # ---- ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = false) (ORBmatcher.cc:1015-1181): the matching core ----
     def FuseSearch(self, keysK, descK, scale_factors, inv_level_sigma2, bounds, u_right, valid, uv, ur, dist3d, min_dist,
-                   max_dist, level, descMP, th=3.0):
+                   max_dist, level, descMP, th=3.0, th_dist=None):
         """The matcher of LocalMapping::SearchInNeighbors up to the fuse decision (:1147).  Per map point i: valid[i] =
         present, not bad, not already in pKF, depth >= 0, viewing-angle test passed; uv[i] = projection into pKF, ur[i] =
         uv.x - bf * invz; dist3d[i] against [min_dist, max_dist]; level[i] = PredictScale.  Key frame: mvKeysUn, mDescriptors,
@@ -449,18 +449,35 @@ class ORBmatcher:
         _, (i1, d1, _, _) = self.candidates(np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)[q], descK, off2, idx[keep], top2=True)
         best_idx, best_dist = np.full(n, -1, np.int32), np.full(n, 256, np.int32)
         best_dist[q] = d1
-        fused = d1 <= self.TH_LOW
+        fused = d1 <= (self.TH_LOW if th_dist is None else th_dist)
         best_idx[q[fused]] = i1[fused]
         return int(fused.sum()), best_idx, best_dist
 
-    def FuseSearchSim3(self, keysK, descK, scale_factors, bounds, valid, uv, dist3d, min_dist, max_dist, level, descMP, th=3.0):
+    def FuseSearchSim3(self, keysK, descK, scale_factors, bounds, valid, uv, dist3d, min_dist, max_dist, level, descMP, th=3.0,
+                       th_dist=None):
         """Matching core of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1182-1292, LoopClosing):
         FuseSearch without the reprojection gates.  valid[i] = not bad, not already a map point of pKF, depth >= 0,
         viewing-angle test passed.  The caller fills vpReplacePoint / AddObservation from best_idx (:1268-1280)."""
         n, k = len(np.asarray(uv).reshape(-1, 2)), len(keysK)
         return self.FuseSearch(keysK, descK, scale_factors, np.zeros(len(scale_factors), np.float32), bounds,
                                np.full(k, -1.0, np.float32), valid, uv, np.zeros(n, np.float32), dist3d, min_dist, max_dist, level,
-                               descMP, th)
+                               descMP, th, th_dist)
+
+    # ---- ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (ORBmatcher.cc:1293-1497) ----
+    def SearchBySim3(self, keys1, desc1, keys2, desc2, scale_factors, bounds, valid1, uv12, dist12, min1, max1, level12, valid2,
+                     uv21, dist21, min2, max2, level21, th=7.5):
+        """LoopClosing's Sim3-guided matcher.  valid1[i1] = feature i1 of pKF1 has a map point that is not bad and not matched
+        yet (vbAlreadyMatched1), depth >= 0 in camera 2; uv12 / dist12 / level12 = its projection into image 2, |p3Dc2| against
+        [min1, max1], PredictScale; the *2 / *21 arguments likewise for pKF2's points in image 1 (valid2 excludes
+        vbAlreadyMatched2).  Both key frames share scale factors and image bounds.  Each direction is the gate-free fuse search
+        with TH_HIGH; a pair is kept when both directions agree (:1483-1494).  Returns (nFound, match12)."""
+        _, vn1, _ = self.FuseSearchSim3(keys2, desc2, scale_factors, bounds, valid1, uv12, dist12, min1, max1, level12, desc1, th,
+                                        self.TH_HIGH)
+        _, vn2, _ = self.FuseSearchSim3(keys1, desc1, scale_factors, bounds, valid2, uv21, dist21, min2, max2, level21, desc2, th,
+                                        self.TH_HIGH)
+        i1 = np.arange(len(vn1))
+        ok = (vn1 >= 0) & (vn2[np.maximum(vn1, 0)] == i1)
+        return int(ok.sum()), np.where(ok, vn1, -1).astype(np.int32)
 
     # ---- ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming) ----
     def SearchByProjectionSim3(self, keysK, descK, scale_factors, bounds, occupied, valid, uv, dist3d, min_dist, max_dist, level,

@@ -169,6 +169,21 @@ int main(int argc, char** argv) {
             std::fwrite(&ns, 4, 1, f); std::fwrite(&nfs, 4, 1, f);
             std::fwrite(kmS.data(), 4, kmS.size(), f);
             std::fwrite(fIdxS.data(), 4, fIdxS.size(), f);
+            // SearchBySim3 between the right image and itself shifted: points of "key frame 1" (= right image) project half a
+            // pixel off their own key point in "key frame 2" (= right image) and vice versa -> mutual matches
+            std::vector<uint8_t> v1S(nR), v2S(nR);
+            std::vector<cv::Point2f> uv1S(nR), uv2S(nR);
+            std::vector<int> lvS(nR);
+            for (int i = 0; i < nR; ++i) {
+                v1S[i] = i % 4 != 0; v2S[i] = i % 5 != 0; lvS[i] = R.keys[i].octave;
+                uv1S[i] = cv::Point2f(R.keys[i].pt.x + 0.5f, R.keys[i].pt.y - 0.5f);
+                uv2S[i] = cv::Point2f(R.keys[i].pt.x - 0.25f, R.keys[i].pt.y + 0.25f);
+            }
+            std::vector<int> m12S;
+            const int nsim = mi.SearchBySim3(R.keys, R.desc, grid, R.keys, R.desc, grid, sf, sf, v1S, uv1S, d3F, dminF, dmaxF, lvS, v2S,
+                                             uv2S, d3F, dminF, dmaxF, lvS, 7.5f, m12S);
+            std::fwrite(&nsim, 4, 1, f);
+            std::fwrite(m12S.data(), 4, m12S.size(), f);
         }
         // the empty-image contract of operator() (ORBextractor.cc:1017)
         cv::Mat empty; Result E;

@@ -147,3 +147,11 @@ def test_stereo_frame_through_cpp_adapter(oracle, driver, tmp_path):
                                    ii % 9 != 0, uv_f, zeros, d3_f, zeros, big, rk["octave"][j], rd[j], 4.0)
     assert ns == rn5 and np.array_equal(km_s, rkm5) and rn5 > 100
     assert nfs == rn6 and np.array_equal(f_idx_s, rbest6) and rn6 > 300
+    # ORBmatcherAccel::SearchBySim3 (right image against itself, half-pixel offsets), executed in C++
+    nsim = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    m12s = np.frombuffer(buf, np.int32, nR, off); off += 4 * nR
+    uv1 = np.stack([rk["x"] + np.float32(0.5), rk["y"] - np.float32(0.5)], 1).astype(np.float32)
+    uv2 = np.stack([rk["x"] - np.float32(0.25), rk["y"] + np.float32(0.25)], 1).astype(np.float32)
+    rn7, rm7 = M.search_by_sim3(rk, rd, rk, rd, sf, (0, 0, 752, 480), ir % 4 != 0, uv1, d3_f, zeros, big, rk["octave"], ir % 5 != 0,
+                                uv2, d3_f, zeros, big, rk["octave"], 7.5)
+    assert nsim == rn7 and np.array_equal(m12s, rm7) and rn7 > 300

@@ -150,6 +150,29 @@ def test_fuse_search_matches_oracle(oracle, M, seed, th, stereo):
     assert rn > 40
 
 
+@pytest.mark.parametrize("seed,th", [(71, 7.5), (72, 3.0)])
+def test_search_by_sim3_matches_oracle(oracle, M, seed, th):
+    """ORBmatcher::SearchBySim3 (R/lib_src/ORBmatcher.cc:1293-1497); oracle pinned in tests/test_ref_frame_pin.py."""
+    from rumi_slam_b200 import ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed + 400)
+    f32 = np.float32
+
+    def side(ka, dx, dy):
+        n = len(ka)
+        uv = (np.stack([ka["x"] + dx, ka["y"] + dy], 1).astype(f32) + rng.normal(0, 0.8, (n, 2)).astype(f32))
+        uv[rng.random(n) < 0.03] += f32(700.0)
+        level = np.clip(ka["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+        dist = rng.uniform(1.0, 100.0, n).astype(f32)
+        mn = rng.uniform(0.0, 20.0, n).astype(f32)
+        return rng.random(n) < 0.8, uv, dist, mn, (mn + rng.uniform(10.0, 500.0, n)).astype(f32), level
+    a, b = side(k1, -3.0, 2.0), side(k2, 3.0, -2.0)
+    sf = oracle.tables()["scale"]
+    n, m = ORBmatcher().SearchBySim3(k1, d1, k2, d2, sf, (0, 0, 640, 480), *a, *b, th)
+    rn, rm = M.search_by_sim3(k1, d1, k2, d2, sf, (0, 0, 640, 480), *a, *b, th)
+    assert n == rn and np.array_equal(m, rm) and rn > 30
+
+
 @pytest.mark.parametrize("seed,th,ratio", [(51, 3, 1.0), (53, 10, 0.8), (54, 30, 1.5)])
 def test_sim3_matchers_match_oracle(oracle, M, seed, th, ratio):
     """ORBmatcher::SearchByProjection(pKF, Scw, ...) (R/lib_src/ORBmatcher.cc:372-580) and Fuse(pKF, Scw, ...) (:1182-1292); the

@@ -375,3 +375,44 @@ def test_fuse_sim3_equals_reference(oracle, rf, M, seed, th):
                                (state == 1) & ~(depth < 0), uv, np.zeros(n1, np.float32), dist3d, min_d, max_d, level, d1, th)
     assert rn >= 0 and n == rn and np.array_equal(best, rbest)
     assert rn > 50
+
+
+def _sim3_pair_case(oracle, seed):
+    """Two key frames of a loop: frame 1 / frame 2 of a known image motion; every feature's map point projects into the other
+    image where the feature moved (+ noise); depths are powers of two (see _sim3_case)."""
+    k1, d1, k2, d2 = _frame_pair(oracle, seed)
+    rng = np.random.default_rng(seed + 400)
+    f32 = np.float32
+
+    def side(ka, dx, dy):
+        n = len(ka)
+        uv = (np.stack([ka["x"] + dx, ka["y"] + dy], 1).astype(f32) + rng.normal(0, 0.8, (n, 2)).astype(f32))
+        uv[rng.random(n) < 0.03] += f32(700.0)
+        depth = rng.choice([0.5, 1.0, 2.0, 4.0, 8.0, -1.0], n, p=[0.2, 0.2, 0.2, 0.2, 0.17, 0.03]).astype(f32)
+        state = rng.choice([0, 1, 1, 1, 1, 1, 2], n).astype(np.uint8)
+        level = np.clip(ka["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+        mn = rng.uniform(0.0, 50.0, n).astype(f32)
+        mx = (mn + rng.uniform(100.0, 5000.0, n)).astype(f32)
+        return uv, depth, state, level, mn, mx
+    s1, s2 = side(k1, -3.0, 2.0), side(k2, 3.0, -2.0)
+    pre = np.full(len(k1), -2, np.int32)                              # vpMatches12 on entry
+    some = rng.random(len(k1)) < 0.1
+    pre[some] = rng.integers(-1, len(k2), int(some.sum()))
+    return k1, d1, k2, d2, s1, s2, pre
+
+
+@pytest.mark.parametrize("seed,th", [(71, 7.5), (72, 3.0), (73, 15.0)])
+def test_search_by_sim3_equals_reference(oracle, rf, M, seed, th):
+    """ORBmatcher::SearchBySim3 (R/lib_src/ORBmatcher.cc:1293-1497): both search directions, 'already matched' features on
+    both sides, TH_HIGH, and the mutual-agreement test."""
+    k1, d1, k2, d2, (uv12, z1, st1, lv12, mn1, mx1), (uv21, z2, st2, lv21, mn2, mx2), pre = _sim3_pair_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    rn, rm, q12, q21 = rf.search_by_sim3(k1, d1, k2, d2, sf, (0, 0, 640, 480), st1, pre, uv12, z1, mn1, mx1, lv12, st2, uv21, z2,
+                                         mn2, mx2, lv21, th)
+    matched2 = np.zeros(len(k2), bool)
+    matched2[pre[pre >= 0]] = True
+    v1 = (st1 == 1) & (pre == -2) & ~(z1 < 0)
+    v2 = (st2 == 1) & ~matched2 & ~(z2 < 0)
+    n, m = M.search_by_sim3(k1, d1, k2, d2, sf, (0, 0, 640, 480), v1, uv12, q12, mn1, mx1, lv12, v2, uv21, q21, mn2, mx2, lv21, th)
+    assert n == rn and np.array_equal(m, rm)
+    assert rn > 30

@@ -78,6 +78,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     uint8_t *pyr = nullptr, *blur = nullptr;
     uint32_t *cand = nullptr, *candOrdered = nullptr, *sel = nullptr;
+    int *countBase = nullptr;           // [chunk] frameDone counters followed by levelCount: ONE memset clears both
     int *levelCount = nullptr, *cellOff = nullptr, *cellCount = nullptr, *selCount = nullptr, *slot = nullptr;
     uint64_t* bigKeys = nullptr;
     KeyPointRec* kps = nullptr;
@@ -129,6 +130,9 @@ struct rumi_orb {
     // [0] a TMA transaction of the tile pyramid timed out, [1] a pyramid level dependency timed out
     int* errHost = nullptr; int* errDev = nullptr;
     uint8_t* descBuf = nullptr; size_t descCap = 0;   // scratch of rumi_orb_describe* (images, keypoints, descriptors)
+    cudaStream_t auxStream = nullptr;                      // small calls: blur runs here, beside FAST / quad-tree / slots
+    cudaEvent_t evFork = nullptr, evJoinAux = nullptr;
+    uint8_t* outStage = nullptr; size_t outStageCap = 0;   // pinned: results of the single-frame call land here with ONE sync
     uint8_t* dbgBuf = nullptr;     // test hook: FAST tile dump
     long long* octClk = nullptr;   // profiling hook: octree phase cycle counters
     int dbgCell = 0;
@@ -149,7 +153,7 @@ namespace {
 
 void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
-    cudaFree(w.levelCount); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
+    cudaFree(w.countBase); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
     cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono);
     cudaStream_t s = w.stream;
     w = Workspace();
@@ -174,7 +178,8 @@ int alloc_workspace(rumi_orb* h, Workspace& w) {
     CU_TRY(cudaMalloc(&w.cand, 4 * h->candElems));
     CU_TRY(cudaMalloc(&w.candOrdered, 4 * h->candElems));
     CU_TRY(cudaMalloc(&w.bigKeys, 8 * h->bigKeysElems));
-    CU_TRY(cudaMalloc(&w.levelCount, 4 * n * oc.nlevels));
+    CU_TRY(cudaMalloc(&w.countBase, 4 * n * (oc.nlevels + 1)));
+    w.levelCount = w.countBase + n;
     CU_TRY(cudaMalloc(&w.selCount, 4 * n * oc.nlevels));
     CU_TRY(cudaMalloc(&w.cellOff, 4 * n * oc.totalCells));
     CU_TRY(cudaMalloc(&w.cellCount, 4 * n * oc.totalCells));
@@ -500,7 +505,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         cv.src[l] = l == 0 ? l0 : internal_view(h, w.pyr, l);
         cv.blur[l] = internal_view(h, w.blur, l);
     }
-    if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.levelCount, 0, 4ull * n * oc.nlevels, s));
+    if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.countBase, 0, 4ull * (h->chunk + (size_t)n * oc.nlevels), s));
     if (h->profile) prof_event(h, s);
     // K1: all levels in ONE launch (a CTA carries a strip of a frame through every level in shared memory) when every
     // source row can be read as aligned 32-bit words: always true for the internal buffers, caller device memory only if
@@ -561,16 +566,40 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         oa.bigKeysLevelOff[l] = h->bigKeysLevelOff[l];
         oa.bigKeysCap[l] = h->bigKeysCap[l];
     }
+    // Calls of a few frames leave most SMs idle and are bound by the latency of the dependent launches: the blur needs
+    // only the pyramid, so it runs on a second stream beside FAST -> quad-tree -> slots and joins before the descriptors
+    // (single frame: 17 us off the critical path).  Large chunks fill the GPU on their own.
+    const bool fork = n <= 4 && !h->profile && !(skip & 16) && getenv("RUMI_NO_FORK") == nullptr;
+    if (fork) {
+        if (!h->auxStream) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->auxStream, cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&h->evJoinAux, cudaEventDisableTiming));
+        }
+        CU_TRY(cudaEventRecord(h->evFork, s));
+        CU_TRY(cudaStreamWaitEvent(h->auxStream, h->evFork, 0));
+        launch_blur(cv, oc, h->auxStream);
+        CU_TRY(cudaEventRecord(h->evJoinAux, h->auxStream));
+    }
     if (!(skip & 2)) launch_fast(fa, oc, s);
     prof_mark(h, s, ST_FAST, 1);
-    if (!(skip & 4)) launch_octree(oa, oc, sh);
-    prof_mark(h, s, ST_OCTREE, 1);
     DescribeArgs da;
     da.cv = cv; da.sel = w.sel; da.selCount = w.selCount; da.lap0 = lap0; da.lap1 = lap1; da.slot = w.slot;
     da.kps = dKps; da.desc = dDesc; da.nkp = dNkp; da.nmono = dNmono; da.outCap = outCap;
-    launch_assign_slots(da, oc, sh);
-    prof_mark(h, s, ST_SLOTS, 1);
-    if (!(skip & 16)) launch_blur(cv, oc, s);
+    // the slot assignment rides in the tail of the quad-tree kernel (last CTA of a frame) unless that kernel is skipped,
+    // split per level, or RUMI_SLOTS_KERNEL=1 asks for the stand-alone launch (A/B runs)
+    static const bool slotsKernel = getenv("RUMI_SLOTS_KERNEL") != nullptr || getenv("RUMI_OCTREE_SPLIT") != nullptr;
+    const bool fuse = !(skip & 4) && !slotsKernel;
+    oa.fuseSlots = fuse ? 1 : 0;
+    oa.frameDone = w.countBase;
+    oa.slots.sel = w.sel; oa.slots.selCount = w.selCount; oa.slots.lap0 = lap0; oa.slots.lap1 = lap1; oa.slots.slot = w.slot;
+    oa.slots.nkp = dNkp; oa.slots.nmono = dNmono;
+    if (!(skip & 4)) launch_octree(oa, oc, sh);
+    prof_mark(h, s, ST_OCTREE, 1);
+    if (!fuse) launch_assign_slots(da, oc, sh);
+    prof_mark(h, s, ST_SLOTS, fuse ? 0 : 1);
+    if (fork) CU_TRY(cudaStreamWaitEvent(s, h->evJoinAux, 0));
+    else if (!(skip & 16)) launch_blur(cv, oc, s);
     prof_mark(h, s, ST_BLUR, 1);
     if (!(skip & 32)) launch_describe(da, oc, s);
     prof_mark(h, s, ST_DESCRIBE, 1);
@@ -658,6 +687,10 @@ void rumi_orb_destroy(rumi_orb* h) {
     cudaFree(h->dbgBuf);
     cudaFree(h->octClk);
     cudaFree(h->descBuf);
+    if (h->outStage) cudaFreeHost(h->outStage);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoinAux) cudaEventDestroy(h->evJoinAux);
+    if (h->auxStream) cudaStreamDestroy(h->auxStream);
     if (h->errHost) cudaFreeHost(h->errHost);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->evStart) cudaEventDestroy(h->evStart);
@@ -784,17 +817,32 @@ int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t st
     if ((rc = upload_level0(h, ws, img, 1, stride, stride * (size_t)h_px))) return rc;
     const LevelView l0 = internal_view(h, ws.pyr, 0);
     if ((rc = run_chunk(h, ws, l0, true, 1, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
-    int counts[2];
+    // Results: counts, key points and descriptors of the whole frame capacity (60 KB) go to a pinned staging block with four
+    // back-to-back asynchronous copies and ONE synchronisation; the rows in use are then copied to the caller's (possibly
+    // pageable) buffers on the host.  (Was: two count copies, a sync, then two synchronous copies -- three round trips; the
+    // single-frame latency is dominated by such fixed costs, 120 us of kernels in a 213 us call.)
+    const size_t kpBytes = sizeof(rumi_kp) * (size_t)oc.kpCap, dBytes = 32 * (size_t)oc.kpCap, need = 64 + kpBytes + dBytes;
+    if (need > h->outStageCap) {
+        if (h->outStage) cudaFreeHost(h->outStage);
+        h->outStage = nullptr; h->outStageCap = 0;
+        CU_TRY(cudaHostAlloc((void**)&h->outStage, need, cudaHostAllocDefault));
+        h->outStageCap = need;
+    }
+    int* counts = reinterpret_cast<int*>(h->outStage);
+    uint8_t* sKps = h->outStage + 64;
+    uint8_t* sDesc = sKps + kpBytes;
     CU_TRY(cudaMemcpyAsync(&counts[0], ws.nkp, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaMemcpyAsync(&counts[1], ws.nmono, 4, cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(cudaMemcpyAsync(sKps, ws.kps, kpBytes, cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(cudaMemcpyAsync(sDesc, ws.desc, dBytes, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaStreamSynchronize(ws.stream));
     if ((rc = check_device_flags(h))) return rc;
     *n_kp = counts[0]; *n_mono = counts[1];
     const int m = std::min(counts[0], cap);
     if (m > 0) {
         if (!kps || !desc) return fail(RUMI_ERR_ARG, "kps/desc NULL");
-        CU_TRY(cudaMemcpy(kps, ws.kps, sizeof(rumi_kp) * (size_t)m, cudaMemcpyDeviceToHost));
-        CU_TRY(cudaMemcpy(desc, ws.desc, 32 * (size_t)m, cudaMemcpyDeviceToHost));
+        std::memcpy(kps, sKps, sizeof(rumi_kp) * (size_t)m);
+        std::memcpy(desc, sDesc, 32 * (size_t)m);
     }
     h->lastWs = 0;
     return RUMI_OK;

@@ -8,6 +8,7 @@
 // blurred level.  Float32 steps use explicit round-to-nearest mul/add (no FMA) and glibc's sinf/cosf algorithm so
 // that sample coordinates round exactly as on the reference's x86-64 build.
 #include "kernels.cuh"
+#include "slots.cuh"
 #include "orb_math.cuh"
 
 namespace rumi {
@@ -29,57 +30,15 @@ __device__ __forceinline__ int round_half_even(float v) {
     return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
 }
 
-__global__ void __launch_bounds__(256) assign_slots_kernel(const __grid_constant__ DescribeArgs a,
+__global__ void __launch_bounds__(256) assign_slots_kernel(const __grid_constant__ SlotArgs a,
                                                            const __grid_constant__ OrbConst oc) {
-    __shared__ int s_part[257];
-    __shared__ int s_lvlBase[kMaxLevels + 1];
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const int* selCount = a.selCount + (long long)f * oc.nlevels;
-    if (tid == 0) {
-        int n = 0;
-        for (int l = 0; l < oc.nlevels; ++l) { s_lvlBase[l] = n; n += selCount[l]; }
-        s_lvlBase[oc.nlevels] = n;
-    }
-    __syncthreads();
-    const int nkp = s_lvlBase[oc.nlevels];
-    // thread t owns a contiguous run of the concatenated level-ordered keypoints
-    const int chunk = (nkp + 255) / 256;
-    const int i0 = min(tid * chunk, nkp), i1 = min(i0 + chunk, nkp);
-    const uint32_t* sel = a.sel + (long long)f * oc.kpCap;
-    auto lapping = [&](int i, int& slotIdx) {
-        int l = 0;
-        while (i >= s_lvlBase[l + 1]) ++l;
-        slotIdx = oc.lv[l].kpBase + (i - s_lvlBase[l]);
-        const uint32_t c = sel[slotIdx];
-        float x = (float)(cand_x(c) + kMinBorder);
-        if (l != 0) x = __fmul_rn(x, oc.lv[l].scale);                 // keypoint->pt *= scale  (:1073-1075)
-        return x >= (float)a.lap0 && x <= (float)a.lap1;              // (:1077)
-    };
-    int nlap = 0;
-    for (int i = i0; i < i1; ++i) { int s; nlap += lapping(i, s) ? 1 : 0; }
-    s_part[tid] = nlap;
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int t = 0; t < 256; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
-        s_part[256] = run;
-        a.nkp[f] = nkp;
-        a.nmono[f] = nkp - run;
-    }
-    __syncthreads();
-    int lapBefore = s_part[tid];
-    int* slot = a.slot + (long long)f * oc.kpCap;
-    for (int i = i0; i < i1; ++i) {
-        int s;
-        const bool lp = lapping(i, s);
-        // lapping keypoints fill from the back, the others from the front, both in level order
-        slot[s] = lp ? (nkp - 1 - lapBefore) : (i - lapBefore);
-        lapBefore += lp ? 1 : 0;
-    }
+    assign_slots_frame(a, oc, blockIdx.x, threadIdx.x);
 }
 
 void launch_assign_slots(const DescribeArgs& a, const OrbConst& oc, cudaStream_t s) {
-    assign_slots_kernel<<<a.cv.nframes, 256, 0, s>>>(a, oc);
+    SlotArgs sa;
+    sa.sel = a.sel; sa.selCount = a.selCount; sa.lap0 = a.lap0; sa.lap1 = a.lap1; sa.slot = a.slot; sa.nkp = a.nkp; sa.nmono = a.nmono;
+    assign_slots_kernel<<<a.cv.nframes, 256, 0, s>>>(sa, oc);
 }
 
 // 512 rotated samples -> 32 bytes; lane = byte index.  `center` points at the keypoint in the (blurred) image.

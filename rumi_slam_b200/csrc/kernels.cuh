@@ -96,6 +96,14 @@ struct FastArgs {
 };
 void launch_fast(const FastArgs& a, const OrbConst& oc, cudaStream_t s);
 
+// ORBextractor::operator() output order (:1077-1085): what the slot assignment of one frame needs
+struct SlotArgs {
+    const uint32_t* sel; const int* selCount;      // [frame][kpCap], [frame][nlevels]
+    int lap0, lap1;
+    int* slot;                                     // [frame][kpCap] output slot of each level-ordered keypoint
+    int* nkp; int* nmono;                          // [frame]
+};
+
 struct OctreeArgs {
     int nframes;
     const uint32_t* cand;    // as written by FAST
@@ -111,6 +119,11 @@ struct OctreeArgs {
     int levelFirst;          // level of blockIdx.y == 0 (0 unless the launch is split per level)
     int smemKeys;            // keys that fit the shared-memory sort buffer
     int maxNodeCap;
+    // fused slot assignment: the LAST level CTA of a frame to finish (frameDone counter) assigns the output slots of that
+    // frame, which saves the separate one-CTA-per-frame launch (fuseSlots = 0: launch_assign_slots runs instead)
+    int fuseSlots;
+    int* frameDone;          // [frame], zeroed per call
+    SlotArgs slots;
 };
 void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s);
 size_t octree_smem_bytes(int smemKeys, int maxNodeCap, int nthreads);

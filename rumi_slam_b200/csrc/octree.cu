@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include "slots.cuh"
 #include "octree_core.cuh"
 
 namespace rumi {
@@ -383,6 +384,16 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
     if (ctx.clk && threadIdx.x == 0) { ctx.clk[12] = M; ctx.clk[13] = w.scal[SC_NOUT]; ctx.clk[14] += w.scal[SC_NREPLAY]; }
     __syncthreads();
     if (threadIdx.x == 0) a.selCount[(long long)f * oc.nlevels + l] = min(w.scal[SC_NOUT], slots);
+    if (!a.fuseSlots) return;
+    // ---- the last level CTA of this frame assigns the output slots (every CTA publishes its selection first) ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.frameDone + f, 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    assign_slots_frame(a.slots, oc, f, threadIdx.x);
 }
 
 void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {

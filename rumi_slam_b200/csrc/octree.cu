@@ -398,11 +398,8 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
 
 void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
     const size_t smem = octree_smem_bytes(a.smemKeys, a.maxNodeCap, kOctThreads);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    // per device and cheap: set on every launch rather than cached in a process-wide flag (a process may drive several GPUs)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     static int split = -1;                      // RUMI_OCTREE_SPLIT=1: one launch per level (per-level timing under ncu)
     if (split < 0) { const char* e = getenv("RUMI_OCTREE_SPLIT"); split = e && e[0] == '1'; }
     if (split) {

@@ -621,19 +621,19 @@ def run_b200(args):
         m.launch_count(reset=True)
 
     # ---- configs[2] / [3]: stereo frames.  Per pair, as Frame::Frame does (Frame.cc:116-119, 828-985): the left and the
-    #      right extractor run in two host threads on two handles, then ComputeStereoMatches on the device-resident
+    #      right extractor run on two handles with both frames in flight, then ComputeStereoMatches on the device-resident
     #      pyramids.  Host images in, mvKeys / descriptors / mvuRight / mvDepth out: an end-to-end figure. ----
     def stereo_row(name, w, h, nf, fx, bf, npairs, unique):
-        from concurrent.futures import ThreadPoolExecutor
         pairs = [stereo_pair(100 * rank + s, w, h) for s in range(unique)]
         exl, exr = ORBextractor(nf, 1.2, 8, 20, 7, device=local), ORBextractor(nf, 1.2, 8, 20, 7, device=local)
         ms_ = ORBmatcher(device=local)
-        pool = ThreadPoolExecutor(max_workers=2)
 
         def one(i):
+            # both frames are put in flight from this thread (rumi_orb_extract_begin x 2), then collected: the GPU-side
+            # equivalent of the two std::threads of Frame::Frame
             left, right = pairs[i % unique]
-            fl, fr = pool.submit(exl, left), pool.submit(exr, right)
-            (_, lk, ld), (_, rk, rd) = fl.result(), fr.result()
+            exl.begin(left); exr.begin(right)
+            (_, lk, ld), (_, rk, rd) = exl.end(), exr.end()
             u, d, n = ms_.stereo_match(exl, exr, lk, ld, rk, rd, bf, bf / fx)
             return lk, ld, rk, rd, u, d, n
         for i in range(8):
@@ -649,7 +649,7 @@ def run_b200(args):
         barrier()
         windows.append((t0, time.perf_counter()))
         row = {"workload": "%s: %d synthetic %dx%d stereo pairs per GPU, %d features per image, left + right extraction "
-                           "(two handles, two host threads) + Frame::ComputeStereoMatches; host images in, results out"
+                           "(two handles, both frames in flight from one host thread) + Frame::ComputeStereoMatches; host images in, results out"
                            % (name, npairs, w, h, nf),
                "pairs_per_s": world * npairs / dt, "frames_per_s": 2 * world * npairs / dt, "ms_per_pair": 1e3 * dt / npairs,
                "mean_stereo_matches": nm / float(npairs),
@@ -678,7 +678,7 @@ def run_b200(args):
                 row["cpu_baseline"] = {"value": nsamp / dtc, "unit": "pairs/s", "cores": cores,
                                        "kind": cpu.kind + " extraction + port of ComputeStereoMatches",
                                        "sample": "%d of the same pairs on %d host threads (%.1f s)" % (nsamp, cores, dtc)}
-        exl.close(); exr.close(); ms_.close(); pool.shutdown()
+        exl.close(); exr.close(); ms_.close()
         return row
 
     stereo = {}

@@ -83,6 +83,14 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
 int rumi_orb_wait_stream(rumi_orb* h, void* stream);
 int rumi_orb_signal_stream(rumi_orb* h, void* stream);
 
+/* The same call in two halves, for callers that run several extractors from ONE host thread (the reference starts two
+ * std::threads for the left and the right image of a stereo frame, R/lib_src/Frame.cc:116-119, because its extraction is CPU
+ * bound; on the GPU the two frames only have to be IN FLIGHT together): _begin enqueues upload, kernels and the download
+ * into the handle's pinned staging block and returns without waiting; _end waits and fills the outputs exactly like
+ * rumi_orb_extract.  One frame in flight per handle. */
+int rumi_orb_extract_begin(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1);
+int rumi_orb_extract_end(rumi_orb* h, rumi_kp* kps, uint8_t* desc, int cap, int* n_kp, int* n_mono);
+
 /* ORBextractor::CloudFrameComputeDescriptors(image, keypoints, descriptors)   R/lib_src/ORBextractor.cc:989-1011
  * HOST pointers.  Returns n (like the reference) or an error code. */
 int rumi_orb_describe(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, const rumi_kp* kps, int n,

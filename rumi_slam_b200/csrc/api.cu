@@ -130,6 +130,7 @@ struct rumi_orb {
     // [0] a TMA transaction of the tile pyramid timed out, [1] a pyramid level dependency timed out
     int* errHost = nullptr; int* errDev = nullptr;
     uint8_t* descBuf = nullptr; size_t descCap = 0;   // scratch of rumi_orb_describe* (images, keypoints, descriptors)
+    bool pendingSingle = false;                            // rumi_orb_extract_begin issued, _end not yet called
     cudaStream_t auxStream = nullptr;                      // small calls: blur runs here, beside FAST / quad-tree / slots
     cudaEvent_t evFork = nullptr, evJoinAux = nullptr;
     uint8_t* outStage = nullptr; size_t outStageCap = 0;   // pinned: results of the single-frame call land here with ONE sync
@@ -803,11 +804,10 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
     return check_device_flags(h);
 }
 
-int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1,
-                     rumi_kp* kps, uint8_t* desc, int cap, int* n_kp, int* n_mono) {
+int rumi_orb_extract_begin(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1) {
     if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
     if (!img || w <= 0 || h_px <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
-    if (!n_kp || !n_mono || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad output / stride");
+    if (stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad stride");
     CU_TRY(cudaSetDevice(h->device));
     int rc = ensure_geometry(h, w, h_px);
     if (rc) return rc;
@@ -818,9 +818,9 @@ int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t st
     const LevelView l0 = internal_view(h, ws.pyr, 0);
     if ((rc = run_chunk(h, ws, l0, true, 1, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
     // Results: counts, key points and descriptors of the whole frame capacity (60 KB) go to a pinned staging block with four
-    // back-to-back asynchronous copies and ONE synchronisation; the rows in use are then copied to the caller's (possibly
-    // pageable) buffers on the host.  (Was: two count copies, a sync, then two synchronous copies -- three round trips; the
-    // single-frame latency is dominated by such fixed costs, 120 us of kernels in a 213 us call.)
+    // back-to-back asynchronous copies; rumi_orb_extract_end synchronises ONCE and copies the rows in use to the caller's
+    // (possibly pageable) buffers on the host.  (Was: two count copies, a sync, then two synchronous copies -- three round
+    // trips; the single-frame latency is dominated by such fixed costs, 120 us of kernels in a 213 us call.)
     const size_t kpBytes = sizeof(rumi_kp) * (size_t)oc.kpCap, dBytes = 32 * (size_t)oc.kpCap, need = 64 + kpBytes + dBytes;
     if (need > h->outStageCap) {
         if (h->outStage) cudaFreeHost(h->outStage);
@@ -830,13 +830,28 @@ int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t st
     }
     int* counts = reinterpret_cast<int*>(h->outStage);
     uint8_t* sKps = h->outStage + 64;
-    uint8_t* sDesc = sKps + kpBytes;
     CU_TRY(cudaMemcpyAsync(&counts[0], ws.nkp, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaMemcpyAsync(&counts[1], ws.nmono, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaMemcpyAsync(sKps, ws.kps, kpBytes, cudaMemcpyDeviceToHost, ws.stream));
-    CU_TRY(cudaMemcpyAsync(sDesc, ws.desc, dBytes, cudaMemcpyDeviceToHost, ws.stream));
-    CU_TRY(cudaStreamSynchronize(ws.stream));
-    if ((rc = check_device_flags(h))) return rc;
+    CU_TRY(cudaMemcpyAsync(sKps + kpBytes, ws.desc, dBytes, cudaMemcpyDeviceToHost, ws.stream));
+    h->pendingSingle = true;
+    h->lastWs = 0;
+    return RUMI_OK;
+}
+
+int rumi_orb_extract_end(rumi_orb* h, rumi_kp* kps, uint8_t* desc, int cap, int* n_kp, int* n_mono) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    if (!n_kp || !n_mono) return fail(RUMI_ERR_ARG, "bad output");
+    if (!h->pendingSingle) return fail(RUMI_ERR_ARG, "rumi_orb_extract_end without rumi_orb_extract_begin");
+    h->pendingSingle = false;
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->ws[0].stream));
+    int rc = check_device_flags(h);
+    if (rc) return rc;
+    const OrbConst& oc = h->oc;
+    const int* counts = reinterpret_cast<const int*>(h->outStage);
+    const uint8_t* sKps = h->outStage + 64;
+    const uint8_t* sDesc = sKps + sizeof(rumi_kp) * (size_t)oc.kpCap;
     *n_kp = counts[0]; *n_mono = counts[1];
     const int m = std::min(counts[0], cap);
     if (m > 0) {
@@ -844,8 +859,15 @@ int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t st
         std::memcpy(kps, sKps, sizeof(rumi_kp) * (size_t)m);
         std::memcpy(desc, sDesc, 32 * (size_t)m);
     }
-    h->lastWs = 0;
     return RUMI_OK;
+}
+
+int rumi_orb_extract(rumi_orb* h, const uint8_t* img, int w, int h_px, size_t stride, int lap0, int lap1,
+                     rumi_kp* kps, uint8_t* desc, int cap, int* n_kp, int* n_mono) {
+    if (!n_kp || !n_mono) return fail(RUMI_ERR_ARG, "bad output / stride");
+    const int rc = rumi_orb_extract_begin(h, img, w, h_px, stride, lap0, lap1);
+    if (rc) return rc;
+    return rumi_orb_extract_end(h, kps, desc, cap, n_kp, n_mono);
 }
 
 int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int w, int h_px, size_t stride,

@@ -85,6 +85,29 @@ class ORBextractor:
         self._last_shape = (h, w)
         return m.value, kps[:n.value], desc[:n.value]
 
+    def begin(self, image, vLappingArea=(0, 0)):
+        """First half of __call__: enqueues the frame and returns at once (rumi_orb_extract_begin).  Lets ONE host thread
+        keep several extractors busy (left / right image of a stereo frame); finish with end()."""
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.size, "CV_8UC1 expected"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        self._pending = (image, h, w)                 # the upload reads the image until end()
+        check(self._L.rumi_orb_extract_begin(self._h, ptr(image), w, h, image.strides[0], int(vLappingArea[0]),
+                                             int(vLappingArea[1])))
+
+    def end(self):
+        """Second half of __call__: waits for the frame of begin() and returns (monoIndex, keypoints, descriptors)."""
+        _, h, w = self._pending
+        self._pending = None
+        cap = self.frame_capacity(w, h)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, m = C.c_int32(0), C.c_int32(0)
+        check(self._L.rumi_orb_extract_end(self._h, ptr(kps), ptr(desc), cap, C.byref(n), C.byref(m)))
+        self._last_shape = (h, w)
+        return m.value, kps[:n.value], desc[:n.value]
+
     def extract_batch(self, images, vLappingArea=(0, 0), out=None):
         """images: [n,h,w] uint8 HOST array (pinned memory makes the copies asynchronous).
         Returns (kps[n,cap], desc[n,cap,32], n_kp[n], n_mono[n]) host arrays."""

@@ -198,3 +198,24 @@ def test_benchmark_pipeline_matches_oracle(oracle):
     for i in range(70):
         rk, rd, rm = ref2[i]
         assert n2[i] == len(rk) and m2[i] == rm and np.array_equal(k2[i, :len(rk)], rk) and np.array_equal(d2[i, :len(rk)], rd), i
+
+
+def test_begin_end_equals_call_and_two_extractors_in_flight(oracle):
+    """rumi_orb_extract_begin / _end: the same result as the one-shot call; two handles in flight from one host thread (the
+    left / right image of a stereo frame); _end without _begin is an error."""
+    from rumi_slam_b200 import ORBextractor
+    from rumi_slam_b200.synth import synthetic_frame
+    a, b = synthetic_frame(31, 752, 480), synthetic_frame(32, 752, 480)
+    exl, exr = ORBextractor(1200, 1.2, 8, 20, 7), ORBextractor(1200, 1.2, 8, 20, 7)
+    for _ in range(3):
+        exl.begin(a); exr.begin(b)
+        ml, kl, dl = exl.end()
+        mr, kr, dr = exr.end()
+        for (m, k, d), img in (((ml, kl, dl), a), ((mr, kr, dr), b)):
+            ok, od, om = oracle.extract(img, nfeatures=1200)
+            assert m == om and np.array_equal(k, ok) and np.array_equal(d, od)
+    m2, k2, d2 = exl(a)
+    assert m2 == ml and np.array_equal(k2, kl) and np.array_equal(d2, dl)
+    exl._pending = (a, 480, 752)
+    with pytest.raises(Exception):
+        exl.end()

@@ -31,20 +31,27 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 
 ORBextractor::~ORBextractor() { rumi_orb_destroy(handle); }
 
-int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
-                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
-    if (_image.empty()) return -1;                                   // :1017
-    cv::Mat image = _image.getMat();
-    assert(image.type() == CV_8UC1);                                 // :1021
-    const int cap = rumi_orb_frame_capacity(handle, image.cols, image.rows);
+bool ORBextractor::Begin(cv::InputArray _image, std::vector<int>& vLappingArea) {
+    pendingEmpty = _image.empty();
+    if (pendingEmpty) return false;                                  // :1017
+    pendingImage = _image.getMat();
+    assert(pendingImage.type() == CV_8UC1);                          // :1021
+    const int rc = rumi_orb_extract_begin(handle, pendingImage.data, pendingImage.cols, pendingImage.rows,
+                                          (size_t)pendingImage.step, vLappingArea[0], vLappingArea[1]);
+    if (rc == RUMI_ERR_EMPTY) { pendingEmpty = true; return false; }
+    if (rc != RUMI_OK) throw std::runtime_error(std::string("ORBextractor: ") + rumi_last_error());
+    return true;
+}
+
+int ORBextractor::End(std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors) {
+    if (pendingEmpty) return -1;
+    const int cap = rumi_orb_frame_capacity(handle, pendingImage.cols, pendingImage.rows);
     if (cap < 0) throw std::runtime_error(std::string("ORBextractor: ") + rumi_last_error());
     kpBuf.resize(sizeof(rumi_kp) * (size_t)cap);
     descBuf.resize(32 * (size_t)cap);
     int nkp = 0, mono = 0;
-    const int rc = rumi_orb_extract(handle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0],
-                                    vLappingArea[1], reinterpret_cast<rumi_kp*>(kpBuf.data()), descBuf.data(), cap,
-                                    &nkp, &mono);
-    if (rc == RUMI_ERR_EMPTY) return -1;
+    const int rc = rumi_orb_extract_end(handle, reinterpret_cast<rumi_kp*>(kpBuf.data()), descBuf.data(), cap, &nkp, &mono);
+    pendingImage = cv::Mat();
     if (rc != RUMI_OK) throw std::runtime_error(std::string("ORBextractor: ") + rumi_last_error());
     if (nkp == 0) {
         _descriptors.release();                                      // :1035-1036
@@ -64,6 +71,12 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, st
         }
     }
     return mono;                                                     // :1090
+}
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+    if (!Begin(_image, vLappingArea)) return -1;
+    return End(_keypoints, _descriptors);
 }
 
 int ORBextractor::CloudFrameComputeDescriptors(cv::InputArray _image, const std::vector<cv::KeyPoint>& _keypoints,

@@ -30,6 +30,12 @@ public:
     int operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
                    cv::OutputArray _descriptors, std::vector<int>& vLappingArea);
 
+    // operator() in two halves (rumi_orb_extract_begin / _end): Begin enqueues the frame and returns, End waits and fills the
+    // outputs.  Lets ONE thread keep the left and the right extractor of a stereo frame busy instead of the two std::threads
+    // of Frame::Frame (R/lib_src/Frame.cc:116-119).  Begin returns false for an empty image (End then returns -1).
+    bool Begin(cv::InputArray _image, std::vector<int>& vLappingArea);
+    int End(std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors);
+
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return scaleFactor; }
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
@@ -63,6 +69,8 @@ private:
     rumi_orb* handle;
     bool downloadPyramid;
     std::vector<unsigned char> kpBuf, descBuf;
+    cv::Mat pendingImage;                // keeps the frame of Begin alive until End
+    bool pendingEmpty = false;
 };
 
 }  // namespace ORB_SLAM3

@@ -6,8 +6,8 @@ from rumi_slam_b200.synth import synthetic_batch
 n = 1024
 host = synthetic_batch(n, 640, 480, seed0=0, unique=16)
 pinned = torch.from_numpy(host).pin_memory(); hp = pinned.numpy(); dev = pinned.cuda()
-for streams in (2, 3, 4):
-  for chunk in (32, 64):
+for streams in [int(x) for x in os.environ.get('PROBE_STREAMS', '2,3,4').split(',')]:
+  for chunk in [int(x) for x in os.environ.get('PROBE_CHUNKS', '32,64').split(',')]:
     os.environ["RUMI_STREAMS"] = str(streams)
     ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=chunk)
     cap = ex.frame_capacity(640, 480)

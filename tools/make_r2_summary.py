@@ -92,7 +92,7 @@ issuer); `pyramid_level_kernel<true>` has `UTMALDG.3D` (TMA tensor load); blur /
 
 `parity_ok` true at every N (incl. sharded == unsharded on all queries of cfg 5a and of cfg 5b).  Extraction and both matcher
 configurations scale linearly on the device; `e2e` does not: the box's host links deliver 55 GB/s to one GPU but ~23 GB/s per
-GPU when eight copy at once, so the end-to-end rate stays at 0.8-0.87 of what the host links allow at every N.
+GPU when eight copy at once, so the end-to-end rate stays at 0.77-0.87 of what the host links allow at every N.
 `tests/test_gpu_match.py -k shard` (4 tests incl. the NCCL path through `rumi_hamming_top2_sharded`) passes at N = 2.
 """
 open(P("r2_summary.md"), "w").write(md)

@@ -1156,6 +1156,7 @@ struct rumi_match {
     uint64_t* partial = nullptr; size_t partialCap = 0;
     uint8_t *dQ = nullptr, *dT = nullptr; size_t qCap = 0, tCap = 0;
     uint8_t* dOut = nullptr; size_t outCap = 0;      // idx1 (4 B) | d1 (2 B) | d2 (2 B) per query
+    uint8_t* hStage = nullptr; size_t hStageCap = 0; // pinned: inputs / results of per-frame sized calls (one round trip)
     uint8_t* tx = nullptr; size_t txCap = 0;         // train set as ready-to-load UMMA operand tiles (K8-P)
     int mode = 0;                                    // 0 auto, 1 LOP3+POPC kernel only, 3 tcgen05 UMMA only
     int lastPath = 0;                                // kernel of the last top-2 call: 1 LOP3+POPC, 3 UMMA
@@ -1174,6 +1175,19 @@ int grow(void** p, size_t* cap, size_t need) {
     *p = nullptr; *cap = 0;
     CU_TRY(cudaMalloc(p, need));
     *cap = need;
+    return RUMI_OK;
+}
+
+// Per-frame sized calls with HOST pointers are bound by round trips, not by bytes: copies from / to pageable memory are
+// synchronous, one by one (1000 x 1000 top-2: 0.10 ms for ~10 us of kernel).  Below kSmallCallBytes the arguments are packed
+// into ONE pinned block on the host, travel with asynchronous copies, and the results come back in one copy + one sync.
+constexpr size_t kSmallCallBytes = 4u << 20;
+int host_stage(rumi_match* m, size_t need) {
+    if (need <= m->hStageCap) return RUMI_OK;
+    if (m->hStage) cudaFreeHost(m->hStage);
+    m->hStage = nullptr; m->hStageCap = 0;
+    CU_TRY(cudaHostAlloc((void**)&m->hStage, need, cudaHostAllocDefault));
+    m->hStageCap = need;
     return RUMI_OK;
 }
 
@@ -1291,6 +1305,7 @@ void rumi_match_destroy(rumi_match* m) {
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
     cudaFree(m->partial); cudaFree(m->dQ); cudaFree(m->dT); cudaFree(m->dOut); cudaFree(m->tx);
     cudaFree(m->shardSend); cudaFree(m->shardRecv);
+    if (m->hStage) cudaFreeHost(m->hStage);
     if (m->comm && m->ownComm && nccl_api().ok) nccl_api().commDestroy(m->comm);
     if (m->evStart) { cudaEventDestroy(m->evStart); cudaEventDestroy(m->evStop); }
     if (m->evOrder) cudaEventDestroy(m->evOrder);
@@ -1322,8 +1337,25 @@ int rumi_hamming_top2(rumi_match* m, const uint8_t* Q, int nq, const uint8_t* T,
     int32_t* dIdx = reinterpret_cast<int32_t*>(m->dOut);
     uint16_t* dD1 = reinterpret_cast<uint16_t*>(m->dOut + 4 * (size_t)nq);
     uint16_t* dD2 = dD1 + nq;
-    CU_TRY(cudaMemcpyAsync(m->dQ, Q, 32 * (size_t)nq, cudaMemcpyHostToDevice, m->stream));
-    if (nt > 0) CU_TRY(cudaMemcpyAsync(m->dT, T, 32 * (size_t)nt, cudaMemcpyHostToDevice, m->stream));
+    const size_t qBytes = 32 * (size_t)nq, tBytes = 32 * (size_t)nt, oBytes = 8 * (size_t)nq;
+    if (qBytes + tBytes + oBytes <= kSmallCallBytes) {
+        if ((rc = host_stage(m, qBytes + tBytes + oBytes))) return rc;
+        uint8_t* hs = m->hStage;
+        std::memcpy(hs, Q, qBytes);
+        if (nt > 0) std::memcpy(hs + qBytes, T, tBytes);
+        CU_TRY(cudaMemcpyAsync(m->dQ, hs, qBytes, cudaMemcpyHostToDevice, m->stream));
+        if (nt > 0) CU_TRY(cudaMemcpyAsync(m->dT, hs + qBytes, tBytes, cudaMemcpyHostToDevice, m->stream));
+        if ((rc = top2_device(m, m->dQ, nq, m->dT, nt, 0, dIdx, dD1, dD2))) return rc;
+        uint8_t* ho = hs + qBytes + tBytes;
+        CU_TRY(cudaMemcpyAsync(ho, m->dOut, oBytes, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(cudaStreamSynchronize(m->stream));
+        std::memcpy(idx1, ho, 4 * (size_t)nq);
+        std::memcpy(d1, ho + 4 * (size_t)nq, 2 * (size_t)nq);
+        std::memcpy(d2, ho + 6 * (size_t)nq, 2 * (size_t)nq);
+        return RUMI_OK;
+    }
+    CU_TRY(cudaMemcpyAsync(m->dQ, Q, qBytes, cudaMemcpyHostToDevice, m->stream));
+    if (nt > 0) CU_TRY(cudaMemcpyAsync(m->dT, T, tBytes, cudaMemcpyHostToDevice, m->stream));
     if ((rc = top2_device(m, m->dQ, nq, m->dT, nt, 0, dIdx, dD1, dD2))) return rc;
     CU_TRY(cudaMemcpyAsync(idx1, dIdx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(d1, dD1, 2 * (size_t)nq, cudaMemcpyDeviceToHost, m->stream));
@@ -1402,10 +1434,21 @@ int rumi_hamming_candidates(rumi_match* m, const uint8_t* Q, int nq, const uint8
     if (rc) return rc;
     uint8_t* p = m->dT;
     cudaStream_t s = m->stream;
-    CU_TRY(cudaMemcpyAsync(p, Q, 32 * (size_t)nq, cudaMemcpyHostToDevice, s));
-    if (nt > 0) CU_TRY(cudaMemcpyAsync(p + oT, T, 32 * (size_t)nt, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(p + oOff, cand_off, 4 * ((size_t)nq + 1), cudaMemcpyHostToDevice, s));
-    if (ne > 0) CU_TRY(cudaMemcpyAsync(p + oIdx, cand_idx, 4 * (size_t)ne, cudaMemcpyHostToDevice, s));
+    const bool small = need <= kSmallCallBytes;          // one packed block up, one block down (see host_stage)
+    if (small) {
+        if ((rc = host_stage(m, need))) return rc;
+        uint8_t* hs = m->hStage;
+        std::memcpy(hs, Q, 32 * (size_t)nq);
+        if (nt > 0) std::memcpy(hs + oT, T, 32 * (size_t)nt);
+        std::memcpy(hs + oOff, cand_off, 4 * ((size_t)nq + 1));
+        if (ne > 0) std::memcpy(hs + oIdx, cand_idx, 4 * (size_t)ne);
+        CU_TRY(cudaMemcpyAsync(p, hs, oDist, cudaMemcpyHostToDevice, s));
+    } else {
+        CU_TRY(cudaMemcpyAsync(p, Q, 32 * (size_t)nq, cudaMemcpyHostToDevice, s));
+        if (nt > 0) CU_TRY(cudaMemcpyAsync(p + oT, T, 32 * (size_t)nt, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(p + oOff, cand_off, 4 * ((size_t)nq + 1), cudaMemcpyHostToDevice, s));
+        if (ne > 0) CU_TRY(cudaMemcpyAsync(p + oIdx, cand_idx, 4 * (size_t)ne, cudaMemcpyHostToDevice, s));
+    }
     int32_t* dI1 = reinterpret_cast<int32_t*>(p + oRes);
     int32_t* dI2 = dI1 + nq;
     uint16_t* dD1 = reinterpret_cast<uint16_t*>(dI2 + nq);
@@ -1415,6 +1458,20 @@ int rumi_hamming_candidates(rumi_match* m, const uint8_t* Q, int nq, const uint8
     m->launches += 1;
     m->lastPath = 1;
     CU_TRY(cudaGetLastError());
+    if (small) {
+        uint8_t* hs = m->hStage;
+        CU_TRY(cudaMemcpyAsync(hs + oDist, p + oDist, (top2 ? need : oRes) - oDist, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        if (ne > 0) std::memcpy(dist, hs + oDist, 2 * (size_t)ne);
+        if (top2) {
+            const uint8_t* r = hs + oRes;
+            std::memcpy(idx1, r, 4 * (size_t)nq);
+            std::memcpy(idx2, r + 4 * (size_t)nq, 4 * (size_t)nq);
+            std::memcpy(d1, r + 8 * (size_t)nq, 2 * (size_t)nq);
+            std::memcpy(d2, r + 10 * (size_t)nq, 2 * (size_t)nq);
+        }
+        return RUMI_OK;
+    }
     if (ne > 0) CU_TRY(cudaMemcpyAsync(dist, p + oDist, 2 * (size_t)ne, cudaMemcpyDeviceToHost, s));
     if (top2) {
         CU_TRY(cudaMemcpyAsync(idx1, dI1, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));

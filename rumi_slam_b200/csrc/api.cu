@@ -1676,13 +1676,31 @@ int rumi_stereo_match(rumi_match* m, rumi_orb* left, rumi_orb* right, const rumi
     // the pyramids were produced on the extractors' own streams
     CU_TRY(cudaStreamSynchronize(left->ws[left->lastWs].stream));
     CU_TRY(cudaStreamSynchronize(right->ws[right->lastWs].stream));
-    CU_TRY(cudaMemcpyAsync(dLd, Ld, 32 * (size_t)nL, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(dLk, Lk, kb * nL, cudaMemcpyHostToDevice, s));
-    if (nR > 0) {
-        CU_TRY(cudaMemcpyAsync(dRd, Rd, 32 * (size_t)nR, cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(dRk, Rk, kb * nR, cudaMemcpyHostToDevice, s));
+    // inputs (descriptors, key points, scale table) are contiguous on the device from dLd to the end of dSf, results from dU
+    // to the end of dSad: per-frame sized calls pack them into one pinned block -- one copy up, one down (see host_stage)
+    const size_t inBytes = (size_t)((uint8_t*)dBest - m->dT), outOff = (size_t)((uint8_t*)dU - m->dT),
+                 outBytes = (size_t)(p - (uint8_t*)dU);
+    const bool small = need <= kSmallCallBytes;
+    if (small) {
+        if ((rc = host_stage(m, need))) return rc;
+        uint8_t* hs = m->hStage;
+        std::memcpy(hs + ((uint8_t*)dLd - m->dT), Ld, 32 * (size_t)nL);
+        std::memcpy(hs + ((uint8_t*)dLk - m->dT), Lk, kb * nL);
+        if (nR > 0) {
+            std::memcpy(hs + ((uint8_t*)dRd - m->dT), Rd, 32 * (size_t)nR);
+            std::memcpy(hs + ((uint8_t*)dRk - m->dT), Rk, kb * nR);
+        }
+        std::memcpy(hs + ((uint8_t*)dSf - m->dT), left->tables.scale.data(), 4 * (size_t)nlevels);
+        CU_TRY(cudaMemcpyAsync(m->dT, hs, inBytes, cudaMemcpyHostToDevice, s));
+    } else {
+        CU_TRY(cudaMemcpyAsync(dLd, Ld, 32 * (size_t)nL, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(dLk, Lk, kb * nL, cudaMemcpyHostToDevice, s));
+        if (nR > 0) {
+            CU_TRY(cudaMemcpyAsync(dRd, Rd, 32 * (size_t)nR, cudaMemcpyHostToDevice, s));
+            CU_TRY(cudaMemcpyAsync(dRk, Rk, kb * nR, cudaMemcpyHostToDevice, s));
+        }
+        CU_TRY(cudaMemcpyAsync(dSf, left->tables.scale.data(), 4 * (size_t)nlevels, cudaMemcpyHostToDevice, s));
     }
-    CU_TRY(cudaMemcpyAsync(dSf, left->tables.scale.data(), 4 * (size_t)nlevels, cudaMemcpyHostToDevice, s));
     const float minD = 0.f, maxD = mbf / mb;                                   // Frame.cc:856-858
     launch_stereo_best1(dLk, dLd, nL, dRk, dRd, nR, dSf, left->H, minD, maxD, dBest, dDist, s);
     StereoRefineArgs ra;
@@ -1698,10 +1716,19 @@ int rumi_stereo_match(rumi_match* m, rumi_orb* left, rumi_orb* right, const rumi
     m->launches += 2;
     CU_TRY(cudaGetLastError());
     std::vector<int> sad(nL);
-    CU_TRY(cudaMemcpyAsync(u_right, dU, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(depth, dD, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(sad.data(), dSad, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
+    if (small) {
+        uint8_t* ho = m->hStage + outOff;
+        CU_TRY(cudaMemcpyAsync(ho, dU, outBytes, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        std::memcpy(u_right, ho, 4 * (size_t)nL);
+        std::memcpy(depth, ho + ((uint8_t*)dD - (uint8_t*)dU), 4 * (size_t)nL);
+        std::memcpy(sad.data(), ho + ((uint8_t*)dSad - (uint8_t*)dU), 4 * (size_t)nL);
+    } else {
+        CU_TRY(cudaMemcpyAsync(u_right, dU, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(depth, dD, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(sad.data(), dSad, 4 * (size_t)nL, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+    }
     // median-based outlier cut (Frame.cc:973-984): sequential host logic, kept as in the reference
     std::vector<std::pair<int, int>> vDistIdx;
     for (int i = 0; i < nL; ++i)

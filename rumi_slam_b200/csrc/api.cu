@@ -1771,6 +1771,8 @@ struct rumi_vocab {
     rumi::BowTreeView view;
     uint8_t* scratch = nullptr;        // host-call staging: descriptors + outputs
     size_t scratchCap = 0;
+    uint8_t* hStage = nullptr;         // pinned mirror of `scratch` for per-frame sized calls (one copy up, one down)
+    size_t hStageCap = 0;
     cudaEvent_t evOrder = nullptr;
     long long launches = 0;
 };
@@ -1843,6 +1845,7 @@ void rumi_vocab_destroy(rumi_vocab* v) {
     cudaSetDevice(v->device);
     if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
     cudaFree(v->blob); cudaFree(v->scratch);
+    if (v->hStage) cudaFreeHost(v->hStage);
     if (v->evOrder) cudaEventDestroy(v->evOrder);
     delete v;
 }
@@ -1898,6 +1901,23 @@ int rumi_bow_transform(rumi_vocab* v, const uint8_t* desc, int n, int levelsup, 
     double* dW = reinterpret_cast<double*>(v->scratch + oW);
     int32_t* dWord = reinterpret_cast<int32_t*>(v->scratch + oWord);
     int32_t* dNode = reinterpret_cast<int32_t*>(v->scratch + oNode);
+    if (need <= kSmallCallBytes) {                       // Frame::ComputeBoW of one frame: one round trip (see host_stage)
+        if (need > v->hStageCap) {
+            if (v->hStage) cudaFreeHost(v->hStage);
+            v->hStage = nullptr; v->hStageCap = 0;
+            CU_TRY(cudaHostAlloc((void**)&v->hStage, need, cudaHostAllocDefault));
+            v->hStageCap = need;
+        }
+        std::memcpy(v->hStage, desc, 32 * (size_t)n);
+        CU_TRY(cudaMemcpyAsync(v->scratch, v->hStage, 32 * (size_t)n, cudaMemcpyHostToDevice, v->stream));
+        if ((rc = rumi_bow_transform_device(v, v->scratch, n, levelsup, dWord, dW, dNode, 0))) return rc;
+        CU_TRY(cudaMemcpyAsync(v->hStage + oW, v->scratch + oW, need - oW, cudaMemcpyDeviceToHost, v->stream));
+        CU_TRY(cudaStreamSynchronize(v->stream));
+        std::memcpy(weight, v->hStage + oW, 8 * (size_t)n);
+        std::memcpy(word_id, v->hStage + oWord, 4 * (size_t)n);
+        std::memcpy(node_id, v->hStage + oNode, 4 * (size_t)n);
+        return RUMI_OK;
+    }
     CU_TRY(cudaMemcpyAsync(v->scratch, desc, 32 * (size_t)n, cudaMemcpyHostToDevice, v->stream));
     if ((rc = rumi_bow_transform_device(v, v->scratch, n, levelsup, dWord, dW, dNode, 0))) return rc;
     CU_TRY(cudaMemcpyAsync(word_id, dWord, 4 * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
@@ -1931,16 +1951,34 @@ int rumi_bow_node_distances(rumi_match* m, const uint8_t* descA, int nA, const u
     int rc = grow((void**)&m->dT, &m->tCap, need);
     if (rc) return rc;
     uint8_t* p = m->dT;
+    const bool small = need <= kSmallCallBytes;          // one key-frame pair: one copy up, one down (see host_stage)
+    if (small) {
+        if ((rc = host_stage(m, need))) return rc;
+        uint8_t* hs = m->hStage;
+        std::memcpy(hs, descA, 32 * (size_t)nA);
+        std::memcpy(hs + oB, descB, 32 * (size_t)nB);
+        std::memcpy(hs + oAi, a_idx, 4 * (size_t)n_a_idx);
+        std::memcpy(hs + oBi, b_idx, 4 * (size_t)n_b_idx);
+        std::memcpy(hs + oSeg, segs, 20 * (size_t)nseg);
+        CU_TRY(cudaMemcpyAsync(p, hs, oDist, cudaMemcpyHostToDevice, m->stream));
+    } else {
     CU_TRY(cudaMemcpyAsync(p, descA, 32 * (size_t)nA, cudaMemcpyHostToDevice, m->stream));
     CU_TRY(cudaMemcpyAsync(p + oB, descB, 32 * (size_t)nB, cudaMemcpyHostToDevice, m->stream));
     CU_TRY(cudaMemcpyAsync(p + oAi, a_idx, 4 * (size_t)n_a_idx, cudaMemcpyHostToDevice, m->stream));
     CU_TRY(cudaMemcpyAsync(p + oBi, b_idx, 4 * (size_t)n_b_idx, cudaMemcpyHostToDevice, m->stream));
     CU_TRY(cudaMemcpyAsync(p + oSeg, segs, 20 * (size_t)nseg, cudaMemcpyHostToDevice, m->stream));
+    }
     launch_bow_node_distances(p, p + oB, reinterpret_cast<const int32_t*>(p + oAi), reinterpret_cast<const int32_t*>(p + oBi),
                               reinterpret_cast<const BowSegment*>(p + oSeg), nseg, reinterpret_cast<uint16_t*>(p + oDist),
                               m->stream);
     m->launches += 1;
     CU_TRY(cudaGetLastError());
+    if (small) {
+        CU_TRY(cudaMemcpyAsync(m->hStage + oDist, p + oDist, 2 * (size_t)ndist, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(cudaStreamSynchronize(m->stream));
+        std::memcpy(dist, m->hStage + oDist, 2 * (size_t)ndist);
+        return RUMI_OK;
+    }
     CU_TRY(cudaMemcpyAsync(dist, p + oDist, 2 * (size_t)ndist, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
     return RUMI_OK;

@@ -570,7 +570,8 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     // Calls of a few frames leave most SMs idle and are bound by the latency of the dependent launches: the blur needs
     // only the pyramid, so it runs on a second stream beside FAST -> quad-tree -> slots and joins before the descriptors
     // (single frame: 17 us off the critical path).  Large chunks fill the GPU on their own.
-    const bool fork = n <= 4 && !h->profile && !(skip & 16) && getenv("RUMI_NO_FORK") == nullptr;
+    static const int forkMax = getenv("RUMI_FORK_MAX") ? atoi(getenv("RUMI_FORK_MAX")) : 4;
+    const bool fork = n <= forkMax && !h->profile && !(skip & 16) && getenv("RUMI_NO_FORK") == nullptr;
     if (fork) {
         if (!h->auxStream) {
             CU_TRY(cudaStreamCreateWithFlags(&h->auxStream, cudaStreamNonBlocking));

@@ -259,3 +259,38 @@ def test_associate_submap_40_plus_40_keyframes(oracle, M):
         agree += int((px[both] == want[both]).sum())
     assert total > 40 * 100 and pix > 40 * 100
     assert agree > 0.6 * pix                                  # same physical points found by descriptors alone
+
+
+def test_projection_matchers_edge_cases(oracle, M):
+    """No usable map point, projections outside the image, an empty current frame: every projection matcher returns 0
+    matches and all -1, like the reference loops that `continue` on every point."""
+    from rumi_slam_b200 import KP_DTYPE, ORBmatcher
+    k1, d1, k2, d2 = frame_pair(oracle, 5)
+    n1, n2 = len(k1), len(k2)
+    f32 = np.float32
+    sf = oracle.tables()["scale"]
+    uv = np.stack([k1["x"], k1["y"]], 1).astype(f32)
+    ones, zeros = np.ones(n1, f32), np.zeros(n1, f32)
+    big = np.full(n1, 1e9, f32)
+    m = ORBmatcher(0.9, True)
+    none = np.zeros(n1, bool)
+    outside = uv + f32(5000.0)
+    for valid, pts in ((none, uv), (~none, outside)):
+        n, cm = m.SearchByProjectionLastFrame(k2, d2, sf, (0, 0, 640, 480), valid, pts, ones, k1["octave"], k1["angle"], d1, ~none)
+        assert n == 0 and np.all(cm == -1)
+        n, cm = m.SearchByProjectionKeyFrame(k2, d2, sf, (0, 0, 640, 480), valid, pts, ones, zeros, big, k1["octave"], k1["angle"], d1)
+        assert n == 0 and np.all(cm == -1)
+        n, km = m.SearchByProjectionSim3(k2, d2, sf, (0, 0, 640, 480), np.zeros(n2, bool), valid, pts, ones, zeros, big, k1["octave"], d1)
+        assert n == 0 and np.all(km == -1)
+        n, best, bd = m.FuseSearchSim3(k2, d2, sf, (0, 0, 640, 480), valid, pts, ones, zeros, big, k1["octave"], d1)
+        assert n == 0 and np.all(best == -1) and np.all(bd == 256)
+    # every feature of the current frame already taken
+    n, cm = m.SearchByProjectionKeyFrame(k2, d2, sf, (0, 0, 640, 480), ~none, uv, ones, zeros, big, k1["octave"], k1["angle"], d1,
+                                         occupied=np.ones(n2, bool))
+    assert n == 0 and np.all(cm == -1)
+    # an empty current frame / key frame
+    e_k, e_d = np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+    n, cm = m.SearchByProjectionLastFrame(e_k, e_d, sf, (0, 0, 640, 480), ~none, uv, ones, k1["octave"], k1["angle"], d1, ~none)
+    assert n == 0 and len(cm) == 0
+    n, best, bd = m.FuseSearchSim3(e_k, e_d, sf, (0, 0, 640, 480), ~none, uv, ones, zeros, big, k1["octave"], d1)
+    assert n == 0 and np.all(best == -1)

@@ -24,7 +24,7 @@ for n in (1, 2, 4, 8):
         big["ms_per_step"], big["pairs_per_s"]))
 md = f"""# Round 2 -- final state (B200, one GPU unless stated)
 
-Everything here comes from `tools/r2_profile_all.sh` on the final code (GPU tests 147 passed / 1 skipped, smoke ok, then bench,
+Everything here comes from `tools/r2_profile_all.sh` on the final code (GPU tests 148 passed / 1 skipped, smoke ok, then bench,
 reference arm and the ncu passes) and, for section 5, from `bench.py --gpus N` under torchrun.  Bench numbers are never taken
 under ncu.  (This file is generated: `python tools/make_r2_summary.py`.)
 

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rumi_orb.h"
@@ -88,6 +89,10 @@ struct Workspace {
     bool tmapOk[kMaxLevels];
     int lastFrames = 0;
     bool ready = false;                // every buffer above is allocated
+    // pinned staging of the PAGEABLE host batch path (images in, results out) + "results landed" event
+    uint8_t *hIn = nullptr, *hOut = nullptr;
+    size_t hInCap = 0, hOutCap = 0;
+    cudaEvent_t evOut = nullptr;
 };
 
 }  // namespace
@@ -156,6 +161,9 @@ void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
     cudaFree(w.countBase); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
     cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono);
+    if (w.hIn) cudaFreeHost(w.hIn);
+    if (w.hOut) cudaFreeHost(w.hOut);
+    if (w.evOut) cudaEventDestroy(w.evOut);
     cudaStream_t s = w.stream;
     w = Workspace();
     w.stream = s;
@@ -726,6 +734,113 @@ int rumi_orb_frame_capacity(rumi_orb* h, int w, int h_px) {
     return oc.kpCap;
 }
 
+namespace {
+// memcpy with several host threads: one thread moves ~10 GB/s, the host links take 55 GB/s
+void parallel_copy(void* dst, const void* src, size_t bytes, int nthreads) {
+    if (bytes < (4u << 20) || nthreads <= 1) { std::memcpy(dst, src, bytes); return; }
+    const size_t slice = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) {
+        const size_t o = slice * t;
+        if (o >= bytes) break;
+        pool.emplace_back([=] { std::memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, std::min(slice, bytes - o)); });
+    }
+    std::memcpy(dst, src, std::min(slice, bytes));
+    for (auto& th : pool) th.join();
+}
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int copy_threads() {
+    static const int n = [] {
+        const char* e = getenv("RUMI_COPY_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        return std::max(1, e ? atoi(e) : std::min(4, std::max(1, hw / 2)));   // 4: measured best (1 / 2 / 4 / 8 / 16 threads)
+    }();
+    return n;
+}
+
+// Host batch path for PAGEABLE caller memory (cv::Mat images, std::vector outputs): a cudaMemcpyAsync from / to pageable
+// memory is staged by the driver with one host thread (~8 GB/s: 25 k frames/s).  Here every chunk is copied into the
+// workspace's own pinned block by several host threads while the GPU works on the previous chunks, travels with truly
+// asynchronous copies, and its results are copied out of a pinned block the same way once their event has fired.
+int extract_batch_pageable(rumi_orb* h, const std::vector<int>& sizes, const uint8_t* imgs, size_t frame_pitch, int lap0,
+                           int lap1, rumi_kp* kps, uint8_t* desc, int cap_per_frame, int* n_kp, int* n_mono) {
+    const OrbConst& oc = h->oc;
+    const LevelGeom& g = oc.lv[0];
+    const size_t frameBytes = (size_t)g.stride * g.h;
+    const size_t kpRow = sizeof(rumi_kp) * (size_t)oc.kpCap, dRow = 32 * (size_t)oc.kpCap;
+    const int nt = copy_threads();
+    struct Pending { int f0 = 0, m = 0; bool live = false; };
+    std::vector<Pending> pend(h->nws);
+    auto finalize = [&](int wi) -> int {
+        Pending& p = pend[wi];
+        if (!p.live) return RUMI_OK;
+        Workspace& ws = h->ws[wi];
+        CU_TRY(cudaEventSynchronize(ws.evOut));
+        const uint8_t* o = ws.hOut;
+        const size_t oD = kpRow * h->chunk, oN = oD + dRow * h->chunk, oM = oN + 4 * (size_t)h->chunk;
+        if (cap_per_frame == oc.kpCap) {
+            parallel_copy(kps + (size_t)p.f0 * cap_per_frame, o, kpRow * p.m, nt);
+            parallel_copy(desc + (size_t)p.f0 * cap_per_frame * 32, o + oD, dRow * p.m, nt);
+        } else {
+            for (int i = 0; i < p.m; ++i) {
+                std::memcpy(kps + (size_t)(p.f0 + i) * cap_per_frame, o + kpRow * i, kpRow);
+                std::memcpy(desc + (size_t)(p.f0 + i) * cap_per_frame * 32, o + oD + dRow * i, dRow);
+            }
+        }
+        std::memcpy(n_kp + p.f0, o + oN, 4 * (size_t)p.m);
+        std::memcpy(n_mono + p.f0, o + oM, 4 * (size_t)p.m);
+        p.live = false;
+        return RUMI_OK;
+    };
+    int rc, f0 = 0;
+    for (size_t c = 0; c < sizes.size(); ++c) {
+        const int wi = (int)(c % (size_t)h->nws), m = sizes[c];
+        if ((rc = ensure_workspace(h, wi))) return rc;
+        Workspace& ws = h->ws[wi];
+        if ((rc = finalize(wi))) return rc;                    // the chunk that used this workspace (and its staging) before
+        const size_t inNeed = frameBytes * h->chunk, outNeed = (kpRow + dRow + 8) * (size_t)h->chunk;
+        if (ws.hInCap < inNeed) {
+            if (ws.hIn) cudaFreeHost(ws.hIn);
+            ws.hIn = nullptr; ws.hInCap = 0;
+            CU_TRY(cudaHostAlloc((void**)&ws.hIn, inNeed, cudaHostAllocDefault));
+            ws.hInCap = inNeed;
+        }
+        if (ws.hOutCap < outNeed) {
+            if (ws.hOut) cudaFreeHost(ws.hOut);
+            ws.hOut = nullptr; ws.hOutCap = 0;
+            CU_TRY(cudaHostAlloc((void**)&ws.hOut, outNeed, cudaHostAllocDefault));
+            ws.hOutCap = outNeed;
+        }
+        if (!ws.evOut) CU_TRY(cudaEventCreateWithFlags(&ws.evOut, cudaEventDisableTiming));
+        parallel_copy(ws.hIn, imgs + (size_t)f0 * frame_pitch, frameBytes * m, nt);
+        CU_TRY(cudaMemcpyAsync(ws.pyr + h->pyrLevelOff[0], ws.hIn, frameBytes * m, cudaMemcpyHostToDevice, ws.stream));
+        const LevelView l0 = internal_view(h, ws.pyr, 0);
+        if ((rc = run_chunk(h, ws, l0, true, m, lap0, lap1, ws.kps, ws.desc, oc.kpCap, ws.nkp, ws.nmono))) return rc;
+        const size_t oD = kpRow * h->chunk, oN = oD + dRow * h->chunk, oM = oN + 4 * (size_t)h->chunk;
+        CU_TRY(cudaMemcpyAsync(ws.hOut, ws.kps, kpRow * m, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaMemcpyAsync(ws.hOut + oD, ws.desc, dRow * m, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaMemcpyAsync(ws.hOut + oN, ws.nkp, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaMemcpyAsync(ws.hOut + oM, ws.nmono, 4 * (size_t)m, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(cudaEventRecord(ws.evOut, ws.stream));
+        pend[wi].f0 = f0; pend[wi].m = m; pend[wi].live = true;
+        h->lastWs = wi;
+        f0 += m;
+    }
+    // drain in submission order
+    for (size_t k = 0; k < (size_t)h->nws; ++k) {
+        const int wi = (int)((sizes.size() + k) % (size_t)h->nws);
+        if ((rc = finalize(wi))) return rc;
+    }
+    return check_device_flags(h);
+}
+}  // namespace
+
 int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h_px, size_t stride,
                            size_t frame_pitch, int lap0, int lap1, rumi_kp* kps, uint8_t* desc, int cap_per_frame,
                            int* n_kp, int* n_mono) {
@@ -762,6 +877,10 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
         while (left > 0) { const int sz = std::min(c, left); sizes.push_back(sz); left -= sz; }
         for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
     }
+    // pageable caller memory, rows contiguous: the library stages the chunks itself with several host threads
+    if (!h->profile && stride == (size_t)oc.lv[0].stride && frame_pitch == stride * (size_t)h_px && getenv("RUMI_NO_HOST_STAGING") == nullptr &&
+        is_pageable(imgs) && is_pageable(kps) && is_pageable(desc))
+        return extract_batch_pageable(h, sizes, imgs, frame_pitch, lap0, lap1, kps, desc, cap_per_frame, n_kp, n_mono);
     int f0 = 0;
     for (size_t c = 0; c < sizes.size(); ++c) {
         const int wi = (int)(c % (size_t)h->nws);

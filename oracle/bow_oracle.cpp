@@ -159,11 +159,14 @@ static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& i
 // Feature vectors are flattened (sorted node ids, offsets, feature indices).  kf_valid[i] != 0 <=> the keyframe
 // feature has a map point that is not bad (:227-233).  match_f[j] = keyframe feature matched to frame feature j or -1
 // (the reference stores the MapPoint*).  Returns nmatches.
-int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid,
+// n_left = F.Nleft: -1 for a mono / rectified frame; otherwise features [0, n_left) belong to the left and [n_left, nf)
+// to the right fisheye camera, each side keeps its own best / second best and the right one is accepted without a ratio
+// test (":316 ... || true"), only when the left one passed TH_LOW (:290-340).
+int bow_oracle_search_by_bow_nleft(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid,
                              const int32_t* kf_nodes, const int32_t* kf_off, const int32_t* kf_idx, int kf_nnodes,
                              const uint8_t* desc_f, const float* angle_f, int nf,
                              const int32_t* f_nodes, const int32_t* f_off, const int32_t* f_idx, int f_nnodes,
-                             float nnratio, int check_ori, int th_low, int32_t* match_f) {
+                             float nnratio, int check_ori, int th_low, int n_left, int32_t* match_f) {
     const int HISTO_LENGTH = 30;
     for (int j = 0; j < nf; ++j) match_f[j] = -1;
     int nmatches = 0;
@@ -177,25 +180,33 @@ int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, cons
                 if (!kf_valid[realIdxKF]) continue;
                 const uint8_t* dKF = desc_kf + 32 * (size_t)realIdxKF;
                 int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                int bestDist1R = 256, bestIdxFR = -1, bestDist2R = 256;
                 for (int iF = f_off[b]; iF < f_off[b + 1]; ++iF) {
                     const int realIdxF = f_idx[iF];
                     if (match_f[realIdxF] >= 0) continue;                         // :249
                     const int dist = forb_distance(dKF, desc_f + 32 * (size_t)realIdxF);
-                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
-                    else if (dist < bestDist2) { bestDist2 = dist; }
-                }
-                if (bestDist1 <= th_low) {
-                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
-                        match_f[bestIdxF] = realIdxKF;
-                        if (check_ori) {
-                            float rot = angle_kf[realIdxKF] - angle_f[bestIdxF];
-                            if (rot < 0.0) rot += 360.0f;
-                            int bin = (int)std::round(rot * factor);
-                            if (bin == HISTO_LENGTH) bin = 0;
-                            rotHist[bin].push_back(bestIdxF);
-                        }
-                        nmatches++;
+                    if (n_left == -1 || realIdxF < n_left) {
+                        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                        else if (dist < bestDist2) { bestDist2 = dist; }
+                    } else {
+                        if (dist < bestDist1R) { bestDist2R = bestDist1R; bestDist1R = dist; bestIdxFR = realIdxF; }
+                        else if (dist < bestDist2R) { bestDist2R = dist; }
                     }
+                }
+                auto accept = [&](int idxF) {
+                    match_f[idxF] = realIdxKF;
+                    if (check_ori) {
+                        float rot = angle_kf[realIdxKF] - angle_f[idxF];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idxF);
+                    }
+                    nmatches++;
+                };
+                if (bestDist1 <= th_low) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) accept(bestIdxF);
+                    if (bestDist1R <= th_low) accept(bestIdxFR);                  // ":316 ... || true": no ratio test on the right
                 }
             }
             ++a; ++b;
@@ -214,6 +225,15 @@ int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, cons
         }
     }
     return nmatches;
+}
+
+int bow_oracle_search_by_bow(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid,
+                             const int32_t* kf_nodes, const int32_t* kf_off, const int32_t* kf_idx, int kf_nnodes,
+                             const uint8_t* desc_f, const float* angle_f, int nf,
+                             const int32_t* f_nodes, const int32_t* f_off, const int32_t* f_idx, int f_nnodes,
+                             float nnratio, int check_ori, int th_low, int32_t* match_f) {
+    return bow_oracle_search_by_bow_nleft(desc_kf, angle_kf, kf_valid, kf_nodes, kf_off, kf_idx, kf_nnodes, desc_f, angle_f, nf,
+                                          f_nodes, f_off, f_idx, f_nnodes, nnratio, check_ori, th_low, -1, match_f);
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), R/lib_src/ORBmatcher.cc:682-804 (NLeft == -1 for both).

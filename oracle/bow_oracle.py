@@ -130,7 +130,7 @@ def flatten_fv(fv):
     return nodes, off, np.array(idx if idx else [0], np.int32)[:max(len(idx), 0) or None] if idx else np.zeros(0, np.int32)
 
 
-def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnratio=0.7, check_ori=True, th_low=50):
+def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnratio=0.7, check_ori=True, th_low=50, n_left=-1):
     dk, df = np.ascontiguousarray(desc_kf, np.uint8), np.ascontiguousarray(desc_f, np.uint8)
     ak, af = np.ascontiguousarray(angle_kf, np.float32), np.ascontiguousarray(angle_f, np.float32)
     vk = np.ascontiguousarray(kf_valid, np.uint8)
@@ -139,10 +139,14 @@ def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnr
     ki = np.ascontiguousarray(np.append(ki, 0), np.int32)
     fi = np.ascontiguousarray(np.append(fi, 0), np.int32)
     match = np.zeros(max(len(df), 1), np.int32)
-    n = lib().bow_oracle_search_by_bow(_p(dk, _u8p), _p(ak, _f32p), _p(vk, _u8p), _p(kn, _i32p), _p(ko, _i32p),
-                                       _p(ki, _i32p), len(kn), _p(df, _u8p), _p(af, _f32p), len(df), _p(fn, _i32p),
-                                       _p(fo, _i32p), _p(fi, _i32p), len(fn), nnratio, 1 if check_ori else 0, th_low,
-                                       _p(match, _i32p))
+    L = lib()
+    L.bow_oracle_search_by_bow_nleft.restype = C.c_int
+    L.bow_oracle_search_by_bow_nleft.argtypes = [_u8p, _f32p, _u8p, _i32p, _i32p, _i32p, C.c_int, _u8p, _f32p, C.c_int, _i32p, _i32p,
+                                                 _i32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _i32p]
+    n = L.bow_oracle_search_by_bow_nleft(_p(dk, _u8p), _p(ak, _f32p), _p(vk, _u8p), _p(kn, _i32p), _p(ko, _i32p),
+                                         _p(ki, _i32p), len(kn), _p(df, _u8p), _p(af, _f32p), len(df), _p(fn, _i32p),
+                                         _p(fo, _i32p), _p(fi, _i32p), len(fn), nnratio, 1 if check_ori else 0, th_low,
+                                         int(n_left), _p(match, _i32p))
     return n, match[:len(df)]
 
 

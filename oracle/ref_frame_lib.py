@@ -94,7 +94,7 @@ def _nodes(fv, n):
     return node
 
 
-def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnratio=0.7, check_ori=True):
+def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnratio=0.7, check_ori=True, n_left=-1):
     """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...).  fv_*: {node id: [feature indices in ascending order]} (the order
     DBoW2::FeatureVector::addFeature produces when features are added by ascending index).  (nmatches, matchF)."""
     dk, df = np.ascontiguousarray(desc_kf, np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
@@ -103,9 +103,10 @@ def search_by_bow(desc_kf, angle_kf, kf_valid, fv_kf, desc_f, angle_f, fv_f, nnr
     nk, nf = _nodes(fv_kf, len(dk)), _nodes(fv_f, len(df))
     match = np.zeros(max(len(df), 1), np.int32)
     L = lib()
-    L.ref_search_by_bow.argtypes = [_u8p, _f32p, _u8p, _i32p, C.c_int, _u8p, _f32p, _i32p, C.c_int, C.c_float, C.c_int, _i32p]
-    n = L.ref_search_by_bow(_p(dk, _u8p), _p(ak, _f32p), _p(vk, _u8p), _p(nk, _i32p), len(dk), _p(df, _u8p), _p(af, _f32p),
-                            _p(nf, _i32p), len(df), float(nnratio), 1 if check_ori else 0, _p(match, _i32p))
+    L.ref_search_by_bow_nleft.argtypes = [_u8p, _f32p, _u8p, _i32p, C.c_int, _u8p, _f32p, _i32p, C.c_int, C.c_float, C.c_int, C.c_int,
+                                          _i32p]
+    n = L.ref_search_by_bow_nleft(_p(dk, _u8p), _p(ak, _f32p), _p(vk, _u8p), _p(nk, _i32p), len(dk), _p(df, _u8p), _p(af, _f32p),
+                                  _p(nf, _i32p), len(df), float(nnratio), 1 if check_ori else 0, int(n_left), _p(match, _i32p))
     return n, match[:len(df)]
 
 

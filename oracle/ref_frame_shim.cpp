@@ -327,16 +327,26 @@ int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...): node ids per feature (-1 = feature not in the FeatureVector);
 // kfValid[i] = the keyframe feature has a map point that is not bad.  matchF[j] = keyframe feature index or -1.
+int ref_search_by_bow_nleft(const uint8_t* dKF, const float* angKF, const uint8_t* kfValid, const int32_t* nodeKF, int nKF,
+                            const uint8_t* dF, const float* angF, const int32_t* nodeF, int nF, float ratio, int checkOri,
+                            int nLeft, int32_t* matchF);
 int ref_search_by_bow(const uint8_t* dKF, const float* angKF, const uint8_t* kfValid, const int32_t* nodeKF, int nKF,
                       const uint8_t* dF, const float* angF, const int32_t* nodeF, int nF, float ratio, int checkOri,
                       int32_t* matchF) {
+    return ref_search_by_bow_nleft(dKF, angKF, kfValid, nodeKF, nKF, dF, angF, nodeF, nF, ratio, checkOri, -1, matchF);
+}
+// nLeft = F.Nleft (-1: mono / rectified frame; otherwise the stereo-fisheye branches of :258-340 run; the key frame has no
+// second camera, so every key point is read from mvKeysUn / F.mvKeys as :296-303 does)
+int ref_search_by_bow_nleft(const uint8_t* dKF, const float* angKF, const uint8_t* kfValid, const int32_t* nodeKF, int nKF,
+                            const uint8_t* dF, const float* angF, const int32_t* nodeF, int nF, float ratio, int checkOri,
+                            int nLeft, int32_t* matchF) {
     KeyFrame kf; Frame F;
     std::vector<MapPoint> mps(nKF);
     kf.mDescriptors = rows32(dKF, nKF);
     kf.mvKeysUn.resize(nKF); kf.mvpMapPoints.assign(nKF, nullptr);
     for (int i = 0; i < nKF; ++i) { kf.mvKeysUn[i].angle = angKF[i]; if (kfValid[i]) kf.mvpMapPoints[i] = &mps[i]; }
     fill_featvec(kf.mFeatVec, nodeKF, nKF);
-    F.N = nF; F.mDescriptors = rows32(dF, nF); F.mvKeys.resize(nF);
+    F.N = nF; F.Nleft = nLeft; F.mDescriptors = rows32(dF, nF); F.mvKeys.resize(nF);
     for (int j = 0; j < nF; ++j) F.mvKeys[j].angle = angF[j];
     fill_featvec(F.mFeatVec, nodeF, nF);
     ORBmatcher m(ratio, checkOri != 0);

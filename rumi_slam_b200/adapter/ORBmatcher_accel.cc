@@ -294,7 +294,7 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
                                  const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF,
                                  const cv::Mat& descF, const std::vector<float>& angleF,
                                  const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF,
-                                 bool checkOrientation, std::vector<int>& matchF) {
+                                 bool checkOrientation, std::vector<int>& matchF, int Nleft) {
     matchF.assign(descF.rows, -1);
     std::vector<int32_t> aIdx, bIdx, segs;
     std::vector<uint16_t> dist;
@@ -304,6 +304,17 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
     std::vector<int> rotHist[HISTO_LENGTH];
     for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
     const float factor = 1.0f / HISTO_LENGTH;
+    auto accept = [&](int realIdxKF, int idxF) {
+        matchF[idxF] = realIdxKF;
+        if (checkOrientation) {
+            float rot = angleKF[realIdxKF] - angleF[idxF];
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)std::round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rotHist[bin].push_back(idxF);
+        }
+        nmatches++;
+    };
     for (size_t s = 0; s < segs.size(); s += 5) {
         const int a0 = segs[s], ac = segs[s + 1], b0 = segs[s + 2], bc = segs[s + 3];
         const uint16_t* block = dist.data() + segs[s + 4];
@@ -311,25 +322,22 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
             const int realIdxKF = aIdx[a0 + iKF];
             if (!kfValid[realIdxKF]) continue;                                   // :229-233
             int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+            int bestDist1R = 256, bestIdxFR = -1, bestDist2R = 256;              // right fisheye camera (F.Nleft != -1, :258-283)
             for (int iF = 0; iF < bc; iF++) {
                 const int realIdxF = bIdx[b0 + iF];
                 if (matchF[realIdxF] >= 0) continue;                              // :249
                 const int d = block[(size_t)iKF * bc + iF];
-                if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = realIdxF; }
-                else if (d < bestDist2) { bestDist2 = d; }
+                if (Nleft == -1 || realIdxF < Nleft) {
+                    if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = realIdxF; }
+                    else if (d < bestDist2) { bestDist2 = d; }
+                } else {
+                    if (d < bestDist1R) { bestDist2R = bestDist1R; bestDist1R = d; bestIdxFR = realIdxF; }
+                    else if (d < bestDist2R) { bestDist2R = d; }
+                }
             }
             if (bestDist1 <= TH_LOW) {
-                if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
-                    matchF[bestIdxF] = realIdxKF;
-                    if (checkOrientation) {
-                        float rot = angleKF[realIdxKF] - angleF[bestIdxF];
-                        if (rot < 0.0) rot += 360.0f;
-                        int bin = (int)std::round(rot * factor);
-                        if (bin == HISTO_LENGTH) bin = 0;
-                        rotHist[bin].push_back(bestIdxF);
-                    }
-                    nmatches++;
-                }
+                if (static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) accept(realIdxKF, bestIdxF);
+                if (bestDist1R <= TH_LOW) accept(realIdxKF, bestIdxFR);           // :314-316 ("|| true": no ratio test on the right)
             }
         }
     }
@@ -342,6 +350,22 @@ int ORBmatcherAccel::SearchByBoW(const cv::Mat& descKF, const std::vector<float>
         }
     }
     return nmatches;
+}
+
+void ORBmatcherAccel::StereoFishEyeMatches(const cv::Mat& descLeft, int monoLeft, const cv::Mat& descRight, int monoRight,
+                                           std::vector<std::pair<int, int> >& pairs) {
+    pairs.clear();
+    const int nq = descLeft.rows - monoLeft, nt = descRight.rows - monoRight;
+    if (nq <= 0 || nt < 2) return;                     // knnMatch returns fewer than 2 neighbours: "size() >= 2" fails (:1146)
+    cv::Mat Q(nq, 32, CV_8U), T(nt, 32, CV_8U);
+    for (int i = 0; i < nq; ++i) std::memcpy(Q.ptr(i), descLeft.ptr(monoLeft + i), 32);
+    for (int i = 0; i < nt; ++i) std::memcpy(T.ptr(i), descRight.ptr(monoRight + i), 32);
+    std::vector<int> idx;
+    std::vector<uint16_t> d1, d2;
+    Top2(Q, T, idx, d1, d2);
+    for (int q = 0; q < nq; ++q)
+        if (idx[q] >= 0 && (float)d1[q] < (float)d2[q] * 0.7)                    // DMatch::distance is float, 0.7 a double
+            pairs.push_back(std::make_pair(q + monoLeft, idx[q] + monoRight));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

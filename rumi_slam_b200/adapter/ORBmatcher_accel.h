@@ -87,7 +87,14 @@ public:
                     const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecKF, const cv::Mat& descF,
                     const std::vector<float>& angleF,
                     const std::vector<std::pair<unsigned, std::vector<unsigned> > >& featVecF, bool checkOrientation,
-                    std::vector<int>& matchF);
+                    std::vector<int>& matchF, int Nleft = -1);   // Nleft = F.Nleft: the stereo-fisheye branches of :258-340
+
+    // Frame::ComputeStereoFishEyeMatches (R/lib_src/Frame.cc:1120-1161), the matching core: brute-force k = 2 between the
+    // lapping-area descriptors (rows monoLeft.. / monoRight.., :1122-1126) + Lowe's ratio d0 < d1 * 0.7 (:1146).  pairs =
+    // (left feature, right feature) in the reference's order, indices in the full arrays; the caller triangulates each pair
+    // with its camera model (KannalaBrandt8::TriangulateMatches) and keeps those with depth > 0.0001 (:1151-1158).
+    void StereoFishEyeMatches(const cv::Mat& descLeft, int monoLeft, const cv::Mat& descRight, int monoRight,
+                              std::vector<std::pair<int, int> >& pairs);
 
     // ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (R/lib_src/ORBmatcher.cc:682-804), NLeft == -1 for both
     // keyframes.  valid1 / valid2: the feature has a map point that is not bad.  match12[i] = feature of keyframe 2

@@ -617,9 +617,12 @@ class ORBmatcher:
         return 0 if b == self.HISTO_LENGTH else b
 
     # ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:198-370, F.Nleft == -1) ----
-    def SearchByBoW(self, desc_kf, angle_kf, kf_valid, featvec_kf, desc_f, angle_f, featvec_f):
+    def SearchByBoW(self, desc_kf, angle_kf, kf_valid, featvec_kf, desc_f, angle_f, featvec_f, n_left=-1):
         """desc_*: [n,32] descriptors; angle_*: keypoint angles (mvKeysUn[i].angle / mvKeys[i].angle); kf_valid[i]:
         the keyframe feature has a map point that is not bad (:227-233); featvec_*: FeatureVector {node: [indices]}.
+        n_left = F.Nleft: -1 for a mono / rectified frame; for a stereo-fisheye frame features [0, n_left) are the left and
+        [n_left, N) the right camera (:258-340: a best / second best per side; the right match needs no ratio test but is
+        only taken when the left one passed TH_LOW).
         Returns (nmatches, match_f) with match_f[j] = keyframe feature whose map point was assigned to frame feature
         j, or -1.  The GPU computes every distance of every common vocabulary node; the acceptance (TH_LOW, ratio,
         the "already matched" skip :249 and the rotation histogram) is replayed here in the reference's order."""
@@ -628,26 +631,39 @@ class ORBmatcher:
         nmatches = 0
         rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
         ratio = np.float32(self.mfNNratio)
+
+        def accept(real_kf, idx_f):
+            match_f[idx_f] = real_kf
+            if self.mbCheckOrientation:
+                rot_hist[self._rot_bin(angle_kf[real_kf], angle_f[idx_f])].append(idx_f)
+            return 1
         for a_idx, b_idx, block in self._bow_blocks(desc_kf, featvec_kf, desc_f, featvec_f):
             for i in range(len(a_idx)):
                 real_kf = int(a_idx[i])
                 if not kf_valid[real_kf]:
                     continue
                 best1, best_f, best2 = 256, -1, 256
+                best1r, best_fr, best2r = 256, -1, 256
                 for j in range(len(b_idx)):
                     real_f = int(b_idx[j])
                     if match_f[real_f] >= 0:
                         continue
                     d = int(block[i, j])
-                    if d < best1:
-                        best2, best1, best_f = best1, d, real_f
-                    elif d < best2:
-                        best2 = d
-                if best1 <= self.TH_LOW and np.float32(best1) < ratio * np.float32(best2):
-                    match_f[best_f] = real_kf
-                    if self.mbCheckOrientation:
-                        rot_hist[self._rot_bin(angle_kf[real_kf], angle_f[best_f])].append(best_f)
-                    nmatches += 1
+                    if n_left == -1 or real_f < n_left:
+                        if d < best1:
+                            best2, best1, best_f = best1, d, real_f
+                        elif d < best2:
+                            best2 = d
+                    else:
+                        if d < best1r:
+                            best2r, best1r, best_fr = best1r, d, real_f
+                        elif d < best2r:
+                            best2r = d
+                if best1 <= self.TH_LOW:
+                    if np.float32(best1) < ratio * np.float32(best2):
+                        nmatches += accept(real_kf, best_f)
+                    if best1r <= self.TH_LOW:                   # ":316 ... || true": no ratio test on the right side
+                        nmatches += accept(real_kf, best_fr)
         if self.mbCheckOrientation:
             keep = _three_maxima(rot_hist)
             for i in range(self.HISTO_LENGTH):
@@ -657,6 +673,20 @@ class ORBmatcher:
                     match_f[j] = -1
                     nmatches -= 1
         return nmatches, match_f
+
+    # ---- Frame::ComputeStereoFishEyeMatches (Frame.cc:1120-1161): the matching core ----
+    def StereoFishEyeMatches(self, desc_left, mono_left, desc_right, mono_right, ratio=0.7):
+        """Brute-force k = 2 match of the lapping-area descriptors (rows mono_left.. of the left, mono_right.. of the right
+        image: what operator() with vLappingArea put at the back, :1122-1126) + Lowe's ratio d0 < d1 * 0.7 (:1146).  Returns
+        [(left feature, right feature)] in the reference's order, indices in the full arrays; the caller triangulates
+        each pair with its camera model and keeps those with positive depth (:1151-1158)."""
+        dl = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32)[mono_left:]
+        dr = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)[mono_right:]
+        if len(dl) == 0 or len(dr) < 2:                       # knnMatch returns fewer than 2 neighbours: size() >= 2 fails
+            return []
+        i1, d1, d2 = self.top2(dl, dr)
+        ok = self.accept_knn_ratio(d1, d2, ratio) & (i1 >= 0)
+        return [(int(q) + mono_left, int(i1[q]) + mono_right) for q in np.flatnonzero(ok)]
 
     # ---- ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (ORBmatcher.cc:682-804, NLeft == -1) ----
     def SearchByBoW_KF(self, desc1, angle1, valid1, featvec1, desc2, angle2, valid2, featvec2):

@@ -198,3 +198,49 @@ def test_search_for_triangulation_matches_oracle(bow_oracle, seed, only_stereo, 
                                                  (320.0, 240.0), epi, only_stereo, coarse, check_ori)
     assert n == rn and np.array_equal(m, rm) and rn > 50
     assert (len(calls) == 0) == coarse and len(calls) < 20 * n1
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,frac", [(7, 0.5), (8, 0.7)])
+def test_search_by_bow_stereo_fisheye_branch_matches_oracle(bow_oracle, seed, frac, check_ori):
+    """The F.Nleft != -1 branches of SearchByBoW (R/lib_src/ORBmatcher.cc:258-340); oracle pinned in
+    tests/test_ref_frame_pin.py::test_search_by_bow_stereo_fisheye_branch_equals_reference."""
+    from rumi_slam_b200 import ORBVocabulary, ORBmatcher
+    k, L = 10, 4
+    par, leaf, desc, w = synthetic_vocabulary(k, L, seed=11)
+    V = ORBVocabulary(k, L, par, leaf, desc, w)
+    rng = np.random.default_rng(seed)
+    nk, nf = 900, 1000
+    dk = descriptors_near_vocabulary(desc, leaf, nk, 20 + seed, flip=0.04)
+    src = rng.integers(0, nk, 800)
+    df = np.concatenate([dk[src] ^ np.packbits(rng.random((800, 256)) < 0.03, axis=1),
+                         descriptors_near_vocabulary(desc, leaf, nf - 800, 30 + seed)])[rng.permutation(nf)]
+    ak = rng.random(nk).astype(np.float32) * 360
+    af = rng.random(nf).astype(np.float32) * 360
+    valid = (rng.random(nk) < 0.8).astype(np.uint8)
+    _, fv_k = V.transform(dk, 2)
+    _, fv_f = V.transform(df, 2)
+    n_left = int(nf * frac)
+    n, m = ORBmatcher(0.75, check_ori).SearchByBoW(dk, ak, valid, fv_k, df, af, fv_f, n_left=n_left)
+    rn, rm = bow_oracle.search_by_bow(dk, ak, valid, fv_k, df, af, fv_f, nnratio=0.75, check_ori=check_ori, n_left=n_left)
+    assert n == rn and np.array_equal(m, rm) and rn > 100 and (rm[n_left:] >= 0).sum() > 20
+
+
+def test_stereo_fisheye_matches_equal_cv2_knn(bow_oracle):
+    """Frame::ComputeStereoFishEyeMatches (R/lib_src/Frame.cc:1120-1161), matching core == cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2)
+    + Lowe's ratio 0.7 on the lapping-area rows."""
+    import cv2
+    from rumi_slam_b200 import ORBmatcher
+    rng = np.random.default_rng(5)
+    nl, nr, mono_l, mono_r = 1200, 1100, 400, 350
+    dr = rng.integers(0, 256, (nr, 32), dtype=np.uint8)
+    dl = rng.integers(0, 256, (nl, 32), dtype=np.uint8)
+    pick = rng.integers(mono_r, nr, nl - mono_l)                      # most lapping-area features have a noisy twin on the right
+    dl[mono_l:] = dr[pick] ^ np.packbits(rng.random((nl - mono_l, 256)) < 0.06, axis=1)
+    pairs = ORBmatcher().StereoFishEyeMatches(dl, mono_l, dr, mono_r)
+    ref = []
+    for mm in cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(dl[mono_l:], dr[mono_r:], 2):
+        if len(mm) >= 2 and mm[0].distance < mm[1].distance * 0.7:
+            ref.append((mm[0].queryIdx + mono_l, mm[0].trainIdx + mono_r))
+    assert pairs == ref and len(ref) > 300
+    assert ORBmatcher().StereoFishEyeMatches(dl, mono_l, dr[:mono_r + 1], mono_r) == []      # one candidate: size() >= 2 fails

@@ -106,6 +106,22 @@ def test_search_by_bow_equals_reference(rf, B, seed, check_ori):
 
 
 @pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,frac", [(7, 0.5), (8, 0.7), (9, 0.3)])
+def test_search_by_bow_stereo_fisheye_branch_equals_reference(rf, B, seed, frac, check_ori):
+    """The F.Nleft != -1 branches of SearchByBoW(KeyFrame*, Frame&, ...) (R/lib_src/ORBmatcher.cc:258-340): features
+    [0, Nleft) are the left, [Nleft, N) the right fisheye camera; separate best / second best per side, the right match needs
+    no ratio test but only counts when the left one passed TH_LOW."""
+    dk, ak, fvk, df, af, fvf, rng = _scene(B, seed)
+    valid = (rng.random(len(dk)) < 0.8).astype(np.uint8)
+    n_left = int(len(df) * frac)
+    for ratio in (0.6, 0.9):
+        n, m = B.search_by_bow(dk, ak, valid, fvk, df, af, fvf, nnratio=ratio, check_ori=check_ori, n_left=n_left)
+        rn, rm = rf.search_by_bow(dk, ak, valid, fvk, df, af, fvf, nnratio=ratio, check_ori=check_ori, n_left=n_left)
+        assert n == rn and np.array_equal(m, rm), (seed, ratio)
+    assert rn > 100 and (rm[n_left:] >= 0).sum() > 20
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
 @pytest.mark.parametrize("seed", [4, 5, 6])
 def test_search_by_bow_keyframes_equals_reference(rf, B, seed, check_ori):
     """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (R/lib_src/ORBmatcher.cc:682-804), strict '<' TH_LOW."""

@@ -279,3 +279,23 @@ def test_keyframe_pair_association_equals_pairwise(oracle):
         nmatch += int((mt >= 0).sum())
     assert nmatch > 1000
     assert m.top2_pairs([], []) == []
+
+
+def test_top2_umma_random_shapes(oracle):
+    """The persistent tensor-core kernel cuts the flattened (query block, train tile) grid into one range per SM: ranges that
+    start / end inside a query block, several segments per CTA, ragged last tiles and blocks.  40 random shapes, forced onto
+    that kernel, against the oracle scan."""
+    rng = np.random.default_rng(123)
+    base = real_descriptors(oracle, (2, 3, 4))
+    m = matcher("umma")
+    shapes = [(int(rng.integers(1, 6000)), int(rng.integers(1, 9000))) for _ in range(34)]
+    shapes += [(256, 128), (257, 129), (255, 127), (512, 148 * 128), (148 * 256, 128), (300, 18945)]
+    for nq, nt in shapes:
+        Q = perturbed_descriptors(base, nq, seed=nq, flip_p=0.05)
+        T = perturbed_descriptors(base[::-1].copy(), nt, seed=nt, flip_p=0.05)
+        if nt > 3:
+            T[nt - 1] = T[nt // 3]                             # a tie between far-apart rows: the earlier index must win
+        i1, d1, d2 = m.top2(Q, T)
+        ri, rd1, rd2 = oracle.hamming_top2(Q, T)
+        assert m.last_path() == "umma"
+        assert np.array_equal(i1, ri) and np.array_equal(d1, rd1) and np.array_equal(d2, rd2), (nq, nt)

@@ -219,3 +219,29 @@ def test_begin_end_equals_call_and_two_extractors_in_flight(oracle):
     exl._pending = (a, 480, 752)
     with pytest.raises(Exception):
         exl.end()
+
+
+def test_random_shapes_and_parameters(oracle):
+    """16 random (width, height, nfeatures, levels, scale factor) combinations -- odd widths (partial words, partial cells),
+    non-standard aspect ratios (1-4 quad-tree roots), 2-9 levels -- single frame and a 5-frame chunk against the oracle."""
+    from rumi_slam_b200 import ORBextractor
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 16:
+        w, h = int(rng.integers(240, 1300)), int(rng.integers(200, 800))
+        levels, scale = int(rng.integers(2, 10)), float(rng.choice([1.1, 1.2, 1.25, 1.4]))
+        nf = int(rng.integers(200, 2500))
+        if min(w, h) / scale ** (levels - 1) < 80 or w / h > 3.4 or h / w > 1.6:      # the reference's own limits (cells, roots)
+            continue
+        frames = synthetic_batch(5, w, h, seed0=9000 + done)
+        ex = ORBextractor(nf, scale, levels, 20, 7, max_batch=5)
+        ref = [oracle.extract(frames[i], nfeatures=nf, scale=scale, nlevels=levels) for i in range(5)]
+        mono, kps, desc = ex(frames[0])
+        assert mono == ref[0][2] and np.array_equal(kps, ref[0][0]) and np.array_equal(desc, ref[0][1]), (w, h, nf, levels, scale)
+        bk, bd, nkp, nmono = ex.extract_batch(frames)
+        for i in range(5):
+            rk, rd, rm = ref[i]
+            assert nkp[i] == len(rk) and nmono[i] == rm, (w, h, nf, levels, scale, i)
+            assert np.array_equal(bk[i, :nkp[i]], rk) and np.array_equal(bd[i, :nkp[i]], rd), (w, h, nf, levels, scale, i)
+        ex.close()
+        done += 1

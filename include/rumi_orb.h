@@ -105,6 +105,10 @@ int rumi_orb_describe_batch(rumi_orb* h, const uint8_t* imgs, int nimg, int w, i
 /* mvImagePyramid[level] of the LAST rumi_orb_extract call (R/include/cloud_edge_slam_lib/ORBextractor.h:86;
  * read by Frame::ComputeStereoMatches, R/lib_src/Frame.cc:834,918-932).  Copies the level to host memory. */
 int rumi_orb_pyramid_level(rumi_orb* h, int level, uint8_t* dst, size_t dst_stride, int* w, int* h_px);
+/* on != 0: every single-frame call (rumi_orb_extract / _begin) also brings the frame's pyramid to a pinned host block behind
+ * the kernels, so that rumi_orb_pyramid_level is a host copy without a device round trip -- for callers that read
+ * mvImagePyramid after every frame (the reference's Frame::ComputeStereoMatches, R/lib_src/Frame.cc:834, 918-932). */
+int rumi_orb_set_pyramid_staging(rumi_orb* h, int on);
 /* Blurred level of the last call (test hook for the 7x7 Gaussian, R/lib_src/ORBextractor.cc:1057-1058). */
 int rumi_orb_blurred_level(rumi_orb* h, int level, uint8_t* dst, size_t dst_stride, int* w, int* h_px);
 /* Stage-level test hooks: FAST candidates of `level` of the last single-frame call in the reference's insertion

@@ -29,6 +29,7 @@ SIGNATURES = {
     "rumi_orb_frame_capacity": (C.c_int, [_vp, C.c_int, C.c_int]),
     "rumi_orb_extract": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, _vp, _vp, C.c_int,
                                    _i32p, _i32p]),
+    "rumi_orb_set_pyramid_staging": (C.c_int, [_vp, C.c_int]),
     "rumi_orb_extract_begin": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int]),
     "rumi_orb_extract_end": (C.c_int, [_vp, _vp, _vp, C.c_int, _i32p, _i32p]),
     "rumi_orb_extract_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int,

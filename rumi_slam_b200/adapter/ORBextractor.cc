@@ -27,9 +27,15 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     rumi_orb_tables(handle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
                     mvInvLevelSigma2.data(), mnFeaturesPerLevel.data());
     mvImagePyramid.resize(nlevels);
+    rumi_orb_set_pyramid_staging(handle, 1);               // downloadPyramid is on by default
 }
 
 ORBextractor::~ORBextractor() { rumi_orb_destroy(handle); }
+
+void ORBextractor::SetPyramidDownload(bool on) {
+    downloadPyramid = on;
+    rumi_orb_set_pyramid_staging(handle, on ? 1 : 0);     // the levels then come down behind the kernels of every frame
+}
 
 bool ORBextractor::Begin(cv::InputArray _image, std::vector<int>& vLappingArea) {
     pendingEmpty = _image.empty();

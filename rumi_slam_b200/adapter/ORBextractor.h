@@ -46,7 +46,7 @@ public:
     // Filled after every operator() call (read by Frame::ComputeStereoMatches, R/lib_src/Frame.cc:834,918-932).
     // Monocular callers that never read it can switch the device-to-host copy off.
     std::vector<cv::Mat> mvImagePyramid;
-    void SetPyramidDownload(bool on) { downloadPyramid = on; }
+    void SetPyramidDownload(bool on);
     // C-ABI handle (lets ORBmatcherAccel::ComputeStereoMatches use the device-resident pyramid in place)
     rumi_orb* Handle() const { return handle; }
 

@@ -136,6 +136,10 @@ struct rumi_orb {
     int* errHost = nullptr; int* errDev = nullptr;
     uint8_t* descBuf = nullptr; size_t descCap = 0;   // scratch of rumi_orb_describe* (images, keypoints, descriptors)
     bool pendingSingle = false;                            // rumi_orb_extract_begin issued, _end not yet called
+    // mvImagePyramid of single-frame calls: levels downloaded behind the kernels into a pinned block (rumi_orb_set_pyramid_staging)
+    bool stagePyr = false, pyrStageValid = false;
+    uint8_t* pyrStage = nullptr; size_t pyrStageCap = 0;
+    size_t pyrStageOff[kMaxLevels] = {};
     cudaStream_t auxStream = nullptr;                      // small calls: blur runs here, beside FAST / quad-tree / slots
     cudaEvent_t evFork = nullptr, evJoinAux = nullptr;
     uint8_t* outStage = nullptr; size_t outStageCap = 0;   // pinned: results of the single-frame call land here with ONE sync
@@ -698,6 +702,7 @@ void rumi_orb_destroy(rumi_orb* h) {
     cudaFree(h->octClk);
     cudaFree(h->descBuf);
     if (h->outStage) cudaFreeHost(h->outStage);
+    if (h->pyrStage) cudaFreeHost(h->pyrStage);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoinAux) cudaEventDestroy(h->evJoinAux);
     if (h->auxStream) cudaStreamDestroy(h->auxStream);
@@ -848,6 +853,7 @@ int rumi_orb_extract_batch(rumi_orb* h, const uint8_t* imgs, int n, int w, int h
     if (!imgs || w <= 0 || h_px <= 0 || n <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
     if (!kps || !desc || !n_kp || !n_mono || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad output / stride");
     CU_TRY(cudaSetDevice(h->device));
+    h->pyrStageValid = false;
     int rc = ensure_geometry(h, w, h_px);
     if (rc) return rc;
     const OrbConst& oc = h->oc;
@@ -955,6 +961,26 @@ int rumi_orb_extract_begin(rumi_orb* h, const uint8_t* img, int w, int h_px, siz
     CU_TRY(cudaMemcpyAsync(&counts[1], ws.nmono, 4, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaMemcpyAsync(sKps, ws.kps, kpBytes, cudaMemcpyDeviceToHost, ws.stream));
     CU_TRY(cudaMemcpyAsync(sKps + kpBytes, ws.desc, dBytes, cudaMemcpyDeviceToHost, ws.stream));
+    h->pyrStageValid = false;
+    if (h->stagePyr) {
+        // the pyramid of this frame follows the results into a pinned block: level 0 is the caller's image (copied on the host
+        // while the GPU works), levels 1.. come down with asynchronous copies; rumi_orb_pyramid_level then needs no round trip
+        size_t total = 0;
+        for (int l = 0; l < oc.nlevels; ++l) { h->pyrStageOff[l] = total; total += (size_t)oc.lv[l].stride * oc.lv[l].h; }
+        if (total > h->pyrStageCap) {
+            if (h->pyrStage) cudaFreeHost(h->pyrStage);
+            h->pyrStage = nullptr; h->pyrStageCap = 0;
+            CU_TRY(cudaHostAlloc((void**)&h->pyrStage, total, cudaHostAllocDefault));
+            h->pyrStageCap = total;
+        }
+        for (int l = 1; l < oc.nlevels; ++l) {
+            const LevelView v = internal_view(h, ws.pyr, l);
+            CU_TRY(cudaMemcpyAsync(h->pyrStage + h->pyrStageOff[l], v.ptr, (size_t)v.stride * v.h, cudaMemcpyDeviceToHost, ws.stream));
+        }
+        const int s0 = oc.lv[0].stride;
+        for (int y = 0; y < h_px; ++y) std::memcpy(h->pyrStage + (size_t)y * s0, img + (size_t)y * stride, (size_t)w);
+        h->pyrStageValid = true;                       // complete once the stream has been synchronised (rumi_orb_extract_end)
+    }
     h->pendingSingle = true;
     h->lastWs = 0;
     return RUMI_OK;
@@ -998,6 +1024,7 @@ int rumi_orb_extract_batch_device(rumi_orb* h, const uint8_t* d_imgs, int n, int
     if (!d_imgs || w <= 0 || h_px <= 0 || n <= 0) return fail(RUMI_ERR_EMPTY, "empty image");
     if (!d_kps || !d_desc || !d_n_kp || !d_n_mono || stride < (size_t)w) return fail(RUMI_ERR_ARG, "bad output / stride");
     CU_TRY(cudaSetDevice(h->device));
+    h->pyrStageValid = false;
     int rc = ensure_geometry(h, w, h_px);
     if (rc) return rc;
     if (cap_per_frame < h->oc.kpCap)
@@ -1091,7 +1118,19 @@ static int copy_level(rumi_orb* h, const uint8_t* base, int level, uint8_t* dst,
     if (dst_stride < (size_t)v.w) return fail(RUMI_ERR_ARG, "dst_stride too small");
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaStreamSynchronize(h->ws[h->lastWs].stream));
+    if (h->pyrStageValid && h->lastWs == 0 && base == h->ws[0].pyr) {          // staged behind the last single-frame call
+        const uint8_t* src = h->pyrStage + h->pyrStageOff[level];
+        for (int y = 0; y < v.h; ++y) std::memcpy(dst + (size_t)y * dst_stride, src + (size_t)y * v.stride, (size_t)v.w);
+        return RUMI_OK;
+    }
     CU_TRY(cudaMemcpy2D(dst, dst_stride, v.ptr, v.stride, v.w, v.h, cudaMemcpyDeviceToHost));
+    return RUMI_OK;
+}
+
+int rumi_orb_set_pyramid_staging(rumi_orb* h, int on) {
+    if (!h) return fail(RUMI_ERR_ARG, "handle is NULL");
+    h->stagePyr = on != 0;
+    if (!on) h->pyrStageValid = false;
     return RUMI_OK;
 }
 

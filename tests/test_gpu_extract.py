@@ -245,3 +245,26 @@ def test_random_shapes_and_parameters(oracle):
             assert np.array_equal(bk[i, :nkp[i]], rk) and np.array_equal(bd[i, :nkp[i]], rd), (w, h, nf, levels, scale, i)
         ex.close()
         done += 1
+
+
+def test_staged_pyramid_download(oracle):
+    """rumi_orb_set_pyramid_staging: the levels that follow a single-frame call into the pinned block are the same bytes the
+    device-side download returns; a batch call in between invalidates the block (the levels of ITS last chunk are served)."""
+    from rumi_slam_b200 import ORBextractor
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    ex._L.rumi_orb_set_pyramid_staging(ex._h, 1)
+    for seed, (w, h) in ((21, (640, 480)), (22, (641, 479)), (23, (640, 480))):
+        img = synthetic_frame(seed, w, h)
+        _, kps, desc = ex(img)
+        ref = oracle.pyramid(img)
+        got = ex.mvImagePyramid
+        for l in range(8):
+            assert got[l].shape == ref[l].shape and np.array_equal(got[l], ref[l]), (seed, l)
+        rk, rd, _ = oracle.extract(img)
+        assert np.array_equal(kps, rk) and np.array_equal(desc, rd)
+    frames = synthetic_batch(3, 640, 480, seed0=500)
+    ex.extract_batch(frames)
+    got = ex.mvImagePyramid                                   # served by the device-side path again: the last chunk (= frame 2)
+    ref = oracle.pyramid(frames[2])
+    for l in range(8):
+        assert np.array_equal(got[l], ref[l]), l

@@ -79,7 +79,8 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     uint8_t *pyr = nullptr, *blur = nullptr;
     uint32_t *cand = nullptr, *candOrdered = nullptr, *sel = nullptr;
-    int *countBase = nullptr;           // [chunk] frameDone counters followed by levelCount: ONE memset clears both
+    int *countBase = nullptr;           // [chunk] frameDone counters, [4] bigCount (+ pad), then levelCount: ONE memset clears all
+    int *bigList = nullptr;             // [chunk * nlevels] work list of the quad-tree's second pass
     int *levelCount = nullptr, *cellOff = nullptr, *cellCount = nullptr, *selCount = nullptr, *slot = nullptr;
     uint64_t* bigKeys = nullptr;
     KeyPointRec* kps = nullptr;
@@ -124,7 +125,7 @@ struct rumi_orb {
     struct StripVariant { int nstrips; const int2* ranges; size_t smemBytes; int buf1Offset, rowTabOffset; int rowsPerItem[kMaxLevels]; };
     std::vector<StripVariant> stripVariants;          // ascending nstrips
     int stripForce = 0;                               // RUMI_PYR_STRIPS: force a strip count (tuning)
-    int smemKeys = 4096, maxNodeCap = 0;
+    int smemKeys = 4096, smemKeysBig = 0, maxNodeCap = 0;
     Workspace ws[kMaxWs];          // chunk c runs on ws[c % nws]: copies and kernels of consecutive chunks overlap
     int nws = 4;
     int skipMask = 0;              // RUMI_SKIP_STAGES (timing experiments only: results are wrong) bit s = skip stage s
@@ -163,7 +164,7 @@ namespace {
 
 void free_workspace(Workspace& w) {
     cudaFree(w.pyr); cudaFree(w.blur); cudaFree(w.cand); cudaFree(w.candOrdered); cudaFree(w.sel);
-    cudaFree(w.countBase); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
+    cudaFree(w.countBase); cudaFree(w.bigList); cudaFree(w.cellOff); cudaFree(w.cellCount); cudaFree(w.selCount); cudaFree(w.slot);
     cudaFree(w.bigKeys); cudaFree(w.kps); cudaFree(w.desc); cudaFree(w.nkp); cudaFree(w.nmono);
     if (w.hIn) cudaFreeHost(w.hIn);
     if (w.hOut) cudaFreeHost(w.hOut);
@@ -191,8 +192,9 @@ int alloc_workspace(rumi_orb* h, Workspace& w) {
     CU_TRY(cudaMalloc(&w.cand, 4 * h->candElems));
     CU_TRY(cudaMalloc(&w.candOrdered, 4 * h->candElems));
     CU_TRY(cudaMalloc(&w.bigKeys, 8 * h->bigKeysElems));
-    CU_TRY(cudaMalloc(&w.countBase, 4 * n * (oc.nlevels + 1)));
-    w.levelCount = w.countBase + n;
+    CU_TRY(cudaMalloc(&w.countBase, 4 * (n * (oc.nlevels + 1) + 4)));
+    w.levelCount = w.countBase + n + 4;
+    CU_TRY(cudaMalloc(&w.bigList, 4 * n * oc.nlevels));
     CU_TRY(cudaMalloc(&w.selCount, 4 * n * oc.nlevels));
     CU_TRY(cudaMalloc(&w.cellOff, 4 * n * oc.totalCells));
     CU_TRY(cudaMalloc(&w.cellCount, 4 * n * oc.totalCells));
@@ -438,8 +440,11 @@ int build_geometry(rumi_orb* h, int W, int H) {
     h->maxNodeCap = nodeCap;
     // 2048 keys in shared memory (16 KB): five problems per SM stay resident, which is what hides the latency of the
     // serial phases; a level with more candidates sorts in the global scratch instead
-    h->smemKeys = 2048;
+    h->smemKeys = getenv("RUMI_OCT_KEYS") ? atoi(getenv("RUMI_OCT_KEYS")) : 2048;
     while (h->smemKeys > 256 && octree_smem_bytes(h->smemKeys, nodeCap, 256) > 200 * 1024) h->smemKeys >>= 1;
+    // second pass (levels denser than smemKeys): as many keys as one SM's shared memory takes, up to 16384
+    h->smemKeysBig = 16384;
+    while (h->smemKeysBig > h->smemKeys && octree_smem_bytes(h->smemKeysBig, nodeCap, 256) > 200 * 1024) h->smemKeysBig >>= 1;
     if (octree_smem_bytes(h->smemKeys, nodeCap, 256) > 220 * 1024)
         return fail(RUMI_ERR_CAPACITY, "nfeatures %d needs more shared memory than one SM has", h->nfeatures);
     return RUMI_OK;
@@ -518,7 +523,7 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
         cv.src[l] = l == 0 ? l0 : internal_view(h, w.pyr, l);
         cv.blur[l] = internal_view(h, w.blur, l);
     }
-    if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.countBase, 0, 4ull * (h->chunk + (size_t)n * oc.nlevels), s));
+    if (!(h->skipMask & 2)) CU_TRY(cudaMemsetAsync(w.countBase, 0, 4ull * (h->chunk + 4 + (size_t)n * oc.nlevels), s));
     if (h->profile) prof_event(h, s);
     // K1: all levels in ONE launch (a CTA carries a strip of a frame through every level in shared memory) when every
     // source row can be read as aligned 32-bit words: always true for the internal buffers, caller device memory only if
@@ -606,10 +611,15 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     const bool fuse = !(skip & 4) && !slotsKernel;
     oa.fuseSlots = fuse ? 1 : 0;
     oa.frameDone = w.countBase;
+    static const bool onePass = getenv("RUMI_OCTREE_ONE_PASS") != nullptr;          // A/B: big levels sorted in global memory
+    oa.bigCount = w.countBase + h->chunk; oa.bigList = (onePass || h->smemKeysBig <= h->smemKeys) ? nullptr : w.bigList;
+    oa.smemKeysBig = h->smemKeysBig;
+    // a few frames never fill the SMs: every level CTA gets the large key buffer at once and the second launch is saved
+    if (n <= 4 && oa.bigList) { oa.smemKeys = h->smemKeysBig; oa.bigList = nullptr; }
     oa.slots.sel = w.sel; oa.slots.selCount = w.selCount; oa.slots.lap0 = lap0; oa.slots.lap1 = lap1; oa.slots.slot = w.slot;
     oa.slots.nkp = dNkp; oa.slots.nmono = dNmono;
     if (!(skip & 4)) launch_octree(oa, oc, sh);
-    prof_mark(h, s, ST_OCTREE, 1);
+    prof_mark(h, s, ST_OCTREE, oa.bigList ? 2 : 1);
     if (!fuse) launch_assign_slots(da, oc, sh);
     prof_mark(h, s, ST_SLOTS, fuse ? 0 : 1);
     if (fork) CU_TRY(cudaStreamWaitEvent(s, h->evJoinAux, 0));

@@ -124,6 +124,11 @@ struct OctreeArgs {
     int fuseSlots;
     int* frameDone;          // [frame], zeroed per call
     SlotArgs slots;
+    // levels with more candidates than smemKeys: appended to bigList by the first launch, processed by a second one with a
+    // key buffer of smemKeysBig keys (bigList == nullptr: everything in the first launch, global scratch for big levels)
+    int* bigCount;           // zeroed per call
+    int* bigList;            // [frame * nlevels] (frame << 8 | level)
+    int smemKeysBig;
 };
 void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s);
 size_t octree_smem_bytes(int smemKeys, int maxNodeCap, int nthreads);

@@ -4,6 +4,8 @@
 // work buffers out of shared memory (or a global scratch for pathological candidate counts) and runs it.
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "slots.cuh"
 #include "octree_core.cuh"
@@ -80,6 +82,41 @@ __device__ void block_sort_regs(uint64_t* a, int n, int tid) {
     __syncthreads();
 }
 
+// Exclusive scan of the bucket counts in start[0 .. nb) (nb <= 4 * nthr): per-thread chunk + warp scans + one pass over the
+// warp sums; start[nb] = n.  Sets fill[nb] when a bucket holds more than 192 keys.  Ends with a barrier.
+__device__ __forceinline__ void bucket_scan(int* start, int* fill, int nb, int n, int tid, int nthr) {
+    const int per = (nb + nthr - 1) / nthr;
+    const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+    int s = 0, mx = 0;
+    for (int b = b0; b < b1; ++b) { s += start[b]; mx = max(mx, start[b]); }
+    if (mx > 192) fill[nb] = 1;                                      // crowded bucket: quadratic ranking would be slow
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ int wsum[33];
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int t = lane < nw ? wsum[lane] : 0;
+        int ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, ti, o);
+            if (lane >= o) ti += u;
+        }
+        if (lane < nw) wsum[lane] = ti - t;
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s;
+    for (int b = b0; b < b1; ++b) { const int c = start[b]; start[b] = run; run += c; }
+    if (tid == nthr - 1) start[nb] = n;
+    __syncthreads();
+}
+
 // Block-wide ascending sort of the first n (<= 16 * blockDim.x) u64 keys by BUCKETS of their leading bits: bucket(key) =
 // key >> bshift < nb.  Tree keys are (path code | insertion index | response): the code of a candidate is unique (every
 // leaf of the full-depth tree is one pixel), the leading 2p digits of the code spread the keys over nb = roots * 4^p
@@ -103,39 +140,7 @@ __device__ bool block_bucket_sort(uint64_t* a, int n, int bshift, int nb, int* s
         if (i < n) atomicAdd(&start[(int)(v[r] >> bshift)], 1);
     }
     __syncthreads();
-    // exclusive scan of the bucket counts (nb <= 4 * nthr): per-thread chunk + warp scans + one pass over the warp sums
-    {
-        const int per = (nb + nthr - 1) / nthr;
-        const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
-        int s = 0, mx = 0;
-        for (int b = b0; b < b1; ++b) { s += start[b]; mx = max(mx, start[b]); }
-        if (mx > 192) fill[nb] = 1;                                  // crowded bucket: quadratic ranking would be slow
-        const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-        int incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        __shared__ int wsum[33];
-        if (lane == 31) wsum[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            const int t = lane < nw ? wsum[lane] : 0;
-            int ti = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xFFFFFFFFu, ti, o);
-                if (lane >= o) ti += u;
-            }
-            if (lane < nw) wsum[lane] = ti - t;
-        }
-        __syncthreads();
-        int run = wsum[wid] + incl - s;
-        for (int b = b0; b < b1; ++b) { const int c = start[b]; start[b] = run; run += c; }
-        if (tid == nthr - 1) start[nb] = n;
-    }
-    __syncthreads();
+    bucket_scan(start, fill, nb, n, tid, nthr);
     if (fill[nb]) return false;                                        // uniform: read after the barrier
 #pragma unroll
     for (int r = 0; r < E; ++r) {
@@ -173,6 +178,43 @@ __device__ bool block_bucket_sort(uint64_t* a, int n, int bshift, int nb, int* s
     return true;
 }
 
+// Loop form of the bucket sort for more keys than a thread holds in registers (dense frames: thousands of candidates on
+// a level).  a[] is the shared-memory key buffer; the keys are scattered bucket by bucket into `bounce` (global memory,
+// >= n u64, L2-resident), copied back, ranked inside their now contiguous bucket and bounced once more into their final
+// places: four coalesced-or-scattered passes over 8 n bytes of L2 plus ~n * (bucket size) shared reads, against the
+// ~n log^2 n shared compare-exchanges of the bitonic network (442 k -> 30 k cycles for 10 700 keys).  scratch: ints [2 * nb + 2].
+__device__ bool block_bucket_sort_loop(uint64_t* a, int n, int bshift, int nb, int* scratch, uint64_t* bounce, int tid,
+                                       int nthr) {
+    int* start = scratch;                 // [nb + 1]
+    int* fill = scratch + nb + 1;         // [nb] (+1: crowded flag)
+    for (int b = tid; b <= nb; b += nthr) { start[b] = 0; fill[b] = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) atomicAdd(&start[(int)(a[i] >> bshift)], 1);
+    __syncthreads();
+    bucket_scan(start, fill, nb, n, tid, nthr);
+    if (fill[nb]) return false;                                        // uniform: read after the barrier
+    for (int i = tid; i < n; i += nthr) {
+        const uint64_t k = a[i];
+        const int b = (int)(k >> bshift);
+        bounce[start[b] + atomicAdd(&fill[b], 1)] = k;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) a[i] = __ldcg(bounce + i);
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) {
+        const uint64_t k = a[i];
+        const int b = (int)(k >> bshift);
+        const int p0 = start[b], p1 = start[b + 1];
+        int c = p0;
+        for (int p = p0; p < p1; ++p) c += a[p] < k;                   // distinct keys
+        bounce[c] = k;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) a[i] = __ldcg(bounce + i);
+    __syncthreads();
+    return true;
+}
+
 // Ascending sort of n <= 2 * blockDim.x u64 keys by counting, per key, the smaller ones (distinct keys): two passes
 // over shared memory instead of a sorting network (the leaf-list keys: a few hundred).
 __device__ void block_rank_sort(uint64_t* a, int n, int tid, int nthr) {
@@ -203,6 +245,7 @@ struct BlockCtx {
     long long last;
     int* sortScratch;        // shared memory that is idle while the tree keys are sorted
     int sortScratchBytes;
+    uint64_t* bounce;        // global scratch of the loop-form bucket sort (>= the level's candidate capacity), or nullptr
     // adds the cycles since the previous mark to accumulator `id` (thread 0 only)
     __device__ __forceinline__ void mark(int id) {
         if (clk && tid == 0) { const long long now = clock64(); clk[id] += now - last; last = now; }
@@ -223,7 +266,10 @@ struct BlockCtx {
         else if (fits && m > nthr && m <= 2 * nthr) { if (block_bucket_sort<2>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
         else if (fits && m > 2 * nthr && m <= 4 * nthr) { if (block_bucket_sort<4>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
         else if (fits && m > 4 * nthr && m <= 8 * nthr) { if (block_bucket_sort<8>(a, m, bshift, nb, sortScratch, tid, nthr)) return; }
-        sort_u64(a, npad);                                 // > 2048 keys, crowded buckets or a tiny problem
+        else if (m > 8 * nthr && bounce && nb <= 4 * nthr && (size_t)sortScratchBytes >= 4 * (size_t)(2 * nb + 2)) {
+            if (block_bucket_sort_loop(a, m, bshift, nb, sortScratch, bounce, tid, nthr)) return;
+        }
+        sort_u64(a, npad);                                 // crowded buckets, keys in global memory or a tiny problem
     }
     __device__ __forceinline__ int warp_id() const { return tid >> 5; }
     __device__ __forceinline__ int num_warps() const { return nthr >> 5; }
@@ -297,15 +343,13 @@ size_t octree_smem_bytes(int smemKeys, int maxNodeCap, int nthreads) {
     return octree_layout(smemKeys, maxNodeCap, nthreads).total;
 }
 
-__global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_constant__ OctreeArgs a,
-                                                             const __grid_constant__ OrbConst oc) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int f = blockIdx.x, l = blockIdx.y + a.levelFirst;
+// One (frame, level) problem, by a whole CTA.  smemKeys = keys that fit the shared-memory key buffer of THIS launch.
+__device__ void octree_problem(const OctreeArgs& a, const OrbConst& oc, uint8_t* smem, int smemKeys, int f, int l) {
     const LevelGeom& g = oc.lv[l];
-    const OctreeSmemLayout L = octree_layout(a.smemKeys, a.maxNodeCap, kOctThreads);
+    const OctreeSmemLayout L = octree_layout(smemKeys, a.maxNodeCap, kOctThreads);
     // while the tree keys are sorted everything between the key buffer and the histograms is idle
     BlockCtx ctx{(int)threadIdx.x, kOctThreads, (a.dbgClk && f == 0) ? a.dbgClk + 16 * l : nullptr, clock64(),
-                 reinterpret_cast<int*>(smem + L.lkeys), (int)(L.hist - L.lkeys)};
+                 reinterpret_cast<int*>(smem + L.lkeys), (int)(L.hist - L.lkeys), nullptr};
 
     const int M = a.levelCount[(long long)f * oc.nlevels + l];
     const uint32_t* cand = a.cand + a.candLevelOff[l] + (long long)f * g.candCap;
@@ -319,7 +363,7 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
         const int ncell = g.nCols * g.nRows;
         const int* cc = a.cellCount + (long long)f * oc.totalCells + g.cellBase;
         const int* co = a.cellOff + (long long)f * oc.totalCells + g.cellBase;
-        int* cellDst = ncell + 1 <= 2 * a.smemKeys
+        int* cellDst = ncell + 1 <= 2 * smemKeys
                            ? reinterpret_cast<int*>(smem + L.keys)
                            : reinterpret_cast<int*>(a.bigKeys + a.bigKeysLevelOff[l] + (long long)f * a.bigKeysCap[l]);
         const int chunk = (ncell + kOctThreads - 1) / kOctThreads;
@@ -357,8 +401,9 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
 
     OctreeWork w;
     const int Mpad = next_pow2(M > 8 ? M : 8);
-    w.keys = Mpad <= a.smemKeys ? reinterpret_cast<uint64_t*>(smem + L.keys)
-                                : a.bigKeys + a.bigKeysLevelOff[l] + (long long)f * a.bigKeysCap[l];
+    uint64_t* const gkeys = a.bigKeys + a.bigKeysLevelOff[l] + (long long)f * a.bigKeysCap[l];
+    w.keys = Mpad <= smemKeys ? reinterpret_cast<uint64_t*>(smem + L.keys) : gkeys;
+    if (Mpad <= smemKeys) ctx.bounce = gkeys;          // keys in shared memory: the global buffer is free as sort scratch
     w.lkeys = reinterpret_cast<uint64_t*>(smem + L.lkeys);
     w.pend = reinterpret_cast<uint64_t*>(smem + L.pend);
     w.lsort = reinterpret_cast<uint64_t*>(smem + L.lsort);
@@ -389,11 +434,42 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(a.frameDone + f, 1) == (int)gridDim.y - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(a.frameDone + f, 1) == oc.nlevels - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     assign_slots_frame(a.slots, oc, f, threadIdx.x);
+}
+
+
+// Pass 0: one CTA per (frame, level).  A level with more candidates than the shared-memory key buffer holds (2048: denser
+// than the benchmark frames, common on real textured images) is not sorted in global memory here -- that path costs 5x
+// per key -- but appended to a work list for pass 1.
+__global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_constant__ OctreeArgs a,
+                                                             const __grid_constant__ OrbConst oc) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int f = blockIdx.x, l = blockIdx.y + a.levelFirst;
+    if (a.bigList) {
+        const int M = a.levelCount[(long long)f * oc.nlevels + l];
+        if (next_pow2(M > 8 ? M : 8) > a.smemKeys) {
+            if (threadIdx.x == 0) a.bigList[atomicAdd(a.bigCount, 1)] = (f << 8) | l;
+            return;
+        }
+    }
+    octree_problem(a, oc, smem, a.smemKeys, f, l);
+}
+
+// Pass 1: a few persistent CTAs with a large key buffer (16384 keys = 128 KB of shared memory) walk the work list; on sparse
+// frames the list is empty and the launch costs a couple of microseconds.
+__global__ void __launch_bounds__(kOctThreads) octree_big_kernel(const __grid_constant__ OctreeArgs a,
+                                                                 const __grid_constant__ OrbConst oc) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = *a.bigCount;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int item = a.bigList[i];
+        octree_problem(a, oc, smem, a.smemKeysBig, item >> 8, item & 0xFF);
+        __syncthreads();                                   // the next problem reuses the shared memory
+    }
 }
 
 void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
@@ -406,11 +482,20 @@ void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
         for (int l = 0; l < oc.nlevels; ++l) {
             OctreeArgs b = a;
             b.levelFirst = l;
+            b.bigList = nullptr;                // everything in one pass
             octree_kernel<<<dim3(a.nframes, 1), kOctThreads, smem, s>>>(b, oc);
         }
         return;
     }
     octree_kernel<<<dim3(a.nframes, oc.nlevels), kOctThreads, smem, s>>>(a, oc);
+    if (a.bigList) {
+        const size_t smemBig = octree_smem_bytes(a.smemKeysBig, a.maxNodeCap, kOctThreads);
+        cudaFuncSetAttribute(octree_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBig);
+        static int maxCtas = -1;                // RUMI_OCT_BIG_CTAS: persistent CTAs of pass 1 (A/B runs)
+        if (maxCtas < 0) { const char* e = getenv("RUMI_OCT_BIG_CTAS"); maxCtas = e ? std::max(1, atoi(e)) : 148; }
+        const int ctas = std::min(a.nframes * oc.nlevels, maxCtas);
+        octree_big_kernel<<<ctas, kOctThreads, smemBig, s>>>(a, oc);
+    }
 }
 
 }  // namespace rumi

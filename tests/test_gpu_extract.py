@@ -268,3 +268,31 @@ def test_staged_pyramid_download(oracle):
     ref = oracle.pyramid(frames[2])
     for l in range(8):
         assert np.array_equal(got[l], ref[l]), l
+
+
+def test_dense_frames_take_the_large_key_paths(oracle):
+    """Textured (noisy) frames put thousands of FAST candidates on a level: more than the 2048-key shared-memory buffer of
+    the quad-tree's first pass.  Single frames run every level with the large buffer (loop-form bucket sort), batches defer
+    dense levels to the second pass, and beyond 16384 keys the global-memory network takes over -- all bit-exact."""
+    w, h = 640, 480
+    rng = np.random.default_rng(5)
+    base = synthetic_frame(3, w, h).astype(np.int32)
+    frames = np.stack([np.clip(base + rng.integers(-a, a + 1, base.shape), 0, 255).astype(np.uint8)
+                       for a in (8, 14, 22, 30, 60, 0, 12, 40)])
+    refs = [oracle.extract(f, nfeatures=1000) for f in frames]
+    single = make(1000)
+    dense = 0
+    for f, (rk, rd, rmono) in zip(frames, refs):
+        mono, kps, desc = single(f)
+        dense += len(single.debug_candidates(0)) > 2048
+        assert mono == rmono and np.array_equal(desc, rd)
+        for fld in ("x", "y", "size", "angle", "response", "octave"):
+            assert np.array_equal(kps[fld], rk[fld]), fld
+    assert dense >= 6                                    # the inputs do exercise the dense paths
+    ex = make(1000, max_batch=8)                         # one chunk of 8: sparse and dense levels in the same launch
+    kps, desc, nkp, nmono = ex.extract_batch(frames)
+    for i, (rk, rd, rmono) in enumerate(refs):
+        assert nkp[i] == len(rk) and nmono[i] == rmono
+        assert np.array_equal(desc[i, :nkp[i]], rd)
+        for fld in ("x", "y", "angle", "response", "octave"):
+            assert np.array_equal(kps[i, :nkp[i]][fld], rk[fld]), fld

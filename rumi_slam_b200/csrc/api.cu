@@ -444,7 +444,7 @@ int build_geometry(rumi_orb* h, int W, int H) {
     while (h->smemKeys > 256 && octree_smem_bytes(h->smemKeys, nodeCap, 256) > 200 * 1024) h->smemKeys >>= 1;
     // second pass (levels denser than smemKeys): as many keys as one SM's shared memory takes, up to 16384
     h->smemKeysBig = 16384;
-    while (h->smemKeysBig > h->smemKeys && octree_smem_bytes(h->smemKeysBig, nodeCap, 256) > 200 * 1024) h->smemKeysBig >>= 1;
+    while (h->smemKeysBig > h->smemKeys && octree_smem_bytes(h->smemKeysBig, nodeCap, 1024) > 200 * 1024) h->smemKeysBig >>= 1;
     if (octree_smem_bytes(h->smemKeys, nodeCap, 256) > 220 * 1024)
         return fail(RUMI_ERR_CAPACITY, "nfeatures %d needs more shared memory than one SM has", h->nfeatures);
     return RUMI_OK;
@@ -615,7 +615,11 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     oa.bigCount = w.countBase + h->chunk; oa.bigList = (onePass || h->smemKeysBig <= h->smemKeys) ? nullptr : w.bigList;
     oa.smemKeysBig = h->smemKeysBig;
     // a few frames never fill the SMs: every level CTA gets the large key buffer at once and the second launch is saved
-    if (n <= 4 && oa.bigList) { oa.smemKeys = h->smemKeysBig; oa.bigList = nullptr; }
+    // and 1024 threads, which hide the latencies nobody else on the SM would (RUMI_OCT_NARROW=1: 256, A/B runs)
+    static const bool narrow = getenv("RUMI_OCT_NARROW") != nullptr;
+    static const int wideThreads = getenv("RUMI_OCT_WIDE") ? atoi(getenv("RUMI_OCT_WIDE")) : 1024;
+    oa.threads = 256;
+    if (n <= 4 && oa.bigList) { oa.smemKeys = h->smemKeysBig; oa.bigList = nullptr; oa.threads = narrow ? 256 : wideThreads; }
     oa.slots.sel = w.sel; oa.slots.selCount = w.selCount; oa.slots.lap0 = lap0; oa.slots.lap1 = lap1; oa.slots.slot = w.slot;
     oa.slots.nkp = dNkp; oa.slots.nmono = dNmono;
     if (!(skip & 4)) launch_octree(oa, oc, sh);

@@ -126,6 +126,7 @@ struct OctreeArgs {
     SlotArgs slots;
     // levels with more candidates than smemKeys: appended to bigList by the first launch, processed by a second one with a
     // key buffer of smemKeysBig keys (bigList == nullptr: everything in the first launch, global scratch for big levels)
+    int threads;             // CTA width of the first launch: 256, or 1024 for calls of a few frames (0 = 256)
     int* bigCount;           // zeroed per call
     int* bigList;            // [frame * nlevels] (frame << 8 | level)
     int smemKeysBig;

@@ -12,7 +12,8 @@
 
 namespace rumi {
 
-constexpr int kOctThreads = 256;
+constexpr int kOctThreads = 256;        // pass 0 of a chunk: many CTAs per SM hide each other's latencies
+constexpr int kOctThreadsBig = 1024;    // calls of a few frames and pass 1: one CTA per SM, so the CTA brings its own warps
 
 // Block-wide ascending sort of n u64 keys (n a power of two, E <= n <= E * blockDim.x) held E per thread in REGISTERS:
 // a bitonic network whose stages with partner distance j < E are pure register compare-exchanges, E <= j < 32 E are
@@ -226,11 +227,13 @@ __device__ void block_rank_sort(uint64_t* a, int n, int tid, int nthr) {
         v[r] = i < n ? a[i] : ~0ull;
         rank[r] = 0;
     }
+    if (tid < n) {                                        // threads without a key only join the barriers
 #pragma unroll 8
-    for (int j = 0; j < n; ++j) {                         // n is a power of two >= 8: the loads of 8 keys are in flight
-        const uint64_t o = a[j];
+        for (int j = 0; j < n; ++j) {                     // n is a power of two >= 8: the loads of 8 keys are in flight
+            const uint64_t o = a[j];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) rank[r] += (o < v[r]) || (o == v[r] && j < tid + r * nthr);
+            for (int r = 0; r < 2; ++r) rank[r] += (o < v[r]) || (o == v[r] && j < tid + r * nthr);
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -254,7 +257,7 @@ struct BlockCtx {
     __device__ __forceinline__ void sync_warp() { __syncwarp(); }
     // ascending sort of n (power of two >= 8) u64 keys; everything written before the call is visible (callers sync)
     __device__ __forceinline__ void sort_u64(uint64_t* a, int n) {
-        if (n <= nthr) block_rank_sort(a, n, tid, nthr);
+        if (n <= 256) block_rank_sort(a, n, tid, nthr);   // leaf lists: one pass over n keys per thread
         else if (n <= 8 * nthr) block_sort_regs<8>(a, n, tid);
         else if (n <= 16 * nthr) block_sort_regs<16>(a, n, tid);
         else bitonic_sort_u64(*this, a, n);               // global-memory scratch for pathological candidate counts
@@ -346,9 +349,10 @@ size_t octree_smem_bytes(int smemKeys, int maxNodeCap, int nthreads) {
 // One (frame, level) problem, by a whole CTA.  smemKeys = keys that fit the shared-memory key buffer of THIS launch.
 __device__ void octree_problem(const OctreeArgs& a, const OrbConst& oc, uint8_t* smem, int smemKeys, int f, int l) {
     const LevelGeom& g = oc.lv[l];
-    const OctreeSmemLayout L = octree_layout(smemKeys, a.maxNodeCap, kOctThreads);
+    const int nthr = blockDim.x;
+    const OctreeSmemLayout L = octree_layout(smemKeys, a.maxNodeCap, nthr);
     // while the tree keys are sorted everything between the key buffer and the histograms is idle
-    BlockCtx ctx{(int)threadIdx.x, kOctThreads, (a.dbgClk && f == 0) ? a.dbgClk + 16 * l : nullptr, clock64(),
+    BlockCtx ctx{(int)threadIdx.x, nthr, (a.dbgClk && f == 0) ? a.dbgClk + 16 * l : nullptr, clock64(),
                  reinterpret_cast<int*>(smem + L.lkeys), (int)(L.hist - L.lkeys), nullptr};
 
     const int M = a.levelCount[(long long)f * oc.nlevels + l];
@@ -366,7 +370,7 @@ __device__ void octree_problem(const OctreeArgs& a, const OrbConst& oc, uint8_t*
         int* cellDst = ncell + 1 <= 2 * smemKeys
                            ? reinterpret_cast<int*>(smem + L.keys)
                            : reinterpret_cast<int*>(a.bigKeys + a.bigKeysLevelOff[l] + (long long)f * a.bigKeysCap[l]);
-        const int chunk = (ncell + kOctThreads - 1) / kOctThreads;
+        const int chunk = (ncell + nthr - 1) / nthr;
         const int c0 = min((int)threadIdx.x * chunk, ncell), c1 = min(c0 + chunk, ncell);
         int s = 0;
         for (int c = c0; c < c1; ++c) s += cc[c];
@@ -376,11 +380,11 @@ __device__ void octree_problem(const OctreeArgs& a, const OrbConst& oc, uint8_t*
         if (threadIdx.x == 0) cellDst[ncell] = M;
         __syncthreads();
         constexpr int U = 4;
-        for (int i0 = threadIdx.x; i0 < M; i0 += U * kOctThreads) {
+        for (int i0 = threadIdx.x; i0 < M; i0 += U * nthr) {
             uint32_t v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kOctThreads;
+                const int i = i0 + u * nthr;
                 if (i < M) {
                     int lo = 0, hi = ncell;                 // largest c with cellDst[c] <= i (empty cells share a start)
                     while (hi - lo > 1) {
@@ -392,7 +396,7 @@ __device__ void octree_problem(const OctreeArgs& a, const OrbConst& oc, uint8_t*
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * kOctThreads;
+                const int i = i0 + u * nthr;
                 if (i < M) ordered[i] = v[u];
             }
         }
@@ -445,8 +449,9 @@ __device__ void octree_problem(const OctreeArgs& a, const OrbConst& oc, uint8_t*
 // Pass 0: one CTA per (frame, level).  A level with more candidates than the shared-memory key buffer holds (2048: denser
 // than the benchmark frames, common on real textured images) is not sorted in global memory here -- that path costs 5x
 // per key -- but appended to a work list for pass 1.
-__global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_constant__ OctreeArgs a,
-                                                             const __grid_constant__ OrbConst oc) {
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) octree_kernel(const __grid_constant__ OctreeArgs a,
+                                                          const __grid_constant__ OrbConst oc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int f = blockIdx.x, l = blockIdx.y + a.levelFirst;
     if (a.bigList) {
@@ -461,8 +466,8 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(const __grid_consta
 
 // Pass 1: a few persistent CTAs with a large key buffer (16384 keys = 128 KB of shared memory) walk the work list; on sparse
 // frames the list is empty and the launch costs a couple of microseconds.
-__global__ void __launch_bounds__(kOctThreads) octree_big_kernel(const __grid_constant__ OctreeArgs a,
-                                                                 const __grid_constant__ OrbConst oc) {
+__global__ void __launch_bounds__(kOctThreadsBig) octree_big_kernel(const __grid_constant__ OctreeArgs a,
+                                                                    const __grid_constant__ OrbConst oc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int n = *a.bigCount;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
@@ -473,9 +478,12 @@ __global__ void __launch_bounds__(kOctThreads) octree_big_kernel(const __grid_co
 }
 
 void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
-    const size_t smem = octree_smem_bytes(a.smemKeys, a.maxNodeCap, kOctThreads);
+    const bool wide = a.threads > kOctThreads;
+    const int nthr = wide ? a.threads : kOctThreads;          // the 1024-thread build also runs with 512
+    auto kernel = wide ? octree_kernel<kOctThreadsBig> : octree_kernel<kOctThreads>;
+    const size_t smem = octree_smem_bytes(a.smemKeys, a.maxNodeCap, nthr);
     // per device and cheap: set on every launch rather than cached in a process-wide flag (a process may drive several GPUs)
-    if (smem > 48 * 1024) cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     static int split = -1;                      // RUMI_OCTREE_SPLIT=1: one launch per level (per-level timing under ncu)
     if (split < 0) { const char* e = getenv("RUMI_OCTREE_SPLIT"); split = e && e[0] == '1'; }
     if (split) {
@@ -483,18 +491,18 @@ void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
             OctreeArgs b = a;
             b.levelFirst = l;
             b.bigList = nullptr;                // everything in one pass
-            octree_kernel<<<dim3(a.nframes, 1), kOctThreads, smem, s>>>(b, oc);
+            kernel<<<dim3(a.nframes, 1), nthr, smem, s>>>(b, oc);
         }
         return;
     }
-    octree_kernel<<<dim3(a.nframes, oc.nlevels), kOctThreads, smem, s>>>(a, oc);
+    kernel<<<dim3(a.nframes, oc.nlevels), nthr, smem, s>>>(a, oc);
     if (a.bigList) {
-        const size_t smemBig = octree_smem_bytes(a.smemKeysBig, a.maxNodeCap, kOctThreads);
+        const size_t smemBig = octree_smem_bytes(a.smemKeysBig, a.maxNodeCap, kOctThreadsBig);
         cudaFuncSetAttribute(octree_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBig);
         static int maxCtas = -1;                // RUMI_OCT_BIG_CTAS: persistent CTAs of pass 1 (A/B runs)
         if (maxCtas < 0) { const char* e = getenv("RUMI_OCT_BIG_CTAS"); maxCtas = e ? std::max(1, atoi(e)) : 148; }
         const int ctas = std::min(a.nframes * oc.nlevels, maxCtas);
-        octree_big_kernel<<<ctas, kOctThreads, smemBig, s>>>(a, oc);
+        octree_big_kernel<<<ctas, kOctThreadsBig, smemBig, s>>>(a, oc);
     }
 }
 

@@ -286,13 +286,22 @@ RUMI_HD void distribute_quadtree(Ctx& ctx, const uint32_t* cand, int M, int N, c
     const int Mpad = next_pow2(M > 8 ? M : 8);
 
     // 1. keys
-    for (int i = ctx.tid; i < Mpad; i += ctx.nthr) {
-        uint64_t k = ~0ull;
-        if (i < M) {
-            const uint32_t c = cand[i];
-            k = make_tree_key(tree_code(cand_x(c), cand_y(c), g.hX, g.nIni, height, D), (uint32_t)i, cand_resp(c));
+    // four candidates per thread and trip: their (L2-latency) loads are in flight together
+    for (int i0 = ctx.tid; i0 < Mpad; i0 += 4 * ctx.nthr) {
+        uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * ctx.nthr;
+            c[u] = i < M ? cand[i] : 0u;
         }
-        w.keys[i] = k;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * ctx.nthr;
+            if (i >= Mpad) break;
+            w.keys[i] = i < M ? make_tree_key(tree_code(cand_x(c[u]), cand_y(c[u]), g.hX, g.nIni, height, D), (uint32_t)i,
+                                              cand_resp(c[u]))
+                              : ~0ull;
+        }
     }
     for (int i = ctx.tid; i < 2 * (kMaxTreeDepth + 2); i += ctx.nthr) w.hist[i] = 0;
     ctx.sync();

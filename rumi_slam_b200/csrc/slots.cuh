@@ -1,6 +1,6 @@
 // Output slots of one frame's key points (ORBextractor::operator(), R/lib_src/ORBextractor.cc:1077-1085): key points inside the
 // lapping area fill the output from the back, the others from the front, both in level order.  Two prefix sums replace the
-// sequential front / back fill.  Called by a whole CTA of 256 threads: either the stand-alone kernel (describe.cu) or the last
+// sequential front / back fill.  Called by a whole CTA of >= 256 threads (the first 256 work, the others only join the barriers): either the stand-alone kernel (describe.cu) or the last
 // quad-tree CTA of the frame (octree.cu); the inputs were written by other CTAs, so they are read past L1 (__ldcg).
 #pragma once
 #include "kernels.cuh"
@@ -41,7 +41,7 @@ __device__ __forceinline__ void assign_slots_frame(const SlotArgs& a, const OrbC
         const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if ((tid & 31) >= o) incl += v;
     }
-    if ((tid & 31) == 31) s_part[tid >> 5] = incl;
+    if ((tid & 31) == 31 && tid < 256) s_part[tid >> 5] = incl;
     __syncthreads();
     int warpBase = 0, total = 0;
 #pragma unroll

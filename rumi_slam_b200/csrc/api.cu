@@ -611,15 +611,23 @@ int run_chunk(rumi_orb* h, Workspace& w, const LevelView& l0, bool l0Internal, i
     const bool fuse = !(skip & 4) && !slotsKernel;
     oa.fuseSlots = fuse ? 1 : 0;
     oa.frameDone = w.countBase;
-    static const bool onePass = getenv("RUMI_OCTREE_ONE_PASS") != nullptr;          // A/B: big levels sorted in global memory
-    oa.bigCount = w.countBase + h->chunk; oa.bigList = (onePass || h->smemKeysBig <= h->smemKeys) ? nullptr : w.bigList;
+    // Quad-tree passes.  A chunk runs ONE launch as long as this handle has never met a level with more candidates than the
+    // first pass keeps in shared memory (such a level is then sorted in global memory: correct, slow, and it raises the
+    // mapped flag errHost[2]); from the next chunk on dense levels are deferred to a second launch with a large key buffer.
+    // Sparse workloads never pay for the second launch (0.4 % of the resident rate), dense ones pay once for learning.
+    // RUMI_OCTREE_ONE_PASS=1 / RUMI_OCTREE_TWO_PASS=1 pin either behaviour (A/B runs, tests).
+    static const int passMode = getenv("RUMI_OCTREE_TWO_PASS") ? 2 : getenv("RUMI_OCTREE_ONE_PASS") ? 1 : 0;
+    const bool canDefer = h->smemKeysBig > h->smemKeys && passMode != 1;
+    const bool twoPass = canDefer && (passMode == 2 || *(volatile int*)(h->errHost + 2) != 0);
+    oa.bigCount = w.countBase + h->chunk; oa.bigList = twoPass ? w.bigList : nullptr;
+    oa.denseFlag = h->errDev + 2;
     oa.smemKeysBig = h->smemKeysBig;
-    // a few frames never fill the SMs: every level CTA gets the large key buffer at once and the second launch is saved
+    // a few frames never fill the SMs: every level CTA gets the large key buffer at once
     // and 1024 threads, which hide the latencies nobody else on the SM would (RUMI_OCT_NARROW=1: 256, A/B runs)
     static const bool narrow = getenv("RUMI_OCT_NARROW") != nullptr;
     static const int wideThreads = getenv("RUMI_OCT_WIDE") ? atoi(getenv("RUMI_OCT_WIDE")) : 1024;
     oa.threads = 256;
-    if (n <= 4 && oa.bigList) { oa.smemKeys = h->smemKeysBig; oa.bigList = nullptr; oa.threads = narrow ? 256 : wideThreads; }
+    if (n <= 4 && canDefer) { oa.smemKeys = h->smemKeysBig; oa.bigList = nullptr; oa.threads = narrow ? 256 : wideThreads; }
     oa.slots.sel = w.sel; oa.slots.selCount = w.selCount; oa.slots.lap0 = lap0; oa.slots.lap1 = lap1; oa.slots.slot = w.slot;
     oa.slots.nkp = dNkp; oa.slots.nmono = dNmono;
     if (!(skip & 4)) launch_octree(oa, oc, sh);
@@ -690,13 +698,13 @@ int rumi_orb_create(rumi_orb** out, int nfeatures, float scale_factor, int nleve
     const char* ns = getenv("RUMI_STREAMS");
     if (ns && ns[0] >= '1' && ns[0] <= '0' + kMaxWs) { h->nws = ns[0] - '0'; h->nwsSet = true; }
     h->nwsDefault = h->nws; h->nwsSetDefault = h->nwsSet;
-    if (cudaHostAlloc((void**)&h->errHost, 2 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&h->errHost, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&h->errDev, h->errHost, 0) != cudaSuccess) {
         if (h->errHost) cudaFreeHost(h->errHost);
         delete h;
         return fail(RUMI_ERR_CUDA, "cannot allocate the mapped error flags: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    h->errHost[0] = h->errHost[1] = 0;
+    h->errHost[0] = h->errHost[1] = h->errHost[2] = h->errHost[3] = 0;
     *out = h;
     return RUMI_OK;
 }

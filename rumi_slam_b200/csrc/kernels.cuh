@@ -128,6 +128,7 @@ struct OctreeArgs {
     // key buffer of smemKeysBig keys (bigList == nullptr: everything in the first launch, global scratch for big levels)
     int threads;             // CTA width of the first launch: 256, or 1024 for calls of a few frames (0 = 256)
     int* bigCount;           // zeroed per call
+    int* denseFlag;          // mapped host int: set when a level had to be sorted in global memory (no second pass this call)
     int* bigList;            // [frame * nlevels] (frame << 8 | level)
     int smemKeysBig;
 };

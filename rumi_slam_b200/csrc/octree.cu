@@ -454,12 +454,13 @@ __global__ void __launch_bounds__(kThreads) octree_kernel(const __grid_constant_
                                                           const __grid_constant__ OrbConst oc) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int f = blockIdx.x, l = blockIdx.y + a.levelFirst;
-    if (a.bigList) {
-        const int M = a.levelCount[(long long)f * oc.nlevels + l];
-        if (next_pow2(M > 8 ? M : 8) > a.smemKeys) {
+    const int M = a.levelCount[(long long)f * oc.nlevels + l];
+    if (next_pow2(M > 8 ? M : 8) > a.smemKeys) {
+        if (a.bigList) {
             if (threadIdx.x == 0) a.bigList[atomicAdd(a.bigCount, 1)] = (f << 8) | l;
             return;
         }
+        if (threadIdx.x == 0) *(volatile int*)a.denseFlag = 1;       // tells the host to run two passes from now on
     }
     octree_problem(a, oc, smem, a.smemKeys, f, l);
 }

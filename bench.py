@@ -467,6 +467,53 @@ def run_b200(args):
                    "median_ms": float(np.median(ts)), "p90_ms": float(np.percentile(ts, 90)), "calls": len(ts)}
         ex1.close()
 
+    # ---- textured frames (context, rank 0 only): the same frames + uniform noise of +-20 grey levels put ~4x the FAST
+    # candidates on every level (real camera images sit between the two), which moves the quad-tree onto its dense paths ----
+    textured = None
+    if rank == 0 and not args.no_textured:
+        try:
+            nd = 256
+            rngd = np.random.default_rng(20)
+            noisy = np.clip(host[:nd].astype(np.int16) + rngd.integers(-20, 21, host[:nd].shape, dtype=np.int16),
+                            0, 255).astype(np.uint8)
+            exd = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_batch=chunk)
+            ddev = torch.from_numpy(noisy).to(dev)
+            od = None
+            for _ in range(3):
+                od = exd.extract_batch_device(ddev, out=od)
+            exd.launch_count(reset=True)
+            exd.timer_start()
+            for _ in range(5):
+                exd.extract_batch_device(ddev, out=od, sync=False)
+            ms_d = exd.timer_stop()
+            nl_d = exd.launch_count(reset=True)
+            ex1 = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local)
+            for _ in range(10):
+                ex1(noisy[0])
+            ts = []
+            for i in range(50):
+                t0 = time.perf_counter()
+                ex1(noisy[i % nd])
+                ts.append(time.perf_counter() - t0)
+            cand0 = len(ex1.debug_candidates(0))
+            ex1.close()
+            textured = {"workload": "%d of the same frames + uniform noise of +-20 grey levels, resident in HBM" % nd,
+                        "frames_per_s": nd * 5 / (ms_d / 1e3), "gpu_launches": nl_d,
+                        "level0_fast_candidates_last_frame": cand0,
+                        "single_frame_median_ms": float(np.median(ts) * 1e3)}
+            if check_oracle:
+                pick = [0, 85, 170, 255]
+                refd = orb_oracle.extract_mt([noisy[i] for i in pick], threads=threads_here)
+                dk = od[0][pick].cpu().numpy()
+                dd = od[1][pick].cpu().numpy()
+                dn = od[2].cpu().numpy()
+                textured["parity_ok"] = bool(all(dn[i] == len(rk) and kp_bytes_equal(dk[j], rk) and
+                                                 np.array_equal(dd[j, :len(rk)], rd)
+                                                 for j, (i, (rk, rd, rm)) in enumerate(zip(pick, refd))))
+            exd.close()
+        except Exception as e:                               # context row only: never fails the bench
+            textured = {"error": str(e)[:200]}
+
     # ---- matching: cfg 5a, 40 front + 40 back keyframes x 1000 descriptors, all pairs; train sharded over ranks ----
     nq = nt = 40 * 1000
     desc = out_dev[1][:80]                                      # 80 extracted frames of this rank
@@ -919,7 +966,8 @@ def run_b200(args):
                      and parity.get("pageable_path_ok", False)
                      and (matching or {}).get("parity_ok", True) and (match_big or {}).get("parity_ok", True)
                      and all(v.get("parity_ok", True) for v in stereo.values())
-                     and (submap or {}).get("parity_ok", True)) if check_oracle else None
+                     and (submap or {}).get("parity_ok", True)
+                     and (textured or {}).get("parity_ok", True)) if check_oracle else None
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -948,6 +996,7 @@ def run_b200(args):
             "bow": bow,
             "flow": flow,
             "single_frame_latency": latency,
+            "textured_frames": textured,
             "clocks": clocks}
     emit(json.dumps(line))
     if world > 1:
@@ -989,6 +1038,7 @@ def main():
     ap.add_argument("--no-flow", action="store_true")
     ap.add_argument("--no-stereo", action="store_true")
     ap.add_argument("--no-submap", action="store_true")
+    ap.add_argument("--no-textured", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle parity checks (they run outside the timed regions)")
     ap.add_argument("--stereo-pairs", type=int, default=256)
     ap.add_argument("--match-big", type=int, default=1000000, help="cfg 5b descriptors per side (0 = skip)")

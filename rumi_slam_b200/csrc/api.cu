@@ -47,16 +47,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // looked up once; a function-local static initialiser is thread safe (two extractors may be created concurrently)
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
+            return (EncodeTiledFn)p;
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -1428,22 +1427,21 @@ struct NcclId { char internal[128]; };       // == ncclUniqueId (nccl.h: NCCL_UN
 constexpr int kNcclUint64 = 5;               // ncclDataType_t ncclUint64 (nccl.h)
 
 NcclApi& nccl_api() {
-    static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static NcclApi api = [] {                          // thread-safe one-time lookup
+        NcclApi a;
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* n : names)
-            if ((api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
-        if (api.lib) {
-            api.getUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
-            api.commDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
-            api.allGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
-            api.errorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
-            api.commInitRank = dlsym(api.lib, "ncclCommInitRank");
-            api.ok = api.getUniqueId && api.commDestroy && api.allGather && api.errorString && api.commInitRank;
+            if ((a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (a.lib) {
+            a.getUniqueId = (int (*)(void*))dlsym(a.lib, "ncclGetUniqueId");
+            a.commDestroy = (int (*)(void*))dlsym(a.lib, "ncclCommDestroy");
+            a.allGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(a.lib, "ncclAllGather");
+            a.errorString = (const char* (*)(int))dlsym(a.lib, "ncclGetErrorString");
+            a.commInitRank = dlsym(a.lib, "ncclCommInitRank");
+            a.ok = a.getUniqueId && a.commDestroy && a.allGather && a.errorString && a.commInitRank;
         }
-    }
+        return a;
+    }();
     return api;
 }
 #define NCCL_TRY(expr)                                                                                  \

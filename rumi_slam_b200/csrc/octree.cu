@@ -485,8 +485,8 @@ void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
     const size_t smem = octree_smem_bytes(a.smemKeys, a.maxNodeCap, nthr);
     // per device and cheap: set on every launch rather than cached in a process-wide flag (a process may drive several GPUs)
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    static int split = -1;                      // RUMI_OCTREE_SPLIT=1: one launch per level (per-level timing under ncu)
-    if (split < 0) { const char* e = getenv("RUMI_OCTREE_SPLIT"); split = e && e[0] == '1'; }
+    // RUMI_OCTREE_SPLIT=1: one launch per level (per-level timing under ncu)
+    static const bool split = [] { const char* e = getenv("RUMI_OCTREE_SPLIT"); return e && e[0] == '1'; }();
     if (split) {
         for (int l = 0; l < oc.nlevels; ++l) {
             OctreeArgs b = a;
@@ -500,8 +500,8 @@ void launch_octree(const OctreeArgs& a, const OrbConst& oc, cudaStream_t s) {
     if (a.bigList) {
         const size_t smemBig = octree_smem_bytes(a.smemKeysBig, a.maxNodeCap, kOctThreadsBig);
         cudaFuncSetAttribute(octree_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBig);
-        static int maxCtas = -1;                // RUMI_OCT_BIG_CTAS: persistent CTAs of pass 1 (A/B runs)
-        if (maxCtas < 0) { const char* e = getenv("RUMI_OCT_BIG_CTAS"); maxCtas = e ? std::max(1, atoi(e)) : 148; }
+        // RUMI_OCT_BIG_CTAS: persistent CTAs of pass 1 (A/B runs)
+        static const int maxCtas = [] { const char* e = getenv("RUMI_OCT_BIG_CTAS"); return e ? std::max(1, atoi(e)) : 148; }();
         const int ctas = std::min(a.nframes * oc.nlevels, maxCtas);
         octree_big_kernel<<<ctas, kOctThreadsBig, smemBig, s>>>(a, oc);
     }

@@ -206,6 +206,88 @@ int mo_search_by_projection(const void* kFv, const uint8_t* dF, int nF, const fl
     return nmatches;
 }
 
+// The WHOLE of ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ..) (ORBmatcher.cc:39-189) as Tracking::SearchLocalPoints
+// meets it: a frame that already holds matches (occupied[j] = F.mvpMapPoints[j] is a point with observations on entry,
+// :80-82), rectified stereo / RGB-D frames (uRight[j] = F.mvuRight[j] > 0: the right-image gate of :84-88 against
+// mTrackProjXR) and stereo-fisheye rigs (nR > 0: Nleft = nL, the right camera's key points kR, descriptor rows nL + i, its own
+// grid, the second half of the loop :125-185, and the cross assignments through l2r = mvLeftToRightMatch / r2l =
+// mvRightToLeftMatch, :114-118 / :175-179).  Per map point: inView / inViewR = mbTrackInView / mbTrackInViewR,
+// proj = (mTrackProjX, mTrackProjY), projR = (mTrackProjXR, mTrackProjYR), level / levelR, viewCos / viewCosR, descriptor,
+// hasObs = Observations() > 0.  bFarPoints and isBad() are the caller's filter.  frameMatch[j] (nL + nR entries) = map point
+// this call stored in F.mvpMapPoints[j], -1 = untouched.  Nullable: kR, uRight, occupied, l2r, r2l, inViewR and the *R arrays.
+int mo_search_by_projection_ex(const void* kLv, int nL, const void* kRv, int nR, const uint8_t* dF, const float* scaleFactors,
+                               int minX, int minY, int maxX, int maxY, const float* uRight, const uint8_t* occupied,
+                               const int32_t* l2r, const int32_t* r2l, const uint8_t* inView, const uint8_t* inViewR,
+                               const float* proj, const float* projR, const int32_t* level, const int32_t* levelR,
+                               const float* viewCos, const float* viewCosR, const uint8_t* dMP, const uint8_t* hasObs, int nMP,
+                               float th, float ratio, int32_t* frameMatch) {
+    const KP *kL = (const KP*)kLv, *kR = (const KP*)kRv;
+    const int Nleft = nR > 0 ? nL : -1, N = nL + nR;
+    Grid g(kL, nL, minX, minY, maxX, maxY), gR(kR, nR, minX, minY, maxX, maxY);
+    // state of F.mvpMapPoints[j]: -2 = a point with observations that was there on entry, -1 = none (or one without
+    // observations), >= 0 = map point stored by this call
+    std::vector<int> st(N, -1);
+    if (occupied) for (int j = 0; j < N; ++j) if (occupied[j]) st[j] = -2;
+    auto taken = [&](int j) { return st[j] == -2 || (st[j] >= 0 && hasObs[st[j]]); };
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < nMP; ++iMP) {
+        const bool inV = inView ? inView[iMP] != 0 : true, inVR = inViewR ? inViewR[iMP] != 0 : false;
+        if (!inV && !inVR) continue;
+        if (inV) {
+            const int nPredictedLevel = level[iMP];
+            float r = viewCos[iMP] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos :191-196
+            if (bFactor) r *= th;
+            g.query(proj[2 * iMP], proj[2 * iMP + 1], r * scaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, vIndices);
+            if (!vIndices.empty()) {
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for (int idx : vIndices) {
+                    if (taken(idx)) continue;
+                    if (Nleft == -1 && uRight && uRight[idx] > 0) {
+                        const float er = std::fabs(projR[2 * iMP] - uRight[idx]);
+                        if (er > r * scaleFactors[nPredictedLevel]) continue;
+                    }
+                    const int dist = descriptor_distance(dMP + 32 * (size_t)iMP, dF + 32 * (size_t)idx);
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kL[idx].octave; bestIdx = idx; }
+                    else if (dist < bestDist2) { bestLevel2 = kL[idx].octave; bestDist2 = dist; }
+                }
+                if (bestDist <= TH_HIGH) {
+                    if (bestLevel == bestLevel2 && bestDist > ratio * bestDist2) continue;      // skips the right half too
+                    if (bestLevel != bestLevel2 || bestDist <= ratio * bestDist2) {
+                        st[bestIdx] = iMP;
+                        if (Nleft != -1 && l2r && l2r[bestIdx] != -1) { st[l2r[bestIdx] + Nleft] = iMP; nmatches++; }
+                        nmatches++;
+                    }
+                }
+            }
+        }
+        if (Nleft != -1 && inVR) {
+            const int nPredictedLevel = levelR[iMP];
+            if (nPredictedLevel != -1) {
+                const float r = viewCosR[iMP] > 0.998 ? 2.5f : 4.0f;      // no th factor on this side (:129)
+                gR.query(projR[2 * iMP], projR[2 * iMP + 1], r * scaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, vIndices);
+                if (vIndices.empty()) continue;
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for (int idx : vIndices) {
+                    if (taken(idx + Nleft)) continue;
+                    const int dist = descriptor_distance(dMP + 32 * (size_t)iMP, dF + 32 * (size_t)(idx + Nleft));
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kR[idx].octave; bestIdx = idx; }
+                    else if (dist < bestDist2) { bestLevel2 = kR[idx].octave; bestDist2 = dist; }
+                }
+                if (bestDist <= TH_HIGH) {
+                    if (bestLevel == bestLevel2 && bestDist > ratio * bestDist2) continue;
+                    if (r2l && r2l[bestIdx] != -1) { st[r2l[bestIdx]] = iMP; nmatches++; }
+                    st[bestIdx + Nleft] = iMP;
+                    nmatches++;
+                }
+            }
+        }
+    }
+    for (int j = 0; j < N; ++j) frameMatch[j] = st[j] >= 0 ? st[j] : -1;
+    return nmatches;
+}
+
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (ORBmatcher.cc:1498-1684), the
 // matcher of Tracking::TrackWithMotionModel, for frames without a second fisheye camera (Nleft == -1).  Per feature i of
 // the last frame: valid[i] = it has a map point and is not an outlier (:1518-1520); uv[i] = projection of that point into

@@ -109,6 +109,41 @@ def _f32(a):
     return np.ascontiguousarray(a, np.float32)
 
 
+def search_by_projection_ex(kL, dF, scale_factors, bounds, proj, level, view_cos, dMP, has_obs, th=3.0, nnratio=0.8, kR=None, u_right=None,
+                            occupied=None, l2r=None, r2l=None, in_view=None, in_view_r=None, proj_r=None, level_r=None,
+                            view_cos_r=None):
+    """Oracle restatement of the whole ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th): occupied features, mvuRight
+    gate, stereo-fisheye halves.  (nmatches, frameMatch[nL + nR])."""
+    kL = np.ascontiguousarray(kL, KP_DTYPE)
+    kR = np.zeros(0, KP_DTYPE) if kR is None else np.ascontiguousarray(kR, KP_DTYPE)
+    nL, nR = len(kL), len(kR)
+    dF, dMP = np.ascontiguousarray(dF, np.uint8).reshape(-1, 32), np.ascontiguousarray(dMP, np.uint8).reshape(-1, 32)
+    assert len(dF) == nL + nR
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    keep = []                                            # keeps the converted arrays alive during the call
+
+    def opt(a, dt, ptr):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dt)
+        keep.append(a)
+        return a.ctypes.data_as(ptr)
+    out = np.zeros(max(nL + nR, 1), np.int32)
+    L = lib()
+    fn = L.mo_search_by_projection_ex
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, _u8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p,
+                   _i32p, _i32p, _u8p, _u8p, _f32p, _f32p, _i32p, _i32p, _f32p, _f32p, _u8p, _u8p, C.c_int, C.c_float,
+                   C.c_float, _i32p]
+    n = fn(kL.ctypes.data, nL, kR.ctypes.data if nR else None, nR, _p(dF, _u8p), _p(sf, _f32p),
+           *[int(b) for b in bounds], opt(u_right, np.float32, _f32p), opt(occupied, np.uint8, _u8p), opt(l2r, np.int32, _i32p),
+           opt(r2l, np.int32, _i32p), opt(in_view, np.uint8, _u8p), opt(in_view_r, np.uint8, _u8p),
+           opt(proj, np.float32, _f32p), opt(proj_r, np.float32, _f32p), opt(level, np.int32, _i32p),
+           opt(level_r, np.int32, _i32p), opt(view_cos, np.float32, _f32p), opt(view_cos_r, np.float32, _f32p),
+           _p(dMP, _u8p), opt(has_obs, np.uint8, _u8p), len(dMP), float(th), float(nnratio), _p(out, _i32p))
+    return n, out[:nL + nR]
+
+
 def search_by_projection_last(kC, dC, scale_factors, bounds, valid, uv, invz, octave, angle_last, dMP, mp_has_obs, th=15.0,
                               u_right=None, occupied=None, mbf=0.0, forward=False, backward=False, check_ori=True):
     """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1498-1684, Nleft == -1):

@@ -434,6 +434,53 @@ int ref_search_by_projection(const void* kF, const uint8_t* dF, int nF, const fl
     return n;
 }
 
+// The same reference function with everything Tracking::SearchLocalPoints can hand it: a frame that already holds matches
+// (occupied[j]: mvpMapPoints[j] = a point with observations), mvuRight (rectified stereo / RGB-D), and a stereo-fisheye
+// frame (nR > 0: Nleft = nL, mvKeysRight, descriptor rows nL + i, mvLeftToRightMatch / mvRightToLeftMatch).  Map points carry
+// both halves of their tracking state.  frameMatch[j] = map point stored by the call (-1: untouched).
+int ref_search_by_projection_ex(const void* kL, int nL, const void* kR, int nR, const uint8_t* dF, const float* scaleFactors,
+                                int nlevels, int minX, int minY, int maxX, int maxY, const float* uRight, const uint8_t* occupied,
+                                const int32_t* l2r, const int32_t* r2l, const uint8_t* inView, const uint8_t* inViewR,
+                                const float* proj, const float* projR, const int32_t* level, const int32_t* levelR,
+                                const float* viewCos, const float* viewCosR, const uint8_t* dMP, const uint8_t* hasObs, int nMP,
+                                float th, float ratio, int32_t* frameMatch) {
+    set_grid(minX, minY, maxX, maxY);
+    const int N = nL + nR;
+    Frame F;
+    F.N = N; F.mvKeys = keys(kL, nL); F.mvKeysUn = F.mvKeys; F.mDescriptors = rows32(dF, N);
+    if (nR > 0) { F.Nleft = nL; F.mvKeysRight = keys(kR, nR); }
+    F.mvuRight.assign(N, -1.0f);
+    if (uRight) for (int j = 0; j < nL; ++j) F.mvuRight[j] = uRight[j];
+    F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint taken; taken.nObs = 1;
+    F.mvpMapPoints.assign(N, nullptr);
+    if (occupied) for (int j = 0; j < N; ++j) if (occupied[j]) F.mvpMapPoints[j] = &taken;
+    F.mvLeftToRightMatch.assign(nL, -1); F.mvRightToLeftMatch.assign(nR, -1);
+    if (l2r) F.mvLeftToRightMatch.assign(l2r, l2r + nL);
+    if (r2l) F.mvRightToLeftMatch.assign(r2l, r2l + nR);
+    F.AssignFeaturesToGrid();
+    std::vector<MapPoint> mps(nMP);
+    std::vector<MapPoint*> ptrs(nMP);
+    for (int i = 0; i < nMP; ++i) {
+        MapPoint& m = mps[i];
+        m.mbTrackInView = inView ? inView[i] != 0 : true;
+        m.mbTrackInViewR = inViewR ? inViewR[i] != 0 : false;
+        m.mTrackProjX = proj[2 * i]; m.mTrackProjY = proj[2 * i + 1];
+        m.mnTrackScaleLevel = level[i]; m.mTrackViewCos = viewCos[i];
+        if (projR) { m.mTrackProjXR = projR[2 * i]; m.mTrackProjYR = projR[2 * i + 1]; }
+        if (levelR) m.mnTrackScaleLevelR = levelR[i];
+        if (viewCosR) m.mTrackViewCosR = viewCosR[i];
+        m.mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+        m.nObs = hasObs[i] ? 1 : 0;
+        ptrs[i] = &m;
+    }
+    ORBmatcher m(ratio, true);
+    const int n = m.SearchByProjection(F, ptrs, th, false, 50.0f);
+    for (int j = 0; j < N; ++j)
+        frameMatch[j] = (F.mvpMapPoints[j] && F.mvpMapPoints[j] != &taken) ? (int)(F.mvpMapPoints[j] - mps.data()) : -1;
+    return n;
+}
+
 // ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1498-1684), Nleft == -1.  Last frame:
 // valid[i] = has a map point and is not an outlier, (uv, depth) = where the stand-in camera puts it in the current frame,
 // octave / angle of its key point, descriptor and Observations() > 0 of its map point.  Current frame: key points,

@@ -200,6 +200,83 @@ def test_search_by_projection_equals_reference(oracle, rf, M, seed, th, ratio):
     assert rn > 50
 
 
+def _local_points_case(oracle, seed, mode):
+    """Tracking::SearchLocalPoints as the reference function sees it.  Frame 2 = the current frame; map points = the
+    features of frame 1 projected with the known image motion plus noise.  mode 'occupied': the frame already holds matches
+    with observations; 'stereo': mvuRight set on most features and mTrackProjXR near / far from it; 'fisheye': a third
+    extraction plays the right camera (Nleft = n2), map points are in view of the left, the right or both cameras, some
+    left / right features are stereo partners of each other."""
+    k1, d1, k2, d2 = _frame_pair(oracle, seed)
+    rng = np.random.default_rng(100 + seed)
+    n1, n2 = len(k1), len(k2)
+    kw = dict(proj=np.stack([k1["x"] - 3.0, k1["y"] + 2.0], 1).astype(np.float32) + rng.normal(0, 0.7, (n1, 2)).astype(np.float32),
+              level=np.clip(k1["octave"] + rng.integers(-1, 2, n1), 0, 7).astype(np.int32),
+              view_cos=rng.choice([0.9, 0.9985, 1.0], n1).astype(np.float32),
+              has_obs=(rng.random(n1) < 0.7).astype(np.uint8))
+    kL, dF = k2, d2
+    if mode in ("occupied", "stereo"):
+        kw["occupied"] = (rng.random(n2) < 0.25).astype(np.uint8)
+    if mode == "stereo":
+        ur = (k2["x"] - rng.uniform(2, 40, n2)).astype(np.float32)
+        ur[rng.random(n2) < 0.3] = -1.0                                     # no stereo match for that feature
+        kw["u_right"] = ur
+        # mTrackProjXR: mostly close to the right coordinate of the feature the point should hit, sometimes far off
+        pr = np.zeros((n1, 2), np.float32)
+        pr[:, 0] = kw["proj"][:, 0] - rng.uniform(2, 40, n1).astype(np.float32)
+        pr[:, 1] = kw["proj"][:, 1]
+        kw["proj_r"] = pr
+    if mode == "fisheye":
+        from rumi_slam_b200.synth import motion_sequence
+        kR, dR, _ = oracle.extract(motion_sequence(2, 640, 480, seed=seed, vx=9.0, vy=-2.0)[1])      # "right camera"
+        nR = len(kR)
+        kw["kR"] = kR
+        dF = np.concatenate([d2, dR])
+        kw["in_view"] = (rng.random(n1) < 0.8).astype(np.uint8)
+        kw["in_view_r"] = (rng.random(n1) < 0.6).astype(np.uint8)
+        kw["proj_r"] = np.stack([k1["x"] - 9.0, k1["y"] + 2.0], 1).astype(np.float32) + rng.normal(0, 0.7, (n1, 2)).astype(np.float32)
+        lr = np.clip(k1["octave"] + rng.integers(-1, 2, n1), 0, 7).astype(np.int32)
+        lr[rng.random(n1) < 0.05] = -1                                      # mnTrackScaleLevelR == -1: right half skipped
+        kw["level_r"] = lr
+        kw["view_cos_r"] = rng.choice([0.9, 0.9985, 1.0], n1).astype(np.float32)
+        # stereo partners: a partial one-to-one map between left and right features
+        m = min(n2, nR) // 3
+        li, ri = rng.permutation(n2)[:m], rng.permutation(nR)[:m]
+        l2r, r2l = np.full(n2, -1, np.int32), np.full(nR, -1, np.int32)
+        l2r[li] = ri
+        r2l[ri] = li
+        kw["l2r"], kw["r2l"] = l2r, r2l
+        kw["occupied"] = (rng.random(n2 + nR) < 0.15).astype(np.uint8)
+    return kL, dF, d1, kw
+
+
+@pytest.mark.parametrize("mode", ["occupied", "stereo", "fisheye"])
+@pytest.mark.parametrize("seed,th,ratio", [(6, 3.0, 0.8), (7, 1.0, 0.8), (8, 5.0, 0.9), (9, 15.0, 0.6)])
+def test_search_by_projection_all_branches_equal_reference(oracle, rf, M, seed, th, ratio, mode):
+    """The whole ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) (R/lib_src/ORBmatcher.cc:39-189): features that
+    already hold a map point with observations (:80-82), the right-image gate of rectified stereo / RGB-D frames (:84-88)
+    and both halves of the stereo-fisheye loop with their cross assignments (:114-118, :125-185)."""
+    kL, dF, dMP, kw = _local_points_case(oracle, seed, mode)
+    sf = oracle.tables()["scale"]
+    args = dict(kw)
+    proj, level, view_cos, has_obs = args.pop("proj"), args.pop("level"), args.pop("view_cos"), args.pop("has_obs")
+    n, fm = M.search_by_projection_ex(kL, dF, sf, (0, 0, 640, 480), proj, level, view_cos, dMP, has_obs, th, ratio, **args)
+    rn, rfm = rf.search_by_projection_ex(kL, dF, sf, (0, 0, 640, 480), proj, level, view_cos, dMP, has_obs, th, ratio, **args)
+    assert n == rn and np.array_equal(fm, rfm)
+    assert rn > 40
+    if mode == "fisheye":
+        nL = len(kL)
+        assert (rfm[nL:] >= 0).sum() > 20 and (rfm[:nL] >= 0).sum() > 20          # both cameras received matches
+    if mode == "stereo":                                                         # the gate did reject candidates
+        n0, _ = rf.search_by_projection_ex(kL, dF, sf, (0, 0, 640, 480), proj, level, view_cos, dMP, has_obs, th, ratio,
+                                           occupied=args["occupied"])
+        assert n0 != rn
+    # without any of the extras the extended entry equals the mono one
+    if mode == "occupied":
+        a = M.search_by_projection_ex(kL, dF, sf, (0, 0, 640, 480), proj, level, view_cos, dMP, has_obs, th, ratio)
+        b = M.search_by_projection(kL, dF, sf, (0, 0, 640, 480), proj, level, view_cos, dMP, has_obs, th, ratio)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
 def _last_frame_case(oracle, seed, stereo):
     """Frame 1 = last frame (its features carry map points), frame 2 = current frame; map point i is projected to where
     frame 1's feature moved (known image motion + noise), with a depth; some features lack a map point / are outliers,

@@ -529,6 +529,101 @@ int ORBmatcherAccel::SearchByProjection(const std::vector<cv::KeyPoint>& keysF, 
     return nmatches;
 }
 
+int ORBmatcherAccel::SearchByProjection(const std::vector<cv::KeyPoint>& keysF, const cv::Mat& descF,
+                                        const FrameGridAccel& gridF, const std::vector<float>& scaleFactors,
+                                        const std::vector<cv::Point2f>& proj, const std::vector<int>& level,
+                                        const std::vector<float>& viewCos, const cv::Mat& descMP,
+                                        const std::vector<uint8_t>& hasObservations, float th, const LocalPointsExtras& ex,
+                                        std::vector<int>& frameMatch) {
+    const int nMP = (int)proj.size(), nL = (int)keysF.size();
+    const bool fisheye = ex.keysRight && ex.gridRight && !ex.keysRight->empty();
+    const int nR = fisheye ? (int)ex.keysRight->size() : 0, Nleft = fisheye ? nL : -1;
+    const bool bFactor = th != 1.0;
+    auto inV = [&](int i) { return ex.inView ? (*ex.inView)[i] != 0 : true; };
+    auto inVR = [&](int i) { return fisheye && ex.inViewR && (*ex.inViewR)[i] != 0; };
+    // candidate lists of every window of both cameras: queries [0, nMP) = left halves, [nMP, 2 nMP) = right halves
+    std::vector<int32_t> off(1, 0), idx;
+    std::vector<float> radius(nMP, 0.0f);
+    for (int i = 0; i < nMP; ++i) {
+        if (inV(i)) {
+            float r = viewCos[i] > 0.998 ? 2.5f : 4.0f;                                          // RadiusByViewingCos
+            if (bFactor) r *= th;
+            radius[i] = r * scaleFactors[level[i]];
+            const std::vector<size_t> v = gridF.GetFeaturesInArea(proj[i].x, proj[i].y, radius[i], level[i] - 1, level[i]);
+            idx.insert(idx.end(), v.begin(), v.end());
+        }
+        off.push_back((int32_t)idx.size());
+    }
+    for (int i = 0; i < nMP; ++i) {
+        if (inVR(i) && (*ex.levelR)[i] != -1) {
+            const int lv = (*ex.levelR)[i];
+            const float r = (*ex.viewCosR)[i] > 0.998 ? 2.5f : 4.0f;                             // no th factor here (:129)
+            const std::vector<size_t> v = ex.gridRight->GetFeaturesInArea((*ex.projR)[i].x, (*ex.projR)[i].y, r * scaleFactors[lv],
+                                                                          lv - 1, lv);
+            for (size_t j : v) idx.push_back((int32_t)j + nL);                                   // descriptor row of a right key point
+        }
+        off.push_back((int32_t)idx.size());
+    }
+    std::vector<uint8_t> Q = rows32(descMP);
+    if (fisheye) Q.insert(Q.end(), Q.begin(), Q.begin() + (size_t)32 * nMP);                     // the right halves ask with the same descriptors
+    std::vector<uint16_t> dist;
+    CandidateDistances(Q, fisheye ? 2 * nMP : nMP, descF, fisheye ? off : std::vector<int32_t>(off.begin(), off.begin() + nMP + 1),
+                       idx, dist);
+    // state of F.mvpMapPoints[j]: -2 = held a point with observations on entry, -1 = none, >= 0 = stored by this call
+    std::vector<int> st(nL + nR, -1);
+    if (ex.occupied) for (int j = 0; j < nL + nR; ++j) if ((*ex.occupied)[j]) st[j] = -2;
+    auto taken = [&](int j) { return st[j] == -2 || (st[j] >= 0 && hasObservations[st[j]]); };
+    int nmatches = 0;
+    for (int iMP = 0; iMP < nMP; ++iMP) {
+        if (!inV(iMP) && !inVR(iMP)) continue;
+        if (inV(iMP)) {
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int p = off[iMP]; p < off[iMP + 1]; ++p) {
+                const int j = idx[p], d = dist[p];
+                if (taken(j)) continue;                                                          // :80-82
+                if (Nleft == -1 && ex.uRight && (*ex.uRight)[j] > 0) {                           // :84-88
+                    const float er = fabs((*ex.projR)[iMP].x - (*ex.uRight)[j]);
+                    if (er > radius[iMP]) continue;
+                }
+                if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = keysF[j].octave; bestIdx = j; }
+                else if (d < bestDist2) { bestLevel2 = keysF[j].octave; bestDist2 = d; }
+            }
+            if (bestDist <= TH_HIGH && bestIdx >= 0) {
+                if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;       // leaves the right half out too
+                if (bestLevel != bestLevel2 || bestDist <= mfNNratio * bestDist2) {
+                    st[bestIdx] = iMP;
+                    if (Nleft != -1 && ex.leftToRight && (*ex.leftToRight)[bestIdx] != -1) {     // :114-118
+                        st[(*ex.leftToRight)[bestIdx] + Nleft] = iMP;
+                        nmatches++;
+                    }
+                    nmatches++;
+                }
+            }
+        }
+        if (Nleft != -1 && inVR(iMP) && (*ex.levelR)[iMP] != -1) {
+            const int q = nMP + iMP;
+            if (off[q] == off[q + 1]) continue;
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int p = off[q]; p < off[q + 1]; ++p) {
+                const int j = idx[p], d = dist[p];                                               // j = Nleft + right index
+                if (taken(j)) continue;
+                const int oct = (*ex.keysRight)[j - Nleft].octave;
+                if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = j - Nleft; }
+                else if (d < bestDist2) { bestLevel2 = oct; bestDist2 = d; }
+            }
+            if (bestDist <= TH_HIGH && bestIdx >= 0) {
+                if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;
+                if (ex.rightToLeft && (*ex.rightToLeft)[bestIdx] != -1) { st[(*ex.rightToLeft)[bestIdx]] = iMP; nmatches++; }   // :175-179
+                st[bestIdx + Nleft] = iMP;
+                nmatches++;
+            }
+        }
+    }
+    frameMatch.resize(nL + nR);
+    for (int j = 0; j < nL + nR; ++j) frameMatch[j] = st[j] >= 0 ? st[j] : -1;
+    return nmatches;
+}
+
 void ORBmatcherAccel::CandidateDistances(const std::vector<uint8_t>& Q, int nq, const cv::Mat& T, const std::vector<int32_t>& off,
                                          const std::vector<int32_t>& idx, std::vector<uint16_t>& dist) {
     dist.assign(idx.size() + 1, 0);

@@ -138,6 +138,28 @@ public:
                            const std::vector<int>& level, const std::vector<float>& viewCos, const cv::Mat& descMP,
                            const std::vector<uint8_t>& hasObservations, float th, std::vector<int>& frameMatch);
 
+    // The rest of that function (R/lib_src/ORBmatcher.cc:39-189) as Tracking::SearchLocalPoints meets it.  All members optional.
+    struct LocalPointsExtras {
+        const std::vector<uint8_t>* occupied = nullptr;     // F.mvpMapPoints[j] holds a point with observations on entry (:80-82)
+        const std::vector<float>* uRight = nullptr;         // F.mvuRight: right-image gate of rectified stereo / RGB-D (:84-88) ...
+        const std::vector<cv::Point2f>* projR = nullptr;    // ... against mTrackProjXR (.x); .y = mTrackProjYR (fisheye only)
+        // stereo-fisheye rig (F.Nleft = keysF.size(); descF = left rows, then right rows): the second half of the loop (:125-185)
+        const std::vector<cv::KeyPoint>* keysRight = nullptr;          // F.mvKeysRight
+        const FrameGridAccel* gridRight = nullptr;                     // grid over keysRight (F.mGridRight)
+        const std::vector<uint8_t>* inView = nullptr;                  // mbTrackInView (default: all)
+        const std::vector<uint8_t>* inViewR = nullptr;                 // mbTrackInViewR
+        const std::vector<int>* levelR = nullptr;                      // mnTrackScaleLevelR
+        const std::vector<float>* viewCosR = nullptr;                  // mTrackViewCosR
+        const std::vector<int>* leftToRight = nullptr;                 // F.mvLeftToRightMatch
+        const std::vector<int>* rightToLeft = nullptr;                 // F.mvRightToLeftMatch
+    };
+    // frameMatch gets keysF.size() (+ keysRight->size()) entries: the map point this call stored in F.mvpMapPoints[j], or -1.
+    int SearchByProjection(const std::vector<cv::KeyPoint>& keysF, const cv::Mat& descF, const FrameGridAccel& gridF,
+                           const std::vector<float>& scaleFactors, const std::vector<cv::Point2f>& proj,
+                           const std::vector<int>& level, const std::vector<float>& viewCos, const cv::Mat& descMP,
+                           const std::vector<uint8_t>& hasObservations, float th, const LocalPointsExtras& ex,
+                           std::vector<int>& frameMatch);
+
     // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (R/lib_src/ORBmatcher.cc:1498-1684),
     // the matcher of Tracking::TrackWithMotionModel, frames without a second fisheye camera (Nleft == -1).  Last frame, per
     // feature i: valid[i] = has a map point and is not an outlier (:1518-1520); uv[i], invzc[i] = projection of that point

@@ -272,9 +272,18 @@ class ORBmatcher:
         return nmatches, m12, prev
 
     # ---- ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, ...) (ORBmatcher.cc:39-118, mono frame) ----
-    def SearchByProjection(self, keysF, descF, scale_factors, bounds, proj, level, view_cos, descMP, has_obs, th=3.0):
+    def SearchByProjection(self, keysF, descF, scale_factors, bounds, proj, level, view_cos, descMP, has_obs, th=3.0, *,
+                           occupied=None, u_right=None, proj_r=None, keys_right=None, in_view=None, in_view_r=None,
+                           level_r=None, view_cos_r=None, l2r=None, r2l=None):
         """Map points in view (mbTrackInView) with their projection (mTrackProjX/Y), predicted level, viewing cosine,
-        descriptor and Observations() > 0 flag.  Returns (nmatches, frame_match[j] = map point index or -1)."""
+        descriptor and Observations() > 0 flag.  Returns (nmatches, frame_match[j] = map point index or -1).
+        Keyword extras = the rest of the reference function (ORBmatcher.cc:39-189), see _search_by_projection_full:
+        occupied (features that already hold a point with observations), u_right + proj_r (mvuRight / mTrackProjXR:
+        right-image gate of rectified stereo and RGB-D frames), keys_right ... r2l (stereo-fisheye rigs)."""
+        if any(a is not None for a in (occupied, u_right, keys_right, in_view, in_view_r)):
+            return self._search_by_projection_full(keysF, descF, scale_factors, bounds, proj, level, view_cos, descMP, has_obs, th,
+                                                   occupied, u_right, proj_r, keys_right, in_view, in_view_r, level_r,
+                                                   view_cos_r, l2r, r2l)
         kF = np.ascontiguousarray(keysF, KP_DTYPE)
         sf = np.asarray(scale_factors, np.float32)
         proj = np.asarray(proj, np.float32).reshape(-1, 2)
@@ -304,6 +313,109 @@ class ORBmatcher:
                 fm[best_idx] = i
                 nmatches += 1
         return nmatches, fm
+
+    def _search_by_projection_full(self, keysF, descF, scale_factors, bounds, proj, level, view_cos, descMP, has_obs, th,
+                                   occupied, u_right, proj_r, keys_right, in_view, in_view_r, level_r, view_cos_r, l2r, r2l):
+        """The whole ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) (ORBmatcher.cc:39-189) as
+        Tracking::SearchLocalPoints meets it.  keysF = mvKeysUn (mvKeys of the left camera on a stereo-fisheye rig),
+        keys_right = mvKeysRight (then descF holds the left rows followed by the right rows, Nleft = len(keysF)).  Every
+        DescriptorDistance of both cameras' windows runs in ONE launch; the scan, whose skips depend on what earlier map
+        points were assigned, is replayed in the reference's order."""
+        f32 = np.float32
+        kL = np.ascontiguousarray(keysF, KP_DTYPE)
+        kR = None if keys_right is None else np.ascontiguousarray(keys_right, KP_DTYPE)
+        nL, nR = len(kL), 0 if kR is None else len(kR)
+        fisheye = nR > 0
+        sf = np.asarray(scale_factors, f32)
+        proj = np.asarray(proj, f32).reshape(-1, 2)
+        nMP = len(proj)
+        level = np.asarray(level, np.int32)
+        inv = np.ones(nMP, bool) if in_view is None else np.asarray(in_view, bool)
+        invr = np.zeros(nMP, bool) if (in_view_r is None or not fisheye) else np.asarray(in_view_r, bool)
+        r = np.where(np.asarray(view_cos, f32) > 0.998, f32(2.5), f32(4.0)).astype(f32)
+        if th != 1.0:
+            r = (r * f32(th)).astype(f32)
+        rad = (r * sf[level]).astype(f32)
+        qL = np.flatnonzero(inv)
+        offL, idxL = FrameGrid(kL, bounds).candidate_lists(proj[qL], rad[qL], level[qL] - 1, level[qL])
+        if fisheye:
+            pr = np.asarray(proj_r, f32).reshape(-1, 2)
+            lr = np.asarray(level_r, np.int32)
+            rr = np.where(np.asarray(view_cos_r, f32) > 0.998, f32(2.5), f32(4.0)).astype(f32)     # no th factor (:129)
+            qR = np.flatnonzero(invr & (lr != -1))
+            radR = (rr[qR] * sf[lr[qR]]).astype(f32)
+            offR, idxR = FrameGrid(kR, bounds).candidate_lists(pr[qR], radR, lr[qR] - 1, lr[qR])
+        else:
+            pr = None if proj_r is None else np.asarray(proj_r, f32).reshape(-1, 2)
+            qR, offR, idxR = np.zeros(0, np.int64), np.zeros(1, np.int32), np.zeros(0, np.int32)
+        # one launch: the left windows, then the right windows (descriptor rows nL + i)
+        dMP = np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)
+        off = np.concatenate([offL, offL[-1] + offR[1:]]).astype(np.int32)
+        idx = np.concatenate([idxL, idxR + nL]).astype(np.int32)
+        dist = self.candidates(np.concatenate([dMP[qL], dMP[qR]]), descF, off, idx)
+        slotL = np.full(nMP, -1, np.int64); slotL[qL] = np.arange(len(qL))
+        slotR = np.full(nMP, -1, np.int64); slotR[qR] = len(qL) + np.arange(len(qR))
+        has_obs = np.asarray(has_obs, bool)
+        ur = None if (u_right is None or fisheye) else np.asarray(u_right, f32)
+        st = np.full(nL + nR, -1, np.int64)                   # -2: held a point with observations on entry
+        if occupied is not None:
+            st[np.asarray(occupied, bool)] = -2
+        octL = kL["octave"]
+        octR = None if kR is None else kR["octave"]
+        ratio = f32(self.mfNNratio)
+        nmatches = 0
+
+        def taken(j):
+            return st[j] == -2 or (st[j] >= 0 and has_obs[st[j]])
+
+        for i in range(nMP):
+            if not inv[i] and not invr[i]:
+                continue
+            skip_right = False
+            if inv[i]:
+                q = slotL[i]
+                best, best_level, best2, best_level2, best_idx = 256, -1, 256, -1, -1
+                for p in range(off[q], off[q + 1]):
+                    j, d = int(idx[p]), int(dist[p])
+                    if taken(j):
+                        continue
+                    if ur is not None and ur[j] > 0:
+                        if abs(f32(pr[i, 0] - ur[j])) > rad[i]:
+                            continue
+                    if d < best:
+                        best2, best, best_level2, best_level, best_idx = best, d, best_level, int(octL[j]), j
+                    elif d < best2:
+                        best_level2, best2 = int(octL[j]), d
+                if best <= self.TH_HIGH and best_idx >= 0:
+                    if best_level == best_level2 and f32(best) > ratio * f32(best2):
+                        skip_right = True                      # the reference's `continue` leaves the whole iteration
+                    else:
+                        st[best_idx] = i
+                        if fisheye and l2r is not None and l2r[best_idx] != -1:
+                            st[int(l2r[best_idx]) + nL] = i
+                            nmatches += 1
+                        nmatches += 1
+            if skip_right or not fisheye or not invr[i] or slotR[i] < 0:
+                continue
+            q = slotR[i]
+            best, best_level, best2, best_level2, best_idx = 256, -1, 256, -1, -1
+            for p in range(off[q], off[q + 1]):
+                j, d = int(idx[p]), int(dist[p])              # j = nL + index among the right key points
+                if taken(j):
+                    continue
+                if d < best:
+                    best2, best, best_level2, best_level, best_idx = best, d, best_level, int(octR[j - nL]), j - nL
+                elif d < best2:
+                    best_level2, best2 = int(octR[j - nL]), d
+            if best <= self.TH_HIGH and best_idx >= 0:
+                if best_level == best_level2 and f32(best) > ratio * f32(best2):
+                    continue
+                if r2l is not None and r2l[best_idx] != -1:
+                    st[int(r2l[best_idx])] = i
+                    nmatches += 1
+                st[best_idx + nL] = i
+                nmatches += 1
+        return nmatches, np.where(st >= 0, st, -1).astype(np.int32)
 
     # ---- ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1498-1684), Nleft == -1 ----
     def SearchByProjectionLastFrame(self, keysC, descC, scale_factors, bounds, valid, uv, invz, octave, angle_last, descMP,

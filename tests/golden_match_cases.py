@@ -118,5 +118,19 @@ def initialization(oracle, B, rf, reference, seed=2, window=100, ratio=0.9):
     return {"n": n, "match": m, "prev": p}
 
 
+def _local_points(mode, seed, th, ratio):
+    def case(oracle, B, rf, reference):
+        from oracle import match_oracle as M
+        kL, dF, dMP, kw = T._local_points_case(oracle, seed, mode)
+        sf = oracle.tables()["scale"]
+        proj, level, view_cos, has_obs = kw.pop("proj"), kw.pop("level"), kw.pop("view_cos"), kw.pop("has_obs")
+        fn = (rf if reference else M).search_by_projection_ex
+        n, fm = fn(kL, dF, sf, BOUNDS, proj, level, view_cos, dMP, has_obs, th, ratio, **kw)
+        return {"n": n, "match": fm}
+    return case
+
+
 CASES = {"last_frame": last_frame, "keyframe": keyframe, "fuse": fuse, "triangulation": triangulation, "sim3_pair": sim3_pair,
-         "initialization": initialization}
+         "initialization": initialization,
+         "local_points_occupied": _local_points("occupied", 41, 3.0, 0.8), "local_points_stereo": _local_points("stereo", 42, 5.0, 0.8),
+         "local_points_fisheye": _local_points("fisheye", 43, 3.0, 0.8)}

@@ -355,6 +355,85 @@ int mo_search_by_projection_last(const void* kCv, const uint8_t* dC, int nC, con
     return nmatches;
 }
 
+// The same function on a stereo-fisheye CURRENT frame (CurrentFrame.Nleft = nC != -1, ORBmatcher.cc:1602-1656 in addition):
+// kR = mvKeysRight (descriptor rows nC + i, their own grid), uvR[i] = projection of last-frame point i into the right camera
+// (GetRelativePoseTrl() * x3Dc through the camera model: the caller's).  The left half loses its mvuRight gate (Nleft != -1),
+// the right half is a best-1 search without bounds test that only runs when the left window was not empty (the `continue`
+// of :1552-1553 leaves the iteration).  occupied has nC + nR entries, so has curMatch.  angleLast / octave are per last-frame
+// feature whichever camera it came from.
+int mo_search_by_projection_last_fisheye(const void* kCv, int nC, const void* kRv, int nR, const uint8_t* dC,
+                                         const float* scaleFactors, int minX, int minY, int maxX, int maxY,
+                                         const uint8_t* occupied, const uint8_t* valid, const float* uv, const float* uvR,
+                                         const float* invz, const int32_t* octave, const float* angleLast, const uint8_t* dMP,
+                                         const uint8_t* mpHasObs, int nL, float th, int forward, int backward, int checkOri,
+                                         int32_t* curMatch) {
+    const KP *kC = (const KP*)kCv, *kR = (const KP*)kRv;
+    Grid g(kC, nC, minX, minY, maxX, maxY), gR(kR, nR, minX, minY, maxX, maxY);
+    const int N = nC + nR, Nleft = nC;
+    for (int j = 0; j < N; ++j) curMatch[j] = -1;
+    auto taken = [&](int j) { return (occupied && occupied[j]) || (curMatch[j] >= 0 && mpHasObs[curMatch[j]]); };
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    auto vote = [&](int i, float angleCF, int slot) {
+        float rot = angleLast[i] - angleCF;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(slot);
+    };
+    std::vector<int> vIndices2;
+    for (int i = 0; i < nL; ++i) {
+        if (!valid[i]) continue;
+        if (invz[i] < 0) continue;
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        if (u < (float)minX || u > (float)maxX) continue;
+        if (v < (float)minY || v > (float)maxY) continue;
+        const int nLastOctave = octave[i];
+        const float radius = th * scaleFactors[nLastOctave];
+        if (forward) g.query(u, v, radius, nLastOctave, -1, vIndices2);
+        else if (backward) g.query(u, v, radius, 0, nLastOctave, vIndices2);
+        else g.query(u, v, radius, nLastOctave - 1, nLastOctave + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (taken(i2)) continue;
+            const int dist = descriptor_distance(dMP + 32 * (size_t)i, dC + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            curMatch[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) vote(i, kC[bestIdx2].angle, bestIdx2);
+        }
+        // right camera (:1602-1656)
+        const float ur = uvR[2 * i], vr = uvR[2 * i + 1];
+        if (forward) gR.query(ur, vr, radius, nLastOctave, -1, vIndices2);
+        else if (backward) gR.query(ur, vr, radius, 0, nLastOctave, vIndices2);
+        else gR.query(ur, vr, radius, nLastOctave - 1, nLastOctave + 1, vIndices2);
+        bestDist = 256; bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (taken(i2 + Nleft)) continue;
+            const int dist = descriptor_distance(dMP + 32 * (size_t)i, dC + 32 * (size_t)(i2 + Nleft));
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            curMatch[bestIdx2 + Nleft] = i;
+            nmatches++;
+            if (checkOri) vote(i, kR[bestIdx2].angle, bestIdx2 + Nleft);
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { curMatch[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794),
 // the matcher of Tracking::Relocalization.  Per key-frame feature i: valid[i] = map point present, not bad, not in
 // sAlreadyFound (:1703-1704); uv[i] = its projection, dist3D[i] = |x3Dw - Ow| with the window [minDist, maxDist]

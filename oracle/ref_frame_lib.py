@@ -229,6 +229,31 @@ def search_by_projection_last(kC, dC, scale_factors, bounds, valid, uv, depth, o
     return n, out[:len(kC)]
 
 
+def search_by_projection_last_fisheye(kC, kR, dC, scale_factors, bounds, valid, uv, shift, depth, octave, angle_last, dMP,
+                                      mp_has_obs, th=15.0, occupied=None, forward=False, backward=False, check_ori=True):
+    """The reference's SearchByProjection(CurrentFrame, LastFrame, th, false) with a stereo-fisheye current frame (Nleft =
+    len(kC)); the right camera sees point i at uv[i] + shift.  (nmatches, curMatch[len(kC) + len(kR)])."""
+    kC, kR = np.ascontiguousarray(kC, KP_DTYPE), np.ascontiguousarray(kR, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    dC, dMP, sf, uv, depth, al = u8(dC).reshape(-1, 32), u8(dMP).reshape(-1, 32), f32(scale_factors), f32(uv), f32(depth), f32(angle_last)
+    N = len(kC) + len(kR)
+    occ = u8(np.zeros(N) if occupied is None else occupied)
+    va, ho, oc = u8(valid), u8(mp_has_obs), np.ascontiguousarray(octave, np.int32)
+    out = np.zeros(max(N, 1), np.int32)
+    L = lib()
+    fn = L.ref_search_by_projection_last_fisheye
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, _u8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p,
+                   _f32p, C.c_float, C.c_float, _f32p, _i32p, _f32p, _u8p, _u8p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float,
+                   C.c_int, _i32p]
+    n = fn(kC.ctypes.data, len(kC), kR.ctypes.data, len(kR), _p(dC, _u8p), _p(sf, _f32p), len(sf), *[int(b) for b in bounds],
+           _p(occ, _u8p), _p(va, _u8p), _p(uv, _f32p), float(shift[0]), float(shift[1]), _p(depth, _f32p), _p(oc, _i32p),
+           _p(al, _f32p), _p(dMP, _u8p), _p(ho, _u8p), len(dMP), float(th), int(forward), int(backward), 0.9, int(check_ori),
+           _p(out, _i32p))
+    return n, out[:N]
+
+
 def search_by_projection_kf(kC, dC, scale_factors, bounds, state, uv, depth, level, min_dist, max_dist, angle_kf, dMP, th=10.0,
                             orb_dist=100, occupied=None, check_ori=True):
     """The reference's ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist); state[i]: 0 no map

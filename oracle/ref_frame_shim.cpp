@@ -526,6 +526,50 @@ int ref_search_by_projection_last(const void* kC, const uint8_t* dC, int nC, con
     return n;
 }
 
+// The same reference function with a stereo-fisheye current frame: Nleft = nC, mvKeysRight = kR, descriptor rows nC + i;
+// the right camera sees last-frame point i at uv[i] + (shiftX, shiftY) (GetRelativePoseTrl() = that translation under the
+// pass-through stand-in camera).  occupied / curMatch have nC + nR entries.
+int ref_search_by_projection_last_fisheye(const void* kC, int nC, const void* kR, int nR, const uint8_t* dC,
+                                          const float* scaleFactors, int nlevels, int minX, int minY, int maxX, int maxY,
+                                          const uint8_t* occupied, const uint8_t* valid, const float* uv, float shiftX,
+                                          float shiftY, const float* depth, const int32_t* octave, const float* angleLast,
+                                          const uint8_t* dMP, const uint8_t* mpHasObs, int nL, float th, int forward,
+                                          int backward, float ratio, int checkOri, int32_t* curMatch) {
+    set_grid(minX, minY, maxX, maxY);
+    GeometricCamera cam;
+    Frame C, Lf;
+    const int N = nC + nR;
+    C.N = N; C.Nleft = nC; C.mvKeys = keys(kC, nC); C.mvKeysUn = C.mvKeys; C.mvKeysRight = keys(kR, nR);
+    C.mDescriptors = rows32(dC, N);
+    C.mvuRight.assign(N, -1.0f);
+    C.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    C.mbf = 40.0f; C.mb = 1.0f; C.mpCamera = &cam;
+    C.mTrl.t = Eigen::Vector3f(shiftX, shiftY, 0.0f);
+    MapPoint taken; taken.nObs = 1;
+    C.mvpMapPoints.assign(N, nullptr);
+    for (int j = 0; j < N; ++j) if (occupied && occupied[j]) C.mvpMapPoints[j] = &taken;
+    C.AssignFeaturesToGrid();
+    std::vector<MapPoint> mps(nL);
+    Lf.N = nL; Lf.mvKeys.resize(nL); Lf.mvKeysUn.resize(nL); Lf.mvpMapPoints.assign(nL, nullptr); Lf.mvbOutlier.assign(nL, false);
+    for (int i = 0; i < nL; ++i) {
+        Lf.mvKeys[i].octave = octave[i]; Lf.mvKeysUn[i].octave = octave[i];
+        Lf.mvKeys[i].angle = angleLast[i]; Lf.mvKeysUn[i].angle = angleLast[i];
+        mps[i].mWorldPos = Eigen::Vector3f(uv[2 * i], uv[2 * i + 1], depth[i]);
+        mps[i].mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+        mps[i].nObs = mpHasObs[i] ? 1 : 0;
+        if (valid[i]) Lf.mvpMapPoints[i] = &mps[i];
+        else if (i & 1) { Lf.mvpMapPoints[i] = &mps[i]; Lf.mvbOutlier[i] = true; }
+    }
+    Lf.mTcw.t = Eigen::Vector3f(0, 0, forward ? 2.0f : backward ? -2.0f : 0.0f);
+    ORBmatcher m(ratio, checkOri != 0);
+    const int n = m.SearchByProjection(C, Lf, th, false);
+    for (int j = 0; j < N; ++j) {
+        MapPoint* p = C.mvpMapPoints[j];
+        curMatch[j] = (p && p != &taken) ? (int)(p - mps.data()) : -1;
+    }
+    return n;
+}
+
 // ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794).  Key frame:
 // state[i] = 0 no map point, 1 usable, 2 bad, 3 in sAlreadyFound; (uv, depth), predicted level (stand-in PredictScale),
 // distance-invariance window [minDist, maxDist] against |x3Dw - Ow| (Ow = 0 here), key point angle, descriptor.

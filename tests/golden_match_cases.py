@@ -118,6 +118,21 @@ def initialization(oracle, B, rf, reference, seed=2, window=100, ratio=0.9):
     return {"n": n, "match": m, "prev": p}
 
 
+def last_frame_fisheye(oracle, B, rf, reference, seed=61, th=15.0):
+    from oracle import match_oracle as M
+    k1, d1, kC, kR, dC, uv, depth, valid, has_obs, occupied, shift = T._last_frame_fisheye_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    if reference:
+        n, cm = rf.search_by_projection_last_fisheye(kC, kR, dC, sf, BOUNDS, valid, uv, shift, depth, k1["octave"], k1["angle"], d1,
+                                                     has_obs, th, occupied, False, False, True)
+    else:
+        invz = (1.0 / depth.astype(np.float64)).astype(np.float32)
+        uvr = (uv + np.asarray(shift, np.float32)).astype(np.float32)
+        n, cm = M.search_by_projection_last_fisheye(kC, kR, dC, sf, BOUNDS, valid, uv, uvr, invz, k1["octave"], k1["angle"], d1,
+                                                    has_obs, th, occupied, False, False, True)
+    return {"n": n, "match": cm}
+
+
 def _local_points(mode, seed, th, ratio):
     def case(oracle, B, rf, reference):
         from oracle import match_oracle as M
@@ -133,4 +148,4 @@ def _local_points(mode, seed, th, ratio):
 CASES = {"last_frame": last_frame, "keyframe": keyframe, "fuse": fuse, "triangulation": triangulation, "sim3_pair": sim3_pair,
          "initialization": initialization,
          "local_points_occupied": _local_points("occupied", 41, 3.0, 0.8), "local_points_stereo": _local_points("stereo", 42, 5.0, 0.8),
-         "local_points_fisheye": _local_points("fisheye", 43, 3.0, 0.8)}
+         "local_points_fisheye": _local_points("fisheye", 43, 3.0, 0.8), "last_frame_fisheye": last_frame_fisheye}

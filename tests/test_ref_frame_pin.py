@@ -200,6 +200,44 @@ def test_search_by_projection_equals_reference(oracle, rf, M, seed, th, ratio):
     assert rn > 50
 
 
+def _right_camera(oracle, seed, dx=-6):
+    """Key points / descriptors of a 'right camera' that sees the second frame of _frame_pair(seed) shifted by dx pixels."""
+    from rumi_slam_b200.synth import motion_sequence
+    img = np.roll(motion_sequence(2, 640, 480, seed=seed, vx=3.0, vy=-2.0)[1], dx, axis=1)
+    kR, dR, _ = oracle.extract(np.ascontiguousarray(img))
+    return kR, dR
+
+
+def _last_frame_fisheye_case(oracle, seed):
+    """_last_frame_case with a second extraction playing the right camera of the current frame; the right camera sees every
+    point 6 px further left."""
+    k1, d1, k2, d2, uv, depth, valid, has_obs, _, _ = _last_frame_case(oracle, seed, False)
+    kR, dR = _right_camera(oracle, seed)
+    rng = np.random.default_rng(seed + 500)
+    occupied = (rng.random(len(k2) + len(kR)) < 0.05).astype(np.uint8)
+    return k1, d1, k2, kR, np.concatenate([d2, dR]), uv, depth, valid, has_obs, occupied, (-6.0, 0.0)
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,direction", [(51, 15.0, "none"), (52, 7.0, "none"), (53, 15.0, "forward"), (54, 15.0, "backward")])
+def test_search_by_projection_last_frame_fisheye_equals_reference(oracle, rf, M, seed, th, direction, check_ori):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, false) with CurrentFrame.Nleft != -1 (R/lib_src/ORBmatcher.cc:
+    1498-1684 incl. :1602-1656): the second, right-camera search of every last-frame point and its votes in the shared
+    rotation histogram."""
+    k1, d1, kC, kR, dC, uv, depth, valid, has_obs, occupied, shift = _last_frame_fisheye_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    fw, bw = direction == "forward", direction == "backward"
+    rn, rcm = rf.search_by_projection_last_fisheye(kC, kR, dC, sf, (0, 0, 640, 480), valid, uv, shift, depth, k1["octave"],
+                                                   k1["angle"], d1, has_obs, th, occupied, fw, bw, check_ori)
+    invz = (1.0 / depth.astype(np.float64)).astype(np.float32)
+    uvr = (uv + np.asarray(shift, np.float32)).astype(np.float32)
+    n, cm = M.search_by_projection_last_fisheye(kC, kR, dC, sf, (0, 0, 640, 480), valid, uv, uvr, invz, k1["octave"], k1["angle"],
+                                                d1, has_obs, th, occupied, fw, bw, check_ori)
+    assert n == rn and np.array_equal(cm, rcm)
+    nL = len(kC)
+    assert (rcm[:nL] >= 0).sum() > 20 and (rcm[nL:] >= 0).sum() > 20
+
+
 def _local_points_case(oracle, seed, mode):
     """Tracking::SearchLocalPoints as the reference function sees it.  Frame 2 = the current frame; map points = the
     features of frame 1 projected with the known image motion plus noise.  mode 'occupied': the frame already holds matches
@@ -226,8 +264,7 @@ def _local_points_case(oracle, seed, mode):
         pr[:, 1] = kw["proj"][:, 1]
         kw["proj_r"] = pr
     if mode == "fisheye":
-        from rumi_slam_b200.synth import motion_sequence
-        kR, dR, _ = oracle.extract(motion_sequence(2, 640, 480, seed=seed, vx=9.0, vy=-2.0)[1])      # "right camera"
+        kR, dR = _right_camera(oracle, seed)
         nR = len(kR)
         kw["kR"] = kR
         dF = np.concatenate([d2, dR])

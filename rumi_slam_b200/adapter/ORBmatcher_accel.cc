@@ -713,6 +713,75 @@ int ORBmatcherAccel::SearchByProjectionLastFrame(const std::vector<cv::KeyPoint>
     return nmatches;
 }
 
+int ORBmatcherAccel::SearchByProjectionLastFrameFisheye(
+    const std::vector<cv::KeyPoint>& keysC, const std::vector<cv::KeyPoint>& keysRight, const cv::Mat& descC,
+    const FrameGridAccel& gridC, const FrameGridAccel& gridRight, const std::vector<float>& scaleFactors,
+    const std::vector<uint8_t>& occupied, const std::vector<uint8_t>& valid, const std::vector<cv::Point2f>& uv,
+    const std::vector<cv::Point2f>& uvR, const std::vector<float>& invzc, const std::vector<int>& octaveLast,
+    const std::vector<float>& angleLast, const cv::Mat& descMP, const std::vector<uint8_t>& mpHasObservations, float th,
+    bool bForward, bool bBackward, bool checkOrientation, std::vector<int>& curMatch) {
+    const int Nleft = (int)keysC.size();
+    curMatch.assign(keysC.size() + keysRight.size(), -1);
+    auto window = [&](const FrameGridAccel& g, const cv::Point2f& p, float radius, int nLastOctave) {
+        return bForward    ? g.GetFeaturesInArea(p.x, p.y, radius, nLastOctave)
+               : bBackward ? g.GetFeaturesInArea(p.x, p.y, radius, 0, nLastOctave)
+                           : g.GetFeaturesInArea(p.x, p.y, radius, nLastOctave - 1, nLastOctave + 1);
+    };
+    // queries [0, nq): left windows; [nq, 2 nq): the right windows of the same last-frame points
+    std::vector<int> query;
+    std::vector<int32_t> offL(1, 0), idxL, offR(1, 0), idxR;
+    std::vector<uint8_t> Q;
+    for (size_t i = 0; i < uv.size(); i++) {
+        if (!valid[i]) continue;
+        if (invzc[i] < 0) continue;                                                              // :1529-1530
+        if (uv[i].x < gridC.mnMinX || uv[i].x > gridC.mnMaxX) continue;
+        if (uv[i].y < gridC.mnMinY || uv[i].y > gridC.mnMaxY) continue;
+        const int nLastOctave = octaveLast[i];
+        const float radius = th * scaleFactors[nLastOctave];
+        const std::vector<size_t> v = window(gridC, uv[i], radius, nLastOctave);
+        if (v.empty()) continue;                                                                 // :1552-1553: leaves the right half out too
+        const std::vector<size_t> vr = window(gridRight, uvR[i], radius, nLastOctave);
+        query.push_back((int)i);
+        idxL.insert(idxL.end(), v.begin(), v.end());
+        offL.push_back((int32_t)idxL.size());
+        for (size_t j : vr) idxR.push_back((int32_t)j + Nleft);                                  // descriptor row of a right key point
+        offR.push_back((int32_t)idxR.size());
+        Q.insert(Q.end(), descMP.ptr((int)i), descMP.ptr((int)i) + 32);
+    }
+    const int nq = (int)query.size();
+    std::vector<int32_t> off(offL), idx(idxL);
+    for (int k = 1; k <= nq; ++k) off.push_back(offL[nq] + offR[k]);
+    idx.insert(idx.end(), idxR.begin(), idxR.end());
+    Q.insert(Q.end(), Q.begin(), Q.begin() + (size_t)32 * nq);
+    std::vector<uint16_t> dist;
+    CandidateDistances(Q, 2 * nq, descC, off, idx, dist);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int qi = 0; qi < nq; ++qi) {
+        const int i = query[qi];
+        for (int side = 0; side < 2; ++side) {
+            const int ql = side * nq + qi;
+            int bestDist = 256, bestIdx2 = -1;
+            for (int p = off[ql]; p < off[ql + 1]; ++p) {
+                const int i2 = idx[p];                                                           // right camera: Nleft + index
+                if ((!occupied.empty() && occupied[i2]) || (curMatch[i2] >= 0 && mpHasObservations[curMatch[i2]])) continue;
+                const int d = dist[p];
+                if (d < bestDist) { bestDist = d; bestIdx2 = i2; }
+            }
+            if (bestDist <= TH_HIGH) {
+                curMatch[bestIdx2] = i;
+                nmatches++;
+                if (checkOrientation) {
+                    const float angleCF = side ? keysRight[bestIdx2 - Nleft].angle : keysC[bestIdx2].angle;
+                    rotHist[rotation_bin(angleLast[i], angleCF, HISTO_LENGTH)].push_back(bestIdx2);
+                }
+            }
+        }
+    }
+    if (checkOrientation) nmatches -= clear_rotation_outliers(rotHist, HISTO_LENGTH, curMatch);
+    return nmatches;
+}
+
 int ORBmatcherAccel::SearchByProjectionKeyFrame(const std::vector<cv::KeyPoint>& keysC, const cv::Mat& descC,
                                                 const FrameGridAccel& gridC, const std::vector<float>& scaleFactors,
                                                 const std::vector<uint8_t>& occupied, const std::vector<uint8_t>& valid,

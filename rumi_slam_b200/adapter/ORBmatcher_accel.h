@@ -176,6 +176,20 @@ public:
                                     const cv::Mat& descMP, const std::vector<uint8_t>& mpHasObservations, float th,
                                     bool bForward, bool bBackward, bool checkOrientation, std::vector<int>& curMatch);
 
+    // The same with a stereo-fisheye CURRENT frame (CurrentFrame.Nleft = keysC.size(), R/lib_src/ORBmatcher.cc:1602-1656 in
+    // addition): keysRight = mvKeysRight with their own grid, descC = left rows followed by right rows, uvR[i] = projection of
+    // point i into the right camera (GetRelativePoseTrl() * x3Dc through the caller's camera model).  A point whose left window
+    // is not empty is also searched, best-1, in the right camera; both vote in one rotation histogram.  occupied (may be
+    // empty) and curMatch cover keysC.size() + keysRight.size() features.
+    int SearchByProjectionLastFrameFisheye(const std::vector<cv::KeyPoint>& keysC, const std::vector<cv::KeyPoint>& keysRight,
+                                           const cv::Mat& descC, const FrameGridAccel& gridC, const FrameGridAccel& gridRight,
+                                           const std::vector<float>& scaleFactors, const std::vector<uint8_t>& occupied,
+                                           const std::vector<uint8_t>& valid, const std::vector<cv::Point2f>& uv,
+                                           const std::vector<cv::Point2f>& uvR, const std::vector<float>& invzc,
+                                           const std::vector<int>& octaveLast, const std::vector<float>& angleLast,
+                                           const cv::Mat& descMP, const std::vector<uint8_t>& mpHasObservations, float th,
+                                           bool bForward, bool bBackward, bool checkOrientation, std::vector<int>& curMatch);
+
     // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (R/lib_src/ORBmatcher.cc:1685-1794),
     // the matcher of Tracking::Relocalization.  Key frame, per feature i: valid[i] = map point present, not bad, not in
     // sAlreadyFound; uv[i] = its projection; dist3D[i] = |x3Dw - Ow| against [minDistance[i], maxDistance[i]] (:1717-1725);

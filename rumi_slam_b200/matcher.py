@@ -477,6 +477,68 @@ class ORBmatcher:
                         nmatches -= 1
         return nmatches, cm
 
+    # ---- the same with a stereo-fisheye CURRENT frame (CurrentFrame.Nleft != -1, ORBmatcher.cc:1602-1656 in addition) ----
+    def SearchByProjectionLastFrameFisheye(self, keysC, keys_right, descC, scale_factors, bounds, valid, uv, uv_r, invz, octave,
+                                           angle_last, descMP, mp_has_obs, th=15.0, occupied=None, forward=False,
+                                           backward=False):
+        """keysC = CurrentFrame.mvKeys (left camera, Nleft of them), keys_right = mvKeysRight, descC = the left rows followed
+        by the right rows; uv_r[i] = projection of last-frame point i into the right camera (GetRelativePoseTrl() * x3Dc
+        through the caller's camera model).  Every last-frame point whose LEFT window is not empty is also searched, best-1,
+        in the right camera; both searches vote in one rotation histogram.  occupied / cur_match: Nleft + len(keys_right)."""
+        f32 = np.float32
+        kC, kR = np.ascontiguousarray(keysC, KP_DTYPE), np.ascontiguousarray(keys_right, KP_DTYPE)
+        nC, nR = len(kC), len(kR)
+        sf = np.asarray(scale_factors, f32)
+        uv, uvr = np.asarray(uv, f32).reshape(-1, 2), np.asarray(uv_r, f32).reshape(-1, 2)
+        invz, octave = np.asarray(invz, f32), np.asarray(octave, np.int32)
+        ok = np.asarray(valid, bool) & ~(invz < 0) & ~(uv[:, 0] < f32(bounds[0])) & ~(uv[:, 0] > f32(bounds[2])) \
+            & ~(uv[:, 1] < f32(bounds[1])) & ~(uv[:, 1] > f32(bounds[3]))
+        q = np.flatnonzero(ok)
+        radius = (f32(th) * sf[octave[q]]).astype(f32)
+        if forward:
+            lo, hi = octave[q], np.full(len(q), -1, np.int32)
+        elif backward:
+            lo, hi = np.zeros(len(q), np.int32), octave[q]
+        else:
+            lo, hi = octave[q] - 1, octave[q] + 1
+        offL, idxL = FrameGrid(kC, bounds).candidate_lists(uv[q], radius, lo, hi)
+        offR, idxR = FrameGrid(kR, bounds).candidate_lists(uvr[q], radius, lo, hi)
+        dMP = np.ascontiguousarray(descMP, np.uint8).reshape(-1, 32)
+        off = np.concatenate([offL, offL[-1] + offR[1:]]).astype(np.int32)          # left windows, then right windows
+        idx = np.concatenate([idxL, idxR + nC]).astype(np.int32)
+        dist = self.candidates(np.concatenate([dMP[q], dMP[q]]), descC, off, idx)
+        occ = np.zeros(nC + nR, bool) if occupied is None else np.asarray(occupied, bool)
+        has_obs = np.asarray(mp_has_obs, bool)
+        cm = np.full(nC + nR, -1, np.int32)
+        rot_hist = [[] for _ in range(self.HISTO_LENGTH)]
+        nmatches = 0
+        nq = len(q)
+        for qi, i in enumerate(q):
+            if off[qi] == off[qi + 1]:
+                continue                                        # empty left window: the right camera is not searched either
+            for side, ql, ang in ((0, qi, kC["angle"]), (1, nq + qi, kR["angle"])):
+                best, best_idx = 256, -1
+                for p in range(off[ql], off[ql + 1]):
+                    j = int(idx[p])
+                    if occ[j] or (cm[j] >= 0 and has_obs[cm[j]]):
+                        continue
+                    d = int(dist[p])
+                    if d < best:
+                        best, best_idx = d, j
+                if best <= self.TH_HIGH:
+                    cm[best_idx] = i
+                    nmatches += 1
+                    if self.mbCheckOrientation:
+                        rot_hist[self._rot_bin(angle_last[i], ang[best_idx - side * nC])].append(best_idx)
+        if self.mbCheckOrientation:
+            keep = _three_maxima(rot_hist)
+            for b in range(self.HISTO_LENGTH):
+                if b not in keep:
+                    for j in rot_hist[b]:
+                        cm[j] = -1
+                        nmatches -= 1
+        return nmatches, cm
+
     # ---- ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1685-1794) ----
     def SearchByProjectionKeyFrame(self, keysC, descC, scale_factors, bounds, valid, uv, dist3d, min_dist, max_dist, level,
                                    angle_kf, descMP, th=10.0, orb_dist=100, occupied=None):

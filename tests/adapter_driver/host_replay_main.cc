@@ -64,7 +64,28 @@ int main(int argc, char** argv) {
     if (argc < 3) return 2;
     Reader r{std::fopen(argv[1], "rb")};
     if (!r.f) return 2;
-    const std::vector<float> par = r.arr<float>();                    // th, ratio, minX, minY, maxX, maxY
+    const std::vector<float> par = r.arr<float>();                    // th, ratio, minX, minY, maxX, maxY [, mode, fwd, bwd, checkOri]
+    if (par.size() > 6 && par[6] == 1.0f) {                          // SearchByProjectionLastFrameFisheye
+        const std::vector<cv::KeyPoint> kC = keypoints(r.arr<KpRec>()), kR = keypoints(r.arr<KpRec>());
+        const cv::Mat dC = rows(r.arr<uint8_t>()), dMP = rows(r.arr<uint8_t>());
+        const std::vector<float> sf = r.arr<float>();
+        const std::vector<uint8_t> occupied = r.arr<uint8_t>(), valid = r.arr<uint8_t>(), hasObs = r.arr<uint8_t>();
+        const std::vector<cv::Point2f> uv = points(r.arr<float>()), uvR = points(r.arr<float>());
+        const std::vector<float> invz = r.arr<float>(), angleLast = r.arr<float>();
+        const std::vector<int> octave = r.arr<int>();
+        std::fclose(r.f);
+        ORB_SLAM3::FrameGridAccel gC(kC, par[2], par[3], par[4], par[5]), gR(kR, par[2], par[3], par[4], par[5]);
+        ORB_SLAM3::ORBmatcherAccel m(par[1]);
+        std::vector<int> cm;
+        const int n = m.SearchByProjectionLastFrameFisheye(kC, kR, dC, gC, gR, sf, occupied, valid, uv, uvR, invz, octave, angleLast,
+                                                           dMP, hasObs, par[0], par[7] != 0, par[8] != 0, par[9] != 0, cm);
+        FILE* o = std::fopen(argv[2], "wb");
+        const int32_t head[3] = {n, (int32_t)cm.size(), -1};
+        std::fwrite(head, 4, 3, o);
+        std::fwrite(cm.data(), 4, cm.size(), o);
+        std::fclose(o);
+        return 0;
+    }
     const std::vector<cv::KeyPoint> kL = keypoints(r.arr<KpRec>()), kR = keypoints(r.arr<KpRec>());
     const cv::Mat dF = rows(r.arr<uint8_t>()), dMP = rows(r.arr<uint8_t>());
     const std::vector<float> sf = r.arr<float>();

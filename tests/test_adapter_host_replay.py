@@ -88,3 +88,41 @@ def test_cpp_search_by_projection_host_logic_equals_oracle(oracle, M, driver, tm
         n0s = int(np.frombuffer(buf, np.int32, 1, 12 + 4 * nfm)[0])
         fm0 = np.frombuffer(buf, np.int32, n0s, 16 + 4 * nfm)
         assert n0 == n and np.array_equal(fm0, fm)
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,direction", [(51, 15.0, "none"), (53, 15.0, "forward"), (54, 15.0, "backward")])
+def test_cpp_last_frame_fisheye_host_logic_equals_oracle(oracle, M, driver, tmp_path, seed, th, direction, check_ori):
+    global KP
+    from rumi_slam_b200 import KP_DTYPE
+    from test_ref_frame_pin import _last_frame_fisheye_case
+    KP = KP_DTYPE
+    k1, d1, kC, kR, dC, uv, depth, valid, has_obs, occupied, shift = _last_frame_fisheye_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    fw, bw = direction == "forward", direction == "backward"
+    invz = (1.0 / depth.astype(np.float64)).astype(np.float32)
+    uvr = (uv + np.asarray(shift, np.float32)).astype(np.float32)
+    n, cm = M.search_by_projection_last_fisheye(kC, kR, dC, sf, (0, 0, 640, 480), valid, uv, uvr, invz, k1["octave"], k1["angle"],
+                                                d1, has_obs, th, occupied, fw, bw, check_ori)
+    scen, out = tmp_path / "scenario.bin", tmp_path / "out.bin"
+    with open(scen, "wb") as f:
+        _write(f, [th, 0.9, 0, 0, 640, 480, 1, fw, bw, check_ori], np.float32)
+        _write(f, np.ascontiguousarray(kC, KP_DTYPE), KP_DTYPE)
+        _write(f, np.ascontiguousarray(kR, KP_DTYPE), KP_DTYPE)
+        _write(f, dC, np.uint8)
+        _write(f, d1, np.uint8)
+        _write(f, sf, np.float32)
+        _write(f, occupied, np.uint8)
+        _write(f, valid, np.uint8)
+        _write(f, has_obs, np.uint8)
+        _write(f, uv, np.float32)
+        _write(f, uvr, np.float32)
+        _write(f, invz, np.float32)
+        _write(f, k1["angle"], np.float32)
+        _write(f, k1["octave"], np.int32)
+    r = subprocess.run([driver, str(scen), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    buf = open(out, "rb").read()
+    gn, ncm, _ = np.frombuffer(buf, np.int32, 3)
+    assert gn == n and np.array_equal(np.frombuffer(buf, np.int32, ncm, 12), cm)
+    assert n > 100

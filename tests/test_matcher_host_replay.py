@@ -52,3 +52,22 @@ def test_default_arguments_take_the_original_path(oracle, M):
     n, fm = M.search_by_projection(kL, dF, sf, (0, 0, 640, 480), kw["proj"], kw["level"], kw["view_cos"], dMP, kw["has_obs"], 3.0, 0.8)
     gn, gfm = m.SearchByProjection(kL, dF, sf, (0, 0, 640, 480), kw["proj"], kw["level"], kw["view_cos"], dMP, kw["has_obs"], 3.0)
     assert gn == n and np.array_equal(gfm, fm)
+
+
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,th,direction", [(51, 15.0, "none"), (52, 7.0, "none"), (53, 15.0, "forward"), (54, 15.0, "backward")])
+def test_last_frame_fisheye_replay_equals_oracle(oracle, M, seed, th, direction, check_ori):
+    from test_ref_frame_pin import _last_frame_fisheye_case
+    k1, d1, kC, kR, dC, uv, depth, valid, has_obs, occupied, shift = _last_frame_fisheye_case(oracle, seed)
+    sf = oracle.tables()["scale"]
+    fw, bw = direction == "forward", direction == "backward"
+    invz = (1.0 / depth.astype(np.float64)).astype(np.float32)
+    uvr = (uv + np.asarray(shift, np.float32)).astype(np.float32)
+    n, cm = M.search_by_projection_last_fisheye(kC, kR, dC, sf, (0, 0, 640, 480), valid, uv, uvr, invz, k1["octave"], k1["angle"],
+                                                d1, has_obs, th, occupied, fw, bw, check_ori)
+    m = _mirror_with_numpy_distances()
+    m.mbCheckOrientation = check_ori
+    gn, gcm = m.SearchByProjectionLastFrameFisheye(kC, kR, dC, sf, (0, 0, 640, 480), valid, uv, uvr, invz, k1["octave"],
+                                                   k1["angle"], d1, has_obs, th, occupied, fw, bw)
+    assert gn == n and np.array_equal(gcm, cm)
+    assert n > 100

@@ -301,6 +301,31 @@ def fuse(kK, dK, scale_factors, inv_level_sigma2, bounds, u_right, kf_has_point,
     return nf, out[:n]
 
 
+def fuse_right(n_left, kR, dAll, scale_factors, inv_level_sigma2, bounds, u_right_all, kf_has_point, bf, state, uv, depth, min_dist,
+               max_dist, level, dMP, n_obs, th=3.0):
+    """The reference's ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = true) on a stereo-fisheye key frame (NLeft = n_left, right
+    key points kR, descriptor rows n_left + i): (nFused, bestIdx[i] = n_left + right feature, -1 = none / no trace)."""
+    kR = np.ascontiguousarray(kR, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    dAll, dMP = u8(dAll).reshape(-1, 32), u8(dMP).reshape(-1, 32)
+    assert len(dAll) == n_left + len(kR)
+    sf = f32(scale_factors)
+    n = len(dMP)
+    out = np.zeros(max(n, 1), np.int32)
+    L = lib()
+    fn = L.ref_fuse_right
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p,
+                   C.c_float, _u8p, _f32p, _f32p, _f32p, _f32p, _i32p, _u8p, _i32p, C.c_int, C.c_float, _i32p]
+    nf = fn(int(n_left), kR.ctypes.data, len(kR), _p(dAll, _u8p), _p(sf, _f32p), _p(f32(inv_level_sigma2), _f32p), len(sf),
+            *[int(b) for b in bounds], _p(f32(u_right_all), _f32p), _p(u8(kf_has_point), _u8p), float(bf), _p(u8(state), _u8p),
+            _p(f32(uv), _f32p), _p(f32(depth), _f32p), _p(f32(min_dist), _f32p), _p(f32(max_dist), _f32p), _p(i32(level), _i32p),
+            _p(dMP, _u8p), _p(i32(n_obs), _i32p), n, float(th), _p(out, _i32p))
+    return nf, out[:n]
+
+
 def search_for_triangulation(k1, d1, has_mp1, u_right1, fv1, k2, d2, has_mp2, u_right2, fv2, scale_factors2, ep, epi_ok,
                              only_stereo=False, coarse=False, check_ori=True):
     """The reference's ORBmatcher::SearchForTriangulation over stand-in poses / camera (epipole = ep, epipolarConstrain = the

@@ -670,6 +670,64 @@ int ref_fuse(const void* kK, const uint8_t* dK, int nK, const float* scaleFactor
     return nFused;
 }
 
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = true): the key frame of a stereo-fisheye rig (NLeft = nLeft; mvKeysRight = kR
+// with mGridRight; descriptor rows nLeft + i; mpCamera2, GetRightPose / GetRightCameraCenter = the stand-ins of the left
+// side).  dAll = all N = nLeft + nR descriptor rows, uRightAll = mvuRight (the reference indexes it with the RIGHT-relative
+// index, :1131), kfHasPoint over all N features.  bestIdx[i] = feature (nLeft + right index) point i was fused with.
+int ref_fuse_right(int nLeft, const void* kR, int nR, const uint8_t* dAll, const float* scaleFactors, const float* invLevelSigma2,
+                   int nlevels, int minX, int minY, int maxX, int maxY, const float* uRightAll, const uint8_t* kfHasPoint, float bf,
+                   const uint8_t* state, const float* uv, const float* depth, const float* minDist, const float* maxDist,
+                   const int32_t* level, const uint8_t* dMP, const int32_t* nObs, int nMP, float th, int32_t* bestIdx) {
+    set_grid(minX, minY, maxX, maxY);
+    GeometricCamera cam;
+    const int N = nLeft + nR;
+    Frame F;                                       // builds the right camera's grid exactly as Frame::AssignFeaturesToGrid does
+    F.N = N; F.Nleft = nLeft; F.mvKeys.resize(nLeft); F.mvKeysUn = F.mvKeys; F.mvKeysRight = keys(kR, nR);
+    for (auto& k : F.mvKeys) { k.pt.x = -1e6f; k.pt.y = -1e6f; }                       // left features: outside every grid cell
+    F.AssignFeaturesToGrid();
+    KeyFrame kf;
+    kf.N = N; kf.NLeft = nLeft; kf.mvKeys = F.mvKeys; kf.mvKeysUn = F.mvKeys; kf.mvKeysRight = F.mvKeysRight;
+    kf.mDescriptors = rows32(dAll, N);
+    kf.mvuRight.assign(uRightAll, uRightAll + N);
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvInvLevelSigma2.assign(invLevelSigma2, invLevelSigma2 + nlevels);
+    kf.mpCamera = &cam; kf.mpCamera2 = &cam; kf.mbf = bf;
+    kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    kf.mnMinX = minX; kf.mnMinY = minY; kf.mnMaxX = maxX; kf.mnMaxY = maxY;
+    kf.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    kf.mGridRight.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) { kf.mGrid[i][j] = F.mGrid[i][j]; kf.mGridRight[i][j] = F.mGridRight[i][j]; }
+    MapPoint inKF, badInKF;
+    inKF.nObs = 5; inKF.id = -1000; badInKF.mbBad = true; badInKF.id = -1000;
+    kf.mvpMapPoints.assign(N, nullptr);
+    for (int j = 0; j < N; ++j) kf.mvpMapPoints[j] = kfHasPoint[j] == 1 ? &inKF : kfHasPoint[j] == 2 ? &badInKF : nullptr;
+    std::vector<MapPoint> mps(nMP);
+    std::vector<MapPoint*> ptrs(nMP, nullptr);
+    for (int i = 0; i < nMP; ++i) {
+        MapPoint& m = mps[i];
+        m.id = i;
+        m.mWorldPos = Eigen::Vector3f(uv[2 * i], uv[2 * i + 1], depth[i]);
+        const float n = m.mWorldPos.norm();
+        const float sgn = state[i] == 4 ? -1.0f : 1.0f;
+        m.mNormal = Eigen::Vector3f(sgn * m.mWorldPos(0) / n, sgn * m.mWorldPos(1) / n, sgn * m.mWorldPos(2) / n);
+        m.mDescriptor = rows32(dMP + 32 * (size_t)i, 1);
+        m.mnTrackScaleLevel = level[i];
+        m.mfMinDistance = minDist[i]; m.mfMaxDistance = maxDist[i];
+        m.nObs = nObs[i];
+        m.mbBad = state[i] == 2; m.mbInKF = state[i] == 3;
+        if (state[i]) ptrs[i] = &m;
+        bestIdx[i] = -1;
+    }
+    g_fuseLog.clear();
+    ORBmatcher matcher(0.6f, true);
+    const int nFused = matcher.Fuse(&kf, ptrs, th, true);
+    for (const auto& e : g_fuseLog)
+        if (e.first >= 0) bestIdx[e.first] = e.second;
+        else if (kfHasPoint[e.second] != 2) return -1000 - e.second;
+    return nFused;
+}
+
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:806-1013), key frames
 // without a second camera.  node*[i] = vocabulary node of feature i (-1: not in the feature vector); hasMP*[i]; uRight*[i];
 // the epipole (epx, epy) is produced through the stand-in poses (T1w = identity, T2w = translation (epx, epy, 1), camera

@@ -415,6 +415,45 @@ def test_fuse_search_equals_reference(oracle, rf, M, seed, th, stereo):
     assert rn > 40 and (best >= 0).sum() == rn
 
 
+@pytest.mark.parametrize("seed,th", [(36, 3.0), (37, 5.0), (38, 2.0)])
+def test_fuse_in_the_right_camera_is_fuse_search_on_the_right_arrays(oracle, rf, M, seed, th):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = true) (R/lib_src/ORBmatcher.cc:1015-1181 with mGridRight / mvKeysRight /
+    descriptor rows NLeft + i): the same search as bRight = false on the right camera's arrays -- what the adapters' FuseSearch
+    computes when it is handed mvKeysRight, the right rows of mDescriptors and a grid over mvKeysRight; bestIdx + NLeft."""
+    k1, d1, k2, d2, uv, depth, _, _, _, _ = _last_frame_case(oracle, seed, False)
+    kR, dR = _right_camera(oracle, seed)
+    rng = np.random.default_rng(seed + 300)
+    n1, nL, nR = len(k1), len(k2), len(kR)
+    f32 = np.float32
+    uv = (np.stack([k1["x"] - 9.0, k1["y"] + 2.0], 1).astype(f32) + rng.normal(0, 0.8, (n1, 2)).astype(f32))   # in the right image
+    uv[rng.random(n1) < 0.03] += f32(700.0)
+    tab = oracle.tables()
+    sf, inv_sigma2 = tab["scale"], (1.0 / (tab["scale"].astype(np.float64) ** 2)).astype(f32)
+    state = rng.choice([0, 1, 1, 1, 1, 1, 1, 2, 3, 4], n1).astype(np.uint8)
+    level = np.clip(k1["octave"] + rng.integers(0, 2, n1), 0, 7).astype(np.int32)
+    bf = 40.0
+    u_right_all = np.full(nL + nR, -1.0, f32)                     # fisheye frames carry no rectified right coordinate ...
+    u_right_all[:nR][rng.random(nR) < 0.1] = f32(5.0)             # ... but the function would read entry [right index] if one were set
+    kf_has = rng.choice([0, 0, 0, 1, 2], nL + nR).astype(np.uint8)
+    n_obs = rng.integers(1, 10, n1).astype(np.int32)
+    x, y, z = uv[:, 0], uv[:, 1], depth
+    dist3d = np.sqrt(((x * x + y * y).astype(f32) + z * z).astype(f32)).astype(f32)
+    invz = (f32(1.0) / z).astype(f32)
+    ur = (x - (f32(bf) * invz).astype(f32)).astype(f32)
+    min_d = (dist3d * rng.choice([0.5, 0.9, 1.01], n1)).astype(f32)
+    max_d = (dist3d * rng.choice([0.99, 1.1, 2.0], n1)).astype(f32)
+    rn, rbest = rf.fuse_right(nL, kR, np.concatenate([d2, dR]), sf, inv_sigma2, (0, 0, 640, 480), u_right_all, kf_has, bf, state, uv,
+                              depth, min_d, max_d, level, d1, n_obs, th)
+    valid = (state == 1) & ~(z < 0)
+    n, best, _ = M.fuse_search(kR, dR, sf, inv_sigma2, (0, 0, 640, 480), u_right_all[:nR], valid, uv, ur, dist3d, min_d, max_d, level,
+                               d1, th)
+    best = np.where(best >= 0, best + nL, -1)
+    assert rn >= 0 and n == rn
+    traced = (best < 0) | (kf_has[np.maximum(best, 0)] != 2)
+    assert np.array_equal(best[traced], rbest[traced]) and np.all(rbest[~traced] == -1)
+    assert rn > 40
+
+
 def _triangulation_case(B, seed):
     """Two key frames whose descriptors share vocabulary nodes (the SearchByBoW scene), with key points, map-point flags,
     stereo flags, an epipole inside image 2 and a pseudo-random epipolar-constraint table."""

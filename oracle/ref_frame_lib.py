@@ -348,6 +348,28 @@ def search_for_triangulation(k1, d1, has_mp1, u_right1, fv1, k2, d2, has_mp2, u_
     return n, match[:len(d1)]
 
 
+def search_for_triangulation_rig(k1, d1, has_mp1, fv1, n_left1, k2, d2, has_mp2, fv2, n_left2, scale_factors2, ep, epi_ok,
+                                 only_stereo=False, coarse=False, check_ori=True):
+    """The reference's ORBmatcher::SearchForTriangulation on two key frames of a stereo-fisheye rig (mpCamera2 set; k* = the
+    left key points followed by the right ones, NLeft = n_left*): (nmatches, match12)."""
+    k1, k2 = np.ascontiguousarray(k1, KP_DTYPE), np.ascontiguousarray(k2, KP_DTYPE)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    d1, d2 = u8(d1).reshape(-1, 32), u8(d2).reshape(-1, 32)
+    sf = f32(scale_factors2)
+    n1, n2 = _nodes(fv1, len(d1)), _nodes(fv2, len(d2))
+    match = np.zeros(max(len(d1), 1), np.int32)
+    L = lib()
+    fn = L.ref_search_for_triangulation_rig
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, _u8p, _u8p, _i32p, C.c_int, C.c_int, C.c_void_p, _u8p, _u8p, _i32p, C.c_int, C.c_int, _f32p, C.c_int,
+                   C.c_float, C.c_float, C.c_int, C.c_int, _u8p, C.c_float, C.c_int, _i32p]
+    n = fn(k1.ctypes.data, _p(d1, _u8p), _p(u8(has_mp1), _u8p), _p(n1, _i32p), len(d1), int(n_left1), k2.ctypes.data, _p(d2, _u8p),
+           _p(u8(has_mp2), _u8p), _p(n2, _i32p), len(d2), int(n_left2), _p(sf, _f32p), len(sf), float(ep[0]), float(ep[1]),
+           int(only_stereo), int(coarse), _p(u8(epi_ok), _u8p), 0.6, int(check_ori), _p(match, _i32p))
+    return n, match[:len(d1)]
+
+
 def _sim3_args(kK, dK, scale_factors, bounds, occupied, state, already_at, uv, depth, min_dist, max_dist, level, dMP):
     kK = np.ascontiguousarray(kK, KP_DTYPE)
     u8 = lambda a: np.ascontiguousarray(a, np.uint8)

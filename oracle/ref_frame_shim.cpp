@@ -763,6 +763,42 @@ int ref_search_for_triangulation(const void* k1, const uint8_t* d1, const uint8_
     return n;
 }
 
+// The same reference function on two key frames of a stereo-fisheye rig (mpCamera2 set, NLeft = nLeft*, mvKeys = the first
+// nLeft* key points, mvKeysRight = the rest; class_id = flattened feature number, so the epipolar table is indexed as before).
+int ref_search_for_triangulation_rig(const void* k1, const uint8_t* d1, const uint8_t* hasMP1, const int32_t* node1, int n1,
+                                     int nLeft1, const void* k2, const uint8_t* d2, const uint8_t* hasMP2, const int32_t* node2,
+                                     int n2, int nLeft2, const float* scaleFactors2, int nlevels, float epx, float epy,
+                                     int onlyStereo, int coarse, const uint8_t* epiOk, float ratio, int checkOri, int32_t* match12) {
+    GeometricCamera cam, cam2;
+    GeometricCamera::epiTable = epiOk; GeometricCamera::epiCols = n2;
+    MapPoint some;
+    KeyFrame kf1, kf2;
+    auto fill = [&](KeyFrame& kf, const void* k, const uint8_t* d, const uint8_t* hasMP, const int32_t* node, int n, int nLeft) {
+        std::vector<cv::KeyPoint> all = keys(k, n);
+        for (int i = 0; i < n; ++i) all[i].class_id = i;
+        kf.N = n; kf.NLeft = nLeft;
+        kf.mvKeys.assign(all.begin(), all.begin() + nLeft); kf.mvKeysUn = kf.mvKeys;
+        kf.mvKeysRight.assign(all.begin() + nLeft, all.end());
+        kf.mDescriptors = rows32(d, n);
+        kf.mvuRight.assign(n, 5.0f);                   // would make every feature "stereo" if the second camera did not rule it out
+        kf.mvpMapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; ++i) if (hasMP[i]) kf.mvpMapPoints[i] = &some;
+        fill_featvec(kf.mFeatVec, node, n);
+        kf.mpCamera = &cam; kf.mpCamera2 = &cam2;
+        kf.mvScaleFactors.assign(scaleFactors2, scaleFactors2 + nlevels);
+        kf.mvLevelSigma2.assign(nlevels, 1.0f);
+    };
+    fill(kf1, k1, d1, hasMP1, node1, n1, nLeft1);
+    fill(kf2, k2, d2, hasMP2, node2, n2, nLeft2);
+    kf2.mTcw.t = Eigen::Vector3f(epx, epy, 1.0f);
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher m(ratio, checkOri != 0);
+    const int n = m.SearchForTriangulation(&kf1, &kf2, pairs, onlyStereo != 0, coarse != 0);
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (const auto& p : pairs) match12[p.first] = (int)p.second;
+    return n;
+}
+
 }  // extern "C"
 
 namespace {

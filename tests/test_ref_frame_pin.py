@@ -489,6 +489,28 @@ def test_search_for_triangulation_equals_reference(oracle, rf, B, seed, only_ste
     assert rn > (20 if only_stereo else 60)
 
 
+@pytest.mark.parametrize("check_ori", [False, True])
+@pytest.mark.parametrize("seed,coarse", [(44, False), (45, True), (46, False)])
+def test_search_for_triangulation_on_a_stereo_fisheye_rig(oracle, rf, B, seed, coarse, check_ori):
+    """The same function with mpCamera2 set on both key frames (R/lib_src/ORBmatcher.cc:870, :878-880, :908-916): no feature counts
+    as stereo, the epipole exclusion zone is off, key points come from mvKeys / mvKeysRight by the flattened index.  That is the
+    existing entry point with stereo flags all false, the flattened key points and an epipole nothing comes close to (the
+    camera pair of the epipolar test is the caller's predicate either way)."""
+    d1, a1, fv1, k1, has1, _, d2, a2, fv2, k2, has2, _, epi, ep = _triangulation_case(B, seed)
+    sf = oracle.tables()["scale"]
+    nl1, nl2 = len(k1) * 2 // 3, len(k2) // 2
+    rn, rm = rf.search_for_triangulation_rig(k1, d1, has1, fv1, nl1, k2, d2, has2, fv2, nl2, sf, ep, epi, False, coarse, check_ori)
+    none1, none2 = np.zeros(len(d1), bool), np.zeros(len(d2), bool)
+    far = (3.0e9, 3.0e9)
+    n, m = B.search_for_triangulation(d1, a1, has1, none1, fv1, d2, a2, has2, none2, k2["x"], k2["y"], k2["octave"], fv2, sf, far,
+                                      epi, False, coarse, check_ori)
+    assert n == rn and np.array_equal(m, rm)
+    assert rn > 60
+    # bOnlyStereo on a rig: nothing is stereo, nothing matches
+    rn2, rm2 = rf.search_for_triangulation_rig(k1, d1, has1, fv1, nl1, k2, d2, has2, fv2, nl2, sf, ep, epi, True, coarse, check_ori)
+    assert rn2 == 0 and np.all(rm2 == -1)
+
+
 def _sim3_case(oracle, seed):
     """Loop-closing scene: key frame = frame 2, candidate map points = the features of frame 1 projected to where they moved;
     depths are powers of two so that the overload projecting with fx * x / z + cx reproduces the prescribed pixel exactly."""

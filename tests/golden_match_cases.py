@@ -93,6 +93,19 @@ def triangulation(oracle, B, rf, reference, seed=40):
     return {"n": n, "match": m}
 
 
+def triangulation_rig(oracle, B, rf, reference, seed=47):
+    """Two key frames of a stereo-fisheye rig: the existing entry point with flattened key points, no stereo flags, far epipole."""
+    d1, a1, fv1, k1, has1, _, d2, a2, fv2, k2, has2, _, epi, ep = T._triangulation_case(B, seed)
+    sf = oracle.tables()["scale"]
+    if reference:
+        n, m = rf.search_for_triangulation_rig(k1, d1, has1, fv1, len(k1) * 2 // 3, k2, d2, has2, fv2, len(k2) // 2, sf, ep, epi,
+                                               False, False, True)
+    else:
+        n, m = B.search_for_triangulation(d1, a1, has1, np.zeros(len(d1), bool), fv1, d2, a2, has2, np.zeros(len(d2), bool),
+                                          k2["x"], k2["y"], k2["octave"], fv2, sf, (3.0e9, 3.0e9), epi, False, False, True)
+    return {"n": n, "match": m}
+
+
 def sim3_pair(oracle, B, rf, reference, seed=71, th=7.5):
     from oracle import match_oracle as M
     k1, d1, k2, d2, (uv12, z1, st1, lv12, mn1, mx1), (uv21, z2, st2, lv21, mn2, mx2), pre = T._sim3_pair_case(oracle, seed)
@@ -148,4 +161,5 @@ def _local_points(mode, seed, th, ratio):
 CASES = {"last_frame": last_frame, "keyframe": keyframe, "fuse": fuse, "triangulation": triangulation, "sim3_pair": sim3_pair,
          "initialization": initialization,
          "local_points_occupied": _local_points("occupied", 41, 3.0, 0.8), "local_points_stereo": _local_points("stereo", 42, 5.0, 0.8),
-         "local_points_fisheye": _local_points("fisheye", 43, 3.0, 0.8), "last_frame_fisheye": last_frame_fisheye}
+         "local_points_fisheye": _local_points("fisheye", 43, 3.0, 0.8), "last_frame_fisheye": last_frame_fisheye,
+         "triangulation_rig": triangulation_rig}
